@@ -1,0 +1,334 @@
+// api.cu -- the C ABI of libhop.so (include/hop_c_api.h): context, clouds, host/device entry points.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+
+#include "hop_common.cuh"
+
+static std::string g_create_error;
+
+void *hop_ctx::ensure_scratch(size_t bytes) {
+  if (bytes <= scratch_bytes) return d_scratch;
+  if (d_scratch) { cudaStreamSynchronize(stream); cudaFree(d_scratch); d_scratch = nullptr; scratch_bytes = 0; }
+  size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+  if (cudaMalloc(&d_scratch, cap) != cudaSuccess) { d_scratch = nullptr; return nullptr; }
+  scratch_bytes = cap;
+  return d_scratch;
+}
+
+void *hop_ctx::ensure_pinned(size_t bytes) {
+  if (bytes <= pinned_bytes) return h_pinned;
+  if (h_pinned) { cudaStreamSynchronize(stream); cudaFreeHost(h_pinned); h_pinned = nullptr; pinned_bytes = 0; }
+  size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+  if (cudaHostAlloc(&h_pinned, cap, cudaHostAllocDefault) != cudaSuccess) { h_pinned = nullptr; return nullptr; }
+  pinned_bytes = cap;
+  return h_pinned;
+}
+
+namespace {
+
+// raw staging (xyz | nrm | prob, each contiguous) -> the two padded float4 streams
+__global__ void repack_cloud_kernel(const float *__restrict__ xyz, const float *__restrict__ nrm, const float *__restrict__ prob,
+                                    int n, int n_padded, float4 *__restrict__ pw, float4 *__restrict__ nv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_padded) return;
+  if (i >= n) {
+    pw[i] = make_float4(HOP_SENTINEL, HOP_SENTINEL, HOP_SENTINEL, 0.f);
+    nv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    return;
+  }
+  float w = prob ? prob[i] : 1.f;
+  pw[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], w);
+  float nx = 0.f, ny = 0.f, nz = 0.f, inv = 0.f;
+  if (nrm) {
+    nx = nrm[3 * i]; ny = nrm[3 * i + 1]; nz = nrm[3 * i + 2];
+    float s = nx * nx + ny * ny + nz * nz;
+    inv = s > 0.f ? 1.f / sqrtf(s) : 0.f;  // NaN normals: s is NaN -> inv 0, and the NaN stays in (nx,ny,nz)
+  }
+  nv[i] = make_float4(nx, ny, nz, inv);
+}
+
+int cloud_fill(hop_ctx *ctx, hop_cloud *c, const float *xyz, const float *nrm, const float *prob, int n) {
+  if (n < 0 || (n > 0 && !xyz)) { ctx->err = "hop_cloud: bad arguments"; return HOP_EINVAL; }
+  const int n_padded = std::max(HOP_TILE_PTS, (n + HOP_TILE_PTS - 1) / HOP_TILE_PTS * HOP_TILE_PTS);
+  if (n_padded > c->capacity) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->d_pw); cudaFree(c->d_nv); cudaFree(c->d_stage);
+    c->d_pw = c->d_nv = nullptr; c->d_stage = nullptr;
+    HOP_CUDA(ctx, cudaMalloc(&c->d_pw, sizeof(float4) * (size_t)n_padded));
+    HOP_CUDA(ctx, cudaMalloc(&c->d_nv, sizeof(float4) * (size_t)n_padded));
+    HOP_CUDA(ctx, cudaMalloc(&c->d_stage, sizeof(float) * 7 * (size_t)n_padded));
+    c->capacity = n_padded;
+  }
+  c->n = n; c->n_padded = n_padded; c->version++;
+  // one pass over the caller's arrays: copy into pinned staging and take the bounding box (finite points only)
+  float *h = (float *)ctx->ensure_pinned(sizeof(float) * 7 * (size_t)std::max(n, 1));
+  if (!h) { ctx->err = "hop_cloud: pinned staging allocation failed"; return HOP_ENOMEM; }
+  // the staging buffer may still feed an earlier async copy of this context
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  std::memcpy(h, xyz, sizeof(float) * 3 * (size_t)n);
+  for (int i = 0; i < n; ++i) {
+    const float *p = xyz + 3 * (size_t)i;
+    if (std::isfinite(p[0]) && std::isfinite(p[1]) && std::isfinite(p[2]) && std::fabs(p[0]) < 1e20f && std::fabs(p[1]) < 1e20f &&
+        std::fabs(p[2]) < 1e20f)
+      for (int d = 0; d < 3; ++d) { mn[d] = std::min(mn[d], p[d]); mx[d] = std::max(mx[d], p[d]); }
+  }
+  if (!(mn[0] <= mx[0])) { for (int d = 0; d < 3; ++d) mn[d] = mx[d] = 0.f; }
+  for (int d = 0; d < 3; ++d) { c->bbox_min[d] = mn[d]; c->bbox_max[d] = mx[d]; }
+  float *hn = h + 3 * (size_t)n, *hp = h + 6 * (size_t)n;
+  if (nrm) std::memcpy(hn, nrm, sizeof(float) * 3 * (size_t)n);
+  if (prob) std::memcpy(hp, prob, sizeof(float) * (size_t)n);
+  float *dx = c->d_stage, *dn = c->d_stage + 3 * (size_t)n, *dp = c->d_stage + 6 * (size_t)n;
+  if (n > 0) {
+    // xyz|nrm|prob are contiguous in both staging buffers: one copy when all three are present
+    if (nrm && prob) HOP_CUDA(ctx, cudaMemcpyAsync(dx, h, sizeof(float) * 7 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    else {
+      HOP_CUDA(ctx, cudaMemcpyAsync(dx, h, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+      if (nrm) HOP_CUDA(ctx, cudaMemcpyAsync(dn, hn, sizeof(float) * 3 * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+      if (prob) HOP_CUDA(ctx, cudaMemcpyAsync(dp, hp, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  repack_cloud_kernel<<<(n_padded + 255) / 256, 256, 0, ctx->stream>>>(dx, nrm ? dn : nullptr, prob ? dp : nullptr, n, n_padded,
+                                                                      c->d_pw, c->d_nv);
+  ctx->launches += 1;
+  HOP_CUDA(ctx, cudaGetLastError());
+  return HOP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hop_create(int device, hop_ctx **out) {
+  if (!out) return HOP_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0) {
+    g_create_error = std::string("hop_create: no CUDA device (") + cudaGetErrorString(e) + "); libhop has no CPU path";
+    return HOP_ENODEV;
+  }
+  if (device < 0 || device >= count) { g_create_error = "hop_create: device index out of range"; return HOP_EINVAL; }
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) { g_create_error = "hop_create: cudaGetDeviceProperties failed"; return HOP_ECUDA; }
+  if (prop.major < 10) {
+    g_create_error = "hop_create: libhop is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
+    return HOP_ENODEV;
+  }
+  if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "hop_create: cudaSetDevice failed"; return HOP_ECUDA; }
+  hop_ctx *ctx = new hop_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) != cudaSuccess) {
+    g_create_error = "hop_create: stream/counter allocation failed";
+    delete ctx;
+    return HOP_ECUDA;
+  }
+  cudaMemset(ctx->d_counter, 0, 64 * sizeof(int));
+  *out = ctx;
+  return HOP_OK;
+}
+
+void hop_destroy(hop_ctx *ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  cudaFree(ctx->d_scratch);
+  cudaFreeHost(ctx->h_pinned);
+  cudaFree(ctx->d_counter);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char *hop_last_error(const hop_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int hop_set_stream(hop_ctx *ctx, void *cuda_stream) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (cuda_stream) {
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    ctx->stream = (cudaStream_t)cuda_stream;
+    ctx->own_stream = false;
+  } else if (!ctx->own_stream) {
+    HOP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    ctx->own_stream = true;
+  }
+  return HOP_OK;
+}
+
+int hop_sync(hop_ctx *ctx) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+int64_t hop_launch_count(const hop_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+void hop_default_icp_params(hop_icp_params *p) {
+  if (!p) return;
+  p->max_iter = 10; p->angle_deg = 45.f; p->max_dist = 0.01f; p->abs_mse_eps = 1e-6; p->mode = 0; p->solver = 0;
+  p->team_warps = 0; p->reserved = 0;
+}
+void hop_default_lcp_params(hop_lcp_params *p) {
+  if (!p) return;
+  p->dist = 0.001f; p->angle_deg = 10.f; p->use_normal = 1; p->use_dot_score = 1; p->use_reciprocal = 1; p->team_warps = 0;
+}
+
+int hop_malloc(hop_ctx *ctx, size_t bytes, void **dev_ptr) {
+  if (!ctx || !dev_ptr) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaMalloc(dev_ptr, bytes ? bytes : 1));
+  return HOP_OK;
+}
+int hop_free(hop_ctx *ctx, void *dev_ptr) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaFree(dev_ptr));
+  return HOP_OK;
+}
+int hop_host_alloc(hop_ctx *ctx, size_t bytes, void **host_ptr) {
+  if (!ctx || !host_ptr) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaHostAlloc(host_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
+  return HOP_OK;
+}
+int hop_host_free(hop_ctx *ctx, void *host_ptr) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaFreeHost(host_ptr));
+  return HOP_OK;
+}
+int hop_memcpy_h2d(hop_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  return HOP_OK;
+}
+int hop_memcpy_d2h(hop_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+  if (!ctx) return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  return HOP_OK;
+}
+
+int hop_cloud_upload(hop_ctx *ctx, const float *xyz, const float *nrm, const float *prob, int n, hop_cloud **out) {
+  if (!ctx || !out) return HOP_EINVAL;
+  hop_cloud *c = new hop_cloud();
+  int rc = cloud_fill(ctx, c, xyz, nrm, prob, n);
+  if (rc != HOP_OK) { hop_cloud_free(ctx, c); *out = nullptr; return rc; }
+  *out = c;
+  return HOP_OK;
+}
+
+int hop_cloud_update(hop_ctx *ctx, hop_cloud *cloud, const float *xyz, const float *nrm, const float *prob, int n) {
+  if (!ctx || !cloud) return HOP_EINVAL;
+  return cloud_fill(ctx, cloud, xyz, nrm, prob, n);
+}
+
+int hop_cloud_free(hop_ctx *ctx, hop_cloud *cloud) {
+  if (!cloud) return HOP_OK;
+  if (ctx) cudaStreamSynchronize(ctx->stream);
+  for (NNGridHost *g : cloud->grids) hop_free_nn_grid(g);
+  cudaFree(cloud->d_pw); cudaFree(cloud->d_nv); cudaFree(cloud->d_stage);
+  delete cloud;
+  return HOP_OK;
+}
+
+int hop_cloud_size(const hop_cloud *cloud) { return cloud ? cloud->n : 0; }
+
+// ---- K4 -------------------------------------------------------------------------------------------------------
+int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *d_poses_inout, int H, const hop_icp_params *params,
+                       int32_t *d_iters_out, int32_t *d_converged_out) {
+  if (!ctx || !scene || !model || !params || H < 0 || (H > 0 && !d_poses_inout)) { if (ctx) ctx->err = "hop_icp_refine: bad arguments"; return HOP_EINVAL; }
+  if (H == 0) return HOP_OK;
+  if (!(params->max_dist > 0.f)) { ctx->err = "hop_icp_refine: max_dist must be > 0"; return HOP_EINVAL; }
+  if (model->n <= 0) { ctx->err = "hop_icp_refine: empty model cloud"; return HOP_EINVAL; }
+  NNGridHost *G = nullptr;
+  int rc = hop_get_nn_grid(ctx, model, params->max_dist, 0.f, &G);
+  if (rc != HOP_OK) return rc;
+  return hop_launch_icp(ctx, scene->dev(), model->dev(), G->dev, d_poses_inout, H, *params, d_iters_out, d_converged_out);
+}
+
+int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *poses_inout, int H, const hop_icp_params *params,
+                   int32_t *iters_out, int32_t *converged_out) {
+  if (!ctx || (H > 0 && !poses_inout)) return HOP_EINVAL;
+  if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
+  const size_t pb = sizeof(float) * 16 * (size_t)H, ib = sizeof(int32_t) * (size_t)H;
+  // device staging for this call: poses | iters | conv   (kept separate from the grid-build scratch)
+  float *d_poses = nullptr;
+  HOP_CUDA(ctx, cudaMallocAsync((void **)&d_poses, pb + 2 * ib, ctx->stream));
+  int32_t *d_it = (int32_t *)((char *)d_poses + pb), *d_cv = d_it + H;
+  HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses_inout, pb, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = hop_icp_refine_dev(ctx, scene, model, d_poses, H, params, d_it, d_cv);
+  if (rc == HOP_OK) {
+    cudaMemcpyAsync(poses_inout, d_poses, pb, cudaMemcpyDeviceToHost, ctx->stream);
+    if (iters_out) cudaMemcpyAsync(iters_out, d_it, ib, cudaMemcpyDeviceToHost, ctx->stream);
+    if (converged_out) cudaMemcpyAsync(converged_out, d_cv, ib, cudaMemcpyDeviceToHost, ctx->stream);
+  }
+  cudaFreeAsync(d_poses, ctx->stream);
+  if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---- K5 -------------------------------------------------------------------------------------------------------
+int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H, const hop_lcp_params *params,
+                      int use_weights, float *d_scores_out) {
+  if (!ctx || !scene || !model || !params || H < 0 || (H > 0 && (!d_poses || !d_scores_out))) { if (ctx) ctx->err = "hop_lcp_score: bad arguments"; return HOP_EINVAL; }
+  if (H == 0) return HOP_OK;
+  if (!(params->dist > 0.f)) { ctx->err = "hop_lcp_score: dist must be > 0"; return HOP_EINVAL; }
+  if (model->n <= 0 || scene->n <= 0) {  // empty clouds score 0 (the reference loop body never runs)
+    HOP_CUDA(ctx, cudaMemsetAsync(d_scores_out, 0, sizeof(float) * (size_t)H, ctx->stream));
+    return HOP_OK;
+  }
+  NNGridHost *Gm = nullptr, *Gs = nullptr;
+  int rc = hop_get_nn_grid(ctx, model, params->dist, 0.f, &Gm);
+  if (rc != HOP_OK) return rc;
+  // the reciprocal neighbour is at most `dist` away (see lcp_score_kernel); a little head room for rounding
+  rc = hop_get_nn_grid(ctx, scene, params->dist * 1.01f, 0.f, &Gs);
+  if (rc != HOP_OK) return rc;
+  return hop_launch_lcp(ctx, scene->dev(), model->dev(), Gm->dev, Gs->dev, d_poses, H, *params, use_weights, d_scores_out);
+}
+
+int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *poses, int H, const hop_lcp_params *params,
+                  int use_weights, float *scores_out) {
+  if (!ctx || (H > 0 && (!poses || !scores_out))) return HOP_EINVAL;
+  if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
+  const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H;
+  float *d_poses = nullptr;
+  HOP_CUDA(ctx, cudaMallocAsync((void **)&d_poses, pb + sb, ctx->stream));
+  float *d_scores = (float *)((char *)d_poses + pb);
+  HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses, pb, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = hop_lcp_score_dev(ctx, scene, model, d_poses, H, params, use_weights, d_scores);
+  if (rc == HOP_OK) cudaMemcpyAsync(scores_out, d_scores, sb, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaFreeAsync(d_poses, ctx->stream);
+  if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---- winners ---------------------------------------------------------------------------------------------------
+int hop_select_topk_dev(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset, int32_t frame,
+                        hop_pose_rec *d_out) {
+  if (!ctx || H < 0 || K < 0 || (K > 0 && !d_out) || (H > 0 && (!d_poses || !d_scores))) return HOP_EINVAL;
+  return hop_launch_topk(ctx, d_poses, d_scores, H, K, id_offset, frame, d_out);
+}
+
+int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H, int K, int32_t id_offset, int32_t frame,
+                    hop_pose_rec *out) {
+  if (!ctx || H < 0 || K < 0 || (K > 0 && !out) || (H > 0 && (!poses || !scores))) return HOP_EINVAL;
+  if (K == 0) return HOP_OK;
+  const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H, rb = sizeof(hop_pose_rec) * (size_t)K;
+  char *d = nullptr;
+  HOP_CUDA(ctx, cudaMallocAsync((void **)&d, pb + sb + rb + 64, ctx->stream));
+  float *d_poses = (float *)d, *d_scores = (float *)(d + pb);
+  hop_pose_rec *d_out = (hop_pose_rec *)(d + ((pb + sb + 15) / 16) * 16);
+  if (H > 0) {
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses, pb, cudaMemcpyHostToDevice, ctx->stream));
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_scores, scores, sb, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  int rc = hop_launch_topk(ctx, d_poses, d_scores, H, K, id_offset, frame, d_out);
+  if (rc == HOP_OK) cudaMemcpyAsync(out, d_out, rb, cudaMemcpyDeviceToHost, ctx->stream);
+  cudaFreeAsync(d, ctx->stream);
+  if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+}  // extern "C"

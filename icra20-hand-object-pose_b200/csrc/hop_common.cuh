@@ -1,0 +1,229 @@
+// hop_common.cuh -- shared device/host definitions for libhop (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <math.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/hop_c_api.h"
+
+#ifndef __CUDA_ARCH__
+#define HOP_HOST_ONLY 1
+#endif
+
+// ------------------------------------------------------------------------------------------------------------
+// device data layout
+//   cloud  : pw[i] = (x, y, z, prob)   nv[i] = (nx, ny, nz, 1/|n| or 0)     both padded to a multiple of
+//            HOP_TILE_PTS with sentinel points (x = HOP_SENTINEL) so tiles are always whole 16-byte-aligned
+//            bulk copies.
+//   nn grid: dense voxel grid over the cloud's bounding box inflated by the query radius.  cell[v] = (offset,
+//            count) into cand[]; cand[k] = (x, y, z, int_as_float(point index)).  The list of a voxel holds every
+//            point that can be the nearest neighbour (within `radius`) of ANY query falling in that voxel, so a
+//            query is: one 8-byte gather + a short linear scan.  Exact, not approximate.
+// ------------------------------------------------------------------------------------------------------------
+#define HOP_TILE_PTS 256
+#define HOP_SENTINEL 1.0e30f
+
+struct NNGridDev {
+  float ox, oy, oz;  // min corner
+  float inv_e;       // 1 / voxel edge
+  int nx, ny, nz;
+  float radius;      // queries are exact for neighbours within this distance
+  const uint2 *cell;
+  const float4 *cand;
+};
+
+struct CloudDev {
+  const float4 *pw;
+  const float4 *nv;
+  int n;         // real points
+  int n_padded;  // multiple of HOP_TILE_PTS
+};
+
+struct Rigid {  // y = R x + t, row-major R
+  float r[9];
+  float t[3];
+};
+
+#ifdef __CUDACC__
+// ---- small math ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float3 rigid_apply(const Rigid &T, float x, float y, float z) {
+  return make_float3(fmaf(T.r[0], x, fmaf(T.r[1], y, fmaf(T.r[2], z, T.t[0]))),
+                     fmaf(T.r[3], x, fmaf(T.r[4], y, fmaf(T.r[5], z, T.t[1]))),
+                     fmaf(T.r[6], x, fmaf(T.r[7], y, fmaf(T.r[8], z, T.t[2]))));
+}
+__device__ __forceinline__ float3 rigid_rotate(const Rigid &T, float x, float y, float z) {
+  return make_float3(fmaf(T.r[0], x, fmaf(T.r[1], y, T.r[2] * z)), fmaf(T.r[3], x, fmaf(T.r[4], y, T.r[5] * z)),
+                     fmaf(T.r[6], x, fmaf(T.r[7], y, T.r[8] * z)));
+}
+// general inverse of an affine map with (nearly) orthonormal R: uses the adjugate so a slightly non-orthonormal
+// input is inverted, not transposed.
+__device__ __forceinline__ Rigid rigid_inverse(const Rigid &T) {
+  const float *a = T.r;
+  float c00 = a[4] * a[8] - a[5] * a[7], c01 = a[5] * a[6] - a[3] * a[8], c02 = a[3] * a[7] - a[4] * a[6];
+  float det = a[0] * c00 + a[1] * c01 + a[2] * c02;
+  float id = 1.0f / det;
+  Rigid I;
+  I.r[0] = c00 * id; I.r[1] = (a[2] * a[7] - a[1] * a[8]) * id; I.r[2] = (a[1] * a[5] - a[2] * a[4]) * id;
+  I.r[3] = c01 * id; I.r[4] = (a[0] * a[8] - a[2] * a[6]) * id; I.r[5] = (a[2] * a[3] - a[0] * a[5]) * id;
+  I.r[6] = c02 * id; I.r[7] = (a[1] * a[6] - a[0] * a[7]) * id; I.r[8] = (a[0] * a[4] - a[1] * a[3]) * id;
+  I.t[0] = -(I.r[0] * T.t[0] + I.r[1] * T.t[1] + I.r[2] * T.t[2]);
+  I.t[1] = -(I.r[3] * T.t[0] + I.r[4] * T.t[1] + I.r[5] * T.t[2]);
+  I.t[2] = -(I.r[6] * T.t[0] + I.r[7] * T.t[1] + I.r[8] * T.t[2]);
+  return I;
+}
+// C = A o B  (apply B first)
+__device__ __forceinline__ Rigid rigid_compose(const Rigid &A, const Rigid &B) {
+  Rigid C;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) C.r[3 * i + j] = A.r[3 * i] * B.r[j] + A.r[3 * i + 1] * B.r[3 + j] + A.r[3 * i + 2] * B.r[6 + j];
+    C.t[i] = A.r[3 * i] * B.t[0] + A.r[3 * i + 1] * B.t[1] + A.r[3 * i + 2] * B.t[2] + A.t[i];
+  }
+  return C;
+}
+// column-major 4x4 (Eigen) <-> Rigid
+__device__ __forceinline__ Rigid rigid_load_colmajor(const float *m) {
+  Rigid T;
+#pragma unroll
+  for (int i = 0; i < 3; ++i) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) T.r[3 * i + j] = m[4 * j + i];
+    T.t[i] = m[12 + i];
+  }
+  return T;
+}
+__device__ __forceinline__ void rigid_store_colmajor(const Rigid &T, float *m) {
+#pragma unroll
+  for (int j = 0; j < 3; ++j) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) m[4 * j + i] = T.r[3 * i + j];
+    m[4 * j + 3] = 0.f;
+  }
+  m[12] = T.t[0]; m[13] = T.t[1]; m[14] = T.t[2]; m[15] = 1.f;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// ---- exact nearest neighbour through the voxel grid ------------------------------------------------------------
+// returns the point index (or -1) and its squared distance; exact for neighbours within g.radius.
+__device__ __forceinline__ int nn_query(const NNGridDev &g, float px, float py, float pz, float &best_d2, float4 &best_pt) {
+  float fx = (px - g.ox) * g.inv_e, fy = (py - g.oy) * g.inv_e, fz = (pz - g.oz) * g.inv_e;
+  int ix = __float2int_rd(fx), iy = __float2int_rd(fy), iz = __float2int_rd(fz);
+  best_d2 = 3.0e38f;
+  int best = -1;
+  // (the negated comparison also rejects NaN coordinates)
+  if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f) || ix >= g.nx || iy >= g.ny || iz >= g.nz) return -1;
+  uint2 c = __ldg(&g.cell[((size_t)iz * g.ny + iy) * g.nx + ix]);
+  const float4 *lst = g.cand + c.x;
+  for (uint32_t k = 0; k < c.y; ++k) {
+    float4 q = __ldg(&lst[k]);
+    float dx = q.x - px, dy = q.y - py, dz = q.z - pz;
+    float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    if (d2 < best_d2) { best_d2 = d2; best = __float_as_int(q.w); best_pt = q; }
+  }
+  return best;
+}
+
+// ---- mbarrier + 1-D bulk (TMA) copies --------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred P1;\n"
+      "LAB_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "@P1 bra DONE;\n"
+      "bra LAB_WAIT;\n"
+      "DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+// global -> shared bulk copy, completion signalled on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+#endif  // __CUDACC__
+
+// ------------------------------------------------------------------------------------------------------------
+// host-side objects
+// ------------------------------------------------------------------------------------------------------------
+struct NNGridHost {
+  float radius = 0.f, voxel = 0.f;
+  NNGridDev dev{};
+  uint2 *d_cell = nullptr;
+  float4 *d_cand = nullptr;
+  int64_t n_vox = 0, n_cand = 0, cap_vox = 0, cap_cand = 0;
+  int max_list = 0;
+};
+
+struct hop_cloud {
+  int n = 0, n_padded = 0, capacity = 0;
+  float4 *d_pw = nullptr, *d_nv = nullptr;
+  float *d_stage = nullptr;  // raw xyz|nrm|prob staging (capacity * 7 floats)
+  float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
+  uint64_t version = 0;  // bumped by hop_cloud_update; grids are rebuilt when stale
+  std::vector<NNGridHost *> grids;
+  std::vector<uint64_t> grid_version;
+  CloudDev dev() const { return CloudDev{d_pw, d_nv, n, n_padded}; }
+};
+
+struct hop_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t stream = nullptr;
+  bool own_stream = true;
+  int64_t launches = 0;
+  std::string err;
+  // scratch
+  void *d_scratch = nullptr; size_t scratch_bytes = 0;
+  void *h_pinned = nullptr; size_t pinned_bytes = 0;
+  int *d_counter = nullptr;  // work-queue heads (a few ints)
+  void *ensure_scratch(size_t bytes);
+  void *ensure_pinned(size_t bytes);
+};
+
+#define HOP_CUDA(ctx, call)                                                                            \
+  do {                                                                                                 \
+    cudaError_t e_ = (call);                                                                           \
+    if (e_ != cudaSuccess) {                                                                           \
+      (ctx)->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                 \
+      return HOP_ECUDA;                                                                                \
+    }                                                                                                  \
+  } while (0)
+
+// implemented in nn_grid.cu
+int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
+int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
+void hop_free_nn_grid(NNGridHost *g);
+// implemented in icp_lcp.cu
+int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, float *d_poses, int H,
+                   const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv);
+int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &model_grid,
+                   const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
+                   float *d_scores);
+// implemented in select.cu
+int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset, int32_t frame,
+                    hop_pose_rec *d_out);

@@ -1,0 +1,288 @@
+"""ctypes binding of include/hop_c_api.h (the drop-in boundary).  No torch types, plain pointers and sizes."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PKG = os.path.dirname(_HERE)
+_ROOT = os.path.dirname(_PKG)
+_CSRC = os.path.join(_PKG, "csrc")
+_HEADER = os.path.join(_ROOT, "include", "hop_c_api.h")
+
+
+class HopError(RuntimeError):
+    pass
+
+
+class IcpParams(C.Structure):
+    _fields_ = [("max_iter", C.c_int32), ("angle_deg", C.c_float), ("max_dist", C.c_float), ("abs_mse_eps", C.c_double),
+                ("mode", C.c_int32), ("solver", C.c_int32), ("team_warps", C.c_int32), ("reserved", C.c_int32)]
+
+
+class LcpParams(C.Structure):
+    _fields_ = [("dist", C.c_float), ("angle_deg", C.c_float), ("use_normal", C.c_int32), ("use_dot_score", C.c_int32),
+                ("use_reciprocal", C.c_int32), ("team_warps", C.c_int32)]
+
+
+class PoseRec(C.Structure):
+    _fields_ = [("pose", C.c_float * 16), ("score", C.c_float), ("id", C.c_int32), ("frame", C.c_int32), ("pad", C.c_int32)]
+
+
+POSE_REC_DTYPE = np.dtype([("pose", np.float32, (16,)), ("score", np.float32), ("id", np.int32), ("frame", np.int32),
+                           ("pad", np.int32)])
+assert POSE_REC_DTYPE.itemsize == 80 and C.sizeof(PoseRec) == 80
+
+
+def lib_path():
+    return os.path.join(_CSRC, "libhop.so")
+
+
+def build_library(verbose=False):
+    """Compile libhop.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    r = subprocess.run(["make", "-C", _CSRC, "-j4"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise HopError("libhop build failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    if verbose:
+        print(r.stdout[-2000:])
+    return lib_path()
+
+
+def declared_symbols():
+    """Every function the public header declares (used by the CPU tests to check the exports)."""
+    txt = open(_HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(hop_[a-z0-9_]+)\s*\(", txt)))
+
+
+_lib = None
+_vp = C.c_void_p
+
+
+def load_library():
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise HopError(f"{path} is missing: run __graft_entry__.build() (make -C {_CSRC}); there is no CPU fallback")
+    L = C.CDLL(path)
+    L.hop_create.argtypes = [C.c_int, C.POINTER(_vp)]
+    L.hop_destroy.argtypes = [_vp]
+    L.hop_destroy.restype = None
+    L.hop_last_error.argtypes = [_vp]
+    L.hop_last_error.restype = C.c_char_p
+    L.hop_set_stream.argtypes = [_vp, _vp]
+    L.hop_sync.argtypes = [_vp]
+    L.hop_launch_count.argtypes = [_vp]
+    L.hop_launch_count.restype = C.c_int64
+    L.hop_default_icp_params.argtypes = [C.POINTER(IcpParams)]
+    L.hop_default_icp_params.restype = None
+    L.hop_default_lcp_params.argtypes = [C.POINTER(LcpParams)]
+    L.hop_default_lcp_params.restype = None
+    L.hop_malloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp)]
+    L.hop_free.argtypes = [_vp, _vp]
+    L.hop_host_alloc.argtypes = [_vp, C.c_size_t, C.POINTER(_vp)]
+    L.hop_host_free.argtypes = [_vp, _vp]
+    L.hop_memcpy_h2d.argtypes = [_vp, _vp, _vp, C.c_size_t]
+    L.hop_memcpy_d2h.argtypes = [_vp, _vp, _vp, C.c_size_t]
+    L.hop_cloud_upload.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(_vp)]
+    L.hop_cloud_update.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int]
+    L.hop_cloud_free.argtypes = [_vp, _vp]
+    L.hop_cloud_size.argtypes = [_vp]
+    L.hop_cloud_prepare_nn.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_int64)]
+    L.hop_cloud_nn_query.argtypes = [_vp, _vp, C.c_float, _vp, C.c_int, _vp, _vp]
+    L.hop_icp_refine.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
+    L.hop_icp_refine_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
+    L.hop_lcp_score.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
+    L.hop_lcp_score_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
+    L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
+    L.hop_select_topk.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
+    for name in declared_symbols():
+        fn = getattr(L, name)  # raises AttributeError when an export is missing
+        if fn.restype is C.c_int and name not in ("hop_cloud_size",):
+            pass
+    _lib = L
+    return L
+
+
+def _f32(a, shape_last=None):
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if shape_last is not None and (a.ndim != 2 or a.shape[1] != shape_last):
+        raise ValueError(f"expected (N,{shape_last}) array, got {a.shape}")
+    return a
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(_vp)
+
+
+def poses_to_colmajor(poses):
+    """(H,4,4) numpy (row-major, math convention) -> (H,16) column-major float32 = Eigen::Matrix4f::data()."""
+    p = np.asarray(poses, dtype=np.float32).reshape(-1, 4, 4)
+    return np.ascontiguousarray(p.transpose(0, 2, 1).reshape(-1, 16))
+
+
+def colmajor_to_poses(flat):
+    return np.asarray(flat, dtype=np.float32).reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+class Cloud:
+    """Device-resident point cloud handle (hop_cloud*)."""
+
+    def __init__(self, ctx, handle, n):
+        self.ctx, self.handle, self.n = ctx, handle, n
+
+    def update(self, xyz, nrm=None, prob=None):
+        xyz = _f32(xyz, 3)
+        nrm = None if nrm is None else _f32(nrm, 3)
+        prob = None if prob is None else _f32(prob)
+        self.ctx._check(self.ctx.L.hop_cloud_update(self.ctx.h, self.handle, _ptr(xyz), _ptr(nrm), _ptr(prob), len(xyz)))
+        self.n = len(xyz)
+
+    def prepare_nn(self, radius, voxel=0.0):
+        stats = (C.c_int64 * 4)()
+        self.ctx._check(self.ctx.L.hop_cloud_prepare_nn(self.ctx.h, self.handle, radius, voxel, stats))
+        return {"voxels": stats[0], "entries": stats[1], "max_list": stats[2], "bytes": stats[3]}
+
+    def nn_query(self, radius, queries):
+        q = _f32(queries, 3)
+        idx = np.empty(len(q), np.int32)
+        d2 = np.empty(len(q), np.float32)
+        self.ctx._check(self.ctx.L.hop_cloud_nn_query(self.ctx.h, self.handle, radius, _ptr(q), len(q), _ptr(idx), _ptr(d2)))
+        return idx, d2
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.hop_cloud_free(self.ctx.h, self.handle)
+            self.handle = None
+
+
+class Context:
+    """hop_ctx*: one per process/GPU.  Raises HopError when no B200-class device is present (no CPU fallback)."""
+
+    def __init__(self, device=0):
+        self.L = load_library()
+        h = _vp()
+        rc = self.L.hop_create(device, C.byref(h))
+        if rc != 0:
+            raise HopError(f"hop_create({device}) failed ({rc}): {self.L.hop_last_error(None).decode()}")
+        self.h = h
+        self.device = device
+
+    def _check(self, rc):
+        if rc != 0:
+            raise HopError(f"libhop error {rc}: {self.L.hop_last_error(self.h).decode()}")
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hop_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def set_stream(self, cuda_stream_handle):
+        self._check(self.L.hop_set_stream(self.h, _vp(cuda_stream_handle) if cuda_stream_handle else None))
+
+    def sync(self):
+        self._check(self.L.hop_sync(self.h))
+
+    def launch_count(self):
+        return int(self.L.hop_launch_count(self.h))
+
+    def malloc(self, nbytes):
+        p = _vp()
+        self._check(self.L.hop_malloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def free(self, dptr):
+        self._check(self.L.hop_free(self.h, _vp(dptr)))
+
+    def pinned_array(self, shape, dtype=np.float32):
+        """numpy array backed by pinned host memory (cudaHostAlloc); kept alive by the context."""
+        n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        p = _vp()
+        self._check(self.L.hop_host_alloc(self.h, max(n, 1), C.byref(p)))
+        buf = (C.c_char * max(n, 1)).from_address(p.value)
+        arr = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append((p.value, buf))
+        return arr
+
+    def h2d(self, dptr, host_array):
+        a = np.ascontiguousarray(host_array)
+        self._check(self.L.hop_memcpy_h2d(self.h, _vp(dptr), _ptr(a), a.nbytes))
+        return a  # caller keeps it alive until sync
+
+    def d2h(self, host_array, dptr):
+        assert host_array.flags["C_CONTIGUOUS"]
+        self._check(self.L.hop_memcpy_d2h(self.h, _ptr(host_array), _vp(dptr), host_array.nbytes))
+
+    # ---- clouds ----
+    def upload_cloud(self, xyz, nrm=None, prob=None):
+        xyz = _f32(xyz, 3)
+        nrm = None if nrm is None else _f32(nrm, 3)
+        prob = None if prob is None else _f32(prob)
+        h = _vp()
+        self._check(self.L.hop_cloud_upload(self.h, _ptr(xyz), _ptr(nrm), _ptr(prob), len(xyz), C.byref(h)))
+        return Cloud(self, h, len(xyz))
+
+    def icp_params(self, **kw):
+        p = IcpParams()
+        self.L.hop_default_icp_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def lcp_params(self, **kw):
+        p = LcpParams()
+        self.L.hop_default_lcp_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    # ---- K4 / K5 / winners, host buffers (the reference-facing calls) ----
+    def icp_refine(self, scene, model, poses, params=None):
+        """poses (H,4,4) model2scene -> refined (H,4,4), iterations (H,), converged (H,)."""
+        params = params or self.icp_params()
+        flat = poses_to_colmajor(poses)
+        H = len(flat)
+        iters = np.zeros(H, np.int32)
+        conv = np.zeros(H, np.int32)
+        self._check(self.L.hop_icp_refine(self.h, scene.handle, model.handle, _ptr(flat), H, C.byref(params), _ptr(iters), _ptr(conv)))
+        return colmajor_to_poses(flat), iters, conv
+
+    def lcp_score(self, scene, model, poses, params=None, use_weights=False):
+        params = params or self.lcp_params()
+        flat = poses_to_colmajor(poses)
+        H = len(flat)
+        scores = np.zeros(H, np.float32)
+        self._check(self.L.hop_lcp_score(self.h, scene.handle, model.handle, _ptr(flat), H, C.byref(params), int(use_weights), _ptr(scores)))
+        return scores
+
+    def select_topk(self, poses, scores, K, id_offset=0, frame=0):
+        flat = poses_to_colmajor(poses)
+        scores = _f32(scores)
+        out = np.zeros(K, POSE_REC_DTYPE)
+        self._check(self.L.hop_select_topk(self.h, _ptr(flat), _ptr(scores), len(flat), K, id_offset, frame, _ptr(out)))
+        return out
+
+    # ---- device-pointer variants (inputs already resident in HBM) ----
+    def icp_refine_dev(self, scene, model, d_poses, H, params, d_iters=None, d_conv=None):
+        self._check(self.L.hop_icp_refine_dev(self.h, scene.handle, model.handle, _vp(d_poses), H, C.byref(params),
+                                              _vp(d_iters) if d_iters else None, _vp(d_conv) if d_conv else None))
+
+    def lcp_score_dev(self, scene, model, d_poses, H, params, d_scores, use_weights=False):
+        self._check(self.L.hop_lcp_score_dev(self.h, scene.handle, model.handle, _vp(d_poses), H, C.byref(params),
+                                             int(use_weights), _vp(d_scores)))
+
+    def select_topk_dev(self, d_poses, d_scores, H, K, d_out, id_offset=0, frame=0):
+        self._check(self.L.hop_select_topk_dev(self.h, _vp(d_poses), _vp(d_scores), H, K, id_offset, frame, _vp(d_out)))

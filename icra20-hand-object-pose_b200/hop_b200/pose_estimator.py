@@ -1,0 +1,89 @@
+"""Host mirror of the reference's PoseEstimator stage object for the hot path.
+
+Same method names, argument meaning and error behaviour as src/perception/include/PoseEstimator.h:11-49 /
+src/perception/src/PoseEstimator.cpp for the calls on the north-star path:
+    refineByICP()   PoseEstimator.cpp:235-275  -> hop_icp_refine  (K4)
+    selectBest()    PoseEstimator.cpp:465-502  -> hop_lcp_score   (K5) + arg-max
+PCL is absent, so clouds are (xyz, normal[, confidence]) numpy arrays instead of pcl::PointCloud<PointT>::Ptr.
+The native C++ mirror of the same class lives in ../host/ (used by main_realdata_auto).
+"""
+from dataclasses import dataclass, field
+
+import numpy as np
+
+
+@dataclass
+class PoseHypo:
+    """class PoseHypo (src/perception/include/PoseHypo.h:7-27)."""
+    _pose: np.ndarray = field(default_factory=lambda: np.eye(4, dtype=np.float32))
+    _id: int = -1
+    _lcp_score: float = 0.0
+    _wrong_ratio: float = 1.0
+
+
+class PoseEstimator:
+    def __init__(self, ctx, cfg=None):
+        """cfg: dict with the config_autodataset.yaml keys used on this path (icp_dist_thres, icp_angle_thres, lcp.*)."""
+        self.ctx = ctx
+        cfg = cfg or {}
+        self.icp_dist_thres = float(cfg.get("icp_dist_thres", 0.01))
+        self.icp_angle_thres = float(cfg.get("icp_angle_thres", 45))
+        lcp = cfg.get("lcp", {})
+        self.lcp_dist = float(lcp.get("dist", 0.001))
+        self.lcp_normal_angle = float(lcp.get("normal_angle", 10))
+        self.max_icp_candidates = 100  # PoseEstimator.cpp:241
+        self._pose_hypos = []
+        self._scene = self._model = self._model001 = None
+
+    # -- setCurScene (PoseEstimator.cpp:36-45): keeps the high-confidence scene (confidence >= thres)
+    def setCurScene(self, scene_xyz, scene_nrm, confidence=None, high_confidence_thres=0.8):
+        scene_xyz = np.asarray(scene_xyz, np.float32)
+        scene_nrm = np.asarray(scene_nrm, np.float32)
+        if confidence is not None:
+            keep = np.asarray(confidence) >= high_confidence_thres
+            scene_xyz, scene_nrm, confidence = scene_xyz[keep], scene_nrm[keep], np.asarray(confidence, np.float32)[keep]
+        if self._scene is None:
+            self._scene = self.ctx.upload_cloud(scene_xyz, scene_nrm, confidence)
+        else:
+            self._scene.update(scene_xyz, scene_nrm, confidence)
+
+    def setModel(self, model_xyz, model_nrm, model001_xyz=None, model001_nrm=None):
+        """_model (5 mm, ICP / Super4PCS) and _model001 (1 mm, scoring) (main_realdata_auto.cpp:33-38)."""
+        self._model = self.ctx.upload_cloud(model_xyz, model_nrm)
+        if model001_xyz is None:
+            self._model001 = self._model
+        else:
+            self._model001 = self.ctx.upload_cloud(model001_xyz, model001_nrm)
+
+    def setPoseHypos(self, poses, scores=None):
+        poses = np.asarray(poses, np.float32).reshape(-1, 4, 4)
+        scores = np.zeros(len(poses), np.float32) if scores is None else np.asarray(scores, np.float32)
+        self._pose_hypos = [PoseHypo(poses[i].copy(), i, float(scores[i])) for i in range(len(poses))]
+
+    def refineByICP(self):
+        """Keeps the first min(N,100) hypotheses and replaces each pose by T_icp^-1 * pose (PoseEstimator.cpp:235-275)."""
+        keep = self._pose_hypos[: min(len(self._pose_hypos), self.max_icp_candidates)]
+        if not keep:
+            self._pose_hypos = []
+            return
+        poses = np.stack([h._pose for h in keep])
+        params = self.ctx.icp_params(max_iter=10, angle_deg=self.icp_angle_thres, max_dist=self.icp_dist_thres)
+        refined, _, _ = self.ctx.icp_refine(self._scene, self._model, poses, params)
+        for h, p in zip(keep, refined):
+            h._pose = p
+        self._pose_hypos = keep
+
+    def selectBest(self):
+        """Scores every hypothesis with computeLCP(1 mm model, lcp.dist, lcp.normal_angle, true,true,true) and returns
+        the arg-max (first best, best_lcp starts at 0 -> hypothesis 0 when nothing scores) (PoseEstimator.cpp:465-502)."""
+        if not self._pose_hypos:
+            raise IndexError("selectBest on an empty hypothesis list (the reference dereferences _pose_hypos[0])")
+        poses = np.stack([h._pose for h in self._pose_hypos])
+        params = self.ctx.lcp_params(dist=self.lcp_dist, angle_deg=self.lcp_normal_angle)
+        scores = self.ctx.lcp_score(self._scene, self._model001, poses, params)
+        best, best_lcp = self._pose_hypos[0], 0.0
+        for h, s in zip(self._pose_hypos, scores):
+            h._lcp_score = float(s)
+            if h._lcp_score > best_lcp:
+                best, best_lcp = h, h._lcp_score
+        return best

@@ -1,0 +1,143 @@
+/*
+ * hop_c_api.h -- C ABI of libhop.so, the B200 (sm_100a) implementation of the pose-hypothesis hot path of
+ * wenbowen123/icra20-hand-object-pose.  Plain pointers and sizes only; no C++/torch types cross this boundary.
+ *
+ * The reference has no FFI: its boundary is a set of C++ methods.  Each entry point below names the reference
+ * interface it replaces (paths relative to the reference root):
+ *
+ *   hop_icp_refine        <- PoseEstimator<PointT>::refineByICP()   src/perception/src/PoseEstimator.cpp:235-275
+ *                            (per hypothesis: Utils::runICP<PointT>  src/perception/src/Utils.cpp:188-229)
+ *   hop_lcp_score         <- PoseEstimator<PointT>::selectBest()    src/perception/src/PoseEstimator.cpp:465-502
+ *                            (per hypothesis: Utils::computeLCP<PointT> src/perception/src/Utils.cpp:372-444)
+ *   hop_select_topk       <- the argmax inside selectBest (:491-496) / the 100-candidate cap of refineByICP (:241)
+ *   hop_verify_lcp        <- gr::CongruentSetExplorationBase::TryCongruentSet / Verify
+ *                            src/OpenGR_4pcs/src/gr/algorithms/congruentSetExplorationBase.hpp:221-340, 346-435
+ *                            (+ MatchBase::ComputeRigidTransformation matchBase.hpp:230-377)
+ *   hop_hand_overlap      <- objFuncPSO                             src/perception/src/Hand.cpp:10-178
+ *   hop_cloud_upload      <- the pcl::PointCloud<PointT>::Ptr arguments of the calls above (PointSurfel /
+ *                            PointXYZRGBNormal: xyz + normal + confidence)
+ *   hop_pose_rec          <- class PoseHypo                          src/perception/include/PoseHypo.h:7-27
+ *
+ * Conventions
+ *   - every function returns 0 (HOP_OK) or a negative HOP_E* code; hop_last_error() gives the message.
+ *   - 4x4 transforms are 16 floats, COLUMN-major (Eigen::Matrix4f::data() passes through unchanged).
+ *   - units: metres, degrees (as in config_autodataset.yaml).
+ *   - "host" entry points take host pointers and block until results are in the caller's buffers
+ *     (they include the host<->device copies); "_dev" entry points take device pointers, enqueue on the
+ *     context's stream and return without synchronising.
+ *   - there is NO CPU fallback: without a CUDA device hop_create() fails with HOP_ENODEV.
+ */
+#ifndef HOP_C_API_H_
+#define HOP_C_API_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HOP_OK 0
+#define HOP_EINVAL (-1)  /* bad argument */
+#define HOP_ECUDA (-2)   /* CUDA runtime error (message in hop_last_error) */
+#define HOP_ENODEV (-3)  /* no usable CUDA device (this library never computes on the CPU) */
+#define HOP_ENOMEM (-4)
+
+typedef struct hop_ctx hop_ctx;     /* one per host thread / GPU; owns a stream and scratch buffers */
+typedef struct hop_cloud hop_cloud; /* device-resident point cloud (+ cached nearest-neighbour grids) */
+
+/* wire record for winners; mirrors class PoseHypo (80 bytes, PoseHypo.h:7-27) */
+typedef struct hop_pose_rec {
+  float pose[16]; /* model2scene, column-major */
+  float score;    /* _lcp_score */
+  int32_t id;     /* _id (index of the hypothesis in the caller's batch) */
+  int32_t frame;  /* caller-defined tag (frame / rank) */
+  int32_t pad;
+} hop_pose_rec;
+
+/* Utils::runICP arguments (Utils.cpp:188) + the PCL criteria the reference sets (Utils.cpp:207-208) */
+typedef struct hop_icp_params {
+  int32_t max_iter;     /* 10 in refineByICP (PoseEstimator.cpp:266), 50 in handbaseICP (Hand.cpp:734) */
+  float angle_deg;      /* rejection_angle: icp_angle_thres (45) */
+  float max_dist;       /* max_corres_dist: icp_dist_thres (0.01) */
+  double abs_mse_eps;   /* setAbsoluteMSE(1e-6) */
+  int32_t mode;         /* 0 = point-to-plane (the reference's hot ICP); 1 = point-to-point SVD (Utils.cpp:135-184) */
+  int32_t solver;       /* mode 0 only: 0 = exact nonlinear least squares per iteration (what PCL's LM converges to);
+                                         1 = one Gauss-Newton step per iteration (fewer registers, not the parity path) */
+  int32_t team_warps;   /* warps cooperating on one hypothesis: 0 = auto, else 1/2/4/8 */
+  int32_t reserved;
+} hop_icp_params;
+
+/* Utils::computeLCP arguments (Utils.cpp:372) */
+typedef struct hop_lcp_params {
+  float dist;           /* lcp.dist (0.001) */
+  float angle_deg;      /* lcp.normal_angle (10) */
+  int32_t use_normal;   /* selectBest passes true,true,true (PoseEstimator.cpp:488) */
+  int32_t use_dot_score;
+  int32_t use_reciprocal;
+  int32_t team_warps;   /* 0 = auto */
+} hop_lcp_params;
+
+/* ---- context ------------------------------------------------------------------------------------------- */
+int hop_create(int device, hop_ctx **out);
+void hop_destroy(hop_ctx *ctx);
+const char *hop_last_error(const hop_ctx *ctx); /* ctx may be NULL: error of the last failed hop_create */
+/* use the caller's CUDA stream (cudaStream_t as void*) for everything this context enqueues; NULL = own stream */
+int hop_set_stream(hop_ctx *ctx, void *cuda_stream);
+int hop_sync(hop_ctx *ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t hop_launch_count(const hop_ctx *ctx);
+void hop_default_icp_params(hop_icp_params *p);
+void hop_default_lcp_params(hop_lcp_params *p);
+
+/* ---- memory helpers for FFI callers that have no CUDA binding of their own ------------------------------- */
+int hop_malloc(hop_ctx *ctx, size_t bytes, void **dev_ptr);
+int hop_free(hop_ctx *ctx, void *dev_ptr);
+int hop_host_alloc(hop_ctx *ctx, size_t bytes, void **host_ptr); /* pinned */
+int hop_host_free(hop_ctx *ctx, void *host_ptr);
+int hop_memcpy_h2d(hop_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes); /* async on the ctx stream */
+int hop_memcpy_d2h(hop_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes); /* async on the ctx stream */
+
+/* ---- clouds ------------------------------------------------------------------------------------------------ */
+/* xyz: n x 3, nrm: n x 3 or NULL, prob: n (per-point confidence / LCP weight) or NULL.  Host pointers.
+ * The cloud is repacked on the device into two float4 streams (x,y,z,prob) and (nx,ny,nz,1/|n|). */
+int hop_cloud_upload(hop_ctx *ctx, const float *xyz, const float *nrm, const float *prob, int n, hop_cloud **out);
+/* re-use an existing cloud object for a new frame (same or smaller capacity avoids reallocation) */
+int hop_cloud_update(hop_ctx *ctx, hop_cloud *cloud, const float *xyz, const float *nrm, const float *prob, int n);
+int hop_cloud_free(hop_ctx *ctx, hop_cloud *cloud);
+int hop_cloud_size(const hop_cloud *cloud);
+/* Build (or fetch from the cloud's cache) the exact nearest-neighbour grid for queries within `radius`.
+ * voxel <= 0 picks the voxel edge automatically.  Called implicitly by the entry points below; exposed so a
+ * caller can pay the per-model cost up front.  stats (may be NULL): [0]=voxels [1]=candidate entries
+ * [2]=max list length [3]=bytes. */
+int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, int64_t *stats);
+/* exact 1-NN of host queries (nq x 3) within the prepared radius: idx = -1 when none. (test / debug entry) */
+int hop_cloud_nn_query(hop_ctx *ctx, hop_cloud *cloud, float radius, const float *queries, int nq, int32_t *idx, float *d2);
+
+/* ---- K4: ICP refinement of a batch of hypotheses ----------------------------------------------------------- */
+/* poses_inout: H x 16 model2scene; replaced by T_icp^-1 * pose (PoseEstimator.cpp:267-269).
+ * iters_out / converged_out (H, may be NULL): ICP iterations executed / reg.hasConverged(). */
+int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *poses_inout, int H,
+                   const hop_icp_params *params, int32_t *iters_out, int32_t *converged_out);
+int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *d_poses_inout, int H,
+                       const hop_icp_params *params, int32_t *d_iters_out, int32_t *d_converged_out);
+
+/* ---- K5: LCP score of a batch of hypotheses ------------------------------------------------------------------ */
+/* scene weights are the scene cloud's prob channel when use_weights != 0, else 1 (selectBest uses 1). */
+int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *poses, int H,
+                  const hop_lcp_params *params, int use_weights, float *scores_out);
+int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H,
+                      const hop_lcp_params *params, int use_weights, float *d_scores_out);
+
+/* ---- winners ------------------------------------------------------------------------------------------------- */
+/* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).
+ * d_out may be the send slot of a collective (the all-gather of winners). */
+int hop_select_topk_dev(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset,
+                        int32_t frame, hop_pose_rec *d_out);
+int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H, int K, int32_t id_offset,
+                    int32_t frame, hop_pose_rec *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HOP_C_API_H_ */

@@ -1,0 +1,27 @@
+#!/bin/sh
+# Compiles oracle/_ref/libhop_ref.so from the reference tree's sources WHERE THEY LIE (read-only).
+# The OpenGR fork has one defect that makes it unusable as compiled (KdTree::operator= is declared bool but has
+# no return statement: src/OpenGR_4pcs/src/gr/accelerators/kdtree.h:148-156 -> g++ falls through / traps).
+# A one-line-patched copy of THAT header is generated into a throw-away directory that shadows it on the
+# include path for this compilation only; it is deleted afterwards and never enters the repository.
+set -e
+REF="${1:-/root/reference}"
+CXX="${2:-g++}"
+HERE="$(cd "$(dirname "$0")" && pwd)"
+EIGEN="$REF/src/OpenGR_4pcs/3rdparty/Eigen"
+GR="$REF/src/OpenGR_4pcs/src"
+mkdir -p "$HERE/_ref"
+TMP="$(mktemp -d)"
+trap 'rm -rf "$TMP"' EXIT
+SRCS="$HERE/ref_eigen_lm.cpp"
+INCS="-I$EIGEN"
+if [ -f "$HERE/ref_opengr.cpp" ]; then
+  mkdir -p "$TMP/gr/accelerators"
+  # insert "return true;" before the closing brace of operator= (first "}" at 2-space indent after the signature)
+  awk 'BEGIN{s=0} /bool operator=\(/{s=1} {if(s==1 && $0 ~ /^[ \t]*}[ \t]*$/){print "    return true;"; s=2} print}' \
+      "$GR/gr/accelerators/kdtree.h" > "$TMP/gr/accelerators/kdtree.h"
+  SRCS="$SRCS $HERE/ref_opengr.cpp"
+  INCS="-I$TMP -I$GR $INCS"
+fi
+$CXX -std=c++17 -O2 -fopenmp -fPIC -shared -w $INCS -o "$HERE/_ref/libhop_ref.so" $SRCS
+echo "oracle: built $HERE/_ref/libhop_ref.so"

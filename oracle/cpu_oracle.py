@@ -1,0 +1,168 @@
+"""ctypes access to the CPU oracle (TEST INFRASTRUCTURE ONLY).
+
+Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this module.
+liboracle.so = plain-C restatement (hop_oracle*.c); _ref/libhop_ref.so = pieces compiled from the reference tree.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+_i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+def build(verbose=False):
+    r = subprocess.run(["make", "-C", _HERE], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("oracle build failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout)
+
+
+_lib = None
+_ref = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        path = os.path.join(_HERE, "liboracle.so")
+        if not os.path.exists(path):
+            build()
+        _lib = C.CDLL(path)
+        L = _lib
+        L.hop_oracle_nn.argtypes = [_f32p, C.c_int, _f32p, C.c_int, C.c_int, _i32p, _f32p]
+        L.hop_oracle_transform_cloud.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, _f32p]
+        L.hop_oracle_compute_lcp.restype = C.c_float
+        L.hop_oracle_compute_lcp.argtypes = [_f32p, _f32p, C.c_int, C.c_void_p, _f32p, _f32p, C.c_int, C.c_float,
+                                             C.c_float, C.c_int, C.c_int, C.c_int]
+        L.hop_oracle_warp6d.argtypes = [_f32p, _f32p]
+        L.hop_oracle_lm_point_to_plane.restype = C.c_int
+        L.hop_oracle_lm_point_to_plane.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, C.POINTER(C.c_int)]
+        L.hop_oracle_set_lm_backend.argtypes = [C.c_void_p]
+        L.hop_oracle_run_icp.restype = C.c_int
+        L.hop_oracle_run_icp.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.c_float,
+                                         C.c_float, C.c_double, C.POINTER(C.c_int)]
+        L.hop_oracle_refine_by_icp.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, C.c_int,
+                                               C.c_float, C.c_float, C.c_double, C.c_int, _i32p, _i32p]
+        L.hop_oracle_select_best.restype = C.c_int
+        L.hop_oracle_select_best.argtypes = [_f32p, _f32p, C.c_int, C.c_void_p, _f32p, _f32p, C.c_int, _f32p, C.c_int,
+                                             C.c_float, C.c_float, C.c_int, _f32p]
+        L.hop_oracle_num_threads.restype = C.c_int
+    return _lib
+
+
+def ref():
+    """oracle/_ref/libhop_ref.so or None when it was never built (no /root/reference at build time)."""
+    global _ref
+    if _ref is None:
+        path = os.path.join(_HERE, "_ref", "libhop_ref.so")
+        if not os.path.exists(path):
+            return None
+        _ref = C.CDLL(path)
+        _ref.hop_ref_lm_point_to_plane.restype = C.c_int
+        _ref.hop_ref_lm_point_to_plane.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, C.POINTER(C.c_int)]
+    return _ref
+
+
+def _c(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def poses_to_colmajor(poses):
+    """(H,4,4) row-major numpy matrices -> (H,16) column-major float32 (Eigen::Matrix4f::data())."""
+    p = np.asarray(poses, dtype=np.float32).reshape(-1, 4, 4)
+    return np.ascontiguousarray(p.transpose(0, 2, 1).reshape(-1, 16))
+
+
+def colmajor_to_poses(flat):
+    return np.asarray(flat, dtype=np.float32).reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+def nn(pts, q, use_kdtree=True):
+    pts, q = _c(pts), _c(q)
+    idx = np.empty(len(q), np.int32)
+    d2 = np.empty(len(q), np.float32)
+    lib().hop_oracle_nn(pts, len(pts), q, len(q), int(use_kdtree), idx, d2)
+    return idx, d2
+
+
+def transform_cloud(T, xyz, nrm):
+    xyz, nrm = _c(xyz), _c(nrm)
+    oxyz, onrm = np.empty_like(xyz), np.empty_like(nrm)
+    lib().hop_oracle_transform_cloud(poses_to_colmajor(T)[0], xyz, nrm, len(xyz), oxyz, onrm)
+    return oxyz, onrm
+
+
+def compute_lcp(s_xyz, s_nrm, m_xyz, m_nrm, dist, angle, weights=None, use_normal=True, use_dot=True, use_recip=True):
+    s_xyz, s_nrm, m_xyz, m_nrm = _c(s_xyz), _c(s_nrm), _c(m_xyz), _c(m_nrm)
+    w = None if weights is None else _c(weights).ctypes.data_as(C.c_void_p)
+    return float(lib().hop_oracle_compute_lcp(s_xyz, s_nrm, len(s_xyz), w, m_xyz, m_nrm, len(m_xyz), dist, angle,
+                                              int(use_normal), int(use_dot), int(use_recip)))
+
+
+def lm_point_to_plane(src, tgt, nrm, backend="c"):
+    src, tgt, nrm = _c(src), _c(tgt), _c(nrm)
+    x = np.zeros(6, np.float32)
+    nfev = C.c_int(0)
+    if backend == "c":
+        info = lib().hop_oracle_lm_point_to_plane(src, tgt, nrm, len(src), x, C.byref(nfev))
+    else:
+        info = ref().hop_ref_lm_point_to_plane(src, tgt, nrm, len(src), x, C.byref(nfev))
+    return x, info, nfev.value
+
+
+def use_ref_lm(enable=True):
+    """Route the LM step of hop_oracle_run_icp through the reference tree's own Eigen LM (oracle/_ref)."""
+    if enable:
+        r = ref()
+        if r is None:
+            raise RuntimeError("oracle/_ref not built")
+        lib().hop_oracle_set_lm_backend(C.cast(r.hop_ref_lm_point_to_plane, C.c_void_p))
+    else:
+        lib().hop_oracle_set_lm_backend(None)
+
+
+def warp6d(x):
+    T = np.empty(16, np.float32)
+    lib().hop_oracle_warp6d(_c(x), T)
+    return colmajor_to_poses(T)[0]
+
+
+def run_icp(src_xyz, src_nrm, tgt_xyz, tgt_nrm, max_iter=10, angle=45.0, dist=0.01, abs_mse_eps=1e-6):
+    src_xyz, src_nrm, tgt_xyz, tgt_nrm = _c(src_xyz), _c(src_nrm), _c(tgt_xyz), _c(tgt_nrm)
+    T = np.empty(16, np.float32)
+    conv = C.c_int(0)
+    it = lib().hop_oracle_run_icp(src_xyz, src_nrm, len(src_xyz), tgt_xyz, tgt_nrm, len(tgt_xyz), T, max_iter, angle,
+                                  dist, abs_mse_eps, C.byref(conv))
+    return colmajor_to_poses(T)[0], it, bool(conv.value)
+
+
+def refine_by_icp(s_xyz, s_nrm, m_xyz, m_nrm, poses, max_iter=10, angle=45.0, dist=0.01, abs_mse_eps=1e-6, nthreads=0):
+    """poses: (H,4,4) model2scene. Returns refined (H,4,4), iterations (H,), converged (H,)."""
+    s_xyz, s_nrm, m_xyz, m_nrm = _c(s_xyz), _c(s_nrm), _c(m_xyz), _c(m_nrm)
+    flat = poses_to_colmajor(poses)
+    H = len(flat)
+    iters = np.zeros(H, np.int32)
+    conv = np.zeros(H, np.int32)
+    lib().hop_oracle_refine_by_icp(s_xyz, s_nrm, len(s_xyz), m_xyz, m_nrm, len(m_xyz), flat, H, max_iter, angle, dist,
+                                   abs_mse_eps, nthreads, iters, conv)
+    return colmajor_to_poses(flat), iters, conv
+
+
+def select_best(s_xyz, s_nrm, m_xyz, m_nrm, poses, dist=0.001, angle=10.0, weights=None, nthreads=0):
+    s_xyz, s_nrm, m_xyz, m_nrm = _c(s_xyz), _c(s_nrm), _c(m_xyz), _c(m_nrm)
+    flat = poses_to_colmajor(poses)
+    H = len(flat)
+    scores = np.zeros(H, np.float32)
+    w = None if weights is None else _c(weights).ctypes.data_as(C.c_void_p)
+    best = lib().hop_oracle_select_best(s_xyz, s_nrm, len(s_xyz), w, m_xyz, m_nrm, len(m_xyz), flat, H, dist, angle,
+                                        nthreads, scores)
+    return int(best), scores
+
+
+def num_threads():
+    return int(lib().hop_oracle_num_threads())
