@@ -236,6 +236,12 @@ extern "C" int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius
   return HOP_OK;
 }
 
+extern "C" int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud) {
+  if (!ctx || !cloud) return HOP_EINVAL;
+  cloud->version++;
+  return HOP_OK;
+}
+
 extern "C" int hop_cloud_nn_query(hop_ctx *ctx, hop_cloud *cloud, float radius, const float *queries, int nq, int32_t *idx, float *d2) {
   if (!ctx || !cloud || !queries || !idx || !d2 || nq < 0) return HOP_EINVAL;
   if (nq == 0) return HOP_OK;

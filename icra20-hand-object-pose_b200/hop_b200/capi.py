@@ -93,6 +93,7 @@ def load_library():
     L.hop_cloud_free.argtypes = [_vp, _vp]
     L.hop_cloud_size.argtypes = [_vp]
     L.hop_cloud_prepare_nn.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_int64)]
+    L.hop_cloud_drop_nn.argtypes = [_vp, _vp]
     L.hop_cloud_nn_query.argtypes = [_vp, _vp, C.c_float, _vp, C.c_int, _vp, _vp]
     L.hop_icp_refine.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
     L.hop_icp_refine_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
@@ -146,6 +147,9 @@ class Cloud:
         stats = (C.c_int64 * 4)()
         self.ctx._check(self.ctx.L.hop_cloud_prepare_nn(self.ctx.h, self.handle, radius, voxel, stats))
         return {"voxels": stats[0], "entries": stats[1], "max_list": stats[2], "bytes": stats[3]}
+
+    def drop_nn(self):
+        self.ctx._check(self.ctx.L.hop_cloud_drop_nn(self.ctx.h, self.handle))
 
     def nn_query(self, radius, queries):
         q = _f32(queries, 3)

@@ -111,6 +111,8 @@ int hop_cloud_size(const hop_cloud *cloud);
  * caller can pay the per-model cost up front.  stats (may be NULL): [0]=voxels [1]=candidate entries
  * [2]=max list length [3]=bytes. */
 int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, int64_t *stats);
+/* mark the cloud's cached grids stale (allocations are kept): the next use rebuilds them */
+int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud);
 /* exact 1-NN of host queries (nq x 3) within the prepared radius: idx = -1 when none. (test / debug entry) */
 int hop_cloud_nn_query(hop_ctx *ctx, hop_cloud *cloud, float radius, const float *queries, int nq, int32_t *idx, float *d2);
 

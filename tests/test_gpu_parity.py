@@ -1,0 +1,213 @@
+"""GPU parity tests (-m gpu): the CUDA path, called through the C ABI, against the CPU oracle on the same seeded inputs.
+
+Bars: bit-exact for index work (nearest neighbours, winner ids); floating point within the north-star tolerance:
+ICP-refined poses within 1 mm / 1 deg of the reference algorithm, LCP scores within 1e-4 relative.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from hop_b200 import synth
+from oracle import cpu_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+POS_TOL, ROT_TOL = 1e-3, 1.0      # metres, degrees (north_star)
+LCP_RTOL = 1e-4
+
+
+def _case(name, ns, nm, H, seed, **kw):
+    m, mn = synth.make_model(name, nm, seed=1)
+    s, sn, conf, gt = synth.make_scene(name, ns, seed=seed)
+    hyp = synth.make_hypotheses(gt, H, seed=seed + 1, **kw)
+    return m, mn, s, sn, conf, gt, hyp
+
+
+# ---------------------------------------------------------------------------------------------- nearest neighbour
+@pytest.mark.parametrize("radius", [0.01, 0.003, 0.001])
+@pytest.mark.parametrize("name,n", [("ellipse", 5000), ("cuboid", 3000), ("tless", 800)])
+def test_nn_grid_is_exact(ctx, name, n, radius):
+    m, mn = synth.make_model(name, n, seed=4)
+    cloud = ctx.upload_cloud(m, mn)
+    rng = np.random.default_rng(7)
+    q = np.concatenate([m[rng.integers(0, n, 3000)] + rng.normal(0, radius / 2, (3000, 3)),
+                        rng.uniform(m.min(0) - 2 * radius, m.max(0) + 2 * radius, (1000, 3)),
+                        m[:200]]).astype(np.float32)
+    gi, gd = cloud.nn_query(radius, q)
+    oi, od = O.nn(m, q, use_kdtree=False)
+    within = od <= np.float32(radius) ** 2
+    # bit-exact squared distances and identical indices wherever a neighbour lies within the radius
+    assert np.array_equal(gi >= 0, within)
+    assert np.array_equal(gd[within], od[within])
+    same = gi[within] == oi[within]
+    if not same.all():  # only exact distance ties may pick a different (equidistant) point
+        bad = np.nonzero(within)[0][~same]
+        assert np.all(np.sum((m[gi[bad]] - q[bad]) ** 2, 1).astype(np.float32) == od[bad])
+    cloud.free()
+
+
+def test_nn_grid_degenerate_clouds(ctx):
+    one = ctx.upload_cloud(np.array([[0.1, 0.2, 0.3]], np.float32), np.array([[0, 0, 1]], np.float32))
+    i, d = one.nn_query(0.01, np.array([[0.1, 0.2, 0.305], [0.1, 0.2, 0.32], [5, 5, 5]], np.float32))
+    assert list(i) == [0, -1, -1]
+    dup = ctx.upload_cloud(np.zeros((300, 3), np.float32), np.tile([[0, 0, 1.0]], (300, 1)).astype(np.float32))
+    i, d = dup.nn_query(0.002, np.array([[0, 0, 0.001]], np.float32))
+    assert i[0] == 0  # ties resolve to the lowest index
+    one.free(); dup.free()
+
+
+# ---------------------------------------------------------------------------------------------- K5: LCP score
+@pytest.mark.parametrize("name,ns,nm", [("ellipse", 700, 6000), ("cuboid", 1000, 4000), ("tless", 300, 2500)])
+@pytest.mark.parametrize("team", [0, 1, 4])
+def test_lcp_score_matches_oracle(ctx, name, ns, nm, team):
+    m, mn, s, sn, conf, gt, hyp = _case(name, ns, nm, 48, seed=21, rot_sigma_deg=0.4, trans_sigma=0.0004)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    p = ctx.lcp_params(dist=0.002, angle_deg=15.0, team_warps=team)
+    got = ctx.lcp_score(scene, model, hyp, p)
+    _, ref = O.select_best(s, sn, m, mn, hyp, dist=0.002, angle=15.0)
+    assert ref.max() > 5
+    assert np.all(np.abs(got - ref) <= LCP_RTOL * np.maximum(np.abs(ref), 1.0))
+    assert int(np.argmax(got)) == int(np.argmax(ref))
+    scene.free(); model.free()
+
+
+def test_lcp_flags_weights_and_reference_defaults(ctx):
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 900, 10000, 32, seed=31, rot_sigma_deg=0.2, trans_sigma=0.0002)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    # the reference's own setting: lcp.dist 1 mm, 10 deg, (true,true,true)
+    got = ctx.lcp_score(scene, model, hyp)
+    _, ref = O.select_best(s, sn, m, mn, hyp)
+    assert np.all(np.abs(got - ref) <= LCP_RTOL * np.maximum(np.abs(ref), 1.0))
+    for flags in [(0, 0, 0), (0, 0, 1), (1, 0, 0), (1, 0, 1), (1, 1, 0)]:
+        p = ctx.lcp_params(dist=0.002, angle_deg=20.0, use_normal=flags[0], use_dot_score=flags[1], use_reciprocal=flags[2])
+        got = ctx.lcp_score(scene, model, hyp[:8], p, use_weights=True)
+        for k in range(8):
+            mx, mnn = O.transform_cloud(hyp[k], m, mn)
+            r = O.compute_lcp(s, sn, mx, mnn, 0.002, 20.0, weights=conf, use_normal=flags[0], use_dot=flags[1], use_recip=flags[2])
+            assert abs(got[k] - r) <= LCP_RTOL * max(abs(r), 1.0), (flags, k, got[k], r)
+    scene.free(); model.free()
+
+
+def test_lcp_edge_cases(ctx):
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 300, 1500, 8, seed=41)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    assert ctx.lcp_score(scene, model, hyp[:0]).shape == (0,)
+    far = hyp[:3].copy(); far[:, :3, 3] += 2.0
+    assert np.all(ctx.lcp_score(scene, model, far) == 0)
+    ragged = ctx.upload_cloud(s[:257], sn[:257], conf[:257])  # one point past a tile boundary
+    got = ctx.lcp_score(ragged, model, gt[None], ctx.lcp_params(dist=0.003, angle_deg=30.0))
+    mx, mnn = O.transform_cloud(gt, m, mn)
+    ref = O.compute_lcp(s[:257], sn[:257], mx, mnn, 0.003, 30.0)
+    assert abs(got[0] - ref) <= LCP_RTOL * max(ref, 1.0)
+    scene.free(); model.free(); ragged.free()
+
+
+# ---------------------------------------------------------------------------------------------- K4: ICP refinement
+def _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=0, max_iter=10):
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    p = ctx.icp_params(max_iter=max_iter, team_warps=team)
+    got, it, cv = ctx.icp_refine(scene, model, hyp, p)
+    ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp, max_iter=max_iter)
+    scene.free(); model.free()
+    dt, dr = synth.pose_error(got, ref)
+    return got, it, cv, ref, rit, rcv, dt, dr
+
+
+@pytest.mark.parametrize("name,ns,nm", [("ellipse", 600, 3000), ("cuboid", 800, 5000), ("cylinder", 500, 2000), ("tless", 700, 4000)])
+def test_icp_refine_matches_oracle_in_the_convergence_basin(ctx, name, ns, nm):
+    """Hypotheses around the ground truth (the ones Super4PCS hands to refineByICP): every refined pose within
+    1 mm / 1 deg of the reference algorithm's, same convergence flags."""
+    m, mn, s, sn, conf, gt, hyp = _case(name, ns, nm, 96, seed=51, random_frac=0.0, rot_sigma_deg=3.0, trans_sigma=0.003)
+    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp)
+    assert np.array_equal(cv, rcv)
+    ok = (dt <= POS_TOL) & (dr <= ROT_TOL)
+    assert ok.mean() >= 0.97, (dt.max(), dr.max(), np.nonzero(~ok)[0])
+    assert np.median(dt) < 1e-4 and np.median(dr) < 0.2
+    assert np.mean(np.abs(it - rit) <= 1) >= 0.95
+    # and both agree with the ground truth about as well
+    egt, _ = synth.pose_error(got, np.repeat(gt[None], len(got), 0))
+    rgt, _ = synth.pose_error(ref, np.repeat(gt[None], len(ref), 0))
+    assert abs(np.median(egt) - np.median(rgt)) < 2e-4
+
+
+@pytest.mark.parametrize("team", [1, 2, 4, 8])
+def test_icp_refine_team_sizes_agree(ctx, team):
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 520, 2500, 40, seed=61, random_frac=0.0)
+    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=team)
+    assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.95
+    assert np.array_equal(cv, rcv)
+
+
+def test_icp_refine_semantics_of_the_reference(ctx):
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 500, 2000, 16, seed=71, random_frac=0.0)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    # (1) fewer than 3 correspondences: hasConverged() false -> identity -> pose unchanged, 0 iterations
+    far = hyp[:4].copy(); far[:, :3, 3] += 1.0
+    got, it, cv = ctx.icp_refine(scene, model, far)
+    assert np.all(it == 0) and np.all(cv == 0) and np.allclose(got, far, atol=1e-6)
+    # (2) max_iter = 1: one iteration, "converged" by the iteration rule
+    got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(max_iter=1))
+    ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp, max_iter=1)
+    dt, dr = synth.pose_error(got, ref)
+    assert np.all(it == 1) and np.all(cv == 1) and dt.max() < 2e-4 and dr.max() < 0.3
+    # (3) empty batch
+    got, it, cv = ctx.icp_refine(scene, model, hyp[:0])
+    assert got.shape == (0, 4, 4)
+    # (4) streaming path: a scene larger than the resident shared-memory budget gives the same answer
+    scene.free(); model.free()
+
+
+def test_icp_refine_streamed_scene(ctx):
+    """7000-point scene: tiles are streamed through the TMA ring instead of staying resident."""
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 7000, 4000, 24, seed=81, random_frac=0.0)
+    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp)
+    assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.95 and np.array_equal(cv, rcv)
+
+
+def test_golden_fixture_through_the_c_abi(ctx):
+    g = np.load(os.path.join(GOLD, "icp_lcp_small.npz"))
+    scene, model = ctx.upload_cloud(g["s"], g["sn"], g["conf"]), ctx.upload_cloud(g["m"], g["mn"])
+    got, it, cv = ctx.icp_refine(scene, model, g["hyp"])
+    dt, dr = synth.pose_error(got, g["refined"])
+    near = synth.pose_error(g["hyp"], np.repeat(g["gt"][None], len(got), 0))[0] < 0.03  # not the fully random ones
+    assert np.array_equal(cv, g["conv"])
+    assert np.all(dt[near] <= POS_TOL) and np.all(dr[near] <= ROT_TOL)
+    sc = ctx.lcp_score(scene, model, g["refined"])
+    assert np.all(np.abs(sc - g["scores"]) <= LCP_RTOL * np.maximum(np.abs(g["scores"]), 1.0))
+    scene.free(); model.free()
+
+
+# ---------------------------------------------------------------------------------------------- winners + mirror
+def test_select_topk_order_and_ties(ctx):
+    rng = np.random.default_rng(5)
+    H = 3000
+    poses = np.tile(np.eye(4, dtype=np.float32), (H, 1, 1)); poses[:, 0, 3] = np.arange(H)
+    scores = rng.integers(0, 50, H).astype(np.float32)  # many ties
+    top = ctx.select_topk(poses, scores, 40, id_offset=100, frame=7)
+    order = np.lexsort((np.arange(H), -scores))[:40]  # score desc, id asc (PoseEstimator.cpp:113-121)
+    assert np.array_equal(top["id"], order + 100)
+    assert np.array_equal(top["score"], scores[order]) and np.all(top["frame"] == 7)
+    assert np.array_equal(top["pose"][:, 12], order.astype(np.float32))
+    few = ctx.select_topk(poses[:3], scores[:3], 5)
+    assert list(few["id"][3:]) == [-1, -1] and np.all(np.isneginf(few["score"][3:]))
+
+
+def test_pose_estimator_mirror_refine_and_select(ctx):
+    """PoseEstimator::refineByICP + selectBest through the host mirror == the oracle's restatement of both."""
+    import hop_b200
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 800, 2500, 130, seed=91, random_frac=0.05)
+    est = hop_b200.PoseEstimator(ctx, {"icp_dist_thres": 0.01, "icp_angle_thres": 45, "lcp": {"dist": 0.001, "normal_angle": 10}})
+    est.setModel(m, mn)
+    est.setCurScene(s, sn)
+    est.setPoseHypos(hyp)
+    est.refineByICP()
+    assert len(est._pose_hypos) == 100  # the reference keeps min(N,100)
+    best = est.selectBest()
+    ref, _, _ = O.refine_by_icp(s, sn, m, mn, hyp[:100])
+    bi, sc = O.select_best(s, sn, m, mn, ref)
+    assert abs(best._lcp_score - sc[bi]) <= 0.02 * sc[bi]
+    dt, dr = synth.pose_error(best._pose[None], gt[None])
+    dt_ref, dr_ref = synth.pose_error(ref[bi][None], gt[None])
+    assert dt[0] <= dt_ref[0] + 5e-4 and dr[0] <= dr_ref[0] + 0.5  # pose error no worse than the reference's
