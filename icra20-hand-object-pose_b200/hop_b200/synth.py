@@ -144,9 +144,9 @@ def pose_error(A, B):
     A = np.asarray(A, np.float64).reshape(-1, 4, 4)
     B = np.asarray(B, np.float64).reshape(-1, 4, 4)
     dt = np.linalg.norm(A[:, :3, 3] - B[:, :3, 3], axis=1)
-    Rr = np.einsum("nij,nkj->nik", A[:, :3, :3], B[:, :3, :3])
-    c = np.clip((np.trace(Rr, axis1=1, axis2=2) - 1) / 2, -1, 1)
-    return dt, np.rad2deg(np.arccos(c))
+    # angle from the chord |Ra - Rb|_F = 2*sqrt(2)*sin(angle/2): well conditioned near 0 (arccos of the trace is not)
+    chord = np.linalg.norm(A[:, :3, :3] - B[:, :3, :3], axis=(1, 2))
+    return dt, np.rad2deg(2.0 * np.arcsin(np.clip(chord / (2.0 * np.sqrt(2.0)), 0.0, 1.0)))
 
 
 def workload(name):
