@@ -153,7 +153,9 @@ def main():
     dev = torch.device("cuda", local_rank)
 
     ctx = hop_b200.Context(local_rank)  # raises when the CUDA library / device is missing: no fallback
-    stream = torch.cuda.current_stream()
+    # a real (non-default) stream: everything libhop enqueues and every timing event lives on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
 
     model_np, frames = make_frames(wl, rank)

@@ -126,7 +126,8 @@ __device__ __forceinline__ int nn_query(const NNGridDev &g, float px, float py, 
   for (uint32_t k = 0; k < c.y; ++k) {
     float4 q = __ldg(&lst[k]);
     float dx = q.x - px, dy = q.y - py, dz = q.z - pz;
-    float d2 = fmaf(dx, dx, fmaf(dy, dy, dz * dz));
+    // unfused, left to right: the bits of FLANN's / the oracle's dx*dx + dy*dy + dz*dz (index parity needs equal d2)
+    float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
     if (d2 < best_d2) { best_d2 = d2; best = __float_as_int(q.w); best_pt = q; }
   }
   return best;
@@ -175,6 +176,7 @@ struct NNGridHost {
   NNGridDev dev{};
   uint2 *d_cell = nullptr;
   float4 *d_cand = nullptr;
+  unsigned int *d_info = nullptr;  // device: [0] max list length [1] entries [2] overflow flag
   int64_t n_vox = 0, n_cand = 0, cap_vox = 0, cap_cand = 0;
   int max_list = 0;
 };

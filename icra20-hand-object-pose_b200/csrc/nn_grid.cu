@@ -5,10 +5,17 @@
 // inverse pose, and ONE structure per (cloud, radius) is shared by every hypothesis of every frame.
 //
 // Structure: dense voxel grid (edge e, half diagonal h) over the bounding box inflated by the query radius R.
-// For a voxel with centre c let d_c = distance from c to its nearest point.  Any query q inside the voxel has its
-// nearest neighbour m* within |c - m*| <= d_c + 2h, and if only neighbours within R matter, within R + h.  The
-// voxel's list therefore holds { m : |m - c| <= min(d_c + 2h, R + h) } -- a superset of every possible answer, so
-// scanning the list is EXACT.  Built by scatter from the points (three passes: min distance, count, fill).
+// For a voxel V with centre c let m* be the point nearest to c and d_c = |c - m*|.  The voxel's list holds every
+// point m that passes ALL of these necessary conditions for being the nearest neighbour (within R) of some q in V:
+//   (1) |m - c| <= R + h                       only neighbours within R matter;
+//   (2) |m - c| <= d_c + 2h                    triangle inequality through the centre;
+//   (3) |m - c|^2 - d_c^2 <= e * |m - m*|_1    m is not DOMINATED by m* on V: |q-m|^2 - |q-m*|^2 is linear in q, its
+//                                               minimum over the cube is (|c-m|^2 - d_c^2) - e*|m - m*|_1; when that is
+//                                               positive m* is strictly nearer than m everywhere in V.
+// The list is therefore a superset of every possible answer and scanning it is EXACT; (3) keeps lists at a handful
+// of entries even for voxels a centimetre away from the surface, where (2) alone admits hundreds.
+// Built by scatter from the points (three passes: nearest-to-centre, count, fill), with no host synchronisation:
+// the candidate buffer is sized from a geometric upper bound and the fill pass is bounds-checked.
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -25,6 +32,7 @@ struct GridGeom {
   float rc2;    // (R + h)^2
   float h2x;    // 2h
   float rc;     // R + h
+  float e_dom;  // voxel edge with head room, for the dominance test
 };
 
 __device__ __forceinline__ float vox_center_d2(const GridGeom &g, int vx, int vy, int vz, float4 p) {
@@ -33,11 +41,11 @@ __device__ __forceinline__ float vox_center_d2(const GridGeom &g, int vx, int vy
   return dx * dx + dy * dy + dz * dz;
 }
 
-// PASS 0: dnn2[v] = min squared distance (as ordered uint)   PASS 1: cnt[v] += 1   PASS 2: fill cand
+// PASS 0: near[v] = min over points of (d^2 bits << 32 | index)   PASS 1: cnt[v] += 1   PASS 2: fill cand
 template <int PASS>
-__global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, int n, unsigned int *__restrict__ dnn2,
+__global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, int n, unsigned long long *__restrict__ near,
                                     unsigned int *__restrict__ cnt, const unsigned int *__restrict__ off,
-                                    float4 *__restrict__ cand) {
+                                    float4 *__restrict__ cand, unsigned int cap, unsigned int *__restrict__ overflow) {
   const int S = 2 * g.K + 1;
   const int S3 = S * S * S;
   for (int i = blockIdx.x; i < n; i += gridDim.x) {
@@ -51,15 +59,24 @@ __global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, i
       int vy = by + rem / S, vx = bx + rem % S;
       if ((unsigned)vx >= (unsigned)g.nx || (unsigned)vy >= (unsigned)g.ny || (unsigned)vz >= (unsigned)g.nz) continue;
       float d2 = vox_center_d2(g, vx, vy, vz, p);
-      if (d2 > g.rc2) continue;
+      if (d2 > g.rc2) continue;                                                        // (1)
       size_t v = ((size_t)vz * g.ny + vy) * g.nx + vx;
       if (PASS == 0) {
-        atomicMin(&dnn2[v], __float_as_uint(d2));
+        atomicMin(&near[v], ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)i);
       } else {
-        float lim = fminf(sqrtf(__uint_as_float(dnn2[v])) + g.h2x, g.rc);
-        if (d2 <= lim * lim) {
-          unsigned int slot = atomicAdd(&cnt[v], 1u);
-          if (PASS == 2) cand[(size_t)off[v] + slot] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+        const unsigned long long nr = near[v];
+        const float dc2 = __uint_as_float((unsigned int)(nr >> 32));
+        const float lim = sqrtf(dc2) + g.h2x;
+        if (d2 > lim * lim) continue;                                                  // (2)
+        const float4 ms = pw[(unsigned int)nr];
+        const float l1 = fabsf(p.x - ms.x) + fabsf(p.y - ms.y) + fabsf(p.z - ms.z);
+        // (3), with head room for the rounding of d2/dc2 and of the query's voxel assignment at the faces
+        if (d2 - dc2 > g.e_dom * l1 + 8e-6f * d2 + 1e-12f) continue;
+        unsigned int slot = atomicAdd(&cnt[v], 1u);
+        if (PASS == 2) {
+          const unsigned int at = off[v] + slot;
+          if (at < cap) cand[at] = make_float4(p.x, p.y, p.z, __int_as_float(i));
+          else *overflow = 1u;
         }
       }
     }
@@ -68,12 +85,15 @@ __global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, i
 
 // writes cell[v] = (offset,count) and orders each list by point index (deterministic ties)
 __global__ void grid_finalize_kernel(size_t n_vox, const unsigned int *__restrict__ off, const unsigned int *__restrict__ cnt,
-                                     uint2 *__restrict__ cell, float4 *__restrict__ cand, unsigned int *__restrict__ max_list) {
+                                     uint2 *__restrict__ cell, float4 *__restrict__ cand, unsigned int cap,
+                                     unsigned int *__restrict__ max_list) {
   size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   unsigned int c = 0;
   if (v < n_vox) {
     c = cnt[v];
     unsigned int o = off[v];
+    if (o >= cap) c = 0; else if (o + c > cap) c = cap - o;  // (overflow is flagged by the fill pass)
+    if (v == n_vox - 1) { max_list[1] = off[v] + cnt[v]; }   // total entries, for the statistics
     cell[v] = make_uint2(o, c);
     float4 *l = cand + o;
     for (unsigned int a = 1; a < c; ++a) {
@@ -87,12 +107,6 @@ __global__ void grid_finalize_kernel(size_t n_vox, const unsigned int *__restric
   // block max -> one atomic
   for (int o2 = 16; o2 > 0; o2 >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o2));
   if ((threadIdx.x & 31) == 0 && c) atomicMax(max_list, c);
-}
-
-__global__ void fill_u32_kernel(unsigned int *p, size_t n, unsigned int v) {
-  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = v;
 }
 
 __global__ void nn_query_kernel(NNGridDev g, const float *__restrict__ q, int nq, int32_t *__restrict__ idx, float *__restrict__ d2) {
@@ -111,6 +125,7 @@ void hop_free_nn_grid(NNGridHost *g) {
   if (!g) return;
   cudaFree(g->d_cell);
   cudaFree(g->d_cand);
+  cudaFree(g->d_info);
   delete g;
 }
 
@@ -142,62 +157,81 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
   const float h = 0.5f * std::sqrt(3.f) * e * 1.002f + 1e-7f;  // half diagonal, with slack for rounding at voxel faces
   const float R = radius * 1.0005f + 1e-7f;
   g.rc = R + h; g.rc2 = g.rc * g.rc; g.h2x = 2.f * h;
+  g.e_dom = e * 1.004f + 2e-7f;
   g.K = (int)std::ceil(g.rc / e) + 1;
   const int64_t n_vox = (int64_t)g.nx * g.ny * g.nz;
 
-  // aux arrays in scratch: dnn2 | cnt | off | total | maxlist | cub temp
+  // aux arrays in scratch: near (u64) | cnt | off | cub temp
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, (unsigned int *)nullptr, (unsigned int *)nullptr, (int)n_vox, ctx->stream);
-  size_t aux = sizeof(unsigned int) * (size_t)n_vox;
-  size_t need = 3 * aux + 256 + cub_bytes + 256;
+  size_t aux = (sizeof(unsigned int) * (size_t)n_vox + 255) / 256 * 256;
+  size_t need = 4 * aux + cub_bytes + 256;
   char *base = (char *)ctx->ensure_scratch(need);
   if (!base) { ctx->err = "hop_build_nn_grid: scratch allocation failed"; if (!*out) delete G; return HOP_ENOMEM; }
-  unsigned int *d_dnn2 = (unsigned int *)base, *d_cnt = (unsigned int *)(base + aux), *d_off = (unsigned int *)(base + 2 * aux);
-  unsigned int *d_small = (unsigned int *)(base + 3 * aux);  // [0] = max list
-  void *d_cub = base + 3 * aux + 256;
+  unsigned long long *d_near = (unsigned long long *)base;
+  unsigned int *d_cnt = (unsigned int *)(base + 2 * aux), *d_off = (unsigned int *)(base + 3 * aux);
+  void *d_cub = base + 4 * aux;
 
+  if (!G->d_info) HOP_CUDA(ctx, cudaMalloc(&G->d_info, 4 * sizeof(unsigned int)));  // [0] max list [1] entries [2] overflow
   if (G->cap_vox < n_vox) {
     cudaFree(G->d_cell); G->d_cell = nullptr;
     HOP_CUDA(ctx, cudaMalloc(&G->d_cell, sizeof(uint2) * (size_t)n_vox));
     G->cap_vox = n_vox;
   }
-  const int fill_blocks = (int)std::min<int64_t>((n_vox + 255) / 256, 148 * 16);
-  fill_u32_kernel<<<fill_blocks, 256, 0, ctx->stream>>>(d_dnn2, (size_t)n_vox, 0x7f800000u);
+  HOP_CUDA(ctx, cudaMemsetAsync(d_near, 0xff, sizeof(unsigned long long) * (size_t)n_vox, ctx->stream));
   HOP_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, aux, ctx->stream));
-  HOP_CUDA(ctx, cudaMemsetAsync(d_small, 0, 256, ctx->stream));
+  HOP_CUDA(ctx, cudaMemsetAsync(G->d_info, 0, 4 * sizeof(unsigned int), ctx->stream));
   const int S3 = (2 * g.K + 1) * (2 * g.K + 1) * (2 * g.K + 1);
   const int threads = S3 >= 1024 ? 256 : (S3 >= 256 ? 128 : 64);
   const int blocks = cloud->n;
-  grid_scatter_kernel<0><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_dnn2, d_cnt, d_off, nullptr);
-  grid_scatter_kernel<1><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_dnn2, d_cnt, d_off, nullptr);
+  grid_scatter_kernel<0><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_near, d_cnt, d_off, nullptr, 0u, G->d_info + 2);
+  grid_scatter_kernel<1><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_near, d_cnt, d_off, nullptr, 0u, G->d_info + 2);
   cub::DeviceScan::ExclusiveSum(d_cub, cub_bytes, d_cnt, d_off, (int)n_vox, ctx->stream);
-  ctx->launches += 5;
-  // total = off[last] + cnt[last]
-  unsigned int tail[2];
-  HOP_CUDA(ctx, cudaMemcpyAsync(&tail[0], d_off + (n_vox - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-  HOP_CUDA(ctx, cudaMemcpyAsync(&tail[1], d_cnt + (n_vox - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  const int64_t total = (int64_t)tail[0] + tail[1];
-  if (G->cap_cand < total || !G->d_cand) {
-    cudaFree(G->d_cand); G->d_cand = nullptr;
-    int64_t cap = std::max<int64_t>(total + total / 4, 1024);
-    HOP_CUDA(ctx, cudaMalloc(&G->d_cand, sizeof(float4) * (size_t)cap));
-    G->cap_cand = cap;
+  ctx->launches += 4;
+
+  // Candidate capacity.  A voxel lists a point only when its centre lies within rc of it, and the cubes of such
+  // voxels fit in a ball of radius rc + h: at most (4/3) pi (rc + h)^3 / e^3 entries per point.  When that bound is
+  // affordable the buffer is sized from it and the build never synchronises with the host (per-frame scene grids);
+  // otherwise (large static model grids, built once) the exact total is read back.
+  const double per_point = 4.18879 * std::pow((double)(g.rc + h) / e, 3.0);
+  const double bound = per_point * cloud->n + 1024.0;
+  int64_t need_cap;
+  if (bound * sizeof(float4) <= 512.0 * 1024 * 1024) {
+    need_cap = (int64_t)bound;
+  } else {
+    unsigned int tail[2];
+    HOP_CUDA(ctx, cudaMemcpyAsync(&tail[0], d_off + (n_vox - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    HOP_CUDA(ctx, cudaMemcpyAsync(&tail[1], d_cnt + (n_vox - 1), sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
+    HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    need_cap = (int64_t)tail[0] + tail[1] + 16;
   }
+  if (G->cap_cand < need_cap || !G->d_cand) {
+    if (G->d_cand) { HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(G->d_cand); G->d_cand = nullptr; }
+    HOP_CUDA(ctx, cudaMalloc(&G->d_cand, sizeof(float4) * (size_t)need_cap));
+    G->cap_cand = need_cap;
+  }
+  const unsigned int cap = (unsigned int)std::min<int64_t>(G->cap_cand, 0xffffffffll);
   HOP_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, aux, ctx->stream));
-  grid_scatter_kernel<2><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_dnn2, d_cnt, d_off, G->d_cand);
-  grid_finalize_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, ctx->stream>>>((size_t)n_vox, d_off, d_cnt, G->d_cell, G->d_cand, d_small);
+  grid_scatter_kernel<2><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_near, d_cnt, d_off, G->d_cand, cap, G->d_info + 2);
+  grid_finalize_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, ctx->stream>>>((size_t)n_vox, d_off, d_cnt, G->d_cell, G->d_cand, cap, G->d_info);
   ctx->launches += 2;
-  unsigned int max_list = 0;
-  HOP_CUDA(ctx, cudaMemcpyAsync(&max_list, d_small, sizeof(unsigned int), cudaMemcpyDeviceToHost, ctx->stream));
-  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   HOP_CUDA(ctx, cudaGetLastError());
 
-  G->radius = radius; G->voxel = e; G->n_vox = n_vox; G->n_cand = total; G->max_list = (int)max_list;
+  G->radius = radius; G->voxel = e; G->n_vox = n_vox; G->n_cand = -1; G->max_list = -1;  // statistics are read lazily
   G->dev.ox = g.ox; G->dev.oy = g.oy; G->dev.oz = g.oz; G->dev.inv_e = 1.f / e;
   G->dev.nx = g.nx; G->dev.ny = g.ny; G->dev.nz = g.nz; G->dev.radius = radius;
   G->dev.cell = G->d_cell; G->dev.cand = G->d_cand;
   *out = G;
+  return HOP_OK;
+}
+
+// device-side statistics of the last build (synchronises)
+static int grid_fetch_stats(hop_ctx *ctx, NNGridHost *G) {
+  unsigned int info[4] = {0, 0, 0, 0};
+  HOP_CUDA(ctx, cudaMemcpyAsync(info, G->d_info, sizeof(info), cudaMemcpyDeviceToHost, ctx->stream));
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  G->max_list = (int)info[0]; G->n_cand = info[1];
+  if (info[2]) { ctx->err = "nn grid: candidate buffer overflow (bound violated)"; return HOP_ENOMEM; }
   return HOP_OK;
 }
 
@@ -230,6 +264,8 @@ extern "C" int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius
   int rc = hop_get_nn_grid(ctx, cloud, radius, voxel, &G);
   if (rc != HOP_OK) return rc;
   if (stats) {
+    rc = grid_fetch_stats(ctx, G);
+    if (rc != HOP_OK) return rc;
     stats[0] = G->n_vox; stats[1] = G->n_cand; stats[2] = G->max_list;
     stats[3] = G->n_vox * (int64_t)sizeof(uint2) + G->n_cand * (int64_t)sizeof(float4);
   }

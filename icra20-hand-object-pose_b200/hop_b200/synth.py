@@ -149,6 +149,25 @@ def pose_error(A, B):
     return dt, np.rad2deg(2.0 * np.arcsin(np.clip(chord / (2.0 * np.sqrt(2.0)), 0.0, 1.0)))
 
 
+SYMMETRY_AXIS = {"cylinder": 2, "tless": 2}  # continuous rotational symmetry about this model axis (through the origin)
+
+
+def pose_error_sym(A, B, name):
+    """pose_error that ignores the rotation about the object's continuous symmetry axis (it is unobservable: the
+    reference folds it away the same way, object_symmetry in config_autodataset.yaml / PoseEstimator.cpp:134-190)."""
+    dt, dr = pose_error(A, B)
+    ax = SYMMETRY_AXIS.get(name)
+    if ax is None:
+        return dt, dr
+    A = np.asarray(A, np.float64).reshape(-1, 4, 4)
+    B = np.asarray(B, np.float64).reshape(-1, 4, 4)
+    za, zb = A[:, :3, ax], B[:, :3, ax]
+    za = za / np.linalg.norm(za, axis=1, keepdims=True)
+    zb = zb / np.linalg.norm(zb, axis=1, keepdims=True)
+    chord = np.linalg.norm(za - zb, axis=1)
+    return dt, np.rad2deg(2.0 * np.arcsin(np.clip(chord / 2.0, 0.0, 1.0)))
+
+
 def workload(name):
     """Named workloads (BASELINE.json configs, concretised in SURVEY.md 8d)."""
     table = {
