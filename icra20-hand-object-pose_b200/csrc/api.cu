@@ -16,6 +16,15 @@ void *hop_ctx::ensure_scratch(size_t bytes) {
   return d_scratch;
 }
 
+void *hop_ctx::ensure_work(size_t bytes) {
+  if (bytes <= work_bytes) return d_work;
+  if (d_work) { cudaStreamSynchronize(stream); cudaFree(d_work); d_work = nullptr; work_bytes = 0; }
+  size_t cap = std::max(bytes + bytes / 8, (size_t)1 << 20);
+  if (cudaMalloc(&d_work, cap) != cudaSuccess) { d_work = nullptr; return nullptr; }
+  work_bytes = cap;
+  return d_work;
+}
+
 void *hop_ctx::ensure_pinned(size_t bytes) {
   if (bytes <= pinned_bytes) return h_pinned;
   if (h_pinned) { cudaStreamSynchronize(stream); cudaFreeHost(h_pinned); h_pinned = nullptr; pinned_bytes = 0; }
@@ -136,6 +145,7 @@ void hop_destroy(hop_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_scratch);
+  cudaFree(ctx->d_work);
   cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_counter);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);

@@ -203,7 +203,9 @@ struct hop_ctx {
   void *d_scratch = nullptr; size_t scratch_bytes = 0;
   void *h_pinned = nullptr; size_t pinned_bytes = 0;
   int *d_counter = nullptr;  // work-queue heads (a few ints)
+  void *d_work = nullptr; size_t work_bytes = 0;  // ICP state + correspondence records / LCP partials
   void *ensure_scratch(size_t bytes);
+  void *ensure_work(size_t bytes);
   void *ensure_pinned(size_t bytes);
 };
 

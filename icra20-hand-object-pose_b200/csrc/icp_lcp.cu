@@ -8,14 +8,18 @@
 //     nearest-neighbour grid never move; the SCENE is carried into the model frame by X = pose^-1 and ICP iterates
 //     on X.  The point-to-plane objective is frame invariant, and the refined pose is simply X_final^-1
 //     ( = T_icp^-1 * pose of PoseEstimator.cpp:267 ).
-//   * One team of TEAM warps owns one hypothesis (TEAM=1: one warp per hypothesis).  All teams of a CTA read the
-//     same scene, which a dedicated producer warp streams through shared memory in 256-point tiles with 1-D bulk
-//     (TMA) copies completed on mbarriers; small scenes stay resident in shared memory across iterations.
-//   * Per iteration every lane accumulates the moments of its correspondences in registers; a warp-shuffle butterfly
-//     reduces them and the small solve runs cooperatively in the warp out of shared memory.  No tensor cores: these
-//     are gather-bound small reductions.
-//   * Hypotheses are pulled from a global atomic queue at iteration boundaries, so converged hypotheses free their
-//     team immediately (ICP stops after 2-4 of the 10 allowed iterations for most hypotheses).
+//   * The work is gather bound (one voxel cell + a short candidate list + one normal per scene point, all L2
+//     resident), so it is laid out FLAT: one thread per (hypothesis, scene point) at full occupancy, instead of a
+//     warp that owns a hypothesis for the whole ICP (which leaves the SMs latency bound at small batch sizes and
+//     pays the slowest hypothesis' tail).  Each ICP iteration is two launches:
+//        icp_correspond_kernel  grid (scene tiles, hypotheses): nearest neighbour + both rejectors, writes one
+//                               32-byte correspondence record per scene point (coalesced, two float4 planes);
+//        icp_solve_kernel       one warp team per hypothesis: streams the records, accumulates the moments of the
+//                               point-to-plane objective in registers, warp-shuffle reduction, cooperative small
+//                               solve, PCL's convergence rule, state update.
+//     Converged hypotheses retire at once: their tiles exit at the first instruction of later iterations.
+//   * K5 is one flat launch (thread per hypothesis x scene point) + a fixed-order reduction of the tile partials.
+//   * No tensor cores: these are gathers and small reductions, not dense contractions.
 #include <cfloat>
 #include <cmath>
 
@@ -23,44 +27,14 @@
 
 namespace {
 
-constexpr int TILE = HOP_TILE_PTS;
-constexpr int TILE_BYTES = TILE * 16;  // per stream (positions / normals)
-
-// ------------------------------------------------------------------------------------------------------------
-// shared-memory carve-up
-// ------------------------------------------------------------------------------------------------------------
-struct SmemLayout {
-  float4 *tileP, *tileN;
-  uint64_t *full, *empty;
-  int *hyp;      // [2][NT]
-  float *part;   // [NW][NACC_PAD]   per-warp reduced sums
-  float *work;   // [NW][WORK]       per-warp solver workspace
-};
-
-template <int NW, int NT, int NACC_PAD, int WORK>
-__device__ __forceinline__ SmemLayout carve(unsigned char *smem, int stages) {
-  SmemLayout L;
-  L.tileP = reinterpret_cast<float4 *>(smem);
-  L.tileN = L.tileP + (size_t)stages * TILE;
-  unsigned char *p = reinterpret_cast<unsigned char *>(L.tileN + (size_t)stages * TILE);
-  L.full = reinterpret_cast<uint64_t *>(p); p += sizeof(uint64_t) * stages;
-  L.empty = reinterpret_cast<uint64_t *>(p); p += sizeof(uint64_t) * stages;
-  L.hyp = reinterpret_cast<int *>(p); p += sizeof(int) * 2 * NT;
-  p = reinterpret_cast<unsigned char *>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
-  L.part = reinterpret_cast<float *>(p); p += sizeof(float) * NW * NACC_PAD;
-  L.work = reinterpret_cast<float *>(p);
-  return L;
-}
-static size_t smem_bytes(int stages, int NW, int NT, int NACC_PAD, int WORK) {
-  return (size_t)stages * TILE * 32 + 16 * (size_t)stages + sizeof(int) * 2 * NT + 16 + sizeof(float) * NW * (size_t)(NACC_PAD + WORK);
-}
+constexpr int TILE = HOP_TILE_PTS;  // scene points per CTA of the flat kernels (clouds are padded to a multiple)
 
 // ------------------------------------------------------------------------------------------------------------
 // small dense algebra used by the per-iteration solve (uniform across the warp)
 // ------------------------------------------------------------------------------------------------------------
 // solve (H + lambda*diag(H)) x = -g for symmetric 6x6 H (full storage); returns false when not positive definite
 __device__ __forceinline__ bool chol_solve6(const float *Hs, const float *g, float lambda, float *x) {
-  float L[6][6];
+  float L[6][6], inv[6];  // inv[j] = 1 / L[j][j]  (MUFU.RSQ: no division or square root on the dependent chain)
 #pragma unroll
   for (int i = 0; i < 6; ++i) {
 #pragma unroll
@@ -71,9 +45,10 @@ __device__ __forceinline__ bool chol_solve6(const float *Hs, const float *g, flo
       for (int k = 0; k < j; ++k) s -= L[i][k] * L[j][k];
       if (i == j) {
         if (!(s > 0.f)) return false;
-        L[i][i] = sqrtf(s);
+        inv[i] = rsqrtf(s);
+        L[i][i] = s * inv[i];
       } else {
-        L[i][j] = s / L[j][j];
+        L[i][j] = s * inv[j];
       }
     }
   }
@@ -83,14 +58,14 @@ __device__ __forceinline__ bool chol_solve6(const float *Hs, const float *g, flo
     float s = -g[i];
 #pragma unroll
     for (int k = 0; k < i; ++k) s -= L[i][k] * y[k];
-    y[i] = s / L[i][i];
+    y[i] = s * inv[i];
   }
 #pragma unroll
   for (int i = 5; i >= 0; --i) {
     float s = y[i];
 #pragma unroll
     for (int k = i + 1; k < 6; ++k) s -= L[k][i] * x[k];
-    x[i] = s / L[i][i];
+    x[i] = s * inv[i];
   }
   return true;
 }
@@ -125,13 +100,13 @@ template <> struct Acc<0> {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) a[k] = 0.f;
   }
-  __device__ __forceinline__ void add(float3 p, float3 m, float3 n, float d2) {
+  __device__ __forceinline__ void add(float3 p, float3 n, float c, float d2) {
     float v[13];
     v[0] = n.x * p.x; v[1] = n.x * p.y; v[2] = n.x * p.z;
     v[3] = n.y * p.x; v[4] = n.y * p.y; v[5] = n.y * p.z;
     v[6] = n.z * p.x; v[7] = n.z * p.y; v[8] = n.z * p.z;
     v[9] = n.x; v[10] = n.y; v[11] = n.z;
-    v[12] = n.x * (p.x - m.x) + n.y * (p.y - m.y) + n.z * (p.z - m.z);
+    v[12] = c;
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 13; ++i)
@@ -150,11 +125,10 @@ template <> struct Acc<1> {
 #pragma unroll
     for (int k = 0; k < NACC; ++k) a[k] = 0.f;
   }
-  __device__ __forceinline__ void add(float3 p, float3 m, float3 n, float d2) {
+  __device__ __forceinline__ void add(float3 p, float3 n, float c, float d2) {
     float J[6];
     J[0] = p.y * n.z - p.z * n.y; J[1] = p.z * n.x - p.x * n.z; J[2] = p.x * n.y - p.y * n.x;
     J[3] = n.x; J[4] = n.y; J[5] = n.z;
-    float c = n.x * (p.x - m.x) + n.y * (p.y - m.y) + n.z * (p.z - m.z);
     int k = 0;
 #pragma unroll
     for (int i = 0; i < 6; ++i)
@@ -169,7 +143,7 @@ template <> struct Acc<1> {
 };
 
 constexpr int NACC_PAD = 96;
-constexpr int WORK = 512;  // per warp: [0,416) solver (A 169, y, gy, J 78, B 78, H 36, g 6)  [416,512) team totals
+constexpr int WORK = 96;   // per warp: team totals
 
 __device__ __forceinline__ int tri13(int i, int j) {  // index of (i,j), i<=j, in the row-major upper triangle
   return i * 13 - (i * (i - 1)) / 2 + (j - i);
@@ -177,78 +151,84 @@ __device__ __forceinline__ int tri13(int i, int j) {  // index of (i,j), i<=j, i
 
 // Exact minimiser of f(dR,dt) = y^T A y, y = [vec(dR - I); dt; 1], by damped Gauss-Newton on SE(3) from the
 // identity, stopping like MINPACK's lmder does under PCL (relative reduction of the sum of squares <= sqrt(eps)).
-// sums: the 91 reduced moments (shared memory, this warp's row).  W: this warp's workspace.  All lanes return the
-// same (R,t).
-__device__ void solve_exact(const float *sums, float *W, int lane, float *R, float *t) {
-  float *A = W;            // 13x13
-  float *y = W + 176;      // 13
-  float *gy = W + 192;     // 13
-  float *Jm = W + 208;     // 13x6 (rows 12.. zero)
-  float *B = W + 288;      // 13x6
-  float *Hm = W + 368;     // 6x6
-  float *gv = W + 404;     // 6
-  for (int e = lane; e < 169; e += 32) {
-    int i = e / 13, j = e % 13;
-    A[e] = sums[i <= j ? tri13(i, j) : tri13(j, i)];
+// sums: the 91 reduced moments (shared memory).  Register resident: lane i < 13 owns row i of A, (R,t) and every
+// small matrix are replicated in all lanes, rows meet through warp shuffles (no shared-memory round trips, no
+// local memory).  All lanes return the same (R,t).
+__device__ __forceinline__ void solve_exact(const float *sums, float *W, int lane, float *R, float *t) {
+  (void)W;
+  const unsigned FULL = 0xffffffffu;
+  float Arow[13];
+  {
+    const int li = lane < 13 ? lane : 12;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) {
+      const int lo = li < j ? li : j, hi = li < j ? j : li;
+      const float v = sums[tri13(lo, hi)];
+      Arow[j] = lane < 13 ? v : 0.f;
+    }
   }
   R[0] = 1.f; R[1] = 0.f; R[2] = 0.f; R[3] = 0.f; R[4] = 1.f; R[5] = 0.f; R[6] = 0.f; R[7] = 0.f; R[8] = 1.f;
   t[0] = t[1] = t[2] = 0.f;
-  __syncwarp();
-  float f = A[168];
+  // H_tt = A[9+c][9+d] never changes
+  float Htt[6];
+  Htt[0] = __shfl_sync(FULL, Arow[9], 9);  Htt[1] = __shfl_sync(FULL, Arow[10], 9); Htt[2] = __shfl_sync(FULL, Arow[11], 9);
+  Htt[3] = __shfl_sync(FULL, Arow[10], 10); Htt[4] = __shfl_sync(FULL, Arow[11], 10); Htt[5] = __shfl_sync(FULL, Arow[11], 11);
+  // gy = A y; at the identity y = e_12, so gy is the last column of A and f = A[12][12]
+  float gy[13];
+#pragma unroll
+  for (int j = 0; j < 13; ++j) gy[j] = __shfl_sync(FULL, Arow[12], j);
+  float f = gy[12];
   float lambda = 0.f;
   const float ftol = 3.4526698e-4f;  // sqrt(FLT_EPSILON)
-  // gy = A y at the identity is the last column of A
-  if (lane < 13) { y[lane] = (lane == 12) ? 1.f : 0.f; gy[lane] = A[13 * lane + 12]; }
-  __syncwarp();
   int rejects = 0;
   for (int inner = 0; inner < 12; ++inner) {
     if (!(f > 0.f)) break;
-    // Jacobian of y w.r.t. (w, tau):  d vec(R)/dw_k = vec(e_k x R(:,j)),  d t/d tau = I
-    for (int e = lane; e < 78; e += 32) {
-      int row = e / 6, k = e % 6;
-      float v = 0.f;
-      if (row < 9) {
-        if (k < 3) {
-          int i = row / 3, j = row % 3;  // entry (i,j) of [e_k]x R : sum_l eps(i,k,l) R(l,j)
-          int l1 = (k + 1) % 3, l2 = (k + 2) % 3;  // e_k x v = (.. ) : (e_k x v)_{l2} = v_{l1}, (e_k x v)_{l1} = -v_{l2}
-          if (i == l2) v = R[3 * l1 + j];
-          else if (i == l1) v = -R[3 * l2 + j];
-        }
-      } else if (row < 12) {
-        v = (k == row - 9 + 3) ? 1.f : 0.f;
-      }
-      Jm[e] = v;
-    }
-    __syncwarp();
-    for (int e = lane; e < 78; e += 32) {
-      int i = e / 6, k = e % 6;
-      float s = 0.f;
+    // Jacobian of y w.r.t. (w, tau): d vec(R)/dw_k = vec([e_k]x R), d t/d tau = I.   B = A J, this lane's row:
+    float B[6];
+    B[0] = B[1] = B[2] = 0.f;
 #pragma unroll
-      for (int m = 0; m < 12; ++m) s = fmaf(A[13 * i + m], Jm[6 * m + k], s);
-      B[e] = s;
+    for (int c = 0; c < 3; ++c) {
+      B[0] += Arow[6 + c] * R[3 + c] - Arow[3 + c] * R[6 + c];   // [e_0]x R : row1 = -R row2, row2 = R row1
+      B[1] += Arow[0 + c] * R[6 + c] - Arow[6 + c] * R[0 + c];   // [e_1]x R : row0 = R row2, row2 = -R row0
+      B[2] += Arow[3 + c] * R[0 + c] - Arow[0 + c] * R[3 + c];   // [e_2]x R : row0 = -R row1, row1 = R row0
     }
-    __syncwarp();
-    for (int e = lane; e < 42; e += 32) {
-      if (e < 36) {
-        int a = e / 6, b = e % 6;
-        float s = 0.f;
-#pragma unroll
-        for (int m = 0; m < 12; ++m) s = fmaf(Jm[6 * m + a], B[6 * m + b], s);
-        Hm[e] = s;
-      } else {
-        int a = e - 36;
-        float s = 0.f;
-#pragma unroll
-        for (int m = 0; m < 12; ++m) s = fmaf(Jm[6 * m + a], gy[m], s);
-        gv[a] = s;
-      }
-    }
-    __syncwarp();
+    B[3] = Arow[9]; B[4] = Arow[10]; B[5] = Arow[11];
+    // H = J^T B (rows 0..11 of J), g = J^T gy
     float Hl[36], gl[6], dx[6];
+    {
+      float Bw[9][3];  // rows 0..8 of the first three columns of B, gathered from their lanes
 #pragma unroll
-    for (int e = 0; e < 36; ++e) Hl[e] = Hm[e];
+      for (int i = 0; i < 9; ++i)
 #pragma unroll
-    for (int e = 0; e < 6; ++e) gl[e] = gv[e];
+        for (int l = 0; l < 3; ++l) Bw[i][l] = __shfl_sync(FULL, B[l], i);
+#pragma unroll
+      for (int l = 0; l < 3; ++l) {
+        float h0 = 0.f, h1 = 0.f, h2 = 0.f;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          h0 += Bw[6 + c][l] * R[3 + c] - Bw[3 + c][l] * R[6 + c];
+          h1 += Bw[0 + c][l] * R[6 + c] - Bw[6 + c][l] * R[0 + c];
+          h2 += Bw[3 + c][l] * R[0 + c] - Bw[0 + c][l] * R[3 + c];
+        }
+        Hl[0 * 6 + l] = h0; Hl[1 * 6 + l] = h1; Hl[2 * 6 + l] = h2;
+      }
+      // H_wt[k][c] = row (9+c) of B, column k (A is symmetric)
+#pragma unroll
+      for (int c = 0; c < 3; ++c)
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const float v = __shfl_sync(FULL, B[k], 9 + c); Hl[k * 6 + 3 + c] = v; Hl[(3 + c) * 6 + k] = v; }
+      Hl[3 * 6 + 3] = Htt[0]; Hl[3 * 6 + 4] = Htt[1]; Hl[3 * 6 + 5] = Htt[2];
+      Hl[4 * 6 + 3] = Htt[1]; Hl[4 * 6 + 4] = Htt[3]; Hl[4 * 6 + 5] = Htt[4];
+      Hl[5 * 6 + 3] = Htt[2]; Hl[5 * 6 + 4] = Htt[4]; Hl[5 * 6 + 5] = Htt[5];
+      gl[0] = gl[1] = gl[2] = 0.f;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        gl[0] += gy[6 + c] * R[3 + c] - gy[3 + c] * R[6 + c];
+        gl[1] += gy[0 + c] * R[6 + c] - gy[6 + c] * R[0 + c];
+        gl[2] += gy[3 + c] * R[0 + c] - gy[0 + c] * R[3 + c];
+      }
+      gl[3] = gy[9]; gl[4] = gy[10]; gl[5] = gy[11];
+    }
     bool ok = chol_solve6(Hl, gl, lambda, dx);
     while (!ok && rejects < 8) {  // rank deficient (e.g. a plane): regularise
       lambda = fmaxf(lambda * 10.f, 1e-6f);
@@ -264,38 +244,34 @@ __device__ void solve_exact(const float *sums, float *W, int lane, float *R, flo
 #pragma unroll
       for (int j = 0; j < 3; ++j) Rn[3 * i + j] = dR[3 * i] * R[j] + dR[3 * i + 1] * R[3 + j] + dR[3 * i + 2] * R[6 + j];
     tn[0] = t[0] + dx[3]; tn[1] = t[1] + dx[4]; tn[2] = t[2] + dx[5];
-    __syncwarp();
-    if (lane < 13) {
-      float v;
-      if (lane < 9) v = Rn[lane] - ((lane == 0 || lane == 4 || lane == 8) ? 1.f : 0.f);
-      else if (lane < 12) v = tn[lane - 9];
-      else v = 1.f;
-      y[lane] = v;
-    }
-    __syncwarp();
-    float gi = 0.f, yi = 0.f;
-    if (lane < 13) {
+    float yn[13];
 #pragma unroll
-      for (int m = 0; m < 13; ++m) gi = fmaf(A[13 * lane + m], y[m], gi);
-      yi = y[lane];
-    }
-    float fn = warp_sum(gi * yi);
-    if (fn < f) {
-      __syncwarp();
-      if (lane < 13) gy[lane] = gi;
+    for (int e = 0; e < 9; ++e) yn[e] = Rn[e] - ((e % 4 == 0) ? 1.f : 0.f);
+    yn[9] = tn[0]; yn[10] = tn[1]; yn[11] = tn[2]; yn[12] = 1.f;
+    float gi = 0.f;
+#pragma unroll
+    for (int m = 0; m < 13; ++m) gi = fmaf(Arow[m], yn[m], gi);
+    float gn[13];
+    float fn = 0.f;
+#pragma unroll
+    for (int j = 0; j < 13; ++j) { gn[j] = __shfl_sync(FULL, gi, j); fn = fmaf(gn[j], yn[j], fn); }
+    const float rel = (f - fn) / f;
+    const bool accepted = fn < f;
+    if (accepted) {
+#pragma unroll
+      for (int j = 0; j < 13; ++j) gy[j] = gn[j];
 #pragma unroll
       for (int e = 0; e < 9; ++e) R[e] = Rn[e];
       t[0] = tn[0]; t[1] = tn[1]; t[2] = tn[2];
-      float rel = (f - fn) / f;
       f = fn;
       lambda *= 0.1f;
       if (lambda < 1e-7f) lambda = 0.f;
-      __syncwarp();
-      if (rel <= ftol) break;
-    } else {
+    }
+    // lmder's test: |actual reduction| <= ftol (a step that no longer changes the sum of squares, up or down, ends it)
+    if (fabsf(rel) <= ftol) break;
+    if (!accepted) {
       if (++rejects > 8) break;
       lambda = fmaxf(lambda * 10.f, 1e-4f);
-      __syncwarp();
     }
   }
 }
@@ -318,196 +294,229 @@ __device__ void solve_gn(const float *sums, float *R, float *t) {
   t[0] = dx[3]; t[1] = dx[4]; t[2] = dx[5];
 }
 
-struct IcpArgs {
+
+// ------------------------------------------------------------------------------------------------------------
+// per-hypothesis ICP state (global memory, 128 bytes)
+// ------------------------------------------------------------------------------------------------------------
+struct __align__(16) IcpState {
+  float X[12];       // scene -> model frame (row-major R | t), the iterate
+  float inc[12];     // previous increment (PCL keeps transformation_ when LM early-returns)
+  double prev_mse;
+  int iters;
+  int status;        // 0 active, 1 finished + converged, 2 finished, not converged
+  int pad[2];
+};
+static_assert(sizeof(IcpState) == 128, "IcpState layout");
+
+__device__ __forceinline__ Rigid state_load(const float *x) {
+  Rigid T;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) T.r[e] = __ldg(x + e);
+  T.t[0] = __ldg(x + 9); T.t[1] = __ldg(x + 10); T.t[2] = __ldg(x + 11);
+  return T;
+}
+
+// state of every hypothesis of the batch + the batch's first active list (all of them) and iteration counters
+__global__ void icp_init_kernel(const float *__restrict__ poses, int H, IcpState *__restrict__ st, int *__restrict__ list0,
+                                int *__restrict__ counters, int n_counters) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h < n_counters) counters[h] = h == 0 ? H : 0;
+  if (h >= H) return;
+  Rigid P = rigid_load_colmajor(poses + 16 * (size_t)h);
+  Rigid X = rigid_inverse(P);
+  IcpState s;
+#pragma unroll
+  for (int e = 0; e < 9; ++e) { s.X[e] = X.r[e]; s.inc[e] = (e % 4 == 0) ? 1.f : 0.f; }
+#pragma unroll
+  for (int e = 0; e < 3; ++e) { s.X[9 + e] = X.t[e]; s.inc[9 + e] = 0.f; }
+  s.prev_mse = DBL_MAX; s.iters = 0; s.status = 0; s.pad[0] = s.pad[1] = 0;
+  st[h] = s;
+  list0[h] = h;
+}
+
+struct CorrArgs {
   CloudDev scene;
   const float4 *model_nv;
   NNGridDev grid;
-  float *poses;      // H x 16, in/out
-  int H;
-  int max_iter;
-  float cos_thr;     // smallest float whose double value exceeds cos(angle)
+  const IcpState *state;   // already offset to the batch
+  const int *list;         // active hypotheses of this iteration (batch-local ids)
+  const int *n_active;
+  int n_tiles;
+  float cos_thr;           // smallest float whose double value exceeds cos(angle)
   float max_d2;
-  double abs_mse_eps;
-  int *counter;
-  int32_t *iters_out, *conv_out;
-  int stages;
+  float4 *rec0, *rec1;     // [position in list][n_padded]: (p.xyz, n.(p-m)) and (n.xyz, d^2 | -1 when rejected)
 };
 
-// ------------------------------------------------------------------------------------------------------------
-// K4
-// ------------------------------------------------------------------------------------------------------------
+// K4a: correspondence estimation + rejection.  CorrespondenceEstimation (exact 1-NN, d^2 <= max_dist^2) and
+// CorrespondenceRejectorSurfaceNormal (rotated source normal . target normal > cos(angle)).
+// Persistent CTAs stride over the (active hypothesis, scene tile) work items; one thread per scene point.
+__global__ void __launch_bounds__(TILE) icp_correspond_kernel(CorrArgs a) {
+  const int n_work = __ldg(a.n_active) * a.n_tiles;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pos = w / a.n_tiles, tile = w - pos * a.n_tiles;
+    const IcpState *st = a.state + __ldg(&a.list[pos]);
+    const Rigid X = state_load(st->X);
+    const int i = tile * TILE + threadIdx.x;
+    const float4 sp = __ldg(&a.scene.pw[i]);
+    const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
+    float bd; float4 bp;
+    const int j = nn_query(a.grid, p.x, p.y, p.z, bd, bp);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (j >= 0 && bd <= a.max_d2) {
+      const float4 sn = __ldg(&a.scene.nv[i]);
+      const float4 mn = __ldg(&a.model_nv[j]);
+      const float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
+      const float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
+      if (dot >= a.cos_thr) {
+        r0 = make_float4(p.x, p.y, p.z, mn.x * (p.x - bp.x) + mn.y * (p.y - bp.y) + mn.z * (p.z - bp.z));
+        r1 = make_float4(mn.x, mn.y, mn.z, bd);
+      }
+    }
+    const size_t o = (size_t)pos * a.scene.n_padded + i;
+    a.rec0[o] = r0;
+    a.rec1[o] = r1;
+  }
+}
+
+struct SolveArgs {
+  const float4 *rec0, *rec1;
+  int n_padded;
+  IcpState *state;     // offset to the batch
+  float *poses;        // offset to the batch: Hb x 16, written when a hypothesis finishes converged
+  int32_t *iters_out, *conv_out;  // offset to the batch (may be null)
+  const int *list;       // active hypotheses of this iteration
+  const int *n_active;
+  int *next_list;        // survivors are appended here (order is irrelevant to the results)
+  int *next_count;
+  int max_iter;
+  double abs_mse_eps;
+};
+
+// K4b: TransformationEstimationPointToPlane (LM) + DefaultConvergenceCriteria for one hypothesis per warp team.
 template <int NW, int TEAM, int SOLVER>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) icp_refine_kernel(IcpArgs a) {
+__global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
   constexpr int NT = NW / TEAM;
   using AccT = Acc<SOLVER>;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout S = carve<NW, NT, NACC_PAD, WORK>(smem_raw, a.stages);
+  __shared__ __align__(16) float s_part[NW][NACC_PAD];
+  __shared__ __align__(16) float s_work[NW][WORK];
+  __shared__ float s_red[NW][32 * 33];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool producer = warp == NW;
-  const int team = producer ? 0 : warp / TEAM;
-  const int tw = warp % TEAM;
-  const int n_tiles = a.scene.n_padded / TILE;
-  const bool resident = n_tiles <= a.stages;
+  const int team = warp / TEAM, tw = warp % TEAM;
+  const int pos = blockIdx.x * NT + team;
+  const bool active = pos < __ldg(a.n_active);
+  const int h = active ? __ldg(&a.list[pos]) : 0;
+  IcpState *st = a.state + h;
 
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], NW); }
-    mbar_fence_init();
-  }
-  if (!producer && tw == 0 && lane == 0) {
-    int h = atomicAdd(a.counter, 1);
-    S.hyp[team] = h < a.H ? h : -1;
-  }
-  __syncthreads();
-
-  int hyp = -1;
-  Rigid X, inc_prev;
-  int iters = 0;
-  double prev_mse = DBL_MAX;
-  bool fresh = true;
-  uint32_t it = 0;  // running tile counter (ring position / phase)
-  int pass = 0;
-
-  for (;; ++pass) {
-    const int *hq = S.hyp + (pass & 1) * NT;
-    bool any = false;
+  AccT acc;
+  acc.clear();
+  if (active) {
+    const float4 *r0 = a.rec0 + (size_t)pos * a.n_padded;
+    const float4 *r1 = a.rec1 + (size_t)pos * a.n_padded;
+    constexpr int STEP = 32 * TEAM, U = 4;  // n_padded is a multiple of 256 = 8 * 32: whole batches for TEAM <= 2
+    for (int i0 = tw * 32 + lane; i0 < a.n_padded; i0 += STEP * U) {
+      float4 q0[U], q1[U];
 #pragma unroll
-    for (int k = 0; k < NT; ++k) any |= hq[k] >= 0;
-    if (!any) break;
-    const bool load_now = !resident || pass == 0;
-
-    if (producer) {
-      if (lane == 0 && load_now) {
-        for (int tI = 0; tI < n_tiles; ++tI, ++it) {
-          const int slot = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1u;
-          mbar_wait(&S.empty[slot], ph ^ 1u);
-          mbar_arrive_expect_tx(&S.full[slot], 2 * TILE_BYTES);
-          tma_load_1d(S.tileP + (size_t)slot * TILE, a.scene.pw + (size_t)tI * TILE, TILE_BYTES, &S.full[slot]);
-          tma_load_1d(S.tileN + (size_t)slot * TILE, a.scene.nv + (size_t)tI * TILE, TILE_BYTES, &S.full[slot]);
-        }
+      for (int u = 0; u < U; ++u) {  // all loads of the batch in flight before the first use
+        const int i = i0 + u * STEP;
+        const bool in = i < a.n_padded;
+        q1[u] = in ? __ldcs(&r1[i]) : make_float4(0.f, 0.f, 0.f, -1.f);
+        q0[u] = in ? __ldcs(&r0[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+#pragma unroll
+      for (int u = 0; u < U; ++u)
+        if (q1[u].w >= 0.f) acc.add(make_float3(q0[u].x, q0[u].y, q0[u].z), make_float3(q1[u].x, q1[u].y, q1[u].z), q0[u].w, q1[u].w);
+    }
+  }
+  // ---- reduce inside the warp through a padded shared-memory transpose (32 accumulators at a time): lane l ends
+  //      with the totals of accumulators l, 32 + l, 64 + l; then across the team ----
+  float *my_part = s_part[warp];
+  {
+    float *buf = s_red[warp];
+#pragma unroll
+    for (int c = 0; c < (AccT::NACC + 31) / 32; ++c) {
+#pragma unroll
+      for (int k = 0; k < 32; ++k)
+        if (32 * c + k < AccT::NACC) buf[k * 33 + lane] = acc.a[32 * c + k];
       __syncwarp();
-      if (TEAM > 1) __syncthreads();  // (B)
-      __syncthreads();                // (A)
-      continue;
-    }
-
-    // ---- consumer: (re)initialise state when a new hypothesis was assigned ----
-    const int h = hq[team];
-    if (fresh && h >= 0) {
-      Rigid P = rigid_load_colmajor(a.poses + 16 * (size_t)h);
-      X = rigid_inverse(P);
-#pragma unroll
-      for (int e = 0; e < 9; ++e) inc_prev.r[e] = (e % 4 == 0) ? 1.f : 0.f;
-      inc_prev.t[0] = inc_prev.t[1] = inc_prev.t[2] = 0.f;
-      iters = 0; prev_mse = DBL_MAX; fresh = false;
-    }
-    hyp = h;
-
-    AccT acc;
-    acc.clear();
-    for (int tI = 0; tI < n_tiles; ++tI, ++it) {
-      const int slot = resident ? tI : (int)(it % a.stages);
-      if (load_now) mbar_wait(&S.full[slot], resident ? 0u : ((it / a.stages) & 1u));
-      if (hyp >= 0) {
-        const float4 *tp = S.tileP + (size_t)slot * TILE;
-        const float4 *tn = S.tileN + (size_t)slot * TILE;
-#pragma unroll 2
-        for (int i = tw * 32 + lane; i < TILE; i += 32 * TEAM) {
-          float4 sp = tp[i];
-          float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
-          float bd; float4 bp;
-          int j = nn_query(a.grid, p.x, p.y, p.z, bd, bp);
-          if (j >= 0 && bd <= a.max_d2) {
-            float4 sn = tn[i];
-            float4 mn = __ldg(&a.model_nv[j]);
-            float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
-            float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
-            if (dot >= a.cos_thr) acc.add(p, make_float3(bp.x, bp.y, bp.z), make_float3(mn.x, mn.y, mn.z), bd);
-          }
-        }
-      }
-      if (!resident) { __syncwarp(); if (lane == 0) mbar_arrive(&S.empty[slot]); }
-    }
-
-    // ---- reduce: butterfly inside the warp, then across the team through shared memory ----
-    float *my_part = S.part + (size_t)warp * NACC_PAD;
-#pragma unroll
-    for (int k = 0; k < AccT::NACC; ++k) {
-      float v = warp_sum(acc.a[k]);
-      if (lane == (k & 31)) my_part[k] = v;
-    }
-    float *W = S.work + (size_t)warp * WORK;
-    const float *sums = my_part;
-    if (TEAM > 1) {
-      __syncthreads();  // (B) all partial rows of the team are written
-      // every warp of the team forms the same team totals (identical order -> identical bits) in its own workspace
-      float *tot = W + 416;
-      for (int k = lane; k < AccT::NACC; k += 32) {
+      if (32 * c + lane < AccT::NACC) {
         float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < TEAM; ++q) s += S.part[(size_t)(team * TEAM + q) * NACC_PAD + k];
-        tot[k] = s;
+        for (int j = 0; j < 32; ++j) s += buf[lane * 33 + j];
+        my_part[32 * c + lane] = s;
       }
-      sums = tot;
+      __syncwarp();
     }
-    __syncwarp();
-
-    bool finished = false;
-    if (hyp >= 0) {
-      const float cnt_f = sums[AccT::NA + 1];
-      const float sumd2 = sums[AccT::NA];
-      const int cnt = (int)(cnt_f + 0.5f);
-      bool converged = false;
-      if (cnt < 3) {
-        finished = true;  // "Not enough correspondences": hasConverged() false -> identity -> pose unchanged
-      } else {
-        Rigid inc;
-        if (cnt >= 6) {
-          if (SOLVER == 0) solve_exact(sums, W, lane, inc.r, inc.t);
-          else solve_gn(sums, inc.r, inc.t);
-        } else if (cnt >= 4) {
-          // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
+  }
+  float *W = s_work[warp];
+  const float *sums = my_part;
+  if (TEAM > 1) {
+    __syncthreads();
+    if (tw != 0) return;  // the team's first warp sums the partial rows in a fixed order and solves
+    float *tot = W;
+    for (int k = lane; k < AccT::NACC; k += 32) {
+      float s = 0.f;
 #pragma unroll
-          for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
-          inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
-        } else {
-          inc = inc_prev;  // PCL's LM returns early with < 4 correspondences, transformation_ keeps its old value
-        }
-        X = rigid_compose(inc, X);
-        inc_prev = inc;
-        ++iters;
-        if (iters >= a.max_iter) converged = true;
-        else {
-          double cos_angle = 0.5 * ((double)inc.r[0] + (double)inc.r[4] + (double)inc.r[8] - 1.0);
-          double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
-          if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
-          else {
-            double mse = (double)sumd2 / (double)cnt;
-            if (fabs(mse - prev_mse) < a.abs_mse_eps) converged = true;
-            prev_mse = mse;
-          }
-        }
-        finished = converged;
-      }
-      if (finished && tw == 0 && lane == 0) {
-        if (converged) {
-          Rigid P = rigid_inverse(X);
-          rigid_store_colmajor(P, a.poses + 16 * (size_t)hyp);
-        }
-        if (a.iters_out) a.iters_out[hyp] = iters;
-        if (a.conv_out) a.conv_out[hyp] = converged ? 1 : 0;
+      for (int q = 0; q < TEAM; ++q) s += s_part[team * TEAM + q][k];
+      tot[k] = s;
+    }
+    sums = tot;
+  }
+  __syncwarp();
+  if (!active) return;
+
+  const float cnt_f = sums[AccT::NA + 1];
+  const float sumd2 = sums[AccT::NA];
+  const int cnt = (int)(cnt_f + 0.5f);
+  int iters = st->iters;
+  bool converged = false, finished = false;
+  Rigid X = state_load(st->X);
+  if (cnt < 3) {
+    finished = true;  // "Not enough correspondences": hasConverged() false -> identity -> pose unchanged
+  } else {
+    Rigid inc;
+    if (cnt >= 6) {
+      if (SOLVER == 0) solve_exact(sums, W, lane, inc.r, inc.t);
+      else solve_gn(sums, inc.r, inc.t);
+    } else if (cnt >= 4) {
+      // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
+#pragma unroll
+      for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
+      inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
+    } else {
+      inc = state_load(st->inc);  // PCL's LM returns early with < 4 correspondences, transformation_ keeps its old value
+    }
+    X = rigid_compose(inc, X);
+    ++iters;
+    double mse = st->prev_mse;
+    if (iters >= a.max_iter) converged = true;
+    else {
+      double cos_angle = 0.5 * ((double)inc.r[0] + (double)inc.r[4] + (double)inc.r[8] - 1.0);
+      double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
+      if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
+      else {
+        mse = (double)sumd2 / (double)cnt;
+        if (fabs(mse - st->prev_mse) < a.abs_mse_eps) converged = true;
       }
     }
-    // next assignment for this team (written to the other half of the double-buffered table)
+    finished = converged;
     if (tw == 0 && lane == 0) {
-      int nxt = hyp;
-      if (hyp < 0) nxt = -1;
-      else if (finished) { int q = atomicAdd(a.counter, 1); nxt = q < a.H ? q : -1; }
-      S.hyp[((pass + 1) & 1) * NT + team] = nxt;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) { st->X[e] = X.r[e]; st->inc[e] = inc.r[e]; }
+#pragma unroll
+      for (int e = 0; e < 3; ++e) { st->X[9 + e] = X.t[e]; st->inc[9 + e] = inc.t[e]; }
+      st->prev_mse = mse;
+      st->iters = iters;
     }
-    if (finished) fresh = true;
-    __syncthreads();  // (A)
+  }
+  if (!finished && tw == 0 && lane == 0) a.next_list[atomicAdd(a.next_count, 1)] = h;
+  if (finished && tw == 0 && lane == 0) {
+    st->status = converged ? 1 : 2;
+    if (converged) {
+      Rigid P = rigid_inverse(X);
+      rigid_store_colmajor(P, a.poses + 16 * (size_t)h);
+    }
+    if (a.iters_out) a.iters_out[h] = iters;
+    if (a.conv_out) a.conv_out[h] = converged ? 1 : 0;
   }
 }
 
@@ -523,126 +532,67 @@ struct LcpArgs {
   int H;
   float dist, inv_dist, dist2, cos_thr;
   int use_normal, use_dot, use_recip, use_weights;
-  int *counter;
+  float *partial;    // [H][n_tiles]
   float *scores;
-  int stages;
 };
 
-template <int NW, int TEAM>
-__global__ void __launch_bounds__((NW + 1) * 32, 1) lcp_score_kernel(LcpArgs a) {
-  constexpr int NT = NW / TEAM;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  SmemLayout S = carve<NW, NT, 8, 8>(smem_raw, a.stages);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const bool producer = warp == NW;
-  const int team = producer ? 0 : warp / TEAM;
-  const int tw = warp % TEAM;
-  const int n_tiles = a.scene.n_padded / TILE;
-  const bool resident = n_tiles <= a.stages;
-
-  if (threadIdx.x == 0) {
-    for (int s = 0; s < a.stages; ++s) { mbar_init(&S.full[s], 1); mbar_init(&S.empty[s], NW); }
-    mbar_fence_init();
+// one thread per (hypothesis, scene point); the tile's sum goes to partial[h][tile]
+__global__ void __launch_bounds__(TILE) lcp_score_kernel(LcpArgs a) {
+  __shared__ float s_w[TILE / 32];
+  const int h = blockIdx.y;
+  const int i = blockIdx.x * TILE + threadIdx.x;
+  const Rigid T = rigid_load_colmajor(a.poses + 16 * (size_t)h);
+  const Rigid Ti = rigid_inverse(T);
+  const float4 sp = __ldg(&a.scene.pw[i]);
+  const float3 p = rigid_apply(Ti, sp.x, sp.y, sp.z);   // scene point in the model frame
+  float score = 0.f;
+  float bd; float4 bp;
+  const int j = nn_query(a.mgrid, p.x, p.y, p.z, bd, bp);
+  if (j >= 0 && bd < a.dist2) {                         // Utils.cpp:388 (strict)
+    const float w = a.use_weights ? sp.w : 1.f;
+    const float4 mn = __ldg(&a.model_nv[j]);
+    // transformed model normal, normalised (rotation keeps the norm: use the stored 1/|n|)
+    const float3 mr = rigid_rotate(T, mn.x * mn.w, mn.y * mn.w, mn.z * mn.w);
+    if (!a.use_normal) score += w;
+    else {
+      const float4 sn = __ldg(&a.scene.nv[i]);
+      const float dot = (sn.x * mr.x + sn.y * mr.y + sn.z * mr.z) * sn.w;
+      if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(bd) * a.inv_dist) * w : w;
+    }
+    if (a.use_recip) {
+      // nearest scene point of the (transformed) model neighbour; it lies within `dist` because scene point i
+      // itself does, so the radius-limited scene grid is exact here
+      const float3 q = rigid_apply(T, bp.x, bp.y, bp.z);
+      float ed; float4 ep;
+      const int k = nn_query(a.sgrid, q.x, q.y, q.z, ed, ep);
+      if (k >= 0) {
+        if (!a.use_normal) score += w;
+        else {
+          const float4 s2 = __ldg(&a.scene.nv[k]);
+          const float dot = (s2.x * mr.x + s2.y * mr.y + s2.z * mr.z) * s2.w;
+          if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(ed) * a.inv_dist) * w : w;
+        }
+      }
+    }
   }
-  if (!producer && tw == 0 && lane == 0) {
-    int h = atomicAdd(a.counter, 1);
-    S.hyp[team] = h < a.H ? h : -1;
-  }
+  score = warp_sum(score);
+  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = score;
   __syncthreads();
-
-  uint32_t it = 0;
-  for (int pass = 0;; ++pass) {
-    const int *hq = S.hyp + (pass & 1) * NT;
-    bool any = false;
+  if (threadIdx.x == 0) {
+    float s = 0.f;
 #pragma unroll
-    for (int k = 0; k < NT; ++k) any |= hq[k] >= 0;
-    if (!any) break;
-    const bool load_now = !resident || pass == 0;
-    if (producer) {
-      if (lane == 0 && load_now) {
-        for (int tI = 0; tI < n_tiles; ++tI, ++it) {
-          const int slot = it % a.stages;
-          const uint32_t ph = (it / a.stages) & 1u;
-          mbar_wait(&S.empty[slot], ph ^ 1u);
-          mbar_arrive_expect_tx(&S.full[slot], 2 * TILE_BYTES);
-          tma_load_1d(S.tileP + (size_t)slot * TILE, a.scene.pw + (size_t)tI * TILE, TILE_BYTES, &S.full[slot]);
-          tma_load_1d(S.tileN + (size_t)slot * TILE, a.scene.nv + (size_t)tI * TILE, TILE_BYTES, &S.full[slot]);
-        }
-      }
-      __syncwarp();
-      if (TEAM > 1) __syncthreads();
-      __syncthreads();
-      continue;
-    }
-    const int hyp = hq[team];
-    Rigid T, Ti;
-    if (hyp >= 0) { T = rigid_load_colmajor(a.poses + 16 * (size_t)hyp); Ti = rigid_inverse(T); }
-    float score = 0.f;
-    for (int tI = 0; tI < n_tiles; ++tI, ++it) {
-      const int slot = resident ? tI : (int)(it % a.stages);
-      if (load_now) mbar_wait(&S.full[slot], resident ? 0u : ((it / a.stages) & 1u));
-      if (hyp >= 0) {
-        const float4 *tp = S.tileP + (size_t)slot * TILE;
-        const float4 *tn = S.tileN + (size_t)slot * TILE;
-#pragma unroll 2
-        for (int i = tw * 32 + lane; i < TILE; i += 32 * TEAM) {
-          float4 sp = tp[i];
-          float3 p = rigid_apply(Ti, sp.x, sp.y, sp.z);   // scene point in the model frame
-          float bd; float4 bp;
-          int j = nn_query(a.mgrid, p.x, p.y, p.z, bd, bp);
-          if (j >= 0 && bd < a.dist2) {                    // Utils.cpp:388 (strict)
-            const float w = a.use_weights ? sp.w : 1.f;
-            float4 mn = __ldg(&a.model_nv[j]);
-            // transformed model normal, normalised (rotation keeps the norm: use the stored 1/|n|)
-            float3 mr = rigid_rotate(T, mn.x * mn.w, mn.y * mn.w, mn.z * mn.w);
-            if (!a.use_normal) score += w;
-            else {
-              float4 sn = tn[i];
-              float dot = (sn.x * mr.x + sn.y * mr.y + sn.z * mr.z) * sn.w;
-              if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(bd) * a.inv_dist) * w : w;
-            }
-            if (a.use_recip) {
-              // nearest scene point of the (transformed) model neighbour; it lies within `dist` because scene
-              // point i itself does, so the radius-limited scene grid is exact here
-              float3 q = rigid_apply(T, bp.x, bp.y, bp.z);
-              float ed; float4 ep;
-              int k = nn_query(a.sgrid, q.x, q.y, q.z, ed, ep);
-              if (k >= 0) {
-                if (!a.use_normal) score += w;
-                else {
-                  float4 s2 = __ldg(&a.scene.nv[k]);
-                  float dot = (s2.x * mr.x + s2.y * mr.y + s2.z * mr.z) * s2.w;
-                  if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(ed) * a.inv_dist) * w : w;
-                }
-              }
-            }
-          }
-        }
-      }
-      if (!resident) { __syncwarp(); if (lane == 0) mbar_arrive(&S.empty[slot]); }
-    }
-    score = warp_sum(score);
-    if (TEAM > 1) {
-      if (lane == 0) S.part[warp * 8] = score;
-      __syncthreads();
-      if (tw == 0 && lane == 0) {
-        float s = 0.f;
-#pragma unroll
-        for (int q = 0; q < TEAM; ++q) s += S.part[(team * TEAM + q) * 8];
-        score = s;
-      }
-    }
-    if (tw == 0 && lane == 0) {
-      int nxt = -1;
-      if (hyp >= 0) {
-        a.scores[hyp] = score;
-        int q = atomicAdd(a.counter, 1);
-        nxt = q < a.H ? q : -1;
-      }
-      S.hyp[((pass + 1) & 1) * NT + team] = nxt;
-    }
-    __syncthreads();
+    for (int w = 0; w < TILE / 32; ++w) s += s_w[w];
+    a.partial[(size_t)h * gridDim.x + blockIdx.x] = s;
   }
+}
+
+// fixed-order sum of the tile partials (deterministic bits run to run)
+__global__ void lcp_reduce_kernel(const float *__restrict__ partial, int n_tiles, int H, float *__restrict__ scores) {
+  int h = blockIdx.x * blockDim.x + threadIdx.x;
+  if (h >= H) return;
+  float s = 0.f;
+  for (int t = 0; t < n_tiles; ++t) s += partial[(size_t)h * n_tiles + t];
+  scores[h] = s;
 }
 
 // smallest float f with (double)f > thr  (PCL compares the float score against a double threshold with '>')
@@ -662,98 +612,93 @@ static int pick_team(int H, int sm_count, int nw, int requested) {
   return team;
 }
 
-static int pick_stages(int n_tiles, size_t fixed_bytes, size_t limit) {
-  // whole scene resident when it fits, else a 4-deep ring
-  size_t avail = limit > fixed_bytes ? limit - fixed_bytes : 0;
-  int max_stages = (int)(avail / (TILE * 32 + 16));
-  if (n_tiles <= max_stages) return n_tiles < 1 ? 1 : n_tiles;
-  return max_stages < 4 ? max_stages : 4;
-}
+constexpr int SOLVE_NW = 8;
 
-template <int NW, int TEAM, int SOLVER>
-static int launch_icp_t(hop_ctx *ctx, IcpArgs &a, int grid) {
-  constexpr int NT = NW / TEAM;
-  const int n_tiles = a.scene.n_padded / TILE;
-  const size_t fixed = smem_bytes(0, NW, NT, NACC_PAD, WORK) + 256;
-  a.stages = pick_stages(n_tiles, fixed, 200 * 1024);
-  if (a.stages < 1) { ctx->err = "icp: no shared memory for tiles"; return HOP_EINVAL; }
-  const size_t smem = smem_bytes(a.stages, NW, NT, NACC_PAD, WORK) + 128;
-  HOP_CUDA(ctx, cudaFuncSetAttribute(icp_refine_kernel<NW, TEAM, SOLVER>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  icp_refine_kernel<NW, TEAM, SOLVER><<<grid, (NW + 1) * 32, smem, ctx->stream>>>(a);
-  ctx->launches += 1;
-  HOP_CUDA(ctx, cudaGetLastError());
-  return HOP_OK;
-}
-
-template <int NW, int TEAM>
-static int launch_lcp_t(hop_ctx *ctx, LcpArgs &a, int grid) {
-  constexpr int NT = NW / TEAM;
-  const int n_tiles = a.scene.n_padded / TILE;
-  const size_t fixed = smem_bytes(0, NW, NT, 8, 8) + 256;
-  a.stages = pick_stages(n_tiles, fixed, 200 * 1024);
-  const size_t smem = smem_bytes(a.stages, NW, NT, 8, 8) + 128;
-  HOP_CUDA(ctx, cudaFuncSetAttribute(lcp_score_kernel<NW, TEAM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  lcp_score_kernel<NW, TEAM><<<grid, (NW + 1) * 32, smem, ctx->stream>>>(a);
-  ctx->launches += 1;
-  HOP_CUDA(ctx, cudaGetLastError());
-  return HOP_OK;
+template <int TEAM>
+static void launch_solve(hop_ctx *ctx, const SolveArgs &s, int Hb, int solver) {
+  constexpr int NT = SOLVE_NW / TEAM;
+  const int grid = (Hb + NT - 1) / NT;
+  if (solver == 1) icp_solve_kernel<SOLVE_NW, TEAM, 1><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
+  else icp_solve_kernel<SOLVE_NW, TEAM, 0><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
 }
 
 }  // namespace
-
-constexpr int ICP_NW = 8;
-constexpr int LCP_NW = 16;
 
 int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, float *d_poses, int H,
                    const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv) {
   if (H <= 0) return HOP_OK;
   if (p.mode != 0) { ctx->err = "hop_icp_refine: mode 1 (point-to-point) not built yet"; return HOP_EINVAL; }
-  IcpArgs a;
-  a.scene = scene; a.model_nv = model.nv; a.grid = grid; a.poses = d_poses; a.H = H;
-  a.max_iter = p.max_iter < 1 ? 1 : p.max_iter;
-  a.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
-  a.max_d2 = p.max_dist * p.max_dist;
-  a.abs_mse_eps = p.abs_mse_eps;
-  a.counter = ctx->d_counter;
-  a.iters_out = d_iters; a.conv_out = d_conv; a.stages = 0;
-  HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-  const int team = pick_team(H, ctx->sm_count, ICP_NW, p.team_warps);
-  const int teams_per_cta = ICP_NW / team;
-  int grid_dim = (H + teams_per_cta - 1) / teams_per_cta;
-  if (grid_dim > ctx->sm_count) grid_dim = ctx->sm_count;
-#define HOP_ICP_CASE(T)                                                                   \
-  case T:                                                                                 \
-    return p.solver == 1 ? launch_icp_t<ICP_NW, T, 1>(ctx, a, grid_dim) : launch_icp_t<ICP_NW, T, 0>(ctx, a, grid_dim);
-  switch (team) {
-    HOP_ICP_CASE(1)
-    HOP_ICP_CASE(2)
-    HOP_ICP_CASE(4)
-    HOP_ICP_CASE(8)
+  const int max_iter = p.max_iter < 1 ? 1 : p.max_iter;
+  const int n_tiles = scene.n_padded / TILE;
+  // hypotheses per batch: bounded by the correspondence-record buffer (32 B per hypothesis x scene point)
+  const size_t rec_per_h = (size_t)scene.n_padded * 32;
+  const size_t rec_budget = (size_t)1 << 30;
+  const int Hb_max = (int)std::min<size_t>((size_t)H, std::max<size_t>(1, rec_budget / rec_per_h));
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t state_bytes = up(sizeof(IcpState) * (size_t)Hb_max), list_bytes = up(sizeof(int) * (size_t)Hb_max);
+  const size_t cnt_bytes = up(sizeof(int) * (size_t)(max_iter + 1));
+  char *base = (char *)ctx->ensure_work(state_bytes + 2 * list_bytes + cnt_bytes + rec_per_h * Hb_max);
+  if (!base) { ctx->err = "hop_icp_refine: work buffer allocation failed"; return HOP_ENOMEM; }
+  IcpState *state = (IcpState *)base;
+  int *lists[2] = {(int *)(base + state_bytes), (int *)(base + state_bytes + list_bytes)};
+  int *counters = (int *)(base + state_bytes + 2 * list_bytes);
+  float4 *rec0 = (float4 *)(base + state_bytes + 2 * list_bytes + cnt_bytes);
+  float4 *rec1 = rec0 + (size_t)Hb_max * scene.n_padded;
+
+  for (int h0 = 0; h0 < H; h0 += Hb_max) {
+    const int Hb = std::min(Hb_max, H - h0);
+    const int n_init = std::max(Hb, max_iter + 1);
+    icp_init_kernel<<<(n_init + 127) / 128, 128, 0, ctx->stream>>>(d_poses + 16 * (size_t)h0, Hb, state, lists[0], counters, max_iter + 1);
+    ctx->launches += 1;
+    CorrArgs c;
+    c.scene = scene; c.model_nv = model.nv; c.grid = grid; c.state = state; c.n_tiles = n_tiles;
+    c.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
+    c.max_d2 = p.max_dist * p.max_dist;
+    c.rec0 = rec0; c.rec1 = rec1;
+    SolveArgs s;
+    s.rec0 = rec0; s.rec1 = rec1; s.n_padded = scene.n_padded; s.state = state; s.poses = d_poses + 16 * (size_t)h0;
+    s.iters_out = d_iters ? d_iters + h0 : nullptr; s.conv_out = d_conv ? d_conv + h0 : nullptr;
+    s.max_iter = max_iter; s.abs_mse_eps = p.abs_mse_eps;
+    const int team = pick_team(Hb, ctx->sm_count, SOLVE_NW, p.team_warps);
+    const int corr_grid = (int)std::min<long>((long)n_tiles * Hb, (long)ctx->sm_count * 16);
+    for (int it = 0; it < max_iter; ++it) {
+      c.list = lists[it & 1]; c.n_active = counters + it;
+      s.list = c.list; s.n_active = c.n_active; s.next_list = lists[(it + 1) & 1]; s.next_count = counters + it + 1;
+      icp_correspond_kernel<<<corr_grid, TILE, 0, ctx->stream>>>(c);
+      switch (team) {
+        case 1: launch_solve<1>(ctx, s, Hb, p.solver); break;
+        case 2: launch_solve<2>(ctx, s, Hb, p.solver); break;
+        case 4: launch_solve<4>(ctx, s, Hb, p.solver); break;
+        default: launch_solve<8>(ctx, s, Hb, p.solver); break;
+      }
+      ctx->launches += 2;
+    }
   }
-#undef HOP_ICP_CASE
-  return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaGetLastError());
+  return HOP_OK;
 }
 
 int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &model_grid,
                    const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
                    float *d_scores) {
   if (H <= 0) return HOP_OK;
+  const int n_tiles = scene.n_padded / TILE;
   LcpArgs a;
-  a.scene = scene; a.model_nv = model.nv; a.mgrid = model_grid; a.sgrid = scene_grid; a.poses = d_poses; a.H = H;
+  a.scene = scene; a.model_nv = model.nv; a.mgrid = model_grid; a.sgrid = scene_grid; a.H = H;
   a.dist = p.dist; a.inv_dist = 1.f / p.dist; a.dist2 = p.dist * p.dist;
   a.cos_thr = (float)cos((double)p.angle_deg / 180.0 * M_PI);
   a.use_normal = p.use_normal; a.use_dot = p.use_dot_score; a.use_recip = p.use_reciprocal; a.use_weights = use_weights;
-  a.counter = ctx->d_counter + 1; a.scores = d_scores; a.stages = 0;
-  HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter + 1, 0, sizeof(int), ctx->stream));
-  const int team = pick_team(H, ctx->sm_count, LCP_NW, p.team_warps);
-  const int teams_per_cta = LCP_NW / team;
-  int grid_dim = (H + teams_per_cta - 1) / teams_per_cta;
-  if (grid_dim > ctx->sm_count) grid_dim = ctx->sm_count;
-  switch (team) {
-    case 1: return launch_lcp_t<LCP_NW, 1>(ctx, a, grid_dim);
-    case 2: return launch_lcp_t<LCP_NW, 2>(ctx, a, grid_dim);
-    case 4: return launch_lcp_t<LCP_NW, 4>(ctx, a, grid_dim);
-    case 8: return launch_lcp_t<LCP_NW, 8>(ctx, a, grid_dim);
+  const int Hb_max = 65535;
+  float *partial = (float *)ctx->ensure_work(sizeof(float) * (size_t)std::min(H, Hb_max) * n_tiles);
+  if (!partial) { ctx->err = "hop_lcp_score: work buffer allocation failed"; return HOP_ENOMEM; }
+  a.partial = partial;
+  for (int h0 = 0; h0 < H; h0 += Hb_max) {
+    const int Hb = std::min(Hb_max, H - h0);
+    a.poses = d_poses + 16 * (size_t)h0; a.scores = d_scores + h0;
+    lcp_score_kernel<<<dim3(n_tiles, Hb), TILE, 0, ctx->stream>>>(a);
+    lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, n_tiles, Hb, d_scores + h0);
+    ctx->launches += 2;
   }
-  return HOP_EINVAL;
+  HOP_CUDA(ctx, cudaGetLastError());
+  return HOP_OK;
 }

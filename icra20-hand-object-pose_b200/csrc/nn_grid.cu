@@ -20,6 +20,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "hop_common.cuh"
 
@@ -83,8 +84,11 @@ __global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, i
   }
 }
 
-// writes cell[v] = (offset,count) and orders each list by point index (deterministic ties)
-__global__ void grid_finalize_kernel(size_t n_vox, const unsigned int *__restrict__ off, const unsigned int *__restrict__ cnt,
+// per voxel: order the list by point index (deterministic ties), drop every entry that another entry of the list
+// DOMINATES on the voxel's cube (condition (3) between any two list members, not only against m*), write
+// cell[v] = (offset, count).  "m' dominates m" is a strict partial order, so every dropped point is dominated by a
+// kept one and can never be the nearest neighbour of a query inside the voxel: the list stays exact.
+__global__ void grid_finalize_kernel(GridGeom g, size_t n_vox, const unsigned int *__restrict__ off, const unsigned int *__restrict__ cnt,
                                      uint2 *__restrict__ cell, float4 *__restrict__ cand, unsigned int cap,
                                      unsigned int *__restrict__ max_list) {
   size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -93,8 +97,6 @@ __global__ void grid_finalize_kernel(size_t n_vox, const unsigned int *__restric
     c = cnt[v];
     unsigned int o = off[v];
     if (o >= cap) c = 0; else if (o + c > cap) c = cap - o;  // (overflow is flagged by the fill pass)
-    if (v == n_vox - 1) { max_list[1] = off[v] + cnt[v]; }   // total entries, for the statistics
-    cell[v] = make_uint2(o, c);
     float4 *l = cand + o;
     for (unsigned int a = 1; a < c; ++a) {
       float4 key = l[a];
@@ -103,10 +105,33 @@ __global__ void grid_finalize_kernel(size_t n_vox, const unsigned int *__restric
       while (b >= 0 && __float_as_int(l[b].w) > ki) { l[b + 1] = l[b]; --b; }
       l[b + 1] = key;
     }
+    if (c > 1) {
+      const int vx = (int)(v % g.nx), vy = (int)((v / g.nx) % g.ny), vz = (int)(v / ((size_t)g.nx * g.ny));
+      unsigned int kept = 0;
+      for (unsigned int a = 0; a < c; ++a) {
+        const float4 m = l[a];
+        const float d2 = vox_center_d2(g, vx, vy, vz, m);
+        bool dominated = false;
+        // members before `kept` were compacted to the front; members from `a` on are still in place: together they
+        // are the whole original list minus entries already dropped (dropping is transitive-safe, see above)
+        for (unsigned int b = 0; b < c && !dominated; ++b) {
+          if (b >= kept && b <= a) { if (b < a) b = a; continue; }
+          const float4 q = l[b];
+          const float e2 = vox_center_d2(g, vx, vy, vz, q);
+          const float l1 = fabsf(m.x - q.x) + fabsf(m.y - q.y) + fabsf(m.z - q.z);
+          dominated = d2 - e2 > g.e_dom * l1 + 8e-6f * d2 + 1e-12f;
+        }
+        if (!dominated) l[kept++] = m;
+      }
+      c = kept;
+    }
+    cell[v] = make_uint2(o, c);
+    if (v == n_vox - 1) { max_list[1] = off[v] + cnt[v]; }   // entries allocated (before the pairwise pruning)
   }
-  // block max -> one atomic
-  for (int o2 = 16; o2 > 0; o2 >>= 1) c = max(c, __shfl_xor_sync(0xffffffffu, c, o2));
-  if ((threadIdx.x & 31) == 0 && c) atomicMax(max_list, c);
+  // block max -> one atomic; entries kept -> one atomic per warp
+  unsigned int mx = c, sum = c;
+  for (int o2 = 16; o2 > 0; o2 >>= 1) { mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o2)); sum += __shfl_xor_sync(0xffffffffu, sum, o2); }
+  if ((threadIdx.x & 31) == 0 && mx) { atomicMax(max_list, mx); atomicAdd(max_list + 3, sum); }
 }
 
 __global__ void nn_query_kernel(NNGridDev g, const float *__restrict__ q, int nq, int32_t *__restrict__ idx, float *__restrict__ d2) {
@@ -135,7 +160,8 @@ static float auto_voxel(const hop_cloud *c, float radius) {
         dz = std::max(c->bbox_max[2] - c->bbox_min[2], 1e-6f);
   float area = dx * dy + dy * dz + dz * dx;  // ~ half the box surface
   float spacing = std::sqrt(area / std::max(c->n, 1));
-  return std::min(std::max(spacing, radius / 12.f), radius * 0.5f);
+  static const float max_frac = getenv("HOP_VOXEL_MAX_FRAC") ? (float)atof(getenv("HOP_VOXEL_MAX_FRAC")) : 0.5f;  // tuning knob
+  return std::min(std::max(spacing, radius / 12.f), radius * max_frac);
 }
 
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
@@ -172,7 +198,7 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
   unsigned int *d_cnt = (unsigned int *)(base + 2 * aux), *d_off = (unsigned int *)(base + 3 * aux);
   void *d_cub = base + 4 * aux;
 
-  if (!G->d_info) HOP_CUDA(ctx, cudaMalloc(&G->d_info, 4 * sizeof(unsigned int)));  // [0] max list [1] entries [2] overflow
+  if (!G->d_info) HOP_CUDA(ctx, cudaMalloc(&G->d_info, 4 * sizeof(unsigned int)));  // [0] max list [1] entries allocated [2] overflow [3] entries kept
   if (G->cap_vox < n_vox) {
     cudaFree(G->d_cell); G->d_cell = nullptr;
     HOP_CUDA(ctx, cudaMalloc(&G->d_cell, sizeof(uint2) * (size_t)n_vox));
@@ -213,7 +239,7 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
   const unsigned int cap = (unsigned int)std::min<int64_t>(G->cap_cand, 0xffffffffll);
   HOP_CUDA(ctx, cudaMemsetAsync(d_cnt, 0, aux, ctx->stream));
   grid_scatter_kernel<2><<<blocks, threads, 0, ctx->stream>>>(g, cloud->d_pw, cloud->n, d_near, d_cnt, d_off, G->d_cand, cap, G->d_info + 2);
-  grid_finalize_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, ctx->stream>>>((size_t)n_vox, d_off, d_cnt, G->d_cell, G->d_cand, cap, G->d_info);
+  grid_finalize_kernel<<<(unsigned)((n_vox + 127) / 128), 128, 0, ctx->stream>>>(g, (size_t)n_vox, d_off, d_cnt, G->d_cell, G->d_cand, cap, G->d_info);
   ctx->launches += 2;
   HOP_CUDA(ctx, cudaGetLastError());
 
@@ -230,7 +256,7 @@ static int grid_fetch_stats(hop_ctx *ctx, NNGridHost *G) {
   unsigned int info[4] = {0, 0, 0, 0};
   HOP_CUDA(ctx, cudaMemcpyAsync(info, G->d_info, sizeof(info), cudaMemcpyDeviceToHost, ctx->stream));
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  G->max_list = (int)info[0]; G->n_cand = info[1];
+  G->max_list = (int)info[0]; G->n_cand = info[3];  // entries kept after the pairwise pruning ([1] = allocated)
   if (info[2]) { ctx->err = "nn grid: candidate buffer overflow (bound violated)"; return HOP_ENOMEM; }
   return HOP_OK;
 }
