@@ -30,6 +30,9 @@ sys.path.insert(0, os.path.join(ROOT, "icra20-hand-object-pose_b200"))
 METRIC = "pose hypotheses/sec (ICP-refined + LCP-scored)"
 UNIT = "hypotheses/s"
 TOPK = 16
+# dram__bytes_read.sum + dram__bytes_write.sum of one icp_correspond_kernel launch (first ICP iteration, C2), from the
+# ncu --set full capture summarised in profiles/ (None until a capture of the current kernel is committed)
+TRAFFIC_BYTES_PER_LAUNCH = None
 N_FRAMES = 4  # distinct synthetic frames cycled through the steps
 
 
@@ -219,7 +222,18 @@ def main():
     t_lcp = np.array([e[1].elapsed_time(e[2]) for e in ev])
     total_ms = float(t_step.sum())
     iters_mean = float(d_iters.float().mean().item())
-    iters_last = d_iters.cpu().numpy().astype(np.int64)
+
+    # ---- per-kernel device time: the same K steps again with libhop's event profiling on (CUDA events recorded on
+    #      the launching stream around every launch of each kernel family; kept out of the `value` timing) ----
+    ctx.profile_enable(True)
+    iters_sum = 0
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)
+        step_value(k % N_FRAMES)
+        torch.cuda.synchronize()
+        iters_sum += int(torch.clamp(d_iters, min=1).sum().item())
+    prof = ctx.profile_read()
+    ctx.profile_enable(False)
 
     # ---- e2e through the host-buffer ABI ----
     e2e_scene = ctx.upload_cloud(frames[0]["xyz"], frames[0]["nrm"], frames[0]["conf"])
@@ -281,11 +295,13 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         value = world * H * args.steps / (total_ms * 1e-3)
         e2e_value = world * H * args.steps / (e2e_ms * 1e-3)
-        # algorithmic bytes of one icp_refine launch: every executed iteration streams the scene and the
-        # model once as 2 x float4 per point; + pose in/out and the two result ints
-        icp_bytes = float(np.maximum(iters_last, 1).sum()) * 32.0 * (ns + nm) + H * (64 + 64 + 8)
+        # Dominant kernel: icp_correspond_kernel (one launch per ICP iteration).  ALGORITHMIC bytes: every
+        # executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B per point.
+        corr_ms, corr_n = prof["icp_correspond"]
+        corr_bytes = float(iters_sum) * 32.0 * (ns + nm)
+        achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
         icp_ms = float(np.mean(t_icp))
-        achieved = icp_bytes / (icp_ms * 1e-3) / 1e9
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -293,14 +309,19 @@ def main():
             "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": 1, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
                        "icp_solver": "exact" if args.solver == 0 else "gauss-newton", "mean_icp_iterations": iters_mean,
                        "nn_grid_icp": g_icp, "nn_grid_lcp": g_lcp,
-                       "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps}},
+                       "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps},
+                       "kernel_ms": kernels},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "icp_refine_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": None,
+            "roofline": {"bound": "hbm", "kernel": "icp_correspond_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": icp_bytes, "kernel_ms": icp_ms},
+                         "algorithmic_bytes_per_launch": corr_bytes / max(corr_n, 1), "kernel_ms_per_launch": corr_ms / max(corr_n, 1),
+                         "launches": int(corr_n),
+                         "note": "algorithmic = 32 B x (N_scene + N_model) per executed ICP iteration per hypothesis (the brute-force "
+                                 "streaming model of SURVEY 8d); the kernel itself gathers from an L2-resident voxel grid, so real DRAM "
+                                 "traffic (`traffic`, ncu) is far below it"},
         }
         if world == 1 and not args.no_cpu_baseline:
             probe_rate, _, thr = cpu_baseline_run(model_np, frames[0], wl, min(8, H))

@@ -16,6 +16,22 @@ void *hop_ctx::ensure_scratch(size_t bytes) {
   return d_scratch;
 }
 
+cudaEvent_t hop_ctx::prof_event() {
+  if (!event_pool.empty()) { cudaEvent_t e = event_pool.back(); event_pool.pop_back(); return e; }
+  cudaEvent_t e = nullptr;
+  cudaEventCreate(&e);
+  return e;
+}
+
+void *hop_ctx::ensure_io(size_t bytes) {
+  if (bytes <= io_bytes) return d_io;
+  if (d_io) { cudaStreamSynchronize(stream); cudaFree(d_io); d_io = nullptr; io_bytes = 0; }
+  size_t cap = std::max(bytes + bytes / 4, (size_t)1 << 20);
+  if (cudaMalloc(&d_io, cap) != cudaSuccess) { d_io = nullptr; return nullptr; }
+  io_bytes = cap;
+  return d_io;
+}
+
 void *hop_ctx::ensure_work(size_t bytes) {
   if (bytes <= work_bytes) return d_work;
   if (d_work) { cudaStreamSynchronize(stream); cudaFree(d_work); d_work = nullptr; work_bytes = 0; }
@@ -146,8 +162,11 @@ void hop_destroy(hop_ctx *ctx) {
   cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_work);
+  cudaFree(ctx->d_io);
   cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_counter);
+  for (ProfSpan &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
+  for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -175,6 +194,35 @@ int hop_sync(hop_ctx *ctx) {
 }
 
 int64_t hop_launch_count(const hop_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+static int profile_collect(hop_ctx *ctx) {
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (ProfSpan &s : ctx->spans) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) { ctx->prof_ms[s.kind] += ms; ctx->prof_n[s.kind] += 1; }
+    ctx->event_pool.push_back(s.a); ctx->event_pool.push_back(s.b);
+  }
+  ctx->spans.clear();
+  return HOP_OK;
+}
+
+int hop_profile_enable(hop_ctx *ctx, int on) {
+  if (!ctx) return HOP_EINVAL;
+  int rc = profile_collect(ctx);
+  if (rc != HOP_OK) return rc;
+  for (int k = 0; k < HOP_PROF_KINDS; ++k) { ctx->prof_ms[k] = 0.0; ctx->prof_n[k] = 0; }
+  ctx->profiling = on != 0;
+  return HOP_OK;
+}
+
+int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans) {
+  if (!ctx || kind < 0 || kind >= HOP_PROF_KINDS) return HOP_EINVAL;
+  int rc = profile_collect(ctx);
+  if (rc != HOP_OK) return rc;
+  if (total_ms) *total_ms = ctx->prof_ms[kind];
+  if (spans) *spans = ctx->prof_n[kind];
+  return HOP_OK;
+}
 
 void hop_default_icp_params(hop_icp_params *p) {
   if (!p) return;
@@ -261,8 +309,8 @@ int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *pose
   if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
   const size_t pb = sizeof(float) * 16 * (size_t)H, ib = sizeof(int32_t) * (size_t)H;
   // device staging for this call: poses | iters | conv   (kept separate from the grid-build scratch)
-  float *d_poses = nullptr;
-  HOP_CUDA(ctx, cudaMallocAsync((void **)&d_poses, pb + 2 * ib, ctx->stream));
+  float *d_poses = (float *)ctx->ensure_io(pb + 2 * ib);
+  if (!d_poses) { ctx->err = "hop_icp_refine: staging allocation failed"; return HOP_ENOMEM; }
   int32_t *d_it = (int32_t *)((char *)d_poses + pb), *d_cv = d_it + H;
   HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses_inout, pb, cudaMemcpyHostToDevice, ctx->stream));
   int rc = hop_icp_refine_dev(ctx, scene, model, d_poses, H, params, d_it, d_cv);
@@ -271,7 +319,6 @@ int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *pose
     if (iters_out) cudaMemcpyAsync(iters_out, d_it, ib, cudaMemcpyDeviceToHost, ctx->stream);
     if (converged_out) cudaMemcpyAsync(converged_out, d_cv, ib, cudaMemcpyDeviceToHost, ctx->stream);
   }
-  cudaFreeAsync(d_poses, ctx->stream);
   if (rc != HOP_OK) return rc;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
@@ -301,13 +348,12 @@ int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float 
   if (!ctx || (H > 0 && (!poses || !scores_out))) return HOP_EINVAL;
   if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
   const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H;
-  float *d_poses = nullptr;
-  HOP_CUDA(ctx, cudaMallocAsync((void **)&d_poses, pb + sb, ctx->stream));
+  float *d_poses = (float *)ctx->ensure_io(pb + sb);
+  if (!d_poses) { ctx->err = "hop_lcp_score: staging allocation failed"; return HOP_ENOMEM; }
   float *d_scores = (float *)((char *)d_poses + pb);
   HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses, pb, cudaMemcpyHostToDevice, ctx->stream));
   int rc = hop_lcp_score_dev(ctx, scene, model, d_poses, H, params, use_weights, d_scores);
   if (rc == HOP_OK) cudaMemcpyAsync(scores_out, d_scores, sb, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaFreeAsync(d_poses, ctx->stream);
   if (rc != HOP_OK) return rc;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
@@ -325,8 +371,8 @@ int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H
   if (!ctx || H < 0 || K < 0 || (K > 0 && !out) || (H > 0 && (!poses || !scores))) return HOP_EINVAL;
   if (K == 0) return HOP_OK;
   const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H, rb = sizeof(hop_pose_rec) * (size_t)K;
-  char *d = nullptr;
-  HOP_CUDA(ctx, cudaMallocAsync((void **)&d, pb + sb + rb + 64, ctx->stream));
+  char *d = (char *)ctx->ensure_io(pb + sb + rb + 64);
+  if (!d) { ctx->err = "hop_select_topk: staging allocation failed"; return HOP_ENOMEM; }
   float *d_poses = (float *)d, *d_scores = (float *)(d + pb);
   hop_pose_rec *d_out = (hop_pose_rec *)(d + ((pb + sb + 15) / 16) * 16);
   if (H > 0) {
@@ -335,7 +381,6 @@ int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H
   }
   int rc = hop_launch_topk(ctx, d_poses, d_scores, H, K, id_offset, frame, d_out);
   if (rc == HOP_OK) cudaMemcpyAsync(out, d_out, rb, cudaMemcpyDeviceToHost, ctx->stream);
-  cudaFreeAsync(d, ctx->stream);
   if (rc != HOP_OK) return rc;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;

@@ -192,8 +192,17 @@ struct hop_cloud {
   CloudDev dev() const { return CloudDev{d_pw, d_nv, n, n_padded}; }
 };
 
+// per-kernel timing with CUDA events on the launching stream (hop_profile_*): bench.py's roofline source
+struct ProfSpan { int kind; cudaEvent_t a, b; };
+
 struct hop_ctx {
   int device = 0;
+  bool profiling = false;
+  std::vector<ProfSpan> spans;
+  std::vector<cudaEvent_t> event_pool;
+  double prof_ms[HOP_PROF_KINDS] = {0};
+  int64_t prof_n[HOP_PROF_KINDS] = {0};
+  cudaEvent_t prof_event();
   int sm_count = 148;
   cudaStream_t stream = nullptr;
   bool own_stream = true;
@@ -205,8 +214,23 @@ struct hop_ctx {
   int *d_counter = nullptr;  // work-queue heads (a few ints)
   void *d_work = nullptr; size_t work_bytes = 0;  // ICP state + correspondence records / LCP partials
   void *ensure_scratch(size_t bytes);
+  void *d_io = nullptr; size_t io_bytes = 0;      // device staging of the host-buffer entry points (poses, scores, ...)
   void *ensure_work(size_t bytes);
+  void *ensure_io(size_t bytes);
   void *ensure_pinned(size_t bytes);
+};
+
+// times everything enqueued on the context's stream during its lifetime as one span of `kind`
+struct ProfScope {
+  hop_ctx *ctx; int idx = -1;
+  ProfScope(hop_ctx *c, int kind) : ctx(c) {
+    if (!c->profiling) return;
+    ProfSpan s{kind, c->prof_event(), c->prof_event()};
+    cudaEventRecord(s.a, c->stream);
+    c->spans.push_back(s);
+    idx = (int)c->spans.size() - 1;
+  }
+  ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->spans[idx].b, ctx->stream); }
 };
 
 #define HOP_CUDA(ctx, call)                                                                            \

@@ -532,45 +532,49 @@ struct LcpArgs {
   int H;
   float dist, inv_dist, dist2, cos_thr;
   int use_normal, use_dot, use_recip, use_weights;
-  float *partial;    // [H][n_tiles]
+  int n_tiles;
+  float *partial;    // [H][splits]
   float *scores;
 };
 
-// one thread per (hypothesis, scene point); the tile's sum goes to partial[h][tile]
+// CTA = (hypothesis, split): one thread per scene point of every `splits`-th tile; the pose algebra is done once per
+// CTA; the CTA's sum goes to partial[h][split]
 __global__ void __launch_bounds__(TILE) lcp_score_kernel(LcpArgs a) {
   __shared__ float s_w[TILE / 32];
   const int h = blockIdx.y;
-  const int i = blockIdx.x * TILE + threadIdx.x;
   const Rigid T = rigid_load_colmajor(a.poses + 16 * (size_t)h);
   const Rigid Ti = rigid_inverse(T);
-  const float4 sp = __ldg(&a.scene.pw[i]);
-  const float3 p = rigid_apply(Ti, sp.x, sp.y, sp.z);   // scene point in the model frame
   float score = 0.f;
-  float bd; float4 bp;
-  const int j = nn_query(a.mgrid, p.x, p.y, p.z, bd, bp);
-  if (j >= 0 && bd < a.dist2) {                         // Utils.cpp:388 (strict)
-    const float w = a.use_weights ? sp.w : 1.f;
-    const float4 mn = __ldg(&a.model_nv[j]);
-    // transformed model normal, normalised (rotation keeps the norm: use the stored 1/|n|)
-    const float3 mr = rigid_rotate(T, mn.x * mn.w, mn.y * mn.w, mn.z * mn.w);
-    if (!a.use_normal) score += w;
-    else {
-      const float4 sn = __ldg(&a.scene.nv[i]);
-      const float dot = (sn.x * mr.x + sn.y * mr.y + sn.z * mr.z) * sn.w;
-      if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(bd) * a.inv_dist) * w : w;
-    }
-    if (a.use_recip) {
-      // nearest scene point of the (transformed) model neighbour; it lies within `dist` because scene point i
-      // itself does, so the radius-limited scene grid is exact here
-      const float3 q = rigid_apply(T, bp.x, bp.y, bp.z);
-      float ed; float4 ep;
-      const int k = nn_query(a.sgrid, q.x, q.y, q.z, ed, ep);
-      if (k >= 0) {
-        if (!a.use_normal) score += w;
-        else {
-          const float4 s2 = __ldg(&a.scene.nv[k]);
-          const float dot = (s2.x * mr.x + s2.y * mr.y + s2.z * mr.z) * s2.w;
-          if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(ed) * a.inv_dist) * w : w;
+  for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    const int i = tile * TILE + threadIdx.x;
+    const float4 sp = __ldg(&a.scene.pw[i]);
+    const float3 p = rigid_apply(Ti, sp.x, sp.y, sp.z);   // scene point in the model frame
+    float bd; float4 bp;
+    const int j = nn_query(a.mgrid, p.x, p.y, p.z, bd, bp);
+    if (j >= 0 && bd < a.dist2) {                         // Utils.cpp:388 (strict)
+      const float w = a.use_weights ? sp.w : 1.f;
+      const float4 mn = __ldg(&a.model_nv[j]);
+      // transformed model normal, normalised (rotation keeps the norm: use the stored 1/|n|)
+      const float3 mr = rigid_rotate(T, mn.x * mn.w, mn.y * mn.w, mn.z * mn.w);
+      if (!a.use_normal) score += w;
+      else {
+        const float4 sn = __ldg(&a.scene.nv[i]);
+        const float dot = (sn.x * mr.x + sn.y * mr.y + sn.z * mr.z) * sn.w;
+        if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(bd) * a.inv_dist) * w : w;
+      }
+      if (a.use_recip) {
+        // nearest scene point of the (transformed) model neighbour; it lies within `dist` because scene point i
+        // itself does, so the radius-limited scene grid is exact here
+        const float3 q = rigid_apply(T, bp.x, bp.y, bp.z);
+        float ed; float4 ep;
+        const int k = nn_query(a.sgrid, q.x, q.y, q.z, ed, ep);
+        if (k >= 0) {
+          if (!a.use_normal) score += w;
+          else {
+            const float4 s2 = __ldg(&a.scene.nv[k]);
+            const float dot = (s2.x * mr.x + s2.y * mr.y + s2.z * mr.z) * s2.w;
+            if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(ed) * a.inv_dist) * w : w;
+          }
         }
       }
     }
@@ -664,7 +668,8 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
     for (int it = 0; it < max_iter; ++it) {
       c.list = lists[it & 1]; c.n_active = counters + it;
       s.list = c.list; s.n_active = c.n_active; s.next_list = lists[(it + 1) & 1]; s.next_count = counters + it + 1;
-      icp_correspond_kernel<<<corr_grid, TILE, 0, ctx->stream>>>(c);
+      { ProfScope ps(ctx, HOP_PROF_ICP_CORRESPOND); icp_correspond_kernel<<<corr_grid, TILE, 0, ctx->stream>>>(c); }
+      ProfScope ps(ctx, HOP_PROF_ICP_SOLVE);
       switch (team) {
         case 1: launch_solve<1>(ctx, s, Hb, p.solver); break;
         case 2: launch_solve<2>(ctx, s, Hb, p.solver); break;
@@ -689,14 +694,19 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
   a.cos_thr = (float)cos((double)p.angle_deg / 180.0 * M_PI);
   a.use_normal = p.use_normal; a.use_dot = p.use_dot_score; a.use_recip = p.use_reciprocal; a.use_weights = use_weights;
   const int Hb_max = 65535;
-  float *partial = (float *)ctx->ensure_work(sizeof(float) * (size_t)std::min(H, Hb_max) * n_tiles);
+  // CTAs per hypothesis: enough to fill the machine when the batch is small, one when it is large
+  int splits = (int)((8L * ctx->sm_count + H - 1) / H);
+  splits = std::max(1, std::min(splits, n_tiles));
+  a.n_tiles = n_tiles;
+  float *partial = (float *)ctx->ensure_work(sizeof(float) * (size_t)std::min(H, Hb_max) * splits);
   if (!partial) { ctx->err = "hop_lcp_score: work buffer allocation failed"; return HOP_ENOMEM; }
   a.partial = partial;
   for (int h0 = 0; h0 < H; h0 += Hb_max) {
     const int Hb = std::min(Hb_max, H - h0);
     a.poses = d_poses + 16 * (size_t)h0; a.scores = d_scores + h0;
-    lcp_score_kernel<<<dim3(n_tiles, Hb), TILE, 0, ctx->stream>>>(a);
-    lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, n_tiles, Hb, d_scores + h0);
+    ProfScope ps(ctx, HOP_PROF_LCP_SCORE);
+    lcp_score_kernel<<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
+    lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, splits, Hb, d_scores + h0);
     ctx->launches += 2;
   }
   HOP_CUDA(ctx, cudaGetLastError());

@@ -160,12 +160,13 @@ static float auto_voxel(const hop_cloud *c, float radius) {
         dz = std::max(c->bbox_max[2] - c->bbox_min[2], 1e-6f);
   float area = dx * dy + dy * dz + dz * dx;  // ~ half the box surface
   float spacing = std::sqrt(area / std::max(c->n, 1));
-  static const float max_frac = getenv("HOP_VOXEL_MAX_FRAC") ? (float)atof(getenv("HOP_VOXEL_MAX_FRAC")) : 0.5f;  // tuning knob
+  static const float max_frac = getenv("HOP_VOXEL_MAX_FRAC") ? (float)atof(getenv("HOP_VOXEL_MAX_FRAC")) : 1.0f;  // tuning knob
   return std::min(std::max(spacing, radius / 12.f), radius * max_frac);
 }
 
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
   if (!cloud || cloud->n <= 0 || !(radius > 0.f)) { ctx->err = "hop_build_nn_grid: empty cloud or bad radius"; return HOP_EINVAL; }
+  ProfScope ps(ctx, HOP_PROF_NN_BUILD);
   NNGridHost *G = *out ? *out : new NNGridHost();
   float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius);
   const int64_t kMaxVox = 48ll << 20;

@@ -71,6 +71,7 @@ int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, i
   // the bitmap lives at the tail of the context's small counter block when it fits, else in scratch
   unsigned int *taken = (unsigned int *)ctx->ensure_scratch(words * sizeof(unsigned int));
   if (!taken) { ctx->err = "topk: scratch allocation failed"; return HOP_ENOMEM; }
+  ProfScope ps(ctx, HOP_PROF_TOPK);
   topk_kernel<<<1, 1024, 0, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);
   ctx->launches += 1;
   HOP_CUDA(ctx, cudaGetLastError());

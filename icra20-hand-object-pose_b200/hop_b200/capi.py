@@ -78,6 +78,8 @@ def load_library():
     L.hop_sync.argtypes = [_vp]
     L.hop_launch_count.argtypes = [_vp]
     L.hop_launch_count.restype = C.c_int64
+    L.hop_profile_enable.argtypes = [_vp, C.c_int]
+    L.hop_profile_read.argtypes = [_vp, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_int64)]
     L.hop_default_icp_params.argtypes = [C.POINTER(IcpParams)]
     L.hop_default_icp_params.restype = None
     L.hop_default_lcp_params.argtypes = [C.POINTER(LcpParams)]
@@ -99,6 +101,8 @@ def load_library():
     L.hop_icp_refine_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
     L.hop_lcp_score.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
     L.hop_lcp_score_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
+    L.hop_verify_lcp.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.hop_verify_lcp_dev.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
     L.hop_select_topk.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
     for name in declared_symbols():
@@ -201,6 +205,20 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6}
+
+    def profile_enable(self, on=True):
+        self._check(self.L.hop_profile_enable(self.h, int(on)))
+
+    def profile_read(self):
+        """{kernel family: (total ms, spans)} measured with CUDA events on the context's stream (synchronises)."""
+        out = {}
+        for name, k in self.PROF_KINDS.items():
+            ms, n = C.c_double(), C.c_int64()
+            self._check(self.L.hop_profile_read(self.h, k, C.byref(ms), C.byref(n)))
+            out[name] = (ms.value, n.value)
+        return out
+
     def malloc(self, nbytes):
         p = _vp()
         self._check(self.L.hop_malloc(self.h, nbytes, C.byref(p)))
@@ -271,6 +289,21 @@ class Context:
         scores = np.zeros(H, np.float32)
         self._check(self.L.hop_lcp_score(self.h, scene.handle, model.handle, _ptr(flat), H, C.byref(params), int(use_weights), _ptr(scores)))
         return scores
+
+    def verify_lcp(self, P_centered, Q_centered, bases, quads, quad_trial, centroid_P, centroid_Q, delta):
+        """K3 over all congruent quadrilaterals of a frame.  Returns per-quad (poses (M,4,4), lcp, valid) and the
+        emitted hypothesis list (hyp_poses (n,4,4), hyp_lcp) in (trial, quad) order."""
+        Q = _f32(Q_centered, 3)
+        bases = np.ascontiguousarray(bases, np.int32).reshape(-1, 4)
+        quads = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+        qt = np.ascontiguousarray(quad_trial, np.int32)
+        M = len(quads)
+        cP, cQ = _f32(centroid_P), _f32(centroid_Q)
+        poses = np.zeros((M, 16), np.float32); lcp = np.zeros(M, np.float32); valid = np.zeros(M, np.int32)
+        hp = np.zeros((M, 16), np.float32); hl = np.zeros(M, np.float32); n = C.c_int32(0)
+        self._check(self.L.hop_verify_lcp(self.h, P_centered.handle, _ptr(Q), len(Q), _ptr(bases), len(bases), _ptr(quads), _ptr(qt), M,
+                                          _ptr(cP), _ptr(cQ), delta, _ptr(poses), _ptr(lcp), _ptr(valid), _ptr(hp), _ptr(hl), C.byref(n)))
+        return colmajor_to_poses(poses), lcp, valid, colmajor_to_poses(hp[: n.value]), hl[: n.value]
 
     def select_topk(self, poses, scores, K, id_offset=0, frame=0):
         flat = poses_to_colmajor(poses)

@@ -10,7 +10,7 @@
  *   hop_lcp_score         <- PoseEstimator<PointT>::selectBest()    src/perception/src/PoseEstimator.cpp:465-502
  *                            (per hypothesis: Utils::computeLCP<PointT> src/perception/src/Utils.cpp:372-444)
  *   hop_select_topk       <- the argmax inside selectBest (:491-496) / the 100-candidate cap of refineByICP (:241)
- *   hop_verify_lcp        <- gr::CongruentSetExplorationBase::TryCongruentSet / Verify
+ *   hop_verify_lcp        <- gr::CongruentSetExplorationBase::TryCongruentSet / Verify   (all trials of a frame at once)
  *                            src/OpenGR_4pcs/src/gr/algorithms/congruentSetExplorationBase.hpp:221-340, 346-435
  *                            (+ MatchBase::ComputeRigidTransformation matchBase.hpp:230-377)
  *   hop_hand_overlap      <- objFuncPSO                             src/perception/src/Hand.cpp:10-178
@@ -87,6 +87,18 @@ int hop_set_stream(hop_ctx *ctx, void *cuda_stream);
 int hop_sync(hop_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hop_launch_count(const hop_ctx *ctx);
+/* ---- per-kernel device timing (CUDA events on the context's stream around each launch of a kernel family) ------ */
+#define HOP_PROF_ICP_CORRESPOND 0 /* icp_correspond_kernel: NN + rejection, one launch per ICP iteration */
+#define HOP_PROF_ICP_SOLVE 1      /* icp_solve_kernel: moments + point-to-plane solve + convergence */
+#define HOP_PROF_LCP_SCORE 2      /* lcp_score_kernel (+ its fixed-order reduction) */
+#define HOP_PROF_NN_BUILD 3       /* nearest-neighbour grid builds (all kernels of one build = one span) */
+#define HOP_PROF_TOPK 4
+#define HOP_PROF_VERIFY 5         /* verify_lcp_kernel (K3) */
+#define HOP_PROF_HAND 6           /* hand_overlap_kernel (K1) */
+#define HOP_PROF_KINDS 8
+int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
+/* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
+int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans);
 void hop_default_icp_params(hop_icp_params *p);
 void hop_default_lcp_params(hop_lcp_params *p);
 
@@ -130,6 +142,24 @@ int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float 
                   const hop_lcp_params *params, int use_weights, float *scores_out);
 int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H,
                       const hop_lcp_params *params, int use_weights, float *d_scores_out);
+
+/* ---- K3: Super4PCS congruent-set verification ------------------------------------------------------------------- */
+/* For every congruent quadrilateral m (4 indices into Q) of trial quad_trial[m] (whose base is bases[4 * trial ..],
+ * 4 indices into P): the 3-point rigid transform (MatchBase::ComputeRigidTransformation), the rms < delta gate, the
+ * LCP of the sampled model Q against the scene P (Verify) and, for lcp > 0, the hypothesis in the un-centred frame
+ * (TryCongruentSet's getGlobalTransform).
+ *   P_centered : the scene AFTER MatchBase::init removed its centroid (matchBase.hpp:425-432); centroid_P is that centroid
+ *   Q_xyz      : nQ x 3, the sampled model points after centring; centroid_Q likewise
+ *   poses/lcp/valid : per quadrilateral (M x 16 column-major, M, M); may be NULL in the host entry
+ *   hyp_poses/hyp_lcp/n_hyp : the emitted hypotheses, compacted in (trial, quadrilateral) order = the reference's
+ *                single-thread push order (congruentSetExplorationBase.hpp:324-333); capacity M; may be NULL
+ * The _dev variant compacts in place (poses/lcp) when d_n_valid is not NULL. */
+int hop_verify_lcp(hop_ctx *ctx, hop_cloud *P_centered, const float *Q_xyz, int nQ, const int32_t *bases, int T,
+                   const int32_t *quads, const int32_t *quad_trial, int M, const float *centroid_P, const float *centroid_Q,
+                   float delta, float *poses, float *lcp, int32_t *valid, float *hyp_poses, float *hyp_lcp, int32_t *n_hyp);
+int hop_verify_lcp_dev(hop_ctx *ctx, hop_cloud *P_centered, const float *d_Q, int nQ, const int32_t *d_bases, int T,
+                       const int32_t *d_quads, const int32_t *d_quad_trial, int M, const float *centroid_P,
+                       const float *centroid_Q, float delta, float *d_poses, float *d_lcp, int32_t *d_valid, int32_t *d_n_valid);
 
 /* ---- winners ------------------------------------------------------------------------------------------------- */
 /* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).

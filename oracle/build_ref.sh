@@ -18,7 +18,7 @@ INCS="-I$EIGEN"
 if [ -f "$HERE/ref_opengr.cpp" ]; then
   mkdir -p "$TMP/gr/accelerators"
   # insert "return true;" before the closing brace of operator= (first "}" at 2-space indent after the signature)
-  awk 'BEGIN{s=0} /bool operator=\(/{s=1} {if(s==1 && $0 ~ /^[ \t]*}[ \t]*$/){print "    return true;"; s=2} print}' \
+  awk 'BEGIN{s=0} /bool operator= *\(/{s=1} {if(s==1 && $0 ~ /^[ \t]*}[ \t]*$/){print "    return true;"; s=2} print}' \
       "$GR/gr/accelerators/kdtree.h" > "$TMP/gr/accelerators/kdtree.h"
   SRCS="$SRCS $HERE/ref_opengr.cpp"
   INCS="-I$TMP -I$GR $INCS"

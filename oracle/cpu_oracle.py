@@ -51,6 +51,9 @@ def lib():
         L.hop_oracle_select_best.restype = C.c_int
         L.hop_oracle_select_best.argtypes = [_f32p, _f32p, C.c_int, C.c_void_p, _f32p, _f32p, C.c_int, _f32p, C.c_int,
                                              C.c_float, C.c_float, C.c_int, _f32p]
+        L.hop_oracle_verify_quads.restype = C.c_int
+        L.hop_oracle_verify_quads.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _f32p, _f32p, C.c_float,
+                                              _f32p, _f32p, _i32p, C.c_int]
         L.hop_oracle_num_threads.restype = C.c_int
     return _lib
 
@@ -65,7 +68,83 @@ def ref():
         _ref = C.CDLL(path)
         _ref.hop_ref_lm_point_to_plane.restype = C.c_int
         _ref.hop_ref_lm_point_to_plane.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, C.POINTER(C.c_int)]
+        if hasattr(_ref, "hop_ref_s4pcs_run"):
+            _ref.hop_ref_s4pcs_run.restype = C.c_int
+            _ref.hop_ref_s4pcs_run.argtypes = [_f32p, _f32p, C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, _i32p, C.c_int,
+                                               C.POINTER(S4pcsOptions)]
+            _ref.hop_ref_s4pcs_sizes.argtypes = [_i32p]
+            _ref.hop_ref_s4pcs_get.argtypes = [_f32p, _f32p, _i32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]
+            _ref.hop_ref_ppf_pairs.argtypes = [_f32p, _f32p, C.c_int, _i32p]
+            _ref.hop_ref_s4pcs_get_quads.argtypes = [_i32p, _f32p, _f32p]
     return _ref
+
+
+class S4pcsOptions(C.Structure):
+    """the options PoseEstimator::runSuper4pcs sets (PoseEstimator.cpp:66-73), defaults = config_autodataset.yaml:133-140"""
+    _fields_ = [("sample_size", C.c_int32), ("overlap", C.c_float), ("delta", C.c_float), ("dispersion", C.c_float),
+                ("success_quadrilaterals", C.c_int32), ("max_normal_difference", C.c_float), ("max_color_distance", C.c_float),
+                ("max_trials", C.c_int32), ("nthreads", C.c_int32)]
+
+    def __init__(self, **kw):
+        super().__init__(sample_size=100, overlap=0.2, delta=0.003, dispersion=0.5, success_quadrilaterals=10,
+                         max_normal_difference=-1.0, max_color_distance=-1.0, max_trials=0, nthreads=1)
+        for k, v in kw.items():
+            setattr(self, k, v)
+
+
+def ref_ppf_keys(xyz, nrm):
+    """unique PPF keys of all point pairs of a cloud, by the reference's own gr::computePPF (compiled in oracle/_ref)."""
+    R = ref()
+    xyz, nrm = _c(xyz), _c(nrm)
+    n = len(xyz)
+    keys = np.zeros((n * (n - 1) // 2, 4), np.int32)
+    R.hop_ref_ppf_pairs(xyz, nrm, n, keys)
+    return np.unique(keys, axis=0)
+
+
+def ref_super4pcs(P, Pn, Pprob, Q, Qn, ppf_keys, **opts):
+    """The reference's compiled Super4PCS matcher (oracle/_ref).  Returns a dict: poses (H,4,4), lcp (H,), trials (T,9)
+    [base0..3, ok, quad_begin, quad_end, hyp_begin, hyp_end], quads (M,4), centred sampled clouds and centroids."""
+    R = ref()
+    o = S4pcsOptions(**opts)
+    P, Pn, Q, Qn = _c(P), _c(Pn), _c(Q), _c(Qn)
+    keys = np.ascontiguousarray(ppf_keys, np.int32).reshape(-1, 4)
+    prob = None if Pprob is None else _c(Pprob)
+    H = R.hop_ref_s4pcs_run(P, Pn, None if prob is None else prob.ctypes.data_as(C.c_void_p), len(P), Q, Qn, len(Q), keys, len(keys), C.byref(o))
+    sizes = np.zeros(5, np.int32)
+    R.hop_ref_s4pcs_sizes(sizes)
+    H, T, M, nP, nQ = [int(x) for x in sizes]
+    poses = np.zeros((max(H, 1), 16), np.float32); lcp = np.zeros(max(H, 1), np.float32)
+    trials = np.zeros((max(T, 1), 9), np.int32); quads = np.zeros((max(M, 1), 4), np.int32)
+    Pc = np.zeros((nP, 3), np.float32); Pcn = np.zeros((nP, 3), np.float32)
+    Qc = np.zeros((nQ, 3), np.float32); Qcn = np.zeros((nQ, 3), np.float32)
+    cen = np.zeros(6, np.float32); misc = np.zeros(4, np.float32)
+    R.hop_ref_s4pcs_get(poses, lcp, trials, quads, Pc, Pcn, Qc, Qcn, cen, misc)
+    q_ok = np.zeros(max(M, 1), np.int32); q_rms = np.zeros(max(M, 1), np.float32); q_lcp = np.zeros(max(M, 1), np.float32)
+    R.hop_ref_s4pcs_get_quads(q_ok, q_rms, q_lcp)
+    return dict(quad_ok=q_ok[:M], quad_rms=q_rms[:M], quad_lcp=q_lcp[:M], poses=colmajor_to_poses(poses[:H]), lcp=lcp[:H], trials=trials[:T], quads=quads[:M], Pc=Pc, Pn=Pcn, Qc=Qc, Qn=Qcn,
+                centroid_P=cen[:3].copy(), centroid_Q=cen[3:].copy(), diameter=float(misc[0]), delta=o.delta)
+
+
+def verify_quads(Pc, Qc, bases, quads, quad_trial, centroid_P, centroid_Q, delta, nthreads=1):
+    """C restatement of TryCongruentSet + ComputeRigidTransformation + Verify (hop_oracle_verify_quads)."""
+    Pc, Qc = _c(Pc), _c(Qc)
+    bases = np.ascontiguousarray(bases, np.int32).reshape(-1, 4)
+    quads = np.ascontiguousarray(quads, np.int32).reshape(-1, 4)
+    qt = np.ascontiguousarray(quad_trial, np.int32)
+    M = len(quads)
+    poses = np.zeros((max(M, 1), 16), np.float32); lcp = np.zeros(max(M, 1), np.float32); valid = np.zeros(max(M, 1), np.int32)
+    n = lib().hop_oracle_verify_quads(Pc, len(Pc), Qc, len(Qc), bases, quads, qt, M, _c(centroid_P), _c(centroid_Q), delta, poses, lcp,
+                                      valid, nthreads)
+    return colmajor_to_poses(poses[:M]), lcp[:M], valid[:M], n
+
+
+def quad_trial_of(trials, n_quads):
+    """per-quadrilateral trial index from the (T,9) trial table of ref_super4pcs"""
+    qt = np.zeros(n_quads, np.int32)
+    for i, t in enumerate(trials):
+        qt[t[5]:t[6]] = i
+    return qt
 
 
 def _c(a):

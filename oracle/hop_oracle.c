@@ -716,3 +716,102 @@ int hop_oracle_num_threads(void) {
   return 1;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Super4PCS congruent-set verification (K3 oracle).  Restates, for a batch of congruent quadrilaterals:
+ *   gr::MatchBase::ComputeRigidTransformation     src/OpenGR_4pcs/src/gr/algorithms/matchBase.hpp:230-377
+ *   gr::CongruentSetExplorationBase::TryCongruentSet  .../congruentSetExplorationBase.hpp:221-340
+ *   gr::CongruentSetExplorationBase::Verify           .../congruentSetExplorationBase.hpp:346-435
+ *   gr::KdTree::doQueryRestrictedClosestIndex         src/OpenGR_4pcs/src/gr/accelerators/kdtree.h:342-404
+ * PINNED: tests/ compare it with the reference's own matcher compiled in oracle/_ref (ref_opengr.cpp) on the
+ * very quadrilaterals that matcher generated.
+ * Pc / Qc: CENTRED clouds (MatchBase::init removes the centroids, matchBase.hpp:425-432).
+ * ---------------------------------------------------------------------------------------------- */
+/* Eigen evaluates fixed-size 3-term reductions (dot, squaredNorm, 3x3 coefficient products) as t0 + (t1 + t2)
+ * (redux_novec_unroller splits [0,1) | [1,3)); the (R^T R).isIdentity(1e-6) gate sits at float rounding level, so the
+ * restatement keeps that association everywhere. */
+static inline float vq_sum3(float t0, float t1, float t2) { return t0 + (t1 + t2); }
+
+static int vq_frame(const float *a0, const float *a1, const float *a2, float *e /* 3x3 rows */) {
+  float v1[3] = {a1[0] - a0[0], a1[1] - a0[1], a1[2] - a0[2]};
+  float n = vq_sum3(v1[0] * v1[0], v1[1] * v1[1], v1[2] * v1[2]);
+  if (n == 0.f) return 0;
+  n = sqrtf(n); v1[0] /= n; v1[1] /= n; v1[2] /= n;
+  float d[3] = {a2[0] - a0[0], a2[1] - a0[1], a2[2] - a0[2]};
+  float k = vq_sum3(d[0] * v1[0], d[1] * v1[1], d[2] * v1[2]);
+  float v2[3] = {d[0] - k * v1[0], d[1] - k * v1[1], d[2] - k * v1[2]};
+  n = vq_sum3(v2[0] * v2[0], v2[1] * v2[1], v2[2] * v2[2]);
+  if (n == 0.f) return 0;
+  n = sqrtf(n); v2[0] /= n; v2[1] /= n; v2[2] /= n;
+  e[0] = v1[0]; e[1] = v1[1]; e[2] = v1[2]; e[3] = v2[0]; e[4] = v2[1]; e[5] = v2[2];
+  e[6] = v1[1] * v2[2] - v1[2] * v2[1]; e[7] = v1[2] * v2[0] - v1[0] * v2[2]; e[8] = v1[0] * v2[1] - v1[1] * v2[0];
+  return 1;
+}
+
+int hop_oracle_verify_quads(const float *Pc, int nP, const float *Qc, int nQ, const int32_t *bases, const int32_t *quads,
+                            const int32_t *quad_trial, int M, const float *cP, const float *cQ, float delta, float *poses,
+                            float *lcp, int32_t *valid, int nthreads) {
+  kd_tree *tree = kd_build(Pc, nP);
+  const float sq_eps = delta * delta;
+  int emitted = 0;
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel for schedule(dynamic) reduction(+ : emitted)
+  for (int m = 0; m < M; ++m) {
+    const int32_t *b = bases + 4 * quad_trial[m], *q = quads + 4 * m;
+    const float *p0 = Pc + 3 * b[0], *p1 = Pc + 3 * b[1], *p2 = Pc + 3 * b[2];
+    const float *q0 = Qc + 3 * q[0], *q1 = Qc + 3 * q[1], *q2 = Qc + 3 * q[2];
+    float c1[3], c2[3];
+    for (int k = 0; k < 3; ++k) { c1[k] = ((p0[k] + p1[k]) + p2[k]) / 3.f; c2[k] = ((q0[k] + q1[k]) + q2[k]) / 3.f; }
+    float Fp[9], Fq[9], R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1};
+    int ok = vq_frame(p0, p1, p2, Fp) && vq_frame(q0, q1, q2, Fq);
+    float rms = FLT_MAX;
+    if (ok) {
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) R[3 * i + j] = vq_sum3(Fp[i] * Fq[j], Fp[3 + i] * Fq[3 + j], Fp[6 + i] * Fq[6 + j]);
+      for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) { /* (R^T R).isIdentity(1e-6) */
+        float g = vq_sum3(R[i] * R[j], R[3 + i] * R[3 + j], R[6 + i] * R[6 + j]);
+        if (i == j) { if (!(fabsf(g - 1.f) <= 1e-6f * fminf(fabsf(g), 1.f))) ok = 0; }
+        else if (!(fabsf(g) <= 1e-6f)) ok = 0;
+      }
+    }
+    if (ok) {
+      const float *qs[3] = {q0, q1, q2}, *ps[3] = {p0, p1, p2};
+      float s = 0.f;
+      for (int i = 0; i < 3; ++i) {
+        float f[3] = {qs[i][0] - c2[0], qs[i][1] - c2[1], qs[i][2] - c2[2]}, d[3];
+        for (int r = 0; r < 3; ++r) d[r] = (vq_sum3(R[3 * r] * f[0], R[3 * r + 1] * f[1], R[3 * r + 2] * f[2]) - ps[i][r]) + c1[r];
+        s += sqrtf(vq_sum3(d[0] * d[0], d[1] * d[1], d[2] * d[2]));
+      }
+      rms = s / 4.f; /* divides by ref.size() == 4 (matchBase.hpp:357) */
+    }
+    float t[3];
+    for (int r = 0; r < 3; ++r) t[r] = c1[r] - vq_sum3(R[3 * r] * c2[0], R[3 * r + 1] * c2[1], R[3 * r + 2] * c2[2]);
+    float score = 0.f;
+    if (ok && rms >= 0.f && rms < delta) {
+      unsigned good = 0;
+      for (int i = 0; i < nQ; ++i) {
+        const float *x = Qc + 3 * i;
+        float y[3];
+        for (int r = 0; r < 3; ++r) y[r] = R[3 * r] * x[0] + R[3 * r + 1] * x[1] + R[3 * r + 2] * x[2] + t[r];
+        float d2;
+        int j = kd_nn(tree, y, &d2);
+        if (j >= 0 && d2 <= sq_eps) ++good;
+      }
+      score = (float)good / (float)nQ;
+    }
+    lcp[m] = score;
+    valid[m] = score > 0.f;
+    emitted += valid[m];
+    float *o = poses + 16 * (size_t)m;
+    memset(o, 0, 16 * sizeof(float));
+    for (int r = 0; r < 3; ++r) {
+      for (int c = 0; c < 3; ++c) M4(o, r, c) = R[3 * r + c];
+      float g[3] = {c2[0] + cQ[0], c2[1] + cQ[1], c2[2] + cQ[2]};
+      M4(o, r, 3) = c1[r] + cP[r] - (R[3 * r] * g[0] + R[3 * r + 1] * g[1] + R[3 * r + 2] * g[2]);
+    }
+    M4(o, 3, 3) = 1.f;
+  }
+  kd_free(tree);
+  return emitted;
+}

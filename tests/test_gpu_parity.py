@@ -215,3 +215,46 @@ def test_pose_estimator_mirror_refine_and_select(ctx):
     dt, dr = synth.pose_error(best._pose[None], gt[None])
     dt_ref, dr_ref = synth.pose_error(ref[bi][None], gt[None])
     assert dt[0] <= dt_ref[0] + 5e-4 and dr[0] <= dr_ref[0] + 0.5  # pose error no worse than the reference's
+
+
+# ---------------------------------------------------------------------------------------------- K3: Super4PCS verification
+@pytest.mark.skipif(O.ref() is None or not hasattr(O.ref(), "hop_ref_s4pcs_run"), reason="oracle/_ref (compiled OpenGR) not built")
+@pytest.mark.parametrize("name,seed", [("ellipse", 2), ("cuboid", 3), ("tless", 4)])
+def test_verify_lcp_matches_the_compiled_reference(ctx, name, seed):
+    """K3 against the reference's OWN compiled matcher (oracle/_ref): the same bases and congruent sets that matcher
+    generated go through hop_verify_lcp; the ok/rms gate and the LCP of every quadrilateral must agree bit for bit
+    (LCP is an integer count / |Q|), the emitted hypothesis list must be the reference's list in its order."""
+    m, mn = synth.make_model(name, 400, seed=1)
+    keys = O.ref_ppf_keys(m, mn)
+    s, sn, conf, gt = synth.make_scene(name, 500, seed=seed)
+    r = O.ref_super4pcs(s, sn, conf, m, mn, keys)
+    assert len(r["quads"]) > 100 and len(r["poses"]) > 50
+    qt = O.quad_trial_of(r["trials"], len(r["quads"]))
+    P = ctx.upload_cloud(r["Pc"], r["Pn"])
+    poses, lcp, valid, hyp_poses, hyp_lcp = ctx.verify_lcp(P, r["Qc"], r["trials"][:, :4], r["quads"], qt, r["centroid_P"], r["centroid_Q"], r["delta"])
+    assert np.array_equal(lcp, r["quad_lcp"])                      # per quadrilateral, including the gated-out zeros
+    assert np.array_equal(valid.astype(bool), r["quad_lcp"] > 0)
+    assert len(hyp_poses) == len(r["poses"]) and np.array_equal(hyp_lcp, r["lcp"])  # stable compaction = reference order
+    assert np.abs(hyp_poses - r["poses"]).max() < 1e-6
+    # and the C restatement of the same functions agrees with both
+    o_poses, o_lcp, o_valid, n = O.verify_quads(r["Pc"], r["Qc"], r["trials"][:, :4], r["quads"], qt, r["centroid_P"], r["centroid_Q"], r["delta"])
+    assert np.array_equal(o_lcp, lcp) and np.abs(o_poses[valid.astype(bool)] - hyp_poses).max() < 1e-6
+    P.free()
+
+
+def test_verify_lcp_edge_cases(ctx):
+    rng = np.random.default_rng(0)
+    Pc = rng.normal(0, 0.02, (300, 3)).astype(np.float32)
+    P = ctx.upload_cloud(Pc, np.tile([[0, 0, 1.0]], (300, 1)).astype(np.float32))
+    Qc = Pc[:50].copy()
+    z = np.zeros(3, np.float32)
+    # identity congruence: quad == base -> identity transform, every Q point has a neighbour
+    poses, lcp, valid, hp, hl = ctx.verify_lcp(P, Qc, [[0, 1, 2, 3]], [[0, 1, 2, 3]], [0], z, z, 0.003)
+    assert valid[0] == 1 and lcp[0] == 1.0 and np.abs(poses[0] - np.eye(4)).max() < 1e-5
+    # degenerate quadrilateral (repeated point) and an incongruent one: gated out, nothing emitted
+    poses, lcp, valid, hp, hl = ctx.verify_lcp(P, Qc, [[0, 1, 2, 3]], [[5, 5, 6, 7], [0, 10, 20, 30]], [0, 0], z, z, 0.003)
+    assert list(valid) == [0, 0] and len(hp) == 0
+    # empty batch
+    poses, lcp, valid, hp, hl = ctx.verify_lcp(P, Qc, [[0, 1, 2, 3]], np.zeros((0, 4), np.int32), np.zeros(0, np.int32), z, z, 0.003)
+    assert len(lcp) == 0 and len(hp) == 0
+    P.free()
