@@ -27,6 +27,19 @@ class LcpParams(C.Structure):
                 ("use_reciprocal", C.c_int32), ("team_warps", C.c_int32)]
 
 
+HOP_MAX_FINGER_BINS = 32
+
+
+class FingerParams(C.Structure):
+    """hop_finger_params: what objFuncPSO reads from optim::ArgPasser and the YAML (Hand.cpp:10-178)."""
+    _fields_ = [("model2handbase", C.c_float * 16), ("finger_out2parent", C.c_float * 16), ("tip1_local", C.c_float * 3),
+                ("tip2_local", C.c_float * 3), ("pair_tip1_y", C.c_float), ("pair_tip2_y", C.c_float), ("palm_side", C.c_int32),
+                ("right_side", C.c_int32), ("gripper_min_dist", C.c_float), ("dist_thres", C.c_float), ("normal_angle_deg", C.c_float),
+                ("check_normal", C.c_int32), ("num_division", C.c_int32), ("min_z", C.c_float), ("stride_z", C.c_float),
+                ("hist_min_y", C.c_float * HOP_MAX_FINGER_BINS), ("max_outter_pts", C.c_int32), ("outter_pt_dist", C.c_float),
+                ("outter_pt_dist_weight", C.c_float)]
+
+
 class PoseRec(C.Structure):
     _fields_ = [("pose", C.c_float * 16), ("score", C.c_float), ("id", C.c_int32), ("frame", C.c_int32), ("pad", C.c_int32)]
 
@@ -103,6 +116,8 @@ def load_library():
     L.hop_lcp_score_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
     L.hop_verify_lcp.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]
     L.hop_verify_lcp_dev.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]
+    L.hop_hand_overlap.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, C.c_int, _vp, _vp]
+    L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
     L.hop_select_topk.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
     for name in declared_symbols():
@@ -304,6 +319,15 @@ class Context:
         self._check(self.L.hop_verify_lcp(self.h, P_centered.handle, _ptr(Q), len(Q), _ptr(bases), len(bases), _ptr(quads), _ptr(qt), M,
                                           _ptr(cP), _ptr(cQ), delta, _ptr(poses), _ptr(lcp), _ptr(valid), _ptr(hp), _ptr(hl), C.byref(n)))
         return colmajor_to_poses(poses), lcp, valid, colmajor_to_poses(hp[: n.value]), hl[: n.value]
+
+    def hand_overlap(self, finger, scene_hand, scene_noswivel, params, thetas, scene_normals=None):
+        """K1: cost[s] = objFuncPSO(thetas[s]) for S joint angles (radians); returns (cost (S,) float64, arg-min index)."""
+        th = np.ascontiguousarray(thetas, np.float64)
+        cost = np.zeros(len(th), np.float64)
+        best = C.c_int32(-1)
+        self._check(self.L.hop_hand_overlap(self.h, finger.handle, scene_hand.handle, scene_normals.handle if scene_normals else None,
+                                            scene_noswivel.handle, C.byref(params), _ptr(th), len(th), _ptr(cost), C.byref(best)))
+        return cost, int(best.value)
 
     def select_topk(self, poses, scores, K, id_offset=0, frame=0):
         flat = poses_to_colmajor(poses)

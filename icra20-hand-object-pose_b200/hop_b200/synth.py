@@ -178,3 +178,102 @@ def workload(name):
         "tiny": dict(model="ellipse", n_scene=500, n_model=2000, H=64, max_iter=10),
     }
     return table[name]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hand-state search fixtures (K1): a two-finger gripper in the hand-base frame, SURVEY.md 8(d) sizes
+# ------------------------------------------------------------------------------------------------------------------
+def _rot_x(th):
+    c, s = np.cos(th), np.sin(th)
+    return np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1.0]])
+
+
+def make_finger_cloud(n, seed=0, size=(0.02, 0.012, 0.06)):
+    """Surface samples of a finger link: a box, x in [-sx/2,sx/2], y in [-sy/2,sy/2] (+y = inner face), z in [-sz,0]
+    (the tip is at min z, the joint axis is local x through the origin), outward unit normals."""
+    rng = np.random.default_rng(seed)
+    pts, nrm = _cuboid(rng, n, *size)
+    pts[:, 2] -= size[2] / 2
+    return pts.astype(np.float32), nrm.astype(np.float32)
+
+
+def make_hand_case(seed=0, n_finger=300, n_hand=3000, theta_true_deg=15.0, palm_side=False, right_side=False, bad_normals=True,
+                   shifted_lookup=False):
+    """One finger-link search problem.  Returns a dict with the clouds (finger, scene_hand = what the kd-tree indexes,
+    scene_lookup = the cloud the reference reads the neighbour's normal from, scene_noswivel) and the scalar fields of
+    hop_finger_params (everything except the FingerProperty histogram, which the host mirror derives from the cloud)."""
+    rng = np.random.default_rng(seed)
+    f_xyz, f_nrm = make_finger_cloud(n_finger, seed=seed + 1)
+    sgn = 1.0 if not right_side else -1.0            # left finger sits at -y and closes towards +y; the right one is mirrored
+    m2hb = np.eye(4)
+    if right_side:
+        m2hb[:3, :3] = np.diag([-1.0, -1.0, 1.0])    # rotate 180 deg about z: local +y (inner) faces hand-base -y
+    m2hb[:3, 3] = [-0.15, -0.04 * sgn, 0.02]
+    th = np.deg2rad(theta_true_deg)
+    T_true = m2hb @ _rot_x(th)
+    # scene: the true finger (dense, noisy), a palm plate, the grasped object between the fingers, clutter
+    n_f, n_p, n_o = int(0.45 * n_hand), int(0.2 * n_hand), int(0.25 * n_hand)
+    n_c = n_hand - n_f - n_p - n_o
+    fp, fn = _cuboid(rng, n_f, 0.02, 0.012, 0.06)
+    fp[:, 2] -= 0.03
+    fp = fp + fn * rng.normal(0, 0.0003, (n_f, 1))
+    Pf = fp @ T_true[:3, :3].T + T_true[:3, 3]
+    Nf = fn @ T_true[:3, :3].T
+    pp, pn = _cuboid(rng, n_p, 0.06, 0.06, 0.01)
+    Pp = pp + [-0.15, 0.0, 0.03]
+    po, no = _ellipsoid(rng, n_o, 0.02, 0.018, 0.015)
+    Po = po + [-0.15, 0.0, -0.03]
+    Pc = rng.uniform([-0.3, -0.03, -0.06], [-0.05, 0.03, 0.03], (n_c, 3))
+    Nc = rng.normal(size=(n_c, 3))
+    Nc /= np.linalg.norm(Nc, axis=1, keepdims=True)
+    xyz = np.concatenate([Pf, Pp, Po, Pc]).astype(np.float32)
+    nrm = np.concatenate([Nf, pn, no, Nc]).astype(np.float32)
+    if bad_normals:                                   # the reference branches on all-zero and non-finite normals
+        k = rng.choice(n_f, size=max(n_f // 20, 2), replace=False)
+        nrm[k[: len(k) // 2]] = 0.0
+        nrm[k[len(k) // 2:], rng.integers(0, 3)] = np.nan
+    perm = rng.permutation(len(xyz))
+    xyz, nrm = xyz[perm], nrm[perm]
+    # scene_hand_region (lookup) = the unfiltered cloud; scene_hand (kd-tree) = a subset with shifted indices
+    # (shifted_lookup: the noise filters dropped points anywhere, so the reference's index reuse reads unrelated normals;
+    #  otherwise only trailing points were dropped and the indices still line up)
+    keep = rng.random(len(xyz)) > 0.03 if shifted_lookup else np.arange(len(xyz)) < int(0.97 * len(xyz))
+    scene_xyz, scene_nrm = xyz[keep], nrm[keep]
+    sw = (scene_xyz[:, 0] > -0.25) & (scene_xyz[:, 0] < -0.1)  # Hand.cpp:312-318 pass-through
+    f_min, f_max = f_xyz.min(0), f_xyz.max(0)
+    if palm_side:
+        tip1 = [f_min[0], f_max[1], f_min[2]]         # of the distal link, in ITS frame (finger_out_property)
+        tip2 = [f_min[0], f_max[1], f_min[2]]
+    else:
+        tip1 = [f_min[0], f_max[1], f_min[2]]
+        tip2 = [f_min[0], f_max[1], f_max[2]]
+    out2parent = np.eye(4)
+    out2parent[:3, 3] = [0, 0, -0.06]                 # distal link hangs at the proximal link's tip
+    scalars = dict(model2handbase=m2hb.astype(np.float32), finger_out2parent=out2parent.astype(np.float32),
+                   tip1_local=np.array(tip1, np.float32), tip2_local=np.array(tip2, np.float32),
+                   pair_tip1_y=float(0.02 * sgn), pair_tip2_y=float(0.035 * sgn), palm_side=int(palm_side), right_side=int(right_side),
+                   gripper_min_dist=0.03, dist_thres=0.005, normal_angle_deg=60.0, check_normal=1, num_division=10,
+                   max_outter_pts=300, outter_pt_dist=0.002, outter_pt_dist_weight=1.0)
+    return dict(finger_xyz=f_xyz, finger_nrm=f_nrm, scene_xyz=scene_xyz, scene_nrm=scene_nrm, lookup_xyz=xyz, lookup_nrm=nrm,
+                noswivel_xyz=scene_xyz[sw], noswivel_nrm=scene_nrm[sw], theta_true=th, scalars=scalars)
+
+
+def hand_variants():
+    """name -> (make_hand_case kwargs, scalar overrides): together they reach every branch of objFuncPSO."""
+    return {
+        "left": (dict(), dict()),
+        "right": (dict(right_side=True), dict()),
+        "palm": (dict(palm_side=True), dict()),
+        "nogap": (dict(), dict(gripper_min_dist=-1.0, dist_thres=0.0005)),   # no gap penalty, 0.5 mm gate: no match -> 100 - theta
+        "exp": (dict(), dict(outter_pt_dist=1e-4, max_outter_pts=10 ** 6)),  # the exp(avg * 1000) branch
+        "nonormal": (dict(), dict(check_normal=0)),
+        "shifted": (dict(shifted_lookup=True), dict()),                      # index reuse reads unrelated normals
+        "tight": (dict(n_hand=1200, n_finger=150), dict(dist_thres=0.002, normal_angle_deg=30.0)),
+    }
+
+
+def hand_problem(variant, seed=5):
+    kw, over = hand_variants()[variant]
+    case = make_hand_case(seed=seed, **kw)
+    case["scalars"].update(over)
+    return case

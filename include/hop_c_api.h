@@ -161,6 +161,46 @@ int hop_verify_lcp_dev(hop_ctx *ctx, hop_cloud *P_centered, const float *d_Q, in
                        const int32_t *d_quads, const int32_t *d_quad_trial, int M, const float *centroid_P,
                        const float *centroid_Q, float delta, float *d_poses, float *d_lcp, int32_t *d_valid, int32_t *d_n_valid);
 
+/* ---- K1: hand-state overlap objective (the function the reference's swarm minimises) ------------------------------- */
+#define HOP_MAX_FINGER_BINS 32
+/* Everything objFuncPSO reads from optim::ArgPasser / the YAML (Hand.cpp:10-178), flattened.  Matrices column-major. */
+typedef struct hop_finger_params {
+  float model2handbase[16];    /* args->model2handbase: the finger link in the hand-base frame at joint angle 0 (Hand.cpp:646) */
+  float finger_out2parent[16]; /* args->finger_out2parent: the distal link in this link's frame (palm-side fingers, :30, :630) */
+  float tip1_local[3];         /* palm side: finger_out_property (min_x,max_y,min_z), else finger_property (min_x,max_y,min_z) (:28,:38) */
+  float tip2_local[3];         /* palm side: finger_property (min_x,max_y,min_z), else (min_x,max_y,max_z)                       (:33,:41) */
+  float pair_tip1_y, pair_tip2_y; /* args->pair_tip1(1), args->pair_tip2(1): the opposite finger's tips, hand-base frame (:48-54) */
+  int32_t palm_side;           /* name == finger_1_1 || finger_2_1 (:26) */
+  int32_t right_side;          /* name == finger_2_1 || finger_2_2 (:46) */
+  float gripper_min_dist;      /* cfg.gripper_min_dist (0.8 * min bbox extent of the object, main_realdata_auto.cpp:41-45) */
+  float dist_thres;            /* hand_match.finger{1,2}_dist_thres */
+  float normal_angle_deg;      /* hand_match.finger{1,2}_normal_angle */
+  int32_t check_normal;        /* hand_match.check_normal */
+  int32_t num_division;        /* FingerProperty bins along z (10), <= HOP_MAX_FINGER_BINS */
+  float min_z, stride_z;       /* FingerProperty::_min_z, _stride_z */
+  float hist_min_y[HOP_MAX_FINGER_BINS]; /* FingerProperty::_hist_alongz(1, bin): the finger's outer face per z bin */
+  int32_t max_outter_pts;      /* hand_match.max_outter_pts (300) */
+  float outter_pt_dist;        /* hand_match.outter_pt_dist (0.002) */
+  float outter_pt_dist_weight; /* hand_match.outter_pt_dist_weight (1) */
+} hop_finger_params;
+
+/* cost_out[s] = objFuncPSO(thetas[s]) for S joint angles (radians) of one finger link -- the dense, data-parallel
+ * replacement of the 16-particle x 4-evaluation swarm of Hand::matchOneComponentPSO (Hand.cpp:603-672, pso.hpp:146-351).
+ *   finger         : args->model (the link's cloud with normals, its own frame)
+ *   scene_hand     : scene_hand_region_removed_noise, hand-base frame (what args->kdtree_scene indexes)
+ *   scene_normals  : cloud whose NORMALS are read with the neighbour index (args->scene_hand_region, Hand.cpp:94); NULL =
+ *                    scene_hand itself
+ *   scene_noswivel : args->scene_remove_swivel, hand-base frame
+ *   best_out       : (may be NULL) index of the lowest cost, ties -> lowest index */
+int hop_hand_overlap(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop_cloud *scene_normals, hop_cloud *scene_noswivel,
+                     const hop_finger_params *params, const double *thetas, int S, double *cost_out, int32_t *best_out);
+/* device pointers: d_thetas S doubles; d_half_cs S x 2 floats = (cosf(theta/2), sinf(theta/2)) of float(theta) -- the two
+ * numbers Eigen's AngleAxisf -> Quaternionf conversion produces on the host (pass NULL to have the device compute them);
+ * d_cost S doubles; d_best one int32 (may be NULL). */
+int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop_cloud *scene_normals, hop_cloud *scene_noswivel,
+                         const hop_finger_params *params, const double *d_thetas, const float *d_half_cs, int S, double *d_cost,
+                         int32_t *d_best);
+
 /* ---- winners ------------------------------------------------------------------------------------------------- */
 /* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).
  * d_out may be the send slot of a collective (the all-gather of winners). */

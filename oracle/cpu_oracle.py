@@ -55,6 +55,14 @@ def lib():
         L.hop_oracle_verify_quads.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, _i32p, _i32p, C.c_int, _f32p, _f32p, C.c_float,
                                               _f32p, _f32p, _i32p, C.c_int]
         L.hop_oracle_num_threads.restype = C.c_int
+        _f64p = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+        L.hop_oracle_obj_func_pso.restype = C.c_double
+        L.hop_oracle_obj_func_pso.argtypes = [C.c_double, C.c_void_p, _f32p, _f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, C.c_void_p]
+        L.hop_oracle_hand_overlap.argtypes = [C.c_void_p, _f32p, _f32p, C.c_int, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f64p, C.c_int,
+                                              _f64p, C.c_void_p, C.c_int]
+        L.hop_oracle_finger_property.argtypes = [_f32p, C.c_int, C.c_int, C.c_void_p, _f32p]
+        L.hop_oracle_hand_tf_self.argtypes = [C.c_double, _f32p]
+        L.hop_oracle_hand_inverse.argtypes = [_f32p, _f32p]
     return _lib
 
 
@@ -245,3 +253,22 @@ def select_best(s_xyz, s_nrm, m_xyz, m_nrm, poses, dist=0.001, angle=10.0, weigh
 
 def num_threads():
     return int(lib().hop_oracle_num_threads())
+
+
+# ---- K1 oracle: objFuncPSO over a grid of states (hop_oracle_hand.c) -------------------------------------------------
+def hand_overlap(params, f_xyz, f_nrm, nn_xyz, lookup_nrm, w_xyz, thetas, nthreads=0, with_detail=False):
+    """params: a ctypes hop_finger_params (hop_b200.FingerParams).  Returns cost (S,) float64 [, detail (S,4)]."""
+    f_xyz, f_nrm, nn_xyz, lookup_nrm, w_xyz = _c(f_xyz), _c(f_nrm), _c(nn_xyz), _c(lookup_nrm), _c(w_xyz)
+    th = np.ascontiguousarray(thetas, np.float64)
+    cost = np.zeros(len(th), np.float64)
+    detail = np.zeros((len(th), 4), np.float64) if with_detail else None
+    lib().hop_oracle_hand_overlap(C.addressof(params), f_xyz, f_nrm, len(f_xyz), nn_xyz, len(nn_xyz), lookup_nrm, w_xyz, len(w_xyz),
+                                  th, len(th), cost, detail.ctypes.data_as(C.c_void_p) if with_detail else None, nthreads)
+    return (cost, detail) if with_detail else cost
+
+
+def finger_property(xyz, num_division, params):
+    """FingerProperty restatement: fills params.{num_division,min_z,stride_z,hist_min_y}; returns the bounding box (6,)."""
+    bbox = np.zeros(6, np.float32)
+    lib().hop_oracle_finger_property(_c(xyz), len(xyz), num_division, C.addressof(params), bbox)
+    return bbox
