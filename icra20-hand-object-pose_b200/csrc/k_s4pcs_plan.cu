@@ -1,0 +1,378 @@
+// k_s4pcs_plan.cu -- HOST side of Super4PCS: everything that consumes the reference's random streams, planned for all
+// trials before the device starts (no GPU code in this file; it is part of libhop.so because runSuper4pcs calls it).
+//
+//   MatchBase::init                 src/OpenGR_4pcs/src/gr/algorithms/matchBase.hpp:382-462
+//   UniformDistSampler              src/OpenGR_4pcs/src/gr/sampling.h:67-145
+//   PairCreationFunctor::synch3DContent   .../pairCreationFunctor.h:129-161
+//   computePPF / ppfClosestBin      .../matchBase.hpp:27-68
+//   SelectRandomTriangle            .../matchBase.hpp:111-212
+//   SelectQuadrilateral / TryQuadrilateral / distSegmentToSegment   .../match4pcsBase.hpp:50-189,287-354
+//
+// The reference draws from two std::mt19937 streams through std::shuffle, operator() % n and
+// std::discrete_distribution<>; this file uses the same standard-library classes, so built with the same libstdc++ it
+// replays the same sequence.  Float expressions are written in the order Eigen evaluates them on the reference's build
+// (no FMA, fixed-size 3-term reductions as t0 + (t1 + t2)), so bases and invariants come out bit-identical to the
+// compiled reference (tests/test_s4pcs_plan.py pins this against oracle/_ref).
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <limits>
+#include <random>
+#include <unordered_set>
+
+#include "s4pcs.h"
+
+namespace {
+
+typedef std::array<float, 3> V3;
+
+inline V3 sub(const float *a, const float *b) { return V3{a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
+inline float dot(const V3 &a, const V3 &b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+inline float dotp(const float *a, const float *b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
+inline float sqnorm(const V3 &a) { return dot(a, a); }
+inline float norm(const V3 &a) { return std::sqrt(sqnorm(a)); }
+inline V3 normalized(const V3 &a) {  // Eigen: z = squaredNorm(); z > 0 ? a / sqrt(z) : a
+  const float z = sqnorm(a);
+  if (z > 0.f) { const float s = std::sqrt(z); return V3{a[0] / s, a[1] / s, a[2] / s}; }
+  return a;
+}
+
+inline int ppf_closest_bin(int value, int discretization) {
+  int lower_limit = value - (value % discretization);
+  int upper_limit = lower_limit + discretization;
+  int dist_from_lower = value - lower_limit;
+  int dist_from_upper = upper_limit - value;
+  return (dist_from_lower < dist_from_upper) ? lower_limit : upper_limit;
+}
+
+// gr::computePPF (matchBase.hpp:44-68)
+void compute_ppf(const S4Pt &a, const S4Pt &b, int *ppf) {
+  V3 n1 = normalized(V3{a.n[0], a.n[1], a.n[2]}), n2 = normalized(V3{b.n[0], b.n[1], b.n[2]});
+  n1 = normalized(n1); n2 = normalized(n2);  // `.normalized()` then `.normalize()`
+  const int dist = static_cast<int>(norm(sub(a.p, b.p)) * 1000);
+  const V3 d = normalized(sub(b.p, a.p));
+  const int n1_p1p2 = static_cast<int>(std::acos(dot(n1, d)) / M_PI * 180);
+  const int n2_p1p2 = static_cast<int>(std::acos(dot(n2, d)) / M_PI * 180);
+  const int n1_n2 = static_cast<int>(std::acos(dot(n1, n2)) / M_PI * 180);
+  ppf[0] = ppf_closest_bin(dist, 5);
+  ppf[1] = ppf_closest_bin(n1_p1p2, 10);
+  ppf[2] = ppf_closest_bin(n2_p1p2, 10);
+  ppf[3] = ppf_closest_bin(n1_n2, 10);
+}
+
+inline uint64_t pack_key(const int *k) {
+  return ((uint64_t)(uint16_t)k[0] << 48) | ((uint64_t)(uint16_t)k[1] << 32) | ((uint64_t)(uint16_t)k[2] << 16) | (uint64_t)(uint16_t)k[3];
+}
+
+struct Planner {
+  hop_s4pcs_plan &pl;
+  std::unordered_set<uint64_t> keys;
+  std::vector<float> point_probs;   // _point_probs (anneals across trials)
+  std::mt19937 random_generator;    // randomGenerator_
+  std::mt19937 point_index_engine;  // _point_index_engine, seeded 0 (matchBase.hpp:76)
+  float max_base_diameter = -1.f;
+
+  explicit Planner(hop_s4pcs_plan &p) : pl(p), random_generator(p.opt.random_seed ? p.opt.random_seed : std::mt19937::default_seed), point_index_engine(0) {}
+
+  bool has_ppf(const S4Pt &a, const S4Pt &b) const {
+    int k[4];
+    compute_ppf(a, b, k);
+    if (k[0] < 0 || k[0] > 65535 || k[1] < 0 || k[1] > 65535 || k[2] < 0 || k[2] > 65535 || k[3] < 0 || k[3] > 65535) return false;
+    return keys.count(pack_key(k)) != 0;
+  }
+
+  // MatchBase::init
+  void init(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm, int nQ) {
+    auto fill = [](const float *xyz, const float *nrm, int i) {  // fillPointSet + Point3D::set_normal (normalises once)
+      S4Pt q;
+      for (int k = 0; k < 3; ++k) q.p[k] = xyz[3 * i + k];
+      V3 n = normalized(V3{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]});
+      for (int k = 0; k < 3; ++k) q.n[k] = n[k];
+      return q;
+    };
+    pl.P.resize(nP);
+    pl.P_prob.resize(nP);
+    for (int i = 0; i < nP; ++i) { pl.P[i] = fill(P_xyz, P_nrm, i); pl.P_prob[i] = P_prob ? P_prob[i] : 1.f; }
+    pl.Q.clear(); pl.q_ids.clear();
+    if ((size_t)nQ > (size_t)pl.opt.sample_size) {
+      // UniformDistSampler: the first point met in every voxel of edge delta, in input order
+      struct VoxHash { size_t operator()(const std::array<int, 3> &c) const { return (size_t)(100000007ull * (uint64_t)c[0] + 161803409ull * (uint64_t)c[1] + 423606823ull * (uint64_t)c[2]); } };
+      std::unordered_set<std::array<int, 3>, VoxHash> seen;
+      const float scale = 1.0f / pl.opt.delta;
+      std::vector<int> uniform;
+      for (int i = 0; i < nQ; ++i) {
+        std::array<int, 3> c{int(std::floor(Q_xyz[3 * i] * scale)), int(std::floor(Q_xyz[3 * i + 1] * scale)), int(std::floor(Q_xyz[3 * i + 2] * scale))};
+        if (seen.insert(c).second) uniform.push_back(i);
+      }
+      std::shuffle(uniform.begin(), uniform.end(), random_generator);
+      const size_t nb = std::min(uniform.size(), (size_t)pl.opt.sample_size);
+      for (size_t k = 0; k < nb; ++k) { pl.Q.push_back(fill(Q_xyz, Q_nrm, uniform[k])); pl.q_ids.push_back(uniform[k]); }
+    } else {
+      for (int i = 0; i < nQ; ++i) { pl.Q.push_back(fill(Q_xyz, Q_nrm, i)); pl.q_ids.push_back(i); }
+    }
+    point_probs = pl.P_prob;
+    auto center = [](std::vector<S4Pt> &c, float *centroid) {
+      centroid[0] = centroid[1] = centroid[2] = 0.f;
+      for (const S4Pt &q : c) for (int k = 0; k < 3; ++k) centroid[k] += q.p[k];
+      const float n = (float)c.size();
+      for (int k = 0; k < 3; ++k) centroid[k] /= n;
+      for (S4Pt &q : c) for (int k = 0; k < 3; ++k) q.p[k] -= centroid[k];
+    };
+    center(pl.P, pl.centroid_P);
+    center(pl.Q, pl.centroid_Q);
+    // "diameter of P": 1000 random pairs -- of Q (matchBase.hpp:439-448)
+    pl.diameter = 0.f;
+    const size_t nq = pl.Q.size();
+    if (nq > 0)
+      for (int i = 0; i < 1000; ++i) {
+        int at = random_generator() % nq;
+        int bt = random_generator() % nq;
+        float l = norm(sub(pl.Q[bt].p, pl.Q[at].p));
+        if (l > pl.diameter) pl.diameter = l;
+      }
+    max_base_diameter = pl.diameter;
+    // PairCreationFunctor::synch3DContent: Q in the unit cube
+    float mn[3] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    float mx[3] = {std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest(), std::numeric_limits<float>::lowest()};
+    for (const S4Pt &q : pl.Q) for (int k = 0; k < 3; ++k) { mn[k] = std::min(mn[k], q.p[k]); mx[k] = std::max(mx[k], q.p[k]); }
+    float diag = 0.f;
+    for (int k = 0; k < 3; ++k) { pl.gcenter[k] = (mn[k] + mx[k]) / 2.f; diag = k == 0 ? mx[k] - mn[k] : std::max(diag, mx[k] - mn[k]); }
+    pl.ratio = (float)((double)diag + 0.001);
+    pl.Qunit.resize(3 * nq);
+    for (size_t i = 0; i < nq; ++i) for (int k = 0; k < 3; ++k) pl.Qunit[3 * i + k] = (pl.Q[i].p[k] - pl.gcenter[k]) / pl.ratio + 0.5f;
+  }
+
+  // SelectRandomTriangle (matchBase.hpp:111-212).  sample_pool is returned as the pool for the 4th point.
+  bool select_random_triangle(int &base1, int &base2, int &base3, std::vector<int> &sample_pool) {
+    const std::vector<S4Pt> &P = pl.P;
+    const int number_of_points = (int)P.size();
+    base1 = base2 = base3 = -1;
+    std::discrete_distribution<> sampler(point_probs.begin(), point_probs.end());
+    const int first_point = sampler(point_index_engine);
+    point_probs[first_point] *= pl.opt.dispersion;
+    sample_pool.clear();
+    std::vector<float> probs;
+    for (int i = 0; i < number_of_points; ++i) {
+      if (i == first_point) continue;
+      if (has_ppf(P[first_point], P[i])) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
+    }
+    if (sample_pool.size() < 3) return false;
+    const float sq_max_base_diameter = max_base_diameter * max_base_diameter;
+    for (int i = 0; (size_t)i < sample_pool.size() * sample_pool.size() / 4; ++i) {
+      std::discrete_distribution<> sampler1(probs.begin(), probs.end());
+      const int second_point = sampler1(point_index_engine);
+      const int third_point = sampler1(point_index_engine);
+      if (second_point == third_point) continue;
+      if (!has_ppf(P[sample_pool[second_point]], P[sample_pool[third_point]])) continue;
+      probs[second_point] *= pl.opt.dispersion;
+      probs[third_point] *= pl.opt.dispersion;
+      const V3 u = sub(P[sample_pool[second_point]].p, P[first_point].p);
+      const V3 w = sub(P[sample_pool[third_point]].p, P[first_point].p);
+      const float how_wide = dot(normalized(u), normalized(w));
+      if (std::abs(how_wide) <= std::cos(45 * M_PI / 180.0) && sqnorm(u) < sq_max_base_diameter && sqnorm(w) < sq_max_base_diameter) {
+        base1 = first_point; base2 = sample_pool[second_point]; base3 = sample_pool[third_point];
+        break;
+      }
+    }
+    if (base2 == -1 || base3 == -1) return false;
+    std::vector<int> backup = sample_pool;
+    sample_pool.clear();
+    for (int i = 0; (size_t)i < backup.size(); ++i) {
+      if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
+      // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
+      // a point id (match4pcsBase.hpp:159): reproduced
+      if (has_ppf(P[base2], P[backup[i]]) && has_ppf(P[base3], P[backup[i]])) sample_pool.push_back(i);
+    }
+    if (sample_pool.size() < 1) return false;
+    return base1 != -1 && base2 != -1 && base3 != -1;
+  }
+
+  static float dist_segment_to_segment(const float *p1, const float *p2, const float *q1, const float *q2, float &invariant1, float &invariant2) {
+    static const float kSmallNumber = 0.0001;
+    const V3 u = sub(p2, p1), v = sub(q2, q1), w = sub(p1, q1);
+    const float a = dot(u, u), b = dot(u, v), c = dot(v, v), d = dot(u, w), e = dot(v, w);
+    const float f = a * c - b * b;
+    float s1 = 0.0, s2 = f, t1 = 0.0, t2 = f;
+    if (f < kSmallNumber) { s1 = 0.0; s2 = 1.0; t1 = e; t2 = c; }
+    else {
+      s1 = (b * e - c * d);
+      t1 = (a * e - b * d);
+      if (s1 < 0.0) { s1 = 0.0; t1 = e; t2 = c; }
+      else if (s1 > s2) { s1 = s2; t1 = e + b; t2 = c; }
+    }
+    if (t1 < 0.0) {
+      t1 = 0.0;
+      if (-d < 0.0) s1 = 0.0;
+      else if (-d > a) s1 = s2;
+      else { s1 = -d; s2 = a; }
+    } else if (t1 > t2) {
+      t1 = t2;
+      if ((-d + b) < 0.0) s1 = 0;
+      else if ((-d + b) > a) s1 = s2;
+      else { s1 = (-d + b); s2 = a; }
+    }
+    invariant1 = (std::abs(s1) < kSmallNumber ? 0.0 : s1 / s2);
+    invariant2 = (std::abs(t1) < kSmallNumber ? 0.0 : t1 / t2);
+    const V3 r{(w[0] + invariant1 * u[0]) - invariant2 * v[0], (w[1] + invariant1 * u[1]) - invariant2 * v[1], (w[2] + invariant1 * u[2]) - invariant2 * v[2]};
+    return norm(r);
+  }
+
+  // TryQuadrilateral (match4pcsBase.hpp:50-101): pick the pairing of the four points whose segments pass closest
+  static bool try_quadrilateral(S4Pt *base3d, float &invariant1, float &invariant2, int *id) {
+    float min_distance = std::numeric_limits<float>::max();
+    int best1 = -1, best2 = -1, best3 = -1, best4 = -1;
+    for (int i = 0; i < 4; ++i)
+      for (int j = 0; j < 4; ++j) {
+        if (i == j) continue;
+        int k = 0; while (k == i || k == j) k++;
+        int l = 0; while (l == i || l == j || l == k) l++;
+        float li1, li2;
+        const float segment_distance = dist_segment_to_segment(base3d[i].p, base3d[j].p, base3d[k].p, base3d[l].p, li1, li2);
+        if (segment_distance < min_distance) { min_distance = segment_distance; best1 = i; best2 = j; best3 = k; best4 = l; invariant1 = li1; invariant2 = li2; }
+      }
+    if (best1 < 0 || best2 < 0 || best3 < 0 || best4 < 0) return false;
+    const S4Pt tmp[4] = {base3d[0], base3d[1], base3d[2], base3d[3]};
+    base3d[0] = tmp[best1]; base3d[1] = tmp[best2]; base3d[2] = tmp[best3]; base3d[3] = tmp[best4];
+    const int tid[4] = {id[0], id[1], id[2], id[3]};
+    id[0] = tid[best1]; id[1] = tid[best2]; id[2] = tid[best3]; id[3] = tid[best4];
+    return true;
+  }
+
+  // SelectQuadrilateral (match4pcsBase.hpp:107-189)
+  bool select_quadrilateral(S4Trial &t) {
+    const std::vector<S4Pt> &P = pl.P;
+    const float kBaseTooSmall = 0.2;
+    int current_trial = 0;
+    int base1, base2, base3, base4;
+    while (current_trial < 1000) {
+      current_trial++;
+      std::vector<int> sample_pool;
+      if (!select_random_triangle(base1, base2, base3, sample_pool)) continue;
+      S4Pt b3d[4];
+      b3d[0] = P[base1]; b3d[1] = P[base2]; b3d[2] = P[base3];
+      const double x1 = b3d[0].p[0], y1 = b3d[0].p[1], z1 = b3d[0].p[2];
+      const double x2 = b3d[1].p[0], y2 = b3d[1].p[1], z2 = b3d[1].p[2];
+      const double x3 = b3d[2].p[0], y3 = b3d[2].p[1], z3 = b3d[2].p[2];
+      const float denom = (-x3 * y2 * z1 + x2 * y3 * z1 + x3 * y1 * z2 - x1 * y3 * z2 - x2 * y1 * z3 + x1 * y2 * z3);
+      if (denom != 0) {
+        const float A = (-y2 * z1 + y3 * z1 + y1 * z2 - y3 * z2 - y1 * z3 + y2 * z3) / denom;
+        const float B = (x2 * z1 - x3 * z1 - x1 * z2 + x3 * z2 + x1 * z3 - x2 * z3) / denom;
+        const float C = (-x2 * y1 + x3 * y1 + x1 * y2 - x3 * y2 - x1 * y3 + x2 * y3) / denom;
+        base4 = -1;
+        float best_distance = std::numeric_limits<float>::max();
+        const float too_small = std::pow(max_base_diameter * kBaseTooSmall, 2);
+        for (unsigned int i = 0; i < sample_pool.size(); ++i) {
+          const S4Pt &p = P[sample_pool[i]];
+          if (sqnorm(sub(p.p, b3d[0].p)) >= too_small && sqnorm(sub(p.p, b3d[1].p)) >= too_small && sqnorm(sub(p.p, b3d[2].p)) >= too_small) {
+            const float distance = std::abs(A * p.p[0] + B * p.p[1] + C * p.p[2] - 1.0);
+            if (distance < best_distance) { best_distance = distance; base4 = int(sample_pool[i]); }
+          }
+        }
+        if (base4 != -1) {
+          b3d[3] = P[base4];
+          int id[4] = {base1, base2, base3, base4};
+          float inv1, inv2;
+          if (try_quadrilateral(b3d, inv1, inv2, id)) {
+            t.base_ok = 1;
+            for (int k = 0; k < 4; ++k) { t.base[k] = id[k]; t.b[k] = b3d[k]; }
+            t.inv1 = inv1; t.inv2 = inv2;
+            return true;
+          }
+        }
+      }
+    }
+    return false;
+  }
+
+  void plan_trials() {
+    const int T = pl.opt.max_trials > 0 ? pl.opt.max_trials : 30;
+    pl.trials.assign(T, S4Trial());
+    if (pl.P.size() < 4 || pl.Q.size() < 4) return;
+    for (int t = 0; t < T; ++t) {
+      S4Trial &tr = pl.trials[t];
+      if (!select_quadrilateral(tr)) continue;
+      // generateCongruents (match4pcsBase.hpp:243-256)
+      tr.dist1 = norm(sub(tr.b[0].p, tr.b[1].p));
+      tr.dist2 = norm(sub(tr.b[2].p, tr.b[3].p));
+      tr.nangle1 = norm(sub(tr.b[0].n, tr.b[1].n));
+      tr.nangle2 = norm(sub(tr.b[2].n, tr.b[3].n));
+      // FindCongruentQuadrilaterals (FunctorSuper4pcs.h:161-163)
+      tr.alpha = dot(normalized(sub(tr.b[1].p, tr.b[0].p)), normalized(sub(tr.b[3].p, tr.b[2].p)));
+    }
+  }
+};
+
+}  // namespace
+
+extern "C" {
+
+void hop_default_s4pcs_options(hop_s4pcs_options *o) {
+  if (!o) return;
+  o->sample_size = 100; o->overlap = 0.2f; o->delta = 0.003f; o->dispersion = 0.5f; o->success_quadrilaterals = 10;
+  o->max_normal_difference = -1.f; o->max_color_distance = -1.f; o->max_trials = 0; o->random_seed = 0; o->keep_intermediates = 0;
+}
+
+void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const float *n2, int32_t *key) {
+  S4Pt a, b;
+  V3 na = normalized(V3{n1[0], n1[1], n1[2]}), nb = normalized(V3{n2[0], n2[1], n2[2]});  // Point3D::set_normal
+  for (int k = 0; k < 3; ++k) { a.p[k] = p1[k]; b.p[k] = p2[k]; a.n[k] = na[k]; b.n[k] = nb[k]; }
+  int k4[4];
+  compute_ppf(a, b, k4);
+  for (int k = 0; k < 4; ++k) key[k] = k4[k];
+}
+
+int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm,
+                          int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
+  if (!out) return HOP_EINVAL;
+  *out = nullptr;
+  if (!opt || nP < 0 || nQ < 0 || n_keys < 0 || (nP > 0 && (!P_xyz || !P_nrm)) || (nQ > 0 && (!Q_xyz || !Q_nrm)) || (n_keys > 0 && !ppf_keys) ||
+      !(opt->delta > 0.f) || opt->sample_size < 1)
+    return HOP_EINVAL;
+  hop_s4pcs_plan *pl = new hop_s4pcs_plan();
+  pl->opt = *opt;
+  Planner planner(*pl);
+  for (int i = 0; i < n_keys; ++i) {
+    const int k[4] = {ppf_keys[4 * i], ppf_keys[4 * i + 1], ppf_keys[4 * i + 2], ppf_keys[4 * i + 3]};
+    if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) planner.keys.insert(pack_key(k));
+  }
+  planner.init(P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ);
+  planner.plan_trials();
+  *out = pl;
+  return HOP_OK;
+}
+
+void hop_s4pcs_plan_destroy(hop_s4pcs_plan *plan) { delete plan; }
+
+int hop_s4pcs_plan_sizes(const hop_s4pcs_plan *plan, int32_t *sizes) {
+  if (!plan || !sizes) return HOP_EINVAL;
+  sizes[0] = (int32_t)plan->P.size(); sizes[1] = (int32_t)plan->Q.size(); sizes[2] = (int32_t)plan->trials.size();
+  sizes[3] = (int32_t)(plan->pairs.size() / 2); sizes[4] = (int32_t)(plan->quads.size() / 4); sizes[5] = plan->trials_executed;
+  return HOP_OK;
+}
+
+int hop_s4pcs_plan_get(const hop_s4pcs_plan *plan, float *Pc, float *Qc, int32_t *q_ids, float *centroids, float *misc, int32_t *trial_i,
+                       float *trial_f) {
+  if (!plan) return HOP_EINVAL;
+  if (Pc) for (size_t i = 0; i < plan->P.size(); ++i) for (int k = 0; k < 3; ++k) Pc[3 * i + k] = plan->P[i].p[k];
+  if (Qc) for (size_t i = 0; i < plan->Q.size(); ++i) for (int k = 0; k < 3; ++k) Qc[3 * i + k] = plan->Q[i].p[k];
+  if (q_ids) std::memcpy(q_ids, plan->q_ids.data(), sizeof(int32_t) * plan->q_ids.size());
+  if (centroids) for (int k = 0; k < 3; ++k) { centroids[k] = plan->centroid_P[k]; centroids[3 + k] = plan->centroid_Q[k]; }
+  if (misc) { misc[0] = plan->diameter; misc[1] = plan->ratio; }
+  for (size_t t = 0; t < plan->trials.size(); ++t) {
+    const S4Trial &tr = plan->trials[t];
+    if (trial_i) { trial_i[5 * t] = tr.base_ok; for (int k = 0; k < 4; ++k) trial_i[5 * t + 1 + k] = tr.base[k]; }
+    if (trial_f) { trial_f[4 * t] = tr.inv1; trial_f[4 * t + 1] = tr.inv2; trial_f[4 * t + 2] = tr.dist1; trial_f[4 * t + 3] = tr.dist2; }
+  }
+  return HOP_OK;
+}
+
+int hop_s4pcs_plan_intermediates(const hop_s4pcs_plan *plan, int32_t *trial_ranges, int32_t *pairs, int32_t *quads) {
+  if (!plan) return HOP_EINVAL;
+  if (trial_ranges) std::memcpy(trial_ranges, plan->trial_ranges.data(), sizeof(int32_t) * plan->trial_ranges.size());
+  if (pairs) std::memcpy(pairs, plan->pairs.data(), sizeof(int32_t) * plan->pairs.size());
+  if (quads) std::memcpy(quads, plan->quads.data(), sizeof(int32_t) * plan->quads.size());
+  return HOP_OK;
+}
+
+}  // extern "C"

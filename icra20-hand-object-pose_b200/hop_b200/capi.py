@@ -40,6 +40,13 @@ class FingerParams(C.Structure):
                 ("outter_pt_dist_weight", C.c_float)]
 
 
+class S4pcsOptions(C.Structure):
+    """hop_s4pcs_options: what PoseEstimator::runSuper4pcs sets (PoseEstimator.cpp:66-73)."""
+    _fields_ = [("sample_size", C.c_int32), ("overlap", C.c_float), ("delta", C.c_float), ("dispersion", C.c_float),
+                ("success_quadrilaterals", C.c_int32), ("max_normal_difference", C.c_float), ("max_color_distance", C.c_float),
+                ("max_trials", C.c_int32), ("random_seed", C.c_uint32), ("keep_intermediates", C.c_int32)]
+
+
 class PoseRec(C.Structure):
     _fields_ = [("pose", C.c_float * 16), ("score", C.c_float), ("id", C.c_int32), ("frame", C.c_int32), ("pad", C.c_int32)]
 
@@ -116,6 +123,17 @@ def load_library():
     L.hop_lcp_score_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(LcpParams), C.c_int, _vp]
     L.hop_verify_lcp.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp, _vp, _vp]
     L.hop_verify_lcp_dev.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, C.c_int, _vp, _vp, C.c_float, _vp, _vp, _vp, _vp]
+    L.hop_default_s4pcs_options.argtypes = [C.POINTER(S4pcsOptions)]
+    L.hop_default_s4pcs_options.restype = None
+    L.hop_s4pcs_plan_create.argtypes = [_vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(S4pcsOptions), C.POINTER(_vp)]
+    L.hop_s4pcs_plan_destroy.argtypes = [_vp]
+    L.hop_s4pcs_plan_destroy.restype = None
+    L.hop_s4pcs_plan_sizes.argtypes = [_vp, _vp]
+    L.hop_s4pcs_plan_get.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp]
+    L.hop_s4pcs_plan_intermediates.argtypes = [_vp, _vp, _vp, _vp]
+    L.hop_compute_ppf.argtypes = [_vp, _vp, _vp, _vp, _vp]
+    L.hop_compute_ppf.restype = None
+    L.hop_super4pcs_run.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp]
     L.hop_hand_overlap.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, C.c_int, _vp, _vp]
     L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
@@ -147,6 +165,70 @@ def poses_to_colmajor(poses):
 
 def colmajor_to_poses(flat):
     return np.asarray(flat, dtype=np.float32).reshape(-1, 4, 4).transpose(0, 2, 1).copy()
+
+
+def s4pcs_options(**kw):
+    o = S4pcsOptions()
+    load_library().hop_default_s4pcs_options(C.byref(o))
+    for k, v in kw.items():
+        setattr(o, k, v)
+    return o
+
+
+def compute_ppf(p1, n1, p2, n2):
+    """gr::computePPF of one point pair (host function of libhop): 4-int key."""
+    key = np.zeros(4, np.int32)
+    a = [np.ascontiguousarray(v, np.float32) for v in (p1, n1, p2, n2)]
+    load_library().hop_compute_ppf(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(key))
+    return key
+
+
+class S4pcsPlan:
+    """hop_s4pcs_plan*: the host-side plan of one Super4PCS registration (sampling + all bases); no GPU needed."""
+
+    def __init__(self, P_xyz, P_nrm, P_prob, Q_xyz, Q_nrm, ppf_keys, options=None):
+        self.L = load_library()
+        self.options = options or s4pcs_options()
+        P_xyz, P_nrm, Q_xyz, Q_nrm = _f32(P_xyz, 3), _f32(P_nrm, 3), _f32(Q_xyz, 3), _f32(Q_nrm, 3)
+        prob = None if P_prob is None else _f32(P_prob)
+        keys = np.ascontiguousarray(ppf_keys, np.int32).reshape(-1, 4)
+        h = _vp()
+        rc = self.L.hop_s4pcs_plan_create(_ptr(P_xyz), _ptr(P_nrm), _ptr(prob), len(P_xyz), _ptr(Q_xyz), _ptr(Q_nrm), len(Q_xyz), _ptr(keys),
+                                          len(keys), C.byref(self.options), C.byref(h))
+        if rc != 0:
+            raise HopError(f"hop_s4pcs_plan_create failed ({rc})")
+        self.h = h
+
+    def sizes(self):
+        s = np.zeros(6, np.int32)
+        self.L.hop_s4pcs_plan_sizes(self.h, _ptr(s))
+        return dict(nP=int(s[0]), nQ=int(s[1]), trials=int(s[2]), pairs=int(s[3]), quads=int(s[4]), trials_executed=int(s[5]))
+
+    def get(self):
+        z = self.sizes()
+        Pc, Qc = np.zeros((z["nP"], 3), np.float32), np.zeros((z["nQ"], 3), np.float32)
+        q_ids, cen, misc = np.zeros(z["nQ"], np.int32), np.zeros(6, np.float32), np.zeros(2, np.float32)
+        ti, tf = np.zeros((z["trials"], 5), np.int32), np.zeros((z["trials"], 4), np.float32)
+        self.L.hop_s4pcs_plan_get(self.h, _ptr(Pc), _ptr(Qc), _ptr(q_ids), _ptr(cen), _ptr(misc), _ptr(ti), _ptr(tf))
+        return dict(Pc=Pc, Qc=Qc, q_ids=q_ids, centroid_P=cen[:3].copy(), centroid_Q=cen[3:].copy(), diameter=float(misc[0]),
+                    ratio=float(misc[1]), base_ok=ti[:, 0].copy(), bases=ti[:, 1:].copy(), inv=tf[:, :2].copy(), dist=tf[:, 2:].copy())
+
+    def intermediates(self):
+        z = self.sizes()
+        tr, pairs, quads = np.zeros((z["trials"], 6), np.int32), np.zeros((z["pairs"], 2), np.int32), np.zeros((z["quads"], 4), np.int32)
+        self.L.hop_s4pcs_plan_intermediates(self.h, _ptr(tr), _ptr(pairs), _ptr(quads))
+        return tr, pairs, quads
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.hop_s4pcs_plan_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 class Cloud:
@@ -319,6 +401,15 @@ class Context:
         self._check(self.L.hop_verify_lcp(self.h, P_centered.handle, _ptr(Q), len(Q), _ptr(bases), len(bases), _ptr(quads), _ptr(qt), M,
                                           _ptr(cP), _ptr(cQ), delta, _ptr(poses), _ptr(lcp), _ptr(valid), _ptr(hp), _ptr(hl), C.byref(n)))
         return colmajor_to_poses(poses), lcp, valid, colmajor_to_poses(hp[: n.value]), hl[: n.value]
+
+    def super4pcs_run(self, plan, capacity=20000):
+        """Device part of a planned registration.  Returns (poses (n,4,4) model -> scene, lcp (n,)) in (trial, quad) order."""
+        poses = np.zeros((capacity, 16), np.float32)
+        lcp = np.zeros(capacity, np.float32)
+        n = C.c_int32(0)
+        self._check(self.L.hop_super4pcs_run(self.h, plan.h, _ptr(poses), _ptr(lcp), capacity, C.byref(n)))
+        k = min(int(n.value), capacity)
+        return colmajor_to_poses(poses[:k]), lcp[:k].copy()
 
     def hand_overlap(self, finger, scene_hand, scene_noswivel, params, thetas, scene_normals=None):
         """K1: cost[s] = objFuncPSO(thetas[s]) for S joint angles (radians); returns (cost (S,) float64, arg-min index)."""

@@ -161,6 +161,52 @@ int hop_verify_lcp_dev(hop_ctx *ctx, hop_cloud *P_centered, const float *d_Q, in
                        const int32_t *d_quads, const int32_t *d_quad_trial, int M, const float *centroid_P,
                        const float *centroid_Q, float delta, float *d_poses, float *d_lcp, int32_t *d_valid, int32_t *d_n_valid);
 
+/* ---- Super4PCS global registration: PoseEstimator::runSuper4pcs -> pcl::Super4PCS::align ------------------------------ */
+/* the options PoseEstimator::runSuper4pcs sets (PoseEstimator.cpp:66-73; config_autodataset.yaml:133-140) */
+typedef struct hop_s4pcs_options {
+  int32_t sample_size;            /* super4pcs_sample_size (100): points kept of the model Q */
+  float overlap;                  /* super4pcs_overlap (0.2); only configures the (unused) terminate threshold */
+  float delta;                    /* super4pcs_delta (0.003) */
+  float dispersion;               /* super4pcs_dispersion (0.5): sampling weights are multiplied by it once a point is used */
+  int32_t success_quadrilaterals; /* super4pcs_success_quadrilaterals (10) */
+  float max_normal_difference;    /* super4pcs_max_normal_difference (-1 = off) */
+  float max_color_distance;       /* super4pcs_max_color_distance (-1 = off; colours are not carried on this path) */
+  int32_t max_trials;             /* 0 = the reference's effective 30 (congruentSetExplorationBase.hpp:77-100, SURVEY quick facts) */
+  uint32_t random_seed;           /* 0 = std::mt19937::default_seed (matchBase.h:103) */
+  int32_t keep_intermediates;     /* keep pair sets / quadrilaterals on the plan for inspection (tests) */
+} hop_s4pcs_options;
+void hop_default_s4pcs_options(hop_s4pcs_options *o);
+
+/* Host-side plan of one registration (no GPU needed): MatchBase::init (matchBase.hpp:382-462: first-hit voxel sampling
+ * of Q, std::shuffle, centring, diameter) and the RNG-driven base selection of EVERY trial (SelectQuadrilateral
+ * match4pcsBase.hpp:107-189, SelectRandomTriangle matchBase.hpp:111-212, TryQuadrilateral :50-101, computePPF
+ * matchBase.hpp:31-68).  Base selection never depends on what earlier trials found, so all trials are planned up front
+ * and the device then works on all of them at once.  ppf_keys: n_keys x 4 ints, the keys of the model's PPF table
+ * (only membership is ever queried).  P = scene (target), Q = model (source). */
+typedef struct hop_s4pcs_plan hop_s4pcs_plan;
+int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz,
+                          const float *Q_nrm, int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt,
+                          hop_s4pcs_plan **out);
+void hop_s4pcs_plan_destroy(hop_s4pcs_plan *plan);
+/* sizes: [0] nP [1] sampled nQ [2] trials planned [3] pairs kept [4] quadrilaterals kept [5] trials executed */
+int hop_s4pcs_plan_sizes(const hop_s4pcs_plan *plan, int32_t *sizes);
+/* any pointer may be NULL.  Pc/Qc: centred clouds (n x 3); q_ids: index of each sampled Q point in the input Q;
+ * centroids: 6 floats (P then Q); misc: [0] diameter [1] unit-cube ratio; trial_i: T x 5 (base found, base[4] into P);
+ * trial_f: T x 4 (invariant1, invariant2, distance1, distance2) */
+int hop_s4pcs_plan_get(const hop_s4pcs_plan *plan, float *Pc, float *Qc, int32_t *q_ids, float *centroids, float *misc,
+                       int32_t *trial_i, float *trial_f);
+/* after hop_super4pcs_run with keep_intermediates: trial_ranges T x 6 (pairs1 begin,end, pairs2 begin,end, quads begin,end),
+ * pairs n x 2, quads m x 4 (indices into the sampled Q) */
+int hop_s4pcs_plan_intermediates(const hop_s4pcs_plan *plan, int32_t *trial_ranges, int32_t *pairs, int32_t *quads);
+/* gr::computePPF for one pair (exposed for tests): key = 4 ints */
+void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const float *n2, int32_t *key);
+
+/* The device part of a planned registration: pair extraction (K2a), congruent-set search (K2b) and verification (K3) of
+ * all trials, stopping like Perform_N_steps (:129-194) after success_quadrilaterals successful trials.  hyp_poses
+ * (capacity x 16, column-major, model -> scene) / hyp_lcp: every congruent quadrilateral with LCP > 0, in (trial,
+ * quadrilateral) order; *n_hyp = how many there are (may exceed capacity: the first `capacity` are written). */
+int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_poses, float *hyp_lcp, int capacity, int32_t *n_hyp);
+
 /* ---- K1: hand-state overlap objective (the function the reference's swarm minimises) ------------------------------- */
 #define HOP_MAX_FINGER_BINS 32
 /* Everything objFuncPSO reads from optim::ArgPasser / the YAML (Hand.cpp:10-178), flattened.  Matrices column-major. */

@@ -84,6 +84,9 @@ def ref():
             _ref.hop_ref_s4pcs_get.argtypes = [_f32p, _f32p, _i32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p]
             _ref.hop_ref_ppf_pairs.argtypes = [_f32p, _f32p, C.c_int, _i32p]
             _ref.hop_ref_s4pcs_get_quads.argtypes = [_i32p, _f32p, _f32p]
+            _ref.hop_ref_s4pcs_num_pairs.restype = C.c_int
+            _ref.hop_ref_s4pcs_get_trials.argtypes = [_i32p, _f32p, _i32p]
+            _ref.hop_ref_compute_ppf.argtypes = [_f32p, _f32p, _f32p, _f32p, _i32p]
     return _ref
 
 
@@ -130,7 +133,12 @@ def ref_super4pcs(P, Pn, Pprob, Q, Qn, ppf_keys, **opts):
     R.hop_ref_s4pcs_get(poses, lcp, trials, quads, Pc, Pcn, Qc, Qcn, cen, misc)
     q_ok = np.zeros(max(M, 1), np.int32); q_rms = np.zeros(max(M, 1), np.float32); q_lcp = np.zeros(max(M, 1), np.float32)
     R.hop_ref_s4pcs_get_quads(q_ok, q_rms, q_lcp)
-    return dict(quad_ok=q_ok[:M], quad_rms=q_rms[:M], quad_lcp=q_lcp[:M], poses=colmajor_to_poses(poses[:H]), lcp=lcp[:H], trials=trials[:T], quads=quads[:M], Pc=Pc, Pn=Pcn, Qc=Qc, Qn=Qcn,
+    npairs = R.hop_ref_s4pcs_num_pairs()
+    t_i = np.zeros((max(T, 1), 9), np.int32); t_f = np.zeros((max(T, 1), 4), np.float32); pairs = np.zeros((max(npairs, 1), 2), np.int32)
+    R.hop_ref_s4pcs_get_trials(t_i, t_f, pairs)
+    extra = dict(base_ok=t_i[:T, 0].copy(), bases_all=t_i[:T, 1:5].copy(), pair_ranges=t_i[:T, 5:9].copy(), inv=t_f[:T, :2].copy(),
+                 dist=t_f[:T, 2:].copy(), pairs=pairs[:npairs])
+    return dict(**extra, quad_ok=q_ok[:M], quad_rms=q_rms[:M], quad_lcp=q_lcp[:M], poses=colmajor_to_poses(poses[:H]), lcp=lcp[:H], trials=trials[:T], quads=quads[:M], Pc=Pc, Pn=Pcn, Qc=Qc, Qn=Qcn,
                 centroid_P=cen[:3].copy(), centroid_Q=cen[3:].copy(), diameter=float(misc[0]), delta=o.delta)
 
 
@@ -272,3 +280,9 @@ def finger_property(xyz, num_division, params):
     bbox = np.zeros(6, np.float32)
     lib().hop_oracle_finger_property(_c(xyz), len(xyz), num_division, C.addressof(params), bbox)
     return bbox
+
+
+def ref_compute_ppf(p1, n1, p2, n2):
+    key = np.zeros(4, np.int32)
+    ref().hop_ref_compute_ppf(_c(p1), _c(n1), _c(p2), _c(n2), key)
+    return key

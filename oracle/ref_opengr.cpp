@@ -42,6 +42,10 @@ struct TrialRecord {
   int ok;              // generateCongruents succeeded
   int quad_begin, quad_end;
   int hyp_begin, hyp_end;
+  // from the restated generateCongruents (match4pcsBase.hpp:207-281): what SelectQuadrilateral and the two ExtractPairs returned
+  int base_ok = 0;     // SelectQuadrilateral succeeded
+  float inv1 = 0, inv2 = 0, dist1 = 0, dist2 = 0;
+  int pairs1_begin = 0, pairs1_end = 0, pairs2_begin = 0, pairs2_end = 0;
 };
 
 class Matcher : public MatcherBase {
@@ -52,6 +56,30 @@ class Matcher : public MatcherBase {
   // per quadrilateral, from the reference's own ComputeRigidTransformation / Verify called the way TryCongruentSet does
   std::vector<float> quad_rms, quad_lcp;
   std::vector<int> quad_ok;
+  std::vector<std::pair<int, int>> all_pairs;  // pairs1 then pairs2 of every trial (see TrialRecord)
+
+  // generateCongruents (match4pcsBase.hpp:207-281) restated call for call so the intermediate results can be recorded;
+  // SelectQuadrilateral, ExtractPairs and FindCongruentQuadrilaterals themselves run unmodified.
+  bool generateCongruentsRecorded(CongruentBaseType &base, Set &congruent_quads, TrialRecord &tr) {
+    Scalar invariant1, invariant2;
+    if (!this->SelectQuadrilateral(invariant1, invariant2, base[0], base[1], base[2], base[3])) return false;
+    tr.base_ok = 1; tr.base = base; tr.inv1 = invariant1; tr.inv2 = invariant2;
+    const auto &b0 = this->base_3D_[0]; const auto &b1 = this->base_3D_[1];
+    const auto &b2 = this->base_3D_[2]; const auto &b3 = this->base_3D_[3];
+    const Scalar distance1 = (b0.pos() - b1.pos()).norm();
+    const Scalar distance2 = (b2.pos() - b3.pos()).norm();
+    tr.dist1 = distance1; tr.dist2 = distance2;
+    std::vector<std::pair<int, int>> pairs1, pairs2;
+    const Scalar normal_angle1 = (b0.normal() - b1.normal()).norm();
+    const Scalar normal_angle2 = (b2.normal() - b3.normal()).norm();
+    this->fun_.ExtractPairs(distance1, normal_angle1, this->distance_factor * this->options_.delta, 0, 1, pairs1);
+    this->fun_.ExtractPairs(distance2, normal_angle2, this->distance_factor * this->options_.delta, 2, 3, pairs2);
+    tr.pairs1_begin = (int)all_pairs.size(); all_pairs.insert(all_pairs.end(), pairs1.begin(), pairs1.end()); tr.pairs1_end = (int)all_pairs.size();
+    tr.pairs2_begin = (int)all_pairs.size(); all_pairs.insert(all_pairs.end(), pairs2.begin(), pairs2.end()); tr.pairs2_end = (int)all_pairs.size();
+    if (pairs1.size() == 0 || pairs2.size() == 0) return false;
+    return this->fun_.FindCongruentQuadrilaterals(invariant1, invariant2, this->distance_factor * this->options_.delta,
+                                                  this->distance_factor * this->options_.delta, pairs1, pairs2, &congruent_quads);
+  }
 
   void evalQuads(const CongruentBaseType &base, const Set &set) {
     Coordinates references;
@@ -89,7 +117,7 @@ class Matcher : public MatcherBase {
       tr.hyp_begin = tr.hyp_end = (int)this->_pose_hypo.size();
       CongruentBaseType base;
       Set congruent;
-      tr.ok = this->generateCongruents(base, congruent) ? 1 : 0;  // TryOneBase (:201-216)
+      tr.ok = this->generateCongruentsRecorded(base, congruent, tr) ? 1 : 0;  // TryOneBase (:201-216)
       if (tr.ok) {
         ++successes;
         tr.base = base;
@@ -203,6 +231,21 @@ void hop_ref_s4pcs_get(float *poses, float *lcp, int32_t *trials, int32_t *quads
   Eigen::Vector3f cp = m.centroidP(), cq = m.centroidQ();
   for (int k = 0; k < 3; ++k) { centroids[k] = cp[k]; centroids[3 + k] = cq[k]; }
   misc[0] = m.diameter();
+}
+
+// per trial (T x 9 ints): base_ok, base[4], pairs1_begin, pairs1_end, pairs2_begin, pairs2_end; (T x 4 floats): inv1, inv2, dist1, dist2;
+// pairs: n_pairs x 2 ints (hop_ref_s4pcs_num_pairs of them)
+int hop_ref_s4pcs_num_pairs() { return g_last ? (int)g_last->all_pairs.size() : 0; }
+void hop_ref_s4pcs_get_trials(int32_t *ti, float *tf, int32_t *pairs) {
+  if (!g_last) return;
+  for (size_t i = 0; i < g_last->trials.size(); ++i) {
+    const TrialRecord &t = g_last->trials[i];
+    int32_t *r = ti + 9 * i;
+    r[0] = t.base_ok; for (int k = 0; k < 4; ++k) r[1 + k] = t.base[k];
+    r[5] = t.pairs1_begin; r[6] = t.pairs1_end; r[7] = t.pairs2_begin; r[8] = t.pairs2_end;
+    tf[4 * i] = t.inv1; tf[4 * i + 1] = t.inv2; tf[4 * i + 2] = t.dist1; tf[4 * i + 3] = t.dist2;
+  }
+  for (size_t i = 0; i < g_last->all_pairs.size(); ++i) { pairs[2 * i] = g_last->all_pairs[i].first; pairs[2 * i + 1] = g_last->all_pairs[i].second; }
 }
 
 // per quadrilateral: ok flag, rms, lcp (0 when gated out)

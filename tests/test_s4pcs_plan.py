@@ -1,0 +1,74 @@
+"""CPU tests of the host side of Super4PCS (libhop's planner) against the reference's OWN compiled matcher (oracle/_ref):
+sampling, centring, diameter, and -- through the replayed std::mt19937 / std::discrete_distribution streams -- the base
+and invariants of every trial must be bit-identical."""
+import numpy as np
+import pytest
+
+from hop_b200 import capi, synth
+from oracle import cpu_oracle as O
+
+needs_ref = pytest.mark.skipif(O.ref() is None or not hasattr(O.ref(), "hop_ref_s4pcs_get_trials"), reason="oracle/_ref (compiled OpenGR) not built")
+
+
+@needs_ref
+def test_compute_ppf_matches_reference():
+    rng = np.random.default_rng(0)
+    for _ in range(2000):
+        p1, p2 = rng.normal(0, 0.03, 3).astype(np.float32), rng.normal(0, 0.03, 3).astype(np.float32)
+        n1, n2 = rng.normal(size=3).astype(np.float32), rng.normal(size=3).astype(np.float32)
+        assert np.array_equal(capi.compute_ppf(p1, n1, p2, n2), O.ref_compute_ppf(p1, n1, p2, n2))
+    # ties go up, truncation first: 2.5 mm -> bin 5, 2.4999 mm -> bin 0
+    z, n = np.zeros(3, np.float32), np.array([0, 0, 1], np.float32)
+    assert capi.compute_ppf(z, n, np.array([0.0035, 0, 0], np.float32), n)[0] == 5
+    assert capi.compute_ppf(z, n, np.array([0.0024, 0, 0], np.float32), n)[0] == 0
+
+
+@needs_ref
+@pytest.mark.parametrize("name,seed,nq,ns", [("ellipse", 2, 400, 500), ("cuboid", 3, 400, 500), ("tless", 4, 1500, 800), ("cylinder", 5, 90, 300)])
+def test_plan_matches_compiled_reference(name, seed, nq, ns):
+    m, mn = synth.make_model(name, nq, seed=1)
+    keys = O.ref_ppf_keys(m[:400], mn[:400])
+    s, sn, conf, gt = synth.make_scene(name, ns, seed=seed)
+    r = O.ref_super4pcs(s, sn, conf, m, mn, keys)
+    plan = capi.S4pcsPlan(s, sn, conf, m, mn, keys)
+    g = plan.get()
+    assert np.array_equal(g["Qc"], r["Qc"]) and np.array_equal(g["Pc"], r["Pc"])          # sampling + shuffle + centring
+    assert np.array_equal(g["centroid_P"], r["centroid_P"]) and np.array_equal(g["centroid_Q"], r["centroid_Q"])
+    assert g["diameter"] == r["diameter"]
+    assert np.array_equal(m[g["q_ids"]] - g["centroid_Q"], g["Qc"])
+    T = len(r["base_ok"])                                                                   # the reference stops after 10 successes
+    assert T >= 5 and plan.sizes()["trials"] == 30
+    assert np.array_equal(g["base_ok"][:T], r["base_ok"])
+    ok = r["base_ok"].astype(bool)
+    assert ok.sum() >= 5
+    assert np.array_equal(g["bases"][:T][ok], r["bases_all"][ok])                           # RNG replay: same 4 points, same order
+    assert np.array_equal(g["inv"][:T][ok], r["inv"][ok]) and np.array_equal(g["dist"][:T][ok], r["dist"][ok])
+    plan.close()
+
+
+@needs_ref
+def test_plan_small_model_and_options():
+    """Q smaller than sample_size is used whole (matchBase.hpp:406-411); dispersion / trials / seed are honoured."""
+    m, mn = synth.make_model("ellipse", 80, seed=1)
+    keys = O.ref_ppf_keys(m, mn)
+    s, sn, conf, gt = synth.make_scene("ellipse", 300, seed=7)
+    r = O.ref_super4pcs(s, sn, conf, m, mn, keys, dispersion=0.8, success_quadrilaterals=4)
+    plan = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(dispersion=0.8, success_quadrilaterals=4, max_trials=12))
+    g = plan.get()
+    assert plan.sizes()["trials"] == 12 and len(g["Qc"]) == 80 and np.array_equal(g["q_ids"], np.arange(80))
+    T = min(len(r["base_ok"]), 12)
+    ok = r["base_ok"][:T].astype(bool)
+    assert np.array_equal(g["bases"][:T][ok], r["bases_all"][:T][ok]) and np.array_equal(g["inv"][:T][ok], r["inv"][:T][ok])
+    plan.close()
+
+
+def test_plan_degenerate_inputs():
+    m, mn = synth.make_model("ellipse", 50, seed=1)
+    s, sn, conf, gt = synth.make_scene("ellipse", 100, seed=2)
+    plan = capi.S4pcsPlan(s, sn, conf, m, mn, np.zeros((0, 4), np.int32))    # empty PPF table: no base can be found
+    g = plan.get()
+    assert not g["base_ok"].any()
+    plan.close()
+    plan = capi.S4pcsPlan(s[:3], sn[:3], conf[:3], m, mn, np.zeros((0, 4), np.int32))
+    assert not plan.get()["base_ok"].any()
+    plan.close()
