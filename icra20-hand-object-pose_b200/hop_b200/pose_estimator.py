@@ -34,6 +34,7 @@ class PoseEstimator:
         self.max_icp_candidates = 100  # PoseEstimator.cpp:241
         self._pose_hypos = []
         self._scene = self._model = self._model001 = None
+        self._scene_host = self._model_host = None     # host copies: the Super4PCS planner runs on the host
 
     # -- setCurScene (PoseEstimator.cpp:36-45): keeps the high-confidence scene (confidence >= thres)
     def setCurScene(self, scene_xyz, scene_nrm, confidence=None, high_confidence_thres=0.8):
@@ -42,6 +43,7 @@ class PoseEstimator:
         if confidence is not None:
             keep = np.asarray(confidence) >= high_confidence_thres
             scene_xyz, scene_nrm, confidence = scene_xyz[keep], scene_nrm[keep], np.asarray(confidence, np.float32)[keep]
+        self._scene_host = (scene_xyz, scene_nrm, confidence)
         if self._scene is None:
             self._scene = self.ctx.upload_cloud(scene_xyz, scene_nrm, confidence)
         else:
@@ -50,6 +52,7 @@ class PoseEstimator:
     def setModel(self, model_xyz, model_nrm, model001_xyz=None, model001_nrm=None):
         """_model (5 mm, ICP / Super4PCS) and _model001 (1 mm, scoring) (main_realdata_auto.cpp:33-38)."""
         self._model = self.ctx.upload_cloud(model_xyz, model_nrm)
+        self._model_host = (np.asarray(model_xyz, np.float32), np.asarray(model_nrm, np.float32))
         if model001_xyz is None:
             self._model001 = self._model
         else:
@@ -59,6 +62,24 @@ class PoseEstimator:
         poses = np.asarray(poses, np.float32).reshape(-1, 4, 4)
         scores = np.zeros(len(poses), np.float32) if scores is None else np.asarray(scores, np.float32)
         self._pose_hypos = [PoseHypo(poses[i].copy(), i, float(scores[i])) for i in range(len(poses))]
+
+    def runSuper4pcs(self, ppfs, **options):
+        """PoseEstimator::runSuper4pcs (PoseEstimator.cpp:62-100): source = _model, target = _scene_high_confidence; every
+        congruent quadrilateral with LCP > 0 becomes PoseHypo(pose, i, lcp).  ppfs: (n,4) int keys of the model's PPF table
+        (the reference passes the whole std::map; only key membership is ever used).  Returns False when nothing was found
+        (the caller prints "No pose found" and exits, main_realdata_auto.cpp:189-196)."""
+        from . import capi
+        if self._scene_host is None or self._model_host is None:
+            raise RuntimeError("runSuper4pcs needs setCurScene() and setModel() first")
+        sx, sn, sc = self._scene_host
+        mx, mn = self._model_host
+        plan = capi.S4pcsPlan(sx, sn, sc, mx, mn, ppfs, capi.s4pcs_options(**options))
+        try:
+            poses, lcp = self.ctx.super4pcs_run(plan)
+        finally:
+            plan.close()
+        self._pose_hypos = [PoseHypo(poses[i].copy(), i, float(lcp[i])) for i in range(len(poses))]
+        return len(self._pose_hypos) > 0
 
     def refineByICP(self):
         """Keeps the first min(N,100) hypotheses and replaces each pose by T_icp^-1 * pose (PoseEstimator.cpp:235-275)."""
