@@ -134,6 +134,7 @@ def load_library():
     L.hop_compute_ppf.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.hop_compute_ppf.restype = None
     L.hop_super4pcs_run.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp]
+    L.hop_cluster_poses.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
     L.hop_hand_overlap.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, C.c_int, _vp, _vp]
     L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
@@ -181,6 +182,21 @@ def compute_ppf(p1, n1, p2, n2):
     a = [np.ascontiguousarray(v, np.float32) for v in (p1, n1, p2, n2)]
     load_library().hop_compute_ppf(_ptr(a[0]), _ptr(a[1]), _ptr(a[2]), _ptr(a[3]), _ptr(key))
     return key
+
+
+def cluster_poses(poses, scores, angle_diff_deg, dist_diff, symmetry_deg=(360.0, 360.0, 360.0), ids=None):
+    """PoseEstimator::clusterPoses on the host (libhop, no GPU): returns the indices of the kept hypotheses in cluster order."""
+    flat = poses_to_colmajor(poses)
+    sc = _f32(scores)
+    n = len(flat)
+    idv = None if ids is None else np.ascontiguousarray(ids, np.int32)
+    sym = np.ascontiguousarray(symmetry_deg, np.float32)
+    keep = np.zeros(max(n, 1), np.int32)
+    nk = C.c_int32(0)
+    rc = load_library().hop_cluster_poses(_ptr(flat), _ptr(sc), _ptr(idv), n, angle_diff_deg, dist_diff, _ptr(sym), _ptr(keep), C.byref(nk))
+    if rc != 0:
+        raise HopError(f"hop_cluster_poses failed ({rc})")
+    return keep[: nk.value].copy()
 
 
 class S4pcsPlan:

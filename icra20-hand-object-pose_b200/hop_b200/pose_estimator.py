@@ -32,6 +32,8 @@ class PoseEstimator:
         self.lcp_dist = float(lcp.get("dist", 0.001))
         self.lcp_normal_angle = float(lcp.get("normal_angle", 10))
         self.max_icp_candidates = 100  # PoseEstimator.cpp:241
+        sym = cfg.get("object_symmetry", {}).get(cfg.get("model_name", ""), {})
+        self.object_symmetry = (float(sym.get("x", 360)), float(sym.get("y", 360)), float(sym.get("z", 360)))
         self._pose_hypos = []
         self._scene = self._model = self._model001 = None
         self._scene_host = self._model_host = None     # host copies: the Super4PCS planner runs on the host
@@ -80,6 +82,21 @@ class PoseEstimator:
             plan.close()
         self._pose_hypos = [PoseHypo(poses[i].copy(), i, float(lcp[i])) for i in range(len(poses))]
         return len(self._pose_hypos) > 0
+
+    def clusterPoses(self, angle_diff, dist_diff, assign_id=False):
+        """PoseEstimator::clusterPoses(angle_diff [deg], dist_diff [m], assign_id) (PoseEstimator.cpp:106-233): greedy
+        suppression in (lcp desc, id asc) order with the object's symmetry (object_symmetry.<model_name>.{x,y,z})."""
+        from . import capi
+        if not self._pose_hypos:
+            raise IndexError("clusterPoses on an empty hypothesis list (the reference reads hypo_tmp[0])")
+        poses = np.stack([h._pose for h in self._pose_hypos])
+        scores = np.array([h._lcp_score for h in self._pose_hypos], np.float32)
+        ids = np.array([h._id for h in self._pose_hypos], np.int32)
+        keep = capi.cluster_poses(poses, scores, angle_diff, dist_diff, self.object_symmetry, ids)
+        self._pose_hypos = [self._pose_hypos[k] for k in keep]
+        if assign_id:
+            for i, h in enumerate(self._pose_hypos):
+                h._id = i
 
     def refineByICP(self):
         """Keeps the first min(N,100) hypotheses and replaces each pose by T_icp^-1 * pose (PoseEstimator.cpp:235-275)."""

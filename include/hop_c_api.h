@@ -207,6 +207,14 @@ void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const fl
  * quadrilateral) order; *n_hyp = how many there are (may exceed capacity: the first `capacity` are written). */
 int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_poses, float *hyp_lcp, int capacity, int32_t *n_hyp);
 
+/* ---- pose clustering (host) ------------------------------------------------------------------------------------- */
+/* PoseEstimator::clusterPoses (PoseEstimator.cpp:106-233): sort by (score desc, id asc), keep a hypothesis when no kept one
+ * lies within dist_diff AND (all symmetry-folded ZYX Euler differences <= angle_diff OR the geodesic distance <=
+ * angle_diff).  poses n x 16 column-major; ids NULL = 0..n-1; symmetry_deg = object_symmetry.<model>.{x,y,z} (0 = free
+ * axis, negative = no folding).  keep_out (capacity n): indices of the kept hypotheses in cluster order. */
+int hop_cluster_poses(const float *poses, const float *scores, const int32_t *ids, int n, float angle_diff_deg, float dist_diff,
+                      const float *symmetry_deg, int32_t *keep_out, int32_t *n_keep);
+
 /* ---- K1: hand-state overlap objective (the function the reference's swarm minimises) ------------------------------- */
 #define HOP_MAX_FINGER_BINS 32
 /* Everything objFuncPSO reads from optim::ArgPasser / the YAML (Hand.cpp:10-178), flattened.  Matrices column-major. */

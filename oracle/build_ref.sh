@@ -23,5 +23,6 @@ if [ -f "$HERE/ref_opengr.cpp" ]; then
   SRCS="$SRCS $HERE/ref_opengr.cpp"
   INCS="-I$TMP -I$GR $INCS"
 fi
+if [ -f "$HERE/ref_cluster.cpp" ]; then SRCS="$SRCS $HERE/ref_cluster.cpp"; fi
 $CXX -std=c++17 -O2 -fopenmp -fPIC -shared -w $INCS -o "$HERE/_ref/libhop_ref.so" $SRCS
 echo "oracle: built $HERE/_ref/libhop_ref.so"

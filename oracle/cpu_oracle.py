@@ -76,6 +76,11 @@ def ref():
         _ref = C.CDLL(path)
         _ref.hop_ref_lm_point_to_plane.restype = C.c_int
         _ref.hop_ref_lm_point_to_plane.argtypes = [_f32p, _f32p, _f32p, C.c_int, _f32p, C.POINTER(C.c_int)]
+        if hasattr(_ref, "hop_ref_cluster_poses"):
+            _ref.hop_ref_cluster_poses.restype = C.c_int
+            _ref.hop_ref_cluster_poses.argtypes = [_f32p, _f32p, C.c_void_p, C.c_int, C.c_float, C.c_float,
+                                                   np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS"), _i32p]
+            _ref.hop_ref_euler_zyx.argtypes = [_f32p, _f32p]
         if hasattr(_ref, "hop_ref_s4pcs_run"):
             _ref.hop_ref_s4pcs_run.restype = C.c_int
             _ref.hop_ref_s4pcs_run.argtypes = [_f32p, _f32p, C.c_void_p, C.c_int, _f32p, _f32p, C.c_int, _i32p, C.c_int,
@@ -286,3 +291,14 @@ def ref_compute_ppf(p1, n1, p2, n2):
     key = np.zeros(4, np.int32)
     ref().hop_ref_compute_ppf(_c(p1), _c(n1), _c(p2), _c(n2), key)
     return key
+
+
+def ref_cluster_poses(poses, scores, angle_diff, dist_diff, symmetry_deg=(360.0, 360.0, 360.0), ids=None):
+    """clusterPoses restated on the reference tree's own Eigen (oracle/_ref/ref_cluster.cpp): kept indices in cluster order."""
+    flat = poses_to_colmajor(poses)
+    sc = _c(scores)
+    idv = None if ids is None else np.ascontiguousarray(ids, np.int32)
+    keep = np.zeros(max(len(flat), 1), np.int32)
+    n = ref().hop_ref_cluster_poses(flat, sc, None if idv is None else idv.ctypes.data_as(C.c_void_p), len(flat), angle_diff, dist_diff,
+                                    np.ascontiguousarray(symmetry_deg, np.float64), keep)
+    return keep[:n].copy()

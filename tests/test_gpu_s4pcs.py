@@ -90,3 +90,40 @@ def test_run_super4pcs_mirror_recovers_the_pose(ctx):
     assert len(est._pose_hypos) > 10 and [h._id for h in est._pose_hypos] == list(range(len(est._pose_hypos)))
     best = max(est._pose_hypos, key=lambda h: h._lcp_score)
     assert best._lcp_score >= 0.3
+
+
+@pytest.mark.parametrize("name,seed", [("cuboid", 3), ("ellipse", 2)])
+def test_full_pipeline_matches_the_reference_pipeline(ctx, name, seed):
+    """main_realdata_auto.cpp:187-204 through the host mirror: runSuper4pcs -> clusterPoses(30 deg, 15 mm, ids) -> refineByICP
+    -> clusterPoses(5 deg, 3 mm) -> selectBest, against the same chain built from the oracles (compiled OpenGR matcher,
+    Eigen-based clusterPoses, restated ICP / LCP).  The two Super4PCS lists hold the same hypotheses in a different order
+    inside a trial, so the final poses are compared within the north-star tolerance, not bit for bit."""
+    import hop_b200
+    m, mn = synth.make_model(name, 400, seed=1)
+    m001, mn001 = synth.make_model(name, 6000, seed=5)
+    keys = O.ref_ppf_keys(m, mn)
+    s, sn, conf, gt = synth.make_scene(name, 500, seed=seed, outlier_frac=0.05)
+    cfg = {"model_name": name, "object_symmetry": {name: {"x": 180, "y": 180, "z": 180}}}
+    sym = (180.0, 180.0, 180.0)
+    est = hop_b200.PoseEstimator(ctx, cfg)
+    est.setModel(m, mn, m001, mn001)
+    est.setCurScene(s, sn, conf)
+    assert est.runSuper4pcs(keys)
+    est.clusterPoses(30, 0.015, True)
+    est.refineByICP()
+    est.clusterPoses(5, 0.003, False)
+    best = est.selectBest()
+    # the reference chain
+    r = O.ref_super4pcs(s, sn, conf, m, mn, keys)
+    keep = O.ref_cluster_poses(r["poses"], r["lcp"], 30, 0.015, sym)
+    poses, lcp = r["poses"][keep][:100], r["lcp"][keep][:100]
+    refined, _, _ = O.refine_by_icp(s, sn, m, mn, poses)
+    keep2 = O.ref_cluster_poses(refined, lcp, 5, 0.003, sym, np.arange(len(refined), dtype=np.int32))
+    bi, sc = O.select_best(s, sn, m001, mn001, refined[keep2])
+    ref_best = refined[keep2][bi]
+    dt, dr = synth.pose_error(best._pose[None], ref_best[None])
+    egt, rgt = synth.pose_error(best._pose[None], gt[None])
+    egt_ref, rgt_ref = synth.pose_error(ref_best[None], gt[None])
+    # same winner within the north-star tolerance, or at least no worse against the ground truth than the reference's
+    assert (dt[0] <= 1e-3 and dr[0] <= 1.0) or (egt[0] <= egt_ref[0] + 5e-4), (dt, dr, egt, egt_ref)
+    assert abs(best._lcp_score - sc[bi]) <= 0.05 * max(sc[bi], 1.0) or best._lcp_score >= sc[bi]
