@@ -1,0 +1,114 @@
+#include "PoseEstimator.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+void PoseEstimator::check(int rc, const char *what) {
+  if (rc == HOP_OK) return;
+  fprintf(stderr, "%s failed (%d): %s\n", what, rc, hop_last_error(ctx));
+  exit(1);
+}
+
+PoseEstimator::PoseEstimator(ConfigParser *cfg1, const Cloud &model, const Cloud &model001, hop_ctx *c) : cfg(cfg1), ctx(c), _model(model), _model001(model001) {
+  check(hop_cloud_upload(ctx, _model.xyz.data(), _model.nrm.data(), nullptr, (int)_model.size(), &d_model), "upload model");
+  check(hop_cloud_upload(ctx, _model001.xyz.data(), _model001.nrm.data(), nullptr, (int)_model001.size(), &d_model001), "upload model001");
+}
+
+PoseEstimator::~PoseEstimator() {
+  hop_cloud_free(ctx, d_scene); hop_cloud_free(ctx, d_model); hop_cloud_free(ctx, d_model001);
+}
+
+void PoseEstimator::setCurScene(const Cloud &object_segment) {
+  const float thres = cfg->pose_estimator_high_confidence_thres;
+  _scene_high_confidence.clear();
+  for (size_t i = 0; i < object_segment.size(); ++i)
+    if (object_segment.conf[i] >= thres) _scene_high_confidence.push(&object_segment.xyz[3 * i], &object_segment.nrm[3 * i], object_segment.conf[i]);
+  const Cloud &s = _scene_high_confidence;
+  if (!d_scene) check(hop_cloud_upload(ctx, s.xyz.data(), s.nrm.data(), s.conf.data(), (int)s.size(), &d_scene), "upload scene");
+  else check(hop_cloud_update(ctx, d_scene, s.xyz.data(), s.nrm.data(), s.conf.data(), (int)s.size()), "update scene");
+}
+
+bool PoseEstimator::runSuper4pcs(const std::vector<int32_t> &ppf_keys) {
+  hop_s4pcs_options o;
+  hop_default_s4pcs_options(&o);
+  o.sample_size = (int)cfg->yml["super4pcs_sample_size"].as<float>(100.f);
+  o.overlap = cfg->yml["super4pcs_overlap"].as<float>(0.2f);
+  o.delta = cfg->yml["super4pcs_delta"].as<float>(0.003f);
+  o.dispersion = cfg->yml["super4pcs_dispersion"].as<float>(0.5f);
+  o.success_quadrilaterals = cfg->yml["super4pcs_success_quadrilaterals"].as<int>(10);
+  o.max_normal_difference = cfg->super4pcs_max_normal_difference;
+  o.max_color_distance = cfg->super4pcs_max_color_distance;
+  const Cloud &P = _scene_high_confidence;
+  hop_s4pcs_plan *plan = nullptr;
+  int rc = hop_s4pcs_plan_create(P.xyz.data(), P.nrm.data(), P.conf.data(), (int)P.size(), _model.xyz.data(), _model.nrm.data(), (int)_model.size(),
+                                 ppf_keys.data(), (int)(ppf_keys.size() / 4), &o, &plan);
+  if (rc != HOP_OK) { fprintf(stderr, "hop_s4pcs_plan_create failed (%d)\n", rc); return false; }
+  const int cap = cfg->b200_max_hypotheses;   // the reference reserves 20000 (super4pcs.h:134)
+  std::vector<float> poses(16 * (size_t)cap), lcp(cap);
+  int32_t n = 0;
+  rc = hop_super4pcs_run(ctx, plan, poses.data(), lcp.data(), cap, &n);
+  hop_s4pcs_plan_destroy(plan);
+  check(rc, "hop_super4pcs_run");
+  _pose_hypos.clear();
+  for (int i = 0; i < std::min<int>(n, cap); ++i) {
+    Mat4f T;
+    std::memcpy(T.data(), &poses[16 * (size_t)i], 64);
+    _pose_hypos.push_back(PoseHypo(T, i, lcp[i]));
+  }
+  return !_pose_hypos.empty();
+}
+
+void PoseEstimator::clusterPoses(float angle_diff, float dist_diff, bool assign_id) {
+  printf("num original candidates = %d\n", (int)_pose_hypos.size());
+  const int n = (int)_pose_hypos.size();
+  if (n == 0) return;
+  const std::string model_name = cfg->yml["model_name"].as<std::string>();
+  const miniyaml::Node &s = cfg->yml["object_symmetry"][model_name];
+  const float sym[3] = {s["x"].as<float>(360.f), s["y"].as<float>(360.f), s["z"].as<float>(360.f)};
+  printf("object symmetry: x=%f, y=%f, z=%f\n", sym[0] / 180 * M_PI, sym[1] / 180 * M_PI, sym[2] / 180 * M_PI);
+  std::vector<float> poses(16 * (size_t)n), scores(n);
+  std::vector<int32_t> ids(n), keep(n);
+  for (int i = 0; i < n; ++i) { std::memcpy(&poses[16 * (size_t)i], _pose_hypos[i]._pose.data(), 64); scores[i] = _pose_hypos[i]._lcp_score; ids[i] = _pose_hypos[i]._id; }
+  int32_t nk = 0;
+  check(hop_cluster_poses(poses.data(), scores.data(), ids.data(), n, angle_diff, dist_diff, sym, keep.data(), &nk), "hop_cluster_poses");
+  std::vector<PoseHypo> out;
+  for (int k = 0; k < nk; ++k) out.push_back(_pose_hypos[keep[k]]);
+  _pose_hypos.swap(out);
+  if (assign_id) for (size_t i = 0; i < _pose_hypos.size(); i++) _pose_hypos[i]._id = (int)i;
+  printf("num of pose clusters: %d\n", (int)_pose_hypos.size());
+}
+
+void PoseEstimator::refineByICP() {
+  const size_t n = std::min<size_t>(_pose_hypos.size(), 100);   // PoseEstimator.cpp:241
+  _pose_hypos.resize(n);
+  if (n == 0) return;
+  std::vector<float> poses(16 * n);
+  for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
+  hop_icp_params p;
+  hop_default_icp_params(&p);   // 10 iterations, abs MSE 1e-6 (Utils.cpp:207-208; PoseEstimator.cpp:266)
+  p.angle_deg = cfg->yml["icp_angle_thres"].as<float>(45.f);
+  p.max_dist = cfg->yml["icp_dist_thres"].as<float>(0.01f);
+  check(hop_icp_refine(ctx, d_scene, d_model, poses.data(), (int)n, &p, nullptr, nullptr), "hop_icp_refine");
+  for (size_t i = 0; i < n; ++i) std::memcpy(_pose_hypos[i]._pose.data(), &poses[16 * i], 64);
+}
+
+void PoseEstimator::selectBest(PoseHypo &best_hypo) {
+  const size_t n = _pose_hypos.size();
+  if (n == 0) return;
+  std::vector<float> poses(16 * n), scores(n);
+  for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
+  hop_lcp_params p;
+  hop_default_lcp_params(&p);
+  p.dist = cfg->yml["lcp"]["dist"].as<float>(0.001f);
+  p.angle_deg = cfg->yml["lcp"]["normal_angle"].as<float>(10.f);
+  check(hop_lcp_score(ctx, d_scene, d_model001, poses.data(), (int)n, &p, 0, scores.data()), "hop_lcp_score");
+  float best_lcp = 0;
+  best_hypo = _pose_hypos[0];
+  for (size_t i = 0; i < n; ++i) {
+    _pose_hypos[i]._lcp_score = scores[i];
+    if (scores[i] > best_lcp) { best_lcp = scores[i]; best_hypo = _pose_hypos[i]; }
+  }
+  printf("best hypo id=%d, lcp=%f\n", best_hypo._id, best_lcp);
+}

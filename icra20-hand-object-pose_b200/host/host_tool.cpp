@@ -1,0 +1,73 @@
+// host_tool -- small command-line probes of the host-side pieces, used by tests/test_host_cpp.py (no GPU needed):
+//   host_tool yaml <file> <key[.key...]>        prints a scalar or a space-separated sequence
+//   host_tool config <file>                     prints the matrices ConfigParser derives
+//   host_tool png <file>                        width height sum min max of a 16-bit PNG
+//   host_tool voxel <in.ply> <leaf> <out.ply>   pcl::VoxelGrid restatement
+//   host_tool depthcloud <png> fx fy cx cy <out.ply>
+//   host_tool normals <in.ply> <radius> <out.ply>
+#include <cstdio>
+#include <cstdlib>
+#include <iostream>
+#include <sstream>
+
+#include "ConfigParser.h"
+#include "cloud.h"
+
+int main(int argc, char **argv) {
+  if (argc < 3) return 2;
+  const std::string cmd = argv[1];
+  try {
+    if (cmd == "yaml" && argc >= 4) {
+      miniyaml::Node n = miniyaml::LoadFile(argv[2]);
+      const miniyaml::Node *cur = &n;
+      std::stringstream ss(argv[3]);
+      std::string part;
+      while (std::getline(ss, part, '.')) cur = &(*cur)[part];
+      if (cur->kind == miniyaml::Node::Scalar) std::cout << cur->scalar << "\n";
+      else if (cur->kind == miniyaml::Node::Sequence) { for (size_t i = 0; i < cur->size(); ++i) std::cout << (i ? " " : "") << (*cur)[i].scalar; std::cout << "\n"; }
+      else if (cur->kind == miniyaml::Node::Map) { for (auto &k : cur->keys()) std::cout << k << " "; std::cout << "\n"; }
+      else { std::cout << "<undefined>\n"; return 3; }
+      return 0;
+    }
+    if (cmd == "config") {
+      ConfigParser cfg(argv[2]);
+      std::cout.precision(9);
+      std::cout << "cam1_in_leftarm\n" << cfg.cam1_in_leftarm << "\nhandbase_in_palm\n" << cfg.handbase_in_palm << "\npalm_in_baselink\n" << cfg.palm_in_baselink
+                << "\nleftarm_in_base\n" << cfg.leftarm_in_base << "\n";
+      const Mat4f hic = cfg.cam1_in_leftarm.inverse() * (cfg.leftarm_in_base.inverse() * cfg.palm_in_baselink * cfg.handbase_in_palm);
+      std::cout << "handbase_in_cam\n" << hic << "\n";
+      std::cout << "K " << cfg.cam_intrinsic(0, 0) << " " << cfg.cam_intrinsic(1, 1) << " " << cfg.cam_intrinsic(0, 2) << " " << cfg.cam_intrinsic(1, 2) << "\n";
+      return 0;
+    }
+    if (cmd == "png") {
+      std::vector<uint16_t> pix; int w, h; std::string err;
+      if (!readPNG16(argv[2], pix, w, h, &err)) { std::cout << err << "\n"; return 3; }
+      unsigned long long sum = 0; uint16_t mn = 65535, mx = 0;
+      for (uint16_t v : pix) { sum += v; mn = std::min(mn, v); mx = std::max(mx, v); }
+      std::cout << w << " " << h << " " << sum << " " << mn << " " << mx << "\n";
+      return 0;
+    }
+    if (cmd == "voxel" && argc >= 5) {
+      Cloud c, o; std::string err;
+      if (!loadPLYFile(argv[2], c, &err)) { std::cout << err << "\n"; return 3; }
+      downsamplePointCloud(c, o, (float)atof(argv[3]));
+      return savePLYFile(argv[4], o) ? 0 : 3;
+    }
+    if (cmd == "depthcloud" && argc >= 8) {
+      std::vector<float> d; int w, h;
+      readDepthImage(d, w, h, argv[2]);
+      Mat3f K; for (int i = 0; i < 9; ++i) K.m[i] = 0; K(0, 0) = atof(argv[3]); K(1, 1) = atof(argv[4]); K(0, 2) = atof(argv[5]); K(1, 2) = atof(argv[6]); K(2, 2) = 1;
+      Cloud c; convert3dOrganized(d, w, h, K, c);
+      passThrough(c, c, 2, 0.1f, 2.0f);
+      return savePLYFile(argv[7], c) ? 0 : 3;
+    }
+    if (cmd == "normals" && argc >= 5) {
+      Cloud c; std::string err;
+      if (!loadPLYFile(argv[2], c, &err)) { std::cout << err << "\n"; return 3; }
+      const float o[3] = {0, 0, 0};
+      estimateNormals(c, (float)atof(argv[3]), o);
+      return savePLYFile(argv[4], c) ? 0 : 3;
+    }
+  } catch (const std::exception &e) { std::cout << "error: " << e.what() << "\n"; return 4; }
+  return 2;
+}

