@@ -227,7 +227,7 @@ int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans) {
 void hop_default_icp_params(hop_icp_params *p) {
   if (!p) return;
   p->max_iter = 10; p->angle_deg = 45.f; p->max_dist = 0.01f; p->abs_mse_eps = 1e-6; p->mode = 0; p->solver = 0;
-  p->team_warps = 0; p->reserved = 0;
+  p->team_warps = 0; p->pipeline = 0;
 }
 void hop_default_lcp_params(hop_lcp_params *p) {
   if (!p) return;
@@ -283,7 +283,7 @@ int hop_cloud_free(hop_ctx *ctx, hop_cloud *cloud) {
   if (!cloud) return HOP_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   for (NNGridHost *g : cloud->grids) hop_free_nn_grid(g);
-  cudaFree(cloud->d_pw); cudaFree(cloud->d_nv); cudaFree(cloud->d_stage);
+  cudaFree(cloud->d_pw); cudaFree(cloud->d_nv); cudaFree(cloud->d_stage); cudaFree(cloud->d_pw_q); cudaFree(cloud->d_nv_q);
   delete cloud;
   return HOP_OK;
 }
@@ -300,7 +300,9 @@ int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *
   NNGridHost *G = nullptr;
   int rc = hop_get_nn_grid(ctx, model, params->max_dist, 0.f, &G);
   if (rc != HOP_OK) return rc;
-  return hop_launch_icp(ctx, scene->dev(), model->dev(), G->dev, d_poses_inout, H, *params, d_iters_out, d_converged_out);
+  rc = hop_cloud_query_order(ctx, scene);   // the scene is only iterated: walk it along a Morton curve
+  if (rc != HOP_OK) return rc;
+  return hop_launch_icp(ctx, scene->dev_query(), model->dev(), G->dev, d_poses_inout, H, *params, d_iters_out, d_converged_out);
 }
 
 int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *poses_inout, int H, const hop_icp_params *params,
@@ -340,7 +342,10 @@ int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const fl
   // the reciprocal neighbour is at most `dist` away (see lcp_score_kernel); a little head room for rounding
   rc = hop_get_nn_grid(ctx, scene, params->dist * 1.01f, 0.f, &Gs);
   if (rc != HOP_OK) return rc;
-  return hop_launch_lcp(ctx, scene->dev(), model->dev(), Gm->dev, Gs->dev, d_poses, H, *params, use_weights, d_scores_out);
+  rc = hop_cloud_query_order(ctx, scene);
+  if (rc != HOP_OK) return rc;
+  // iterate the Morton-ordered copy; the reciprocal neighbour's normal is looked up by ORIGINAL index (scene grid)
+  return hop_launch_lcp(ctx, scene->dev_query(), scene->d_nv, model->dev(), Gm->dev, Gs->dev, d_poses, H, *params, use_weights, d_scores_out);
 }
 
 int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *poses, int H, const hop_lcp_params *params,

@@ -189,7 +189,13 @@ struct hop_cloud {
   uint64_t version = 0;  // bumped by hop_cloud_update; grids are rebuilt when stale
   std::vector<NNGridHost *> grids;
   std::vector<uint64_t> grid_version;
+  // query-order copy: the same points sorted along a Morton curve, so that the 32 lanes of a warp iterating the cloud fall
+  // into the same few voxels of the structure they query (built lazily by hop_cloud_query_order, nn_grid.cu)
+  float4 *d_pw_q = nullptr, *d_nv_q = nullptr;
+  int q_capacity = 0;
+  uint64_t q_version = ~0ull;
   CloudDev dev() const { return CloudDev{d_pw, d_nv, n, n_padded}; }
+  CloudDev dev_query() const { return CloudDev{d_pw_q, d_nv_q, n, n_padded}; }
 };
 
 // per-kernel timing with CUDA events on the launching stream (hop_profile_*): bench.py's roofline source
@@ -246,10 +252,11 @@ struct ProfScope {
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
 int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
 void hop_free_nn_grid(NNGridHost *g);
+int hop_cloud_query_order(hop_ctx *ctx, hop_cloud *cloud);  // (re)builds d_pw_q / d_nv_q when stale
 // implemented in icp_lcp.cu
 int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, float *d_poses, int H,
                    const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv);
-int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &model_grid,
+int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_by_index, const CloudDev &model, const NNGridDev &model_grid,
                    const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
                    float *d_scores);
 // implemented in select.cu

@@ -22,6 +22,7 @@
 //   * No tensor cores: these are gathers and small reductions, not dense contractions.
 #include <cfloat>
 #include <cmath>
+#include <utility>
 
 #include "hop_common.cuh"
 
@@ -520,11 +521,197 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// K4 fused: the whole ICP of a hypothesis inside one CTA, no correspondence records in global memory.
+//   Persistent CTAs pull hypotheses from a queue.  Per ICP iteration and per chunk of FUSED_CHUNK scene points:
+//     phase A  every thread finds the correspondences of its points (same code path as icp_correspond_kernel) and leaves
+//              the 32-byte records in SHARED memory;
+//     phase B  the 8 warps split the 13x13 moment matrix four ways (24 of its 91 + 2 entries each) and the chunk two
+//              ways, so a thread carries 24 accumulators across all chunks instead of 93 -- registers stay low enough
+//              for three CTAs per SM, which is what hides the gather latency of phase A;
+//   then one shuffle reduction, the small solve + PCL's convergence rule on warp 0, and the new transform goes back to all
+//   threads through shared memory.  A hypothesis that converges frees its CTA for the next one at once; there is no
+//   per-iteration launch, no inter-CTA dependency and nothing but the pose is written to HBM.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int FUSED_THREADS = 256;
+constexpr int FUSED_CHUNK = 2048;
+constexpr int SLICE = 24;
+
+__host__ __device__ constexpr int tri_row(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i; }
+__host__ __device__ constexpr int tri_col(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i + k; }
+
+template <int S, int E>
+__device__ __forceinline__ void acc_one(float (&acc)[SLICE], const float (&v)[13], float d2) {
+  constexpr int k = SLICE * S + E;
+  if constexpr (k < 91) acc[E] = fmaf(v[tri_row(k)], v[tri_col(k)], acc[E]);
+  else if constexpr (k == 91) acc[E] += d2;
+  else if constexpr (k == 92) acc[E] += 1.f;
+}
+template <int S, int... E>
+__device__ __forceinline__ void acc_slice(float (&acc)[SLICE], const float (&v)[13], float d2, std::integer_sequence<int, E...>) {
+  (acc_one<S, E>(acc, v, d2), ...);
+}
+
+template <int S>
+__device__ __forceinline__ void accumulate_chunk(float (&acc)[SLICE], const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
+  for (int i = begin + lane; i < end; i += 32) {
+    const float4 q1 = rec1[i];
+    if (!(q1.w >= 0.f)) continue;
+    const float4 q0 = rec0[i];
+    float v[13];
+    v[0] = q1.x * q0.x; v[1] = q1.x * q0.y; v[2] = q1.x * q0.z;
+    v[3] = q1.y * q0.x; v[4] = q1.y * q0.y; v[5] = q1.y * q0.z;
+    v[6] = q1.z * q0.x; v[7] = q1.z * q0.y; v[8] = q1.z * q0.z;
+    v[9] = q1.x; v[10] = q1.y; v[11] = q1.z;
+    v[12] = q0.w;
+    acc_slice<S>(acc, v, q1.w, std::make_integer_sequence<int, SLICE>());
+  }
+}
+
+struct FusedArgs {
+  CloudDev scene;
+  const float4 *model_nv;
+  NNGridDev grid;
+  float *poses;
+  int H;
+  int32_t *iters_out, *conv_out;
+  int *counter;
+  float cos_thr, max_d2;
+  int max_iter;
+  double abs_mse_eps;
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a) {
+  extern __shared__ __align__(16) float4 fused_smem[];
+  float4 *rec0 = fused_smem, *rec1 = fused_smem + FUSED_CHUNK;
+  __shared__ __align__(16) float s_sums[2][96];
+  __shared__ __align__(16) float s_tot[96];
+  __shared__ float s_X[12];
+  __shared__ int s_ctl[2];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = warp & 3, half = warp >> 2;
+  for (;;) {
+    if (tid == 0) s_ctl[0] = atomicAdd(a.counter, 1);
+    __syncthreads();
+    const int h = s_ctl[0];
+    if (h >= a.H) break;
+    Rigid X = rigid_inverse(rigid_load_colmajor(a.poses + 16 * (size_t)h));
+    // convergence state (meaningful on warp 0; uniform across its lanes)
+    Rigid inc_prev;
+#pragma unroll
+    for (int e = 0; e < 9; ++e) inc_prev.r[e] = (e % 4 == 0) ? 1.f : 0.f;
+    inc_prev.t[0] = inc_prev.t[1] = inc_prev.t[2] = 0.f;
+    double prev_mse = DBL_MAX;
+    int iters = 0;
+    bool finished = false, converged = false;
+    while (!finished) {
+      float acc[SLICE];
+#pragma unroll
+      for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
+      for (int c0 = 0; c0 < a.scene.n_padded; c0 += FUSED_CHUNK) {
+        const int cnt = min(FUSED_CHUNK, a.scene.n_padded - c0);
+        // ---- phase A: correspondences of this chunk -> shared memory ----
+        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+          const float4 sp = __ldg(&a.scene.pw[c0 + i]);
+          const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
+          float bd; float4 bp;
+          const int j = nn_query(a.grid, p.x, p.y, p.z, bd, bp);
+          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, -1.f);
+          if (j >= 0 && bd <= a.max_d2) {
+            const float4 sn = __ldg(&a.scene.nv[c0 + i]);
+            const float4 mn = __ldg(&a.model_nv[j]);
+            const float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
+            const float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
+            if (dot >= a.cos_thr) {
+              r0 = make_float4(p.x, p.y, p.z, mn.x * (p.x - bp.x) + mn.y * (p.y - bp.y) + mn.z * (p.z - bp.z));
+              r1 = make_float4(mn.x, mn.y, mn.z, bd);
+            }
+          }
+          rec0[i] = r0;
+          rec1[i] = r1;
+        }
+        __syncthreads();
+        // ---- phase B: this warp's slice of the moments over its half of the chunk ----
+        const int hb = half == 0 ? 0 : (cnt + 1) / 2, he = half == 0 ? (cnt + 1) / 2 : cnt;
+        switch (slice) {
+          case 0: accumulate_chunk<0>(acc, rec0, rec1, hb, he, lane); break;
+          case 1: accumulate_chunk<1>(acc, rec0, rec1, hb, he, lane); break;
+          case 2: accumulate_chunk<2>(acc, rec0, rec1, hb, he, lane); break;
+          default: accumulate_chunk<3>(acc, rec0, rec1, hb, he, lane); break;
+        }
+        __syncthreads();
+      }
+      // ---- reduce: lanes -> warp totals -> the two halves ----
+      float mine = 0.f;
+#pragma unroll
+      for (int e = 0; e < SLICE; ++e) {
+        const float tot = warp_sum(acc[e]);
+        if (lane == e) mine = tot;
+      }
+      if (lane < SLICE) s_sums[half][SLICE * slice + lane] = mine;
+      __syncthreads();
+      if (warp == 0) {
+        for (int k = lane; k < 96; k += 32) s_tot[k] = s_sums[0][k] + s_sums[1][k];
+        __syncwarp();
+        const float *sums = s_tot;
+        const float cnt_f = sums[92], sumd2 = sums[91];
+        const int cnt = (int)(cnt_f + 0.5f);
+        if (cnt < 3) {
+          finished = true;  // "Not enough correspondences": hasConverged() false -> pose unchanged
+        } else {
+          Rigid inc;
+          if (cnt >= 6) solve_exact(sums, nullptr, lane, inc.r, inc.t);
+          else if (cnt >= 4) {  // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
+#pragma unroll
+            for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
+            inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
+          } else inc = inc_prev;  // PCL's LM returns early with < 4 correspondences, transformation_ keeps its old value
+          X = rigid_compose(inc, X);
+          inc_prev = inc;
+          ++iters;
+          if (iters >= a.max_iter) converged = true;
+          else {
+            const double cos_angle = 0.5 * ((double)inc.r[0] + (double)inc.r[4] + (double)inc.r[8] - 1.0);
+            const double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
+            if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
+            else {
+              const double mse = (double)sumd2 / (double)cnt;
+              if (fabs(mse - prev_mse) < a.abs_mse_eps) converged = true;
+              prev_mse = mse;
+            }
+          }
+          finished = converged;
+        }
+        if (lane == 0) {
+#pragma unroll
+          for (int e = 0; e < 9; ++e) s_X[e] = X.r[e];
+          s_X[9] = X.t[0]; s_X[10] = X.t[1]; s_X[11] = X.t[2];
+          s_ctl[1] = (finished ? 1 : 0) | (converged ? 2 : 0);
+        }
+      }
+      __syncthreads();
+#pragma unroll
+      for (int e = 0; e < 9; ++e) X.r[e] = s_X[e];
+      X.t[0] = s_X[9]; X.t[1] = s_X[10]; X.t[2] = s_X[11];
+      finished = (s_ctl[1] & 1) != 0;
+      converged = (s_ctl[1] & 2) != 0;
+    }
+    if (tid == 0) {
+      if (converged) { const Rigid P = rigid_inverse(X); rigid_store_colmajor(P, a.poses + 16 * (size_t)h); }
+      if (a.iters_out) a.iters_out[h] = iters;
+      if (a.conv_out) a.conv_out[h] = converged ? 1 : 0;
+    }
+    __syncthreads();  // s_ctl / s_X are reused by the next hypothesis
+  }
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // K5
 // ------------------------------------------------------------------------------------------------------------
 struct LcpArgs {
-  CloudDev scene;
+  CloudDev scene;               // iteration order (Morton)
+  const float4 *scene_nv_idx;   // normals addressed by the scene grid's (original) point index
   const float4 *model_nv;
   NNGridDev mgrid;   // model grid (radius >= dist)
   NNGridDev sgrid;   // scene grid (radius >= dist), for the reciprocal term
@@ -571,7 +758,7 @@ __global__ void __launch_bounds__(TILE) lcp_score_kernel(LcpArgs a) {
         if (k >= 0) {
           if (!a.use_normal) score += w;
           else {
-            const float4 s2 = __ldg(&a.scene.nv[k]);
+            const float4 s2 = __ldg(&a.scene_nv_idx[k]);
             const float dot = (s2.x * mr.x + s2.y * mr.y + s2.z * mr.z) * s2.w;
             if (dot > a.cos_thr) score += a.use_dot ? dot * (1.f - sqrtf(ed) * a.inv_dist) * w : w;
           }
@@ -633,6 +820,26 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
   if (H <= 0) return HOP_OK;
   if (p.mode != 0) { ctx->err = "hop_icp_refine: mode 1 (point-to-point) not built yet"; return HOP_EINVAL; }
   const int max_iter = p.max_iter < 1 ? 1 : p.max_iter;
+  if (p.solver == 0 && p.pipeline != 1) {
+    // fused pipeline (default for the parity solver): one persistent launch for the whole batch
+    FusedArgs f;
+    f.scene = scene; f.model_nv = model.nv; f.grid = grid; f.poses = d_poses; f.H = H; f.iters_out = d_iters; f.conv_out = d_conv;
+    f.counter = ctx->d_counter;
+    f.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
+    f.max_d2 = p.max_dist * p.max_dist; f.max_iter = max_iter; f.abs_mse_eps = p.abs_mse_eps;
+    const size_t smem = 2 * (size_t)FUSED_CHUNK * sizeof(float4);
+    static bool attr_set = false;
+    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(icp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+    HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
+    const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * 3);
+    {
+      ProfScope ps(ctx, HOP_PROF_ICP_CORRESPOND);
+      icp_fused_kernel<<<grid_ctas, FUSED_THREADS, smem, ctx->stream>>>(f);
+    }
+    ctx->launches += 1;
+    HOP_CUDA(ctx, cudaGetLastError());
+    return HOP_OK;
+  }
   const int n_tiles = scene.n_padded / TILE;
   // hypotheses per batch: bounded by the correspondence-record buffer (32 B per hypothesis x scene point)
   const size_t rec_per_h = (size_t)scene.n_padded * 32;
@@ -683,13 +890,13 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
   return HOP_OK;
 }
 
-int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &model_grid,
+int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_by_index, const CloudDev &model, const NNGridDev &model_grid,
                    const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
                    float *d_scores) {
   if (H <= 0) return HOP_OK;
   const int n_tiles = scene.n_padded / TILE;
   LcpArgs a;
-  a.scene = scene; a.model_nv = model.nv; a.mgrid = model_grid; a.sgrid = scene_grid; a.H = H;
+  a.scene = scene; a.scene_nv_idx = scene_nv_by_index; a.model_nv = model.nv; a.mgrid = model_grid; a.sgrid = scene_grid; a.H = H;
   a.dist = p.dist; a.inv_dist = 1.f / p.dist; a.dist2 = p.dist * p.dist;
   a.cos_thr = (float)cos((double)p.angle_deg / 180.0 * M_PI);
   a.use_normal = p.use_normal; a.use_dot = p.use_dot_score; a.use_recip = p.use_reciprocal; a.use_weights = use_weights;

@@ -16,6 +16,7 @@
 // of entries even for voxels a centimetre away from the surface, where (2) alone admits hundreds.
 // Built by scatter from the points (three passes: nearest-to-centre, count, fill), with no host synchronisation:
 // the candidate buffer is sized from a geometric upper bound and the fill pass is bounds-checked.
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include <algorithm>
@@ -144,7 +145,73 @@ __global__ void nn_query_kernel(NNGridDev g, const float *__restrict__ q, int nq
   d2[i] = j >= 0 ? bd : 3.0e38f;
 }
 
+// ---- Morton (Z-curve) query order ------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned int spread10(unsigned int v) {  // 10 bits -> every third bit
+  v &= 0x3ffu;
+  v = (v | (v << 16)) & 0x030000ffu;
+  v = (v | (v << 8)) & 0x0300f00fu;
+  v = (v | (v << 4)) & 0x030c30c3u;
+  v = (v | (v << 2)) & 0x09249249u;
+  return v;
+}
+
+__global__ void morton_keys_kernel(const float4 *__restrict__ pw, int n, int n_padded, float ox, float oy, float oz, float scale,
+                                   unsigned int *__restrict__ keys, int *__restrict__ idx) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_padded) return;
+  unsigned int k = 0xffffffffu;  // padding and non-finite points go last
+  if (i < n) {
+    const float4 p = pw[i];
+    if (fabsf(p.x) < 1e20f && fabsf(p.y) < 1e20f && fabsf(p.z) < 1e20f) {
+      const unsigned int x = (unsigned int)fminf(fmaxf((p.x - ox) * scale, 0.f), 1023.f), y = (unsigned int)fminf(fmaxf((p.y - oy) * scale, 0.f), 1023.f),
+                         z = (unsigned int)fminf(fmaxf((p.z - oz) * scale, 0.f), 1023.f);
+      k = spread10(x) | (spread10(y) << 1) | (spread10(z) << 2);
+    } else k = 0xfffffffeu;
+  }
+  keys[i] = k;
+  idx[i] = i;
+}
+
+__global__ void gather_cloud_kernel(const float4 *__restrict__ pw, const float4 *__restrict__ nv, const int *__restrict__ idx, int n_padded,
+                                    float4 *__restrict__ pw_q, float4 *__restrict__ nv_q) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_padded) return;
+  const int j = idx[i];
+  pw_q[i] = pw[j];
+  nv_q[i] = nv[j];
+}
+
 }  // namespace
+
+int hop_cloud_query_order(hop_ctx *ctx, hop_cloud *c) {
+  if (c->q_version == c->version && c->d_pw_q) return HOP_OK;
+  if (c->n_padded <= 0) return HOP_OK;
+  if (c->q_capacity < c->n_padded) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->d_pw_q); cudaFree(c->d_nv_q);
+    c->d_pw_q = c->d_nv_q = nullptr;
+    HOP_CUDA(ctx, cudaMalloc(&c->d_pw_q, sizeof(float4) * (size_t)c->n_padded));
+    HOP_CUDA(ctx, cudaMalloc(&c->d_nv_q, sizeof(float4) * (size_t)c->n_padded));
+    c->q_capacity = c->n_padded;
+  }
+  const int np = c->n_padded;
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, (unsigned int *)nullptr, (unsigned int *)nullptr, (int *)nullptr, (int *)nullptr, np, 0, 32, ctx->stream);
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t arr = up(sizeof(int) * (size_t)np);
+  char *base = (char *)ctx->ensure_scratch(4 * arr + sort_bytes + 256);
+  if (!base) { ctx->err = "hop_cloud_query_order: scratch allocation failed"; return HOP_ENOMEM; }
+  unsigned int *k_in = (unsigned int *)base, *k_out = (unsigned int *)(base + arr);
+  int *i_in = (int *)(base + 2 * arr), *i_out = (int *)(base + 3 * arr);
+  const float ext = std::max(std::max(c->bbox_max[0] - c->bbox_min[0], c->bbox_max[1] - c->bbox_min[1]), std::max(c->bbox_max[2] - c->bbox_min[2], 1e-9f));
+  morton_keys_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(c->d_pw, c->n, np, c->bbox_min[0], c->bbox_min[1], c->bbox_min[2], 1023.f / ext, k_in, i_in);
+  cub::DeviceRadixSort::SortPairs(base + 4 * arr, sort_bytes, k_in, k_out, i_in, i_out, np, 0, 32, ctx->stream);
+  gather_cloud_kernel<<<(np + 255) / 256, 256, 0, ctx->stream>>>(c->d_pw, c->d_nv, i_out, np, c->d_pw_q, c->d_nv_q);
+  ctx->launches += 3;
+  HOP_CUDA(ctx, cudaGetLastError());
+  c->q_version = c->version;
+  return HOP_OK;
+}
 
 void hop_free_nn_grid(NNGridHost *g) {
   if (!g) return;

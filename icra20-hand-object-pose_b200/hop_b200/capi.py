@@ -19,7 +19,7 @@ class HopError(RuntimeError):
 
 class IcpParams(C.Structure):
     _fields_ = [("max_iter", C.c_int32), ("angle_deg", C.c_float), ("max_dist", C.c_float), ("abs_mse_eps", C.c_double),
-                ("mode", C.c_int32), ("solver", C.c_int32), ("team_warps", C.c_int32), ("reserved", C.c_int32)]
+                ("mode", C.c_int32), ("solver", C.c_int32), ("team_warps", C.c_int32), ("pipeline", C.c_int32)]
 
 
 class LcpParams(C.Structure):

@@ -65,7 +65,8 @@ typedef struct hop_icp_params {
   int32_t solver;       /* mode 0 only: 0 = exact nonlinear least squares per iteration (what PCL's LM converges to);
                                          1 = one Gauss-Newton step per iteration (fewer registers, not the parity path) */
   int32_t team_warps;   /* warps cooperating on one hypothesis: 0 = auto, else 1/2/4/8 */
-  int32_t reserved;
+  int32_t pipeline;     /* mode 0, solver 0: 0 = fused (whole ICP of a hypothesis in one CTA, one launch per batch); 1 = two
+                           launches per iteration (correspondence records through global memory) */
 } hop_icp_params;
 
 /* Utils::computeLCP arguments (Utils.cpp:372) */

@@ -105,9 +105,9 @@ def test_lcp_edge_cases(ctx):
 
 
 # ---------------------------------------------------------------------------------------------- K4: ICP refinement
-def _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=0, max_iter=10):
+def _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=0, max_iter=10, pipeline=0):
     scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
-    p = ctx.icp_params(max_iter=max_iter, team_warps=team)
+    p = ctx.icp_params(max_iter=max_iter, team_warps=team, pipeline=pipeline)
     got, it, cv = ctx.icp_refine(scene, model, hyp, p)
     ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp, max_iter=max_iter)
     scene.free(); model.free()
@@ -135,10 +135,22 @@ def test_icp_refine_matches_oracle_in_the_convergence_basin(ctx, name, ns, nm):
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8])
 def test_icp_refine_team_sizes_agree(ctx, team):
+    """the two-launch pipeline (pipeline=1) with every warp-team size"""
     m, mn, s, sn, conf, gt, hyp = _case("ellipse", 520, 2500, 40, seed=61, random_frac=0.0)
-    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=team)
+    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=team, pipeline=1)
     assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.95
     assert np.array_equal(cv, rcv)
+
+
+@pytest.mark.parametrize("name,ns,nm", [("ellipse", 600, 3000), ("cuboid", 2100, 5000)])
+def test_icp_pipelines_agree(ctx, name, ns, nm):
+    """fused (default) and two-launch pipelines: same convergence flags and iteration counts, poses equal to rounding"""
+    m, mn, s, sn, conf, gt, hyp = _case(name, ns, nm, 64, seed=55, random_frac=0.1)
+    a = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, pipeline=0)
+    b = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, pipeline=1)
+    assert np.array_equal(a[2], b[2]) and np.mean(a[1] == b[1]) >= 0.95
+    dt, dr = synth.pose_error(a[0], b[0])
+    assert np.percentile(dt, 95) < 2e-5 and np.percentile(dr, 95) < 0.02
 
 
 def test_icp_refine_semantics_of_the_reference(ctx):
