@@ -8,7 +8,7 @@ One "step" = one depth frame: the frame's scene cloud and its batch of H pose hy
 `value`  : hypotheses/s with the scene cloud and hypotheses already resident in HBM (CUDA events, L2 flushed between steps).
 `e2e`    : the same through the host-buffer C ABI (hop_cloud_update + hop_icp_refine + hop_lcp_score: what
            PoseEstimator::refineByICP()/selectBest() call), pinned host inputs, H2D + D2H inside the timed region.
-`roofline`: dominant kernel (icp_refine_kernel): algorithmic bytes / its own CUDA-event time vs the measured HBM peak.
+`roofline`: dominant kernel (icp_fused_kernel): algorithmic bytes / its own CUDA-event time vs the measured HBM peak.
 `cpu_baseline`: the oracle port of the reference algorithm on this box's host cores (bounded sample), rank 0, N=1.
 Multi-GPU: frames are independent -> every rank processes its own frames (weak scaling), one NCCL all-gather of the
 per-rank winner records per step.
@@ -30,9 +30,9 @@ sys.path.insert(0, os.path.join(ROOT, "icra20-hand-object-pose_b200"))
 METRIC = "pose hypotheses/sec (ICP-refined + LCP-scored)"
 UNIT = "hypotheses/s"
 TOPK = 16
-# dram__bytes_read.sum + dram__bytes_write.sum of one icp_correspond_kernel launch (first ICP iteration, C2), from the
-# ncu --set full capture summarised in profiles/r01_ncu_icp_correspond_kernel_C2.txt (10.14 MB read + 10.29 MB written)
-TRAFFIC_BYTES_PER_LAUNCH = 20430592
+# dram__bytes_read.sum + dram__bytes_write.sum of one icp_fused_kernel launch (a whole C2 batch), from the ncu --set full
+# capture summarised in profiles/r01_ncu_icp_fused_kernel_C2.txt; other workloads were not captured -> null
+TRAFFIC_BYTES_PER_LAUNCH = {"C2": 30083840}
 N_FRAMES = 4  # distinct synthetic frames cycled through the steps
 
 
@@ -202,7 +202,8 @@ def main():
         torch.cuda.synchronize()
 
     # ---- warm-up ----
-    for w in range(max(args.warmup, 3)):
+    # (every distinct frame is visited at least once: a frame's first visit allocates its scene grid)
+    for w in range(max(args.warmup, N_FRAMES)):
         step_value(w % N_FRAMES)
     barrier()
 
@@ -263,7 +264,7 @@ def main():
         ctx._check(ctx.L.hop_lcp_score(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(lcp_p), 0, ptr(p["scores"])))
         return int(np.argmax(p["scores"]))  # selectBest's arg-max on the host, like the reference
 
-    for w in range(3):
+    for w in range(max(args.warmup, N_FRAMES)):
         step_e2e(w % N_FRAMES)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -295,9 +296,10 @@ def main():
         peak = float(peaks.get("hbm_gbs", 6650.0))
         value = world * H * args.steps / (total_ms * 1e-3)
         e2e_value = world * H * args.steps / (e2e_ms * 1e-3)
-        # Dominant kernel: icp_correspond_kernel (one launch per ICP iteration).  ALGORITHMIC bytes: every
-        # executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B per point.
-        corr_ms, corr_n = prof["icp_correspond"]
+        # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
+        # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
+        fused = args.solver == 0
+        corr_ms, corr_n = prof["icp_fused" if fused else "icp_correspond"]
         corr_bytes = float(iters_sum) * 32.0 * (ns + nm)
         achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
         icp_ms = float(np.mean(t_icp))
@@ -314,8 +316,8 @@ def main():
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "icp_correspond_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH,
+            "roofline": {"bound": "hbm", "kernel": "icp_fused_kernel" if fused else "icp_correspond_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if fused else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": corr_bytes / max(corr_n, 1), "kernel_ms_per_launch": corr_ms / max(corr_n, 1),
                          "launches": int(corr_n),

@@ -21,6 +21,8 @@
 //   * K5 is one flat launch (thread per hypothesis x scene point) + a fixed-order reduction of the tile partials.
 //   * No tensor cores: these are gathers and small reductions, not dense contractions.
 #include <cfloat>
+#include <cstdio>
+#include <cstdlib>
 #include <cmath>
 #include <utility>
 
@@ -534,8 +536,6 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
 //   threads through shared memory.  A hypothesis that converges frees its CTA for the next one at once; there is no
 //   per-iteration launch, no inter-CTA dependency and nothing but the pose is written to HBM.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int FUSED_THREADS = 256;
-constexpr int FUSED_CHUNK = 2048;
 constexpr int SLICE = 24;
 
 __host__ __device__ constexpr int tri_row(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i; }
@@ -580,17 +580,26 @@ struct FusedArgs {
   float cos_thr, max_d2;
   int max_iter;
   double abs_mse_eps;
+  long long *prof;   // null, or 6 cycle counters (HOP_FUSED_PROFILE=1)
 };
 
-__global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a) {
+// THREADS per CTA (a multiple of 128: four moment slices x THREADS/128 parts of the chunk), CHUNK scene points whose
+// records sit in shared memory at a time, PROF = with the cycle accounting, MINB resident CTAs per SM.
+template <int THREADS, int CHUNK, bool PROF, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
+  constexpr int PARTS = THREADS / 128;
   extern __shared__ __align__(16) float4 fused_smem[];
-  float4 *rec0 = fused_smem, *rec1 = fused_smem + FUSED_CHUNK;
-  __shared__ __align__(16) float s_sums[2][96];
+  float4 *rec0 = fused_smem, *rec1 = fused_smem + CHUNK;
+  __shared__ __align__(16) float s_sums[PARTS][96];
   __shared__ __align__(16) float s_tot[96];
   __shared__ float s_X[12];
   __shared__ int s_ctl[2];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slice = warp & 3, half = warp >> 2;
+  const int slice = warp & 3, part = warp >> 2;
+  // optional cycle accounting (thread 0 of every CTA): [0] phase A  [1] wait at the barrier after A  [2] phase B + barrier
+  // [3] reduction + solve + broadcast  [4] passes  [5] whole CTA life time
+  long long t_acc[6] = {0, 0, 0, 0, 0, 0}, t_mark = 0;
+  const long long t_start = PROF ? clock64() : 0;
   for (;;) {
     if (tid == 0) s_ctl[0] = atomicAdd(a.counter, 1);
     __syncthreads();
@@ -609,10 +618,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a
       float acc[SLICE];
 #pragma unroll
       for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
-      for (int c0 = 0; c0 < a.scene.n_padded; c0 += FUSED_CHUNK) {
-        const int cnt = min(FUSED_CHUNK, a.scene.n_padded - c0);
+      for (int c0 = 0; c0 < a.scene.n_padded; c0 += CHUNK) {
+        const int cnt = min(CHUNK, a.scene.n_padded - c0);
         // ---- phase A: correspondences of this chunk -> shared memory ----
-        for (int i = tid; i < cnt; i += FUSED_THREADS) {
+        if (PROF && tid == 0) t_mark = clock64();
+        for (int i = tid; i < cnt; i += THREADS) {
           const float4 sp = __ldg(&a.scene.pw[c0 + i]);
           const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
           float bd; float4 bp;
@@ -631,9 +641,12 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a
           rec0[i] = r0;
           rec1[i] = r1;
         }
+        if (PROF && tid == 0) { const long long t = clock64(); t_acc[0] += t - t_mark; t_mark = t; }
         __syncthreads();
-        // ---- phase B: this warp's slice of the moments over its half of the chunk ----
-        const int hb = half == 0 ? 0 : (cnt + 1) / 2, he = half == 0 ? (cnt + 1) / 2 : cnt;
+        if (PROF && tid == 0) { const long long t = clock64(); t_acc[1] += t - t_mark; t_mark = t; }
+        // ---- phase B: this warp's slice of the moments over its part of the chunk ----
+        const int per = (cnt + PARTS - 1) / PARTS;
+        const int hb = min(part * per, cnt), he = min(hb + per, cnt);
         switch (slice) {
           case 0: accumulate_chunk<0>(acc, rec0, rec1, hb, he, lane); break;
           case 1: accumulate_chunk<1>(acc, rec0, rec1, hb, he, lane); break;
@@ -641,18 +654,24 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a
           default: accumulate_chunk<3>(acc, rec0, rec1, hb, he, lane); break;
         }
         __syncthreads();
+        if (PROF && tid == 0) { const long long t = clock64(); t_acc[2] += t - t_mark; t_mark = t; }
       }
-      // ---- reduce: lanes -> warp totals -> the two halves ----
+      // ---- reduce: lanes -> warp totals -> the parts of the chunk ----
       float mine = 0.f;
 #pragma unroll
       for (int e = 0; e < SLICE; ++e) {
         const float tot = warp_sum(acc[e]);
         if (lane == e) mine = tot;
       }
-      if (lane < SLICE) s_sums[half][SLICE * slice + lane] = mine;
+      if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
       __syncthreads();
       if (warp == 0) {
-        for (int k = lane; k < 96; k += 32) s_tot[k] = s_sums[0][k] + s_sums[1][k];
+        for (int k = lane; k < 96; k += 32) {
+          float s = s_sums[0][k];
+#pragma unroll
+          for (int q = 1; q < PARTS; ++q) s += s_sums[q][k];
+          s_tot[k] = s;
+        }
         __syncwarp();
         const float *sums = s_tot;
         const float cnt_f = sums[92], sumd2 = sums[91];
@@ -691,6 +710,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a
         }
       }
       __syncthreads();
+      if (PROF && tid == 0) { const long long t = clock64(); t_acc[3] += t - t_mark; t_mark = t; t_acc[4] += 1; }
 #pragma unroll
       for (int e = 0; e < 9; ++e) X.r[e] = s_X[e];
       X.t[0] = s_X[9]; X.t[1] = s_X[10]; X.t[2] = s_X[11];
@@ -704,6 +724,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3) icp_fused_kernel(FusedArgs a
     }
     __syncthreads();  // s_ctl / s_X are reused by the next hypothesis
   }
+  if (PROF && tid == 0) {
+    t_acc[5] = clock64() - t_start;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) atomicAdd((unsigned long long *)a.prof + k, (unsigned long long)t_acc[k]);
+  }
+}
+
+template <int THREADS, int CHUNK, bool PROF, int MINB>
+static cudaError_t launch_fused(const FusedArgs &f, int H, int sm_count, cudaStream_t stream) {
+  const size_t smem = 2 * (size_t)CHUNK * sizeof(float4);
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(icp_fused_kernel<THREADS, CHUNK, PROF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    attr_set = true;
+  }
+  const int grid_ctas = (int)std::min<long>((long)H, (long)sm_count * MINB);
+  icp_fused_kernel<THREADS, CHUNK, PROF, MINB><<<grid_ctas, THREADS, smem, stream>>>(f);
+  return cudaGetLastError();
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -827,14 +866,32 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
     f.counter = ctx->d_counter;
     f.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
     f.max_d2 = p.max_dist * p.max_dist; f.max_iter = max_iter; f.abs_mse_eps = p.abs_mse_eps;
-    const size_t smem = 2 * (size_t)FUSED_CHUNK * sizeof(float4);
-    static bool attr_set = false;
-    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(icp_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
     HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-    const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * 3);
+    static const int variant = getenv("HOP_FUSED_VARIANT") ? atoi(getenv("HOP_FUSED_VARIANT")) : 0;  // tuning knob: 1 = 256-thread CTAs, 2 = 128-thread CTAs
+    static const bool prof_on = getenv("HOP_FUSED_PROFILE") != nullptr;
+    static long long *d_prof = nullptr;
+    if (prof_on && !d_prof) { HOP_CUDA(ctx, cudaMalloc(&d_prof, 6 * sizeof(long long))); }
+    if (prof_on) HOP_CUDA(ctx, cudaMemsetAsync(d_prof, 0, 6 * sizeof(long long), ctx->stream));
+    f.prof = prof_on ? d_prof : nullptr;
     {
-      ProfScope ps(ctx, HOP_PROF_ICP_CORRESPOND);
-      icp_fused_kernel<<<grid_ctas, FUSED_THREADS, smem, ctx->stream>>>(f);
+      ProfScope ps(ctx, HOP_PROF_ICP_FUSED);
+      cudaError_t e;
+      // small batches: 256-thread CTAs (a hypothesis finishes sooner, shorter tail); large batches: 128-thread CTAs (the
+      // serial small solve idles 3 warps instead of 7).  Record chunk = 4 points per thread: the rest of the 256 KB stays L1.
+      const bool small_ctas = variant == 2 || (variant == 0 && (long)H >= 24L * ctx->sm_count);
+      if (prof_on) e = small_ctas ? launch_fused<128, 512, true, 6>(f, H, ctx->sm_count, ctx->stream)
+                                  : launch_fused<256, 1024, true, 3>(f, H, ctx->sm_count, ctx->stream);
+      else e = small_ctas ? launch_fused<128, 512, false, 6>(f, H, ctx->sm_count, ctx->stream)
+                          : launch_fused<256, 1024, false, 3>(f, H, ctx->sm_count, ctx->stream);
+      HOP_CUDA(ctx, e);
+    }
+    if (prof_on) {
+      long long hp[6];
+      HOP_CUDA(ctx, cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
+      HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      const double tot = (double)std::max<long long>(hp[5], 1);
+      fprintf(stderr, "[hop fused profile] H=%d passes=%lld  A %.1f%%  barrier %.1f%%  B %.1f%%  solve %.1f%%  other %.1f%%  (CTA cycles %.3g)\n", H, hp[4],
+              100.0 * hp[0] / tot, 100.0 * hp[1] / tot, 100.0 * hp[2] / tot, 100.0 * hp[3] / tot, 100.0 * (tot - hp[0] - hp[1] - hp[2] - hp[3]) / tot, tot);
     }
     ctx->launches += 1;
     HOP_CUDA(ctx, cudaGetLastError());

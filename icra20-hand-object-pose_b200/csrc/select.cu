@@ -8,23 +8,41 @@
 namespace {
 
 // K rounds of a block-wide arg-max over (score, -id); H is a few 1e3..1e5 and K <= 128, so one CTA is enough and
-// keeps the whole selection in one launch.  Selected entries are masked through a bitmap in shared/global scratch.
+// keeps the whole selection in one launch.  The scores are staged once in shared memory (SMEM = true, H up to ~50 k):
+// a selected entry is masked by overwriting its copy with a value below every score, and the K rounds never go back
+// to global memory.  Larger batches scan the global array and mask through a bitmap in scratch.
+template <bool SMEM>
 __global__ void __launch_bounds__(1024, 1) topk_kernel(const float *__restrict__ poses, const float *__restrict__ scores, int H,
                                                       int K, int32_t id_offset, int32_t frame, hop_pose_rec *__restrict__ out,
                                                       unsigned int *__restrict__ taken) {
+  extern __shared__ float s_scores[];
   __shared__ float s_val[32];
   __shared__ int s_idx[32];
   __shared__ int s_best;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  for (int i = tid; i < (H + 31) / 32; i += blockDim.x) taken[i] = 0u;
+  if (SMEM) {
+    for (int i = tid; i < H; i += blockDim.x) {
+      float v = scores[i];
+      if (!(v == v)) v = -INFINITY;  // NaN scores never win
+      s_scores[i] = v;
+    }
+  } else {
+    for (int i = tid; i < (H + 31) / 32; i += blockDim.x) taken[i] = 0u;
+  }
   __syncthreads();
   for (int k = 0; k < K; ++k) {
     float bv = -INFINITY;
     int bi = -1;
     for (int i = tid; i < H; i += blockDim.x) {
-      if (taken[i >> 5] & (1u << (i & 31))) continue;
-      float v = scores[i];
-      if (!(v == v)) v = -INFINITY;  // NaN scores never win
+      float v;
+      if (SMEM) {
+        v = s_scores[i];
+        if (__float_as_uint(v) == 0xffc00001u) continue;  // taken (a NaN pattern no staged score can have)
+      } else {
+        if (taken[i >> 5] & (1u << (i & 31))) continue;
+        v = scores[i];
+        if (!(v == v)) v = -INFINITY;
+      }
       if (bi < 0 || v > bv) { bv = v; bi = i; }  // ascending i: first (lowest id) wins ties
     }
     for (int o = 16; o > 0; o >>= 1) {
@@ -44,7 +62,10 @@ __global__ void __launch_bounds__(1024, 1) topk_kernel(const float *__restrict__
       }
       if (lane == 0) {
         s_best = bi;
-        if (bi >= 0) taken[bi >> 5] |= 1u << (bi & 31);
+        if (bi >= 0) {
+          if (SMEM) s_scores[bi] = __uint_as_float(0xffc00001u);
+          else taken[bi >> 5] |= 1u << (bi & 31);
+        }
       }
     }
     __syncthreads();
@@ -57,7 +78,7 @@ __global__ void __launch_bounds__(1024, 1) topk_kernel(const float *__restrict__
       else if (tid == 18) reinterpret_cast<int32_t *>(rec)[18] = frame;
       else reinterpret_cast<int32_t *>(rec)[19] = 0;
     }
-    __syncthreads();
+    if (!SMEM) __syncthreads();  // (SMEM: the next round's barrier orders s_best; records of different rounds are disjoint)
   }
 }
 
@@ -72,7 +93,14 @@ int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, i
   unsigned int *taken = (unsigned int *)ctx->ensure_scratch(words * sizeof(unsigned int));
   if (!taken) { ctx->err = "topk: scratch allocation failed"; return HOP_ENOMEM; }
   ProfScope ps(ctx, HOP_PROF_TOPK);
-  topk_kernel<<<1, 1024, 0, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);
+  const size_t smem = sizeof(float) * (size_t)H;
+  if (smem <= 200 * 1024) {
+    static bool attr_set = false;
+    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    topk_kernel<true><<<1, 1024, smem, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);
+  } else {
+    topk_kernel<false><<<1, 1024, 0, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);
+  }
   ctx->launches += 1;
   HOP_CUDA(ctx, cudaGetLastError());
   return HOP_OK;

@@ -25,8 +25,8 @@ timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
   python bench.py --workload $WL0 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_launch.log 2>&1
 echo "ncu launches exit $?"
 # full capture of the hot kernels (3 launches each, after warm-up)
-for K in icp_correspond_kernel lcp_score_kernel icp_solve_kernel; do
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 12 -c 2 -f -o $OUT/${TAG}_${K}_${WL0} \
+for K in icp_fused_kernel lcp_score_kernel; do
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:$K -s 3 -c 2 -f -o $OUT/${TAG}_${K}_${WL0} \
     python bench.py --workload $WL0 --steps 2 --warmup 3 --no-cpu-baseline > $OUT/${TAG}_ncu_${K}.log 2>&1
   echo "ncu $K exit $?"
 done
