@@ -94,19 +94,28 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(self.rows)}
 
 
+def host_threads():
+    """all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1: not what the CPU arm should get)"""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_baseline_run(model, frame, wl, sample, threads=0):
     """reference algorithm (oracle port: kd-tree rebuilt per hypothesis, LM point-to-plane ICP, LCP) on host cores"""
     from oracle import cpu_oracle as O
+    threads = threads or host_threads()
     m, mn = model
     hy = frame["hyp"][:sample]
     t0 = time.perf_counter()
     ref, it, cv = O.refine_by_icp(frame["xyz"], frame["nrm"], m, mn, hy, max_iter=wl["max_iter"], nthreads=threads)
     best, sc = O.select_best(frame["xyz"], frame["nrm"], m, mn, ref, nthreads=threads)
     dt = time.perf_counter() - t0
-    return len(hy) / dt, dt, O.num_threads()
+    return len(hy) / dt, dt, threads
 
 
-def run_reference(args, wl, rank, world):
+def run_reference(args, wl, rank, world, out):
     """--impl reference: the reference's own CPU algorithm for the path (PCL is not installable -> oracle port)."""
     if rank != 0:
         return
@@ -131,11 +140,21 @@ def run_reference(args, wl, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                              "sample": f"{sample} of {wl['H']} hypotheses per step, all {threads} host threads (OpenMP over hypotheses)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    print(json.dumps(line), file=out, flush=True)
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries (NCCL's version banner, ...) write to file descriptor 1 too:
+    keep a private copy of the real stdout for the result line and point fd 1 at stderr for everybody else."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
 
 
 def main():
     args = parse()
+    out = claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -143,7 +162,7 @@ def main():
     wl = synth.workload(args.workload)
 
     if args.impl == "reference":
-        run_reference(args, wl, rank, world)
+        run_reference(args, wl, rank, world, out)
         return
 
     import torch
@@ -331,7 +350,7 @@ def main():
             rate, dt, thr = cpu_baseline_run(model_np, frames[0], wl, sample)
             line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": thr, "kind": "port",
                                     "sample": f"first {sample} of {H} hypotheses of frame 0, {thr} OpenMP threads, {dt:.1f} s"}
-        print(json.dumps(line))
+        print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
 

@@ -152,6 +152,13 @@ int hop_create(int device, hop_ctx **out) {
     return HOP_ECUDA;
   }
   cudaMemset(ctx->d_counter, 0, 64 * sizeof(int));
+  {  // per-call scratch comes from the stream-ordered pool: keep freed blocks instead of returning them to the driver
+    cudaMemPool_t pool = nullptr;
+    if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess && pool) {
+      unsigned long long keep = ~0ull;
+      cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
+  }
   *out = ctx;
   return HOP_OK;
 }

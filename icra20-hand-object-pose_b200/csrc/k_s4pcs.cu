@@ -23,6 +23,7 @@
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #include <algorithm>
+#include <memory>
 #include <cmath>
 
 #include "hop_common.cuh"
@@ -273,11 +274,21 @@ __global__ void fill_int_ranges_kernel(int *out, const int *begin, const int *en
   for (int k = begin[r] + blockIdx.x * blockDim.x + threadIdx.x; k < end[r]; k += gridDim.x * blockDim.x) out[k] = r;
 }
 
+// stream-ordered scratch of one call: cudaMallocAsync / cudaFreeAsync on the context's stream, served from the device's
+// default memory pool (hop_create raises its release threshold, so after the first frame no call reaches the driver's allocator)
 struct DevBuf {
   void *p = nullptr;
-  ~DevBuf() { if (p) cudaFree(p); }
+  cudaStream_t st;
+  explicit DevBuf(cudaStream_t s) : st(s) {}
+  DevBuf(const DevBuf &) = delete;
+  DevBuf &operator=(const DevBuf &) = delete;
+  ~DevBuf() { if (p) cudaFreeAsync(p, st); }
   template <typename T> T *as() { return (T *)p; }
-  cudaError_t alloc(size_t bytes) { if (p) cudaFree(p); p = nullptr; return cudaMalloc(&p, std::max<size_t>(bytes, 16)); }
+  cudaError_t alloc(size_t bytes) {
+    if (p) cudaFreeAsync(p, st);
+    p = nullptr;
+    return cudaMallocAsync(&p, std::max<size_t>(bytes, 16), st);
+  }
 };
 
 }  // namespace
@@ -350,7 +361,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
 
   // ---- uploads ----
   const long long NP = (long long)nQ * (nQ - 1) / 2;
-  DevBuf bQp, bQn, bQu, bEx, bTp, bFlags, bCnt, bSel, bCub;
+  DevBuf bQp(st), bQn(st), bQu(st), bEx(st), bTp(st), bFlags(st), bCnt(st), bSel(st), bCub(st);
   std::vector<float4> hQp(nQ), hQn(nQ), hQu(nQ);
   for (int i = 0; i < nQ; ++i) {
     hQp[i] = make_float4(plan->Q[i].p[0], plan->Q[i].p[1], plan->Q[i].p[2], 0.f);
@@ -368,6 +379,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
   HOP_CUDA(ctx, cudaMemsetAsync(bCnt.p, 0, sizeof(int) * (2 * T + 4), st));
 
   // ---- K2a ----
+  std::unique_ptr<ProfScope> prof(new ProfScope(ctx, HOP_PROF_S4_PAIRS));
   extract_pairs_kernel<<<dim3((unsigned)((NP + 255) / 256), 2 * T), 256, 0, st>>>(bQp.as<float4>(), bQn.as<float4>(), NP, bEx.as<ExtractParams>(),
                                                                                   bFlags.as<unsigned char>(), bCnt.as<int>());
   ctx->launches += 1;
@@ -382,6 +394,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
   HOP_CUDA(ctx, bCub.alloc(cub_bytes));
   cub::DeviceSelect::Flagged(bCub.p, cub_bytes, counting, bFlags.as<unsigned char>(), bSel.as<long long>(), d_nsel, (int)n_flat, st);
   ctx->launches += 1;
+  prof.reset();
   std::vector<int> cnt(2 * T + 4);
   HOP_CUDA(ctx, cudaMemcpyAsync(cnt.data(), bCnt.p, sizeof(int) * (2 * T + 4), cudaMemcpyDeviceToHost, st));
   HOP_CUDA(ctx, cudaStreamSynchronize(st));
@@ -399,7 +412,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
 
   int M = 0, T_exec = 0;
   std::vector<int> quad_begin(T + 1, 0);
-  DevBuf bR1, bR2, bMeta, bR1Trial, bCounts, bOffsets, bQuads, bQuadTrial;
+  DevBuf bR1(st), bR2(st), bMeta(st), bR1Trial(st), bCounts(st), bOffsets(st), bQuads(st), bQuadTrial(st);
   if (n1 > 0 && n2 > 0) {
     HOP_CUDA(ctx, bR1.alloc(sizeof(PairRec1) * (size_t)n1)); HOP_CUDA(ctx, bR2.alloc(sizeof(PairRec2) * (size_t)n2));
     // meta: ex_begin | rec_base | r1_begin | r1_end | r2_begin | r2_end
@@ -411,6 +424,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     HOP_CUDA(ctx, cudaMemcpyAsync(bMeta.p, meta.data(), sizeof(int) * meta.size(), cudaMemcpyHostToDevice, st));
     const int *d_ex_begin = bMeta.as<int>(), *d_rec_base = d_ex_begin + 2 * T, *d_r1_begin = d_rec_base + 2 * T, *d_r1_end = d_r1_begin + T,
               *d_r2_begin = d_r1_end + T, *d_r2_end = d_r2_begin + T;
+    prof.reset(new ProfScope(ctx, HOP_PROF_S4_JOIN));
     prepare_pairs_kernel<<<(n_sel + 127) / 128, 128, 0, st>>>(bSel.as<long long>(), n_sel, NP, d_ex_begin, bQp.as<float4>(), bQu.as<float4>(),
                                                               bTp.as<TrialParams>(), g, bR1.as<PairRec1>(), bR2.as<PairRec2>(), d_rec_base);
     HOP_CUDA(ctx, bR1Trial.alloc(sizeof(int) * (size_t)n1));
@@ -426,6 +440,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     if (scan_bytes > cub_bytes) { HOP_CUDA(ctx, bCub.alloc(scan_bytes)); cub_bytes = scan_bytes; }
     cub::DeviceScan::ExclusiveSum(bCub.p, scan_bytes, bCounts.as<int>(), bOffsets.as<int>(), n1 + 1, st);
     ctx->launches += 4;
+    prof.reset();
     // quadrilaterals per trial -> which trials Perform_N_steps would have executed
     std::vector<int> offs(n1 + 1);
     HOP_CUDA(ctx, cudaMemcpyAsync(offs.data(), bOffsets.p, sizeof(int) * ((size_t)n1 + 1), cudaMemcpyDeviceToHost, st));
@@ -445,7 +460,10 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     if (M > 0) {
       HOP_CUDA(ctx, bQuads.alloc(sizeof(int4) * (size_t)M)); HOP_CUDA(ctx, bQuadTrial.alloc(sizeof(int) * (size_t)M));
       ja.n1 = r1_end[T_exec - 1]; ja.offsets = bOffsets.as<int>(); ja.quads = bQuads.as<int4>(); ja.quad_trial = bQuadTrial.as<int>();
-      congruent_join_kernel<true><<<(ja.n1 + 7) / 8, 256, 0, st>>>(ja);
+      {
+        ProfScope ps(ctx, HOP_PROF_S4_JOIN);
+        congruent_join_kernel<true><<<(ja.n1 + 7) / 8, 256, 0, st>>>(ja);
+      }
       ctx->launches += 1;
     }
   } else {
@@ -487,7 +505,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
   if (rc != HOP_OK) return rc;
   std::vector<int32_t> bases(4 * (size_t)T);
   for (int t = 0; t < T; ++t) for (int k = 0; k < 4; ++k) bases[4 * t + k] = plan->trials[t].base[k];
-  DevBuf bBases, bQc, bPoses, bLcp, bValid, bN;
+  DevBuf bBases(st), bQc(st), bPoses(st), bLcp(st), bValid(st), bN(st);
   cudaError_t ce = cudaSuccess;
   if ((ce = bBases.alloc(sizeof(int32_t) * 4 * T)) != cudaSuccess || (ce = bQc.alloc(sizeof(float) * 3 * nQ)) != cudaSuccess ||
       (ce = bPoses.alloc(64 * (size_t)M)) != cudaSuccess || (ce = bLcp.alloc(4 * (size_t)M)) != cudaSuccess ||

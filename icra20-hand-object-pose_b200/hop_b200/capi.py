@@ -318,7 +318,7 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
-    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7}
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9}
 
     def profile_enable(self, on=True):
         self._check(self.L.hop_profile_enable(self.h, int(on)))

@@ -97,7 +97,9 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 #define HOP_PROF_VERIFY 5         /* verify_lcp_kernel (K3) */
 #define HOP_PROF_HAND 6           /* hand_overlap_kernel (K1) */
 #define HOP_PROF_ICP_FUSED 7      /* icp_fused_kernel: the whole ICP of a batch in one launch (default pipeline) */
-#define HOP_PROF_KINDS 8
+#define HOP_PROF_S4_PAIRS 8       /* K2a: extract_pairs_kernel + selection (all trials) */
+#define HOP_PROF_S4_JOIN 9        /* K2b: prepare_pairs + congruent_join (count, scan, fill) */
+#define HOP_PROF_KINDS 12
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
 int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans);

@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Stage benches next to bench.py's headline line: K1 (hand-state overlap search) and Super4PCS (K2a pair extraction,
+K2b congruent-set search, K3 verification) at the BASELINE.json sizes, one JSON line per stage.
+
+  python tools/bench_stages.py [--steps K] [--warmup W] [--sizes C2|C5]
+
+Per stage: units/s end to end through the host-buffer C ABI (what Hand::matchOneComponentPSO / PoseEstimator::runSuper4pcs
+call; H2D/D2H inside), the kernel's own CUDA-event time (libhop's per-kernel profiling on the launching stream) and the
+roofline entry from SURVEY 8(d)'s algorithmic bytes:  K1  32 (N_f + N_h) + 32 N_w + 8  per hand state,
+K3  16 (nQ + N_s) + 84  per congruent quadrilateral.  No oracle, no reference: the PPF key set comes from hop_compute_ppf.
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "icra20-hand-object-pose_b200"))
+
+SIZES = {
+    # S hand states, finger / hand-scene points; Super4PCS: scene points, model points handed to the matcher, sample size
+    "C2": dict(S=4096, n_finger=300, n_hand=3000, n_scene=2000, n_model=10000, sample=100),
+    "C5": dict(S=16384, n_finger=400, n_hand=5000, n_scene=50000, n_model=50000, sample=2000),
+}
+
+
+def ppf_keys(xyz, nrm, stride=1):
+    """unique PPF keys of all point pairs (what computePPF.cpp:86-107 tabulates), through the library's own hop_compute_ppf"""
+    import ctypes as C
+    import hop_b200
+    L = hop_b200.load_library()
+    xyz = np.ascontiguousarray(xyz[::stride], np.float32)
+    nrm = np.ascontiguousarray(nrm[::stride], np.float32)
+    n = len(xyz)
+    key = (C.c_int32 * 4)()
+    fp = C.POINTER(C.c_float)
+    seen = set()
+    px = [xyz[i].ctypes.data_as(fp) for i in range(n)]
+    pn = [nrm[i].ctypes.data_as(fp) for i in range(n)]
+    f = L.hop_compute_ppf
+    for i in range(n):
+        for j in range(i + 1, n):
+            f(px[i], pn[i], px[j], pn[j], key)
+            seen.add((key[0], key[1], key[2], key[3]))
+    return np.array(sorted(seen), np.int32).reshape(-1, 4)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--sizes", default="C2")
+    args = ap.parse_args()
+    import hop_b200
+    from hop_b200 import capi, hand, synth
+    sz = SIZES[args.sizes]
+    peaks = {}
+    pk = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk):
+        peaks = json.load(open(pk))
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ctx = hop_b200.Context(0)
+
+    def timed(fn):
+        for _ in range(max(args.warmup, 3)):
+            fn()
+        ctx.sync()
+        ctx.profile_enable(True)
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            fn()
+        ctx.sync()
+        dt = (time.perf_counter() - t0) / args.steps
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        return dt, prof
+
+    # ---------------- K1: S joint angles of one finger link ----------------
+    case = synth.make_hand_case(seed=5, n_finger=sz["n_finger"], n_hand=sz["n_hand"])
+    prop = hand.FingerProperty(case["finger_xyz"], case["scalars"]["num_division"])
+    p = hand.finger_params(prop, case["scalars"])
+    finger = ctx.upload_cloud(case["finger_xyz"], case["finger_nrm"])
+    scene = ctx.upload_cloud(case["scene_xyz"], case["scene_nrm"])
+    lookup = ctx.upload_cloud(case["lookup_xyz"], case["lookup_nrm"])
+    nosw = ctx.upload_cloud(case["noswivel_xyz"], case["noswivel_nrm"])
+    thetas = np.deg2rad(np.linspace(0, 120, sz["S"]))
+    res = {}
+
+    def k1():
+        res["k1"] = ctx.hand_overlap(finger, scene, nosw, p, thetas, lookup)
+
+    dt, prof = timed(k1)
+    S, nf, nh, nw = sz["S"], len(case["finger_xyz"]), len(case["scene_xyz"]), len(case["noswivel_xyz"])
+    k_ms = prof["hand_overlap"][0] / max(prof["hand_overlap"][1], 1)
+    bytes_state = 32 * (nf + nh) + 32 * nw + 8
+    ach = S * bytes_state / (k_ms * 1e-3) / 1e9
+    print(json.dumps({"stage": "K1 hand_overlap (objFuncPSO over a dense grid of joint angles)", "metric": "hand states/sec", "value": S / (k_ms * 1e-3),
+                      "unit": "states/s", "e2e": {"value": S / dt, "unit": "states/s", "ms_per_call": dt * 1e3, "h2d_bytes": 8 * S, "d2h_bytes": 8 * S + 4},
+                      "config": {"sizes": args.sizes, "S": S, "n_finger": nf, "n_scene_hand": nh, "n_noswivel": nw,
+                                 "best_theta_deg": float(np.rad2deg(thetas[res["k1"][1]])), "true_theta_deg": float(np.rad2deg(case["theta_true"]))},
+                      "kernel_ms": k_ms, "dtype": "f32 (f64 cost)",
+                      "roofline": {"bound": "hbm", "kernel": "hand_overlap_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                   "traffic": None, "algorithmic_bytes_per_launch": S * bytes_state}}))
+
+    # ---------------- Super4PCS: plan on the host (untimed: it replays the reference's RNG), K2a + K2b + K3 on the device ----------------
+    m, mn = synth.make_model("ellipse", sz["n_model"], seed=1)
+    s, sn, conf, gt = synth.make_scene("ellipse", sz["n_scene"], seed=2)
+    t0 = time.perf_counter()
+    keys = ppf_keys(m, mn, stride=max(1, len(m) // 400))          # the 5 mm "ppf_density" model of computePPF.cpp: ~400 points
+    t_keys = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    plan = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=sz["sample"]))
+    t_plan = time.perf_counter() - t0
+
+    def s4():
+        res["s4"] = ctx.super4pcs_run(plan, capacity=400000)
+
+    plan_k = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=sz["sample"], keep_intermediates=1))
+    ctx.super4pcs_run(plan_k, capacity=400000)      # once, untimed, with the intermediates kept: how many quadrilaterals K3 verifies
+    info = plan_k.sizes()
+    dt, prof = timed(s4)
+    n_hyp = len(res["s4"][1])
+    steps = args.steps
+    v_ms = prof["verify_lcp"][0] / steps
+    pr_ms = prof["s4pcs_pairs"][0] / steps
+    jn_ms = prof["s4pcs_join"][0] / steps
+    M, nQ = int(info["quads"]), int(info["nQ"])
+    bytes_quad = 16 * (nQ + len(s)) + 84
+    ach = (M * bytes_quad / (v_ms * 1e-3) / 1e9) if v_ms > 0 and M > 0 else 0.0
+    adi = float("nan")
+    if n_hyp:   # ADI of the best-LCP hypothesis (the reference's own metric, scripts/eval_utils.py:181-200; symmetric objects flip freely)
+        from scipy.spatial import cKDTree
+        best = res["s4"][0][int(np.argmax(res["s4"][1]))].astype(np.float64)
+        sub = m[::5].astype(np.float64)
+        adi = float(cKDTree(sub @ gt[:3, :3].T + gt[:3, 3]).query(sub @ best[:3, :3].T + best[:3, 3])[0].mean())
+    print(json.dumps({"stage": "Super4PCS device stages (K2a pairs, K2b congruent sets, K3 verify), all trials of a frame in one call",
+                      "metric": "congruent quadrilaterals verified/sec", "value": (M / (v_ms * 1e-3)) if v_ms > 0 else 0.0, "unit": "quads/s",
+                      "e2e": {"value": n_hyp / dt, "unit": "emitted hypotheses/s", "ms_per_call": dt * 1e3},
+                      "config": {"sizes": args.sizes, "n_scene": len(s), "n_model": len(m), "plan": info, "hypotheses_emitted": n_hyp,
+                                 "ppf_keys": int(len(keys)), "host_plan_ms": t_plan * 1e3, "host_ppf_table_ms": t_keys * 1e3,
+                                 "best_lcp_hypothesis_adi_mm": adi * 1e3},
+                      "kernel_ms": {"k2a_pairs": pr_ms, "k2b_join": jn_ms, "k3_verify": v_ms}, "dtype": "f32 / int32",
+                      "roofline": {"bound": "hbm", "kernel": "verify_lcp_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                                   "traffic": None, "algorithmic_bytes_per_launch": M * bytes_quad}}))
+    ctx.close()
+
+
+if __name__ == "__main__":
+    main()
