@@ -24,7 +24,7 @@ sys.path.insert(0, os.path.join(ROOT, "icra20-hand-object-pose_b200"))
 SIZES = {
     # S hand states, finger / hand-scene points; Super4PCS: scene points, model points handed to the matcher, sample size
     "C2": dict(S=4096, n_finger=300, n_hand=3000, n_scene=2000, n_model=10000, sample=100),
-    "C5": dict(S=16384, n_finger=400, n_hand=5000, n_scene=50000, n_model=50000, sample=2000),
+    "C5": dict(S=16384, n_finger=400, n_hand=5000, n_scene=50000, n_model=50000, sample=400),
 }
 
 
@@ -54,7 +54,11 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sizes", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    sys.stdout.flush()
+    out = os.fdopen(os.dup(1), "w")   # the JSON lines; fd 1 itself goes to stderr (the compiled reference matcher prints its progress)
+    os.dup2(2, 1)
     import hop_b200
     from hop_b200 import capi, hand, synth
     sz = SIZES[args.sizes]
@@ -98,13 +102,22 @@ def main():
     k_ms = prof["hand_overlap"][0] / max(prof["hand_overlap"][1], 1)
     bytes_state = 32 * (nf + nh) + 32 * nw + 8
     ach = S * bytes_state / (k_ms * 1e-3) / 1e9
-    print(json.dumps({"stage": "K1 hand_overlap (objFuncPSO over a dense grid of joint angles)", "metric": "hand states/sec", "value": S / (k_ms * 1e-3),
+    cpu1 = None
+    if not args.no_cpu_baseline:   # the objFuncPSO restatement (oracle port), OpenMP over states, on a bounded sample of the same grid
+        from oracle import cpu_oracle as O
+        thr = max(1, len(os.sched_getaffinity(0)))
+        n_s = min(S, 512)
+        t0 = time.perf_counter()
+        O.hand_overlap(p, case["finger_xyz"], case["finger_nrm"], case["scene_xyz"], case["lookup_nrm"], case["noswivel_xyz"], thetas[:: S // n_s][:n_s], nthreads=thr)
+        tc = time.perf_counter() - t0
+        cpu1 = {"value": n_s / tc, "unit": "states/s", "cores": thr, "kind": "port", "sample": f"{n_s} of {S} states, {tc:.2f} s (kd-tree built once per call; the reference deep-copies it per thread per generation)"}
+    print(json.dumps({"stage": "K1 hand_overlap (objFuncPSO over a dense grid of joint angles)", "metric": "hand states/sec", "value": S / (k_ms * 1e-3), "cpu_baseline": cpu1,
                       "unit": "states/s", "e2e": {"value": S / dt, "unit": "states/s", "ms_per_call": dt * 1e3, "h2d_bytes": 8 * S, "d2h_bytes": 8 * S + 4},
                       "config": {"sizes": args.sizes, "S": S, "n_finger": nf, "n_scene_hand": nh, "n_noswivel": nw,
                                  "best_theta_deg": float(np.rad2deg(thetas[res["k1"][1]])), "true_theta_deg": float(np.rad2deg(case["theta_true"]))},
                       "kernel_ms": k_ms, "dtype": "f32 (f64 cost)",
                       "roofline": {"bound": "hbm", "kernel": "hand_overlap_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                   "traffic": None, "algorithmic_bytes_per_launch": S * bytes_state}}))
+                                   "traffic": None, "algorithmic_bytes_per_launch": S * bytes_state}}), file=out, flush=True)
 
     # ---------------- Super4PCS: plan on the host (untimed: it replays the reference's RNG), K2a + K2b + K3 on the device ----------------
     m, mn = synth.make_model("ellipse", sz["n_model"], seed=1)
@@ -137,7 +150,20 @@ def main():
         best = res["s4"][0][int(np.argmax(res["s4"][1]))].astype(np.float64)
         sub = m[::5].astype(np.float64)
         adi = float(cKDTree(sub @ gt[:3, :3].T + gt[:3, 3]).query(sub @ best[:3, :3].T + best[:3, 3])[0].mean())
-    print(json.dumps({"stage": "Super4PCS device stages (K2a pairs, K2b congruent sets, K3 verify), all trials of a frame in one call",
+    cpu2 = None
+    if not args.no_cpu_baseline and args.sizes == "C2":   # (bounded: the CPU matcher needs minutes at the C5 sizes)
+        from oracle import cpu_oracle as O
+        if O.ref() is not None and hasattr(O.ref(), "hop_ref_s4pcs_run"):   # the reference's own compiled matcher (oracle/_ref), all host threads
+            thr = max(1, len(os.sched_getaffinity(0)))
+            best_t, n_ref = 1e30, 0
+            for _ in range(3):
+                t0 = time.perf_counter()
+                r = O.ref_super4pcs(s, sn, conf, m, mn, keys, sample_size=sz["sample"], nthreads=thr)
+                best_t = min(best_t, time.perf_counter() - t0)
+                n_ref = len(r["lcp"])
+            cpu2 = {"value": n_ref / best_t, "unit": "emitted hypotheses/s", "cores": thr, "kind": "reference", "ms_per_call": best_t * 1e3,
+                    "sample": f"whole registration (init + {len(r['trials'])} trials + verification), best of 3, {n_ref} hypotheses, {len(r['quads'])} quadrilaterals"}
+    print(json.dumps({"stage": "Super4PCS device stages (K2a pairs, K2b congruent sets, K3 verify), all trials of a frame in one call", "cpu_baseline": cpu2,
                       "metric": "congruent quadrilaterals verified/sec", "value": (M / (v_ms * 1e-3)) if v_ms > 0 else 0.0, "unit": "quads/s",
                       "e2e": {"value": n_hyp / dt, "unit": "emitted hypotheses/s", "ms_per_call": dt * 1e3},
                       "config": {"sizes": args.sizes, "n_scene": len(s), "n_model": len(m), "plan": info, "hypotheses_emitted": n_hyp,
@@ -145,7 +171,7 @@ def main():
                                  "best_lcp_hypothesis_adi_mm": adi * 1e3},
                       "kernel_ms": {"k2a_pairs": pr_ms, "k2b_join": jn_ms, "k3_verify": v_ms}, "dtype": "f32 / int32",
                       "roofline": {"bound": "hbm", "kernel": "verify_lcp_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                                   "traffic": None, "algorithmic_bytes_per_launch": M * bytes_quad}}))
+                                   "traffic": None, "algorithmic_bytes_per_launch": M * bytes_quad}}), file=out, flush=True)
     ctx.close()
 
 
