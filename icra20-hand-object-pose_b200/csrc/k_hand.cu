@@ -4,10 +4,13 @@
 //            the swarm that evaluates it      (src/perception/include/unconstrained/pso.hpp:146-351: 16 particles x 4 evaluations,
 //                                              each OpenMP thread deep-copying the clouds AND the FLANN tree, pso.hpp:83-108,232,286)
 //
-// One warp per hand state (joint angle); 8 states per CTA.  The three clouds never move: the finger cloud is carried into
-// the hand-base frame by the state's transform and looked up in ONE exact nearest-neighbour grid of the scene shared by every
-// state; the no-swivel scene is staged into shared memory by 1-D bulk (TMA) copies, double buffered on mbarriers, and
-// every warp of the CTA reads it from there, moving it into ITS finger frame.  Integer results (match count, outer
+// Two launches.  hand_match_kernel: flat over (state, finger point) -- the finger cloud is carried into the hand-base frame by
+// the state's transform and looked up in ONE exact nearest-neighbour grid of the scene shared by every state; the match
+// count of a state is an integer sum, so the order of the atomics does not matter.  (The first version walked the finger
+// points inside the state's warp: ten dependent gather rounds on the critical path of every state that passes the gap
+// test, 95 us for 4096 states; flat, the same queries fill the machine.)  hand_overlap_kernel: one warp per hand state, 8
+// states per CTA; the no-swivel scene is staged into shared memory by 1-D bulk (TMA) copies, double buffered on
+// mbarriers, and every warp of the CTA reads it from there, moving it into ITS finger frame.  Integer results (match count, outer
 // count) come from ballots; the float sums use a fixed shuffle order, so costs are deterministic run to run.
 // The arithmetic follows the reference's types and operation order (see oracle/hop_oracle_hand.c): unfused float
 // transforms (PCL 1.9), `num_match += 1 + X[0]` in double rounded to float per match, double penalties.
@@ -16,7 +19,7 @@
 namespace {
 
 constexpr int HAND_WARPS = 8;
-constexpr int HAND_CHUNK = 2048;  // no-swivel scene points per shared-memory stage (32 KB)
+constexpr int HAND_CHUNK = 1024;  // no-swivel scene points per shared-memory stage (16 KB; two stages: 5 CTAs per SM)
 
 struct HandArgs {
   hop_finger_params p;
@@ -27,6 +30,7 @@ struct HandArgs {
   const double *thetas; const float *half_cs; int S;
   float cos_thr, thr2;
   double *cost;
+  int *matches;                                // per state: finger points with an accepted neighbour (hand_match_kernel)
 };
 
 struct M4f { float m[16]; };  // column-major
@@ -71,31 +75,13 @@ __device__ __forceinline__ void inverse_rows_yz(const float *T, float *ry, float
   rz[3] = __double2float_rn(-__dadd_rn(__dadd_rn(__dmul_rn(I[3], t0), __dmul_rn(I[4], t1)), __dmul_rn(I[5], t2)));
 }
 
-__global__ void __launch_bounds__(HAND_WARPS * 32) hand_overlap_kernel(const __grid_constant__ HandArgs a) {
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  float4 *const stage0 = reinterpret_cast<float4 *>(smem_raw);  // two stages of HAND_CHUNK points
-  __shared__ __align__(8) uint64_t full[2];
-  __shared__ float s_hist[HOP_MAX_FINGER_BINS];
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_chunks = (a.nw_padded + HAND_CHUNK - 1) / HAND_CHUNK;
-  if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
-  if (threadIdx.x < HOP_MAX_FINGER_BINS) s_hist[threadIdx.x] = a.p.hist_min_y[threadIdx.x];
-  __syncthreads();
-  auto issue = [&](int c) {  // one elected thread: bulk copy of chunk c into its stage
-    const int cnt = min(HAND_CHUNK, a.nw_padded - c * HAND_CHUNK);
-    mbar_arrive_expect_tx(&full[c & 1], (uint32_t)cnt * 16u);
-    tma_load_1d(stage0 + (c & 1) * HAND_CHUNK, a.w_pw + (size_t)c * HAND_CHUNK, (uint32_t)cnt * 16u, &full[c & 1]);
-  };
-  if (threadIdx.x == 0 && n_chunks > 0) issue(0);
-
-  // ---- per-state set-up (uniform across the warp) ----
-  const int s = blockIdx.x * HAND_WARPS + warp;
-  const bool valid = s < a.S;
-  const double X = valid ? a.thetas[s] : 0.0;
+// the state's finger-link transform in the hand-base frame and the gripper-gap test (Hand.cpp:15-64).
+// branch: 0 gap penalty (score is final), 4 none yet
+__device__ __forceinline__ void hand_state_setup(const HandArgs &a, int s, bool valid, double &X, float *cur, int &branch, float &score) {
+  X = valid ? a.thetas[s] : 0.0;
   float cw, sx;
   if (a.half_cs) { cw = valid ? a.half_cs[2 * s] : 1.f; sx = valid ? a.half_cs[2 * s + 1] : 0.f; }
   else { const float h = __fmul_rn(0.5f, (float)X); cw = cosf(h); sx = sinf(h); }
-  float cur[16];
   {
     // tf_self = Quaternionf(w = cos(a/2), x = sin(a/2)).toRotationMatrix() (Hand.cpp:15-21)
     const float tx = __fmul_rn(2.f, sx), twx = __fmul_rn(tx, cw), txx = __fmul_rn(tx, sx);
@@ -105,8 +91,8 @@ __global__ void __launch_bounds__(HAND_WARPS * 32) hand_overlap_kernel(const __g
     tf[0] = 1.f; tf[5] = __fsub_rn(1.f, txx); tf[9] = __fsub_rn(0.f, twx); tf[6] = __fadd_rn(0.f, twx); tf[10] = __fsub_rn(1.f, txx); tf[15] = 1.f;
     m4_mul(a.p.model2handbase, tf, cur);
   }
-  int branch = 4;  // 0 gap, 1 no match, 2 hard outer, 3 exp, 4 none
-  float score = 0.f;
+  branch = 4;
+  score = 0.f;
   {
     float tip1y;
     if (a.p.palm_side) {
@@ -130,34 +116,70 @@ __global__ void __launch_bounds__(HAND_WARPS * 32) hand_overlap_kernel(const __g
       branch = 0;
     }
   }
+}
 
-  // ---- matches: finger points against the scene's nearest-neighbour grid ----
-  int matches = 0;
-  if (valid && branch != 0) {
-    for (int i0 = 0; i0 < a.nf; i0 += 32) {
-      const int i = i0 + lane;
-      bool hit = false;
-      if (i < a.nf) {
-        const float4 fp = __ldg(&a.f_pw[i]);
-        const float px = row_pt(cur, 0, fp.x, fp.y, fp.z), py = row_pt(cur, 1, fp.x, fp.y, fp.z), pz = row_pt(cur, 2, fp.x, fp.y, fp.z);
-        float bd; float4 bp;
-        const int j = nn_query(a.grid, px, py, pz, bd, bp);
-        if (j >= 0 && bd <= a.thr2) {
-          if (!a.p.check_normal) hit = true;
-          else if (j < a.n_lk) {
-            const float4 n2 = __ldg(&a.lk_nv[j]);
-            if (n2.x == 0.f && n2.y == 0.f && n2.z == 0.f) hit = true;
-            else if (isfinite(n2.x) && isfinite(n2.y) && isfinite(n2.z)) {
-              const float4 fn = __ldg(&a.f_nv[i]);
-              const float n1x = row_vec(cur, 0, fn.x, fn.y, fn.z), n1y = row_vec(cur, 1, fn.x, fn.y, fn.z), n1z = row_vec(cur, 2, fn.x, fn.y, fn.z);
-              const float dot = __fadd_rn(__fmul_rn(n1x, n2.x), __fadd_rn(__fmul_rn(n1y, n2.y), __fmul_rn(n1z, n2.z)));
-              hit = dot >= a.cos_thr;
-            }
-          }
+constexpr int MATCH_THREADS = 128;
+
+// matches[s] = number of finger points whose nearest scene neighbour passes the distance and normal gates (Hand.cpp:84-125)
+__global__ void __launch_bounds__(MATCH_THREADS) hand_match_kernel(const __grid_constant__ HandArgs a) {
+  const int s = blockIdx.x;
+  double X; float cur[16]; int branch; float score;
+  hand_state_setup(a, s, true, X, cur, branch, score);
+  if (branch == 0) return;   // (uniform across the CTA)
+  const int i = blockIdx.y * MATCH_THREADS + threadIdx.x;
+  bool hit = false;
+  if (i < a.nf) {
+    const float4 fp = __ldg(&a.f_pw[i]);
+    const float px = row_pt(cur, 0, fp.x, fp.y, fp.z), py = row_pt(cur, 1, fp.x, fp.y, fp.z), pz = row_pt(cur, 2, fp.x, fp.y, fp.z);
+    float bd; float4 bp;
+    const int j = nn_query(a.grid, px, py, pz, bd, bp);
+    if (j >= 0 && bd <= a.thr2) {
+      if (!a.p.check_normal) hit = true;
+      else if (j < a.n_lk) {
+        const float4 n2 = __ldg(&a.lk_nv[j]);
+        if (n2.x == 0.f && n2.y == 0.f && n2.z == 0.f) hit = true;
+        else if (isfinite(n2.x) && isfinite(n2.y) && isfinite(n2.z)) {
+          const float4 fn = __ldg(&a.f_nv[i]);
+          const float n1x = row_vec(cur, 0, fn.x, fn.y, fn.z), n1y = row_vec(cur, 1, fn.x, fn.y, fn.z), n1z = row_vec(cur, 2, fn.x, fn.y, fn.z);
+          const float dot = __fadd_rn(__fmul_rn(n1x, n2.x), __fadd_rn(__fmul_rn(n1y, n2.y), __fmul_rn(n1z, n2.z)));
+          hit = dot >= a.cos_thr;
         }
       }
-      matches += __popc(__ballot_sync(0xffffffffu, hit));
     }
+  }
+  const int cnt = __syncthreads_count(hit);
+  if (threadIdx.x == 0 && cnt) atomicAdd(&a.matches[s], cnt);
+}
+
+__global__ void __launch_bounds__(HAND_WARPS * 32) hand_overlap_kernel(const __grid_constant__ HandArgs a) {
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  float4 *const stage0 = reinterpret_cast<float4 *>(smem_raw);  // two stages of HAND_CHUNK points
+  __shared__ __align__(8) uint64_t full[2];
+  __shared__ float s_hist[HOP_MAX_FINGER_BINS];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_chunks = (a.nw_padded + HAND_CHUNK - 1) / HAND_CHUNK;
+  if (threadIdx.x == 0) { mbar_init(&full[0], 1); mbar_init(&full[1], 1); mbar_fence_init(); }
+  if (threadIdx.x < HOP_MAX_FINGER_BINS) s_hist[threadIdx.x] = a.p.hist_min_y[threadIdx.x];
+  __syncthreads();
+  auto issue = [&](int c) {  // one elected thread: bulk copy of chunk c into its stage
+    const int cnt = min(HAND_CHUNK, a.nw_padded - c * HAND_CHUNK);
+    mbar_arrive_expect_tx(&full[c & 1], (uint32_t)cnt * 16u);
+    tma_load_1d(stage0 + (c & 1) * HAND_CHUNK, a.w_pw + (size_t)c * HAND_CHUNK, (uint32_t)cnt * 16u, &full[c & 1]);
+  };
+  if (threadIdx.x == 0 && n_chunks > 0) issue(0);
+
+  // ---- per-state set-up (uniform across the warp) ----
+  const int s = blockIdx.x * HAND_WARPS + warp;
+  const bool valid = s < a.S;
+  double X;
+  float cur[16];
+  int branch;  // 0 gap, 1 no match, 2 hard outer, 3 exp, 4 none
+  float score;
+  hand_state_setup(a, s, valid, X, cur, branch, score);
+
+  // ---- matches: counted by hand_match_kernel ----
+  if (valid && branch != 0) {
+    const int matches = a.matches[s];
     // num_match += 1 + X[0]  (float accumulator, double increment), once per match
     float nm = 0.f;
     const double inc = __dadd_rn(1.0, X);
@@ -273,8 +295,15 @@ extern "C" int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *
   const size_t smem = 2 * (size_t)HAND_CHUNK * sizeof(float4);
   static bool attr_set = false;
   if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(hand_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  a.matches = (int *)ctx->ensure_work(sizeof(int) * (size_t)S);
+  if (!a.matches) { ctx->err = "hop_hand_overlap: work buffer allocation failed"; return HOP_ENOMEM; }
   {
     ProfScope ps(ctx, HOP_PROF_HAND);
+    HOP_CUDA(ctx, cudaMemsetAsync(a.matches, 0, sizeof(int) * (size_t)S, ctx->stream));
+    if (a.nf > 0) {
+      hand_match_kernel<<<dim3(S, (a.nf + MATCH_THREADS - 1) / MATCH_THREADS), MATCH_THREADS, 0, ctx->stream>>>(a);
+      ctx->launches += 1;
+    }
     hand_overlap_kernel<<<(S + HAND_WARPS - 1) / HAND_WARPS, HAND_WARPS * 32, smem, ctx->stream>>>(a);
     ctx->launches += 1;
     if (d_best) { argmin_kernel<<<1, 1024, 0, ctx->stream>>>(d_cost, S, d_best); ctx->launches += 1; }

@@ -135,6 +135,7 @@ def load_library():
     L.hop_compute_ppf.restype = None
     L.hop_super4pcs_run.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp]
     L.hop_cluster_poses.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
+    L.hop_cluster_poses_gpu.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
     L.hop_hand_overlap.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, C.c_int, _vp, _vp]
     L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
@@ -318,7 +319,7 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
-    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9}
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10}
 
     def profile_enable(self, on=True):
         self._check(self.L.hop_profile_enable(self.h, int(on)))
@@ -435,6 +436,19 @@ class Context:
         self._check(self.L.hop_hand_overlap(self.h, finger.handle, scene_hand.handle, scene_normals.handle if scene_normals else None,
                                             scene_noswivel.handle, C.byref(params), _ptr(th), len(th), _ptr(cost), C.byref(best)))
         return cost, int(best.value)
+
+    def cluster_poses(self, poses, scores, angle_diff_deg, dist_diff, symmetry_deg=(360.0, 360.0, 360.0), ids=None):
+        """PoseEstimator::clusterPoses with the comparisons on the device (hop_cluster_poses_gpu): the same keep list as the
+        host function `cluster_poses`, in cluster order."""
+        flat = poses_to_colmajor(poses)
+        sc = _f32(scores)
+        n = len(flat)
+        idv = None if ids is None else np.ascontiguousarray(ids, np.int32)
+        sym = np.ascontiguousarray(symmetry_deg, np.float32)
+        keep = np.zeros(max(n, 1), np.int32)
+        nk = C.c_int32(0)
+        self._check(self.L.hop_cluster_poses_gpu(self.h, _ptr(flat), _ptr(sc), _ptr(idv), n, angle_diff_deg, dist_diff, _ptr(sym), _ptr(keep), C.byref(nk)))
+        return keep[: nk.value].copy()
 
     def select_topk(self, poses, scores, K, id_offset=0, frame=0):
         flat = poses_to_colmajor(poses)

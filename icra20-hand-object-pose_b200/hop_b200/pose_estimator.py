@@ -32,6 +32,7 @@ class PoseEstimator:
         self.lcp_dist = float(lcp.get("dist", 0.001))
         self.lcp_normal_angle = float(lcp.get("normal_angle", 10))
         self.max_icp_candidates = 100  # PoseEstimator.cpp:241
+        self.gpu_cluster_min = 2048    # clusterPoses: device version from this many hypotheses up (same result)
         sym = cfg.get("object_symmetry", {}).get(cfg.get("model_name", ""), {})
         self.object_symmetry = (float(sym.get("x", 360)), float(sym.get("y", 360)), float(sym.get("z", 360)))
         self._pose_hypos = []
@@ -92,7 +93,11 @@ class PoseEstimator:
         poses = np.stack([h._pose for h in self._pose_hypos])
         scores = np.array([h._lcp_score for h in self._pose_hypos], np.float32)
         ids = np.array([h._id for h in self._pose_hypos], np.int32)
-        keep = capi.cluster_poses(poses, scores, angle_diff, dist_diff, self.object_symmetry, ids)
+        # the device version decides identically; it pays from a few thousand hypotheses up
+        if len(poses) >= self.gpu_cluster_min:
+            keep = self.ctx.cluster_poses(poses, scores, angle_diff, dist_diff, self.object_symmetry, ids)
+        else:
+            keep = capi.cluster_poses(poses, scores, angle_diff, dist_diff, self.object_symmetry, ids)
         self._pose_hypos = [self._pose_hypos[k] for k in keep]
         if assign_id:
             for i, h in enumerate(self._pose_hypos):

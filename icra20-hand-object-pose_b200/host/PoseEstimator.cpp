@@ -72,7 +72,9 @@ void PoseEstimator::clusterPoses(float angle_diff, float dist_diff, bool assign_
   std::vector<int32_t> ids(n), keep(n);
   for (int i = 0; i < n; ++i) { std::memcpy(&poses[16 * (size_t)i], _pose_hypos[i]._pose.data(), 64); scores[i] = _pose_hypos[i]._lcp_score; ids[i] = _pose_hypos[i]._id; }
   int32_t nk = 0;
-  check(hop_cluster_poses(poses.data(), scores.data(), ids.data(), n, angle_diff, dist_diff, sym, keep.data(), &nk), "hop_cluster_poses");
+  // the device version decides identically; it pays from a few thousand hypotheses up
+  if (n >= 2048) check(hop_cluster_poses_gpu(ctx, poses.data(), scores.data(), ids.data(), n, angle_diff, dist_diff, sym, keep.data(), &nk), "hop_cluster_poses_gpu");
+  else check(hop_cluster_poses(poses.data(), scores.data(), ids.data(), n, angle_diff, dist_diff, sym, keep.data(), &nk), "hop_cluster_poses");
   std::vector<PoseHypo> out;
   for (int k = 0; k < nk; ++k) out.push_back(_pose_hypos[keep[k]]);
   _pose_hypos.swap(out);

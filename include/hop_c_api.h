@@ -99,6 +99,7 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 #define HOP_PROF_ICP_FUSED 7      /* icp_fused_kernel: the whole ICP of a batch in one launch (default pipeline) */
 #define HOP_PROF_S4_PAIRS 8       /* K2a: extract_pairs_kernel + selection (all trials) */
 #define HOP_PROF_S4_JOIN 9        /* K2b: prepare_pairs + congruent_join (count, scan, fill) */
+#define HOP_PROF_CLUSTER 10       /* hop_cluster_poses_gpu: all block launches of one call = one span */
 #define HOP_PROF_KINDS 12
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
@@ -218,6 +219,11 @@ int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_poses, floa
  * axis, negative = no folding).  keep_out (capacity n): indices of the kept hypotheses in cluster order. */
 int hop_cluster_poses(const float *poses, const float *scores, const int32_t *ids, int n, float angle_diff_deg, float dist_diff,
                       const float *symmetry_deg, int32_t *keep_out, int32_t *n_keep);
+/* The same decisions with the O(n x clusters) comparisons on the device (sorted blocks of 1024: block vs kept clusters on all
+ * SMs, then an exact in-block greedy walk over a shared-memory bit matrix).  Identical keep list; worth it from a few
+ * thousand hypotheses up (the host loop needs 0.5 s at 20 k spread-out hypotheses, 13 s at 65 k). */
+int hop_cluster_poses_gpu(hop_ctx *ctx, const float *poses, const float *scores, const int32_t *ids, int n, float angle_diff_deg,
+                          float dist_diff, const float *symmetry_deg, int32_t *keep_out, int32_t *n_keep);
 
 /* ---- K1: hand-state overlap objective (the function the reference's swarm minimises) ------------------------------- */
 #define HOP_MAX_FINGER_BINS 32

@@ -200,3 +200,35 @@ def test_verify_lcp_c5_batch_of_replicated_sets(ctx):
     assert valid[0] == 1 and lcp[0] == 1.0 and valid[1] == 0
     assert len(hp) == int(valid.sum()) and np.array_equal(hl, lcp[valid.astype(bool)])
     P.free()
+
+
+@pytest.mark.parametrize("n,angle,dist,sym,spread", [(3000, 30.0, 0.015, (360.0, 360.0, 360.0), "wide"), (20000, 30.0, 0.015, (0.0, 180.0, 180.0), "wide"),
+                                                    (20000, 5.0, 0.003, (360.0, 360.0, 360.0), "tight"), (1500, 5.0, 0.003, (180.0, 0.0, -1.0), "tight"),
+                                                    (1025, 30.0, 0.015, (360.0, 360.0, 360.0), "tight")])
+def test_cluster_poses_on_the_device_keeps_the_same_list(ctx, n, angle, dist, sym, spread):
+    """hop_cluster_poses_gpu against the host hop_cluster_poses (itself pinned against the reference tree's Eigen): the keep
+    list must be identical, element by element -- spread-out hypotheses (many clusters), tight ones (many suppressions per
+    cluster, ties in the score), symmetric objects, block boundaries (n = 1025)."""
+    from hop_b200 import capi
+    s, sn, conf, gt = synth.make_scene("ellipse", 500, seed=2)
+    kw = dict(rot_sigma_deg=20, trans_sigma=0.02, random_frac=0.3) if spread == "wide" else dict(rot_sigma_deg=4, trans_sigma=0.003, random_frac=0.05)
+    hyp = synth.make_hypotheses(gt, n, seed=3, **kw)
+    rng = np.random.default_rng(n)
+    sc = np.round(rng.random(n) * 50).astype(np.float32) / 50     # LCP-like scores: many exact ties -> the id decides
+    ids = rng.permutation(n).astype(np.int32)
+    ref = capi.cluster_poses(hyp, sc, angle, dist, sym, ids)
+    got = ctx.cluster_poses(hyp, sc, angle, dist, sym, ids)
+    assert len(got) == len(ref) and np.array_equal(got, ref)
+    assert 1 <= len(ref) <= n
+
+
+def test_cluster_poses_device_edge_cases(ctx):
+    from hop_b200 import capi
+    eye = np.tile(np.eye(4, dtype=np.float32), (5, 1, 1))
+    sc = np.array([0.5, 0.9, 0.9, 0.1, 0.9], np.float32)
+    assert list(ctx.cluster_poses(eye, sc, 30, 0.015)) == list(capi.cluster_poses(eye, sc, 30, 0.015)) == [1]
+    assert len(ctx.cluster_poses(eye[:0], sc[:0], 30, 0.015)) == 0
+    one = ctx.cluster_poses(eye[:1], sc[:1], 30, 0.015)
+    assert list(one) == [0]
+    far = eye.copy(); far[:, 0, 3] = np.arange(5)          # all distinct: everything kept, in score order, ties by id
+    assert list(ctx.cluster_poses(far, sc, 30, 0.015)) == list(capi.cluster_poses(far, sc, 30, 0.015)) == [1, 2, 4, 0, 3]

@@ -172,6 +172,25 @@ def main():
                       "kernel_ms": {"k2a_pairs": pr_ms, "k2b_join": jn_ms, "k3_verify": v_ms}, "dtype": "f32 / int32",
                       "roofline": {"bound": "hbm", "kernel": "verify_lcp_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                    "traffic": None, "algorithmic_bytes_per_launch": M * bytes_quad}}), file=out, flush=True)
+    # ---------------- clusterPoses: host loop vs the device version (identical keep list) ----------------
+    n_cl = 20000 if args.sizes == "C2" else 65536
+    hyp = synth.make_hypotheses(gt, n_cl, seed=3, rot_sigma_deg=20, trans_sigma=0.02, random_frac=0.3)
+    sc = np.random.default_rng(0).random(n_cl).astype(np.float32)
+
+    def cl():
+        res["cl"] = ctx.cluster_poses(hyp, sc, 30.0, 0.015)
+
+    dt, prof = timed(cl)
+    cpu3 = None
+    if not args.no_cpu_baseline and args.sizes == "C2":
+        t0 = time.perf_counter()
+        ref_keep = capi.cluster_poses(hyp, sc, 30.0, 0.015)
+        tc = time.perf_counter() - t0
+        cpu3 = {"value": n_cl / tc, "unit": "hypotheses/s", "cores": 1, "kind": "port", "ms_per_call": tc * 1e3,
+                "sample": "the whole batch, hop_cluster_poses (the reference's sequential loop, Euler angles hoisted)", "same_keep_list": bool(np.array_equal(ref_keep, res["cl"]))}
+    print(json.dumps({"stage": "clusterPoses(30 deg, 15 mm) on the device (hop_cluster_poses_gpu)", "metric": "hypotheses clustered/sec", "value": n_cl / dt,
+                      "unit": "hypotheses/s", "cpu_baseline": cpu3, "e2e": {"value": n_cl / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3},
+                      "config": {"n": n_cl, "clusters": int(len(res["cl"]))}, "kernel_ms": prof["cluster"][0] / max(prof["cluster"][1], 1)}), file=out, flush=True)
     ctx.close()
 
 
