@@ -29,7 +29,7 @@
 struct NNGridDev {
   float ox, oy, oz;  // min corner
   float inv_e;       // 1 / voxel edge
-  int nx, ny, nz;
+  int nx, ny, nz;    // multiples of 4: voxels are stored in 4x4x4 tiles (see nn_vox_index)
   float radius;      // queries are exact for neighbours within this distance
   const uint2 *cell;
   const float4 *cand;
@@ -113,6 +113,20 @@ __device__ __forceinline__ float warp_sum(float v) {
 }
 
 // ---- exact nearest neighbour through the voxel grid ------------------------------------------------------------
+// Storage order of the voxels: 4x4x4 tiles, tile-linear.  The 64 cells of a tile are 512 contiguous bytes and (the
+// candidate lists being allocated by a scan in this order) their lists are contiguous too, so the 32 lanes of a warp that
+// walks a Morton-sorted cloud gather from a handful of cache lines instead of one line per lane.
+__host__ __device__ __forceinline__ size_t nn_vox_index(int ix, int iy, int iz, int nx, int ny) {
+  const size_t tile = ((size_t)(iz >> 2) * (size_t)(ny >> 2) + (size_t)(iy >> 2)) * (size_t)(nx >> 2) + (size_t)(ix >> 2);
+  return tile * 64 + (size_t)(((iz & 3) << 4) | ((iy & 3) << 2) | (ix & 3));
+}
+__host__ __device__ __forceinline__ void nn_vox_coords(size_t v, int nx, int ny, int &ix, int &iy, int &iz) {
+  const size_t tile = v >> 6;
+  const int l = (int)(v & 63), tnx = nx >> 2, tny = ny >> 2;
+  ix = (int)(tile % tnx) * 4 + (l & 3);
+  iy = (int)((tile / tnx) % tny) * 4 + ((l >> 2) & 3);
+  iz = (int)(tile / ((size_t)tnx * tny)) * 4 + (l >> 4);
+}
 // returns the point index (or -1) and its squared distance; exact for neighbours within g.radius.
 __device__ __forceinline__ int nn_query(const NNGridDev &g, float px, float py, float pz, float &best_d2, float4 &best_pt) {
   float fx = (px - g.ox) * g.inv_e, fy = (py - g.oy) * g.inv_e, fz = (pz - g.oz) * g.inv_e;
@@ -121,7 +135,7 @@ __device__ __forceinline__ int nn_query(const NNGridDev &g, float px, float py, 
   int best = -1;
   // (the negated comparison also rejects NaN coordinates)
   if (!(fx >= 0.f && fy >= 0.f && fz >= 0.f) || ix >= g.nx || iy >= g.ny || iz >= g.nz) return -1;
-  uint2 c = __ldg(&g.cell[((size_t)iz * g.ny + iy) * g.nx + ix]);
+  uint2 c = __ldg(&g.cell[nn_vox_index(ix, iy, iz, g.nx, g.ny)]);
   const float4 *lst = g.cand + c.x;
   for (uint32_t k = 0; k < c.y; ++k) {
     float4 q = __ldg(&lst[k]);

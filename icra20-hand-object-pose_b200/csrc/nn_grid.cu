@@ -62,7 +62,7 @@ __global__ void grid_scatter_kernel(GridGeom g, const float4 *__restrict__ pw, i
       if ((unsigned)vx >= (unsigned)g.nx || (unsigned)vy >= (unsigned)g.ny || (unsigned)vz >= (unsigned)g.nz) continue;
       float d2 = vox_center_d2(g, vx, vy, vz, p);
       if (d2 > g.rc2) continue;                                                        // (1)
-      size_t v = ((size_t)vz * g.ny + vy) * g.nx + vx;
+      size_t v = nn_vox_index(vx, vy, vz, g.nx, g.ny);
       if (PASS == 0) {
         atomicMin(&near[v], ((unsigned long long)__float_as_uint(d2) << 32) | (unsigned int)i);
       } else {
@@ -107,7 +107,8 @@ __global__ void grid_finalize_kernel(GridGeom g, size_t n_vox, const unsigned in
       l[b + 1] = key;
     }
     if (c > 1) {
-      const int vx = (int)(v % g.nx), vy = (int)((v / g.nx) % g.ny), vz = (int)(v / ((size_t)g.nx * g.ny));
+      int vx, vy, vz;
+      nn_vox_coords(v, g.nx, g.ny, vx, vy, vz);
       unsigned int kept = 0;
       for (unsigned int a = 0; a < c; ++a) {
         const float4 m = l[a];
@@ -242,9 +243,10 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
     float pad = radius + 2.f * e;
     g.e = e;
     g.ox = cloud->bbox_min[0] - pad; g.oy = cloud->bbox_min[1] - pad; g.oz = cloud->bbox_min[2] - pad;
-    g.nx = (int)std::ceil((cloud->bbox_max[0] - cloud->bbox_min[0] + 2.f * pad) / e) + 1;
-    g.ny = (int)std::ceil((cloud->bbox_max[1] - cloud->bbox_min[1] + 2.f * pad) / e) + 1;
-    g.nz = (int)std::ceil((cloud->bbox_max[2] - cloud->bbox_min[2] + 2.f * pad) / e) + 1;
+    auto tiles = [](float extent, float edge) { return (((int)std::ceil(extent / edge) + 1) + 3) / 4 * 4; };  // whole 4x4x4 tiles
+    g.nx = tiles(cloud->bbox_max[0] - cloud->bbox_min[0] + 2.f * pad, e);
+    g.ny = tiles(cloud->bbox_max[1] - cloud->bbox_min[1] + 2.f * pad, e);
+    g.nz = tiles(cloud->bbox_max[2] - cloud->bbox_min[2] + 2.f * pad, e);
     if ((int64_t)g.nx * g.ny * g.nz <= kMaxVox) break;
     e *= 1.26f;
   }

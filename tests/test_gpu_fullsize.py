@@ -28,6 +28,29 @@ def _workload(name, H=None, seed=11):
     return wl, m, mn, s, sn, conf, gt, hyp
 
 
+def _p2plane_fit(s, sn, m, mn, poses, dist=0.01, angle=45.0):
+    """the ICP objective of Utils::runICP at a pose: RMS of n_m . (X s - m) over the correspondences that pass the 1 cm and
+    45 deg gates (X = pose^-1 carries the scene into the model frame), and how many pass"""
+    from scipy.spatial import cKDTree
+    tree = cKDTree(m.astype(np.float64))
+    rms, cnt = [], []
+    for T in np.asarray(poses, np.float64):
+        if not np.isfinite(T).all() or abs(np.linalg.det(T[:3, :3])) < 1e-6:
+            rms.append(np.inf); cnt.append(0)
+            continue
+        X = np.linalg.inv(T)
+        p = s.astype(np.float64) @ X[:3, :3].T + X[:3, 3]
+        n = sn.astype(np.float64) @ X[:3, :3].T
+        d, j = tree.query(p, distance_upper_bound=dist)
+        okc = np.isfinite(d)
+        jj = np.where(okc, j, 0)
+        okc &= np.einsum("ij,ij->i", n, mn[jj].astype(np.float64)) > np.cos(np.deg2rad(angle))
+        r = np.einsum("ij,ij->i", mn[jj].astype(np.float64), p - m[jj].astype(np.float64))[okc]
+        rms.append(np.sqrt(np.mean(r * r)) if len(r) else np.inf)
+        cnt.append(len(r))
+    return np.array(rms), np.array(cnt)
+
+
 def _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, max_iter, frac=0.9, by_score=False):
     ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp[idx], max_iter=max_iter)
     dt, dr = synth.pose_error(got[idx], ref)
@@ -35,10 +58,10 @@ def _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, max_iter, 
     if by_score:
         # Long runs on objects whose visible part leaves a direction unconstrained (one or two faces of a box, a cylinder's
         # axis): point-to-plane ICP slides freely there and 50 iterations of rounding decide where it stops.  The poses are
-        # then compared by what the pipeline does with them: the reference's own LCP score (Utils::computeLCP restatement).
-        _, sc_got = O.select_best(s, sn, m, mn, got[idx])
-        _, sc_ref = O.select_best(s, sn, m, mn, ref)
-        ok = ok | (sc_got >= 0.97 * sc_ref - 1.0)
+        # then compared by the quantity ICP minimises: the point-to-plane RMS over the gated correspondences (and their number).
+        rms_g, n_g = _p2plane_fit(s, sn, m, mn, got[idx])
+        rms_r, n_r = _p2plane_fit(s, sn, m, mn, ref)
+        ok = ok | ((rms_g <= 1.05 * rms_r + 2e-5) & (n_g >= 0.97 * n_r - 2))
     assert ok.mean() >= frac, (ok.mean(), np.sort(dt)[-5:], np.sort(dr)[-5:])
     # (the 10 % fully random hypotheses sit at the edge of the 1 cm gate: they may keep or lose their last correspondences in
     #  a different iteration than the oracle's run of the same chaotic sequence)
@@ -102,13 +125,19 @@ def test_c3_three_objects_icp_to_convergence(ctx):
         scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
         p = ctx.icp_params(max_iter=50)
         got, it, cv = ctx.icp_refine(scene, model, hyp, p)
+        assert np.isfinite(got).all(), (name, np.nonzero(~np.isfinite(got).all(axis=(1, 2)))[0][:10])
         idx = np.arange(0, 8192, 128)
         _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, 50, frac=0.85, by_score=True)
         assert (it < 50).mean() > 0.9 and it.max() <= 50
+        # fixed point in the sense that matters on a partly unconstrained object: refining the refined poses again does not
+        # lower the objective any further (it may still slide along the free directions)
         again, it2, cv2 = ctx.icp_refine(scene, model, got, p)
-        conv = cv.astype(bool) & (it < 50)
-        dt, dr = synth.pose_error(again[conv], got[conv])
-        assert np.median(dt) <= 1e-4 and np.median(np.deg2rad(dr)) <= 2e-3
+        assert np.isfinite(again).all(), (name, "second refinement")
+        conv = np.nonzero(cv.astype(bool) & (it < 50))[0][:64]
+        rms_1, n_1 = _p2plane_fit(s, sn, m, mn, got[conv])
+        rms_2, n_2 = _p2plane_fit(s, sn, m, mn, again[conv])
+        # (PCL's stop rule is on |dMSE| < 1e-6 m^2, so a restart may still find a little more: most, not all, stay put)
+        assert np.mean(rms_2 >= 0.95 * rms_1 - 2e-5) >= 0.8 and np.mean(np.abs(n_2 - n_1) <= 0.03 * n_1 + 2) >= 0.8
         scene.free(); model.free()
 
 
