@@ -33,7 +33,7 @@ TOPK = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one icp_fused_kernel launch (a whole C2 batch), from the ncu --set full
 # capture summarised in profiles/r01_ncu_icp_fused_kernel_C2.txt; other workloads were not captured -> null
 TRAFFIC_BYTES_PER_LAUNCH = {"C2": 30083840}
-N_FRAMES = 4  # distinct synthetic frames cycled through the steps
+N_FRAMES = 4  # distinct synthetic frames cycled through the steps (a step = `frames_per_step` consecutive frames, default 1)
 
 
 def parse():
@@ -182,6 +182,7 @@ def main():
 
     model_np, frames = make_frames(wl, rank)
     H, ns, nm = wl["H"], wl["n_scene"], wl["n_model"]
+    FPS = int(wl.get("frames_per_step", 1))   # frames of one rank in one step (C4: 16), one all-gather of winners per step
     model = ctx.upload_cloud(*model_np)
     icp_p = ctx.icp_params(max_iter=wl["max_iter"], solver=args.solver)
     lcp_p = ctx.lcp_params()
@@ -196,20 +197,23 @@ def main():
     d_iters = torch.zeros(H, dtype=torch.int32, device=dev)
     d_conv = torch.zeros(H, dtype=torch.int32, device=dev)
     d_score = torch.zeros(H, dtype=torch.float32, device=dev)
-    d_send = torch.zeros(TOPK * 80, dtype=torch.uint8, device=dev)
-    d_recv = torch.zeros(world * TOPK * 80, dtype=torch.uint8, device=dev)
+    d_send = torch.zeros(FPS * TOPK * 80, dtype=torch.uint8, device=dev)
+    d_recv = torch.zeros(world * FPS * TOPK * 80, dtype=torch.uint8, device=dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step_value(fi, evs=None):
-        d_pose.copy_(d_hyp[fi])  # ICP refines in place; keep the inputs pristine (device-to-device, 64 KB)
-        sc = scenes[fi]
-        sc.drop_nn()  # the scene's reciprocal-NN grid is per-frame work: rebuilt inside the timed step
+    def step_value(k, evs=None, on_frame=None):
         if evs: evs[0].record(stream)
-        ctx.icp_refine_dev(sc, model, d_pose.data_ptr(), H, icp_p, d_iters.data_ptr(), d_conv.data_ptr())
-        if evs: evs[1].record(stream)
-        ctx.lcp_score_dev(sc, model, d_pose.data_ptr(), H, lcp_p, d_score.data_ptr())
-        if evs: evs[2].record(stream)
-        ctx.select_topk_dev(d_pose.data_ptr(), d_score.data_ptr(), H, TOPK, d_send.data_ptr(), id_offset=0, frame=rank)
+        for f in range(FPS):
+            fi = (k * FPS + f) % N_FRAMES
+            d_pose.copy_(d_hyp[fi])  # ICP refines in place; keep the inputs pristine (device-to-device, 64 KB per 1024)
+            sc = scenes[fi]
+            sc.drop_nn()  # the scene's reciprocal-NN grid is per-frame work: rebuilt inside the timed step
+            ctx.icp_refine_dev(sc, model, d_pose.data_ptr(), H, icp_p, d_iters.data_ptr(), d_conv.data_ptr())
+            if evs and f == 0: evs[1].record(stream)
+            ctx.lcp_score_dev(sc, model, d_pose.data_ptr(), H, lcp_p, d_score.data_ptr())
+            if evs and f == 0: evs[2].record(stream)
+            ctx.select_topk_dev(d_pose.data_ptr(), d_score.data_ptr(), H, TOPK, d_send.data_ptr() + f * TOPK * 80, id_offset=0, frame=rank * FPS + f)
+            if on_frame: on_frame()
         if world > 1:
             dist.all_gather_into_tensor(d_recv, d_send)
         if evs: evs[3].record(stream)
@@ -223,7 +227,7 @@ def main():
     # ---- warm-up ----
     # (every distinct frame is visited at least once: a frame's first visit allocates its scene grid)
     for w in range(max(args.warmup, N_FRAMES)):
-        step_value(w % N_FRAMES)
+        step_value(w)
     barrier()
 
     # ---- timed: K steps, device time per step from events, L2 flushed before each ----
@@ -234,7 +238,7 @@ def main():
     barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        step_value(k % N_FRAMES, ev[k])
+        step_value(k, ev[k])
     barrier()
     launches = ctx.launch_count() - l0
     t_step = np.array([e[0].elapsed_time(e[3]) for e in ev])
@@ -246,12 +250,16 @@ def main():
     # ---- per-kernel device time: the same K steps again with libhop's event profiling on (CUDA events recorded on
     #      the launching stream around every launch of each kernel family; kept out of the `value` timing) ----
     ctx.profile_enable(True)
-    iters_sum = 0
+    iters_box = [0]
+
+    def count_iters():
+        torch.cuda.synchronize()
+        iters_box[0] += int(torch.clamp(d_iters, min=1).sum().item())
+
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        step_value(k % N_FRAMES)
-        torch.cuda.synchronize()
-        iters_sum += int(torch.clamp(d_iters, min=1).sum().item())
+        step_value(k, None, count_iters)
+    iters_sum = iters_box[0]
     prof = ctx.profile_read()
     ctx.profile_enable(False)
 
@@ -275,16 +283,19 @@ def main():
     def ptr(a):
         return a.ctypes.data_as(vp)
 
-    def step_e2e(fi):
-        p = pin[fi]
-        p["work"][...] = p["hyp"]
-        ctx._check(ctx.L.hop_cloud_update(ctx.h, e2e_scene.handle, ptr(p["xyz"]), ptr(p["nrm"]), ptr(p["conf"]), ns))
-        ctx._check(ctx.L.hop_icp_refine(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(icp_p), ptr(p["iters"]), ptr(p["conv"])))
-        ctx._check(ctx.L.hop_lcp_score(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(lcp_p), 0, ptr(p["scores"])))
-        return int(np.argmax(p["scores"]))  # selectBest's arg-max on the host, like the reference
+    def step_e2e(k):
+        best = []
+        for f in range(FPS):
+            p = pin[(k * FPS + f) % N_FRAMES]
+            p["work"][...] = p["hyp"]
+            ctx._check(ctx.L.hop_cloud_update(ctx.h, e2e_scene.handle, ptr(p["xyz"]), ptr(p["nrm"]), ptr(p["conf"]), ns))
+            ctx._check(ctx.L.hop_icp_refine(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(icp_p), ptr(p["iters"]), ptr(p["conv"])))
+            ctx._check(ctx.L.hop_lcp_score(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(lcp_p), 0, ptr(p["scores"])))
+            best.append(int(np.argmax(p["scores"])))  # selectBest's arg-max on the host, like the reference
+        return best
 
     for w in range(max(args.warmup, N_FRAMES)):
-        step_e2e(w % N_FRAMES)
+        step_e2e(w)
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2e_ms = 0.0
@@ -292,14 +303,14 @@ def main():
         flush.fill_(k & 0xFF)
         torch.cuda.synchronize()
         e0.record(stream)
-        step_e2e(k % N_FRAMES)
+        step_e2e(k)
         e1.record(stream)
         torch.cuda.synchronize()
         e2e_ms += e0.elapsed_time(e1)
     barrier()
     clocks = sampler.summary()
-    h2d = ns * 7 * 4 + 2 * H * 64
-    d2h = H * 64 + H * 8 + H * 4
+    h2d = FPS * (ns * 7 * 4 + 2 * H * 64)
+    d2h = FPS * (H * 64 + H * 8 + H * 4)
 
     # ---- max over ranks ----
     if world > 1:
@@ -313,8 +324,8 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        value = world * H * args.steps / (total_ms * 1e-3)
-        e2e_value = world * H * args.steps / (e2e_ms * 1e-3)
+        value = world * FPS * H * args.steps / (total_ms * 1e-3)
+        e2e_value = world * FPS * H * args.steps / (e2e_ms * 1e-3)
         # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
         # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
         fused = args.solver == 0
@@ -323,14 +334,15 @@ def main():
         achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
         icp_ms = float(np.mean(t_icp))
         kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
+        stage_note = "first frame of the step" if FPS > 1 else "the step's frame"
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": 1, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
+            "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": FPS, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
                        "icp_solver": "exact" if args.solver == 0 else "gauss-newton", "mean_icp_iterations": iters_mean,
                        "nn_grid_icp": g_icp, "nn_grid_lcp": g_lcp,
-                       "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps},
+                       "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps, "of": stage_note},
                        "kernel_ms": kernels},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),

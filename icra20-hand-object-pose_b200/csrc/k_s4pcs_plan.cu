@@ -72,6 +72,7 @@ struct Planner {
   std::mt19937 random_generator;    // randomGenerator_
   std::mt19937 point_index_engine;  // _point_index_engine, seeded 0 (matchBase.hpp:76)
   float max_base_diameter = -1.f;
+  std::vector<unsigned char> member;   // scratch of select_random_triangle
 
   explicit Planner(hop_s4pcs_plan &p) : pl(p), random_generator(p.opt.random_seed ? p.opt.random_seed : std::mt19937::default_seed), point_index_engine(0) {}
 
@@ -153,10 +154,13 @@ struct Planner {
     point_probs[first_point] *= pl.opt.dispersion;
     sample_pool.clear();
     std::vector<float> probs;
-    for (int i = 0; i < number_of_points; ++i) {
-      if (i == first_point) continue;
-      if (has_ppf(P[first_point], P[i])) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
-    }
+    // (the membership tests -- three acos and a set lookup per point -- are the planner's O(N) cost: evaluated on all host
+    //  threads with the same libm, gathered in index order, so the pool is the one a sequential loop builds)
+    member.assign(number_of_points, 0);
+#pragma omp parallel for schedule(static) if (number_of_points >= 4096)
+    for (int i = 0; i < number_of_points; ++i) member[i] = (i != first_point && has_ppf(P[first_point], P[i])) ? 1 : 0;
+    for (int i = 0; i < number_of_points; ++i)
+      if (member[i]) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
     if (sample_pool.size() < 3) return false;
     const float sq_max_base_diameter = max_base_diameter * max_base_diameter;
     for (int i = 0; (size_t)i < sample_pool.size() * sample_pool.size() / 4; ++i) {
@@ -178,12 +182,17 @@ struct Planner {
     if (base2 == -1 || base3 == -1) return false;
     std::vector<int> backup = sample_pool;
     sample_pool.clear();
-    for (int i = 0; (size_t)i < backup.size(); ++i) {
+    const int nb = (int)backup.size();
+    member.assign(nb, 0);
+#pragma omp parallel for schedule(static) if (nb >= 4096)
+    for (int i = 0; i < nb; ++i) {
       if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
-      // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
-      // a point id (match4pcsBase.hpp:159): reproduced
-      if (has_ppf(P[base2], P[backup[i]]) && has_ppf(P[base3], P[backup[i]])) sample_pool.push_back(i);
+      member[i] = (has_ppf(P[base2], P[backup[i]]) && has_ppf(P[base3], P[backup[i]])) ? 1 : 0;
     }
+    // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
+    // a point id (match4pcsBase.hpp:159): reproduced
+    for (int i = 0; i < nb; ++i)
+      if (member[i]) sample_pool.push_back(i);
     if (sample_pool.size() < 1) return false;
     return base1 != -1 && base2 != -1 && base3 != -1;
   }

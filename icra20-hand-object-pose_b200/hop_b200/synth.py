@@ -174,6 +174,8 @@ def workload(name):
         "C2": dict(model="ellipse", n_scene=2000, n_model=10000, H=1024, max_iter=10),
         "headline": dict(model="ellipse", n_scene=10000, n_model=10000, H=16384, max_iter=10),
         "C3": dict(model="cuboid", n_scene=2000, n_model=10000, H=8192, max_iter=50),
+        # 128 depth frames x 4096 hypotheses over 8 GPUs = 16 frames per rank per step (weak scaling: every rank its own frames)
+        "C4": dict(model="ellipse", n_scene=2000, n_model=10000, H=4096, max_iter=10, frames_per_step=16),
         "C5": dict(model="ellipse", n_scene=50000, n_model=50000, H=65536, max_iter=10),
         "tiny": dict(model="ellipse", n_scene=500, n_model=2000, H=64, max_iter=10),
     }
