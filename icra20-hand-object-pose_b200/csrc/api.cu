@@ -123,6 +123,23 @@ int cloud_fill(hop_ctx *ctx, hop_cloud *c, const float *xyz, const float *nrm, c
 
 }  // namespace
 
+// capacity for n points, no contents (the caller fills d_pw / d_nv on the device and sets the bounding box)
+int hop_cloud_reserve(hop_ctx *ctx, hop_cloud *c, int n) {
+  if (n < 0) return HOP_EINVAL;
+  const int n_padded = std::max(HOP_TILE_PTS, (n + HOP_TILE_PTS - 1) / HOP_TILE_PTS * HOP_TILE_PTS);
+  if (n_padded > c->capacity) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(c->d_pw); cudaFree(c->d_nv); cudaFree(c->d_stage);
+    c->d_pw = c->d_nv = nullptr; c->d_stage = nullptr;
+    HOP_CUDA(ctx, cudaMalloc(&c->d_pw, sizeof(float4) * (size_t)n_padded));
+    HOP_CUDA(ctx, cudaMalloc(&c->d_nv, sizeof(float4) * (size_t)n_padded));
+    HOP_CUDA(ctx, cudaMalloc(&c->d_stage, sizeof(float) * 7 * (size_t)n_padded));
+    c->capacity = n_padded;
+  }
+  c->n = n; c->n_padded = n_padded; c->version++;
+  return HOP_OK;
+}
+
 extern "C" {
 
 int hop_create(int device, hop_ctx **out) {

@@ -22,6 +22,13 @@ class IcpParams(C.Structure):
                 ("mode", C.c_int32), ("solver", C.c_int32), ("team_warps", C.c_int32), ("pipeline", C.c_int32)]
 
 
+class FrameParams(C.Structure):
+    """hop_frame_params (include/hop_c_api.h): the per-frame front end of main_realdata_auto.cpp:54-96,144-181"""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("leaf_dense", C.c_float),
+                ("cam_in_handbase", C.c_float * 16), ("handbase_in_cam", C.c_float * 16), ("box_min", C.c_float * 3), ("box_max", C.c_float * 3),
+                ("normal_radius", C.c_float), ("leaf_object", C.c_float), ("viewpoint", C.c_float * 3)]
+
+
 class LcpParams(C.Structure):
     _fields_ = [("dist", C.c_float), ("angle_deg", C.c_float), ("use_normal", C.c_int32), ("use_dot_score", C.c_int32),
                 ("use_reciprocal", C.c_int32), ("team_warps", C.c_int32)]
@@ -135,6 +142,10 @@ def load_library():
     L.hop_compute_ppf.restype = None
     L.hop_super4pcs_run.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp]
     L.hop_cluster_poses.argtypes = [_vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
+    L.hop_default_frame_params.argtypes = [C.POINTER(FrameParams)]
+    L.hop_default_frame_params.restype = None
+    L.hop_frame_to_scene.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(FrameParams), C.POINTER(_vp), _vp]
+    L.hop_cloud_download.argtypes = [_vp, _vp, _vp, _vp, _vp]
     L.hop_cluster_poses_gpu.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.c_float, C.c_float, _vp, _vp, _vp]
     L.hop_hand_overlap.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, C.c_int, _vp, _vp]
     L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
@@ -261,6 +272,13 @@ class Cloud:
         self.ctx._check(self.ctx.L.hop_cloud_update(self.ctx.h, self.handle, _ptr(xyz), _ptr(nrm), _ptr(prob), len(xyz)))
         self.n = len(xyz)
 
+    def download(self):
+        """(xyz (n,3), normals (n,3), confidence (n,)) of the device cloud"""
+        n = int(self.ctx.L.hop_cloud_size(self.handle))
+        xyz, nrm, prob = np.zeros((n, 3), np.float32), np.zeros((n, 3), np.float32), np.zeros(n, np.float32)
+        self.ctx._check(self.ctx.L.hop_cloud_download(self.ctx.h, self.handle, _ptr(xyz), _ptr(nrm), _ptr(prob)))
+        return xyz, nrm, prob
+
     def prepare_nn(self, radius, voxel=0.0):
         stats = (C.c_int64 * 4)()
         self.ctx._check(self.ctx.L.hop_cloud_prepare_nn(self.ctx.h, self.handle, radius, voxel, stats))
@@ -319,7 +337,7 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
-    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10}
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10, "frame": 11}
 
     def profile_enable(self, on=True):
         self._check(self.L.hop_profile_enable(self.h, int(on)))
@@ -436,6 +454,38 @@ class Context:
         self._check(self.L.hop_hand_overlap(self.h, finger.handle, scene_hand.handle, scene_normals.handle if scene_normals else None,
                                             scene_noswivel.handle, C.byref(params), _ptr(th), len(th), _ptr(cost), C.byref(best)))
         return cost, int(best.value)
+
+    def frame_params(self, K=None, cam_in_handbase=None, handbase_in_cam=None, **kw):
+        """hop_frame_params with the reference's defaults; K = (fx, fy, cx, cy); the two 4x4 matrices are numpy (row-major) arrays --
+        handbase_in_cam is `cam_in_handbase.inverse()` as the caller's host code computes it (float32 numeric inverse)."""
+        p = FrameParams()
+        self.L.hop_default_frame_params(C.byref(p))
+        if K is not None:
+            p.fx, p.fy, p.cx, p.cy = [float(v) for v in K]
+        if cam_in_handbase is not None:
+            T = np.asarray(cam_in_handbase, np.float32).reshape(4, 4)
+            Ti = np.asarray(handbase_in_cam, np.float32).reshape(4, 4) if handbase_in_cam is not None else np.linalg.inv(T.astype(np.float64)).astype(np.float32)
+            p.cam_in_handbase[:] = T.T.reshape(-1).tolist()
+            p.handbase_in_cam[:] = Ti.T.reshape(-1).tolist()
+        for k, v in kw.items():
+            if k in ("box_min", "box_max", "viewpoint"):
+                getattr(p, k)[:] = [float(x) for x in v]
+            else:
+                setattr(p, k, v)
+        return p
+
+    def frame_to_scene(self, depth_mm, params, scene=None):
+        """the frame's front end on the device: uint16 depth image [mm] -> object-segment Cloud (+ the 5 stage counts)"""
+        d = np.ascontiguousarray(depth_mm, np.uint16)
+        h, w = d.shape
+        handle = _vp(scene.handle.value if scene is not None else None)
+        counts = np.zeros(5, np.int32)
+        self._check(self.L.hop_frame_to_scene(self.h, _ptr(d), w, h, C.byref(params), C.byref(handle), _ptr(counts)))
+        n = int(self.L.hop_cloud_size(handle))
+        if scene is not None:
+            scene.n = n
+            return scene, counts
+        return Cloud(self, handle, n), counts
 
     def cluster_poses(self, poses, scores, angle_diff_deg, dist_diff, symmetry_deg=(360.0, 360.0, 360.0), ids=None):
         """PoseEstimator::clusterPoses with the comparisons on the device (hop_cluster_poses_gpu): the same keep list as the

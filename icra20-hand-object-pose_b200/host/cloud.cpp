@@ -356,3 +356,30 @@ void estimateNormals(Cloud &c, float radius, const float *vp) {
     c.nrm[3 * i] = nx; c.nrm[3 * i + 1] = ny; c.nrm[3 * i + 2] = nz;
   }
 }
+
+void frameToObjectSegment(const std::vector<float> &depth_m, int w, int h, const Mat3f &K, const Mat4f &cam_in_handbase, Cloud &object_segment,
+                          Cloud *cropped) {
+  Cloud scene;
+  convert3dOrganized(depth_m, w, h, K, scene);
+  passThrough(scene, scene, 2, 0.1f, 2.0f);
+  downsamplePointCloud(scene, scene, 0.001f);
+  transformPointCloudWithNormals(scene, scene, cam_in_handbase);
+  passThrough(scene, scene, 2, -0.12f, 0.05f);
+  passThrough(scene, scene, 0, -0.25f, -0.07f);
+  passThrough(scene, scene, 1, -0.2f, 0.2f);
+  transformPointCloudWithNormals(scene, scene, cam_in_handbase.inverse());
+  if (cropped) *cropped = scene;
+  // object segment: normals over 3 mm, 3 mm voxels, normals towards the camera (main_realdata_auto.cpp:154-177)
+  object_segment = scene;
+  if (object_segment.size() == 0) return;
+  const float origin[3] = {0, 0, 0};
+  estimateNormals(object_segment, 0.003f, origin);
+  downsamplePointCloud(object_segment, object_segment, 0.003f);
+  removeAllNaNFromPointCloud(object_segment);
+  for (size_t i = 0; i < object_segment.size(); ++i) {   // pcl::flipNormalTowardsViewpoint
+    float *n = &object_segment.nrm[3 * i];
+    const float *p = &object_segment.xyz[3 * i];
+    if (-p[0] * n[0] - p[1] * n[1] - p[2] * n[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  }
+  std::fill(object_segment.conf.begin(), object_segment.conf.end(), 1.f);
+}

@@ -36,3 +36,9 @@ void transformPointCloudWithNormals(const Cloud &in, Cloud &out, const Mat4f &T)
 void estimateNormals(Cloud &c, float radius, const float *viewpoint);                             // PCA over a radius, flipped to the viewpoint
 void removeAllNaNFromPointCloud(Cloud &c);
 void getMinMax3D(const Cloud &c, float *mn, float *mx);
+
+// The per-frame front end of main_realdata_auto.cpp:54-96,144-181 as one function (what hop_frame_to_scene does on the device):
+// depth [m] -> organized cloud -> z pass-through -> VoxelGrid(1 mm) -> hand-base crop box -> normals(3 mm) -> VoxelGrid(3 mm)
+// -> NaN removal -> normals towards the camera -> confidence 1.  cropped (may be null) receives the cloud before the normals.
+void frameToObjectSegment(const std::vector<float> &depth_m, int w, int h, const Mat3f &K, const Mat4f &cam_in_handbase, Cloud &object_segment,
+                          Cloud *cropped = nullptr);

@@ -5,6 +5,10 @@
 //   host_tool voxel <in.ply> <leaf> <out.ply>   pcl::VoxelGrid restatement
 //   host_tool depthcloud <png> fx fy cx cy <out.ply>
 //   host_tool normals <in.ply> <radius> <out.ply>
+//   host_tool frame <png> fx fy cx cy <cam_in_handbase.txt> <out.bin>   the whole front end; out.bin = int32 n, then n x 7 float32
+//                                                                       (xyz, normal, confidence), then the 16 floats of
+//                                                                       cam_in_handbase.inverse() (column-major)
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <iostream>
@@ -67,6 +71,28 @@ int main(int argc, char **argv) {
       const float o[3] = {0, 0, 0};
       estimateNormals(c, (float)atof(argv[3]), o);
       return savePLYFile(argv[4], c) ? 0 : 3;
+    }
+    if (cmd == "frame" && argc >= 9) {
+      std::vector<float> d; int w, h;
+      readDepthImage(d, w, h, argv[2]);
+      if (d.empty()) return 3;
+      Mat3f K; for (int i = 0; i < 9; ++i) K.m[i] = 0; K(0, 0) = atof(argv[3]); K(1, 1) = atof(argv[4]); K(0, 2) = atof(argv[5]); K(1, 2) = atof(argv[6]); K(2, 2) = 1;
+      std::vector<float> t;
+      if (!parsePoseTxt(argv[7], t) || t.size() < 16) return 3;
+      Mat4f T; for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) T(r, c) = t[4 * r + c];
+      Cloud seg;
+      const auto t0 = std::chrono::steady_clock::now();
+      frameToObjectSegment(d, w, h, K, T, seg);
+      std::cout << "frame_ms " << std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() << "\n";
+      FILE *f = fopen(argv[8], "wb");
+      if (!f) return 3;
+      const int32_t n = (int32_t)seg.size();
+      fwrite(&n, 4, 1, f);
+      for (int32_t i = 0; i < n; ++i) { fwrite(&seg.xyz[3 * i], 4, 3, f); fwrite(&seg.nrm[3 * i], 4, 3, f); fwrite(&seg.conf[i], 4, 1, f); }
+      const Mat4f Ti = T.inverse();
+      fwrite(Ti.data(), 4, 16, f);
+      fclose(f);
+      return 0;
     }
   } catch (const std::exception &e) { std::cout << "error: " << e.what() << "\n"; return 4; }
   return 2;

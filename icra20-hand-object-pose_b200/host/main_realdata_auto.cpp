@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstring>
 #include <fstream>
 #include <iostream>
 
@@ -50,42 +51,46 @@ int main(int argc, char **argv) {
   const Mat4f handbase_in_leftarm = cfg.leftarm_in_base.inverse() * cfg.palm_in_baselink * cfg.handbase_in_palm;
   const Mat4f handbase_in_cam = cfg.cam1_in_leftarm.inverse() * handbase_in_leftarm;
 
-  std::vector<float> depth;
+  hop_ctx *ctx = nullptr;
+  if (hop_create(cfg.b200_device, &ctx) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(nullptr)); return 1; }
+
+  // the frame's front end on the device (hop_frame_to_scene = cloud.cpp's frameToObjectSegment, main_realdata_auto.cpp:54-96,
+  // 144-181): depth PNG -> back-projection -> 1 mm voxels -> hand-base crop -> normals over 3 mm -> 3 mm voxels -> normals
+  // towards the camera
+  std::vector<uint16_t> depth_mm;
   int w = 0, h = 0;
-  readDepthImage(depth, w, h, cfg.depth_path);
-  if (depth.empty()) return 1;
-  Cloud scene;
-  convert3dOrganized(depth, w, h, cfg.cam_intrinsic, scene);
-  passThrough(scene, scene, 2, 0.1f, 2.0f);
-  downsamplePointCloud(scene, scene, 0.001f);
+  {
+    std::string err;
+    if (!readPNG16(cfg.depth_path, depth_mm, w, h, &err)) { printf("readDepthImage: %s\n", err.c_str()); hop_destroy(ctx); return 1; }
+  }
   const Mat4f cam_in_handbase = handbase_in_cam.inverse();
-  transformPointCloudWithNormals(scene, scene, cam_in_handbase);
-  passThrough(scene, scene, 2, -0.12f, 0.05f);
-  passThrough(scene, scene, 0, -0.25f, -0.07f);
-  passThrough(scene, scene, 1, -0.2f, 0.2f);
-  transformPointCloudWithNormals(scene, scene, cam_in_handbase.inverse());
-  printf("scene in the hand region: %d points\n", (int)scene.size());
-  if (scene.size() == 0) { printf("empty hand region\n"); return 1; }
+  const Mat4f cam_in_handbase_inv = cam_in_handbase.inverse();
+  hop_frame_params fp;
+  hop_default_frame_params(&fp);
+  fp.fx = cfg.cam_intrinsic(0, 0); fp.fy = cfg.cam_intrinsic(1, 1); fp.cx = cfg.cam_intrinsic(0, 2); fp.cy = cfg.cam_intrinsic(1, 2);
+  std::memcpy(fp.cam_in_handbase, cam_in_handbase.data(), 64);
+  std::memcpy(fp.handbase_in_cam, cam_in_handbase_inv.data(), 64);
+  hop_cloud *d_segment = nullptr;
+  int32_t counts[5];
+  if (hop_frame_to_scene(ctx, depth_mm.data(), w, h, &fp, &d_segment, counts) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(ctx)); hop_destroy(ctx); return 1; }
+  printf("scene in the hand region: %d points\n", (int)counts[2]);
+  if (counts[2] == 0) { printf("empty hand region\n"); hop_destroy(ctx); return 1; }
 
   const std::string urdf = cfg.yml["urdf_path"].as<std::string>(std::string());
   if (urdf.empty() || !file_exists(urdf))
     printf("hand model not available (urdf_path): hand-state search and hand-point removal skipped, confidence = 1\n");
 
-  // object segment: normals over 3 mm, 3 mm voxels, normals towards the camera (main_realdata_auto.cpp:154-177)
-  Cloud object_segment = scene;
-  const float origin[3] = {0, 0, 0};
-  estimateNormals(object_segment, 0.003f, origin);
-  downsamplePointCloud(object_segment, object_segment, 0.003f);
-  removeAllNaNFromPointCloud(object_segment);
-  for (size_t i = 0; i < object_segment.size(); ++i) {   // pcl::flipNormalTowardsViewpoint
-    float *n = &object_segment.nrm[3 * i];
-    const float *p = &object_segment.xyz[3 * i];
-    if (-p[0] * n[0] - p[1] * n[1] - p[2] * n[2] < 0) { n[0] = -n[0]; n[1] = -n[1]; n[2] = -n[2]; }
+  // host copy of the object segment: the Super4PCS planner replays the reference's RNG on the host, and scene_normals.ply is written from it
+  Cloud object_segment;
+  {
+    const int n = hop_cloud_size(d_segment);
+    object_segment.xyz.resize(3 * (size_t)n); object_segment.nrm.resize(3 * (size_t)n); object_segment.conf.resize(n);
+    if (hop_cloud_download(ctx, d_segment, object_segment.xyz.data(), object_segment.nrm.data(), object_segment.conf.data()) != HOP_OK) {
+      fprintf(stderr, "%s\n", hop_last_error(ctx)); hop_destroy(ctx); return 1;
+    }
+    hop_cloud_free(ctx, d_segment);
   }
-  std::fill(object_segment.conf.begin(), object_segment.conf.end(), 1.f);
 
-  hop_ctx *ctx = nullptr;
-  if (hop_create(cfg.b200_device, &ctx) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(nullptr)); return 1; }
   {
     PoseEstimator est(&cfg, model, model001, ctx);
     est.setCurScene(object_segment);

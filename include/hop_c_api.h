@@ -100,6 +100,7 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 #define HOP_PROF_S4_PAIRS 8       /* K2a: extract_pairs_kernel + selection (all trials) */
 #define HOP_PROF_S4_JOIN 9        /* K2b: prepare_pairs + congruent_join (count, scan, fill) */
 #define HOP_PROF_CLUSTER 10       /* hop_cluster_poses_gpu: all block launches of one call = one span */
+#define HOP_PROF_FRAME 11         /* hop_frame_to_scene: every launch of one frame's front end = one span */
 #define HOP_PROF_KINDS 12
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
@@ -264,6 +265,32 @@ int hop_hand_overlap(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop
 int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop_cloud *scene_normals, hop_cloud *scene_noswivel,
                          const hop_finger_params *params, const double *d_thetas, const float *d_half_cs, int S, double *d_cost,
                          int32_t *d_best);
+
+/* ---- per-frame front end: depth image -> object-segment cloud (device) --------------------------------------------- */
+/* The pre-processing main_realdata_auto.cpp:54-96,144-181 does with OpenCV / PCL between reading the depth PNG and
+ * PoseEstimator::setCurScene, in the same order: back-projection (Utils.cpp:78-115) of the pixels with 0.1 m < z < 2 m,
+ * VoxelGrid(leaf_dense) (Utils.cpp:333-340), camera -> hand base, crop box (the three PassThroughs), back to the camera frame,
+ * normals over normal_radius flipped to the viewpoint, VoxelGrid(leaf_object) with normals, NaN removal, normals flipped
+ * towards the camera origin, confidence 1.  (The hand-point removal of Hand.cpp:781-888 needs the hand meshes, which the
+ * reference does not ship: every cropped point keeps confidence 1, as in this repository's main_realdata_auto.) */
+typedef struct hop_frame_params {
+  float fx, fy, cx, cy;          /* cam_K */
+  float leaf_dense;              /* 0.001 */
+  float cam_in_handbase[16];     /* column-major: handbase_in_cam.inverse() */
+  float handbase_in_cam[16];     /* column-major: cam_in_handbase.inverse() as the host computed it (the reference inverts numerically) */
+  float box_min[3], box_max[3];  /* crop in the hand-base frame: x [-0.25,-0.07], y [-0.2,0.2], z [-0.12,0.05] */
+  float normal_radius;           /* 0.003 */
+  float leaf_object;             /* 0.003 */
+  float viewpoint[3];            /* for the first normal flip (the camera origin) */
+} hop_frame_params;
+void hop_default_frame_params(hop_frame_params *p);
+/* depth_mm: height x width uint16 millimetres (the PNG's pixels, host memory).  *scene: NULL to create a cloud, or an existing
+ * cloud to refill (its cached NN grids are invalidated).  stage_counts (may be NULL): 5 ints = valid pixels, dense leaves,
+ * cropped points, object leaves, final points. */
+int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *params, hop_cloud **scene,
+                       int32_t *stage_counts);
+/* copies a device cloud back (tests, debugging output such as scene_normals.ply); any pointer may be NULL */
+int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob);
 
 /* ---- winners ------------------------------------------------------------------------------------------------- */
 /* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).

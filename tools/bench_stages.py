@@ -172,6 +172,40 @@ def main():
                       "kernel_ms": {"k2a_pairs": pr_ms, "k2b_join": jn_ms, "k3_verify": v_ms}, "dtype": "f32 / int32",
                       "roofline": {"bound": "hbm", "kernel": "verify_lcp_kernel", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
                                    "traffic": None, "algorithmic_bytes_per_launch": M * bytes_quad}}), file=out, flush=True)
+    # ---------------- the frame's front end: depth image -> object-segment cloud ----------------
+    Kc = (616.5961303710938, 616.59619140625, 307.6278076171875, 239.68692016601562)
+    dense, _ = synth.make_model("ellipse", 400000, seed=7)
+    hb = np.eye(4); hb[:3, 3] = [0.15, 0.0, 0.38]
+    gtf = np.eye(4); gtf[:3, :3] = synth._rot_from_rotvec(np.array([0.4, -0.7, 0.3])); gtf[:3, 3] = [0.0, 0.005, 0.35]
+    Pd = dense.astype(np.float64) @ gtf[:3, :3].T + gtf[:3, 3]
+    uu = np.round(Pd[:, 0] * Kc[0] / Pd[:, 2] + Kc[2]).astype(int); vv = np.round(Pd[:, 1] * Kc[1] / Pd[:, 2] + Kc[3]).astype(int)
+    dimg = np.full((480, 640), np.inf); np.minimum.at(dimg, (vv, uu), Pd[:, 2]); dimg[~np.isfinite(dimg)] = 0.45   # object in front of a wall
+    depth = np.round(dimg * 1000 + np.random.default_rng(1).normal(0, 0.5, dimg.shape)).astype(np.uint16)
+    Tf = np.linalg.inv(hb).astype(np.float32)
+    fpar = ctx.frame_params(K=Kc, cam_in_handbase=Tf)
+    res["frame"] = ctx.frame_to_scene(depth, fpar)
+
+    def fr():
+        res["frame"] = ctx.frame_to_scene(depth, fpar, scene=res["frame"][0])
+
+    dt, prof = timed(fr)
+    cpu4 = None
+    tool = os.path.join(ROOT, "icra20-hand-object-pose_b200", "host", "host_tool")
+    if not args.no_cpu_baseline and os.path.exists(tool):
+        import subprocess, tempfile, cv2
+        with tempfile.TemporaryDirectory() as td:
+            cv2.imwrite(td + "/d.png", depth); np.savetxt(td + "/T.txt", Tf)
+            r = subprocess.run([tool, "frame", td + "/d.png", *map(repr, Kc), td + "/T.txt", td + "/o.bin"], capture_output=True, text=True)
+            ms = [float(l.split()[1]) for l in r.stdout.splitlines() if l.startswith("frame_ms")]
+        if ms:
+            cpu4 = {"value": 1e3 / ms[0], "unit": "frames/s", "cores": 1, "kind": "port", "ms_per_call": ms[0],
+                    "sample": "one 640x480 frame through host/cloud.cpp frameToObjectSegment (the PCL chain restated, single thread like the reference)"}
+    print(json.dumps({"stage": "frame front end on the device (hop_frame_to_scene: back-projection, 2 voxel grids, crop, normals)", "metric": "depth frames/sec",
+                      "value": 1.0 / dt, "unit": "frames/s", "cpu_baseline": cpu4,
+                      "e2e": {"value": 1.0 / dt, "unit": "frames/s", "ms_per_call": dt * 1e3, "h2d_bytes": int(depth.nbytes), "d2h_bytes": 0},
+                      "config": {"image": "640x480 uint16 mm", "stage_counts": [int(x) for x in res["frame"][1]]},
+                      "kernel_ms": prof["frame"][0] / max(prof["frame"][1], 1)}), file=out, flush=True)
+
     # ---------------- clusterPoses: host loop vs the device version (identical keep list) ----------------
     n_cl = 20000 if args.sizes == "C2" else 65536
     hyp = synth.make_hypotheses(gt, n_cl, seed=3, rot_sigma_deg=20, trans_sigma=0.02, random_frac=0.3)
