@@ -184,6 +184,7 @@ void hop_destroy(hop_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->s4_scene) { hop_cloud_free(ctx, ctx->s4_scene); ctx->s4_scene = nullptr; }
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_io);

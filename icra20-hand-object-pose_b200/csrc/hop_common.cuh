@@ -238,6 +238,7 @@ struct hop_ctx {
   void *ensure_work(size_t bytes);
   void *ensure_io(size_t bytes);
   void *ensure_pinned(size_t bytes);
+  hop_cloud *s4_scene = nullptr;   // hop_super4pcs_run: the centred scene of the current frame (buffers reused across frames)
 };
 
 // times everything enqueued on the context's stream during its lifetime as one span of `kind`

@@ -157,7 +157,7 @@ struct Planner {
     // (the membership tests -- three acos and a set lookup per point -- are the planner's O(N) cost: evaluated on all host
     //  threads with the same libm, gathered in index order, so the pool is the one a sequential loop builds)
     member.assign(number_of_points, 0);
-#pragma omp parallel for schedule(static) if (number_of_points >= 4096)
+#pragma omp parallel for schedule(static) if (number_of_points >= 512)
     for (int i = 0; i < number_of_points; ++i) member[i] = (i != first_point && has_ppf(P[first_point], P[i])) ? 1 : 0;
     for (int i = 0; i < number_of_points; ++i)
       if (member[i]) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
@@ -184,7 +184,7 @@ struct Planner {
     sample_pool.clear();
     const int nb = (int)backup.size();
     member.assign(nb, 0);
-#pragma omp parallel for schedule(static) if (nb >= 4096)
+#pragma omp parallel for schedule(static) if (nb >= 512)
     for (int i = 0; i < nb; ++i) {
       if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
       member[i] = (has_ppf(P[base2], P[backup[i]]) && has_ppf(P[base3], P[backup[i]])) ? 1 : 0;

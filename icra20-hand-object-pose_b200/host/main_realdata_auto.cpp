@@ -9,8 +9,10 @@
 //     (what the reference's computePPF app does offline);
 //   * rejectByCollisionOrNonTouching / rejectByRender (SDF + OpenGL) are outside this build's scope.
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <iostream>
@@ -70,43 +72,55 @@ int main(int argc, char **argv) {
   fp.fx = cfg.cam_intrinsic(0, 0); fp.fy = cfg.cam_intrinsic(1, 1); fp.cx = cfg.cam_intrinsic(0, 2); fp.cy = cfg.cam_intrinsic(1, 2);
   std::memcpy(fp.cam_in_handbase, cam_in_handbase.data(), 64);
   std::memcpy(fp.handbase_in_cam, cam_in_handbase_inv.data(), 64);
-  hop_cloud *d_segment = nullptr;
-  int32_t counts[5];
-  if (hop_frame_to_scene(ctx, depth_mm.data(), w, h, &fp, &d_segment, counts) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(ctx)); hop_destroy(ctx); return 1; }
-  printf("scene in the hand region: %d points\n", (int)counts[2]);
-  if (counts[2] == 0) { printf("empty hand region\n"); hop_destroy(ctx); return 1; }
-
   const std::string urdf = cfg.yml["urdf_path"].as<std::string>(std::string());
   if (urdf.empty() || !file_exists(urdf))
     printf("hand model not available (urdf_path): hand-state search and hand-point removal skipped, confidence = 1\n");
 
-  // host copy of the object segment: the Super4PCS planner replays the reference's RNG on the host, and scene_normals.ply is written from it
-  Cloud object_segment;
-  {
-    const int n = hop_cloud_size(d_segment);
-    object_segment.xyz.resize(3 * (size_t)n); object_segment.nrm.resize(3 * (size_t)n); object_segment.conf.resize(n);
-    if (hop_cloud_download(ctx, d_segment, object_segment.xyz.data(), object_segment.nrm.data(), object_segment.conf.data()) != HOP_OK) {
-      fprintf(stderr, "%s\n", hop_last_error(ctx)); hop_destroy(ctx); return 1;
+  // optional second argument: process the frame that many times and report the stage times of the last pass (steady state:
+  // the first pass of a process also pays module loading and the first allocations)
+  const int repeat = argc >= 3 ? std::max(1, atoi(argv[2])) : 1;
+  {   // (the estimator's device clouds must be gone before the context)
+  PoseEstimator est(&cfg, model, model001, ctx);
+  const std::string out_dir = cfg.yml["out_dir"].as<std::string>();
+  for (int pass = 0; pass < repeat; ++pass) {
+    typedef std::chrono::steady_clock Clock;
+    auto ms = [](Clock::time_point a, Clock::time_point b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    const Clock::time_point t0 = Clock::now();
+    hop_cloud *d_segment = nullptr;
+    int32_t counts[5];
+    if (hop_frame_to_scene(ctx, depth_mm.data(), w, h, &fp, &d_segment, counts) != HOP_OK) { fprintf(stderr, "%s\n", hop_last_error(ctx)); exit(1); }
+    printf("scene in the hand region: %d points\n", (int)counts[2]);
+    if (counts[2] == 0) { printf("empty hand region\n"); exit(1); }
+    // host copy of the object segment: the Super4PCS planner replays the reference's RNG on the host, and scene_normals.ply is written from it
+    Cloud object_segment;
+    {
+      const int n = hop_cloud_size(d_segment);
+      object_segment.xyz.resize(3 * (size_t)n); object_segment.nrm.resize(3 * (size_t)n); object_segment.conf.resize(n);
+      if (hop_cloud_download(ctx, d_segment, object_segment.xyz.data(), object_segment.nrm.data(), object_segment.conf.data()) != HOP_OK) {
+        fprintf(stderr, "%s\n", hop_last_error(ctx)); exit(1);
+      }
+      hop_cloud_free(ctx, d_segment);
     }
-    hop_cloud_free(ctx, d_segment);
-  }
-
-  {
-    PoseEstimator est(&cfg, model, model001, ctx);
     est.setCurScene(object_segment);
-    const std::string out_dir = cfg.yml["out_dir"].as<std::string>();
+    const Clock::time_point t1 = Clock::now();
     const bool succeed = est.runSuper4pcs(ppfs);
     if (!succeed) {
       printf("No pose found...\n");
       savePoseTxt(out_dir + "/model2scene.txt", Mat4f());
-      hop_destroy(ctx);
       exit(1);
     }
+    const Clock::time_point t2 = Clock::now();
     est.clusterPoses(30, 0.015, true);
+    const Clock::time_point t3 = Clock::now();
     est.refineByICP();
+    const Clock::time_point t4 = Clock::now();
     est.clusterPoses(5, 0.003, false);
     PoseHypo best(-1);
     est.selectBest(best);
+    const Clock::time_point t5 = Clock::now();
+    printf("timing_ms front_end %.3f super4pcs %.3f cluster %.3f icp %.3f cluster_select %.3f total %.3f\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4),
+           ms(t4, t5), ms(t0, t5));
+    if (pass + 1 < repeat) continue;
     const Mat4f model2scene = best._pose;
     std::cout << "best tf:\n" << model2scene << "\n\n";
     Cloud model_viz;
@@ -114,6 +128,7 @@ int main(int argc, char **argv) {
     saveOBJVertices(out_dir + "/best.obj", model_viz);
     savePLYFile(out_dir + "/scene_normals.ply", object_segment);
     savePoseTxt(out_dir + "/model2scene.txt", model2scene);
+  }
   }
   hop_destroy(ctx);
   return 0;

@@ -206,6 +206,63 @@ def main():
                       "config": {"image": "640x480 uint16 mm", "stage_counts": [int(x) for x in res["frame"][1]]},
                       "kernel_ms": prof["frame"][0] / max(prof["frame"][1], 1)}), file=out, flush=True)
 
+    # ---------------- the whole frame through the drop-in executable: main_realdata_auto <config.yaml> <repeat> ----------------
+    main_bin = os.path.join(ROOT, "icra20-hand-object-pose_b200", "host", "main_realdata_auto")
+    if os.path.exists(main_bin) and args.sizes == "C2":
+        import subprocess, tempfile, cv2
+        from scipy.spatial import cKDTree
+        with tempfile.TemporaryDirectory() as td:
+            cfg = f"""cam_K: [{Kc[0]}, 0.0, {Kc[2]}, 0.0, {Kc[1]}, {Kc[3]}, 0.0, 0.0, 1.0]
+cam1_in_leftarm: [0.0,0.0,0.0,0.0,0.0,0.0,1.0]
+handbase_in_palm: [1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1]
+out_dir: {td}
+rgb_path: {td}/rgb.png
+depth_path: {td}/depth.png
+palm_in_baselink: {td}/palm_in_base.txt
+leftarm_in_base: {td}/arm_left.txt
+model_name: ellipse
+object_model_path: {td}/ellipse.ply
+ppf_path: {td}/ppf_ellipse
+object_symmetry:
+  ellipse:
+    x: 180
+    y: 180
+    z: 180
+lcp:
+  dist: 0.001
+  normal_angle: 10
+pose_estimator_high_confidence_thres: 0.8
+icp_dist_thres: 0.01
+icp_angle_thres: 45
+super4pcs_sample_size: 100
+super4pcs_overlap: 0.2
+super4pcs_delta: 0.003
+super4pcs_dispersion: 0.5
+super4pcs_success_quadrilaterals: 10
+"""
+            open(td + "/cfg.yaml", "w").write(cfg)
+            np.savetxt(td + "/arm_left.txt", np.eye(4)); np.savetxt(td + "/palm_in_base.txt", hb)
+            mm, mmn = synth.make_model("ellipse", 60000, seed=8)
+            with open(td + "/ellipse.ply", "w") as f:
+                f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\nend_header\n" % len(mm))
+                np.savetxt(f, np.concatenate([mm, mmn], 1), fmt="%.9g")
+            dobj = np.full((480, 640), np.inf); np.minimum.at(dobj, (vv, uu), Pd[:, 2]); dobj[~np.isfinite(dobj)] = 0
+            cv2.imwrite(td + "/depth.png", np.round(dobj * 1000).astype(np.uint16))
+            r = subprocess.run([main_bin, td + "/cfg.yaml", "6"], capture_output=True, text=True, timeout=600)
+            tl = [l for l in r.stdout.splitlines() if l.startswith("timing_ms")]
+            if r.returncode == 0 and tl:
+                w_ = tl[-1].split()
+                tm = {w_[i]: float(w_[i + 1]) for i in range(1, len(w_) - 1, 2)}
+                est = np.loadtxt(td + "/model2scene.txt")
+                sub = mm[::20].astype(np.float64)
+                adi = float(cKDTree(sub @ gtf[:3, :3].T + gtf[:3, 3]).query(sub @ est[:3, :3].T + est[:3, 3])[0].mean())
+                print(json.dumps({"stage": "one frame through the drop-in executable (main_realdata_auto <cfg> 6: stage times of the 6th pass)", "metric": "frames/sec, depth image -> best pose",
+                                  "value": 1e3 / tm["total"], "unit": "frames/s", "e2e": {"value": 1e3 / tm["total"], "unit": "frames/s", "ms_per_call": tm["total"]},
+                                  "config": {"stage_ms": tm, "adi_mm": adi * 1e3, "note": "front end, K2a/K2b/K3, both clusterPoses, K4 on <= 100 clusters, K5; the Super4PCS base planner (host, replays the reference's RNG) is inside 'super4pcs'"},
+                                  "kernel_ms": None, "cpu_baseline": None}), file=out, flush=True)
+            else:
+                print("main_realdata_auto failed:", r.returncode, r.stdout[-800:], r.stderr[-800:], file=sys.stderr)
+
     # ---------------- clusterPoses: host loop vs the device version (identical keep list) ----------------
     n_cl = 20000 if args.sizes == "C2" else 65536
     hyp = synth.make_hypotheses(gt, n_cl, seed=3, rot_sigma_deg=20, trans_sigma=0.02, random_frac=0.3)
