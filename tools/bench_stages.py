@@ -247,7 +247,9 @@ super4pcs_success_quadrilaterals: 10
                 f.write("ply\nformat ascii 1.0\nelement vertex %d\nproperty float x\nproperty float y\nproperty float z\nproperty float nx\nproperty float ny\nproperty float nz\nend_header\n" % len(mm))
                 np.savetxt(f, np.concatenate([mm, mmn], 1), fmt="%.9g")
             dobj = np.full((480, 640), np.inf); np.minimum.at(dobj, (vv, uu), Pd[:, 2]); dobj[~np.isfinite(dobj)] = 0
-            cv2.imwrite(td + "/depth.png", np.round(dobj * 1000).astype(np.uint16))
+            dobj_mm = np.round(dobj * 1000).astype(np.uint16)
+            cv2.imwrite(td + "/depth.png", dobj_mm)
+            res["frame_obj"] = ctx.frame_to_scene(dobj_mm, fpar)[0]
             r = subprocess.run([main_bin, td + "/cfg.yaml", "6"], capture_output=True, text=True, timeout=600)
             tl = [l for l in r.stdout.splitlines() if l.startswith("timing_ms")]
             if r.returncode == 0 and tl:
@@ -256,10 +258,36 @@ super4pcs_success_quadrilaterals: 10
                 est = np.loadtxt(td + "/model2scene.txt")
                 sub = mm[::20].astype(np.float64)
                 adi = float(cKDTree(sub @ gtf[:3, :3].T + gtf[:3, 3]).query(sub @ est[:3, :3].T + est[:3, 3])[0].mean())
+                cpu5 = None
+                if not args.no_cpu_baseline:
+                    # the same frame through the CPU side stage by stage: host front end (cloud.cpp), the reference's own compiled
+                    # Super4PCS matcher, host clustering, the ICP / LCP port on the <= 100 clusters (all host threads where the
+                    # reference uses OpenMP)
+                    from oracle import cpu_oracle as O
+                    thr = max(1, len(os.sched_getaffinity(0)))
+                    seg_xyz, seg_nrm, seg_conf = res["frame_obj"].download()
+                    m5, m5n = synth.make_model("ellipse", 644, seed=8)
+                    m1, m1n = synth.make_model("ellipse", 10000, seed=8)
+                    stage = {}
+                    tool = os.path.join(ROOT, "icra20-hand-object-pose_b200", "host", "host_tool")
+                    np.savetxt(td + "/T.txt", Tf)
+                    rr = subprocess.run([tool, "frame", td + "/depth.png", *map(repr, Kc), td + "/T.txt", td + "/o.bin"], capture_output=True, text=True)
+                    fm = [float(l.split()[1]) for l in rr.stdout.splitlines() if l.startswith("frame_ms")]
+                    stage["front_end"] = fm[0] if fm else float("nan")
+                    if O.ref() is not None and hasattr(O.ref(), "hop_ref_s4pcs_run"):
+                        kk = ppf_keys(m5, m5n)
+                        t0 = time.perf_counter(); rs = O.ref_super4pcs(seg_xyz, seg_nrm, seg_conf, m5, m5n, kk, sample_size=100, nthreads=thr); stage["super4pcs"] = (time.perf_counter() - t0) * 1e3
+                        t0 = time.perf_counter(); keep = capi.cluster_poses(rs["poses"], rs["lcp"], 30.0, 0.015, (180.0, 180.0, 180.0)); stage["cluster"] = (time.perf_counter() - t0) * 1e3
+                        cl = rs["poses"][keep[:100]]
+                        t0 = time.perf_counter(); rp, _, _ = O.refine_by_icp(seg_xyz, seg_nrm, m5, m5n, cl, nthreads=thr); stage["icp"] = (time.perf_counter() - t0) * 1e3
+                        t0 = time.perf_counter(); O.select_best(seg_xyz, seg_nrm, m1, m1n, rp, nthreads=thr); stage["select"] = (time.perf_counter() - t0) * 1e3
+                        tot = sum(stage.values())
+                        cpu5 = {"value": 1e3 / tot, "unit": "frames/s", "cores": thr, "kind": "reference (Super4PCS) + port (front end, ICP, LCP)", "ms_per_call": tot,
+                                "sample": "the same frame, stage by stage", "stage_ms": stage}
                 print(json.dumps({"stage": "one frame through the drop-in executable (main_realdata_auto <cfg> 6: stage times of the 6th pass)", "metric": "frames/sec, depth image -> best pose",
                                   "value": 1e3 / tm["total"], "unit": "frames/s", "e2e": {"value": 1e3 / tm["total"], "unit": "frames/s", "ms_per_call": tm["total"]},
                                   "config": {"stage_ms": tm, "adi_mm": adi * 1e3, "note": "front end, K2a/K2b/K3, both clusterPoses, K4 on <= 100 clusters, K5; the Super4PCS base planner (host, replays the reference's RNG) is inside 'super4pcs'"},
-                                  "kernel_ms": None, "cpu_baseline": None}), file=out, flush=True)
+                                  "kernel_ms": None, "cpu_baseline": cpu5}), file=out, flush=True)
             else:
                 print("main_realdata_auto failed:", r.returncode, r.stdout[-800:], r.stderr[-800:], file=sys.stderr)
 
