@@ -765,7 +765,8 @@ struct LcpArgs {
 
 // CTA = (hypothesis, split): one thread per scene point of every `splits`-th tile; the pose algebra is done once per
 // CTA; the CTA's sum goes to partial[h][split]
-__global__ void __launch_bounds__(TILE) lcp_score_kernel(LcpArgs a) {
+template <int MINB>
+__global__ void __launch_bounds__(TILE, MINB) lcp_score_kernel(LcpArgs a) {
   __shared__ float s_w[TILE / 32];
   const int h = blockIdx.y;
   const Rigid T = rigid_load_colmajor(a.poses + 16 * (size_t)h);
@@ -881,7 +882,9 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
       const bool small_ctas = variant == 2 || (variant == 0 && (long)H >= 24L * ctx->sm_count);
       if (prof_on) e = small_ctas ? launch_fused<128, 512, true, 6>(f, H, ctx->sm_count, ctx->stream)
                                   : launch_fused<256, 1024, true, 3>(f, H, ctx->sm_count, ctx->stream);
-      else e = small_ctas ? launch_fused<128, 512, false, 6>(f, H, ctx->sm_count, ctx->stream)
+      // (large batches: 8 CTAs of 128 threads at 64 registers -- the few spilled bytes cost less than the extra warps hide:
+      //  15.39 -> 14.78 ms at the headline size; small batches lose with it)
+      else e = small_ctas ? launch_fused<128, 512, false, 8>(f, H, ctx->sm_count, ctx->stream)
                           : launch_fused<256, 1024, false, 3>(f, H, ctx->sm_count, ctx->stream);
       HOP_CUDA(ctx, e);
     }
@@ -969,7 +972,11 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_b
     const int Hb = std::min(Hb_max, H - h0);
     a.poses = d_poses + 16 * (size_t)h0; a.scores = d_scores + h0;
     ProfScope ps(ctx, HOP_PROF_LCP_SCORE);
-    lcp_score_kernel<<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
+    static const int lcp_variant = getenv("HOP_LCP_VARIANT") ? atoi(getenv("HOP_LCP_VARIANT")) : 0;  // tuning knob
+    if (lcp_variant == 1) lcp_score_kernel<5><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
+    else if (lcp_variant == 2) lcp_score_kernel<6><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
+    else if (lcp_variant == 4) lcp_score_kernel<4><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
+    else lcp_score_kernel<8><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);   // full occupancy: the kernel waits on gathers (measured 4 -> 8 CTAs/SM: -14 %)
     lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, splits, Hb, d_scores + h0);
     ctx->launches += 2;
   }
