@@ -119,3 +119,41 @@ def test_frame_to_pose_pipeline_on_device_cloud(ctx):
     adi = cKDTree(sub @ gt[:3, :3].T + gt[:3, 3]).query(sub @ best[:3, :3].T + best[:3, 3])[0].mean()
     assert adi < 0.002, adi
     scene.free(); model.free()
+
+
+@pytest.mark.skipif(not os.path.exists(TOOL), reason="host tools not built (make -C icra20-hand-object-pose_b200/host)")
+def test_shipped_example_frame_on_the_device(ctx, tmp_path):
+    """the reference's own example frame (tests/golden/example_depth7.png, config_autodataset.yaml calibration): the device
+    front end gives the host chain's cloud (positions bit for bit), and that cloud runs through Super4PCS -> clustering ->
+    ICP -> LCP with a stand-in model (the frame's real object model is an external download: plumbing, not accuracy)."""
+    import cv2
+    import hop_b200
+    from test_host_cpp import example_frame_setup
+    depth, Kx, cam_in_handbase = example_frame_setup(tmp_path)
+    png, txt, out = str(tmp_path / "d.png"), str(tmp_path / "T.txt"), str(tmp_path / "seg.bin")
+    cv2.imwrite(png, depth)
+    np.savetxt(txt, cam_in_handbase)
+    r = subprocess.run([TOOL, "frame", png, *map(repr, Kx), txt, out], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    raw = np.fromfile(out, np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    body = raw[4:4 + 28 * n].view(np.float32).reshape(n, 7)
+    Ti = raw[4 + 28 * n:4 + 28 * n + 64].view(np.float32).reshape(4, 4).T.copy()
+    p = ctx.frame_params(K=Kx, cam_in_handbase=cam_in_handbase, handbase_in_cam=Ti)
+    cloud, counts = ctx.frame_to_scene(depth, p)
+    xyz, nrm, conf = cloud.download()
+    assert counts[0] == 68600 and len(xyz) == n > 200
+    assert np.array_equal(xyz, body[:, :3]) and np.abs(nrm - body[:, 3:6]).max() < 1e-5
+    # plumbing through the rest of the path with a stand-in model
+    m, mn = synth.make_model("ellipse", 3000, seed=1)
+    keys = np.unique(np.array([hop_b200.capi.compute_ppf(m[i], mn[i], m[j], mn[j]) for i in range(0, 3000, 30) for j in range(i + 30, 3000, 30)], np.int32), axis=0)
+    est = hop_b200.PoseEstimator(ctx, {"model_name": "ellipse", "object_symmetry": {"ellipse": {"x": 180, "y": 180, "z": 180}}})
+    est.setModel(m[::5], mn[::5], m, mn)
+    est.setCurScene(xyz, nrm, conf)
+    if est.runSuper4pcs(keys):
+        est.clusterPoses(30, 0.015, True)
+        est.refineByICP()
+        est.clusterPoses(5, 0.003, False)
+        best = est.selectBest()
+        assert np.isfinite(best._pose).all() and len(est._pose_hypos) <= 100
+    cloud.free()

@@ -270,3 +270,15 @@ def test_verify_lcp_edge_cases(ctx):
     poses, lcp, valid, hp, hl = ctx.verify_lcp(P, Qc, [[0, 1, 2, 3]], np.zeros((0, 4), np.int32), np.zeros(0, np.int32), z, z, 0.003)
     assert len(lcp) == 0 and len(hp) == 0
     P.free()
+
+
+def test_icp_with_the_hand_base_parameters(ctx):
+    """Utils::runICP as Hand.cpp:734 calls it for the hand base: one cloud, 50 iterations, 30 deg, 3 cm"""
+    m, mn, s, sn, conf, gt, hyp = _case("cuboid", 900, 4000, 6, seed=83, random_frac=0.0)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    p = ctx.icp_params(max_iter=50, angle_deg=30.0, max_dist=0.03)
+    got, it, cv = ctx.icp_refine(scene, model, hyp, p)
+    ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp, max_iter=50, angle=30.0, dist=0.03)
+    dt, dr = synth.pose_error(got, ref)
+    assert np.array_equal(cv, rcv) and np.all(dt <= POS_TOL) and np.all(dr <= ROT_TOL), (dt, dr)
+    scene.free(); model.free()

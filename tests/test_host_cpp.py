@@ -277,3 +277,57 @@ def test_main_realdata_auto_end_to_end(tmp_path):
     b = sub @ gt[:3, :3].T + gt[:3, 3]
     adi = cKDTree(b).query(a)[0].mean()
     assert adi < 0.002, (adi, r.stdout[-1500:])
+
+
+# ------------------------------------------------------------------------------------- the reference's shipped example frame
+EXAMPLE_CFG = """cam_K: [616.5961303710938, 0.0, 307.6278076171875, 0.0, 616.59619140625, 239.68692016601562, 0.0, 0.0, 1.0]
+cam1_in_leftarm: [-0.004269333556294441,-0.007711530197411776,-0.08680825680494308,-0.006834600586444139,0.9986741542816162,0.04945759475231171,-0.01254322659224272]
+handbase_in_palm: [0    ,               -1             ,       0 ,0.009000016543892384,
+                  -0              ,      0          ,          1  ,0.08699987083673477,
+                  -1     ,              -0       ,             0 , 0.01899999752640724,
+                  -0         ,          -0         ,          -0      ,              1
+]
+out_dir: {out}
+depth_path: {gold}/example_depth7.png
+palm_in_baselink: {gold}/example_palm_in_base7.txt
+leftarm_in_base: {gold}/example_arm_left_link_7_t_7.txt
+model_name: ellipse
+object_model_path: {out}/ellipse.ply
+"""
+
+
+def example_frame_setup(tmp_path):
+    """config of the shipped example frame (config_autodataset.yaml:2,12,14-18 + example/*) -> (depth uint16, K, cam_in_handbase)"""
+    import cv2
+    gold = os.path.join(os.path.dirname(__file__), "golden")
+    (tmp_path / "ex.yaml").write_text(EXAMPLE_CFG.format(out=str(tmp_path), gold=gold))
+    rc, out = _tool("config", str(tmp_path / "ex.yaml"))
+    assert rc == 0, out
+    lines = out.strip().split("\n")
+    k = lines.index("handbase_in_cam")
+    hic = np.array([[float(v) for v in l.split()] for l in lines[k + 1:k + 5]])
+    K = [float(v) for v in lines[-1].split()[1:]]
+    depth = cv2.imread(os.path.join(gold, "example_depth7.png"), cv2.IMREAD_UNCHANGED)
+    return depth, K, np.linalg.inv(hic).astype(np.float32)
+
+
+@needs_tool
+def test_example_frame_plumbing(tmp_path):
+    """BASELINE config C1 (plumbing, no GPU): the reference's shipped depth frame through the host front end.  SURVEY quick
+    facts: 480x640 uint16 mm, 68 600 valid pixels, median 0.349 m; the hand region must come out non-empty."""
+    depth, K, cam_in_handbase = example_frame_setup(tmp_path)
+    assert depth.shape == (480, 640) and depth.dtype == np.uint16
+    d = depth.astype(np.float32) * np.float32(0.001)
+    valid = (d > 0.1) & (d < 2.0)
+    assert valid.sum() == 68600 and abs(float(np.median(d[valid])) - 0.349) < 0.002
+    np.savetxt(tmp_path / "T.txt", cam_in_handbase)
+    rc, out = _tool("frame", os.path.join(os.path.dirname(__file__), "golden", "example_depth7.png"), *K, str(tmp_path / "T.txt"), str(tmp_path / "seg.bin"))
+    assert rc == 0, out
+    raw = np.fromfile(tmp_path / "seg.bin", np.uint8)
+    n = int(raw[:4].view(np.int32)[0])
+    seg = raw[4:4 + 28 * n].view(np.float32).reshape(n, 7)
+    assert 200 < n < 20000                                   # the object + fingers inside the hand-base crop box, 3 mm voxels
+    assert np.isfinite(seg).all() and np.allclose(np.linalg.norm(seg[:, 3:6], axis=1), 1.0, atol=1e-4)
+    assert np.all(np.einsum("ij,ij->i", seg[:, :3], seg[:, 3:6]) <= 1e-6)   # normals face the camera
+    hb = seg[:, :3] @ cam_in_handbase[:3, :3].T + cam_in_handbase[:3, 3]
+    assert hb[:, 0].min() > -0.2505 and hb[:, 0].max() < -0.0695 and hb[:, 2].min() > -0.1205 and hb[:, 2].max() < 0.0505
