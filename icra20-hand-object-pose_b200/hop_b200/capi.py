@@ -54,6 +54,13 @@ class S4pcsOptions(C.Structure):
                 ("max_trials", C.c_int32), ("random_seed", C.c_uint32), ("keep_intermediates", C.c_int32)]
 
 
+class CollisionParams(C.Structure):
+    """hop_collision_params (include/hop_c_api.h)"""
+    _fields_ = [("cam2handbase", C.c_float * 16), ("model_center", C.c_float * 3), ("ob_diameter", C.c_float),
+                ("collision_dist", C.c_float), ("inside_ob_dist", C.c_float), ("non_touch_dist", C.c_float),
+                ("collision_finger_dist", C.c_float), ("collision_finger_volume_ratio", C.c_float), ("finger_status", C.c_int32 * 4)]
+
+
 class PoseRec(C.Structure):
     _fields_ = [("pose", C.c_float * 16), ("score", C.c_float), ("id", C.c_int32), ("frame", C.c_int32), ("pad", C.c_int32)]
 
@@ -151,6 +158,11 @@ def load_library():
     L.hop_hand_overlap_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.POINTER(FingerParams), _vp, _vp, C.c_int, _vp, _vp]
     L.hop_select_topk_dev.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
     L.hop_select_topk.argtypes = [_vp, _vp, _vp, C.c_int, C.c_int, C.c_int32, C.c_int32, _vp]
+    L.hop_mesh_upload.argtypes = [_vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
+    L.hop_mesh_free.argtypes = [_vp, _vp]
+    L.hop_sdf_query.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
+    L.hop_reject_by_collision.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
+    L.hop_reject_by_collision_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # raises AttributeError when an export is missing
         if fn.restype is C.c_int and name not in ("hop_cloud_size",):
@@ -300,6 +312,18 @@ class Cloud:
             self.handle = None
 
 
+class Mesh:
+    """Device-resident triangle mesh with igl's pseudonormals (hop_mesh*)."""
+
+    def __init__(self, ctx, handle, nv, nf):
+        self.ctx, self.handle, self.nv, self.nf = ctx, handle, nv, nf
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.hop_mesh_free(self.ctx.h, self.handle)
+            self.handle = None
+
+
 class Context:
     """hop_ctx*: one per process/GPU.  Raises HopError when no B200-class device is present (no CPU fallback)."""
 
@@ -337,7 +361,7 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
-    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10, "frame": 11}
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10, "frame": 11, "sdf": 12}
 
     def profile_enable(self, on=True):
         self._check(self.L.hop_profile_enable(self.h, int(on)))
@@ -499,6 +523,64 @@ class Context:
         nk = C.c_int32(0)
         self._check(self.L.hop_cluster_poses_gpu(self.h, _ptr(flat), _ptr(sc), _ptr(idv), n, angle_diff_deg, dist_diff, _ptr(sym), _ptr(keep), C.byref(nk)))
         return keep[: nk.value].copy()
+
+    def upload_mesh(self, V, F):
+        """SDFchecker::registerMesh: V (nv,3) float vertices, F (nf,3) int faces"""
+        V = _f32(V, 3)
+        F = np.ascontiguousarray(F, np.int32).reshape(-1, 3)
+        h = _vp()
+        self._check(self.L.hop_mesh_upload(self.h, _ptr(V), len(V), _ptr(F), len(F), C.byref(h)))
+        return Mesh(self, h, len(V), len(F))
+
+    def sdf_query(self, mesh, pts, point_transforms=None, want_faces=False):
+        """signed distance (igl pseudonormal rules) of pts under each of H point transforms (None = one identity placement):
+        dict S (H,n), I (H,n) closest faces (when asked), min, max, n_inside (H,)"""
+        pts = _f32(pts, 3)
+        n = len(pts)
+        flat = None if point_transforms is None else poses_to_colmajor(point_transforms)
+        H = 1 if flat is None else len(flat)
+        S = np.empty((H, n), np.float32)
+        I = np.empty((H, n), np.int32) if want_faces else None
+        mn, mx, cnt = np.empty(H, np.float32), np.empty(H, np.float32), np.empty(H, np.int32)
+        self._check(self.L.hop_sdf_query(self.h, mesh.handle, _ptr(pts), n, _ptr(flat), H, _ptr(S), _ptr(I), _ptr(mn), _ptr(mx), _ptr(cnt)))
+        return {"S": S, "I": I, "min": mn, "max": mx, "n_inside": cnt}
+
+    def collision_params(self, d):
+        p = CollisionParams()
+        p.cam2handbase[:] = np.asarray(d["cam2handbase"], np.float32).T.reshape(-1).tolist()   # column-major
+        p.model_center[:] = [float(v) for v in d["model_center"]]
+        for k in ("ob_diameter", "collision_dist", "inside_ob_dist", "non_touch_dist", "collision_finger_dist", "collision_finger_volume_ratio"):
+            setattr(p, k, float(d[k]))
+        p.finger_status[:] = [int(v) for v in d["finger_status"]]
+        return p
+
+    @staticmethod
+    def _handles4(objs):
+        arr = (_vp * 4)()
+        for k in range(4):
+            o = objs[k] if objs is not None and k < len(objs) else None
+            arr[k] = o.handle if o is not None else None
+        return arr
+
+    def reject_by_collision(self, object_mesh, finger_meshes, finger_clouds, scene_without_hand, hand_cloud, model, poses, params):
+        """PoseEstimator::rejectByCollisionOrNonTouching for all poses: keep (H,) int32, reason (H,), diag (H,10)"""
+        flat = poses_to_colmajor(poses)
+        H = len(flat)
+        keep, reason, diag = np.zeros(H, np.int32), np.zeros(H, np.int32), np.zeros((H, 10), np.float32)
+        fm, fc = self._handles4(finger_meshes), self._handles4(finger_clouds)
+        p = params if isinstance(params, CollisionParams) else self.collision_params(params)
+        self._check(self.L.hop_reject_by_collision(self.h, object_mesh.handle, fm, fc, scene_without_hand.handle if scene_without_hand else None,
+                                                   hand_cloud.handle if hand_cloud else None, model.handle if model else None, _ptr(flat), H,
+                                                   C.byref(p), _ptr(keep), _ptr(reason), _ptr(diag)))
+        return keep, reason, diag
+
+    def reject_by_collision_dev(self, object_mesh, finger_meshes, finger_clouds, scene_without_hand, hand_cloud, model, d_poses, H, params,
+                                d_keep, d_reason=None, d_diag=None):
+        fm, fc = self._handles4(finger_meshes), self._handles4(finger_clouds)
+        self._keepalive = (fm, fc, params)
+        self._check(self.L.hop_reject_by_collision_dev(self.h, object_mesh.handle, fm, fc, scene_without_hand.handle if scene_without_hand else None,
+                                                       hand_cloud.handle if hand_cloud else None, model.handle if model else None, d_poses, H,
+                                                       C.byref(params), d_keep, d_reason, d_diag))
 
     def select_topk(self, poses, scores, K, id_offset=0, frame=0):
         flat = poses_to_colmajor(poses)

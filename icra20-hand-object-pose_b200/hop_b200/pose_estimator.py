@@ -60,6 +60,7 @@ class PoseEstimator:
             self._model001 = self._model
         else:
             self._model001 = self.ctx.upload_cloud(model001_xyz, model001_nrm)
+            self._model001_host = np.asarray(model001_xyz, np.float32)
 
     def setPoseHypos(self, poses, scores=None):
         poses = np.asarray(poses, np.float32).reshape(-1, 4, 4)
@@ -115,6 +116,52 @@ class PoseEstimator:
         for h, p in zip(keep, refined):
             h._pose = p
         self._pose_hypos = keep
+
+    # -- physics pruning ---------------------------------------------------------------------------
+    def registerMesh(self, V, F, name="object"):
+        """PoseEstimator::registerMesh / registerHandMesh (PoseEstimator.cpp:506-521): name = "object" or a finger link
+        ("finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2", vertices already in the hand-base frame)."""
+        if not hasattr(self, "_meshes"):
+            self._meshes = {}
+        if name in self._meshes:
+            self._meshes[name].free()
+        self._meshes[name] = self.ctx.upload_mesh(V, F)
+
+    FINGERS = ("finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2")
+
+    def rejectByCollisionOrNonTouching(self, hand, cfg=None):
+        """PoseEstimator::rejectByCollisionOrNonTouching(HandT42*) (PoseEstimator.cpp:524-735).  `hand`: dict with
+        component_status {name: bool}, finger_clouds {name: xyz in the hand-base frame}, hand_cloud (xyz, hand-base frame),
+        handbase_in_cam (4x4), cloud_withouthand (xyz in the hand-base frame, 5 mm voxel-sampled).  Survivors keep their order."""
+        cfg = cfg or {}
+        if not cfg.get("pose_estimator_use_physics", True):
+            print("Not using physics")
+            return
+        if not self._pose_hypos:
+            return
+        mx = self._model_host[0]
+        m001 = mx if getattr(self, "_model001_host", None) is None else self._model001_host
+        ext = m001.max(0) - m001.min(0)
+        smallest, diam = float(ext.min()), float(np.linalg.norm(ext))
+        status = [bool(hand["component_status"].get(n, False)) for n in self.FINGERS]
+        params = dict(cam2handbase=np.linalg.inv(np.asarray(hand["handbase_in_cam"], np.float32)), model_center=m001.mean(0),
+                      ob_diameter=diam, collision_dist=min(-smallest * float(cfg.get("collision_thres", 0.4)), -0.007),
+                      inside_ob_dist=min(-smallest / 5, -0.01), non_touch_dist=float(cfg.get("non_touch_dist", 0.01)),
+                      collision_finger_dist=-float(cfg.get("collision_finger_dist", 0.012)),
+                      collision_finger_volume_ratio=float(cfg.get("collision_finger_volume_ratio", 0.25)), finger_status=status)
+        meshes = getattr(self, "_meshes", {})
+        fclouds = [self.ctx.upload_cloud(hand["finger_clouds"][n]) if status[k] and n in hand["finger_clouds"] else None
+                   for k, n in enumerate(self.FINGERS)]
+        scene = self.ctx.upload_cloud(hand["cloud_withouthand"]) if len(hand.get("cloud_withouthand", ())) else None
+        hcloud = self.ctx.upload_cloud(hand["hand_cloud"]) if len(hand.get("hand_cloud", ())) else None
+        poses = np.stack([h._pose for h in self._pose_hypos])
+        keep, reason, _ = self.ctx.reject_by_collision(meshes["object"], [meshes.get(n) for n in self.FINGERS], fclouds, scene, hcloud,
+                                                       self._model, poses, params)
+        for c in fclouds + [scene, hcloud]:
+            if c is not None:
+                c.free()
+        self._pose_hypos = [h for h, k in zip(self._pose_hypos, keep) if k]
+        self._reject_reason = reason
 
     def selectBest(self):
         """Scores every hypothesis with computeLCP(1 mm model, lcp.dist, lcp.normal_angle, true,true,true) and returns

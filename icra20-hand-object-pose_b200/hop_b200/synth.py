@@ -279,3 +279,198 @@ def hand_problem(variant, seed=5):
     case = make_hand_case(seed=seed, **kw)
     case["scalars"].update(over)
     return case
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# triangle meshes + grasp scenes for the physics pruning step (PoseEstimator::rejectByCollisionOrNonTouching)
+# ------------------------------------------------------------------------------------------------------------------
+def _orient_outward(V, F):
+    """flip faces whose normal points towards the (star-shaped) mesh's centroid"""
+    c = V.mean(0)
+    a, b, d = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    n = np.cross(b - a, d - a)
+    flip = np.einsum("ij,ij->i", n, (a + b + d) / 3 - c) < 0
+    F = F.copy()
+    F[flip] = F[flip][:, [0, 2, 1]]
+    return F
+
+
+def _icosphere(level):
+    t = (1 + 5 ** 0.5) / 2
+    V = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1),
+         (-t, 0, -1), (-t, 0, 1)]
+    F = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6), (7, 1, 8),
+         (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    V = [np.array(v, float) / np.linalg.norm(v) for v in V]
+    for _ in range(level):
+        cache, F2 = {}, []
+
+        def mid(i, j):
+            key = (min(i, j), max(i, j))
+            if key not in cache:
+                m = V[i] + V[j]
+                V.append(m / np.linalg.norm(m))
+                cache[key] = len(V) - 1
+            return cache[key]
+        for a, b, c in F:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            F2 += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        F = F2
+    return np.array(V), np.array(F, np.int32)
+
+
+def _box_mesh(size, div=1, offset=(0, 0, 0)):
+    """closed box, each face a div x div grid of quads split in two; vertices shared along edges"""
+    h = np.asarray(size, float) / 2
+    key, V, F = {}, [], []
+
+    def vid(p):
+        k = tuple(np.round(p / (h / div)).astype(int))
+        if k not in key:
+            key[k] = len(V)
+            V.append(p)
+        return key[k]
+    for ax in range(3):
+        u, w = (ax + 1) % 3, (ax + 2) % 3
+        for sg in (1.0, -1.0):
+            for i in range(div):
+                for j in range(div):
+                    q = []
+                    for di, dj in ((0, 0), (1, 0), (1, 1), (0, 1)):
+                        p = np.zeros(3)
+                        p[ax] = sg * h[ax]
+                        p[u] = -h[u] + 2 * h[u] * (i + di) / div
+                        p[w] = -h[w] + 2 * h[w] * (j + dj) / div
+                        q.append(vid(p))
+                    F += [(q[0], q[1], q[2]), (q[0], q[2], q[3])]
+    V, F = np.array(V), np.array(F, np.int32)
+    return V + np.asarray(offset, float), _orient_outward(V, F)
+
+
+def _lathe(profile, nseg):
+    """revolve an (r, z) polyline that starts and ends on the axis (r = 0) about z"""
+    prof = np.asarray(profile, float)
+    V, ring = [], []
+    for r, z in prof:
+        if r == 0:
+            V.append((0, 0, z))
+            ring.append([len(V) - 1] * nseg)
+        else:
+            ids = []
+            for s in range(nseg):
+                th = 2 * np.pi * s / nseg
+                V.append((r * np.cos(th), r * np.sin(th), z))
+                ids.append(len(V) - 1)
+            ring.append(ids)
+    F = []
+    for k in range(len(prof) - 1):
+        a, b = ring[k], ring[k + 1]
+        for s in range(nseg):
+            t = (s + 1) % nseg
+            if a[s] != a[t]:
+                F.append((a[s], a[t], b[t]))
+            if b[s] != b[t]:
+                F.append((a[s], b[t], b[s]))
+    V, F = np.array(V), np.array(F, np.int32)
+    # a lathe surface is star-shaped about its axis per z-slab, not about the centroid: orient by the radial/axial direction
+    a, b, c = V[F[:, 0]], V[F[:, 1]], V[F[:, 2]]
+    n = np.cross(b - a, c - a)
+    m = (a + b + c) / 3
+    radial = np.stack([m[:, 0], m[:, 1], np.zeros(len(m))], 1)
+    side = np.abs(n[:, 2]) < 1e-12 * np.linalg.norm(n, axis=1).max()
+    out = np.where(side, np.einsum("ij,ij->i", n, radial), 0.0)
+    flip = out < 0
+    # caps / flange rings: decide by a ray test against the analytic profile (outward = away from the solid)
+    for i in np.where(~side)[0]:
+        r, z = np.hypot(m[i, 0], m[i, 1]), m[i, 2]
+        up = _lathe_inside(prof, r, z + 1e-6)
+        flip[i] = (n[i, 2] > 0) == up
+    F = F.copy()
+    F[flip] = F[flip][:, [0, 2, 1]]
+    return V, F
+
+
+def _lathe_inside(prof, r, z):
+    """point-in-polygon of (r, z) against the closed profile (axis closes it)"""
+    poly = np.concatenate([prof, prof[:1]])
+    inside = False
+    for (r0, z0), (r1, z1) in zip(poly[:-1], poly[1:]):
+        if (z0 > z) != (z1 > z):
+            rc = r0 + (z - z0) * (r1 - r0) / (z1 - z0)
+            if rc > r:
+                inside = not inside
+    return inside
+
+
+def make_mesh(name, level=2):
+    """closed, outward-oriented triangle mesh of a synthetic object (float32 vertices, int32 faces); `level` refines it"""
+    if name == "ellipse":
+        V, F = _icosphere(level)
+        V = V * [0.045, 0.030, 0.020]
+        F = _orient_outward(V, F)
+    elif name == "cuboid":
+        V, F = _box_mesh((0.08, 0.05, 0.03), div=max(1, level))
+    elif name == "cylinder":
+        V, F = _lathe([(0, -0.045), (0.025, -0.045), (0.025, 0.045), (0, 0.045)], 8 * max(1, level))
+    elif name == "tless":
+        V, F = _lathe([(0, -0.03), (0.045, -0.03), (0.045, -0.02), (0.03, -0.02), (0.03, 0.02), (0, 0.02)], 8 * max(1, level))
+    else:
+        raise KeyError(name)
+    return np.ascontiguousarray(V, np.float32), np.ascontiguousarray(F, np.int32)
+
+
+def make_collision_case(name="ellipse", H=256, seed=0, n_model=500, n_finger=300, n_scene=2500, n_hand=1500, mesh_level=2,
+                        rot_sigma_deg=8.0, trans_sigma=0.008, disabled=()):
+    """A grasp in the hand-base frame: the object between two two-link fingers, a camera looking at it, H pose hypotheses (in the
+    camera frame, like PoseHypo::_pose) scattered around the true pose widely enough to hit every reject branch.
+    Returns a dict with everything hop_reject_by_collision / the oracle take.  Finger order: finger_1_1, finger_1_2, finger_2_1,
+    finger_2_2 (proximal, distal of finger 1; proximal, distal of finger 2)."""
+    rng = np.random.default_rng(seed)
+    V, F = make_mesh(name, mesh_level)
+    m_xyz, _ = make_model(name, n_model, seed=seed + 11)
+    ext = V.max(0) - V.min(0)
+    smallest, diam = float(ext.min()), float(np.linalg.norm(ext))
+    # object pose in the hand-base frame: centred between the fingers, which close along y
+    R = random_rotation(rng)
+    obj_in_hb = np.eye(4)
+    obj_in_hb[:3, :3] = R
+    obj_in_hb[:3, 3] = [-0.17, 0.0, -0.02]
+    Vh = V @ R.T + obj_in_hb[:3, 3]
+    half_y = float(np.abs(Vh[:, 1]).max())
+    # camera: looks along +z from 0.35 m
+    cam_in_hb = np.eye(4)
+    cam_in_hb[:3, :3] = _rot_x(np.deg2rad(200.0))[:3, :3] @ _rot_from_rotvec(np.array([0.0, 0.25, 0.1]))
+    cam_in_hb[:3, 3] = [-0.15, 0.05, 0.33]
+    cam2hb = cam_in_hb                                  # maps camera-frame points into the hand base (handbase_in_cam^-1)
+    gt_cam = np.linalg.inv(cam2hb) @ obj_in_hb
+    # fingers: boxes (link meshes) whose inner faces touch the object from -y and +y
+    size = (0.02, 0.012, 0.05)
+    fingers_V, fingers_F, fingers_pts = [], [], []
+    for side in (-1.0, 1.0):
+        for link in range(2):
+            off = np.array([-0.17 + (0.03 if link == 0 else -0.025), side * (half_y + size[1] / 2 + 0.0005), -0.02])
+            fv, ff = _box_mesh(size, div=3, offset=off)
+            fp, _ = _cuboid(rng, n_finger, *size)
+            fingers_V.append(fv.astype(np.float32))
+            fingers_F.append(ff)
+            fingers_pts.append((fp + off).astype(np.float32))
+    status = np.array([0 if k in disabled else 1 for k in range(4)], np.int32)
+    hand_xyz = np.concatenate(fingers_pts + [(_cuboid(rng, n_hand // 3, 0.08, 0.1, 0.02)[0] + [-0.09, 0, -0.02]).astype(np.float32)])
+    hand_xyz = hand_xyz[rng.permutation(len(hand_xyz))[:n_hand]].astype(np.float32)
+    # scene without the hand: visible part of the object + table clutter, in the hand-base frame, 5 mm voxel sampled
+    sp, sn = make_model(name, 6 * n_scene, seed=seed + 12)
+    sp = sp @ R.T + obj_in_hb[:3, 3]
+    view = cam_in_hb[:3, 3] - sp
+    vis = np.einsum("ij,ij->i", sn @ R.T, view) > 0
+    sp = sp[vis] + rng.normal(0, 0.0004, (int(vis.sum()), 3))
+    clutter = rng.uniform([-0.3, -0.15, -0.12], [0.0, 0.15, -0.10], (n_scene, 3))
+    scene = np.concatenate([sp, clutter])
+    vox = np.unique(np.floor(scene / 0.005).astype(np.int64), axis=0, return_index=True)[1]
+    scene = scene[np.sort(vox)][:n_scene].astype(np.float32)
+    poses = make_hypotheses(gt_cam, H, seed=seed + 13, rot_sigma_deg=rot_sigma_deg, trans_sigma=trans_sigma, random_frac=0.05)
+    params = dict(cam2handbase=cam2hb.astype(np.float32), model_center=m_xyz.mean(0).astype(np.float32),
+                  ob_diameter=diam, collision_dist=min(-smallest * 0.4, -0.007), inside_ob_dist=min(-smallest / 5, -0.01),
+                  non_touch_dist=0.01, collision_finger_dist=-0.012, collision_finger_volume_ratio=0.25, finger_status=status)
+    # (config_autodataset.yaml:128-131: collision_thres 0.4, non_touch_dist 0.01, collision_finger_dist 0.012, volume ratio 0.25)
+    return dict(obj_V=V, obj_F=F, finger_V=fingers_V, finger_F=fingers_F, finger_pts=fingers_pts, hand_xyz=hand_xyz, scene_xyz=scene,
+                model_xyz=m_xyz, poses=poses.astype(np.float32), gt=gt_cam.astype(np.float32), params=params)

@@ -101,7 +101,8 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 #define HOP_PROF_S4_JOIN 9        /* K2b: prepare_pairs + congruent_join (count, scan, fill) */
 #define HOP_PROF_CLUSTER 10       /* hop_cluster_poses_gpu: all block launches of one call = one span */
 #define HOP_PROF_FRAME 11         /* hop_frame_to_scene: every launch of one frame's front end = one span */
-#define HOP_PROF_KINDS 12
+#define HOP_PROF_SDF 12           /* sdf_kernel / collision_kernel (physics pruning) */
+#define HOP_PROF_KINDS 13
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
 int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans);
@@ -291,6 +292,51 @@ int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int width, int he
                        int32_t *stage_counts);
 /* copies a device cloud back (tests, debugging output such as scene_normals.ply); any pointer may be NULL */
 int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob);
+
+/* ---- physics pruning: signed distance to meshes, rejectByCollisionOrNonTouching ------------------------------------- */
+/* A triangle mesh with every normal igl::signed_distance builds for SIGNED_DISTANCE_TYPE_PSEUDONORMAL (face, angle-weighted
+ * vertex, uniform edge: src/perception/include/igl/signed_distance.cpp:97-100), resident on the device.  Replaces
+ * SDFchecker::registerMesh (src/perception/src/SDFchecker.cpp:36-78): V nv x 3 floats, F nf x 3 vertex indices. */
+typedef struct hop_mesh hop_mesh;
+int hop_mesh_upload(hop_ctx *ctx, const float *V, int nv, const int32_t *F, int nf, hop_mesh **out);
+int hop_mesh_free(hop_ctx *ctx, hop_mesh *mesh);
+/* SDFchecker::getSignedDistanceMinMaxWithRegistered (SDFchecker.cpp:115-134) for H placements at once:
+ * S[h*n+i] = signed distance (negative inside) of point_transforms[h] * pts[i] to the mesh, I = the closest face (first among
+ * exact ties), min_out/max_out[h] = S.minCoeff()/maxCoeff(), n_inside[h] = #(S < 0).  point_transforms: H x 16 column-major
+ * (NULL = identity, H placements of the same points) -- the INVERSE of the pose SDFchecker::transformMesh would apply to the
+ * mesh.  Any output may be NULL.  n = 0: min = FLT_MAX, max = -FLT_MAX. */
+int hop_sdf_query(hop_ctx *ctx, const hop_mesh *mesh, const float *pts, int n, const float *point_transforms, int H, float *S,
+                  int32_t *I, float *min_out, float *max_out, int32_t *n_inside);
+
+typedef struct hop_collision_params {
+  float cam2handbase[16];  /* column-major: hand->_handbase_in_cam.inverse() (PoseEstimator.cpp:567) */
+  float model_center[3];   /* _model_center_init: centroid of model001 (PoseEstimator.cpp:12) */
+  float ob_diameter;       /* _ob_diameter (PoseEstimator.cpp:20) */
+  float collision_dist;    /* min(-_smallest_dim * collision_thres, -0.007) (:563) */
+  float inside_ob_dist;    /* min(-_smallest_dim / 5, -0.01) (:564) */
+  float non_touch_dist;    /* cfg non_touch_dist */
+  float collision_finger_dist;          /* -cfg collision_finger_dist (:567) */
+  float collision_finger_volume_ratio;  /* cfg collision_finger_volume_ratio */
+  int32_t finger_status[4];             /* hand->_component_status of finger_1_1, finger_1_2, finger_2_1, finger_2_2 */
+} hop_collision_params;
+/* PoseEstimator::rejectByCollisionOrNonTouching (PoseEstimator.cpp:524-735) for H hypotheses in one launch, every test in the
+ * hand-base frame and in the reference's order.  Arrays of 4 follow std::map order: finger_1_1, finger_1_2, finger_2_1,
+ * finger_2_2; finger_clouds[k] = the link's cloud already in the hand-base frame (NULL = link disabled, not in
+ * finger_cloud_eigens), finger_meshes[k] = the link's convex mesh registered in the hand-base frame (registerHandMesh, :513-521;
+ * NULL = not registered).  scene_without_hand = _cloud_withouthand_raw in the hand-base frame after the 5 mm VoxelGrid (:556-559),
+ * hand_cloud = hand->_hand_cloud, model = _model (own frame), poses = H x 16 column-major PoseHypo::_pose (model -> camera).
+ * keep[h] = 1 when hypothesis h survives (the caller compacts in order; the reference's survivors come out in OpenMP order);
+ * reason[h] (may be NULL): 0 kept, 1 scene point deep inside the object, 2 hand point inside the object, 3 a finger cloud
+ * penetrates the object, 4 one whole side does not touch, 5 the object penetrates a finger mesh, 6 the object is inside a finger;
+ * diag (may be NULL): H x 10 = signed distance of the scene point, of the hand point, min over each finger cloud (4), min of the
+ * model over each finger mesh (4); FLT_MAX where a step was not evaluated. */
+int hop_reject_by_collision(hop_ctx *ctx, const hop_mesh *object, const hop_mesh *const *finger_meshes, hop_cloud *const *finger_clouds,
+                            hop_cloud *scene_without_hand, hop_cloud *hand_cloud, hop_cloud *model, const float *poses, int H,
+                            const hop_collision_params *params, int32_t *keep, int32_t *reason, float *diag);
+/* the same on device buffers, stream-ordered on the context's stream (no synchronisation) */
+int hop_reject_by_collision_dev(hop_ctx *ctx, const hop_mesh *object, const hop_mesh *const *finger_meshes, hop_cloud *const *finger_clouds,
+                                hop_cloud *scene_without_hand, hop_cloud *hand_cloud, hop_cloud *model, const float *d_poses, int H,
+                                const hop_collision_params *params, int32_t *d_keep, int32_t *d_reason, float *d_diag);
 
 /* ---- winners ------------------------------------------------------------------------------------------------- */
 /* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).

@@ -24,5 +24,10 @@ if [ -f "$HERE/ref_opengr.cpp" ]; then
   INCS="-I$TMP -I$GR $INCS"
 fi
 if [ -f "$HERE/ref_cluster.cpp" ]; then SRCS="$SRCS $HERE/ref_cluster.cpp"; fi
+# the reference's vendored libigl (header-only use): signed distance to a mesh, what SDFchecker calls
+if [ -f "$HERE/ref_sdf.cpp" ] && [ -f "$REF/src/perception/include/igl/signed_distance.h" ]; then
+  SRCS="$SRCS $HERE/ref_sdf.cpp"
+  INCS="$INCS -I$REF/src/perception/include"
+fi
 $CXX -std=c++17 -O2 -fopenmp -fPIC -shared -w $INCS -o "$HERE/_ref/libhop_ref.so" $SRCS
 echo "oracle: built $HERE/_ref/libhop_ref.so"

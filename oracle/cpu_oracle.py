@@ -302,3 +302,67 @@ def ref_cluster_poses(poses, scores, angle_diff, dist_diff, symmetry_deg=(360.0,
     n = ref().hop_ref_cluster_poses(flat, sc, None if idv is None else idv.ctypes.data_as(C.c_void_p), len(flat), angle_diff, dist_diff,
                                     np.ascontiguousarray(symmetry_deg, np.float64), keep)
     return keep[:n].copy()
+
+
+# ---- physics pruning ---------------------------------------------------------------------------
+class CollisionParams(C.Structure):
+    """same layout as hop_collision_params (include/hop_c_api.h)"""
+    _fields_ = [("cam2handbase", C.c_float * 16), ("model_center", C.c_float * 3), ("ob_diameter", C.c_float),
+                ("collision_dist", C.c_float), ("inside_ob_dist", C.c_float), ("non_touch_dist", C.c_float),
+                ("collision_finger_dist", C.c_float), ("collision_finger_volume_ratio", C.c_float), ("finger_status", C.c_int32 * 4)]
+
+
+def collision_params(d, cls=CollisionParams):
+    p = cls()
+    p.cam2handbase[:] = np.asarray(d["cam2handbase"], np.float32).T.reshape(-1).tolist()   # column-major
+    p.model_center[:] = [float(v) for v in d["model_center"]]
+    for k in ("ob_diameter", "collision_dist", "inside_ob_dist", "non_touch_dist", "collision_finger_dist", "collision_finger_volume_ratio"):
+        setattr(p, k, float(d[k]))
+    p.finger_status[:] = [int(v) for v in d["finger_status"]]
+    return p
+
+
+def signed_distance(pts, V, F):
+    """restated igl::signed_distance (pseudonormal): returns S, closest face, closest point"""
+    L = lib()
+    pts, V, F = _c(pts), _c(V), np.ascontiguousarray(F, np.int32)
+    S, I, Cp = np.empty(len(pts), np.float32), np.empty(len(pts), np.int32), np.empty((len(pts), 3), np.float32)
+    L.hop_oracle_signed_distance.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p, _f32p]
+    rc = L.hop_oracle_signed_distance(pts, len(pts), V, len(V), F, len(F), S, I, Cp)
+    assert rc == 0
+    return S, I, Cp
+
+
+def ref_signed_distance(pts, V, F):
+    """the reference's vendored libigl (compiled where it lies): S, I, C, N of igl::signed_distance"""
+    R = ref()
+    pts, V, F = _c(pts), _c(V), np.ascontiguousarray(F, np.int32)
+    n = len(pts)
+    S, I, Cp, N = np.empty(n, np.float32), np.empty(n, np.int32), np.empty((n, 3), np.float32), np.empty((n, 3), np.float32)
+    R.hop_ref_signed_distance.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p, _f32p, _f32p]
+    R.hop_ref_signed_distance(pts, n, V, len(V), F, len(F), S, I, Cp, N)
+    return S, I, Cp, N
+
+
+def reject_by_collision(case, nthreads=0):
+    """restated PoseEstimator::rejectByCollisionOrNonTouching over a synth.make_collision_case dict: keep, reason, diag"""
+    L = lib()
+    H = len(case["poses"])
+    fV = _c(np.concatenate(case["finger_V"])) if sum(len(v) for v in case["finger_V"]) else np.zeros((1, 3), np.float32)
+    fF = np.ascontiguousarray(np.concatenate(case["finger_F"]), np.int32) if sum(len(f) for f in case["finger_F"]) else np.zeros((1, 3), np.int32)
+    fP = _c(np.concatenate(case["finger_pts"])) if sum(len(v) for v in case["finger_pts"]) else np.zeros((1, 3), np.float32)
+    fnv = np.array([len(v) for v in case["finger_V"]], np.int32)
+    fnf = np.array([len(f) for f in case["finger_F"]], np.int32)
+    fn = np.array([len(v) for v in case["finger_pts"]], np.int32)
+    keep, reason, diag = np.empty(H, np.int32), np.empty(H, np.int32), np.empty((H, 10), np.float32)
+    p = collision_params(case["params"])
+    L.hop_oracle_reject_by_collision.argtypes = [_f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p, _i32p, _i32p, _f32p, _i32p, _f32p, C.c_int,
+                                                 _f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(CollisionParams), _i32p, _i32p, _f32p]
+    import os as _os
+    old = _os.environ.get("OMP_NUM_THREADS")
+    rc = L.hop_oracle_reject_by_collision(_c(case["obj_V"]), len(case["obj_V"]), np.ascontiguousarray(case["obj_F"], np.int32), len(case["obj_F"]),
+                                          fV, fnv, fF, fnf, fP, fn, _c(case["scene_xyz"]), len(case["scene_xyz"]), _c(case["hand_xyz"]),
+                                          len(case["hand_xyz"]), _c(case["model_xyz"]), len(case["model_xyz"]),
+                                          poses_to_colmajor(case["poses"]), H, C.byref(p), keep, reason, diag)
+    assert rc == 0
+    return keep, reason, diag

@@ -49,8 +49,58 @@ def ppf_keys(xyz, nrm, stride=1):
     return np.array(sorted(seen), np.int32).reshape(-1, 4)
 
 
+def collision_stage(ctx, args, out, timed, peak):
+    """physics pruning: PoseEstimator::rejectByCollisionOrNonTouching for a batch of hypotheses (hop_reject_by_collision)"""
+    from hop_b200 import synth
+    H = 1024 if args.sizes == "C2" else 16384
+    n_model = 600 if args.sizes == "C2" else 2000           # _model is the 5 mm cloud (a few hundred points in the reference)
+    case = synth.make_collision_case("ellipse", H=H, seed=51, n_model=n_model, mesh_level=2 if args.sizes == "C2" else 3)
+    obj = ctx.upload_mesh(case["obj_V"], case["obj_F"])
+    fm = [ctx.upload_mesh(v, f) for v, f in zip(case["finger_V"], case["finger_F"])]
+    fc = [ctx.upload_cloud(p) for p in case["finger_pts"]]
+    scene, hand, model = ctx.upload_cloud(case["scene_xyz"]), ctx.upload_cloud(case["hand_xyz"]), ctx.upload_cloud(case["model_xyz"])
+    params = ctx.collision_params(case["params"])
+    res = {}
+
+    def run():
+        res["r"] = ctx.reject_by_collision(obj, fm, fc, scene, hand, model, case["poses"], params)
+
+    dt, prof = timed(run)
+    k_ms = prof["sdf"][0] / max(prof["sdf"][1], 1)
+    keep, reason, diag = res["r"]
+    # point-triangle tests the reference's brute-force equivalent would do for the steps each hypothesis reached
+    nfo, nff = len(case["obj_F"]), sum(len(f) for f in case["finger_F"])
+    npf = sum(len(p) for p in case["finger_pts"])
+    tests = float(np.sum((reason != 1) * 1.0) * 0 + len(reason) * nfo + np.sum(reason != 1) * nfo + np.sum(~np.isin(reason, [1, 2])) * npf * nfo
+                  + np.sum(np.isin(reason, [0, 5, 6])) * len(case["model_xyz"]) * nff)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu_oracle as O
+        thr = max(1, len(os.sched_getaffinity(0)))
+        n_s = min(H, 1024)
+        sub = dict(case)
+        sub["poses"] = case["poses"][:n_s]
+        t0 = time.perf_counter()
+        okeep, oreason, _ = O.reject_by_collision(sub)
+        tc = time.perf_counter() - t0
+        cpu = {"value": n_s / tc, "unit": "hypotheses/s", "cores": thr, "kind": "port", "same_decisions": float(np.mean(oreason == reason[:n_s])),
+               "sample": f"first {n_s} of {H} hypotheses, {tc:.2f} s (restated igl signed distance, brute force over faces, OpenMP over hypotheses; "
+                         "the reference rebuilds an AABB tree per hypothesis instead)"}
+    print(json.dumps({"stage": "rejectByCollisionOrNonTouching (hop_reject_by_collision: signed distances + the whole decision, one launch)",
+                      "metric": "hypotheses pruned/sec", "value": H / (k_ms * 1e-3), "unit": "hypotheses/s", "cpu_baseline": cpu,
+                      "e2e": {"value": H / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3, "h2d_bytes": 64 * H, "d2h_bytes": 48 * H},
+                      "config": {"sizes": args.sizes, "H": H, "object_faces": nfo, "finger_faces": nff, "finger_points": npf, "n_model": len(case["model_xyz"]),
+                                 "n_scene": len(case["scene_xyz"]), "n_hand": len(case["hand_xyz"]), "kept": int(keep.sum()),
+                                 "reasons": np.bincount(reason, minlength=7).tolist()},
+                      "kernel_ms": k_ms, "dtype": "f32", "point_triangle_tests_per_launch": tests,
+                      "gtests_per_s": tests / (k_ms * 1e-3) / 1e9,
+                      "note": "ALU-bound (meshes and clouds stay in L1/L2): the figure of merit is point-triangle tests per second, not HBM bytes"}),
+          file=out, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
+    ap.add_argument("--stages", default="all", help="all | collision (only the physics pruning stage)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sizes", default="C2")
@@ -82,6 +132,11 @@ def main():
         prof = ctx.profile_read()
         ctx.profile_enable(False)
         return dt, prof
+
+    if args.stages == "collision":
+        collision_stage(ctx, args, out, timed, peak)
+        ctx.close()
+        return
 
     # ---------------- K1: S joint angles of one finger link ----------------
     case = synth.make_hand_case(seed=5, n_finger=sz["n_finger"], n_hand=sz["n_hand"])
@@ -310,6 +365,7 @@ super4pcs_success_quadrilaterals: 10
     print(json.dumps({"stage": "clusterPoses(30 deg, 15 mm) on the device (hop_cluster_poses_gpu)", "metric": "hypotheses clustered/sec", "value": n_cl / dt,
                       "unit": "hypotheses/s", "cpu_baseline": cpu3, "e2e": {"value": n_cl / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3},
                       "config": {"n": n_cl, "clusters": int(len(res["cl"]))}, "kernel_ms": prof["cluster"][0] / max(prof["cluster"][1], 1)}), file=out, flush=True)
+    collision_stage(ctx, args, out, timed, peak)
     ctx.close()
 
 
