@@ -344,7 +344,7 @@ def ref_signed_distance(pts, V, F):
     return S, I, Cp, N
 
 
-def reject_by_collision(case, nthreads=0):
+def reject_by_collision(case, nthreads=0, with_ambiguous=False):
     """restated PoseEstimator::rejectByCollisionOrNonTouching over a synth.make_collision_case dict: keep, reason, diag"""
     L = lib()
     H = len(case["poses"])
@@ -356,13 +356,25 @@ def reject_by_collision(case, nthreads=0):
     fn = np.array([len(v) for v in case["finger_pts"]], np.int32)
     keep, reason, diag = np.empty(H, np.int32), np.empty(H, np.int32), np.empty((H, 10), np.float32)
     p = collision_params(case["params"])
-    L.hop_oracle_reject_by_collision.argtypes = [_f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p, _i32p, _i32p, _f32p, _i32p, _f32p, C.c_int,
-                                                 _f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(CollisionParams), _i32p, _i32p, _f32p]
-    import os as _os
-    old = _os.environ.get("OMP_NUM_THREADS")
-    rc = L.hop_oracle_reject_by_collision(_c(case["obj_V"]), len(case["obj_V"]), np.ascontiguousarray(case["obj_F"], np.int32), len(case["obj_F"]),
+    amb = np.zeros(H, np.int32)
+    L.hop_oracle_reject_by_collision_amb.argtypes = [_f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p, _i32p, _i32p, _f32p, _i32p, _f32p, C.c_int,
+                                                     _f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.POINTER(CollisionParams), _i32p, _i32p, _f32p,
+                                                     C.c_void_p]
+    rc = L.hop_oracle_reject_by_collision_amb(_c(case["obj_V"]), len(case["obj_V"]), np.ascontiguousarray(case["obj_F"], np.int32), len(case["obj_F"]),
                                           fV, fnv, fF, fnf, fP, fn, _c(case["scene_xyz"]), len(case["scene_xyz"]), _c(case["hand_xyz"]),
                                           len(case["hand_xyz"]), _c(case["model_xyz"]), len(case["model_xyz"]),
-                                          poses_to_colmajor(case["poses"]), H, C.byref(p), keep, reason, diag)
+                                          poses_to_colmajor(case["poses"]), H, C.byref(p), keep, reason, diag,
+                                          amb.ctypes.data if with_ambiguous else None)
     assert rc == 0
-    return keep, reason, diag
+    return (keep, reason, diag, amb) if with_ambiguous else (keep, reason, diag)
+
+
+def signed_distance_ambiguous(pts, V, F):
+    """S and per-point flags: 1 where the sign of the distance is a coin toss between tied faces / candidate normals
+    (hop_oracle_sdf.c: sdf_point_amb) -- what another summation order, an FMA or igl's AABB traversal may resolve the other way"""
+    L = lib()
+    pts, V, F = _c(pts), _c(V), np.ascontiguousarray(F, np.int32)
+    S, A = np.empty(len(pts), np.float32), np.empty(len(pts), np.int32)
+    L.hop_oracle_signed_distance_amb.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p]
+    assert L.hop_oracle_signed_distance_amb(pts, len(pts), V, len(V), F, len(F), S, A) == 0
+    return S, A

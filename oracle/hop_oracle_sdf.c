@@ -194,6 +194,52 @@ static float pseudonormal_sign(const sdf_mesh *m, int f, const float *q, const f
   return dot3f(qc, n) >= 0.f ? 1.f : -1.f;
 }
 
+/* test support: set to 1 when some face within a relative tie_tol (3e-7, a few ulp) of the smallest squared distance (a float tie that another
+ * summation order, an FMA, or igl's AABB traversal order resolves the other way) would sign the distance differently -- the
+ * reference's own answer is then a coin toss (e.g. a far point whose foot lies within ~1e-6 m of a sharp edge of small faces:
+ * the face fallback of pseudonormal_test.cpp:117-121 signs it with whichever face came first) */
+static float tie_tol = 3e-7f, dot_tol = 1e-6f;
+void hop_oracle_sdf_amb_tolerances(float tie, float dot) { tie_tol = tie; dot_tol = dot; }
+static float sdf_point_amb(const sdf_mesh *m, const float *q, float s, float best, int *amb) {
+  for (int f = 0; f < m->nf; ++f) {
+    float c[3];
+    const float d2 = closest_on_triangle(q, m->tri + 9 * f, m->tri + 9 * f + 3, m->tri + 9 * f + 6, c);
+    if (d2 > best * (1.f + tie_tol) + 1e-14f) continue;
+    /* every normal igl could pick for this foot: the face's, and those of the vertices / edges the foot lies on (within 1e-6 m) */
+    const float qc[3] = {q[0] - c[0], q[1] - c[1], q[2] - c[2]};
+    const float len = sqrtf(dot3f(qc, qc));
+    const float *cand[7]; int nc = 0;
+    cand[nc++] = m->fn + 3 * f;
+    for (int v = 0; v < 3; ++v) {
+      const float *P = m->tri + 9 * f + 3 * v;
+      const float d[3] = {c[0] - P[0], c[1] - P[1], c[2] - P[2]};
+      if (sqrtf(dot3f(d, d)) < 1e-6f) cand[nc++] = m->vn + 9 * f + 3 * v;
+    }
+    for (int e = 0; e < 3; ++e) {
+      const float *S = m->tri + 9 * f + 3 * ((e + 1) % 3), *D = m->tri + 9 * f + 3 * ((e + 2) % 3);
+      float dms[3], sc[3];
+      for (int k = 0; k < 3; ++k) { dms[k] = D[k] - S[k]; sc[k] = c[k] - S[k]; }
+      float t = dot3f(dms, sc) / dot3f(dms, dms);
+      t = t < 0.f ? 0.f : (t > 1.f ? 1.f : t);
+      const float r[3] = {sc[0] - t * dms[0], sc[1] - t * dms[1], sc[2] - t * dms[2]};
+      if (sqrtf(dot3f(r, r)) < 1e-6f) cand[nc++] = m->en + 9 * f + 3 * e;
+    }
+    for (int k = 0; k < nc; ++k) {
+      const float nl = sqrtf(dot3f(cand[k], cand[k]));
+      const float dt = dot3f(qc, cand[k]);
+      if (dt * s < 0.f || fabsf(dt) < dot_tol * len * nl) { *amb = 1; return s; }
+    }
+  }
+  return s;
+}
+
+static float sdf_point(const sdf_mesh *m, const float *q, int *face, float *cp);
+static float sdf_point_flag(const sdf_mesh *m, const float *q, int *amb) {
+  const float s = sdf_point(m, q, NULL, NULL);
+  if (amb && s == s && fabsf(s) > 1e-4f) sdf_point_amb(m, q, s, s * s, amb);   /* next to the surface a flipped sign moves no threshold test */
+  return s;
+}
+
 static float sdf_point(const sdf_mesh *m, const float *q, int *face, float *cp) {
   float best = FLT_MAX, bc[3] = {0, 0, 0};
   int bf = -1;
@@ -270,15 +316,76 @@ static int nn_brute(const float *pts, int n, const float *q, float *d2out) {
  * object, 3 finger cloud penetrates, 4 one side does not touch, 5 object penetrates a finger mesh, 6 object inside a finger.
  * diag (may be NULL): H x 10 floats = sdf of the scene point, of the hand point, min over each finger cloud (4), min of the model
  * over each finger mesh (4); FLT_MAX where the step was not reached. */
-int hop_oracle_reject_by_collision(const float *objV, int onv, const int32_t *objF, int onf, const float *fingerV, const int32_t *fnv,
-                                   const int32_t *fingerF, const int32_t *fnf, const float *finger_pts, const int32_t *finger_n,
-                                   const float *scene_xyz, int ns, const float *hand_xyz, int nh, const float *model_xyz, int nm,
-                                   const float *poses, int H, const hop_oracle_collision_params *p, int32_t *keep, int32_t *reason,
-                                   float *diag) {
+/* mode 0: the distance as found; mode 1 / 2 (test support): a point whose sign is a coin toss (sdf_point_amb) counts as
+ * outside / inside -- a hypothesis whose decision is the same in all three modes does not depend on any coin toss */
+static float sdf_eval(const sdf_mesh *m, const float *q, int mode) {
+  if (mode == 0) return sdf_point(m, q, NULL, NULL);
+  int amb = 0;
+  const float s = sdf_point_flag(m, q, &amb);
+  return amb ? (mode == 1 ? fabsf(s) : -fabsf(s)) : s;
+}
+
+typedef struct {
+  const float *scene_xyz, *hand_xyz, *model_xyz, *finger_pts;
+  const int32_t *finger_n;
+  int ns, nh, nm;
+  const int *poff;
+  const sdf_mesh *fm;
+  const hop_oracle_collision_params *p;
+} reject_ctx;
+
+static int reject_one(const reject_ctx *c, const sdf_mesh *om, const float *M, const float *P, int mode, float *dg) {
+  const hop_oracle_collision_params *p = c->p;
+  float ctr[3];
+  xform_pts(M, p->model_center, 1, ctr);
+  if (c->ns > 0) { /* nearest scene point to the object centre inside the object? (PoseEstimator.cpp:596-615) */
+    const int i = nn_brute(c->scene_xyz, c->ns, ctr, NULL);
+    const float s = sdf_eval(om, c->scene_xyz + 3 * i, mode);
+    if (dg) dg[0] = s;
+    if (s <= p->inside_ob_dist) return 1;
+  }
+  if (c->nh > 0) { /* quick check: the hand point nearest to the object centre (:618-641) */
+    float d2;
+    const int i = nn_brute(c->hand_xyz, c->nh, ctr, &d2);
+    if (sqrtf(d2) < p->ob_diameter / 2) {
+      const float s = sdf_eval(om, c->hand_xyz + 3 * i, mode);
+      if (dg) dg[1] = s;
+      if (s < p->collision_dist) return 2;
+    }
+  }
+  int non_touch[4] = {0, 0, 0, 0};
+  for (int k = 0; k < 4; ++k) { /* finger clouds against the object (:645-668) */
+    if (c->finger_n[k] <= 0) continue;
+    if (!p->finger_status[0] && k < 2) continue;
+    if (!p->finger_status[2] && k >= 2) continue;
+    float mn = FLT_MAX;
+    for (int i = 0; i < c->finger_n[k]; ++i) { const float s = sdf_eval(om, c->finger_pts + 3 * (c->poff[k] + i), mode); if (s < mn) mn = s; }
+    if (dg) dg[2 + k] = mn;
+    if (mn <= p->collision_dist) return 3;
+    if (mn > p->non_touch_dist && p->finger_status[k]) non_touch[k] = 1;
+  }
+  if ((non_touch[0] && non_touch[1]) || (non_touch[2] && non_touch[3])) return 4; /* :675-680 */
+  for (int k = 0; k < 4; ++k) { /* the object's points against every finger mesh (:683-723) */
+    if (c->fm[k].nf <= 0 || c->nm <= 0) continue;
+    float mn = FLT_MAX; int inside = 0;
+    for (int i = 0; i < c->nm; ++i) { const float s = sdf_eval(&c->fm[k], P + 3 * i, mode); if (s < mn) mn = s; if (s < 0.f) ++inside; }
+    if (dg) dg[6 + k] = mn;
+    if (mn < p->collision_finger_dist) return 5;
+    if ((float)(inside / c->nm) > p->collision_finger_volume_ratio) return 6; /* integer division, as in the reference */
+  }
+  return 0;
+}
+
+int hop_oracle_reject_by_collision_amb(const float *objV, int onv, const int32_t *objF, int onf, const float *fingerV, const int32_t *fnv,
+                                       const int32_t *fingerF, const int32_t *fnf, const float *finger_pts, const int32_t *finger_n,
+                                       const float *scene_xyz, int ns, const float *hand_xyz, int nh, const float *model_xyz, int nm,
+                                       const float *poses, int H, const hop_oracle_collision_params *p, int32_t *keep, int32_t *reason,
+                                       float *diag, int32_t *ambiguous /* H or NULL: 1 = the decision hangs on a coin toss (sdf_eval) */) {
   sdf_mesh fm[4];
   int voff[5] = {0}, foff[5] = {0}, poff[5] = {0};
   for (int k = 0; k < 4; ++k) { voff[k + 1] = voff[k] + fnv[k]; foff[k + 1] = foff[k] + fnf[k]; poff[k + 1] = poff[k] + finger_n[k]; }
   for (int k = 0; k < 4; ++k) { fm[k].nf = 0; if (fnf[k] > 0 && sdf_mesh_build(&fm[k], fingerV + 3 * voff[k], fnv[k], fingerF + 3 * foff[k], fnf[k])) return -1; }
+  const reject_ctx c = {scene_xyz, hand_xyz, model_xyz, finger_pts, finger_n, ns, nh, nm, poff, fm, p};
   int rc = 0;
 #pragma omp parallel for schedule(dynamic)
   for (int h = 0; h < H; ++h) {
@@ -289,54 +396,35 @@ int hop_oracle_reject_by_collision(const float *objV, int onv, const int32_t *ob
     float *dg = diag ? diag + 10 * (size_t)h : NULL;
     if (dg) for (int k = 0; k < 10; ++k) dg[k] = FLT_MAX;
     sdf_mesh om;
-    xform_pts(M, objV, onv, Vt);
-    if (!Vt || !P || sdf_mesh_build(&om, Vt, onv, objF, onf)) { rc = -1; free(Vt); free(P); continue; }
-    float ctr[3];
-    xform_pts(M, p->model_center, 1, ctr);
-    int why = 0;
-    do {
-      if (ns > 0) { /* nearest scene point to the object centre inside the object? */
-        const int i = nn_brute(scene_xyz, ns, ctr, NULL);
-        const float s = sdf_point(&om, scene_xyz + 3 * i, NULL, NULL);
-        if (dg) dg[0] = s;
-        if (s <= p->inside_ob_dist) { why = 1; break; }
-      }
-      if (nh > 0) { /* quick check: the hand point nearest to the object centre */
-        float d2;
-        const int i = nn_brute(hand_xyz, nh, ctr, &d2);
-        if (sqrtf(d2) < p->ob_diameter / 2) {
-          const float s = sdf_point(&om, hand_xyz + 3 * i, NULL, NULL);
-          if (dg) dg[1] = s;
-          if (s < p->collision_dist) { why = 2; break; }
-        }
-      }
-      int non_touch[4] = {0, 0, 0, 0};
-      for (int k = 0; k < 4 && !why; ++k) {
-        if (finger_n[k] <= 0) continue;
-        if (!p->finger_status[0] && k < 2) continue;
-        if (!p->finger_status[2] && k >= 2) continue;
-        float mn = FLT_MAX;
-        for (int i = 0; i < finger_n[k]; ++i) { const float s = sdf_point(&om, finger_pts + 3 * (poff[k] + i), NULL, NULL); if (s < mn) mn = s; }
-        if (dg) dg[2 + k] = mn;
-        if (mn <= p->collision_dist) { why = 3; break; }
-        if (mn > p->non_touch_dist && p->finger_status[k]) non_touch[k] = 1;
-      }
-      if (why) break;
-      if ((non_touch[0] && non_touch[1]) || (non_touch[2] && non_touch[3])) { why = 4; break; }
-      xform_pts(M, model_xyz, nm, P);
-      for (int k = 0; k < 4 && !why; ++k) {
-        if (fm[k].nf <= 0 || nm <= 0) continue;
-        float mn = FLT_MAX; int inside = 0;
-        for (int i = 0; i < nm; ++i) { const float s = sdf_point(&fm[k], P + 3 * i, NULL, NULL); if (s < mn) mn = s; if (s < 0.f) ++inside; }
-        if (dg) dg[6 + k] = mn;
-        if (mn < p->collision_finger_dist) { why = 5; break; }
-        if ((float)(inside / nm) > p->collision_finger_volume_ratio) { why = 6; break; } /* integer division, as in the reference */
-      }
-    } while (0);
+    if (!Vt || !P) { rc = -1; free(Vt); free(P); continue; }
+    xform_pts(M, objV, onv, Vt);   /* SDFchecker::transformMesh("object", model2handbase) */
+    if (sdf_mesh_build(&om, Vt, onv, objF, onf)) { rc = -1; free(Vt); free(P); continue; }
+    xform_pts(M, model_xyz, nm, P);
+    const int why = reject_one(&c, &om, M, P, 0, dg);
     keep[h] = why == 0;
     if (reason) reason[h] = why;
+    if (ambiguous) ambiguous[h] = reject_one(&c, &om, M, P, 1, NULL) != why || reject_one(&c, &om, M, P, 2, NULL) != why;
     sdf_mesh_free(&om); free(Vt); free(P);
   }
   for (int k = 0; k < 4; ++k) if (fm[k].nf > 0) sdf_mesh_free(&fm[k]);
   return rc;
+}
+
+int hop_oracle_reject_by_collision(const float *objV, int onv, const int32_t *objF, int onf, const float *fingerV, const int32_t *fnv,
+                                   const int32_t *fingerF, const int32_t *fnf, const float *finger_pts, const int32_t *finger_n,
+                                   const float *scene_xyz, int ns, const float *hand_xyz, int nh, const float *model_xyz, int nm,
+                                   const float *poses, int H, const hop_oracle_collision_params *p, int32_t *keep, int32_t *reason,
+                                   float *diag) {
+  return hop_oracle_reject_by_collision_amb(objV, onv, objF, onf, fingerV, fnv, fingerF, fnf, finger_pts, finger_n, scene_xyz, ns, hand_xyz, nh,
+                                            model_xyz, nm, poses, H, p, keep, reason, diag, NULL);
+}
+
+/* per-point ambiguity flags of hop_oracle_signed_distance (test support, see sdf_point_amb) */
+int hop_oracle_signed_distance_amb(const float *pts, int n, const float *V, int nv, const int32_t *F, int nf, float *S, int32_t *amb) {
+  sdf_mesh m;
+  if (sdf_mesh_build(&m, V, nv, F, nf)) return -1;
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) { int a = 0; S[i] = sdf_point_flag(&m, pts + 3 * i, &a); amb[i] = a; }
+  sdf_mesh_free(&m);
+  return 0;
 }

@@ -15,8 +15,8 @@ from oracle import cpu_oracle as O  # noqa: E402
 out = {}
 for name, seed in (("ellipse", 21), ("cuboid", 22), ("tless", 23)):
     case = synth.make_collision_case(name, H=128, seed=seed)
-    keep, reason, diag = O.reject_by_collision(case)
+    keep, reason, diag, amb = O.reject_by_collision(case, with_ambiguous=True)
     out[f"{name}_H"], out[f"{name}_seed"] = 128, seed
-    out[f"{name}_reason"], out[f"{name}_diag"] = reason, diag
-    print(name, np.bincount(reason, minlength=7))
+    out[f"{name}_reason"], out[f"{name}_diag"], out[f"{name}_ambiguous"] = reason, diag, amb
+    print(name, np.bincount(reason, minlength=7), 'decisions hanging on a coin toss of the sign rules:', int(amb.sum()))
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "collision_golden.npz"), **out)
