@@ -18,6 +18,98 @@ PoseEstimator::PoseEstimator(ConfigParser *cfg1, const Cloud &model, const Cloud
 
 PoseEstimator::~PoseEstimator() {
   hop_cloud_free(ctx, d_scene); hop_cloud_free(ctx, d_model); hop_cloud_free(ctx, d_model001);
+  for (auto &m : _meshes) hop_mesh_free(ctx, m.second);
+}
+
+// ---- physics pruning (PoseEstimator.cpp:506-735) ------------------------------------------------------------------------
+void PoseEstimator::registerMesh(const std::vector<float> &V, const std::vector<int32_t> &F, const std::string &name, const Mat4f &pose) {
+  std::vector<float> Vt(V.size());
+  for (size_t i = 0; i + 2 < V.size(); i += 3)   // SDFchecker::transformVertices: pose * [v; 1], float
+    for (int r = 0; r < 3; ++r) Vt[i + r] = pose(r, 0) * V[i] + pose(r, 1) * V[i + 1] + pose(r, 2) * V[i + 2] + pose(r, 3);
+  hop_mesh *m = nullptr;
+  check(hop_mesh_upload(ctx, Vt.data(), (int)(Vt.size() / 3), F.data(), (int)(F.size() / 3), &m), "hop_mesh_upload");
+  auto it = _meshes.find(name);
+  if (it != _meshes.end()) hop_mesh_free(ctx, it->second);
+  _meshes[name] = m;
+}
+
+bool PoseEstimator::registerMesh(const std::string &mesh_dir, const std::string &name, const Mat4f &pose) {
+  std::vector<float> V;
+  std::vector<int32_t> F;
+  std::string err;
+  if (!loadOBJMesh(mesh_dir, V, F, &err)) { printf("registerMesh(%s): %s\n", name.c_str(), err.c_str()); return false; }
+  registerMesh(V, F, name, pose);
+  return true;
+}
+
+void PoseEstimator::rejectByCollisionOrNonTouching(const HandState &hand, const Cloud &cloud_withouthand_raw) {
+  if (cfg->yml["pose_estimator_use_physics"].as<bool>(true) == false) { printf("Not using physics\n"); return; }
+  if (_pose_hypos.empty()) return;
+  auto obj = _meshes.find("object");
+  if (obj == _meshes.end()) { printf("rejectByCollisionOrNonTouching: no object mesh registered, skipped\n"); return; }
+  static const char *names[4] = {"finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2"};
+  hop_collision_params p;
+  const Mat4f cam2handbase = hand._handbase_in_cam.inverse();
+  std::memcpy(p.cam2handbase, cam2handbase.data(), 64);
+  {   // the constructor's _model_center_init, _smallest_dim, _ob_diameter (PoseEstimator.cpp:12-20): from model001
+    float mn[3], mx[3];
+    getMinMax3D(_model001, mn, mx);
+    double c[3] = {0, 0, 0};
+    for (size_t i = 0; i < _model001.size(); ++i) for (int k = 0; k < 3; ++k) c[k] += _model001.xyz[3 * i + k];
+    for (int k = 0; k < 3; ++k) p.model_center[k] = (float)(c[k] / std::max<size_t>(_model001.size(), 1));
+    const float ex = mx[0] - mn[0], ey = mx[1] - mn[1], ez = mx[2] - mn[2];
+    const float smallest = std::min(std::min(ex, ey), ez);
+    p.ob_diameter = std::sqrt(ex * ex + ey * ey + ez * ez);
+    p.collision_dist = std::min(-smallest * cfg->yml["collision_thres"].as<float>(0.4f), -0.007f);
+    p.inside_ob_dist = std::min(-smallest / 5, -0.01f);
+  }
+  p.non_touch_dist = cfg->yml["non_touch_dist"].as<float>(0.01f);
+  p.collision_finger_dist = -cfg->yml["collision_finger_dist"].as<float>(0.012f);
+  p.collision_finger_volume_ratio = cfg->yml["collision_finger_volume_ratio"].as<float>(0.25f);
+  const hop_mesh *fm[4];
+  hop_cloud *fc[4];
+  for (int k = 0; k < 4; ++k) {
+    auto st = hand._component_status.find(names[k]);
+    p.finger_status[k] = st != hand._component_status.end() && st->second;
+    auto m = _meshes.find(names[k]);
+    fm[k] = m == _meshes.end() ? nullptr : m->second;
+    fc[k] = nullptr;
+    auto c = hand.finger_clouds.find(names[k]);
+    if (p.finger_status[k] && c != hand.finger_clouds.end() && c->second.size() > 0)
+      check(hop_cloud_upload(ctx, c->second.xyz.data(), nullptr, nullptr, (int)c->second.size(), &fc[k]), "upload finger cloud");
+  }
+  // the scene without the hand: into the hand-base frame, then the 5 mm VoxelGrid (PoseEstimator.cpp:556-559)
+  hop_cloud *d_wo = nullptr, *d_hand = nullptr;
+  if (cloud_withouthand_raw.size() > 0) {
+    Cloud hb, ds;
+    if (cloud_withouthand_raw.has_normals()) transformPointCloudWithNormals(cloud_withouthand_raw, hb, cam2handbase);
+    else {
+      hb = cloud_withouthand_raw;
+      for (size_t i = 0; i < hb.size(); ++i) {
+        const float x = hb.xyz[3 * i], y = hb.xyz[3 * i + 1], z = hb.xyz[3 * i + 2];
+        for (int r = 0; r < 3; ++r) hb.xyz[3 * i + r] = cam2handbase(r, 0) * x + cam2handbase(r, 1) * y + cam2handbase(r, 2) * z + cam2handbase(r, 3);
+      }
+    }
+    downsamplePointCloud(hb, ds, 0.005f);
+    if (ds.size() > 0) check(hop_cloud_upload(ctx, ds.xyz.data(), nullptr, nullptr, (int)ds.size(), &d_wo), "upload scene without hand");
+  }
+  if (hand._hand_cloud.size() > 0)
+    check(hop_cloud_upload(ctx, hand._hand_cloud.xyz.data(), nullptr, nullptr, (int)hand._hand_cloud.size(), &d_hand), "upload hand cloud");
+  const size_t n = _pose_hypos.size();
+  std::vector<float> poses(16 * n);
+  std::vector<int32_t> keep(n), reason(n);
+  for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
+  printf("collision_dist=%f, non_touch_dist=%f\n", p.collision_dist, p.non_touch_dist);
+  check(hop_reject_by_collision(ctx, obj->second, fm, fc, d_wo, d_hand, d_model, poses.data(), (int)n, &p, keep.data(), reason.data(), nullptr),
+        "hop_reject_by_collision");
+  std::vector<PoseHypo> kept;
+  int why[7] = {0, 0, 0, 0, 0, 0, 0};
+  for (size_t i = 0; i < n; ++i) { why[reason[i]]++; if (keep[i]) kept.push_back(_pose_hypos[i]); }   // in order (the reference's survivors come out in OpenMP order)
+  printf("physics pruning: %d of %d hypotheses kept (scene-in-object %d, hand-in-object %d, finger collision %d, side not touching %d, object-in-finger %d/%d)\n",
+         why[0], (int)n, why[1], why[2], why[3], why[4], why[5], why[6]);
+  _pose_hypos.swap(kept);
+  for (int k = 0; k < 4; ++k) hop_cloud_free(ctx, fc[k]);
+  hop_cloud_free(ctx, d_wo); hop_cloud_free(ctx, d_hand);
 }
 
 void PoseEstimator::setCurScene(const Cloud &object_segment) {

@@ -2,14 +2,26 @@
 // methods on the hot path; every method body is a call into libhop's C ABI (include/hop_c_api.h).
 //   runSuper4pcs   PoseEstimator.cpp:62-100     clusterPoses   :106-233
 //   refineByICP    :235-275                     selectBest     :465-502
-// rejectByCollisionOrNonTouching / rejectByRender are outside the scope of this build: not declared.
+//   registerMesh / registerHandMesh  :506-521   rejectByCollisionOrNonTouching  :524-735  (physics pruning)
+// rejectByRender is outside the scope of this build: not declared.
 #pragma once
+#include <map>
+#include <string>
 #include <vector>
 
 #include "ConfigParser.h"
 #include "PoseHypo.h"
 #include "cloud.h"
 #include "hop_c_api.h"
+
+// What rejectByCollisionOrNonTouching reads from the reference's HandT42 (Hand.h:29-92), as plain data in the hand-base frame.
+// Link names: finger_1_1, finger_1_2, finger_2_1, finger_2_2.
+struct HandState {
+  std::map<std::string, bool> _component_status;   // hand->_component_status
+  std::map<std::string, Cloud> finger_clouds;      // hand->_clouds[name] transformed by getTFHandBase(name) (PoseEstimator.cpp:541-551)
+  Cloud _hand_cloud;                               // hand->_hand_cloud
+  Mat4f _handbase_in_cam;
+};
 
 class PoseEstimator {
  public:
@@ -21,6 +33,12 @@ class PoseEstimator {
   void clusterPoses(float angle_diff, float dist_diff, bool assign_id);
   void refineByICP();
   void selectBest(PoseHypo &best_hypo);
+  // SDFchecker::registerMesh through PoseEstimator::registerMesh / registerHandMesh: name = "object" or a finger link; the
+  // vertices are moved by `pose` once (a finger link: its getTFHandBase) and stay on the device
+  bool registerMesh(const std::string &mesh_dir, const std::string &name, const Mat4f &pose);
+  void registerMesh(const std::vector<float> &V, const std::vector<int32_t> &F, const std::string &name, const Mat4f &pose);
+  // cloud_withouthand_raw: the scene without the hand, camera frame (setCurScene's _cloud_withouthand_raw)
+  void rejectByCollisionOrNonTouching(const HandState &hand, const Cloud &cloud_withouthand_raw);
 
   std::vector<PoseHypo> _pose_hypos;
   Cloud _scene_high_confidence;
@@ -30,5 +48,6 @@ class PoseEstimator {
   hop_ctx *ctx;
   Cloud _model, _model001;
   hop_cloud *d_scene = nullptr, *d_model = nullptr, *d_model001 = nullptr;
+  std::map<std::string, hop_mesh *> _meshes;
   void check(int rc, const char *what);
 };

@@ -104,6 +104,36 @@ bool savePLYFile(const std::string &path, const Cloud &c) {
   return true;
 }
 
+bool loadOBJMesh(const std::string &path, std::vector<float> &V, std::vector<int32_t> &F, std::string *err) {
+  std::ifstream f(path);
+  if (!f) { if (err) *err = "cannot open " + path; return false; }
+  V.clear(); F.clear();
+  std::string line;
+  while (std::getline(f, line)) {
+    std::istringstream ss(line);
+    std::string tag;
+    if (!(ss >> tag)) continue;
+    if (tag == "v") {
+      float x, y, z;
+      if (!(ss >> x >> y >> z)) { if (err) *err = "bad vertex line in " + path; return false; }
+      V.push_back(x); V.push_back(y); V.push_back(z);
+    } else if (tag == "f") {
+      std::vector<int32_t> idx;
+      std::string tok;
+      while (ss >> tok) {
+        const long v = std::strtol(tok.c_str(), nullptr, 10);   // "a", "a/b", "a/b/c", "a//c": the vertex index comes first
+        if (v == 0) { if (err) *err = "bad face line in " + path; return false; }
+        idx.push_back(v > 0 ? (int32_t)(v - 1) : (int32_t)(V.size() / 3 + v));
+      }
+      for (size_t k = 2; k < idx.size(); ++k) { F.push_back(idx[0]); F.push_back(idx[k - 1]); F.push_back(idx[k]); }
+    }
+  }
+  const int32_t nv = (int32_t)(V.size() / 3);
+  for (int32_t i : F) if (i < 0 || i >= nv) { if (err) *err = "face index out of range in " + path; return false; }
+  if (V.empty() || F.empty()) { if (err) *err = "no mesh in " + path; return false; }
+  return true;
+}
+
 bool saveOBJVertices(const std::string &path, const Cloud &c) {
   std::ofstream f(path);
   if (!f) return false;

@@ -7,7 +7,9 @@
 //     that search, hop_hand_overlap, is exercised by the test-suite on synthetic links);
 //   * ppf_path: a table in libhop's portable format is loaded when present, otherwise it is built from the model on the fly
 //     (what the reference's computePPF app does offline);
-//   * rejectByCollisionOrNonTouching / rejectByRender (SDF + OpenGL) are outside this build's scope.
+//   * rejectByCollisionOrNonTouching runs (main_realdata_auto.cpp:199) when object_mesh_path is readable; without the hand model only
+//     its first test (a scene point deep inside the placed object) has inputs, the finger tests find no enabled link;
+//     rejectByRender (OpenGL) is outside this build's scope.
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -81,6 +83,10 @@ int main(int argc, char **argv) {
   const int repeat = argc >= 3 ? std::max(1, atoi(argv[2])) : 1;
   {   // (the estimator's device clouds must be gone before the context)
   PoseEstimator est(&cfg, model, model001, ctx);
+  const std::string mesh_path = cfg.yml["object_mesh_path"].as<std::string>(std::string());
+  const bool use_physics = cfg.yml["pose_estimator_use_physics"].as<bool>(true) && !mesh_path.empty() && file_exists(mesh_path) &&
+                           est.registerMesh(mesh_path, "object", Mat4f());   // main_realdata_auto.cpp:39
+  if (!use_physics) printf("physics pruning off (pose_estimator_use_physics / object_mesh_path)\n");
   const std::string out_dir = cfg.yml["out_dir"].as<std::string>();
   for (int pass = 0; pass < repeat; ++pass) {
     typedef std::chrono::steady_clock Clock;
@@ -115,6 +121,12 @@ int main(int argc, char **argv) {
     est.refineByICP();
     const Clock::time_point t4 = Clock::now();
     est.clusterPoses(5, 0.003, false);
+    if (use_physics) {   // main_realdata_auto.cpp:199; no hand model -> no enabled link, no hand cloud
+      HandState hand;
+      hand._handbase_in_cam = handbase_in_cam;
+      est.rejectByCollisionOrNonTouching(hand, object_segment);
+      if (est._pose_hypos.empty()) { printf("No pose found...\n"); savePoseTxt(out_dir + "/model2scene.txt", Mat4f()); exit(1); }
+    }
     PoseHypo best(-1);
     est.selectBest(best);
     const Clock::time_point t5 = Clock::now();

@@ -262,6 +262,9 @@ def test_main_realdata_auto_end_to_end(tmp_path):
     dense, dn = synth.make_model("ellipse", 400000, seed=7)
     model, mn = synth.make_model("ellipse", 60000, seed=8)
     _write_ply(out + "/ellipse.ply", model, mn, binary=True)
+    mV, mF = synth.make_mesh("ellipse", 3)                             # object_mesh_path: the physics pruning step registers it
+    with open(out + "/ellipse.obj", "w") as f:
+        f.write("".join("v %.9g %.9g %.9g\n" % tuple(v) for v in mV) + "".join("f %d//%d %d//%d %d//%d\n" % (a, a, b, b, c, c) for a, b, c in mF + 1))
     gt = np.eye(4)
     gt[:3, :3] = synth._rot_from_rotvec(np.array([0.4, -0.7, 0.3]))
     gt[:3, 3] = [0.0, 0.005, 0.35]                                     # = (-0.15, 0.005, -0.03) in the hand-base frame: inside the crop box
@@ -270,6 +273,7 @@ def test_main_realdata_auto_end_to_end(tmp_path):
     r = subprocess.run([MAIN, out + "/cfg.yaml"], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "best tf:" in r.stdout and "num of pose clusters" in r.stdout
+    assert "physics pruning:" in r.stdout                              # rejectByCollisionOrNonTouching ran (no hand model: first test only)
     est = np.loadtxt(out + "/model2scene.txt")
     assert est.shape == (4, 4) and os.path.exists(out + "/best.obj") and os.path.exists(out + "/scene_normals.ply")
     sub = model[::20].astype(np.float64)
