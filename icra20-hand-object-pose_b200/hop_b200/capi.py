@@ -61,6 +61,12 @@ class CollisionParams(C.Structure):
                 ("collision_finger_dist", C.c_float), ("collision_finger_volume_ratio", C.c_float), ("finger_status", C.c_int32 * 4)]
 
 
+class RenderParams(C.Structure):
+    """hop_render_params (include/hop_c_api.h)"""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("z_near", C.c_float), ("z_far", C.c_float), ("roi_weight", C.c_float), ("keep_ratio", C.c_float)]
+
+
 class PoseRec(C.Structure):
     _fields_ = [("pose", C.c_float * 16), ("score", C.c_float), ("id", C.c_int32), ("frame", C.c_int32), ("pad", C.c_int32)]
 
@@ -163,6 +169,12 @@ def load_library():
     L.hop_sdf_query.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
     L.hop_reject_by_collision.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
     L.hop_reject_by_collision_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
+    L.hop_default_render_params.argtypes = [C.POINTER(RenderParams)]
+    L.hop_default_render_params.restype = None
+    L.hop_render_scene_create.argtypes = [_vp, C.POINTER(RenderParams), _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
+    L.hop_render_scene_destroy.argtypes = [_vp, _vp]
+    L.hop_render_depth.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
+    L.hop_reject_by_render.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # raises AttributeError when an export is missing
         if fn.restype is C.c_int and name not in ("hop_cloud_size",):
@@ -324,6 +336,18 @@ class Mesh:
             self.handle = None
 
 
+class RenderScene:
+    """hop_render_scene*: the real depth image + the hand meshes of one frame, rasterised once"""
+
+    def __init__(self, ctx, handle, params):
+        self.ctx, self.handle, self.params = ctx, handle, params
+
+    def free(self):
+        if self.handle:
+            self.ctx.L.hop_render_scene_destroy(self.ctx.h, self.handle)
+            self.handle = None
+
+
 class Context:
     """hop_ctx*: one per process/GPU.  Raises HopError when no B200-class device is present (no CPU fallback)."""
 
@@ -361,7 +385,7 @@ class Context:
     def launch_count(self):
         return int(self.L.hop_launch_count(self.h))
 
-    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10, "frame": 11, "sdf": 12}
+    PROF_KINDS = {"icp_correspond": 0, "icp_solve": 1, "lcp_score": 2, "nn_build": 3, "topk": 4, "verify_lcp": 5, "hand_overlap": 6, "icp_fused": 7, "s4pcs_pairs": 8, "s4pcs_join": 9, "cluster": 10, "frame": 11, "sdf": 12, "render": 13}
 
     def profile_enable(self, on=True):
         self._check(self.L.hop_profile_enable(self.h, int(on)))
@@ -581,6 +605,42 @@ class Context:
         self._check(self.L.hop_reject_by_collision_dev(self.h, object_mesh.handle, fm, fc, scene_without_hand.handle if scene_without_hand else None,
                                                        hand_cloud.handle if hand_cloud else None, model.handle if model else None, d_poses, H,
                                                        C.byref(params), d_keep, d_reason, d_diag))
+
+    def render_params(self, **kw):
+        p = RenderParams()
+        self.L.hop_default_render_params(C.byref(p))
+        for k, v in kw.items():
+            setattr(p, k, v)
+        return p
+
+    def render_scene(self, params, depth_m, hand_V=None, hand_F=None):
+        """Renderer set-up of rejectByRender: depth_m (height,width) float metres, hand meshes in the camera frame"""
+        depth_m = np.ascontiguousarray(depth_m, np.float32)
+        assert depth_m.shape == (params.height, params.width)
+        hV = None if hand_V is None or len(hand_V) == 0 else _f32(hand_V, 3)
+        hF = None if hand_F is None or len(hand_F) == 0 else np.ascontiguousarray(hand_F, np.int32).reshape(-1, 3)
+        h = _vp()
+        self._check(self.L.hop_render_scene_create(self.h, C.byref(params), _ptr(depth_m), _ptr(hV), 0 if hV is None else len(hV), _ptr(hF),
+                                                   0 if hF is None else len(hF), C.byref(h)))
+        return RenderScene(self, h, params)
+
+    def render_depth(self, scene, obj_V, obj_F, pose):
+        """one simulated depth image (metres) + the object mask"""
+        V, F = _f32(obj_V, 3), np.ascontiguousarray(obj_F, np.int32).reshape(-1, 3)
+        flat = poses_to_colmajor(np.asarray(pose, np.float32).reshape(1, 4, 4))
+        depth = np.empty((scene.params.height, scene.params.width), np.float32)
+        mask = np.empty((scene.params.height, scene.params.width), np.uint8)
+        self._check(self.L.hop_render_depth(self.h, scene.handle, _ptr(V), len(V), _ptr(F), len(F), _ptr(flat), _ptr(depth), _ptr(mask)))
+        return depth, mask
+
+    def reject_by_render(self, scene, obj_V, obj_F, poses):
+        """PoseEstimator::rejectByRender: (wrong_ratio (H,), kept hypothesis indices in the reference's output order)"""
+        V, F = _f32(obj_V, 3), np.ascontiguousarray(obj_F, np.int32).reshape(-1, 3)
+        flat = poses_to_colmajor(poses)
+        H = len(flat)
+        wr, order, nk = np.zeros(H, np.float32), np.zeros(max(H, 1), np.int32), C.c_int32(0)
+        self._check(self.L.hop_reject_by_render(self.h, scene.handle, _ptr(V), len(V), _ptr(F), len(F), _ptr(flat), H, _ptr(wr), _ptr(order), C.byref(nk)))
+        return wr, order[: nk.value].copy()
 
     def select_topk(self, poses, scores, K, id_offset=0, frame=0):
         flat = poses_to_colmajor(poses)

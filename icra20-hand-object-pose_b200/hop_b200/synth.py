@@ -474,3 +474,42 @@ def make_collision_case(name="ellipse", H=256, seed=0, n_model=500, n_finger=300
     # (config_autodataset.yaml:128-131: collision_thres 0.4, non_touch_dist 0.01, collision_finger_dist 0.012, volume ratio 0.25)
     return dict(obj_V=V, obj_F=F, finger_V=fingers_V, finger_F=fingers_F, finger_pts=fingers_pts, hand_xyz=hand_xyz, scene_xyz=scene,
                 model_xyz=m_xyz, poses=poses.astype(np.float32), gt=gt_cam.astype(np.float32), params=params)
+
+
+def make_render_case(name="ellipse", H=64, seed=0, width=640, height=480, noise=0.001, dropout=0.03, mesh_level=2, render=None):
+    """A frame for PoseEstimator::rejectByRender: the grasp of make_collision_case seen by the camera.  `render(p_kw, hand_V, hand_F,
+    obj_V, obj_F, pose) -> depth` produces the "real" depth image from the true pose (the tests pass the oracle's renderer); noise,
+    a background plane at 0.8 m where nothing is hit, and dropouts (0 = invalid, like the sensor) are added on top.
+    Returns dict(obj_V, obj_F, hand_V, hand_F (camera frame, concatenated), poses (camera frame), gt, depth_m, cam = dict(fx, fy, cx, cy, width, height))."""
+    case = make_collision_case(name, H=H, seed=seed, mesh_level=mesh_level)
+    rng = np.random.default_rng(seed + 101)
+    # a camera that looks at the grasp (the collision case's camera only has to define a frame): 0.35 m away, slightly off-axis
+    old_cam2hb = case["params"]["cam2handbase"].astype(np.float64)
+    target = np.array([-0.17, 0.0, -0.02])
+    eye = target + np.array([0.03, 0.07, 0.34])
+    zc = (target - eye) / np.linalg.norm(target - eye)
+    xc = np.cross([0.0, 1.0, 0.0], zc); xc /= np.linalg.norm(xc)
+    yc = np.cross(zc, xc)
+    cam2hb = np.eye(4)
+    cam2hb[:3, :3] = np.stack([xc, yc, zc], 1)
+    cam2hb[:3, 3] = eye
+    hb2cam = np.linalg.inv(cam2hb)
+    regauge = hb2cam @ old_cam2hb                       # the hypotheses and the true pose, re-expressed in the new camera frame
+    case["poses"] = np.einsum("ij,hjk->hik", regauge, case["poses"].astype(np.float64)).astype(np.float32)
+    case["gt"] = (regauge @ case["gt"].astype(np.float64)).astype(np.float32)
+    hV, hF, off = [], [], 0
+    for v, f in zip(case["finger_V"], case["finger_F"]):
+        hV.append((v.astype(np.float64) @ hb2cam[:3, :3].T + hb2cam[:3, 3]).astype(np.float32))
+        hF.append(f + off)
+        off += len(v)
+    hand_V, hand_F = np.concatenate(hV), np.concatenate(hF).astype(np.int32)
+    s = width / 640.0
+    cam = dict(fx=616.596 * s, fy=616.596 * s, cx=307.628 * s, cy=239.687 * s, width=width, height=height)
+    out = dict(obj_V=case["obj_V"], obj_F=case["obj_F"], hand_V=hand_V, hand_F=hand_F, poses=case["poses"], gt=case["gt"], cam=cam)
+    if render is not None:
+        d = render(cam, hand_V, hand_F, case["obj_V"], case["obj_F"], case["gt"]).astype(np.float32)
+        hit = d < 1.999
+        d = np.where(hit, d + rng.normal(0, noise, d.shape), 0.8 + rng.normal(0, noise, d.shape)).astype(np.float32)
+        d[rng.random(d.shape) < dropout] = 0.0
+        out["depth_m"] = d
+    return out

@@ -102,7 +102,8 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 #define HOP_PROF_CLUSTER 10       /* hop_cluster_poses_gpu: all block launches of one call = one span */
 #define HOP_PROF_FRAME 11         /* hop_frame_to_scene: every launch of one frame's front end = one span */
 #define HOP_PROF_SDF 12           /* sdf_kernel / collision_kernel (physics pruning) */
-#define HOP_PROF_KINDS 13
+#define HOP_PROF_RENDER 13        /* hop_reject_by_render: bbox + raster + walk kernels of one call = one span */
+#define HOP_PROF_KINDS 14
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
 int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans);
@@ -337,6 +338,38 @@ int hop_reject_by_collision(hop_ctx *ctx, const hop_mesh *object, const hop_mesh
 int hop_reject_by_collision_dev(hop_ctx *ctx, const hop_mesh *object, const hop_mesh *const *finger_meshes, hop_cloud *const *finger_clouds,
                                 hop_cloud *scene_without_hand, hop_cloud *hand_cloud, hop_cloud *model, const float *d_poses, int H,
                                 const hop_collision_params *params, int32_t *d_keep, int32_t *d_reason, float *d_diag);
+
+/* ---- render-based rejection: PoseEstimator::rejectByRender ---------------------------------------------------------- */
+/* The OpenGL camera of the reference's depth_sim package (src/depth_sim/src/range_likelihood.cpp:391-475: projection from the
+ * intrinsics, CV axes; simulation_io.cpp:411-440: depth buffer -> rounded millimetres, image flipped) as a software rasteriser:
+ * image pixel (x, y) samples sx = x + 0.5, sy = y + 0.5 of sx = fx X/Z + cx, sy = fy Y/Z + (height - cy); nearest fragment wins;
+ * sim = round(1000 Z) mm / 1000 clamped to [0.1, 2.0]; background = z_far. */
+typedef struct hop_render_params {
+  float fx, fy, cx, cy;      /* cam_K */
+  int32_t width, height;     /* 640 x 480 (PoseEstimator.cpp:349) */
+  float z_near, z_far;       /* 0.1, 2.0 (simulation_io.cpp:425-426) */
+  float roi_weight;          /* render_roi_weight */
+  float keep_ratio;          /* render_keep_hypo */
+} hop_render_params;
+void hop_default_render_params(hop_render_params *p);
+/* Per frame: the real depth image (_depth_meters: height x width floats, metres) and every enabled hand mesh already in the
+ * camera frame (hand->_handbase_in_cam * getTFHandBase(name) applied, concatenated; Renderer::addObject, PoseEstimator.cpp:362-383;
+ * hand_nf may be 0).  Rasterises the hand once and prepares the per-pixel differences the hypotheses share. */
+typedef struct hop_render_scene hop_render_scene;
+int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *params, const float *depth_m, const float *hand_V, int hand_nv,
+                            const int32_t *hand_F, int hand_nf, hop_render_scene **out);
+int hop_render_scene_destroy(hop_ctx *ctx, hop_render_scene *scene);
+/* Renderer::doRender for one placement of the object mesh (obj_V nv x 3 in the model frame, obj_F nf x 3, pose = 16 floats
+ * column-major model -> camera): depth = height x width simulated depth in metres, mask (may be NULL) = 1 where the object is
+ * the nearest surface (the blue pixels of color_sims, PoseEstimator.cpp:425). */
+int hop_render_depth(hop_ctx *ctx, const hop_render_scene *scene, const float *obj_V, int obj_nv, const int32_t *obj_F, int obj_nf,
+                     const float *pose, float *depth, uint8_t *mask);
+/* PoseEstimator::rejectByRender (PoseEstimator.cpp:345-463) for H hypotheses: wrong_ratio[h] = roi_weight * roi_diff / roi_cnt +
+ * bg_diff / bg_cnt with the reference's row-major float sums; order (may be NULL, room for H) = the hypotheses to keep in the
+ * order the reference's priority queue pops them (ascending wrong ratio; ties and NaN -- an object that owns no pixel -- are
+ * unspecified there: lower index first, NaN last), *n_keep = min(max(int(keep_ratio * H), 10), H). */
+int hop_reject_by_render(hop_ctx *ctx, const hop_render_scene *scene, const float *obj_V, int obj_nv, const int32_t *obj_F, int obj_nf,
+                         const float *poses, int H, float *wrong_ratio, int32_t *order, int32_t *n_keep);
 
 /* ---- winners ------------------------------------------------------------------------------------------------- */
 /* top-K by score (ties -> lower id), written as K hop_pose_rec (unused slots: id = -1, score = -inf).

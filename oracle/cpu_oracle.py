@@ -378,3 +378,54 @@ def signed_distance_ambiguous(pts, V, F):
     L.hop_oracle_signed_distance_amb.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p, _i32p]
     assert L.hop_oracle_signed_distance_amb(pts, len(pts), V, len(V), F, len(F), S, A) == 0
     return S, A
+
+
+# ---- render-based rejection --------------------------------------------------------------------
+class RenderParams(C.Structure):
+    """same layout as hop_render_params (include/hop_c_api.h)"""
+    _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
+                ("z_near", C.c_float), ("z_far", C.c_float), ("roi_weight", C.c_float), ("keep_ratio", C.c_float)]
+
+
+def render_params(**kw):
+    p = RenderParams(616.596, 616.596, 307.628, 239.687, 640, 480, 0.1, 2.0, 2.0, 0.3)
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+_u8p = np.ctypeslib.ndpointer(dtype=np.uint8, flags="C_CONTIGUOUS")
+
+
+def _mesh_args(V, F):
+    if V is None or len(V) == 0 or F is None or len(F) == 0:
+        return np.zeros((1, 3), np.float32), 0, np.zeros((1, 3), np.int32), 0
+    V, F = _c(V), np.ascontiguousarray(F, np.int32)
+    return V, len(V), F, len(F)
+
+
+def render_depth(p, hand_V, hand_F, obj_V, obj_F, pose):
+    """restated Renderer::doRender: (depth (h,w) metres, mask (h,w) uint8 = object pixels)"""
+    L = lib()
+    hV, hnv, hF, hnf = _mesh_args(hand_V, hand_F)
+    oV, onv, oF, onf = _mesh_args(obj_V, obj_F)
+    depth, mask = np.empty((p.height, p.width), np.float32), np.empty((p.height, p.width), np.uint8)
+    L.hop_oracle_render_depth.argtypes = [C.POINTER(RenderParams), _f32p, C.c_int, _i32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p, _f32p, _u8p]
+    rc = L.hop_oracle_render_depth(C.byref(p), hV, hnv, hF, hnf, oV, onv, oF, onf, poses_to_colmajor(np.asarray(pose).reshape(1, 4, 4)), depth, mask)
+    assert rc == 0
+    return depth, mask
+
+
+def reject_by_render(p, depth_m, hand_V, hand_F, obj_V, obj_F, poses):
+    """restated PoseEstimator::rejectByRender: (wrong_ratio (H,), kept indices in the reference's output order)"""
+    L = lib()
+    hV, hnv, hF, hnf = _mesh_args(hand_V, hand_F)
+    oV, onv, oF, onf = _mesh_args(obj_V, obj_F)
+    flat = poses_to_colmajor(poses)
+    H = len(flat)
+    wr, order, nk = np.empty(H, np.float32), np.zeros(max(H, 1), np.int32), C.c_int32(0)
+    L.hop_oracle_reject_by_render.argtypes = [C.POINTER(RenderParams), _f32p, _f32p, C.c_int, _i32p, C.c_int, _f32p, C.c_int, _i32p, C.c_int, _f32p,
+                                              C.c_int, _f32p, _i32p, C.POINTER(C.c_int32)]
+    rc = L.hop_oracle_reject_by_render(C.byref(p), _c(depth_m), hV, hnv, hF, hnf, oV, onv, oF, onf, flat, H, wr, order, C.byref(nk))
+    assert rc == 0
+    return wr, order[: nk.value].copy()

@@ -98,9 +98,55 @@ def collision_stage(ctx, args, out, timed, peak):
           file=out, flush=True)
 
 
+def render_stage(ctx, args, out, timed):
+    """render-based rejection: PoseEstimator::rejectByRender for a batch of hypotheses (hop_reject_by_render)"""
+    from hop_b200 import synth
+    from oracle import cpu_oracle as O
+    H = 1024 if args.sizes == "C2" else 16384
+    cam = {}
+
+    def render(c, hV, hF, oV, oF, T):
+        cam.update(c)
+        return O.render_depth(O.render_params(**c), hV, hF, oV, oF, T)[0]
+    case = synth.make_render_case("ellipse", H=H, seed=12, mesh_level=3, render=render)
+    p = ctx.render_params(**cam)
+    res = {}
+    t0 = time.perf_counter()
+    scene = ctx.render_scene(p, case["depth_m"], case["hand_V"], case["hand_F"])
+    t_scene = time.perf_counter() - t0
+
+    def run():
+        res["r"] = ctx.reject_by_render(scene, case["obj_V"], case["obj_F"], case["poses"])
+
+    dt, prof = timed(run)
+    k_ms = prof["render"][0] / max(prof["render"][1], 1)
+    wr, order = res["r"]
+    cpu = None
+    if not args.no_cpu_baseline:
+        thr = max(1, len(os.sched_getaffinity(0)))
+        n_s = min(H, 256)
+        t0 = time.perf_counter()
+        owr, _ = O.reject_by_render(O.render_params(**cam), case["depth_m"], case["hand_V"], case["hand_F"], case["obj_V"], case["obj_F"], case["poses"][:n_s])
+        tc = time.perf_counter() - t0
+        cpu = {"value": n_s / tc, "unit": "hypotheses/s", "cores": thr, "kind": "port", "bit_identical": bool(np.array_equal(owr, wr[:n_s], equal_nan=True)),
+               "sample": f"first {n_s} of {H} hypotheses, {tc:.2f} s (software rasteriser + the reference's comparison loop, OpenMP over hypotheses; "
+                         "the reference renders serially through one OpenGL context)"}
+    npx = cam["width"] * cam["height"]
+    print(json.dumps({"stage": "rejectByRender (hop_reject_by_render: bbox + rasterise + the reference's row-major float sums, 4 launches)",
+                      "metric": "hypotheses rendered and compared/sec", "value": H / (k_ms * 1e-3), "unit": "hypotheses/s", "cpu_baseline": cpu,
+                      "e2e": {"value": H / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3, "h2d_bytes": 64 * H, "d2h_bytes": 12 * H},
+                      "config": {"sizes": args.sizes, "H": H, "image": [cam["width"], cam["height"]], "object_faces": len(case["obj_F"]),
+                                 "hand_faces": len(case["hand_F"]), "kept": int(len(order)), "scene_setup_ms": t_scene * 1e3},
+                      "kernel_ms": k_ms, "dtype": "f32 sums, f64 depth interpolation, int64 coverage",
+                      "roofline": {"bound": "hbm", "kernel": "walk_kernel", "unit": "GB/s", "achieved": H * 8.0 * npx / (k_ms * 1e-3) / 1e9, "peak": None,
+                                   "note": "algorithmic = the reference's loop reads 2 floats per pixel per hypothesis; the sums are sequential by definition "
+                                           "(latency-bound: one dependent FADD per pixel per hypothesis)"}}), file=out, flush=True)
+    scene.free()
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--stages", default="all", help="all | collision (only the physics pruning stage)")
+    ap.add_argument("--stages", default="all", help="all | collision | render | physics (collision + render)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--sizes", default="C2")
@@ -133,8 +179,11 @@ def main():
         ctx.profile_enable(False)
         return dt, prof
 
-    if args.stages == "collision":
-        collision_stage(ctx, args, out, timed, peak)
+    if args.stages in ("collision", "render", "physics"):
+        if args.stages != "render":
+            collision_stage(ctx, args, out, timed, peak)
+        if args.stages != "collision":
+            render_stage(ctx, args, out, timed)
         ctx.close()
         return
 
@@ -366,6 +415,7 @@ super4pcs_success_quadrilaterals: 10
                       "unit": "hypotheses/s", "cpu_baseline": cpu3, "e2e": {"value": n_cl / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3},
                       "config": {"n": n_cl, "clusters": int(len(res["cl"]))}, "kernel_ms": prof["cluster"][0] / max(prof["cluster"][1], 1)}), file=out, flush=True)
     collision_stage(ctx, args, out, timed, peak)
+    render_stage(ctx, args, out, timed)
     ctx.close()
 
 
