@@ -29,7 +29,7 @@ struct hop_render_scene {
   float *d_real = nullptr;       // the real depth image, metres
   float *d_zhand = nullptr;      // nearest hand surface per pixel (Z, metres; FLT_MAX = none)
   float *d_base_diff = nullptr;  // per-pixel difference of the hand-only render to the real image
-  float *d_prefix = nullptr;     // n_px + 1: running float sum of d_base_diff in row-major order (prefix[i] = sum of pixels < i)
+  float *d_prefix = nullptr;     // n_px + 1 slots; [y * width] = running float sum of d_base_diff over the pixels before row y, [n_px] = the total
 };
 
 namespace {
@@ -47,6 +47,12 @@ struct RasterArgs {
   unsigned int *zbuf;
   int H;
 };
+
+// 4-byte asynchronous global -> shared copy (LDGSTS): the producers put a whole row in flight at once, no register staging
+__device__ __forceinline__ void cp_async4(float *dst_smem, const void *src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 __device__ __forceinline__ long long snap(float s) { return (long long)floor(__dadd_rn(__dmul_rn((double)s, (double)SUBPX), 0.5)); }
 
@@ -130,16 +136,40 @@ __global__ void base_diff_kernel(const float *zhand, const float *real, int n, f
   if (i < n) base_diff[i] = diff_of(sim_of(zhand[i], z_far), real[i]);
 }
 
-// the reference's running sum is sequential by definition: one thread (once per frame; the loads do not depend on the sum)
-__global__ void prefix_kernel(const float *base_diff, int n, float *prefix) {
-  if (blockIdx.x != 0 || threadIdx.x != 0) return;
+// The reference's running sum is sequential by definition: thread 0 adds, row by row out of shared memory, while warps 1-3 fetch
+// the next row (once per frame).  Only the sums at the row starts (and the total) are ever used.
+constexpr int PREFIX_THREADS = 128;
+__global__ void __launch_bounds__(PREFIX_THREADS) prefix_kernel(const float *base_diff, int W, int Hh, float *prefix) {
+  extern __shared__ __align__(16) float prefix_smem[];   // 2 rows, padded to a multiple of 32 with zeros (x + 0 = x)
+  const int Wp = (W + 31) & ~31;
+  const int tid = threadIdx.x;
+  auto produce = [&](int y) {
+    if (y >= Hh) return;
+    float *dst = prefix_smem + (y & 1) * Wp;
+    for (int x = tid - 32; x < Wp; x += PREFIX_THREADS - 32) { if (x < W) cp_async4(dst + x, base_diff + (size_t)y * W + x); else dst[x] = 0.f; }
+    cp_async_wait_all();
+  };
+  if (tid >= 32) produce(0);
   float s = 0.f;
-  prefix[0] = 0.f;
-  for (int i = 0; i < n; ++i) { s = __fadd_rn(s, base_diff[i]); prefix[i + 1] = s; }
+  for (int y = 0; y < Hh; ++y) {
+    __syncthreads();
+    if (tid >= 32) { produce(y + 1); continue; }
+    if (tid != 0) continue;
+    prefix[(size_t)y * W] = s;
+    const float4 *r4 = reinterpret_cast<const float4 *>(prefix_smem + (y & 1) * Wp);
+    for (int x = 0; x < Wp; x += 32) {
+      float4 v[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = r4[(x >> 2) + k];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { s = __fadd_rn(s, v[k].x); s = __fadd_rn(s, v[k].y); s = __fadd_rn(s, v[k].z); s = __fadd_rn(s, v[k].w); }
+    }
+  }
+  if (tid == 0) prefix[(size_t)W * Hh] = s;
 }
 
 // bounding tile of the object under each hypothesis (pixels whose centre any projected vertex can reach, clamped to the image)
-struct BboxArgs { hop_render_params p; const float *V; int nv; const float *poses; int H; Tile *tiles; long long *area; };
+struct BboxArgs { hop_render_params p; const float *V; int nv; const float *poses; int H; Tile *tiles; };
 __global__ void __launch_bounds__(128) bbox_kernel(BboxArgs a) {
   __shared__ long long s_mn[2][4], s_mx[2][4];
   const int h = blockIdx.x;
@@ -170,46 +200,121 @@ __global__ void __launch_bounds__(128) bbox_kernel(BboxArgs a) {
       if (mxx - SUBPX / 2 >= 0 && mxy - SUBPX / 2 >= 0 && x0 <= x1 && y0 <= y1) { t.x0 = (int)x0; t.y0 = (int)y0; t.w = (int)(x1 - x0 + 1); t.h = (int)(y1 - y0 + 1); }
     }
     a.tiles[h] = t;
-    a.area[h] = (long long)t.w * t.h;
   }
 }
 
-__global__ void tile_offsets_kernel(Tile *tiles, const long long *off, int H) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h < H) tiles[h].off = off[h];
+// per tile pixel, in place: the float bits of Z become the pixel's contribution when the object owns it (its difference to the
+// real image, >= 0) or -1 when it does not (empty, or behind the hand) -- everything the walk needs besides the shared image
+struct ResolveArgs { hop_render_params p; const float *real, *zhand; const Tile *tiles; unsigned int *zbuf; int H; };
+__global__ void __launch_bounds__(256) resolve_kernel(ResolveArgs a) {
+  const int h = blockIdx.y;
+  const Tile t = a.tiles[h];
+  const long long n = (long long)t.w * t.h;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int x = t.x0 + (int)(i % t.w), y = t.y0 + (int)(i / t.w);
+    const float zo = __uint_as_float(a.zbuf[t.off + i]);
+    float v = -1.f;
+    if (zo < FLT_MAX && zo < a.zhand[(size_t)y * a.p.width + x]) v = diff_of(sim_of(zo, a.p.z_far), a.real[(size_t)y * a.p.width + x]);
+    a.zbuf[t.off + i] = __float_as_uint(v);
+  }
 }
 
-// one thread per hypothesis replays the reference's comparison loop (PoseEstimator.cpp:399-443) from the first row of its tile
+// The reference's comparison loop (PoseEstimator.cpp:399-443) for 32 hypotheses per CTA.  Lane l of warp 0 carries hypothesis l's
+// two running float sums add by add in row-major order (the background sum starts from the shared running sum at the first row the
+// hypothesis' tile touches); the 32 lanes walk the image in lock step from the first row any of them needs.  Warps 1-3 are
+// producers: while warp 0 adds row y out of shared memory they fetch row y + 1 (the shared difference row and every lane's tile
+// segment) into the other buffer, so the sequential adds never wait on global memory.
 struct WalkArgs {
   hop_render_params p;
-  const float *real, *zhand, *base_diff, *prefix;
-  const Tile *tiles; const unsigned int *zbuf;
-  int H;
+  const float *base_diff, *prefix;
+  const Tile *tiles; const unsigned int *zbuf;   // resolved tiles
+  const int *perm; int n;                        // the hypotheses of this launch (grouped by tile width, ordered by first row)
   float *wrong_ratio;
 };
-__global__ void __launch_bounds__(64) walk_kernel(WalkArgs a) {
-  const int h = blockIdx.x * blockDim.x + threadIdx.x;
-  if (h >= a.H) return;
-  const Tile t = a.tiles[h];
+constexpr int WALK_THREADS = 128;
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile_stride) {
+  extern __shared__ __align__(16) float walk_smem[];
+  __shared__ Tile s_t[32];
+  __shared__ int s_first;
   const int W = a.p.width, Hh = a.p.height, n = W * Hh;
-  float roi = 0.f, bg;
-  int roi_cnt = 0;
-  if (t.w <= 0 || t.h <= 0) bg = a.prefix[n];
-  else {
-    bg = a.prefix[t.y0 * W];
-    const unsigned int *zt = a.zbuf + t.off;
-    for (int y = t.y0; y < t.y0 + t.h; ++y) {
-      const int row = y * W;
-      for (int x = 0; x < t.x0; ++x) bg = __fadd_rn(bg, a.base_diff[row + x]);
-      for (int x = t.x0; x < t.x0 + t.w; ++x) {
-        const float zo = __uint_as_float(zt[(size_t)(y - t.y0) * t.w + (x - t.x0)]);
-        if (zo < a.zhand[row + x]) { roi = __fadd_rn(roi, diff_of(sim_of(zo, a.p.z_far), a.real[row + x])); ++roi_cnt; }
-        else bg = __fadd_rn(bg, a.base_diff[row + x]);
-      }
-      for (int x = t.x0 + t.w; x < W; ++x) bg = __fadd_rn(bg, a.base_diff[row + x]);
-    }
-    for (int i = (t.y0 + t.h) * W; i < n; ++i) bg = __fadd_rn(bg, a.base_diff[i]);
+  const int Wp = (W + 31) & ~31;                   // rows padded with zeros to a multiple of 32 (x + 0 = x)
+  float *s_base = walk_smem;                       // 2 x Wp
+  float *s_tile = walk_smem + 2 * Wp;              // 2 x 32 x tile_stride
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (warp == 0) {
+    const int slot = blockIdx.x * 32 + lane;
+    Tile t; t.x0 = t.y0 = 0; t.w = t.h = 0; t.off = 0;
+    if (slot < a.n) t = a.tiles[a.perm[slot]];
+    if (t.w <= 0 || t.h <= 0) { t.w = t.h = 0; t.y0 = Hh; }
+    s_t[lane] = t;
+    int first = t.y0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) first = min(first, __shfl_xor_sync(0xffffffffu, first, o));
+    if (lane == 0) s_first = first;
   }
+  __syncthreads();
+  const int first = s_first;
+  // producer: row y -> buffer (y & 1)
+  auto produce = [&](int y) {
+    if (y >= Hh) return;
+    float *db = s_base + (y & 1) * Wp, *dt = s_tile + (size_t)(y & 1) * 32 * tile_stride;
+    const float *src = a.base_diff + (size_t)y * W;
+    for (int x = tid - 32; x < Wp; x += WALK_THREADS - 32) { if (x < W) cp_async4(db + x, src + x); else db[x] = 0.f; }
+    for (int l = 0; l < 32; ++l) {
+      const Tile t = s_t[l];
+      if (y < t.y0 || y >= t.y0 + t.h) continue;
+      const unsigned int *zr = a.zbuf + t.off + (size_t)(y - t.y0) * t.w;
+      for (int x = tid - 32; x < t.w; x += WALK_THREADS - 32) cp_async4(dt + l * tile_stride + x, zr + x);
+    }
+    cp_async_wait_all();
+  };
+  if (warp != 0) produce(first);
+  const Tile t = s_t[lane];
+  float roi = 0.f, bg = 0.f;
+  int roi_cnt = 0;
+  for (int y = first; y < Hh; ++y) {
+    __syncthreads();                               // row y is in its buffer; the other buffer is free
+    if (warp != 0) { produce(y + 1); continue; }
+    const float *sb = s_base + (y & 1) * Wp;
+    const float *st = s_tile + (size_t)(y & 1) * 32 * tile_stride + lane * tile_stride;   // this lane's tile segment of row y
+    if (y == t.y0) bg = a.prefix[(size_t)y * W];
+    const bool started = y >= t.y0, in_rows = started && y < t.y0 + t.h;
+    // x + 0.f = x exactly for the non-negative sums carried here, so "not mine" adds a zero: two independent add chains per pixel,
+    // every shared-memory read of a group of 32 (8) pixels issued ahead of its adds
+    if (!__any_sync(0xffffffffu, in_rows)) {
+      if (started) {
+        const float4 *r4 = reinterpret_cast<const float4 *>(sb);
+        for (int x = 0; x < Wp; x += 32) {       // the row is padded to a multiple of 32 with zeros
+          float4 v[8];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) v[k] = r4[(x >> 2) + k];
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { bg = __fadd_rn(bg, v[k].x); bg = __fadd_rn(bg, v[k].y); bg = __fadd_rn(bg, v[k].z); bg = __fadd_rn(bg, v[k].w); }
+        }
+      }
+    } else {
+      const int xa = in_rows ? t.x0 : Wp, xb = in_rows ? t.x0 + t.w : Wp;
+      for (int x0 = 0; x0 < Wp; x0 += 8) {
+        const float4 b0 = *reinterpret_cast<const float4 *>(sb + x0), b1 = *reinterpret_cast<const float4 *>(sb + x0 + 4);
+        const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+        float v[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { const int x = x0 + k; v[k] = (x >= xa && x < xb) ? st[x - xa] : -1.f; }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const bool hit = !(v[k] < 0.f);   // (a NaN difference -- NaN in the real image -- still belongs to the object)
+          roi = __fadd_rn(roi, hit ? v[k] : 0.f);
+          roi_cnt += hit;
+          bg = __fadd_rn(bg, (started && !hit) ? b[k] : 0.f);
+        }
+      }
+    }
+  }
+  if (warp != 0) return;
+  const int slot = blockIdx.x * 32 + lane;
+  if (slot >= a.n) return;
+  const int h = a.perm[slot];
+  if (t.w == 0) bg = a.prefix[n];
   const int bg_cnt = n - roi_cnt;
   // float diff_total = roi_weight * roi_diff / roi_cnt + bg_diff / bg_cnt  (0 / 0 = NaN when the object owns no pixel)
   a.wrong_ratio[h] = __fadd_rn(__fdiv_rn(__fmul_rn(a.p.roi_weight, roi), (float)roi_cnt), __fdiv_rn(bg, (float)bg_cnt));
@@ -268,7 +373,7 @@ extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *pa
     ctx->launches += 1;
   }
   base_diff_kernel<<<(s->n_px + 255) / 256, 256, 0, st>>>(s->d_zhand, s->d_real, s->n_px, s->p.z_far, s->d_base_diff);
-  prefix_kernel<<<1, 32, 0, st>>>(s->d_base_diff, s->n_px, s->d_prefix);
+  prefix_kernel<<<1, PREFIX_THREADS, sizeof(float) * 2 * (size_t)((s->p.width + 31) & ~31), st>>>(s->d_base_diff, s->p.width, s->p.height, s->d_prefix);
   ctx->launches += 2;
   const cudaError_t e = cudaStreamSynchronize(st);
   cudaFree(d_V); cudaFree(d_F); d_V = nullptr; d_F = nullptr;
@@ -287,11 +392,13 @@ extern "C" int hop_render_scene_destroy(hop_ctx *ctx, hop_render_scene *s) {
 
 namespace {
 // uploads the object mesh into ctx scratch: returns device V, F
-int upload_object(hop_ctx *ctx, const float *V, int nv, const int32_t *F, int nf, float **d_V, int32_t **d_F) {
+int upload_object(hop_ctx *ctx, const float *V, int nv, const int32_t *F, int nf, float **d_V, int32_t **d_F, size_t extra = 0, size_t *used = nullptr) {
   if (!V || !F || nv < 3 || nf < 1) { ctx->err = "hop_render: bad object mesh"; return HOP_EINVAL; }
   for (int k = 0; k < 3 * nf; ++k) if (F[k] < 0 || F[k] >= nv) { ctx->err = "hop_render: face index out of range"; return HOP_EINVAL; }
   const size_t vb = (sizeof(float) * 3 * (size_t)nv + 255) / 256 * 256, fb = sizeof(int32_t) * 3 * (size_t)nf;
-  char *d = (char *)ctx->ensure_scratch(vb + fb);
+  const size_t fbp = (fb + 255) / 256 * 256;
+  char *d = (char *)ctx->ensure_scratch(vb + fbp + extra);
+  if (used) *used = vb + fbp;
   if (!d) { ctx->err = "hop_render: scratch allocation failed"; return HOP_ENOMEM; }
   *d_V = (float *)d; *d_F = (int32_t *)(d + vb);
   HOP_CUDA(ctx, cudaMemcpyAsync(*d_V, V, sizeof(float) * 3 * (size_t)nv, cudaMemcpyHostToDevice, ctx->stream));
@@ -333,37 +440,81 @@ extern "C" int hop_reject_by_render(hop_ctx *ctx, const hop_render_scene *scene,
   if (n_keep) *n_keep = 0;
   if (H == 0) return HOP_OK;
   float *d_V; int32_t *d_F;
-  int rc = upload_object(ctx, obj_V, obj_nv, obj_F, obj_nf, &d_V, &d_F);
+  size_t vb_obj = 0;
+  int rc = upload_object(ctx, obj_V, obj_nv, obj_F, obj_nf, &d_V, &d_F, sizeof(int) * (size_t)H, &vb_obj);
   if (rc != HOP_OK) return rc;
   cudaStream_t st = ctx->stream;
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
-  const size_t pb = up(sizeof(float) * 16 * (size_t)H), tb = up(sizeof(Tile) * (size_t)H), ab = up(sizeof(long long) * (size_t)H), wb = up(sizeof(float) * (size_t)H);
-  char *d = (char *)ctx->ensure_io(pb + tb + 2 * ab + wb);
+  const size_t pb = up(sizeof(float) * 16 * (size_t)H), tb = up(sizeof(Tile) * (size_t)H), wb = up(sizeof(float) * (size_t)H);
+  char *d = (char *)ctx->ensure_io(pb + tb + wb);
   if (!d) { ctx->err = "hop_reject_by_render: staging allocation failed"; return HOP_ENOMEM; }
-  float *d_poses = (float *)d; Tile *d_tiles = (Tile *)(d + pb); long long *d_area = (long long *)(d + pb + tb), *d_off = (long long *)(d + pb + tb + ab);
-  float *d_wr = (float *)(d + pb + tb + 2 * ab);
+  float *d_poses = (float *)d; Tile *d_tiles = (Tile *)(d + pb);
+  float *d_wr = (float *)(d + pb + tb);
   HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses, sizeof(float) * 16 * (size_t)H, cudaMemcpyHostToDevice, st));
   ProfScope ps(ctx, HOP_PROF_RENDER);
-  BboxArgs ba; ba.p = scene->p; ba.V = d_V; ba.nv = obj_nv; ba.poses = d_poses; ba.H = H; ba.tiles = d_tiles; ba.area = d_area;
+  BboxArgs ba; ba.p = scene->p; ba.V = d_V; ba.nv = obj_nv; ba.poses = d_poses; ba.H = H; ba.tiles = d_tiles;
   bbox_kernel<<<H, 128, 0, st>>>(ba);
   ctx->launches += 1;
-  // tile offsets: a host scan of H numbers (the arena is sized from their sum)
-  std::vector<long long> area(H), off(H);
-  HOP_CUDA(ctx, cudaMemcpyAsync(area.data(), d_area, sizeof(long long) * (size_t)H, cudaMemcpyDeviceToHost, st));
+  // tile offsets: a host scan over the H tiles (the arena is sized from the sum of their areas)
+  std::vector<Tile> tiles(H);
+  HOP_CUDA(ctx, cudaMemcpyAsync(tiles.data(), d_tiles, sizeof(Tile) * (size_t)H, cudaMemcpyDeviceToHost, st));
   HOP_CUDA(ctx, cudaStreamSynchronize(st));
-  long long total = 0;
-  for (int h = 0; h < H; ++h) { off[h] = total; total += area[h]; }
+  long long total = 0, max_area = 1;
+  int max_w = 1;
+  for (int h = 0; h < H; ++h) {
+    tiles[h].off = total;
+    const long long ar = (long long)tiles[h].w * tiles[h].h;
+    total += ar; max_area = std::max(max_area, ar); max_w = std::max(max_w, tiles[h].w);
+  }
   unsigned int *d_z = (unsigned int *)ctx->ensure_work(sizeof(unsigned int) * (size_t)std::max<long long>(total, 1));
   if (!d_z) { ctx->err = "hop_reject_by_render: tile arena allocation failed"; return HOP_ENOMEM; }
-  HOP_CUDA(ctx, cudaMemcpyAsync(d_off, off.data(), sizeof(long long) * (size_t)H, cudaMemcpyHostToDevice, st));
-  tile_offsets_kernel<<<(H + 127) / 128, 128, 0, st>>>(d_tiles, d_off, H);
+  HOP_CUDA(ctx, cudaMemcpyAsync(d_tiles, tiles.data(), sizeof(Tile) * (size_t)H, cudaMemcpyHostToDevice, st));
   fill_kernel<<<592, 256, 0, st>>>(d_z, total);
   RasterArgs ra; ra.p = scene->p; ra.V = d_V; ra.F = d_F; ra.nf = obj_nf; ra.poses = d_poses; ra.tiles = d_tiles; ra.zbuf = d_z; ra.H = H;
   const long long work = (long long)H * obj_nf;
   raster_kernel<<<(unsigned int)((work + 127) / 128), 128, 0, st>>>(ra);
-  WalkArgs wa; wa.p = scene->p; wa.real = scene->d_real; wa.zhand = scene->d_zhand; wa.base_diff = scene->d_base_diff; wa.prefix = scene->d_prefix;
-  wa.tiles = d_tiles; wa.zbuf = d_z; wa.H = H; wa.wrong_ratio = d_wr;
-  walk_kernel<<<(H + 63) / 64, 64, 0, st>>>(wa);
+  {
+    ResolveArgs rs; rs.p = scene->p; rs.real = scene->d_real; rs.zhand = scene->d_zhand; rs.tiles = d_tiles; rs.zbuf = d_z; rs.H = H;
+    const int bx = (int)std::max<long long>(1, std::min<long long>(64, (max_area + 2047) / 2048));
+    for (int h0 = 0; h0 < H; h0 += 65535) {
+      ResolveArgs r2 = rs; r2.tiles += h0; r2.H = std::min(65535, H - h0);
+      resolve_kernel<<<dim3(bx, r2.H), 256, 0, st>>>(r2);
+    }
+  }
+  {
+    // The shared-memory stride of a walk launch is its widest tile: one stray hypothesis that fills the image would cost every CTA
+    // its occupancy, so the hypotheses are split into narrow tiles (<= 191 pixels: 4 CTAs per SM) and the rest, each group ordered by
+    // first row so that the 32 lanes of a CTA start their walk together.
+    std::vector<int> perm(H);
+    std::iota(perm.begin(), perm.end(), 0);
+    const int narrow = 191;
+    std::stable_sort(perm.begin(), perm.end(), [&](int x, int y) {
+      const bool wx = tiles[x].w > narrow, wy = tiles[y].w > narrow;
+      if (wx != wy) return wy;
+      const int fx = tiles[x].w > 0 ? tiles[x].y0 : scene->p.height, fy = tiles[y].w > 0 ? tiles[y].y0 : scene->p.height;
+      return fx < fy;
+    });
+    int n_narrow = 0;
+    for (int h = 0; h < H; ++h) n_narrow += tiles[h].w <= narrow;
+    int *d_perm = (int *)ctx->ensure_scratch(vb_obj + sizeof(int) * (size_t)H) ;
+    if (!d_perm) { ctx->err = "hop_reject_by_render: scratch allocation failed"; return HOP_ENOMEM; }
+    d_perm = (int *)((char *)d_perm + vb_obj);
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_perm, perm.data(), sizeof(int) * (size_t)H, cudaMemcpyHostToDevice, st));
+    const int Wp = (scene->p.width + 31) & ~31;
+    for (int part = 0; part < 2; ++part) {
+      const int begin = part == 0 ? 0 : n_narrow, count = part == 0 ? n_narrow : H - n_narrow;
+      if (count <= 0) continue;
+      const int stride = (part == 0 ? std::min(max_w, narrow) : max_w) | 1;   // odd: the 32 lanes' segments start in different banks
+      WalkArgs wa; wa.p = scene->p; wa.base_diff = scene->d_base_diff; wa.prefix = scene->d_prefix;
+      wa.tiles = d_tiles; wa.zbuf = d_z; wa.perm = d_perm + begin; wa.n = count; wa.wrong_ratio = d_wr;
+      const size_t smem = sizeof(float) * (2 * (size_t)Wp + 2 * 32 * (size_t)stride);
+      if (smem > 200 * 1024) { ctx->err = "hop_reject_by_render: image too wide for the walk kernel's shared memory"; return HOP_EINVAL; }
+      static size_t attr = 0;
+      if (smem > attr) { HOP_CUDA(ctx, cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+      walk_kernel<<<(count + 31) / 32, WALK_THREADS, smem, st>>>(wa, stride);
+      ctx->launches += 1;
+    }
+  }
   ctx->launches += 4;
   HOP_CUDA(ctx, cudaGetLastError());
   HOP_CUDA(ctx, cudaMemcpyAsync(wrong_ratio, d_wr, sizeof(float) * (size_t)H, cudaMemcpyDeviceToHost, st));

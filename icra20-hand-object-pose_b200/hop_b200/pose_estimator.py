@@ -126,6 +126,9 @@ class PoseEstimator:
         if name in self._meshes:
             self._meshes[name].free()
         self._meshes[name] = self.ctx.upload_mesh(V, F)
+        if not hasattr(self, "_mesh_host"):
+            self._mesh_host = {}
+        self._mesh_host[name] = (np.asarray(V, np.float32), np.asarray(F, np.int32))
 
     FINGERS = ("finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2")
 
@@ -162,6 +165,38 @@ class PoseEstimator:
                 c.free()
         self._pose_hypos = [h for h, k in zip(self._pose_hypos, keep) if k]
         self._reject_reason = reason
+
+    def rejectByRender(self, projection_thres, hand, depth_meters, cam_K, cfg=None):
+        """PoseEstimator::rejectByRender(projection_thres, HandT42*) (PoseEstimator.cpp:345-463): renders the hand + the object under
+        every hypothesis, compares with the real depth image and keeps the max(render_keep_hypo * N, 10) hypotheses with the lowest
+        wrong ratio, in ascending order (projection_thres is unused by the reference too).  `hand`: dict with component_status
+        {name: bool}, meshes {name: (V in the link frame, F)}, tf_in_base {name: 4x4 getTFHandBase}, handbase_in_cam; the object
+        mesh is the one given to registerMesh(V, F, "object") (kept on the host for the renderer)."""
+        cfg = cfg or {}
+        print(f"before projection check, #hypo={len(self._pose_hypos)}")
+        if not self._pose_hypos:
+            return
+        K = np.asarray(cam_K, np.float32).reshape(3, 3)
+        h, w = np.asarray(depth_meters).shape
+        params = self.ctx.render_params(fx=float(K[0, 0]), fy=float(K[1, 1]), cx=float(K[0, 2]), cy=float(K[1, 2]), width=int(w), height=int(h),
+                                        roi_weight=float(cfg.get("render_roi_weight", 2.0)), keep_ratio=float(cfg.get("render_keep_hypo", 0.3)))
+        hV, hF, off = [], [], 0
+        for name, (V, F) in sorted(hand.get("meshes", {}).items()):          # std::map order
+            if not hand["component_status"].get(name, False):
+                continue
+            T = np.asarray(hand["handbase_in_cam"], np.float32) @ np.asarray(hand["tf_in_base"][name], np.float32)
+            hV.append((np.asarray(V, np.float32) @ T[:3, :3].T + T[:3, 3]).astype(np.float32))
+            hF.append(np.asarray(F, np.int32) + off)
+            off += len(V)
+        scene = self.ctx.render_scene(params, depth_meters, np.concatenate(hV) if hV else None, np.concatenate(hF) if hF else None)
+        oV, oF = self._mesh_host["object"]
+        poses = np.stack([hy._pose for hy in self._pose_hypos])
+        wr, order = self.ctx.reject_by_render(scene, oV, oF, poses)
+        scene.free()
+        for hy, r in zip(self._pose_hypos, wr):
+            hy._wrong_ratio = float(r)
+        self._pose_hypos = [self._pose_hypos[k] for k in order]
+        print(f"after projection check, #hypo={len(self._pose_hypos)}")
 
     def selectBest(self):
         """Scores every hypothesis with computeLCP(1 mm model, lcp.dist, lcp.normal_angle, true,true,true) and returns

@@ -31,6 +31,35 @@ void PoseEstimator::registerMesh(const std::vector<float> &V, const std::vector<
   auto it = _meshes.find(name);
   if (it != _meshes.end()) hop_mesh_free(ctx, it->second);
   _meshes[name] = m;
+  if (name == "object") { _obj_mesh_V = Vt; _obj_mesh_F = F; }
+}
+
+void PoseEstimator::rejectByRender(float /*projection_thres: unused by the reference too*/, const HandState &hand, const std::vector<float> &depth_meters,
+                                   int width, int height) {
+  printf("before projection check, #hypo=%d\n", (int)_pose_hypos.size());
+  if (_pose_hypos.empty()) return;
+  if (_obj_mesh_F.empty()) { printf("rejectByRender: no object mesh registered, skipped\n"); return; }
+  hop_render_params p;
+  hop_default_render_params(&p);
+  p.fx = cfg->cam_intrinsic(0, 0); p.fy = cfg->cam_intrinsic(1, 1); p.cx = cfg->cam_intrinsic(0, 2); p.cy = cfg->cam_intrinsic(1, 2);
+  p.width = width; p.height = height;
+  p.roi_weight = cfg->yml["render_roi_weight"].as<float>(2.0f);
+  p.keep_ratio = cfg->yml["render_keep_hypo"].as<float>(0.3f);
+  hop_render_scene *scene = nullptr;
+  check(hop_render_scene_create(ctx, &p, depth_meters.data(), hand.meshes_in_cam_V.data(), (int)(hand.meshes_in_cam_V.size() / 3),
+                                hand.meshes_in_cam_F.data(), (int)(hand.meshes_in_cam_F.size() / 3), &scene), "hop_render_scene_create");
+  const size_t n = _pose_hypos.size();
+  std::vector<float> poses(16 * n), wrong(n);
+  std::vector<int32_t> order(n);
+  int32_t n_keep = 0;
+  for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
+  check(hop_reject_by_render(ctx, scene, _obj_mesh_V.data(), (int)(_obj_mesh_V.size() / 3), _obj_mesh_F.data(), (int)(_obj_mesh_F.size() / 3), poses.data(),
+                             (int)n, wrong.data(), order.data(), &n_keep), "hop_reject_by_render");
+  hop_render_scene_destroy(ctx, scene);
+  std::vector<PoseHypo> kept;
+  for (int i = 0; i < n_keep; ++i) { PoseHypo h = _pose_hypos[order[i]]; h._wrong_ratio = wrong[order[i]]; kept.push_back(h); }
+  _pose_hypos.swap(kept);
+  printf("after projection check, #hypo=%d\n", (int)_pose_hypos.size());
 }
 
 bool PoseEstimator::registerMesh(const std::string &mesh_dir, const std::string &name, const Mat4f &pose) {

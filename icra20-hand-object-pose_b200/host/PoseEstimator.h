@@ -3,7 +3,7 @@
 //   runSuper4pcs   PoseEstimator.cpp:62-100     clusterPoses   :106-233
 //   refineByICP    :235-275                     selectBest     :465-502
 //   registerMesh / registerHandMesh  :506-521   rejectByCollisionOrNonTouching  :524-735  (physics pruning)
-// rejectByRender is outside the scope of this build: not declared.
+//   rejectByRender  :345-463  (render-based rejection, SURVEY.md 8f rank 4: a software rasteriser in place of the GL context)
 #pragma once
 #include <map>
 #include <string>
@@ -21,6 +21,10 @@ struct HandState {
   std::map<std::string, Cloud> finger_clouds;      // hand->_clouds[name] transformed by getTFHandBase(name) (PoseEstimator.cpp:541-551)
   Cloud _hand_cloud;                               // hand->_hand_cloud
   Mat4f _handbase_in_cam;
+  // hand->_meshes of the enabled links, already moved by _handbase_in_cam * getTFHandBase(name) and concatenated
+  // (what Renderer::addObject receives, PoseEstimator.cpp:362-383)
+  std::vector<float> meshes_in_cam_V;
+  std::vector<int32_t> meshes_in_cam_F;
 };
 
 class PoseEstimator {
@@ -39,6 +43,8 @@ class PoseEstimator {
   void registerMesh(const std::vector<float> &V, const std::vector<int32_t> &F, const std::string &name, const Mat4f &pose);
   // cloud_withouthand_raw: the scene without the hand, camera frame (setCurScene's _cloud_withouthand_raw)
   void rejectByCollisionOrNonTouching(const HandState &hand, const Cloud &cloud_withouthand_raw);
+  // depth_meters: the frame's depth image (_depth_meters, height x width, metres); the object mesh is the registered "object"
+  void rejectByRender(float projection_thres, const HandState &hand, const std::vector<float> &depth_meters, int width, int height);
 
   std::vector<PoseHypo> _pose_hypos;
   Cloud _scene_high_confidence;
@@ -49,5 +55,7 @@ class PoseEstimator {
   Cloud _model, _model001;
   hop_cloud *d_scene = nullptr, *d_model = nullptr, *d_model001 = nullptr;
   std::map<std::string, hop_mesh *> _meshes;
+  std::vector<float> _obj_mesh_V;      // _obj_mesh (model frame), kept for the renderer
+  std::vector<int32_t> _obj_mesh_F;
   void check(int rc, const char *what);
 };

@@ -9,7 +9,7 @@
 //     (what the reference's computePPF app does offline);
 //   * rejectByCollisionOrNonTouching runs (main_realdata_auto.cpp:199) when object_mesh_path is readable; without the hand model only
 //     its first test (a scene point deep inside the placed object) has inputs, the finger tests find no enabled link;
-//     rejectByRender (OpenGL) is outside this build's scope.
+//     rejectByRender (:200) runs right after it on the software rasteriser (object only when there is no hand model).
 #include <algorithm>
 #include <chrono>
 #include <cmath>
@@ -66,6 +66,11 @@ int main(int argc, char **argv) {
   {
     std::string err;
     if (!readPNG16(cfg.depth_path, depth_mm, w, h, &err)) { printf("readDepthImage: %s\n", err.c_str()); hop_destroy(ctx); return 1; }
+  }
+  std::vector<float> depth_meters((size_t)w * h);   // Utils::readDepthImage (Utils.cpp:36-55): metres, 0 outside 0.1 .. 2 m
+  for (size_t i = 0; i < depth_meters.size(); ++i) {
+    const float d = (float)((float)depth_mm[i] * 0.001);   // (float)depthShort * SR300_DEPTH_UNIT: the unit is a double literal (Utils.h:107)
+    depth_meters[i] = (d > 2.0 || d < 0.1) ? 0.f : d;
   }
   const Mat4f cam_in_handbase = handbase_in_cam.inverse();
   const Mat4f cam_in_handbase_inv = cam_in_handbase.inverse();
@@ -126,6 +131,7 @@ int main(int argc, char **argv) {
       hand._handbase_in_cam = handbase_in_cam;
       est.rejectByCollisionOrNonTouching(hand, object_segment);
       if (est._pose_hypos.empty()) { printf("No pose found...\n"); savePoseTxt(out_dir + "/model2scene.txt", Mat4f()); exit(1); }
+      est.rejectByRender(cfg.yml["pose_estimator_wrong_ratio"].as<float>(0.f), hand, depth_meters, w, h);   // main_realdata_auto.cpp:200
     }
     PoseHypo best(-1);
     est.selectBest(best);

@@ -95,3 +95,20 @@ def test_reject_by_render_full_size_properties(ctx):
     assert np.array_equal(wr[sample], owr, equal_nan=True)
     assert len(order) == 307 and (wr < wr[0]).sum() < 16 and 0 in order
     scene.free()
+
+
+def test_pose_estimator_reject_by_render_method(ctx):
+    """the host mirror: PoseEstimator.rejectByRender keeps max(0.3 N, 10) hypotheses in ascending wrong ratio"""
+    from hop_b200.pose_estimator import PoseEstimator
+    case = _case("cuboid", 48, 21)
+    pe = PoseEstimator(ctx, {})
+    pe.registerMesh(case["obj_V"], case["obj_F"], "object")
+    pe.setPoseHypos(case["poses"])
+    cam = case["cam"]
+    K = [[cam["fx"], 0, cam["cx"]], [0, cam["fy"], cam["cy"]], [0, 0, 1]]
+    hand = dict(component_status={"finger": True, "palm": False}, meshes={"finger": (case["hand_V"], case["hand_F"]), "palm": (case["hand_V"], case["hand_F"])},
+                tf_in_base={"finger": np.eye(4), "palm": np.eye(4)}, handbase_in_cam=np.eye(4))
+    pe.rejectByRender(0.3, hand, case["depth_m"], K, {"render_roi_weight": 2.0, "render_keep_hypo": 0.3})
+    owr, oorder = O.reject_by_render(_oparams(cam), case["depth_m"], case["hand_V"], case["hand_F"], case["obj_V"], case["obj_F"], case["poses"])
+    assert [h._id for h in pe._pose_hypos] == list(oorder) and len(oorder) == 14
+    assert np.array_equal(np.array([h._wrong_ratio for h in pe._pose_hypos], np.float32), owr[oorder])

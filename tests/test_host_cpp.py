@@ -274,6 +274,7 @@ def test_main_realdata_auto_end_to_end(tmp_path):
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert "best tf:" in r.stdout and "num of pose clusters" in r.stdout
     assert "physics pruning:" in r.stdout                              # rejectByCollisionOrNonTouching ran (no hand model: first test only)
+    assert "after projection check" in r.stdout                       # rejectByRender ran on the software rasteriser
     est = np.loadtxt(out + "/model2scene.txt")
     assert est.shape == (4, 4) and os.path.exists(out + "/best.obj") and os.path.exists(out + "/scene_normals.ply")
     sub = model[::20].astype(np.float64)
