@@ -51,6 +51,19 @@ int main(int argc, char **argv) {
       std::cout << w << " " << h << " " << sum << " " << mn << " " << mx << "\n";
       return 0;
     }
+    if (cmd == "obj") {   // loadOBJMesh: vertex / face counts, index range, signed volume (orientation) and the first face
+      std::vector<float> V; std::vector<int32_t> F; std::string err;
+      if (!loadOBJMesh(argv[2], V, F, &err)) { std::cout << err << "\n"; return 3; }
+      double vol = 0;
+      for (size_t f = 0; f + 2 < F.size(); f += 3) {
+        const float *a = &V[3 * F[f]], *b = &V[3 * F[f + 1]], *c = &V[3 * F[f + 2]];
+        vol += (double)a[0] * ((double)b[1] * c[2] - (double)b[2] * c[1]) - (double)a[1] * ((double)b[0] * c[2] - (double)b[2] * c[0]) +
+               (double)a[2] * ((double)b[0] * c[1] - (double)b[1] * c[0]);
+      }
+      std::cout.precision(9);
+      std::cout << V.size() / 3 << " " << F.size() / 3 << " " << vol / 6 << " " << F[0] << " " << F[1] << " " << F[2] << "\n";
+      return 0;
+    }
     if (cmd == "voxel" && argc >= 5) {
       Cloud c, o; std::string err;
       if (!loadPLYFile(argv[2], c, &err)) { std::cout << err << "\n"; return 3; }

@@ -205,6 +205,27 @@ def test_voxel_grid_and_ply_io(tmp_path, binary):
 
 
 @needs_tool
+def test_obj_mesh_reader(tmp_path):
+    """loadOBJMesh (igl::readOBJ stand-in of SDFchecker::registerMesh): plain, v/vt/vn and negative indices, quads fanned"""
+    V, F = synth.make_mesh("tless", 2)
+    vol = np.einsum("ij,ij->i", V[F[:, 0]].astype(float), np.cross(V[F[:, 1]].astype(float), V[F[:, 2]].astype(float))).sum() / 6
+    vs = "".join("v %.9g %.9g %.9g\n" % tuple(v) for v in V)
+    (tmp_path / "a.obj").write_text("# comment\n" + vs + "vn 0 0 1\n" + "".join("f %d %d %d\n" % tuple(f + 1) for f in F))
+    (tmp_path / "b.obj").write_text(vs + "".join("f %d/1/1 %d//1 %d\n" % (f[0] + 1, f[1] + 1, f[2] - len(V)) for f in F))
+    for name in ("a.obj", "b.obj"):
+        rc, out = _tool("obj", tmp_path / name)
+        assert rc == 0, out
+        nv, nf, v, f0, f1, f2 = out.split()
+        assert (int(nv), int(nf)) == (len(V), len(F)) and abs(float(v) - vol) < 1e-9 and [int(f0), int(f1), int(f2)] == list(F[0])
+    (tmp_path / "q.obj").write_text("v 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nf 1 2 3 4\n")
+    rc, out = _tool("obj", tmp_path / "q.obj")
+    assert rc == 0 and out.split()[:2] == ["4", "2"]
+    (tmp_path / "bad.obj").write_text("v 0 0 0\nv 1 0 0\nf 1 2 9\n")
+    assert _tool("obj", tmp_path / "bad.obj")[0] == 3
+    assert _tool("obj", tmp_path / "missing.obj")[0] == 3
+
+
+@needs_tool
 def test_depth_backprojection(tmp_path):
     import cv2
     rng = np.random.default_rng(1)
