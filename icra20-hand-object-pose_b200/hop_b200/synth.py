@@ -497,6 +497,7 @@ def make_render_case(name="ellipse", H=64, seed=0, width=640, height=480, noise=
     regauge = hb2cam @ old_cam2hb                       # the hypotheses and the true pose, re-expressed in the new camera frame
     case["poses"] = np.einsum("ij,hjk->hik", regauge, case["poses"].astype(np.float64)).astype(np.float32)
     case["gt"] = (regauge @ case["gt"].astype(np.float64)).astype(np.float32)
+    case["params"] = dict(case["params"], cam2handbase=cam2hb.astype(np.float32))
     hV, hF, off = [], [], 0
     for v, f in zip(case["finger_V"], case["finger_F"]):
         hV.append((v.astype(np.float64) @ hb2cam[:3, :3].T + hb2cam[:3, 3]).astype(np.float32))
@@ -505,7 +506,8 @@ def make_render_case(name="ellipse", H=64, seed=0, width=640, height=480, noise=
     hand_V, hand_F = np.concatenate(hV), np.concatenate(hF).astype(np.int32)
     s = width / 640.0
     cam = dict(fx=616.596 * s, fy=616.596 * s, cx=307.628 * s, cy=239.687 * s, width=width, height=height)
-    out = dict(obj_V=case["obj_V"], obj_F=case["obj_F"], hand_V=hand_V, hand_F=hand_F, poses=case["poses"], gt=case["gt"], cam=cam)
+    out = dict(obj_V=case["obj_V"], obj_F=case["obj_F"], hand_V=hand_V, hand_F=hand_F, poses=case["poses"], gt=case["gt"], cam=cam,
+               collision=case)            # the same grasp as a make_collision_case dict in the new camera's gauge
     if render is not None:
         d = render(cam, hand_V, hand_F, case["obj_V"], case["obj_F"], case["gt"]).astype(np.float32)
         hit = d < 1.999

@@ -101,13 +101,15 @@ def collision_stage(ctx, args, out, timed, peak):
 def render_stage(ctx, args, out, timed):
     """render-based rejection: PoseEstimator::rejectByRender for a batch of hypotheses (hop_reject_by_render)"""
     from hop_b200 import synth
-    from oracle import cpu_oracle as O
     H = 1024 if args.sizes == "C2" else 16384
     cam = {}
 
-    def render(c, hV, hF, oV, oF, T):
+    def render(c, hV, hF, oV, oF, T):   # the "real" depth image of the synthetic frame: the product's own renderer, true pose
         cam.update(c)
-        return O.render_depth(O.render_params(**c), hV, hF, oV, oF, T)[0]
+        sc0 = ctx.render_scene(ctx.render_params(**c), np.zeros((c["height"], c["width"]), np.float32), hV, hF)
+        d = ctx.render_depth(sc0, oV, oF, T)[0]
+        sc0.free()
+        return d
     case = synth.make_render_case("ellipse", H=H, seed=12, mesh_level=3, render=render)
     p = ctx.render_params(**cam)
     res = {}
@@ -122,7 +124,8 @@ def render_stage(ctx, args, out, timed):
     k_ms = prof["render"][0] / max(prof["render"][1], 1)
     wr, order = res["r"]
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline:   # the only use of the oracle here: the CPU baseline leg
+        from oracle import cpu_oracle as O
         thr = max(1, len(os.sched_getaffinity(0)))
         n_s = min(H, 256)
         t0 = time.perf_counter()
