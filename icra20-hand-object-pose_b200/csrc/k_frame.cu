@@ -453,6 +453,113 @@ extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int wi
   return HOP_OK;
 }
 
+// ---- HandT42::removeSurroundingPointsAndAssignProbability (Hand.cpp:781-888) ------------------------------------------------------
+namespace {
+constexpr int MAX_LINKS = 16;
+struct HandRemovalArgs {
+  const float4 *pw, *nv; int n;                 // the scene, camera frame
+  const float4 *link[MAX_LINKS]; int link_n[MAX_LINKS]; float link_thr[MAX_LINKS]; int n_links;
+  Xf cam_in_hb, hb_in_cam, hb_in_f12, hb_in_f22;
+  float min_z;
+  float4 *out_pw, *out_nv; unsigned char *flag;
+};
+
+__device__ __forceinline__ float xf_rot(const Xf &T, int r, float x, float y, float z) {   // (T0 x + T1 y) + T2 z
+  return __fadd_rn(__fadd_rn(__fmul_rn(T.m[4 * r], x), __fmul_rn(T.m[4 * r + 1], y)), __fmul_rn(T.m[4 * r + 2], z));
+}
+
+// one thread per scene point; every link cloud is scanned by all lanes at the same address (broadcast loads): the clouds are a
+// few thousand points, a brute-force exact nearest neighbour at ANY distance (the confidence needs it) is a few microseconds
+__global__ void __launch_bounds__(128) hand_removal_kernel(HandRemovalArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.n) return;
+  const float4 p = a.pw[i], q = a.nv[i];
+  const float x = xf_row(a.cam_in_hb, 0, p.x, p.y, p.z), y = xf_row(a.cam_in_hb, 1, p.x, p.y, p.z), z = xf_row(a.cam_in_hb, 2, p.x, p.y, p.z);
+  const float nx = xf_rot(a.cam_in_hb, 0, q.x, q.y, q.z), ny = xf_rot(a.cam_in_hb, 1, q.x, q.y, q.z), nz = xf_rot(a.cam_in_hb, 2, q.x, q.y, q.z);
+  bool near = false;
+  float min_dist = 1.0f;
+  for (int k = 0; k < a.n_links && !near; ++k) {
+    const int m = a.link_n[k];
+    if (m <= 0) continue;
+    const float4 *lp = a.link[k];
+    float bd = 3.4e38f; int bi = 0;
+    for (int j = 0; j < m; ++j) {
+      const float4 c = __ldg(lp + j);
+      const float dx = c.x - x, dy = c.y - y, dz = c.z - z;
+      const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+      if (d2 < bd) { bd = d2; bi = j; }
+    }
+    min_dist = fminf(min_dist, __fsqrt_rn(bd));
+    if (bd <= a.link_thr[k]) { near = true; break; }
+    const float4 c = __ldg(lp + bi);
+    const float px = x - c.x, py = y - c.y;
+    const float planar = __fadd_rn(__fmul_rn(px, px), __fmul_rn(py, py));
+    if (planar <= a.link_thr[k] && (double)fabsf(z - c.z) <= 0.005) { near = true; break; }
+  }
+  bool ok = !near;
+  if (ok) {
+    const float y1 = xf_row(a.hb_in_f12, 1, x, y, z), z1 = xf_row(a.hb_in_f12, 2, x, y, z);
+    const float y2 = xf_row(a.hb_in_f22, 1, x, y, z), z2 = xf_row(a.hb_in_f22, 2, x, y, z);
+    if ((y1 < 0.f && z1 >= a.min_z) || (y2 < 0.f && z2 >= a.min_z)) ok = false;
+  }
+  const float conf = 1.f - expf(__fmul_rn(-231.04906018664843f, min_dist));
+  a.out_pw[i] = make_float4(xf_row(a.hb_in_cam, 0, x, y, z), xf_row(a.hb_in_cam, 1, x, y, z), xf_row(a.hb_in_cam, 2, x, y, z), conf);
+  a.out_nv[i] = make_float4(xf_rot(a.hb_in_cam, 0, nx, ny, nz), xf_rot(a.hb_in_cam, 1, nx, ny, nz), xf_rot(a.hb_in_cam, 2, nx, ny, nz), 0.f);
+  a.flag[i] = ok ? 1 : 0;
+}
+
+Xf xf_of(const float *colmajor) {
+  Xf T;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) T.m[4 * r + c] = colmajor[4 * c + r];
+  return T;
+}
+}  // namespace
+
+extern "C" int hop_remove_hand_points(hop_ctx *ctx, const hop_cloud *scene, const hop_cloud *const *links, const int32_t *link_kind, int n_links,
+                                      const hop_hand_removal_params *params, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!scene || !params || !out || n_links < 0 || n_links > MAX_LINKS || (n_links > 0 && (!links || !link_kind))) {
+    ctx->err = "hop_remove_hand_points: bad arguments (at most 16 links)"; return HOP_EINVAL;
+  }
+  cudaStream_t st = ctx->stream;
+  const int n = scene->n;
+  int kept = 0, rc;
+  FBuf A(st), NA(st), B(st), NB(st), fl(st);
+  if (n > 0) {
+    FR_CUDA(A.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(NA.alloc(sizeof(float4) * (size_t)n));
+    FR_CUDA(B.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(NB.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(fl.alloc((size_t)n));
+    HandRemovalArgs a;
+    a.pw = scene->d_pw; a.nv = scene->d_nv; a.n = n; a.n_links = n_links;
+    for (int k = 0; k < n_links; ++k) {
+      a.link[k] = links[k] ? links[k]->d_pw : nullptr;
+      a.link_n[k] = links[k] ? links[k]->n : 0;
+      a.link_thr[k] = link_kind[k] == 1 ? (float)(0.005 * 0.005) : (link_kind[k] == 2 ? (float)(0.02 * 0.02) : params->dist_thres_sq);
+    }
+    a.cam_in_hb = xf_of(params->cam_in_handbase); a.hb_in_cam = xf_of(params->handbase_in_cam);
+    a.hb_in_f12 = xf_of(params->handbase_in_finger_1_2); a.hb_in_f22 = xf_of(params->handbase_in_finger_2_2);
+    a.min_z = params->min_z;
+    a.out_pw = A.as<float4>(); a.out_nv = NA.as<float4>(); a.flag = fl.as<unsigned char>();
+    {
+      ProfScope ps(ctx, HOP_PROF_FRAME);
+      hand_removal_kernel<<<(n + 127) / 128, 128, 0, st>>>(a);
+      ctx->launches += 1;
+    }
+    FR_CUDA(cudaGetLastError());
+    if ((rc = compact2(ctx, A.as<float4>(), NA.as<float4>(), fl.as<unsigned char>(), n, B.as<float4>(), NB.as<float4>(), &kept)) != HOP_OK) return rc;
+  }
+  hop_cloud *c = *out ? *out : new hop_cloud();
+  rc = hop_cloud_reserve(ctx, c, kept);
+  if (rc != HOP_OK) { if (!*out) hop_cloud_free(ctx, c); return rc; }
+  to_cloud_kernel<<<blocks(c->n_padded), 256, 0, st>>>(B.as<float4>(), NB.as<float4>(), kept, c->n_padded, c->d_pw, c->d_nv);
+  ctx->launches += 1;
+  float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  if (kept > 0 && (rc = cloud_bounds(ctx, B.as<float4>(), kept, mn, mx)) != HOP_OK) { if (!*out) hop_cloud_free(ctx, c); return rc; }
+  for (int k = 0; k < 3; ++k) { c->bbox_min[k] = mn[k]; c->bbox_max[k] = mx[k]; }
+  FR_CUDA(cudaGetLastError());
+  *out = c;
+  return HOP_OK;
+}
+
 extern "C" int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob) {
   if (!ctx || !cloud) return HOP_EINVAL;
   const int n = cloud->n;

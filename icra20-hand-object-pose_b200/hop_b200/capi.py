@@ -61,6 +61,12 @@ class CollisionParams(C.Structure):
                 ("collision_finger_dist", C.c_float), ("collision_finger_volume_ratio", C.c_float), ("finger_status", C.c_int32 * 4)]
 
 
+class HandRemovalParams(C.Structure):
+    """hop_hand_removal_params (include/hop_c_api.h)"""
+    _fields_ = [("cam_in_handbase", C.c_float * 16), ("handbase_in_cam", C.c_float * 16), ("handbase_in_finger_1_2", C.c_float * 16),
+                ("handbase_in_finger_2_2", C.c_float * 16), ("min_z", C.c_float), ("dist_thres_sq", C.c_float)]
+
+
 class RenderParams(C.Structure):
     """hop_render_params (include/hop_c_api.h)"""
     _fields_ = [("fx", C.c_float), ("fy", C.c_float), ("cx", C.c_float), ("cy", C.c_float), ("width", C.c_int32), ("height", C.c_int32),
@@ -169,6 +175,7 @@ def load_library():
     L.hop_sdf_query.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
     L.hop_reject_by_collision.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
     L.hop_reject_by_collision_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
+    L.hop_remove_hand_points.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(HandRemovalParams), C.POINTER(_vp)]
     L.hop_default_render_params.argtypes = [C.POINTER(RenderParams)]
     L.hop_default_render_params.restype = None
     L.hop_render_scene_create.argtypes = [_vp, C.POINTER(RenderParams), _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(_vp)]
@@ -605,6 +612,28 @@ class Context:
         self._check(self.L.hop_reject_by_collision_dev(self.h, object_mesh.handle, fm, fc, scene_without_hand.handle if scene_without_hand else None,
                                                        hand_cloud.handle if hand_cloud else None, model.handle if model else None, d_poses, H,
                                                        C.byref(params), d_keep, d_reason, d_diag))
+
+    def hand_removal_params(self, handbase_in_cam, finger_1_2_in_handbase, finger_2_2_in_handbase, min_z, near_hand_dist):
+        p = HandRemovalParams()
+        hic = np.asarray(handbase_in_cam, np.float32)
+        for name, M in (("cam_in_handbase", np.linalg.inv(hic)), ("handbase_in_cam", hic),
+                        ("handbase_in_finger_1_2", np.linalg.inv(np.asarray(finger_1_2_in_handbase, np.float32))),
+                        ("handbase_in_finger_2_2", np.linalg.inv(np.asarray(finger_2_2_in_handbase, np.float32)))):
+            getattr(p, name)[:] = np.asarray(M, np.float32).T.reshape(-1).tolist()
+        p.min_z = float(min_z)
+        p.dist_thres_sq = float(np.float32(near_hand_dist) * np.float32(near_hand_dist))
+        return p
+
+    def remove_hand_points(self, scene, links, link_kind, params):
+        """HandT42::removeSurroundingPointsAndAssignProbability: scene (Cloud, camera frame) -> new Cloud with confidences;
+        links: Clouds in the hand-base frame in std::map order of their names, link_kind: 0 / 1 (proximal fingers) / 2 (base, swivels)"""
+        arr = (_vp * max(len(links), 1))()
+        for k, c in enumerate(links):
+            arr[k] = c.handle if c is not None else None
+        kinds = np.ascontiguousarray(link_kind, np.int32)
+        h = _vp()
+        self._check(self.L.hop_remove_hand_points(self.h, scene.handle, arr, _ptr(kinds), len(links), C.byref(params), C.byref(h)))
+        return Cloud(self, h, int(self.L.hop_cloud_size(h)))
 
     def render_params(self, **kw):
         p = RenderParams()

@@ -515,3 +515,53 @@ def make_render_case(name="ellipse", H=64, seed=0, width=640, height=480, noise=
         d[rng.random(d.shape) < dropout] = 0.0
         out["depth_m"] = d
     return out
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# hand-point removal fixtures (HandT42::removeSurroundingPointsAndAssignProbability)
+# ------------------------------------------------------------------------------------------------------------------
+HAND_LINKS = ("base", "finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2", "swivel_1", "swivel_2")   # std::map order
+HAND_LINK_KIND = (2, 1, 0, 1, 0, 2, 2)
+
+
+def make_hand_removal_case(seed=0, n_scene=6000, n_link=400):
+    """A cropped scene in the camera frame (hand + grasped object + clutter, with normals) and the seven link clouds of a T42-like
+    hand in the hand-base frame.  Returns dict(scene_xyz, scene_nrm, links (list in HAND_LINKS order), kinds, handbase_in_cam,
+    finger_1_2_in_handbase, finger_2_2_in_handbase, min_z, near_hand_dist)."""
+    rng = np.random.default_rng(seed)
+    boxes = {"base": ((0.08, 0.10, 0.03), (-0.06, 0.0, 0.0)), "swivel_1": ((0.03, 0.03, 0.03), (-0.10, -0.04, 0.0)),
+             "swivel_2": ((0.03, 0.03, 0.03), (-0.10, 0.04, 0.0)), "finger_1_1": ((0.05, 0.012, 0.02), (-0.14, -0.045, 0.0)),
+             "finger_1_2": ((0.05, 0.012, 0.02), (-0.19, -0.04, 0.0)), "finger_2_1": ((0.05, 0.012, 0.02), (-0.14, 0.045, 0.0)),
+             "finger_2_2": ((0.05, 0.012, 0.02), (-0.19, 0.04, 0.0))}
+    links = []
+    for name in HAND_LINKS:
+        size, off = boxes[name]
+        p, _ = _cuboid(rng, n_link, *size)
+        links.append((p + off).astype(np.float32))
+    # distal link frames: origin at the link's centre, +y towards the other finger (so y < 0 is the outer side), z along the hand's x
+    def frame(off, inward):
+        T = np.eye(4)
+        T[:3, 0] = [0, 0, 1.0]
+        T[:3, 1] = [0, inward, 0]
+        T[:3, 2] = np.cross(T[:3, 0], T[:3, 1])
+        T[:3, 3] = off
+        return T
+    f12 = frame(boxes["finger_1_2"][1], 1.0)
+    f22 = frame(boxes["finger_2_2"][1], -1.0)
+    n_h, n_o = n_scene // 2, n_scene // 4
+    pick = rng.integers(0, len(HAND_LINKS), n_h)
+    hand_pts = np.stack([links[k][rng.integers(0, n_link)] for k in pick]) + rng.normal(0, 0.0015, (n_h, 3))
+    obj, _ = _ellipsoid(rng, n_o, 0.03, 0.025, 0.02)
+    obj = obj + [-0.19, 0.0, 0.0]
+    clutter = rng.uniform([-0.3, -0.12, -0.08], [0.0, 0.12, 0.08], (n_scene - n_h - n_o, 3))
+    hb = np.concatenate([hand_pts, obj, clutter])
+    hb = hb[rng.permutation(len(hb))]
+    nrm = rng.normal(size=hb.shape)
+    nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+    hic = np.eye(4)
+    hic[:3, :3] = random_rotation(rng)
+    hic[:3, 3] = [0.1, -0.05, 0.45]
+    scene = hb @ hic[:3, :3].T + hic[:3, 3]
+    return dict(scene_xyz=scene.astype(np.float32), scene_nrm=(nrm @ hic[:3, :3].T).astype(np.float32), links=links, kinds=np.array(HAND_LINK_KIND, np.int32),
+                handbase_in_cam=hic.astype(np.float32), finger_1_2_in_handbase=f12.astype(np.float32), finger_2_2_in_handbase=f22.astype(np.float32),
+                min_z=-0.02, near_hand_dist=0.003)

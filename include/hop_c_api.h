@@ -291,6 +291,24 @@ void hop_default_frame_params(hop_frame_params *p);
  * cropped points, object leaves, final points. */
 int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *params, hop_cloud **scene,
                        int32_t *stage_counts);
+/* HandT42::removeSurroundingPointsAndAssignProbability (Hand.cpp:781-888; main_realdata_auto.cpp:144-148): drops the scene points
+ * that belong to the hand and gives the others the confidence 1 - exp(-231.049 * min_dist), min_dist = the smallest exact
+ * nearest-neighbour distance to the link clouds visited (start value 1.0), then drops the points on the outer side of either
+ * distal link (y < 0 and z >= min_z in the link's frame).  scene: camera frame, with normals.  links: hand->_kdtrees' clouds in
+ * the hand-base frame, in std::map order of their names (the reference stops at the first link that claims a point);
+ * link_kind[k]: 0 = the dist_thres_sq below, 1 = finger_1_1 / finger_2_1 (5 mm), 2 = base / swivel_1 / swivel_2 (20 mm).
+ * *out: NULL to create the cloud (camera frame, confidence in the weight channel), or a cloud to refill; points keep their
+ * input order (the reference's order is that of its OpenMP critical section). */
+typedef struct hop_hand_removal_params {
+  float cam_in_handbase[16];          /* column-major: _handbase_in_cam.inverse() */
+  float handbase_in_cam[16];
+  float handbase_in_finger_1_2[16];   /* getTFHandBase("finger_1_2").inverse() */
+  float handbase_in_finger_2_2[16];
+  float min_z;                        /* _finger_properties["finger_1_2"]._min_z */
+  float dist_thres_sq;                /* near_hand_dist^2 (main_realdata_auto.cpp:147-148) */
+} hop_hand_removal_params;
+int hop_remove_hand_points(hop_ctx *ctx, const hop_cloud *scene, const hop_cloud *const *links, const int32_t *link_kind, int n_links,
+                           const hop_hand_removal_params *params, hop_cloud **out);
 /* copies a device cloud back (tests, debugging output such as scene_normals.ply); any pointer may be NULL */
 int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob);
 

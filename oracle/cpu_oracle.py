@@ -429,3 +429,26 @@ def reject_by_render(p, depth_m, hand_V, hand_F, obj_V, obj_F, poses):
     rc = L.hop_oracle_reject_by_render(C.byref(p), _c(depth_m), hV, hnv, hF, hnf, oV, onv, oF, onf, flat, H, wr, order, C.byref(nk))
     assert rc == 0
     return wr, order[: nk.value].copy()
+
+
+# ---- hand-point removal (Hand.cpp:781-888) ------------------------------------------------------------------------
+class HandRemovalParams(C.Structure):
+    """same layout as hop_hand_removal_params (include/hop_c_api.h)"""
+    _fields_ = [("cam_in_handbase", C.c_float * 16), ("handbase_in_cam", C.c_float * 16), ("handbase_in_finger_1_2", C.c_float * 16),
+                ("handbase_in_finger_2_2", C.c_float * 16), ("min_z", C.c_float), ("dist_thres_sq", C.c_float)]
+
+
+def remove_hand_points(xyz, nrm, links, link_kind, params):
+    """restated HandT42::removeSurroundingPointsAndAssignProbability; params: any structure with hop_hand_removal_params' layout"""
+    L = lib()
+    xyz, nrm = _c(xyz), _c(nrm)
+    n = len(xyz)
+    lk = _c(np.concatenate([np.asarray(l, np.float32).reshape(-1, 3) for l in links])) if len(links) and sum(len(l) for l in links) else np.zeros((1, 3), np.float32)
+    ln = np.array([len(l) for l in links], np.int32) if len(links) else np.zeros(1, np.int32)
+    kinds = np.ascontiguousarray(link_kind, np.int32) if len(links) else np.zeros(1, np.int32)
+    ox, on, oc = np.empty((max(n, 1), 3), np.float32), np.empty((max(n, 1), 3), np.float32), np.empty(max(n, 1), np.float32)
+    L.hop_oracle_remove_hand_points.argtypes = [_f32p, _f32p, C.c_int, _f32p, _i32p, _i32p, C.c_int, C.c_void_p, _f32p, _f32p, _f32p]
+    m = L.hop_oracle_remove_hand_points(xyz if n else np.zeros((1, 3), np.float32), nrm if n else np.zeros((1, 3), np.float32), n, lk, ln, kinds, len(links),
+                                        C.cast(C.byref(params), C.c_void_p), ox, on, oc)
+    assert m >= 0
+    return ox[:m].copy(), on[:m].copy(), oc[:m].copy()

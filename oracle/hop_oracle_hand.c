@@ -269,3 +269,81 @@ double hop_oracle_pso_1d(double lb, double ub, int n_pop, int n_gen, double c_co
   free(P); free(V); free(bp); free(bv);
   return gbest;
 }
+
+/* ---- HandT42::removeSurroundingPointsAndAssignProbability (src/perception/src/Hand.cpp:781-888) ----------------------------
+ * TEST INFRASTRUCTURE ONLY.  The scene (camera frame, with normals) goes into the hand-base frame; a point within `dist_thres`
+ * (squared; 5 mm for the proximal finger links, 20 mm for base / swivels) of its nearest neighbour in ANY link cloud, or
+ * within that planar (x, y) distance and 5 mm in z of that neighbour, is dropped; the others get the confidence
+ * 1 - exp(-lambda * min_dist), lambda = 231.049..., min_dist = the smallest nearest-neighbour distance over the links visited
+ * (starting at 1.0).  Then points on the outer side of either distal link (y < 0 and z >= min_z in the link's own frame) are
+ * dropped and the rest goes back to the camera frame.  Links are visited in std::map order of their names: the caller
+ * passes them sorted.  kind[k]: 0 = dist_thres, 1 = finger_1_1 / finger_2_1 (5 mm), 2 = base / swivel_1 / swivel_2 (20 mm).
+ * Output in input order (the reference's order is the OpenMP critical-section order).  Returns the number of points kept.
+ * PARITY UNPINNED against PCL (FLANN nearest neighbour: exact, ties -> lowest index here). */
+typedef struct hop_oracle_hand_removal_params { /* same layout as hop_hand_removal_params (include/hop_c_api.h) */
+  float cam_in_handbase[16];   /* column-major: _handbase_in_cam.inverse() */
+  float handbase_in_cam[16];
+  float handbase_in_finger_1_2[16], handbase_in_finger_2_2[16]; /* getTFHandBase(name).inverse() */
+  float min_z;                 /* _finger_properties["finger_1_2"]._min_z */
+  float dist_thres_sq;         /* near_hand_dist^2 */
+} hop_oracle_hand_removal_params;
+
+static inline float hr_row(const float *T, int r, float x, float y, float z) { return ((T[r] * x + T[r + 4] * y) + T[r + 8] * z) + T[r + 12]; }
+static inline float hr_rot(const float *T, int r, float x, float y, float z) { return (T[r] * x + T[r + 4] * y) + T[r + 8] * z; }
+
+int hop_oracle_remove_hand_points(const float *xyz, const float *nrm, int n, const float *link_xyz, const int32_t *link_n, const int32_t *link_kind,
+                                  int n_links, const hop_oracle_hand_removal_params *p, float *out_xyz, float *out_nrm, float *out_conf) {
+  const float lambda = 231.04906018664843f;
+  int *keep = (int *)malloc(sizeof(int) * (size_t)(n > 0 ? n : 1));
+  float *hb = (float *)malloc(sizeof(float) * 7 * (size_t)(n > 0 ? n : 1));
+  if (!keep || !hb) { free(keep); free(hb); return -1; }
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < n; ++i) {
+    const float x = hr_row(p->cam_in_handbase, 0, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    const float y = hr_row(p->cam_in_handbase, 1, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    const float z = hr_row(p->cam_in_handbase, 2, xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]);
+    float *h = hb + 7 * (size_t)i;
+    h[0] = x; h[1] = y; h[2] = z;
+    for (int r = 0; r < 3; ++r) h[3 + r] = hr_rot(p->cam_in_handbase, r, nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]);
+    int near = 0;
+    float min_dist = 1.0f;
+    const float *lp = link_xyz;
+    for (int k = 0; k < n_links && !near; lp += 3 * (size_t)link_n[k], ++k) {
+      const float thr = link_kind[k] == 1 ? (float)(0.005 * 0.005) : (link_kind[k] == 2 ? (float)(0.02 * 0.02) : p->dist_thres_sq);
+      if (link_n[k] <= 0) continue;                       /* nearestKSearch returns 0 on an empty cloud */
+      int bi = 0; float bd = FLT_MAX;
+      for (int j = 0; j < link_n[k]; ++j) {
+        const float dx = lp[3 * j] - x, dy = lp[3 * j + 1] - y, dz = lp[3 * j + 2] - z;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2 < bd) { bd = d2; bi = j; }
+      }
+      const float d = sqrtf(bd);
+      if (d < min_dist) min_dist = d;
+      if (bd <= thr) { near = 1; break; }
+      const float px = x - lp[3 * bi], py = y - lp[3 * bi + 1];
+      const float planar = px * px + py * py;
+      if (planar <= thr && (double)fabsf(z - lp[3 * bi + 2]) <= 0.005) { near = 1; break; }
+    }
+    h[6] = 1 - expf(-lambda * min_dist);
+    int ok = !near;
+    if (ok) { /* outer side of the distal links */
+      const float y1 = hr_row(p->handbase_in_finger_1_2, 1, x, y, z), z1 = hr_row(p->handbase_in_finger_1_2, 2, x, y, z);
+      const float y2 = hr_row(p->handbase_in_finger_2_2, 1, x, y, z), z2 = hr_row(p->handbase_in_finger_2_2, 2, x, y, z);
+      if ((y1 < 0 && z1 >= p->min_z) || (y2 < 0 && z2 >= p->min_z)) ok = 0;
+    }
+    keep[i] = ok;
+  }
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (!keep[i]) continue;
+    const float *h = hb + 7 * (size_t)i;
+    for (int r = 0; r < 3; ++r) {
+      out_xyz[3 * m + r] = hr_row(p->handbase_in_cam, r, h[0], h[1], h[2]);
+      out_nrm[3 * m + r] = hr_rot(p->handbase_in_cam, r, h[3], h[4], h[5]);
+    }
+    out_conf[m] = h[6];
+    ++m;
+  }
+  free(keep); free(hb);
+  return m;
+}

@@ -98,6 +98,36 @@ def collision_stage(ctx, args, out, timed, peak):
           file=out, flush=True)
 
 
+def hand_removal_stage(ctx, args, out, timed):
+    """hand-point removal with confidences (HandT42::removeSurroundingPointsAndAssignProbability) on the device"""
+    from hop_b200 import synth
+    n = 6000 if args.sizes == "C2" else 50000
+    case = synth.make_hand_removal_case(seed=5, n_scene=n, n_link=400 if args.sizes == "C2" else 2000)
+    p = ctx.hand_removal_params(case["handbase_in_cam"], case["finger_1_2_in_handbase"], case["finger_2_2_in_handbase"], case["min_z"], case["near_hand_dist"])
+    scene = ctx.upload_cloud(case["scene_xyz"], case["scene_nrm"])
+    lc = [ctx.upload_cloud(l) for l in case["links"]]
+    res = {}
+
+    def run():
+        o = ctx.remove_hand_points(scene, lc, case["kinds"], p)
+        res["n"] = o.n
+        o.free()
+
+    dt, prof = timed(run)
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import cpu_oracle as O
+        t0 = time.perf_counter()
+        ox, _, _ = O.remove_hand_points(case["scene_xyz"], case["scene_nrm"], case["links"], case["kinds"], p)
+        tc = time.perf_counter() - t0
+        cpu = {"value": n / tc, "unit": "scene points/s", "cores": max(1, len(os.sched_getaffinity(0))), "kind": "port", "ms_per_call": tc * 1e3,
+               "same_count": bool(len(ox) == res["n"]), "sample": "the whole cloud (brute-force exact nearest neighbour per link, OpenMP over points)"}
+    print(json.dumps({"stage": "hand-point removal + confidences (hop_remove_hand_points)", "metric": "scene points/sec", "value": n / dt, "unit": "scene points/s",
+                      "cpu_baseline": cpu, "e2e": {"value": n / dt, "unit": "scene points/s", "ms_per_call": dt * 1e3},
+                      "config": {"sizes": args.sizes, "n_scene": n, "links": len(lc), "points_per_link": len(case["links"][0]), "kept": res["n"]},
+                      "kernel_ms": None, "dtype": "f32"}), file=out, flush=True)
+
+
 def render_stage(ctx, args, out, timed):
     """render-based rejection: PoseEstimator::rejectByRender for a batch of hypotheses (hop_reject_by_render)"""
     from hop_b200 import synth
@@ -182,6 +212,10 @@ def main():
         ctx.profile_enable(False)
         return dt, prof
 
+    if args.stages == "hand_removal":
+        hand_removal_stage(ctx, args, out, timed)
+        ctx.close()
+        return
     if args.stages in ("collision", "render", "physics"):
         if args.stages != "render":
             collision_stage(ctx, args, out, timed, peak)
@@ -417,6 +451,7 @@ super4pcs_success_quadrilaterals: 10
     print(json.dumps({"stage": "clusterPoses(30 deg, 15 mm) on the device (hop_cluster_poses_gpu)", "metric": "hypotheses clustered/sec", "value": n_cl / dt,
                       "unit": "hypotheses/s", "cpu_baseline": cpu3, "e2e": {"value": n_cl / dt, "unit": "hypotheses/s", "ms_per_call": dt * 1e3},
                       "config": {"n": n_cl, "clusters": int(len(res["cl"]))}, "kernel_ms": prof["cluster"][0] / max(prof["cluster"][1], 1)}), file=out, flush=True)
+    hand_removal_stage(ctx, args, out, timed)
     collision_stage(ctx, args, out, timed, peak)
     render_stage(ctx, args, out, timed)
     ctx.close()
