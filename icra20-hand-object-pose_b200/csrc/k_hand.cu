@@ -344,3 +344,64 @@ extern "C" int hop_hand_overlap(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scen
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
 }
+
+// ---- HandT42::adjustHandHeight (Hand.cpp:999-1051; main_realdata_auto.cpp:141) ---------------------------------------------------
+// The 13 trial heights are 13 more "hand states": one thread per (height, hand point) finds the point's exact nearest scene
+// neighbour through the scene's grid, counts it when it lies within 5 mm and the (un-normalised, Eigen-ordered) normal dot
+// product reaches cos 45 deg; the host keeps the first height with the most matches.
+namespace {
+struct HeightArgs {
+  const float4 *h_pw, *h_nv; int nh;      // hand->_hand_cloud, hand-base frame
+  NNGridDev grid; const float4 *s_nv;     // the hand-region scene in the hand-base frame
+  const float *heights; int n_heights;
+  double cos_thr;                         // std::cos(45 / 180.0 * M_PI) from the host's libm, compared in double like the reference
+  int *counts;
+};
+__global__ void __launch_bounds__(128) hand_height_kernel(HeightArgs a) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x, t = blockIdx.y;
+  if (i >= a.nh) return;
+  const float4 p = a.h_pw[i];
+  const float z = __fadd_rn(p.z, a.heights[t]);   // pcl::transformPointCloudWithNormals with offset(2,3) = height: x, y and the normal are unchanged
+  float bd; float4 bp;
+  const int j = nn_query(a.grid, p.x, p.y, z, bd, bp);
+  if (j < 0 || bd > (float)(0.005 * 0.005)) return;
+  const float4 n = a.h_nv[i], m = a.s_nv[j];
+  const float dot = __fadd_rn(__fmul_rn(n.x, m.x), __fadd_rn(__fmul_rn(n.y, m.y), __fmul_rn(n.z, m.z)));   // Eigen: x0 y0 + (x1 y1 + x2 y2)
+  if ((double)dot >= a.cos_thr) atomicAdd(a.counts + t, 1);
+}
+}  // namespace
+
+extern "C" int hop_adjust_hand_height(hop_ctx *ctx, hop_cloud *hand_cloud, hop_cloud *scene_handbase, const float *heights, int n_heights,
+                                      int32_t *match_counts, int32_t *best_index) {
+  if (!ctx) return HOP_EINVAL;
+  if (!hand_cloud || !scene_handbase || !heights || n_heights < 1 || n_heights > 4096 || !best_index) { ctx->err = "hop_adjust_hand_height: bad arguments"; return HOP_EINVAL; }
+  std::vector<int32_t> counts(n_heights, 0);
+  if (hand_cloud->n > 0 && scene_handbase->n > 0) {
+    NNGridHost *G = nullptr;
+    int rc = hop_get_nn_grid(ctx, scene_handbase, 0.005f * 1.0001f, 0.f, &G);
+    if (rc != HOP_OK) return rc;
+    auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+    char *d = (char *)ctx->ensure_io(2 * up(sizeof(float) * (size_t)n_heights));
+    if (!d) { ctx->err = "hop_adjust_hand_height: staging allocation failed"; return HOP_ENOMEM; }
+    float *d_h = (float *)d; int *d_c = (int *)(d + up(sizeof(float) * (size_t)n_heights));
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_h, heights, sizeof(float) * (size_t)n_heights, cudaMemcpyHostToDevice, ctx->stream));
+    HOP_CUDA(ctx, cudaMemsetAsync(d_c, 0, sizeof(int) * (size_t)n_heights, ctx->stream));
+    HeightArgs a;
+    a.h_pw = hand_cloud->d_pw; a.h_nv = hand_cloud->d_nv; a.nh = hand_cloud->n; a.grid = G->dev; a.s_nv = scene_handbase->d_nv;
+    a.heights = d_h; a.n_heights = n_heights; a.counts = d_c; a.cos_thr = std::cos(45 / 180.0 * M_PI);
+    {
+      ProfScope ps(ctx, HOP_PROF_HAND);
+      hand_height_kernel<<<dim3((a.nh + 127) / 128, n_heights), 128, 0, ctx->stream>>>(a);
+      ctx->launches += 1;
+    }
+    HOP_CUDA(ctx, cudaGetLastError());
+    HOP_CUDA(ctx, cudaMemcpyAsync(counts.data(), d_c, sizeof(int32_t) * (size_t)n_heights, cudaMemcpyDeviceToHost, ctx->stream));
+    HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  }
+  // Hand.cpp:1040-1045: the first height whose count exceeds every earlier one; none above zero -> best_height stays 0 (index -1 here)
+  int best = -1, max_match = 0;
+  for (int t = 0; t < n_heights; ++t) if (counts[t] > max_match) { max_match = counts[t]; best = t; }
+  *best_index = best;
+  if (match_counts) for (int t = 0; t < n_heights; ++t) match_counts[t] = counts[t];
+  return HOP_OK;
+}

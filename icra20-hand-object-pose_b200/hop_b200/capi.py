@@ -175,6 +175,7 @@ def load_library():
     L.hop_sdf_query.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
     L.hop_reject_by_collision.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
     L.hop_reject_by_collision_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
+    L.hop_adjust_hand_height.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]
     L.hop_remove_hand_points.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(HandRemovalParams), C.POINTER(_vp)]
     L.hop_default_render_params.argtypes = [C.POINTER(RenderParams)]
     L.hop_default_render_params.restype = None
@@ -612,6 +613,15 @@ class Context:
         self._check(self.L.hop_reject_by_collision_dev(self.h, object_mesh.handle, fm, fc, scene_without_hand.handle if scene_without_hand else None,
                                                        hand_cloud.handle if hand_cloud else None, model.handle if model else None, d_poses, H,
                                                        C.byref(params), d_keep, d_reason, d_diag))
+
+    TRIAL_HEIGHTS = (-0.03, -0.025, -0.02, -0.015, -0.01, -0.005, 0, 0.005, 0.01, 0.015, 0.02, 0.025, 0.03)   # Hand.cpp:1011
+
+    def adjust_hand_height(self, hand_cloud, scene_handbase, heights=None):
+        """HandT42::adjustHandHeight: (match counts per trial height, index of the chosen height or -1)"""
+        hs = np.ascontiguousarray(self.TRIAL_HEIGHTS if heights is None else heights, np.float32)
+        counts, best = np.zeros(len(hs), np.int32), C.c_int32(-1)
+        self._check(self.L.hop_adjust_hand_height(self.h, hand_cloud.handle, scene_handbase.handle, _ptr(hs), len(hs), _ptr(counts), C.byref(best)))
+        return counts, int(best.value)
 
     def hand_removal_params(self, handbase_in_cam, finger_1_2_in_handbase, finger_2_2_in_handbase, min_z, near_hand_dist):
         p = HandRemovalParams()

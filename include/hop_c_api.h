@@ -268,6 +268,15 @@ int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand,
                          const hop_finger_params *params, const double *d_thetas, const float *d_half_cs, int S, double *d_cost,
                          int32_t *d_best);
 
+/* HandT42::adjustHandHeight (Hand.cpp:999-1051; main_realdata_auto.cpp:141): for each trial height h (the reference's 13 offsets
+ * -0.03 .. 0.03 m of the hand base along its z), the number of points of hand->_hand_cloud (hand-base frame, shifted by h in z)
+ * whose nearest point of the hand-region scene (given in the hand-base frame: _scene_hand_region moved by
+ * _handbase_in_cam.inverse()) lies within 5 mm with a normal dot product >= cos 45 deg.  *best_index = the first height with the
+ * highest non-zero count, or -1 when nothing matches (the reference then leaves _handbase_in_cam unchanged); the caller applies
+ * _handbase_in_cam = _handbase_in_cam * offset(heights[best]).  match_counts (may be NULL): n_heights ints. */
+int hop_adjust_hand_height(hop_ctx *ctx, hop_cloud *hand_cloud, hop_cloud *scene_handbase, const float *heights, int n_heights,
+                           int32_t *match_counts, int32_t *best_index);
+
 /* ---- per-frame front end: depth image -> object-segment cloud (device) --------------------------------------------- */
 /* The pre-processing main_realdata_auto.cpp:54-96,144-181 does with OpenCV / PCL between reading the depth PNG and
  * PoseEstimator::setCurScene, in the same order: back-projection (Utils.cpp:78-115) of the pixels with 0.1 m < z < 2 m,

@@ -452,3 +452,13 @@ def remove_hand_points(xyz, nrm, links, link_kind, params):
                                         C.cast(C.byref(params), C.c_void_p), ox, on, oc)
     assert m >= 0
     return ox[:m].copy(), on[:m].copy(), oc[:m].copy()
+
+
+def adjust_hand_height(hand_xyz, hand_nrm, scene_xyz, scene_nrm, heights):
+    """restated HandT42::adjustHandHeight: (counts per height, chosen index or -1); scene in the hand-base frame"""
+    L = lib()
+    hs = np.ascontiguousarray(heights, np.float32)
+    counts = np.zeros(len(hs), np.int32)
+    L.hop_oracle_adjust_hand_height.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, _i32p]
+    best = L.hop_oracle_adjust_hand_height(_c(hand_xyz), _c(hand_nrm), len(hand_xyz), _c(scene_xyz), _c(scene_nrm), len(scene_xyz), hs, len(hs), counts)
+    return counts, int(best)

@@ -347,3 +347,31 @@ int hop_oracle_remove_hand_points(const float *xyz, const float *nrm, int n, con
   free(keep); free(hb);
   return m;
 }
+
+/* ---- HandT42::adjustHandHeight (Hand.cpp:999-1051) -- TEST INFRASTRUCTURE ONLY ------------------------------------------------
+ * counts[t] = #{hand points p : NN of (p.x, p.y, p.z + heights[t]) in the scene (hand-base frame) has d^2 <= 0.005^2 and
+ * n_p . n_nn >= cos(45 deg)}; returns the first index with the highest non-zero count, or -1.  Exact NN, ties -> lowest index. */
+int hop_oracle_adjust_hand_height(const float *hand_xyz, const float *hand_nrm, int nh, const float *scene_xyz, const float *scene_nrm, int ns,
+                                  const float *heights, int n_heights, int32_t *counts) {
+  int best = -1, max_match = 0;
+  for (int t = 0; t < n_heights; ++t) {
+    int c = 0;
+#pragma omp parallel for reduction(+ : c) schedule(static)
+    for (int i = 0; i < nh; ++i) {
+      const float x = hand_xyz[3 * i], y = hand_xyz[3 * i + 1], z = hand_xyz[3 * i + 2] + heights[t];
+      int bi = -1; float bd = FLT_MAX;
+      for (int j = 0; j < ns; ++j) {
+        const float dx = scene_xyz[3 * j] - x, dy = scene_xyz[3 * j + 1] - y, dz = scene_xyz[3 * j + 2] - z;
+        const float d2 = (dx * dx + dy * dy) + dz * dz;
+        if (d2 < bd) { bd = d2; bi = j; }
+      }
+      if (bi < 0 || bd > (float)(0.005 * 0.005)) continue;
+      const float *n = hand_nrm + 3 * i, *m = scene_nrm + 3 * bi;
+      const float dot = n[0] * m[0] + (n[1] * m[1] + n[2] * m[2]);   /* Eigen's 3-vector dot: x0 y0 + (x1 y1 + x2 y2) */
+      if ((double)dot >= cos(45 / 180.0 * M_PI)) ++c;
+    }
+    counts[t] = c;
+    if (c > max_match) { max_match = c; best = t; }
+  }
+  return best;
+}

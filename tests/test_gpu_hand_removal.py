@@ -53,3 +53,39 @@ def test_remove_hand_points_edge_cases(ctx):
     allhand = dict(case, scene_xyz=pts.astype(np.float32), scene_nrm=np.tile([0, 0, 1.0], (len(pts), 1)).astype(np.float32))
     (x, nr, c), (ox, _, _) = _run(ctx, allhand)
     assert len(x) == len(ox) == 0
+
+
+def _height_case(seed, true_height):
+    """the hand cloud (links of the removal fixture, outward normals) and a hand-region scene that shows the hand `true_height`
+    higher along the hand base's z than the kinematics say"""
+    rng = np.random.default_rng(seed)
+    pts, nrm = [], []
+    for size, off in (((0.08, 0.10, 0.03), (-0.06, 0.0, 0.0)), ((0.05, 0.012, 0.02), (-0.14, -0.045, 0.0)), ((0.05, 0.012, 0.02), (-0.14, 0.045, 0.0))):
+        p, n = synth._cuboid(rng, 500, *size)
+        pts.append(p + off); nrm.append(n)
+    hand_xyz, hand_nrm = np.concatenate(pts).astype(np.float32), np.concatenate(nrm).astype(np.float32)
+    seen = rng.choice(len(hand_xyz), 900, replace=False)
+    scene = hand_xyz[seen] + [0, 0, true_height] + rng.normal(0, 0.0005, (900, 3))
+    snrm = hand_nrm[seen] + rng.normal(0, 0.05, (900, 3))
+    clutter = rng.uniform([-0.2, -0.1, -0.06], [0.0, 0.1, 0.06], (600, 3))
+    cn = rng.normal(size=(600, 3)); cn /= np.linalg.norm(cn, axis=1, keepdims=True)
+    return hand_xyz, hand_nrm, np.concatenate([scene, clutter]).astype(np.float32), np.concatenate([snrm, cn]).astype(np.float32)
+
+
+@pytest.mark.parametrize("true_height", [0.01, -0.02, 0.0])
+def test_adjust_hand_height_matches_oracle(ctx, true_height):
+    hx, hn, sx, sn = _height_case(3, true_height)
+    hand, scene = ctx.upload_cloud(hx, hn), ctx.upload_cloud(sx, sn)
+    counts, best = ctx.adjust_hand_height(hand, scene)
+    ocounts, obest = O.adjust_hand_height(hx, hn, sx, sn, ctx.TRIAL_HEIGHTS)
+    assert np.array_equal(counts, ocounts) and best == obest
+    assert abs(ctx.TRIAL_HEIGHTS[best] - true_height) < 1e-6 and counts[best] > 300
+    hand.free(); scene.free()
+
+
+def test_adjust_hand_height_nothing_matches(ctx):
+    hx, hn, sx, sn = _height_case(4, 0.0)
+    hand, scene = ctx.upload_cloud(hx, hn), ctx.upload_cloud((sx + [0, 0, 1.0]).astype(np.float32), sn)
+    counts, best = ctx.adjust_hand_height(hand, scene)
+    assert best == -1 and counts.sum() == 0            # the reference keeps _handbase_in_cam (best_height stays 0)
+    hand.free(); scene.free()
