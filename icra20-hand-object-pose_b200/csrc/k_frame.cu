@@ -453,6 +453,188 @@ extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int wi
   return HOP_OK;
 }
 
+// ---- cloud filters of Hand::setCurScene (Hand.cpp:279-334): VoxelGrid, transform, PassThrough, RadiusOutlierRemoval x2,
+//      StatisticalOutlierRemoval -- each returns a new device cloud, points in input order -------------------------------------------
+namespace {
+Xf xf_from(const float *colmajor) {
+  Xf T;
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 4; ++c) T.m[4 * r + c] = colmajor[4 * c + r];
+  return T;
+}
+
+// compacted (xyz, w) / normal arrays -> *out (created when null), with its bounding box
+int make_cloud(hop_ctx *ctx, const float4 *pts, const float4 *nrm, int n, hop_cloud **out) {
+  hop_cloud *c = *out ? *out : new hop_cloud();
+  int rc = hop_cloud_reserve(ctx, c, n);
+  if (rc != HOP_OK) { if (!*out) hop_cloud_free(ctx, c); return rc; }
+  to_cloud_kernel<<<blocks(c->n_padded), 256, 0, ctx->stream>>>(pts, nrm, n, c->n_padded, c->d_pw, c->d_nv);
+  ctx->launches += 1;
+  float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
+  if (n > 0 && (rc = cloud_bounds(ctx, pts, n, mn, mx)) != HOP_OK) { if (!*out) hop_cloud_free(ctx, c); return rc; }
+  for (int k = 0; k < 3; ++k) { c->bbox_min[k] = mn[k]; c->bbox_max[k] = mx[k]; }
+  FR_CUDA(cudaGetLastError());
+  *out = c;
+  return HOP_OK;
+}
+
+__global__ void transform_kernel(const float4 *__restrict__ pw, const float4 *__restrict__ nv, int n, Xf T, float4 *__restrict__ opw, float4 *__restrict__ onv) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pw[i], q = nv[i];
+  opw[i] = make_float4(xf_row(T, 0, p.x, p.y, p.z), xf_row(T, 1, p.x, p.y, p.z), xf_row(T, 2, p.x, p.y, p.z), p.w);
+  onv[i] = make_float4(__fadd_rn(__fadd_rn(__fmul_rn(T.m[0], q.x), __fmul_rn(T.m[1], q.y)), __fmul_rn(T.m[2], q.z)),
+                       __fadd_rn(__fadd_rn(__fmul_rn(T.m[4], q.x), __fmul_rn(T.m[5], q.y)), __fmul_rn(T.m[6], q.z)),
+                       __fadd_rn(__fadd_rn(__fmul_rn(T.m[8], q.x), __fmul_rn(T.m[9], q.y)), __fmul_rn(T.m[10], q.z)), 0.f);
+}
+
+__global__ void pass_flag_kernel(const float4 *__restrict__ pw, int n, int axis, float lo, float hi, unsigned char *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pw[i];
+  const float v = axis == 0 ? p.x : (axis == 1 ? p.y : p.z);
+  flag[i] = (finite3(p.x, p.y, p.z) && !(v < lo || v > hi)) ? 1 : 0;   // pcl::PassThrough keeps lo <= v <= hi
+}
+
+// pcl::RadiusOutlierRemoval (dense input): a point stays when its (min_pts + 1)-th nearest neighbour, itself included, lies within
+// the radius, i.e. when at least min_pts + 1 points have d^2 <= r^2.  One thread per point, all lanes scan the cloud together.
+__global__ void __launch_bounds__(128) ror_kernel(const float4 *__restrict__ pw, int n, float r2, int need, unsigned char *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = i < n;
+  const float4 p = live ? pw[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+  for (int j = 0; j < n; ++j) {
+    const float4 c = __ldg(pw + j);
+    const float dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    cnt += d2 <= r2;
+  }
+  if (live) flag[i] = (finite3(p.x, p.y, p.z) && cnt >= need) ? 1 : 0;
+}
+
+// pcl::StatisticalOutlierRemoval, first pass: mean distance to the mean_k nearest neighbours (the nearest hit, normally the point
+// itself, is skipped), distances summed in ascending order in double.  KMAX bounds mean_k + 1.
+constexpr int SOR_KMAX = 65;
+__global__ void __launch_bounds__(128) sor_mean_kernel(const float4 *__restrict__ pw, int n, int k1 /* mean_k + 1 */, float *__restrict__ mean_dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pw[i];
+  float best[SOR_KMAX];
+  for (int k = 0; k < k1; ++k) best[k] = FLT_MAX;
+  for (int j = 0; j < n; ++j) {
+    const float4 c = __ldg(pw + j);
+    const float dx = c.x - p.x, dy = c.y - p.y, dz = c.z - p.z;
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    if (!(d2 < best[k1 - 1])) continue;
+    int k = k1 - 1;
+    while (k > 0 && best[k - 1] > d2) { best[k] = best[k - 1]; --k; }
+    best[k] = d2;
+  }
+  double sum = 0.0;
+  const int have = min(k1, n);
+  for (int k = 1; k < have; ++k) sum += (double)__fsqrt_rn(best[k]);
+  mean_dist[i] = (float)(sum / (double)(k1 - 1));
+}
+
+__global__ void sor_flag_kernel(const float4 *__restrict__ pw, const float *__restrict__ mean_dist, int n, double thr, unsigned char *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pw[i];
+  flag[i] = (finite3(p.x, p.y, p.z) && (double)mean_dist[i] <= thr) ? 1 : 0;
+}
+
+// keep the flagged points of `in` (order preserved) as a new cloud
+int keep_flagged(hop_ctx *ctx, const hop_cloud *in, const unsigned char *flag, hop_cloud **out) {
+  cudaStream_t st = ctx->stream;
+  FBuf B(st), NB(st);
+  int kept = 0, rc;
+  if (in->n > 0) {
+    FR_CUDA(B.alloc(sizeof(float4) * (size_t)in->n)); FR_CUDA(NB.alloc(sizeof(float4) * (size_t)in->n));
+    if ((rc = compact2(ctx, in->d_pw, in->d_nv, flag, in->n, B.as<float4>(), NB.as<float4>(), &kept)) != HOP_OK) return rc;
+  }
+  return make_cloud(ctx, B.as<float4>(), NB.as<float4>(), kept, out);
+}
+}  // namespace
+
+extern "C" int hop_cloud_voxel_grid(hop_ctx *ctx, const hop_cloud *in, float leaf, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || !(leaf > 0.f)) { ctx->err = "hop_cloud_voxel_grid: bad arguments"; return HOP_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  FBuf B(st), NB(st);
+  int m = 0, rc;
+  if (in->n > 0) {
+    FR_CUDA(B.alloc(sizeof(float4) * (size_t)in->n)); FR_CUDA(NB.alloc(sizeof(float4) * (size_t)in->n));
+    ProfScope ps(ctx, HOP_PROF_FRAME);
+    if ((rc = voxel_grid(ctx, in->d_pw, in->d_nv, in->n, leaf, B.as<float4>(), NB.as<float4>(), &m)) != HOP_OK) return rc;
+  }
+  return make_cloud(ctx, B.as<float4>(), NB.as<float4>(), m, out);
+}
+
+extern "C" int hop_cloud_transform(hop_ctx *ctx, const hop_cloud *in, const float *T, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || !T) { ctx->err = "hop_cloud_transform: bad arguments"; return HOP_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  FBuf B(st), NB(st);
+  if (in->n > 0) {
+    FR_CUDA(B.alloc(sizeof(float4) * (size_t)in->n)); FR_CUDA(NB.alloc(sizeof(float4) * (size_t)in->n));
+    transform_kernel<<<blocks(in->n), 256, 0, st>>>(in->d_pw, in->d_nv, in->n, xf_from(T), B.as<float4>(), NB.as<float4>());
+    ctx->launches += 1;
+  }
+  return make_cloud(ctx, B.as<float4>(), NB.as<float4>(), in->n, out);
+}
+
+extern "C" int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axis, float lo, float hi, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || axis < 0 || axis > 2) { ctx->err = "hop_cloud_pass_through: bad arguments"; return HOP_EINVAL; }
+  FBuf fl(ctx->stream);
+  if (in->n > 0) {
+    FR_CUDA(fl.alloc((size_t)in->n));
+    pass_flag_kernel<<<blocks(in->n), 256, 0, ctx->stream>>>(in->d_pw, in->n, axis, lo, hi, fl.as<unsigned char>());
+    ctx->launches += 1;
+  }
+  return keep_flagged(ctx, in, fl.as<unsigned char>(), out);
+}
+
+extern "C" int hop_cloud_radius_outlier_removal(hop_ctx *ctx, const hop_cloud *in, float radius, int min_neighbors, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || !(radius > 0.f) || min_neighbors < 0) { ctx->err = "hop_cloud_radius_outlier_removal: bad arguments"; return HOP_EINVAL; }
+  FBuf fl(ctx->stream);
+  if (in->n > 0) {
+    FR_CUDA(fl.alloc((size_t)in->n));
+    ProfScope ps(ctx, HOP_PROF_FRAME);
+    ror_kernel<<<(in->n + 127) / 128, 128, 0, ctx->stream>>>(in->d_pw, in->n, (float)((double)radius * (double)radius), min_neighbors + 1, fl.as<unsigned char>());
+    ctx->launches += 1;
+  }
+  return keep_flagged(ctx, in, fl.as<unsigned char>(), out);
+}
+
+extern "C" int hop_cloud_statistical_outlier_removal(hop_ctx *ctx, const hop_cloud *in, int mean_k, float stddev_mul, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || mean_k < 1 || mean_k + 1 > SOR_KMAX) { ctx->err = "hop_cloud_statistical_outlier_removal: bad arguments (mean_k 1..64)"; return HOP_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  FBuf fl(st), md(st);
+  const int n = in->n;
+  if (n > 0) {
+    FR_CUDA(fl.alloc((size_t)n)); FR_CUDA(md.alloc(sizeof(float) * (size_t)n));
+    {
+      ProfScope ps(ctx, HOP_PROF_FRAME);
+      sor_mean_kernel<<<(n + 127) / 128, 128, 0, st>>>(in->d_pw, n, mean_k + 1, md.as<float>());
+      ctx->launches += 1;
+    }
+    // the global statistics are a sequential double sum over the points in order (statistical_outlier_removal.hpp): on the host
+    std::vector<float> h(n);
+    FR_CUDA(cudaMemcpyAsync(h.data(), md.p, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost, st));
+    FR_CUDA(cudaStreamSynchronize(st));
+    double sum = 0, sq_sum = 0;
+    for (int i = 0; i < n; ++i) { sum += h[i]; sq_sum += (double)h[i] * h[i]; }
+    const double mean = sum / (double)n;
+    const double variance = (sq_sum - sum * sum / (double)n) / ((double)n - 1);
+    const double thr = mean + (double)stddev_mul * std::sqrt(variance);
+    sor_flag_kernel<<<blocks(n), 256, 0, st>>>(in->d_pw, md.as<float>(), n, thr, fl.as<unsigned char>());
+    ctx->launches += 1;
+  }
+  return keep_flagged(ctx, in, fl.as<unsigned char>(), out);
+}
+
 // ---- HandT42::removeSurroundingPointsAndAssignProbability (Hand.cpp:781-888) ------------------------------------------------------
 namespace {
 constexpr int MAX_LINKS = 16;

@@ -175,6 +175,11 @@ def load_library():
     L.hop_sdf_query.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp, _vp, _vp]
     L.hop_reject_by_collision.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
     L.hop_reject_by_collision_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(CollisionParams), _vp, _vp, _vp]
+    L.hop_cloud_voxel_grid.argtypes = [_vp, _vp, C.c_float, C.POINTER(_vp)]
+    L.hop_cloud_transform.argtypes = [_vp, _vp, _vp, C.POINTER(_vp)]
+    L.hop_cloud_pass_through.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.POINTER(_vp)]
+    L.hop_cloud_radius_outlier_removal.argtypes = [_vp, _vp, C.c_float, C.c_int, C.POINTER(_vp)]
+    L.hop_cloud_statistical_outlier_removal.argtypes = [_vp, _vp, C.c_int, C.c_float, C.POINTER(_vp)]
     L.hop_adjust_hand_height.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]
     L.hop_remove_hand_points.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(HandRemovalParams), C.POINTER(_vp)]
     L.hop_default_render_params.argtypes = [C.POINTER(RenderParams)]
@@ -330,6 +335,28 @@ class Cloud:
         if self.handle:
             self.ctx.L.hop_cloud_free(self.ctx.h, self.handle)
             self.handle = None
+
+    # -- the filters of Hand::setCurScene (Hand.cpp:279-334): each returns a new device cloud, input order kept
+    def _new(self, fn, *args):
+        h = _vp()
+        self.ctx._check(fn(self.ctx.h, self.handle, *args, C.byref(h)))
+        return Cloud(self.ctx, h, int(self.ctx.L.hop_cloud_size(h)))
+
+    def voxel_grid(self, leaf):
+        return self._new(self.ctx.L.hop_cloud_voxel_grid, C.c_float(leaf))
+
+    def transform(self, T):
+        flat = poses_to_colmajor(np.asarray(T, np.float32).reshape(1, 4, 4))
+        return self._new(self.ctx.L.hop_cloud_transform, _ptr(flat))
+
+    def pass_through(self, axis, lo, hi):
+        return self._new(self.ctx.L.hop_cloud_pass_through, {"x": 0, "y": 1, "z": 2}.get(axis, axis), C.c_float(lo), C.c_float(hi))
+
+    def radius_outlier_removal(self, radius, min_neighbors):
+        return self._new(self.ctx.L.hop_cloud_radius_outlier_removal, C.c_float(radius), int(min_neighbors))
+
+    def statistical_outlier_removal(self, mean_k, stddev_mul):
+        return self._new(self.ctx.L.hop_cloud_statistical_outlier_removal, int(mean_k), C.c_float(stddev_mul))
 
 
 class Mesh:

@@ -120,3 +120,21 @@ class HandMatcher:
         self._component_status[model_name] = True
         self.angle = float(angle)
         return True
+
+
+def set_cur_scene(scene_hand_region, handbase_in_cam):
+    """The cloud chain of Hand::setCurScene (Hand.cpp:279-334) on the device, from the cropped hand-region cloud (a capi.Cloud in
+    the camera frame, with normals): VoxelGrid 3 mm -> into the hand-base frame -> RadiusOutlierRemoval(0.02, 30) ->
+    RadiusOutlierRemoval(0.04, 100) -> StatisticalOutlierRemoval(20, 2) -> PassThrough x in [-0.25, -0.1].
+    Returns the three clouds _pso_args holds (all in the hand-base frame): scene_hand_region (what the normals are looked up in),
+    scene_hand_region_removed_noise (what the kd-tree indexes), scene_remove_swivel.  (handbaseICP, Hand.cpp:677-763, runs before
+    this on the organised scene through hop_icp_refine and may have moved handbase_in_cam.)"""
+    ds = scene_hand_region.voxel_grid(0.003)
+    hb = ds.transform(np.linalg.inv(np.asarray(handbase_in_cam, np.float32)))
+    r1 = hb.radius_outlier_removal(0.02, 30)
+    r2 = r1.radius_outlier_removal(0.04, 100)
+    clean = r2.statistical_outlier_removal(20, 2.0)
+    noswivel = clean.pass_through("x", -0.25, -0.1)
+    for c in (ds, r1, r2):
+        c.free()
+    return {"scene_hand_region": hb, "scene_hand_region_removed_noise": clean, "scene_remove_swivel": noswivel}

@@ -300,6 +300,21 @@ void hop_default_frame_params(hop_frame_params *p);
  * cropped points, object leaves, final points. */
 int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *params, hop_cloud **scene,
                        int32_t *stage_counts);
+/* The cloud filters of Hand::setCurScene (Hand.cpp:279-334) on device clouds; each writes a NEW cloud (*out NULL) or refills
+ * *out (which must not be `in`); points keep their input order; normals and the weight channel travel with the points.
+ *   hop_cloud_voxel_grid                   Utils::downsamplePointCloud = pcl::VoxelGrid (Utils.cpp:333-340): leaf centroids in leaf-index order
+ *   hop_cloud_transform                    pcl::transformPointCloudWithNormals, T = 16 floats column-major
+ *   hop_cloud_pass_through                 pcl::PassThrough on axis 0 / 1 / 2: keeps lo <= v <= hi
+ *   hop_cloud_radius_outlier_removal       pcl::RadiusOutlierRemoval: keeps a point with more than min_neighbors points (itself included)
+ *                                          within the radius, d^2 <= float(r^2)
+ *   hop_cloud_statistical_outlier_removal  pcl::StatisticalOutlierRemoval: mean distance to the mean_k (<= 64) nearest neighbours,
+ *                                          kept when <= mean + stddev_mul * stddev over the cloud (statistics in double, in point order) */
+int hop_cloud_voxel_grid(hop_ctx *ctx, const hop_cloud *in, float leaf, hop_cloud **out);
+int hop_cloud_transform(hop_ctx *ctx, const hop_cloud *in, const float *T, hop_cloud **out);
+int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axis, float lo, float hi, hop_cloud **out);
+int hop_cloud_radius_outlier_removal(hop_ctx *ctx, const hop_cloud *in, float radius, int min_neighbors, hop_cloud **out);
+int hop_cloud_statistical_outlier_removal(hop_ctx *ctx, const hop_cloud *in, int mean_k, float stddev_mul, hop_cloud **out);
+
 /* HandT42::removeSurroundingPointsAndAssignProbability (Hand.cpp:781-888; main_realdata_auto.cpp:144-148): drops the scene points
  * that belong to the hand and gives the others the confidence 1 - exp(-231.049 * min_dist), min_dist = the smallest exact
  * nearest-neighbour distance to the link clouds visited (start value 1.0), then drops the points on the outer side of either

@@ -462,3 +462,34 @@ def adjust_hand_height(hand_xyz, hand_nrm, scene_xyz, scene_nrm, heights):
     L.hop_oracle_adjust_hand_height.argtypes = [_f32p, _f32p, C.c_int, _f32p, _f32p, C.c_int, _f32p, C.c_int, _i32p]
     best = L.hop_oracle_adjust_hand_height(_c(hand_xyz), _c(hand_nrm), len(hand_xyz), _c(scene_xyz), _c(scene_nrm), len(scene_xyz), hs, len(hs), counts)
     return counts, int(best)
+
+
+# ---- the cloud filters of Hand::setCurScene (Hand.cpp:279-334), numpy restatements (float32 distances in PCL/FLANN's order) ----
+def _d2_matrix(xyz):
+    p = np.asarray(xyz, np.float32)
+    dx = p[None, :, 0] - p[:, None, 0]
+    dy = p[None, :, 1] - p[:, None, 1]
+    dz = p[None, :, 2] - p[:, None, 2]
+    return (dx * dx + dy * dy) + dz * dz           # float32, unfused, left to right
+
+
+def radius_outlier_removal(xyz, radius, min_neighbors):
+    """pcl::RadiusOutlierRemoval (dense input): keep mask; a point stays with more than min_neighbors points (itself included) in d^2 <= float(r^2)"""
+    r2 = np.float32(float(radius) * float(radius))
+    return (_d2_matrix(xyz) <= r2).sum(1) >= min_neighbors + 1
+
+
+def statistical_outlier_removal(xyz, mean_k, stddev_mul):
+    """pcl::StatisticalOutlierRemoval: (keep mask, mean distances); double sums in ascending / point order like the reference"""
+    d2 = np.sort(_d2_matrix(xyz), axis=1)[:, 1:mean_k + 1]
+    s = np.zeros(len(d2), np.float64)
+    for k in range(d2.shape[1]):
+        s = s + np.sqrt(d2[:, k]).astype(np.float64)
+    dist = (s / float(mean_k)).astype(np.float32)
+    n = len(dist)
+    total = np.cumsum(dist.astype(np.float64))[-1]
+    sq = np.cumsum(dist.astype(np.float64) * dist.astype(np.float64))[-1]
+    mean = total / n
+    var = (sq - total * total / n) / (n - 1)
+    thr = mean + float(np.float32(stddev_mul)) * np.sqrt(var)
+    return dist.astype(np.float64) <= thr, dist
