@@ -31,8 +31,8 @@ METRIC = "pose hypotheses/sec (ICP-refined + LCP-scored)"
 UNIT = "hypotheses/s"
 TOPK = 16
 # dram__bytes_read.sum + dram__bytes_write.sum of one icp_fused_kernel launch (a whole C2 batch), from the ncu --set full
-# capture summarised in profiles/r01_ncu_icp_fused_kernel_C2.txt; other workloads were not captured -> null
-TRAFFIC_BYTES_PER_LAUNCH = {"C2": 30083840}
+# captures summarised in profiles/r01_ncu_icp_fused_kernel_C2.txt and _headline.txt; other workloads were not captured -> null
+TRAFFIC_BYTES_PER_LAUNCH = {"C2": 30083840, "headline": 36006144}
 N_FRAMES = 4  # distinct synthetic frames cycled through the steps (a step = `frames_per_step` consecutive frames, default 1)
 
 
