@@ -542,6 +542,20 @@ __global__ void sor_flag_kernel(const float4 *__restrict__ pw, const float *__re
   flag[i] = (finite3(p.x, p.y, p.z) && (double)mean_dist[i] <= thr) ? 1 : 0;
 }
 
+// Hand::handbaseICP's hand-base region (Hand.cpp:704-728): drops the finger connection discs (15 mm around (y1, z1) and (y2, z2) in
+// the y-z plane) and the strip between the two finger axes within 10 mm of z1 (the reference tests z1 twice)
+__global__ void handbase_region_kernel(const float4 *__restrict__ pw, int n, float y1, float z1, float y2, float z2, unsigned char *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pw[i];
+  bool keep = true;
+  const float a1 = __fsub_rn(p.z, z1), b1 = __fsub_rn(p.y, y1), a2 = __fsub_rn(p.z, z2), b2 = __fsub_rn(p.y, y2);
+  if ((double)__fadd_rn(__fmul_rn(a1, a1), __fmul_rn(b1, b1)) <= 0.015 * 0.015) keep = false;
+  else if ((double)__fadd_rn(__fmul_rn(a2, a2), __fmul_rn(b2, b2)) <= 0.015 * 0.015) keep = false;
+  else if (((p.y >= y1 && p.y <= y2) || (p.y >= y2 && p.y <= y1)) && (double)fabsf(a1) <= 0.01) keep = false;
+  flag[i] = keep ? 1 : 0;
+}
+
 // keep the flagged points of `in` (order preserved) as a new cloud
 int keep_flagged(hop_ctx *ctx, const hop_cloud *in, const unsigned char *flag, hop_cloud **out) {
   cudaStream_t st = ctx->stream;
@@ -589,6 +603,18 @@ extern "C" int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axi
   if (in->n > 0) {
     FR_CUDA(fl.alloc((size_t)in->n));
     pass_flag_kernel<<<blocks(in->n), 256, 0, ctx->stream>>>(in->d_pw, in->n, axis, lo, hi, fl.as<unsigned char>());
+    ctx->launches += 1;
+  }
+  return keep_flagged(ctx, in, fl.as<unsigned char>(), out);
+}
+
+extern "C" int hop_cloud_handbase_region(hop_ctx *ctx, const hop_cloud *in, float y1, float z1, float y2, float z2, hop_cloud **out) {
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in) { ctx->err = "hop_cloud_handbase_region: bad arguments"; return HOP_EINVAL; }
+  FBuf fl(ctx->stream);
+  if (in->n > 0) {
+    FR_CUDA(fl.alloc((size_t)in->n));
+    handbase_region_kernel<<<blocks(in->n), 256, 0, ctx->stream>>>(in->d_pw, in->n, y1, z1, y2, z2, fl.as<unsigned char>());
     ctx->launches += 1;
   }
   return keep_flagged(ctx, in, fl.as<unsigned char>(), out);

@@ -178,6 +178,7 @@ def load_library():
     L.hop_cloud_voxel_grid.argtypes = [_vp, _vp, C.c_float, C.POINTER(_vp)]
     L.hop_cloud_transform.argtypes = [_vp, _vp, _vp, C.POINTER(_vp)]
     L.hop_cloud_pass_through.argtypes = [_vp, _vp, C.c_int, C.c_float, C.c_float, C.POINTER(_vp)]
+    L.hop_cloud_handbase_region.argtypes = [_vp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.POINTER(_vp)]
     L.hop_cloud_radius_outlier_removal.argtypes = [_vp, _vp, C.c_float, C.c_int, C.POINTER(_vp)]
     L.hop_cloud_statistical_outlier_removal.argtypes = [_vp, _vp, C.c_int, C.c_float, C.POINTER(_vp)]
     L.hop_adjust_hand_height.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp]
@@ -351,6 +352,9 @@ class Cloud:
 
     def pass_through(self, axis, lo, hi):
         return self._new(self.ctx.L.hop_cloud_pass_through, {"x": 0, "y": 1, "z": 2}.get(axis, axis), C.c_float(lo), C.c_float(hi))
+
+    def handbase_region(self, y1, z1, y2, z2):
+        return self._new(self.ctx.L.hop_cloud_handbase_region, C.c_float(y1), C.c_float(z1), C.c_float(y2), C.c_float(z2))
 
     def radius_outlier_removal(self, radius, min_neighbors):
         return self._new(self.ctx.L.hop_cloud_radius_outlier_removal, C.c_float(radius), int(min_neighbors))

@@ -138,3 +138,54 @@ def set_cur_scene(scene_hand_region, handbase_in_cam):
     for c in (ds, r1, r2):
         c.free()
     return {"scene_hand_region": hb, "scene_hand_region_removed_noise": clean, "scene_remove_swivel": noswivel}
+
+
+def euler_zyx(R):
+    """Eigen's Matrix3f::eulerAngles(2, 1, 0) (first angle in [0, pi]), as Hand::handbaseICP reads the pitch (Hand.cpp:747-748)"""
+    R = np.asarray(R, np.float32)
+    a0 = np.float32(np.arctan2(R[1, 0], R[0, 0]))
+    c2 = np.float32(np.hypot(R[2, 2], R[2, 1]))
+    if a0 < 0:
+        a0 = np.float32(a0 + np.float32(np.pi))
+        a1 = np.float32(np.arctan2(-R[2, 0], -c2))
+    else:
+        a1 = np.float32(np.arctan2(-R[2, 0], c2))
+    s1, c1 = np.float32(np.sin(a0)), np.float32(np.cos(a0))
+    a2 = np.float32(np.arctan2(s1 * R[0, 2] - c1 * R[1, 2], c1 * R[1, 1] - s1 * R[0, 1]))
+    return np.array([a0, a1, a2], np.float32)
+
+
+def handbase_icp(ctx, scene_organized, base_link_cloud, handbase_in_cam, finger_1_1_in_parent, finger_2_1_in_parent):
+    """Hand::handbaseICP (Hand.cpp:677-763) on the device: VoxelGrid 5 mm -> into the hand-base frame -> PassThrough x [-0.07, 0.03],
+    z [-0.18, 0.01] -> finger connection parts removed -> runICP(scene -> base_link cloud, 50 iterations, 30 deg, 0.03 m) -> the
+    reference's sanity gates.  scene_organized / base_link_cloud: capi.Cloud (camera frame / hand-base frame, with normals).
+    Returns (handbase_in_cam after the correction, handbase matched?, cam2handbase_offset)."""
+    hic = np.asarray(handbase_in_cam, np.float32)
+    ds = scene_organized.voxel_grid(0.005)
+    hb = ds.transform(np.linalg.inv(hic))
+    px = hb.pass_through("x", -0.07, 0.03)
+    pz = px.pass_through("z", -0.18, 0.01)
+    f1, f2 = np.asarray(finger_1_1_in_parent, np.float32), np.asarray(finger_2_1_in_parent, np.float32)
+    region = pz.handbase_region(float(f1[1, 3]), float(f1[2, 3]), float(f2[1, 3]), float(f2[2, 3]))
+    offset = np.eye(4, dtype=np.float32)
+    if region.n > 0 and base_link_cloud.n > 0:
+        params = ctx.icp_params(max_iter=50, angle_deg=30.0, max_dist=0.03)
+        # Utils::runICP(src = scene_handbase, tgt = handbase, T): hop_icp_refine refines poses of the TARGET (model -> scene),
+        # i.e. pose <- T^-1 * pose; starting from the identity the returned pose is T^-1
+        refined, _, _ = ctx.icp_refine(region, base_link_cloud, np.eye(4, dtype=np.float32)[None], params)
+        offset = np.linalg.inv(refined[0].astype(np.float64)).astype(np.float32)
+    for c in (ds, hb, px, pz, region):
+        c.free()
+    translation = float(np.linalg.norm(offset[:3, 3]))
+    if translation >= 0.05:
+        offset = np.eye(4, dtype=np.float32)
+    # Utils::rotationGeodesicDistance(I, R) (Utils.cpp:29-32): acos((trace - 1) / 2), clamped
+    cosv = float(np.clip((np.trace(offset[:3, :3]) - 1.0) / 2.0, -1.0, 1.0))
+    rot_diff = np.degrees(np.arccos(cosv))
+    pitch = float(euler_zyx(offset[:3, :3])[1])
+    pitch = min(abs(pitch), abs(float(np.float32(np.pi)) - pitch))
+    pitch = min(abs(pitch), abs(float(np.float32(np.pi)) + pitch))
+    if rot_diff >= 10 or abs(pitch) >= 10 / 180.0 * np.pi:
+        offset = np.eye(4, dtype=np.float32)
+    matched = not np.array_equal(offset, np.eye(4, dtype=np.float32))
+    return (hic.astype(np.float64) @ np.linalg.inv(offset.astype(np.float64))).astype(np.float32), matched, offset

@@ -313,6 +313,10 @@ int hop_cloud_voxel_grid(hop_ctx *ctx, const hop_cloud *in, float leaf, hop_clou
 int hop_cloud_transform(hop_ctx *ctx, const hop_cloud *in, const float *T, hop_cloud **out);
 int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axis, float lo, float hi, hop_cloud **out);
 int hop_cloud_radius_outlier_removal(hop_ctx *ctx, const hop_cloud *in, float radius, int min_neighbors, hop_cloud **out);
+/* the per-point filter of Hand::handbaseICP (Hand.cpp:704-728) on a cloud in the hand-base frame: drops the points within 15 mm
+ * (in the y-z plane) of either proximal finger axis (y1, z1) = _tf_in_parent["finger_1_1"](1..2,3), (y2, z2) = ...["finger_2_1"],
+ * and the points between the two axes in y that lie within 10 mm of z1 */
+int hop_cloud_handbase_region(hop_ctx *ctx, const hop_cloud *in, float y1, float z1, float y2, float z2, hop_cloud **out);
 int hop_cloud_statistical_outlier_removal(hop_ctx *ctx, const hop_cloud *in, int mean_k, float stddev_mul, hop_cloud **out);
 
 /* HandT42::removeSurroundingPointsAndAssignProbability (Hand.cpp:781-888; main_realdata_auto.cpp:144-148): drops the scene points

@@ -118,3 +118,54 @@ def test_set_cur_scene_chain(ctx):
     assert np.array_equal(gx, x3[m]) and len(gx) > 0
     for cl in list(got.values()) + [c, ds]:
         cl.free()
+
+
+def test_handbase_icp_chain(ctx):
+    """Hand::handbaseICP (Hand.cpp:677-763) through the mirror: the region cloud bit-exact against the restated filters, the ICP
+    correction within the north-star tolerance of the oracle's runICP, the corrected hand base near the truth"""
+    rng = np.random.default_rng(11)
+    bp, bn = synth._cuboid(rng, 1500, 0.08, 0.10, 0.03)
+    base_xyz, base_nrm = (bp + [-0.02, 0.0, -0.08]).astype(np.float32), bn.astype(np.float32)     # base_link cloud, hand-base frame
+    # the kinematics put the hand base at hic_hat; the real one is off by a few millimetres and degrees
+    hic_hat = np.eye(4); hic_hat[:3, :3] = synth.random_rotation(rng); hic_hat[:3, 3] = [0.05, -0.02, 0.5]
+    true_off = np.eye(4); true_off[:3, :3] = synth._rot_from_rotvec(np.deg2rad([2.0, -3.0, 1.5])); true_off[:3, 3] = [0.004, -0.006, 0.005]
+    hic_true = hic_hat @ np.linalg.inv(true_off)
+    vis = np.nonzero(bn @ np.array([0.3, 0.2, 1.0]) > 0)[0]                   # the faces a camera above the hand sees
+    sp = base_xyz[vis] + rng.normal(0, 0.0004, (len(vis), 3))
+    clutter = rng.uniform([-0.3, -0.2, -0.3], [0.2, 0.2, 0.1], (3000, 3))
+    cn = rng.normal(size=(3000, 3)); cn /= np.linalg.norm(cn, axis=1, keepdims=True)
+    hb_pts = np.concatenate([sp, clutter]); hb_nrm = np.concatenate([bn[vis], cn])
+    scene_xyz = (hb_pts @ hic_true[:3, :3].T + hic_true[:3, 3]).astype(np.float32)
+    scene_nrm = (hb_nrm @ hic_true[:3, :3].T).astype(np.float32)
+    f11 = np.eye(4); f11[:3, 3] = [0.0, -0.045, 0.02]
+    f21 = np.eye(4); f21[:3, 3] = [0.0, 0.045, 0.02]
+    scene, base = ctx.upload_cloud(scene_xyz, scene_nrm), ctx.upload_cloud(base_xyz, base_nrm)
+    new_hic, matched, offset = hand.handbase_icp(ctx, scene, base, hic_hat.astype(np.float32), f11, f21)
+    # the restated chain on the device's voxel grid output
+    ds = scene.voxel_grid(0.005)
+    dx, dn, _ = ds.download()
+    hx, hn = O.transform_cloud(np.linalg.inv(hic_hat.astype(np.float32)), dx, dn)
+    m = (hx[:, 0] >= np.float32(-0.07)) & (hx[:, 0] <= np.float32(0.03))
+    hx, hn = hx[m], hn[m]
+    m = (hx[:, 2] >= np.float32(-0.18)) & (hx[:, 2] <= np.float32(0.01))
+    hx, hn = hx[m], hn[m]
+    y1, z1, y2, z2 = np.float32(-0.045), np.float32(0.02), np.float32(0.045), np.float32(0.02)
+    d1 = ((hx[:, 2] - z1) ** 2 + (hx[:, 1] - y1) ** 2).astype(np.float64) <= 0.015 * 0.015
+    d2 = ((hx[:, 2] - z2) ** 2 + (hx[:, 1] - y2) ** 2).astype(np.float64) <= 0.015 * 0.015
+    strip = (hx[:, 1] >= y1) & (hx[:, 1] <= y2) & (np.abs(hx[:, 2] - z1).astype(np.float64) <= 0.01)
+    keep = ~(d1 | d2 | strip)
+    rx, rn = hx[keep], hn[keep]
+    tmp = ctx.upload_cloud(dx, dn)
+    t1 = tmp.transform(np.linalg.inv(hic_hat.astype(np.float32))); t2 = t1.pass_through("x", -0.07, 0.03); t3 = t2.pass_through("z", -0.18, 0.01)
+    t4 = t3.handbase_region(float(y1), float(z1), float(y2), float(z2))
+    gx, gn, _ = t4.download()
+    assert np.array_equal(gx, rx) and np.array_equal(gn, rn) and len(rx) > 200
+    T_ref, it, conv = O.run_icp(rx, rn, base_xyz, base_nrm, max_iter=50, angle=30.0, dist=0.03)
+    dt, dr = synth.pose_error(offset[None], np.asarray(T_ref, np.float32).reshape(1, 4, 4))
+    assert dt[0] <= 1e-3 and dr[0] <= 1.0, (dt, dr)
+    assert matched
+    et, er = synth.pose_error(new_hic[None], hic_true.astype(np.float32)[None])
+    e0, r0 = synth.pose_error(hic_hat.astype(np.float32)[None], hic_true.astype(np.float32)[None])
+    assert et[0] < 0.003 and er[0] < 1.5 and et[0] < e0[0]
+    for c in (scene, base, ds, tmp, t1, t2, t3, t4):
+        c.free()
