@@ -232,7 +232,7 @@ struct WalkArgs {
   float *wrong_ratio;
 };
 constexpr int WALK_THREADS = 128;
-__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile_stride) {
+__global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile_stride, int lanes /* hypotheses per CTA, <= 32 */) {
   extern __shared__ __align__(16) float walk_smem[];
   __shared__ Tile s_t[32];
   __shared__ int s_first;
@@ -242,9 +242,9 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile
   float *s_tile = walk_smem + 2 * Wp;              // 2 x 32 x tile_stride
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   if (warp == 0) {
-    const int slot = blockIdx.x * 32 + lane;
+    const int slot = blockIdx.x * lanes + lane;
     Tile t; t.x0 = t.y0 = 0; t.w = t.h = 0; t.off = 0;
-    if (slot < a.n) t = a.tiles[a.perm[slot]];
+    if (lane < lanes && slot < a.n) t = a.tiles[a.perm[slot]];
     if (t.w <= 0 || t.h <= 0) { t.w = t.h = 0; t.y0 = Hh; }
     s_t[lane] = t;
     int first = t.y0;
@@ -257,10 +257,10 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile
   // producer: row y -> buffer (y & 1)
   auto produce = [&](int y) {
     if (y >= Hh) return;
-    float *db = s_base + (y & 1) * Wp, *dt = s_tile + (size_t)(y & 1) * 32 * tile_stride;
+    float *db = s_base + (y & 1) * Wp, *dt = s_tile + (size_t)(y & 1) * lanes * tile_stride;
     const float *src = a.base_diff + (size_t)y * W;
     for (int x = tid - 32; x < Wp; x += WALK_THREADS - 32) { if (x < W) cp_async4(db + x, src + x); else db[x] = 0.f; }
-    for (int l = 0; l < 32; ++l) {
+    for (int l = 0; l < lanes; ++l) {
       const Tile t = s_t[l];
       if (y < t.y0 || y >= t.y0 + t.h) continue;
       const unsigned int *zr = a.zbuf + t.off + (size_t)(y - t.y0) * t.w;
@@ -276,7 +276,7 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile
     __syncthreads();                               // row y is in its buffer; the other buffer is free
     if (warp != 0) { produce(y + 1); continue; }
     const float *sb = s_base + (y & 1) * Wp;
-    const float *st = s_tile + (size_t)(y & 1) * 32 * tile_stride + lane * tile_stride;   // this lane's tile segment of row y
+    const float *st = s_tile + (size_t)(y & 1) * lanes * tile_stride + (lane < lanes ? lane : 0) * tile_stride;   // this lane's tile segment of row y
     if (y == t.y0) bg = a.prefix[(size_t)y * W];
     const bool started = y >= t.y0, in_rows = started && y < t.y0 + t.h;
     // x + 0.f = x exactly for the non-negative sums carried here, so "not mine" adds a zero: two independent add chains per pixel,
@@ -311,8 +311,8 @@ __global__ void __launch_bounds__(WALK_THREADS) walk_kernel(WalkArgs a, int tile
     }
   }
   if (warp != 0) return;
-  const int slot = blockIdx.x * 32 + lane;
-  if (slot >= a.n) return;
+  const int slot = blockIdx.x * lanes + lane;
+  if (lane >= lanes || slot >= a.n) return;
   const int h = a.perm[slot];
   if (t.w == 0) bg = a.prefix[n];
   const int bg_cnt = n - roi_cnt;
@@ -507,11 +507,14 @@ extern "C" int hop_reject_by_render(hop_ctx *ctx, const hop_render_scene *scene,
       const int stride = (part == 0 ? std::min(max_w, narrow) : max_w) | 1;   // odd: the 32 lanes' segments start in different banks
       WalkArgs wa; wa.p = scene->p; wa.base_diff = scene->d_base_diff; wa.prefix = scene->d_prefix;
       wa.tiles = d_tiles; wa.zbuf = d_z; wa.perm = d_perm + begin; wa.n = count; wa.wrong_ratio = d_wr;
-      const size_t smem = sizeof(float) * (2 * (size_t)Wp + 2 * 32 * (size_t)stride);
-      if (smem > 200 * 1024) { ctx->err = "hop_reject_by_render: image too wide for the walk kernel's shared memory"; return HOP_EINVAL; }
+      // 32 hypotheses per CTA when their tile rows fit the shared memory twice over, fewer for very wide tiles / images
+      const size_t budget = 200 * 1024, base_bytes = sizeof(float) * 2 * (size_t)Wp, per_lane = sizeof(float) * 2 * (size_t)stride;
+      if (base_bytes + per_lane > budget) { ctx->err = "hop_reject_by_render: image too wide for the walk kernel's shared memory"; return HOP_EINVAL; }
+      const int lanes = (int)std::min<size_t>(32, (budget - base_bytes) / per_lane);
+      const size_t smem = base_bytes + per_lane * (size_t)lanes;
       static size_t attr = 0;
       if (smem > attr) { HOP_CUDA(ctx, cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
-      walk_kernel<<<(count + 31) / 32, WALK_THREADS, smem, st>>>(wa, stride);
+      walk_kernel<<<(count + lanes - 1) / lanes, WALK_THREADS, smem, st>>>(wa, stride, lanes);
       ctx->launches += 1;
     }
   }

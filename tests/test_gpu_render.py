@@ -112,3 +112,18 @@ def test_pose_estimator_reject_by_render_method(ctx):
     owr, oorder = O.reject_by_render(_oparams(cam), case["depth_m"], case["hand_V"], case["hand_F"], case["obj_V"], case["obj_F"], case["poses"])
     assert [h._id for h in pe._pose_hypos] == list(oorder) and len(oorder) == 14
     assert np.array_equal(np.array([h._wrong_ratio for h in pe._pose_hypos], np.float32), owr[oorder])
+
+
+def test_wide_image_uses_fewer_hypotheses_per_cta(ctx):
+    """1280 x 720 with hypotheses whose tiles span the whole width: the walk kernel's shared-memory rows no longer fit 32 hypotheses
+    per CTA (18 here); results stay bit-exact"""
+    case = _case("ellipse", 40, 14, width=1280, height=720)
+    near = case["gt"].copy(); near[:3, 3] = [0.0, 0.0, 0.13]                  # fills the image
+    poses = np.concatenate([case["poses"][:36], np.stack([near, near, case["gt"], case["gt"]])])
+    scene = ctx.render_scene(_params(ctx, case["cam"]), case["depth_m"], case["hand_V"], case["hand_F"])
+    wr, order = ctx.reject_by_render(scene, case["obj_V"], case["obj_F"], poses)
+    owr, oorder = O.reject_by_render(_oparams(case["cam"]), case["depth_m"], case["hand_V"], case["hand_F"], case["obj_V"], case["obj_F"], poses)
+    assert np.array_equal(wr, owr, equal_nan=True) and np.array_equal(order, oorder)
+    d, m = ctx.render_depth(scene, case["obj_V"], case["obj_F"], near)
+    assert m[:, 0].any() and m[:, -1].any()                                   # the tile really spans the width
+    scene.free()
