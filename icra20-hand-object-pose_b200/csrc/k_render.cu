@@ -100,18 +100,25 @@ __global__ void raster_kernel(RasterArgs a) {
   x1 = min(x1, (long long)(t.x0 + t.w - 1)); y1 = min(y1, (long long)(t.y0 + t.h - 1));
   const double iz0 = __drcp_rn((double)Z[0]), iz1 = __drcp_rn((double)Z[1]), iz2 = __drcp_rn((double)Z[2]);
   const double darea = (double)area;
-  for (long long y = y0; y <= y1; ++y)
-    for (long long x = x0; x <= x1; ++x) {
-      const long long px = x * SUBPX + SUBPX / 2, py = y * SUBPX + SUBPX / 2;
-      const long long e0 = (SX[2] - SX[1]) * (py - SY[1]) - (SY[2] - SY[1]) * (px - SX[1]);
-      const long long e1 = (SX[0] - SX[2]) * (py - SY[2]) - (SY[0] - SY[2]) * (px - SX[2]);
-      const long long e2 = (SX[1] - SX[0]) * (py - SY[0]) - (SY[1] - SY[0]) * (px - SX[0]);
+  if (x0 > x1 || y0 > y1) return;
+  // edge functions at the first pixel centre, then stepped: +1 pixel in x adds -(dy) * SUBPX, +1 pixel in y adds (dx) * SUBPX (exact integers)
+  const long long px0 = x0 * SUBPX + SUBPX / 2, py0 = y0 * SUBPX + SUBPX / 2;
+  const long long a0 = -(SY[2] - SY[1]) * SUBPX, b0 = (SX[2] - SX[1]) * SUBPX;
+  const long long a1 = -(SY[0] - SY[2]) * SUBPX, b1 = (SX[0] - SX[2]) * SUBPX;
+  const long long a2 = -(SY[1] - SY[0]) * SUBPX, b2 = (SX[1] - SX[0]) * SUBPX;
+  long long r0 = (SX[2] - SX[1]) * (py0 - SY[1]) - (SY[2] - SY[1]) * (px0 - SX[1]);
+  long long r1 = (SX[0] - SX[2]) * (py0 - SY[2]) - (SY[0] - SY[2]) * (px0 - SX[2]);
+  long long r2 = (SX[1] - SX[0]) * (py0 - SY[0]) - (SY[1] - SY[0]) * (px0 - SX[0]);
+  for (long long y = y0; y <= y1; ++y, r0 += b0, r1 += b1, r2 += b2) {
+    long long e0 = r0, e1 = r1, e2 = r2;
+    for (long long x = x0; x <= x1; ++x, e0 += a0, e1 += a1, e2 += a2) {
       if (e0 < 0 || e1 < 0 || e2 < 0) continue;
       const double iz = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn((double)e0, iz0), __dmul_rn((double)e1, iz1)), __dmul_rn((double)e2, iz2)), darea);
       const float z = (float)__drcp_rn(iz);
       if (!(z > a.p.z_near && z < a.p.z_far)) continue;
       atomicMin(a.zbuf + t.off + (size_t)(y - t.y0) * t.w + (x - t.x0), __float_as_uint(z));
     }
+  }
 }
 
 __device__ __forceinline__ float sim_of(float z, float z_far) {
