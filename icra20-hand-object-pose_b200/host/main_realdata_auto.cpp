@@ -126,18 +126,22 @@ int main(int argc, char **argv) {
     est.refineByICP();
     const Clock::time_point t4 = Clock::now();
     est.clusterPoses(5, 0.003, false);
+    const Clock::time_point t4a = Clock::now();
+    Clock::time_point t4b = t4a, t4c = t4a;
     if (use_physics) {   // main_realdata_auto.cpp:199; no hand model -> no enabled link, no hand cloud
       HandState hand;
       hand._handbase_in_cam = handbase_in_cam;
       est.rejectByCollisionOrNonTouching(hand, object_segment);
       if (est._pose_hypos.empty()) { printf("No pose found...\n"); savePoseTxt(out_dir + "/model2scene.txt", Mat4f()); exit(1); }
+      t4b = Clock::now();
       est.rejectByRender(cfg.yml["pose_estimator_wrong_ratio"].as<float>(0.f), hand, depth_meters, w, h);   // main_realdata_auto.cpp:200
+      t4c = Clock::now();
     }
     PoseHypo best(-1);
     est.selectBest(best);
     const Clock::time_point t5 = Clock::now();
-    printf("timing_ms front_end %.3f super4pcs %.3f cluster %.3f icp %.3f cluster_select %.3f total %.3f\n", ms(t0, t1), ms(t1, t2), ms(t2, t3), ms(t3, t4),
-           ms(t4, t5), ms(t0, t5));
+    printf("timing_ms front_end %.3f super4pcs %.3f cluster %.3f icp %.3f cluster_select %.3f physics %.3f render %.3f total %.3f\n", ms(t0, t1), ms(t1, t2),
+           ms(t2, t3), ms(t3, t4), ms(t4, t4a) + ms(t4c, t5), ms(t4a, t4b), ms(t4b, t4c), ms(t0, t5));
     if (pass + 1 < repeat) continue;
     const Mat4f model2scene = best._pose;
     std::cout << "best tf:\n" << model2scene << "\n\n";

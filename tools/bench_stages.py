@@ -391,6 +391,25 @@ super4pcs_success_quadrilaterals: 10
             dobj_mm = np.round(dobj * 1000).astype(np.uint16)
             cv2.imwrite(td + "/depth.png", dobj_mm)
             res["frame_obj"] = ctx.frame_to_scene(dobj_mm, fpar)[0]
+            # the same frame with the physics + render stages on: object_mesh_path readable (no hand model ships: object-only scene)
+            mV, mF = synth.make_mesh("ellipse", 3)
+            with open(td + "/ellipse.obj", "w") as f:
+                f.write("".join("v %.9g %.9g %.9g\n" % tuple(v) for v in mV) + "".join("f %d %d %d\n" % tuple(t + 1) for t in mF))
+            open(td + "/cfg_phys.yaml", "w").write(cfg + f"object_mesh_path: {td}/ellipse.obj\npose_estimator_use_physics: true\nrender_roi_weight: 2.0\nrender_keep_hypo: 0.3\n")
+            r2 = subprocess.run([main_bin, td + "/cfg_phys.yaml", "6"], capture_output=True, text=True, timeout=600)
+            tl2 = [l for l in r2.stdout.splitlines() if l.startswith("timing_ms")]
+            if r2.returncode == 0 and tl2:
+                w2 = tl2[-1].split()
+                tm2 = {w2[i]: float(w2[i + 1]) for i in range(1, len(w2) - 1, 2)}
+                est2 = np.loadtxt(td + "/model2scene.txt")
+                sub2 = mm[::20].astype(np.float64)
+                adi2 = float(cKDTree(sub2 @ gtf[:3, :3].T + gtf[:3, 3]).query(sub2 @ est2[:3, :3].T + est2[:3, 3])[0].mean())
+                print(json.dumps({"stage": "one frame through the drop-in executable with rejectByCollisionOrNonTouching + rejectByRender on (object mesh given; 6th pass)",
+                                  "metric": "frames/sec, depth image -> best pose", "value": 1e3 / tm2["total"], "unit": "frames/s",
+                                  "e2e": {"value": 1e3 / tm2["total"], "unit": "frames/s", "ms_per_call": tm2["total"]},
+                                  "config": {"stage_ms": tm2, "adi_mm": adi2 * 1e3}, "kernel_ms": None, "cpu_baseline": None}), file=out, flush=True)
+            else:
+                print("main_realdata_auto (physics) failed:", r2.returncode, r2.stdout[-800:], r2.stderr[-800:], file=sys.stderr)
             r = subprocess.run([main_bin, td + "/cfg.yaml", "6"], capture_output=True, text=True, timeout=600)
             tl = [l for l in r.stdout.splitlines() if l.startswith("timing_ms")]
             if r.returncode == 0 and tl:
