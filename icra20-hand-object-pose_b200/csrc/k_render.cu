@@ -363,15 +363,26 @@ extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *pa
   s->p = *params; s->n_px = params->width * params->height;
   const size_t nb = sizeof(float) * (size_t)s->n_px;
   cudaStream_t st = ctx->stream;
+  // per-frame object: every buffer comes from the context's stream-ordered pool (cudaMalloc / cudaFree cost milliseconds per frame)
   float *d_V = nullptr; int32_t *d_F = nullptr;
-  auto fail = [&](int code, const char *msg) { ctx->err = msg; cudaFree(d_V); cudaFree(d_F); cudaFree(s->d_real); cudaFree(s->d_zhand); cudaFree(s->d_base_diff); cudaFree(s->d_prefix); delete s; return code; };
-  if (cudaMalloc(&s->d_real, nb) != cudaSuccess || cudaMalloc(&s->d_zhand, nb) != cudaSuccess || cudaMalloc(&s->d_base_diff, nb) != cudaSuccess ||
-      cudaMalloc(&s->d_prefix, nb + sizeof(float)) != cudaSuccess) return fail(HOP_ENOMEM, "hop_render_scene_create: allocation failed");
+  auto release = [&]() {
+    if (d_V) cudaFreeAsync(d_V, st); if (d_F) cudaFreeAsync(d_F, st);
+    d_V = nullptr; d_F = nullptr;
+  };
+  auto fail = [&](int code, const char *msg) {
+    ctx->err = msg; release();
+    if (s->d_real) cudaFreeAsync(s->d_real, st); if (s->d_zhand) cudaFreeAsync(s->d_zhand, st);
+    if (s->d_base_diff) cudaFreeAsync(s->d_base_diff, st); if (s->d_prefix) cudaFreeAsync(s->d_prefix, st);
+    delete s; return code;
+  };
+  if (cudaMallocAsync(&s->d_real, nb, st) != cudaSuccess || cudaMallocAsync(&s->d_zhand, nb, st) != cudaSuccess ||
+      cudaMallocAsync(&s->d_base_diff, nb, st) != cudaSuccess || cudaMallocAsync(&s->d_prefix, nb + sizeof(float), st) != cudaSuccess)
+    return fail(HOP_ENOMEM, "hop_render_scene_create: allocation failed");
   if (cudaMemcpyAsync(s->d_real, depth_m, nb, cudaMemcpyHostToDevice, st) != cudaSuccess) return fail(HOP_ECUDA, "hop_render_scene_create: copy failed");
   fill_kernel<<<296, 256, 0, st>>>((unsigned int *)s->d_zhand, s->n_px);
   ctx->launches += 1;
   if (hand_nf > 0) {
-    if (cudaMalloc(&d_V, sizeof(float) * 3 * (size_t)hand_nv) != cudaSuccess || cudaMalloc(&d_F, sizeof(int32_t) * 3 * (size_t)hand_nf) != cudaSuccess)
+    if (cudaMallocAsync(&d_V, sizeof(float) * 3 * (size_t)hand_nv, st) != cudaSuccess || cudaMallocAsync(&d_F, sizeof(int32_t) * 3 * (size_t)hand_nf, st) != cudaSuccess)
       return fail(HOP_ENOMEM, "hop_render_scene_create: allocation failed");
     cudaMemcpyAsync(d_V, hand_V, sizeof(float) * 3 * (size_t)hand_nv, cudaMemcpyHostToDevice, st);
     cudaMemcpyAsync(d_F, hand_F, sizeof(int32_t) * 3 * (size_t)hand_nf, cudaMemcpyHostToDevice, st);
@@ -382,8 +393,8 @@ extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *pa
   base_diff_kernel<<<(s->n_px + 255) / 256, 256, 0, st>>>(s->d_zhand, s->d_real, s->n_px, s->p.z_far, s->d_base_diff);
   prefix_kernel<<<1, PREFIX_THREADS, sizeof(float) * 2 * (size_t)((s->p.width + 31) & ~31), st>>>(s->d_base_diff, s->p.width, s->p.height, s->d_prefix);
   ctx->launches += 2;
-  const cudaError_t e = cudaStreamSynchronize(st);
-  cudaFree(d_V); cudaFree(d_F); d_V = nullptr; d_F = nullptr;
+  const cudaError_t e = cudaStreamSynchronize(st);   // the host arrays (depth image, hand mesh) may be reused by the caller after the call
+  release();
   if (e != cudaSuccess || cudaGetLastError() != cudaSuccess) return fail(HOP_ECUDA, "hop_render_scene_create: kernel failed");
   *out = s;
   return HOP_OK;
@@ -391,8 +402,8 @@ extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *pa
 
 extern "C" int hop_render_scene_destroy(hop_ctx *ctx, hop_render_scene *s) {
   if (!s) return HOP_OK;
-  if (ctx) cudaStreamSynchronize(ctx->stream);
-  cudaFree(s->d_real); cudaFree(s->d_zhand); cudaFree(s->d_base_diff); cudaFree(s->d_prefix);
+  cudaStream_t st = ctx ? ctx->stream : (cudaStream_t)0;   // stream-ordered: the frees queue behind the scene's last use on the context's stream
+  cudaFreeAsync(s->d_real, st); cudaFreeAsync(s->d_zhand, st); cudaFreeAsync(s->d_base_diff, st); cudaFreeAsync(s->d_prefix, st);
   delete s;
   return HOP_OK;
 }
