@@ -12,7 +12,7 @@
 // atomicMin on the float bits); one thread per hypothesis then replays the reference's row-major float sums from the first
 // row its object touches -- everything above is the shared prefix -- so the wrong ratio carries the same rounding as the
 // reference's loop (its 3e5-term float sums lose the small differences once the sum is large; a tidier sum would rank the
-// hypotheses differently).  Coverage is decided in integer arithmetic on a 1/256 sub-pixel grid and depth in unfused double,
+// hypotheses differently).  Coverage is decided in integer arithmetic on a 1/256 sub-pixel grid and depth as a fused double dot product + one float reciprocal,
 // operation for operation what oracle/hop_oracle_render.c does: the two agree bit for bit.
 #include <algorithm>
 #include <cfloat>
@@ -99,8 +99,9 @@ __global__ void raster_kernel(RasterArgs a) {
   long long y0 = mny - SUBPX / 2 < 0 ? 0 : (mny - SUBPX / 2 + SUBPX - 1) / SUBPX, y1 = (mxy - SUBPX / 2) / SUBPX;
   x0 = max(x0, (long long)t.x0); y0 = max(y0, (long long)t.y0);
   x1 = min(x1, (long long)(t.x0 + t.w - 1)); y1 = min(y1, (long long)(t.y0 + t.h - 1));
-  const double iz0 = __drcp_rn((double)Z[0]), iz1 = __drcp_rn((double)Z[1]), iz2 = __drcp_rn((double)Z[2]);
+  // 1/Z is affine in window space: per-triangle weights w_k = (1/Z_k) / area, per pixel one fused dot product and one float reciprocal
   const double darea = (double)area;
+  const double w0 = __ddiv_rn(__drcp_rn((double)Z[0]), darea), w1 = __ddiv_rn(__drcp_rn((double)Z[1]), darea), w2 = __ddiv_rn(__drcp_rn((double)Z[2]), darea);
   if (x0 > x1 || y0 > y1) return;
   // edge functions at the first pixel centre, then stepped: +1 pixel in x adds -(dy) * SUBPX, +1 pixel in y adds (dx) * SUBPX (exact integers)
   const long long px0 = x0 * SUBPX + SUBPX / 2, py0 = y0 * SUBPX + SUBPX / 2;
@@ -114,8 +115,8 @@ __global__ void raster_kernel(RasterArgs a) {
     long long e0 = r0, e1 = r1, e2 = r2;
     for (long long x = x0; x <= x1; ++x, e0 += a0, e1 += a1, e2 += a2) {
       if (e0 < 0 || e1 < 0 || e2 < 0) continue;
-      const double iz = __ddiv_rn(__dadd_rn(__dadd_rn(__dmul_rn((double)e0, iz0), __dmul_rn((double)e1, iz1)), __dmul_rn((double)e2, iz2)), darea);
-      const float z = (float)__drcp_rn(iz);
+      const double iz = __fma_rn((double)e2, w2, __fma_rn((double)e1, w1, __dmul_rn((double)e0, w0)));
+      const float z = __fdiv_rn(1.0f, (float)iz);
       if (!(z > a.p.z_near && z < a.p.z_far)) continue;
       atomicMin(a.zbuf + t.off + (size_t)(y - t.y0) * t.w + (x - t.x0), __float_as_uint(z));
     }

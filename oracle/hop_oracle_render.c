@@ -13,7 +13,7 @@
  * The camera: a CV-frame point (X, Y, Z) lands at window x = fx X/Z + cx, window y (bottom-up) = cy - fy Y/Z; GL samples pixel
  * centres, and both read-backs flip the image, so image pixel (x, y) samples sx = x + 0.5, sy = y + 0.5 of
  *     sx = fx X/Z + cx,   sy = fy Y/Z + (height - cy).
- * Depth: 1/Z is affine over a triangle in window space; the nearest fragment wins (GL_LESS, 32-bit depth); the object is drawn
+ * Depth: 1/Z is affine over a triangle in window space (evaluated in double with fma, then one float reciprocal); the nearest fragment wins (GL_LESS, 32-bit depth); the object is drawn
  * after the hand, so it owns a pixel only where it is strictly nearer.  sim = round(1000 Z) mm / 1000, clamped to [0.1, 2.0];
  * background = the cleared depth = z_far = 2.0.
  */
@@ -72,7 +72,8 @@ static void raster(const hop_oracle_render_params *p, const float *V, const int3
     if (y0 < 0) y0 = 0;
     if (x1 > W - 1) x1 = W - 1;
     if (y1 > H - 1) y1 = H - 1;
-    const double iz0 = 1.0 / (double)Z[i0], iz1 = 1.0 / (double)Z[i1], iz2 = 1.0 / (double)Z[i2];
+    /* 1/Z is affine in window space: per-triangle weights w_k = (1/Z_k) / area, per pixel one fused dot product and one float reciprocal */
+    const double w0 = (1.0 / (double)Z[i0]) / (double)area, w1 = (1.0 / (double)Z[i1]) / (double)area, w2 = (1.0 / (double)Z[i2]) / (double)area;
     for (long long y = y0; y <= y1; ++y)
       for (long long x = x0; x <= x1; ++x) {
         const long long px = x * SUB + SUB / 2, py = y * SUB + SUB / 2;
@@ -80,8 +81,8 @@ static void raster(const hop_oracle_render_params *p, const float *V, const int3
         const long long e1 = (SX[i0] - SX[i2]) * (py - SY[i2]) - (SY[i0] - SY[i2]) * (px - SX[i2]);
         const long long e2 = (SX[i1] - SX[i0]) * (py - SY[i0]) - (SY[i1] - SY[i0]) * (px - SX[i0]);
         if (e0 < 0 || e1 < 0 || e2 < 0) continue;
-        const double iz = (((double)e0 * iz0 + (double)e1 * iz1) + (double)e2 * iz2) / (double)area;
-        const float z = (float)(1.0 / iz);
+        const double iz = fma((double)e2, w2, fma((double)e1, w1, (double)e0 * w0));
+        const float z = 1.0f / (float)iz;
         if (!(z > p->z_near && z < p->z_far)) continue;   /* clipped by the near / far planes */
         float *dst = zbuf + (size_t)y * W + x;
         if (z < *dst) *dst = z;
