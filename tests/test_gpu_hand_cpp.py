@@ -52,14 +52,14 @@ def _hand(seed=1):
     links, tf_parent, parent = {}, {}, {}
     for name in ("finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2"):
         links[name] = synth.make_finger_cloud(900, seed=seed + len(links), size=size)
-    bp, bn = synth._cuboid(rng, 1500, 0.06, 0.10, 0.02)
+    bp, bn = synth._cuboid(rng, 1500, 0.06, 0.13, 0.02)
     links["base_link"] = ((bp + [-0.09, 0.0, 0.035]).astype(np.float32), bn.astype(np.float32))
-    left = np.eye(4); left[:3, 3] = [-0.15, -0.04, 0.02]
-    right = np.eye(4); right[:3, :3] = np.diag([-1.0, -1.0, 1.0]); right[:3, 3] = [-0.15, 0.04, 0.02]
+    left = np.eye(4); left[:3, 3] = [-0.15, -0.055, 0.02]
+    right = np.eye(4); right[:3, :3] = np.diag([-1.0, -1.0, 1.0]); right[:3, 3] = [-0.15, 0.055, 0.02]
     out = np.eye(4); out[:3, 3] = [0, 0, -0.06]
     tf_parent.update(finger_1_1=left, finger_1_2=out, finger_2_1=right, finger_2_2=out, base_link=np.eye(4))
     parent.update(finger_1_1="base_link", finger_1_2="finger_1_1", finger_2_1="base_link", finger_2_2="finger_2_1", base_link="base_link")
-    truth = dict(finger_1_1=15.0, finger_1_2=10.0, finger_2_1=12.0, finger_2_2=8.0)
+    truth = dict(finger_1_1=10.0, finger_1_2=6.0, finger_2_1=8.0, finger_2_2=5.0)   # the tips stay > gripper_min_dist apart, around the object
     in_hb = {"base_link": np.eye(4)}
     for f in ("1", "2"):
         in_hb[f"finger_{f}_1"] = tf_parent[f"finger_{f}_1"] @ _rotx(truth[f"finger_{f}_1"])
@@ -103,7 +103,7 @@ def test_cpp_hand_chain_recovers_the_grasp(tmp_path):
         if l.startswith("tf_self "):
             _, name, c, s = l.split()
             got = np.rad2deg(np.arctan2(float(s), float(c)))
-            assert abs(got - truth[name]) < 2.5, (name, got, truth[name])
+            assert abs(got - truth[name]) < 3.0, (name, got, truth[name])
     k = lines.index("handbase_in_cam")
     hic_out = np.array([[float(v) for v in l.split()] for l in lines[k + 1:k + 5]])
     assert np.abs(hic_out - hic).max() < 6e-3                      # no spurious height correction beyond one 5 mm step
