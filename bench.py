@@ -354,7 +354,8 @@ def main():
                          "launches": int(corr_n),
                          "note": "algorithmic = 32 B x (N_scene + N_model) per executed ICP iteration per hypothesis (the brute-force "
                                  "streaming model of SURVEY 8d); the kernel itself gathers from an L2-resident voxel grid, so real DRAM "
-                                 "traffic (`traffic`, ncu) is far below it"},
+                                 "traffic (`traffic`, ncu) is far below it; what bounds it is the L1TEX pipe (81.7 % of peak at the headline "
+                                 "size, profiles/r01_ncu_icp_fused_kernel_headline.txt)"},
         }
         if world == 1 and not args.no_cpu_baseline:
             # bounded sample of the same workload: whole frames' batches (or the first hypotheses of one) for >= ~10 s of CPU work
