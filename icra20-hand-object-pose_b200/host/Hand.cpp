@@ -1,6 +1,8 @@
 // Hand.cpp -- see Hand.h.  Host glue only: kinematics, thresholds and the reference's accept / reject rules; the clouds live on the device.
 #include "Hand.h"
 
+#include "urdf.h"
+
 #include <algorithm>
 #include <cfloat>
 #include <cmath>
@@ -72,6 +74,34 @@ void Hand::addComponent(const std::string &name, const std::string &parent_name,
   auto it = d_clouds.find(name);
   if (it != d_clouds.end()) hop_cloud_free(ctx, it->second);
   d_clouds[name] = d;
+}
+
+bool Hand::parseURDF(const std::string &urdf_path, std::string *err) {
+  std::vector<UrdfLink> links;
+  std::string e;
+  if (!parseUrdfLinks(urdf_path, links, &e)) { if (err) *err = e; return false; }
+  for (const UrdfLink &L : links) {
+    const std::string &name = L.name;
+    Cloud cloud;
+    const std::string cloud_path = cfg->yml["Hand"][name]["cloud"].as<std::string>(std::string());
+    if (cloud_path.empty() || !loadPLYFile(cloud_path, cloud, &e) || cloud.size() == 0) { if (err) *err = "Hand." + name + ".cloud: " + (cloud_path.empty() ? "not configured" : e); return false; }
+    for (size_t i = 0; i < cloud.size(); ++i) for (int k = 0; k < 3; ++k) cloud.xyz[3 * i + k] *= L.scale[k];
+    Cloud moved;
+    transformPointCloudWithNormals(cloud, moved, L.tf_init);   // "component init pose must be applied at beginning according to URDF"
+    for (const char *kind : {"mesh", "convex_mesh"}) {
+      const std::string mp = cfg->yml["Hand"][name][kind].as<std::string>(std::string());
+      LinkMesh lm;
+      if (mp.empty() || !loadOBJMesh(mp, lm.V, lm.F, nullptr)) continue;   // meshes feed the physics / render stages only
+      for (size_t i = 0; i + 2 < lm.V.size(); i += 3) {
+        const float x = lm.V[i] * L.scale[0], y = lm.V[i + 1] * L.scale[1], z = lm.V[i + 2] * L.scale[2];
+        for (int r = 0; r < 3; ++r) lm.V[i + r] = L.tf_init(r, 0) * x + L.tf_init(r, 1) * y + L.tf_init(r, 2) * z + L.tf_init(r, 3);
+      }
+      (std::string(kind) == "mesh" ? _meshes : _convex_meshes)[name] = lm;
+    }
+    std::printf("adding component name:%s\n", name.c_str());
+    addComponent(name, L.parent, moved, L.tf_in_parent);
+  }
+  return !_clouds.empty();
 }
 
 void Hand::getTFHandBase(std::string cur_name, Mat4f &tf_in_handbase) const {

@@ -34,6 +34,12 @@ class Hand {
   ~Hand();
   // Hand::addComponent (Hand.cpp:526-535): the link cloud is downsampled to 5 mm like the reference
   void addComponent(const std::string &name, const std::string &parent_name, const Cloud &cloud, const Mat4f &tf_in_parent);
+  // Hand::parseURDF (Hand.cpp:375-502): every <link> (except the rails) becomes a component -- cloud from Hand.<name>.cloud scaled by
+  // the visual mesh scale and moved by the visual origin, pose in the parent from the <joint> whose child it is.  Convex meshes
+  // (Hand.<name>.convex_mesh, same scale and origin) are collected for PoseEstimator::registerHandMesh.  False when a file is missing.
+  bool parseURDF(const std::string &urdf_path, std::string *err = nullptr);
+  struct LinkMesh { std::vector<float> V; std::vector<int32_t> F; };
+  std::map<std::string, LinkMesh> _convex_meshes, _meshes;   // link frame
   void getTFHandBase(std::string cur_name, Mat4f &tf_in_handbase) const;
   // scene_organized: the whole frame's cloud (camera frame, normals) for handbaseICP; scene_hand_region: the cropped hand region
   void setCurScene(const Cloud &scene_organized, const Cloud &scene_hand_region, const Mat4f &handbase_in_cam);

@@ -1,7 +1,8 @@
 // hand_demo -- drives the C++ Hand class (Hand.h) the way main_realdata_auto.cpp:100-148 drives HandT42, on inputs read from a
 // directory (the hand's URDF / link clouds do not ship with the reference; the test-suite writes synthetic ones):
 //     hand_demo <config.yaml> <dir>
-//   <dir>/links.txt            one link per line: name parent cloud.ply t00 t01 ... t33 (tf_in_parent, row-major)
+//   <dir>/links.txt            one link per line: name parent cloud.ply t00 t01 ... t33 (tf_in_parent, row-major); not read when the
+//                              config names urdf_path + Hand.<link>.cloud (then Hand::parseURDF builds the hand like the reference)
 //   <dir>/scene_organized.ply  the frame's cloud (camera frame, normals)       <dir>/scene_hand_region.ply  the cropped hand region
 //   <dir>/handbase_in_cam.txt  4x4
 // Prints the four link searches, the corrected hand base and the hand-point removal; writes <dir>/object1.ply (x y z nx ny nz confidence).
@@ -24,9 +25,14 @@ int main(int argc, char **argv) {
   {
     Hand hand(&cfg, ctx);
     cfg.gripper_min_dist = cfg.yml["gripper_min_dist"].as<float>(0.03f);
+    const std::string urdf_path = cfg.yml["urdf_path"].as<std::string>(std::string());
+    if (!urdf_path.empty()) {   // the reference's way (Hand::Hand -> parseURDF, Hand.cpp:375-502): links, clouds and meshes named by the config
+      std::string err;
+      if (!hand.parseURDF(urdf_path, &err)) { printf("parseURDF: %s\n", err.c_str()); return 1; }
+    }
     std::ifstream lf(dir + "/links.txt");
     std::string line;
-    while (std::getline(lf, line)) {
+    while (urdf_path.empty() && std::getline(lf, line)) {
       std::istringstream ss(line);
       std::string name, parent, ply;
       if (!(ss >> name >> parent >> ply)) continue;

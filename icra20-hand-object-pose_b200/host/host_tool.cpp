@@ -16,6 +16,7 @@
 
 #include "ConfigParser.h"
 #include "cloud.h"
+#include "urdf.h"
 
 int main(int argc, char **argv) {
   if (argc < 3) return 2;
@@ -49,6 +50,18 @@ int main(int argc, char **argv) {
       unsigned long long sum = 0; uint16_t mn = 65535, mx = 0;
       for (uint16_t v : pix) { sum += v; mn = std::min(mn, v); mx = std::max(mx, v); }
       std::cout << w << " " << h << " " << sum << " " << mn << " " << mx << "\n";
+      return 0;
+    }
+    if (cmd == "urdf") {   // parseUrdfLinks: name parent | scale | tf_init rows | tf_in_parent rows, one link per line
+      std::vector<UrdfLink> links; std::string err;
+      if (!parseUrdfLinks(argv[2], links, &err)) { std::cout << err << "\n"; return 3; }
+      std::cout.precision(9);
+      for (const UrdfLink &L : links) {
+        std::cout << L.name << " " << (L.parent.empty() ? "-" : L.parent) << " " << L.scale[0] << " " << L.scale[1] << " " << L.scale[2];
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) std::cout << " " << L.tf_init(r, c);
+        for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) std::cout << " " << L.tf_in_parent(r, c);
+        std::cout << "\n";
+      }
       return 0;
     }
     if (cmd == "obj") {   // loadOBJMesh: vertex / face counts, index range, signed volume (orientation) and the first face

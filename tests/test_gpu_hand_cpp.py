@@ -80,11 +80,32 @@ def _hand(seed=1):
     return links, tf_parent, parent, truth, hic, cam_pts, cam_nrm, is_hand, hb_pts
 
 
+def _urdf(links, tf_parent, parent, out):
+    """the same hand as a URDF + Hand.<link>.cloud config entries (what Hand::parseURDF, Hand.cpp:375-502, reads): the link clouds are
+    stored in millimetres with a 0.001 mesh scale, the joint poses as xyz / rpy (the right finger's diag(-1,-1,1) is a yaw of pi)"""
+    xml, yml = ['<?xml version="1.0"?>', '<robot name="synthetic_hand">'], ["urdf_path: " + out + "/hand.urdf", "Hand:"]
+    for name, (x, n) in links.items():
+        _write_ply(out + f"/{name}_mm.ply", (x * 1000.0).astype(np.float32), n, binary=True)
+        xml.append(f'  <link name="{name}"><visual><origin xyz="0 0 0" rpy="0 0 0"/><geometry><mesh filename="{name}.STL" scale="0.001 0.001 0.001"/></geometry></visual></link>')
+        yml += [f"  {name}:", f"    cloud: {out}/{name}_mm.ply"]
+    xml.append('  <link name="rail_1"><visual><geometry><mesh filename="rail.STL"/></geometry></visual></link>')
+    for name, T in tf_parent.items():
+        if name == "base_link":
+            continue
+        yaw = np.arctan2(T[1, 0], T[0, 0])
+        xml.append(f'  <joint name="j_{name}" type="revolute"><parent link="{parent[name]}"/><child link="{name}"/>'
+                   f'<origin xyz="{T[0, 3]!r} {T[1, 3]!r} {T[2, 3]!r}" rpy="0 0 {yaw!r}"/><axis xyz="1 0 0"/></joint>')
+    xml.append("</robot>")
+    open(out + "/hand.urdf", "w").write("\n".join(xml) + "\n")
+    return "\n".join(yml) + "\n"
+
+
 @pytest.mark.skipif(not os.path.exists(DEMO), reason="hand_demo not built")
-def test_cpp_hand_chain_recovers_the_grasp(tmp_path):
+@pytest.mark.parametrize("source", ["links", "urdf"])
+def test_cpp_hand_chain_recovers_the_grasp(tmp_path, source):
     links, tf_parent, parent, truth, hic, cam_pts, cam_nrm, is_hand, hb_pts = _hand()
     out = str(tmp_path)
-    (tmp_path / "cfg.yaml").write_text(CFG.format(out=out))
+    (tmp_path / "cfg.yaml").write_text(CFG.format(out=out) + (_urdf(links, tf_parent, parent, out) if source == "urdf" else ""))
     np.savetxt(out + "/eye.txt", np.eye(4))
     np.savetxt(out + "/handbase_in_cam.txt", hic)
     with open(out + "/links.txt", "w") as f:

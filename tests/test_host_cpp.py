@@ -204,6 +204,66 @@ def test_voxel_grid_and_ply_io(tmp_path, binary):
     assert np.abs(got[:, :3] - ref_p).max() < 1e-6 and np.abs(got[:, 3:6] - ref_n).max() < 1e-5
 
 
+URDF = """<?xml version="1.0"?>
+<!-- a T42-like hand: the subset Hand::parseURDF reads -->
+<robot name="hand">
+  <link name="base_link">
+    <visual><origin xyz="0 0 0" rpy="0 0 0"/><geometry><mesh filename="package://x/base.STL" scale="0.001 0.001 0.001"/></geometry></visual>
+  </link>
+  <link name="rail_1"><visual><geometry><box size="1 1 1"/></geometry></visual></link>
+  <link name="finger_1_1">
+    <visual>
+      <origin xyz="0.01 -0.02 0.03" rpy="0.1 -0.2 1.5707963"/>
+      <geometry><mesh filename='f11.STL' scale="1 2 3"/></geometry>
+    </visual>
+    <collision><geometry><box size="1 1 1"/></geometry></collision>
+  </link>
+  <link name="finger_1_2"><visual><geometry><mesh filename="f12.STL"/></geometry></visual></link>
+  <joint name="j1" type="revolute">
+    <parent link="base_link"/> <child link="finger_1_1"/>
+    <origin xyz="-0.15 -0.04 0.02" rpy="3.1415926 0 0.5"/> <axis xyz="1 0 0"/>
+  </joint>
+  <joint name="j2" type="revolute"><origin rpy="0 0.3 0" xyz="0 0 -0.06"/><parent link="finger_1_1"/><child link="finger_1_2"/></joint>
+</robot>
+"""
+
+
+@needs_tool
+def test_urdf_reader_matches_elementtree(tmp_path):
+    """the built-in XML-subset reader + parseUrdfLinks (what Hand::parseURDF reads, Hand.cpp:375-502) against xml.etree + scipy"""
+    import xml.etree.ElementTree as ET
+    from scipy.spatial.transform import Rotation
+    (tmp_path / "hand.urdf").write_text(URDF)
+    rc, out = _tool("urdf", tmp_path / "hand.urdf")
+    assert rc == 0, out
+    rows = [l.split() for l in out.strip().split("\n")]
+    assert [r[0] for r in rows] == ["base_link", "finger_1_1", "finger_1_2"]          # the rail is skipped
+    root = ET.fromstring(URDF)
+
+    def pose(el):
+        T = np.eye(4)
+        if el is not None:
+            rpy = [float(v) for v in el.get("rpy", "0 0 0").split()]
+            T[:3, :3] = Rotation.from_euler("ZYX", [rpy[2], rpy[1], rpy[0]]).as_matrix()   # Rz(yaw) Ry(pitch) Rx(roll)
+            T[:3, 3] = [float(v) for v in el.get("xyz", "0 0 0").split()]
+        return T
+    for r in rows:
+        name, parent = r[0], r[1]
+        vals = np.array([float(v) for v in r[2:]])
+        link = [l for l in root.findall("link") if l.get("name") == name][0]
+        joint = [j for j in root.findall("joint") if j.find("child").get("link") == name]
+        assert parent == (joint[0].find("parent").get("link") if joint else "-")
+        mesh = link.find("visual/geometry/mesh")
+        scale = [float(v) for v in mesh.get("scale", "1 1 1").split()]
+        assert np.allclose(vals[:3], scale)
+        assert np.abs(vals[3:19].reshape(4, 4) - pose(link.find("visual/origin"))).max() < 1e-6
+        assert np.abs(vals[19:35].reshape(4, 4) - pose(joint[0].find("origin") if joint else None)).max() < 1e-6
+    for bad in ("<robot><link name='a'></robot>", "<robot><link name=a/></robot>", "<robot>", "no xml at all"):
+        (tmp_path / "bad.urdf").write_text(bad)
+        assert _tool("urdf", tmp_path / "bad.urdf")[0] == 3
+    assert _tool("urdf", tmp_path / "missing.urdf")[0] == 3
+
+
 @needs_tool
 def test_obj_mesh_reader(tmp_path):
     """loadOBJMesh (igl::readOBJ stand-in of SDFchecker::registerMesh): plain, v/vt/vn and negative indices, quads fanned"""
