@@ -92,9 +92,9 @@ def _urdf(links, tf_parent, parent, out):
     for name, T in tf_parent.items():
         if name == "base_link":
             continue
-        yaw = np.arctan2(T[1, 0], T[0, 0])
+        yaw = float(np.arctan2(T[1, 0], T[0, 0]))
         xml.append(f'  <joint name="j_{name}" type="revolute"><parent link="{parent[name]}"/><child link="{name}"/>'
-                   f'<origin xyz="{T[0, 3]!r} {T[1, 3]!r} {T[2, 3]!r}" rpy="0 0 {yaw!r}"/><axis xyz="1 0 0"/></joint>')
+                   f'<origin xyz="{float(T[0, 3])!r} {float(T[1, 3])!r} {float(T[2, 3])!r}" rpy="0 0 {yaw!r}"/><axis xyz="1 0 0"/></joint>')
     xml.append("</robot>")
     open(out + "/hand.urdf", "w").write("\n".join(xml) + "\n")
     return "\n".join(yml) + "\n"
