@@ -207,7 +207,8 @@ def main():
             fi = (k * FPS + f) % N_FRAMES
             d_pose.copy_(d_hyp[fi])  # ICP refines in place; keep the inputs pristine (device-to-device, 64 KB per 1024)
             sc = scenes[fi]
-            sc.drop_nn()  # the scene's reciprocal-NN grid is per-frame work: rebuilt inside the timed step
+            sc.drop_nn()  # the scene's reciprocal-NN grid is per-frame work: rebuilt inside the timed step ...
+            sc.prepare_lcp_scene(lcp_p)  # ... on the context's second stream, while the ICP runs (the LCP kernel waits for it)
             ctx.icp_refine_dev(sc, model, d_pose.data_ptr(), H, icp_p, d_iters.data_ptr(), d_conv.data_ptr())
             if evs and f == 0: evs[1].record(stream)
             ctx.lcp_score_dev(sc, model, d_pose.data_ptr(), H, lcp_p, d_score.data_ptr())
@@ -289,6 +290,7 @@ def main():
             p = pin[(k * FPS + f) % N_FRAMES]
             p["work"][...] = p["hyp"]
             ctx._check(ctx.L.hop_cloud_update(ctx.h, e2e_scene.handle, ptr(p["xyz"]), ptr(p["nrm"]), ptr(p["conf"]), ns))
+            e2e_scene.prepare_lcp_scene(lcp_p)
             ctx._check(ctx.L.hop_icp_refine(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(icp_p), ptr(p["iters"]), ptr(p["conv"])))
             ctx._check(ctx.L.hop_lcp_score(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(lcp_p), 0, ptr(p["scores"])))
             best.append(int(np.argmax(p["scores"])))  # selectBest's arg-max on the host, like the reference

@@ -75,6 +75,7 @@ __global__ void repack_cloud_kernel(const float *__restrict__ xyz, const float *
 
 int cloud_fill(hop_ctx *ctx, hop_cloud *c, const float *xyz, const float *nrm, const float *prob, int n) {
   if (n < 0 || (n > 0 && !xyz)) { ctx->err = "hop_cloud: bad arguments"; return HOP_EINVAL; }
+  hop_cloud_join_pending(ctx, c);
   const int n_padded = std::max(HOP_TILE_PTS, (n + HOP_TILE_PTS - 1) / HOP_TILE_PTS * HOP_TILE_PTS);
   if (n_padded > c->capacity) {
     cudaStreamSynchronize(ctx->stream);
@@ -126,6 +127,7 @@ int cloud_fill(hop_ctx *ctx, hop_cloud *c, const float *xyz, const float *nrm, c
 // capacity for n points, no contents (the caller fills d_pw / d_nv on the device and sets the bounding box)
 int hop_cloud_reserve(hop_ctx *ctx, hop_cloud *c, int n) {
   if (n < 0) return HOP_EINVAL;
+  hop_cloud_join_pending(ctx, c);
   const int n_padded = std::max(HOP_TILE_PTS, (n + HOP_TILE_PTS - 1) / HOP_TILE_PTS * HOP_TILE_PTS);
   if (n_padded > c->capacity) {
     cudaStreamSynchronize(ctx->stream);
@@ -185,6 +187,9 @@ void hop_destroy(hop_ctx *ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->s4_scene) { hop_cloud_free(ctx, ctx->s4_scene); ctx->s4_scene = nullptr; }
+  if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  cudaFree(ctx->d_side_scratch);
   cudaFree(ctx->d_scratch);
   cudaFree(ctx->d_work);
   cudaFree(ctx->d_io);
@@ -201,6 +206,7 @@ const char *hop_last_error(const hop_ctx *ctx) { return ctx ? ctx->err.c_str() :
 int hop_set_stream(hop_ctx *ctx, void *cuda_stream) {
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->side) HOP_CUDA(ctx, cudaStreamSynchronize(ctx->side));
   if (cuda_stream) {
     if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
     ctx->stream = (cudaStream_t)cuda_stream;
@@ -307,6 +313,7 @@ int hop_cloud_update(hop_ctx *ctx, hop_cloud *cloud, const float *xyz, const flo
 int hop_cloud_free(hop_ctx *ctx, hop_cloud *cloud) {
   if (!cloud) return HOP_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
+  if (ctx && ctx->side) cudaStreamSynchronize(ctx->side);
   for (NNGridHost *g : cloud->grids) hop_free_nn_grid(g);
   cudaFree(cloud->d_pw); cudaFree(cloud->d_nv); cudaFree(cloud->d_stage); cudaFree(cloud->d_pw_q); cudaFree(cloud->d_nv_q);
   delete cloud;

@@ -193,6 +193,8 @@ struct NNGridHost {
   unsigned int *d_info = nullptr;  // device: [0] max list length [1] entries [2] overflow flag
   int64_t n_vox = 0, n_cand = 0, cap_vox = 0, cap_cand = 0;
   int max_list = 0;
+  cudaEvent_t ready = nullptr;     // recorded on the side stream by hop_cloud_prepare_nn_async
+  bool pending = false;            // built on the side stream; the first consumer on the main stream waits for `ready`
 };
 
 struct hop_cloud {
@@ -238,6 +240,10 @@ struct hop_ctx {
   void *ensure_work(size_t bytes);
   void *ensure_io(size_t bytes);
   void *ensure_pinned(size_t bytes);
+  // hop_cloud_prepare_nn_async: a second stream (with its own scratch) on which a frame's scene grid is built while the main
+  // stream runs the stages that do not need it
+  cudaStream_t side = nullptr; cudaEvent_t ev_fork = nullptr;
+  void *d_side_scratch = nullptr; size_t side_scratch_bytes = 0;
   hop_cloud *s4_scene = nullptr;   // hop_super4pcs_run: the centred scene of the current frame (buffers reused across frames)
 };
 
@@ -262,6 +268,12 @@ struct ProfScope {
       return HOP_ECUDA;                                                                                \
     }                                                                                                  \
   } while (0)
+
+// the main stream waits for the cloud's grids still being built on the side stream (before the cloud's contents change)
+inline void hop_cloud_join_pending(hop_ctx *ctx, hop_cloud *c) {
+  for (NNGridHost *G : c->grids)
+    if (G->pending) { cudaStreamWaitEvent(ctx->stream, G->ready, 0); G->pending = false; }
+}
 
 // implemented in nn_grid.cu
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);

@@ -219,6 +219,7 @@ void hop_free_nn_grid(NNGridHost *g) {
   cudaFree(g->d_cell);
   cudaFree(g->d_cand);
   cudaFree(g->d_info);
+  if (g->ready) cudaEventDestroy(g->ready);
   delete g;
 }
 
@@ -332,7 +333,15 @@ static int grid_fetch_stats(hop_ctx *ctx, NNGridHost *G) {
 }
 
 // cache lookup: a grid built for radius r serves any query radius <= r; rebuilt when the cloud changed
+static int get_nn_grid_on_current_stream(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
+
 int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
+  // a rebuild on this stream must come after a build of the same grid still running on the side stream
+  if (ctx->side && ctx->stream != ctx->side) hop_cloud_join_pending(ctx, cloud);
+  return get_nn_grid_on_current_stream(ctx, cloud, radius, voxel, out);
+}
+
+static int get_nn_grid_on_current_stream(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
   for (size_t i = 0; i < cloud->grids.size(); ++i) {
     NNGridHost *G = cloud->grids[i];
     if (std::fabs(G->radius - radius) <= 1e-9f + 1e-6f * radius && (voxel <= 0.f || std::fabs(G->voxel - voxel) < 1e-9f)) {
@@ -365,6 +374,36 @@ extern "C" int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius
     stats[0] = G->n_vox; stats[1] = G->n_cand; stats[2] = G->max_list;
     stats[3] = G->n_vox * (int64_t)sizeof(uint2) + G->n_cand * (int64_t)sizeof(float4);
   }
+  return HOP_OK;
+}
+
+// Builds (or refreshes) the cloud's grid for `radius` on the context's side stream: ordered after everything enqueued on the main
+// stream so far (the cloud's upload, the last consumers of the grid's previous contents), concurrent with whatever the main
+// stream is given next.  The first main-stream call that looks the grid up waits for it (hop_get_nn_grid).
+extern "C" int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel) {
+  if (!ctx || !cloud) return HOP_EINVAL;
+  if (!ctx->side) {
+    HOP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
+    HOP_CUDA(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  }
+  hop_cloud_join_pending(ctx, cloud);
+  HOP_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+  HOP_CUDA(ctx, cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0));
+  cudaStream_t main_stream = ctx->stream;
+  ctx->stream = ctx->side;
+  std::swap(ctx->d_scratch, ctx->d_side_scratch); std::swap(ctx->scratch_bytes, ctx->side_scratch_bytes);
+  NNGridHost *G = nullptr;
+  int rc = get_nn_grid_on_current_stream(ctx, cloud, radius, voxel, &G);
+  cudaError_t e = cudaSuccess;
+  if (rc == HOP_OK) {
+    if (!G->ready) e = cudaEventCreateWithFlags(&G->ready, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventRecord(G->ready, ctx->side);
+    G->pending = (e == cudaSuccess);
+  }
+  std::swap(ctx->d_scratch, ctx->d_side_scratch); std::swap(ctx->scratch_bytes, ctx->side_scratch_bytes);
+  ctx->stream = main_stream;
+  if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, e);
   return HOP_OK;
 }
 

@@ -141,6 +141,7 @@ def load_library():
     L.hop_cloud_free.argtypes = [_vp, _vp]
     L.hop_cloud_size.argtypes = [_vp]
     L.hop_cloud_prepare_nn.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_int64)]
+    L.hop_cloud_prepare_nn_async.argtypes = [_vp, _vp, C.c_float, C.c_float]
     L.hop_cloud_drop_nn.argtypes = [_vp, _vp]
     L.hop_cloud_nn_query.argtypes = [_vp, _vp, C.c_float, _vp, C.c_int, _vp, _vp]
     L.hop_icp_refine.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
@@ -321,6 +322,14 @@ class Cloud:
         stats = (C.c_int64 * 4)()
         self.ctx._check(self.ctx.L.hop_cloud_prepare_nn(self.ctx.h, self.handle, radius, voxel, stats))
         return {"voxels": stats[0], "entries": stats[1], "max_list": stats[2], "bytes": stats[3]}
+
+    def prepare_nn_async(self, radius, voxel=0.0):
+        """hop_cloud_prepare_nn_async: the grid is built on the context's second stream while the main stream goes on."""
+        self.ctx._check(self.ctx.L.hop_cloud_prepare_nn_async(self.ctx.h, self.handle, radius, voxel))
+
+    def prepare_lcp_scene(self, lcp_params):
+        """the scene grid hop_lcp_score's reciprocal term needs (radius lcp.dist * 1.01f, api.cu), built ahead on the second stream"""
+        self.prepare_nn_async(float(np.float32(lcp_params.dist) * np.float32(1.01)))
 
     def drop_nn(self):
         self.ctx._check(self.ctx.L.hop_cloud_drop_nn(self.ctx.h, self.handle))

@@ -112,6 +112,8 @@ class PoseEstimator:
             return
         poses = np.stack([h._pose for h in keep])
         params = self.ctx.icp_params(max_iter=10, angle_deg=self.icp_angle_thres, max_dist=self.icp_dist_thres)
+        # the scene grid selectBest's computeLCP needs depends on the frame only: built on the second stream while the ICP runs
+        self._scene.prepare_lcp_scene(self.ctx.lcp_params(dist=self.lcp_dist, angle_deg=self.lcp_normal_angle))
         refined, _, _ = self.ctx.icp_refine(self._scene, self._model, poses, params)
         for h, p in zip(keep, refined):
             h._pose = p

@@ -213,6 +213,8 @@ void PoseEstimator::refineByICP() {
   hop_default_icp_params(&p);   // 10 iterations, abs MSE 1e-6 (Utils.cpp:207-208; PoseEstimator.cpp:266)
   p.angle_deg = cfg->yml["icp_angle_thres"].as<float>(45.f);
   p.max_dist = cfg->yml["icp_dist_thres"].as<float>(0.01f);
+  // the scene grid selectBest's computeLCP needs depends on the frame only: built on the context's second stream while the ICP runs
+  check(hop_cloud_prepare_nn_async(ctx, d_scene, cfg->yml["lcp"]["dist"].as<float>(0.001f) * 1.01f, 0.f), "hop_cloud_prepare_nn_async");
   check(hop_icp_refine(ctx, d_scene, d_model, poses.data(), (int)n, &p, nullptr, nullptr), "hop_icp_refine");
   for (size_t i = 0; i < n; ++i) std::memcpy(_pose_hypos[i]._pose.data(), &poses[16 * i], 64);
 }

@@ -131,6 +131,12 @@ int hop_cloud_size(const hop_cloud *cloud);
  * caller can pay the per-model cost up front.  stats (may be NULL): [0]=voxels [1]=candidate entries
  * [2]=max list length [3]=bytes. */
 int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, int64_t *stats);
+/* The same build on a second stream of the context: ordered after everything enqueued so far, concurrent with what is enqueued
+ * next; the first entry point that needs the grid waits for it on the device (no host synchronisation).  The scene kd-tree that
+ * Utils::computeLCP builds on every call (Utils.cpp:378-379) depends on the frame only, not on the hypotheses:
+ * hop_cloud_prepare_nn_async(scene, lcp.dist * 1.01f, 0) right after the upload (PoseEstimator::setCurScene) lets hop_lcp_score's
+ * scene grid be built while hop_icp_refine runs.  Results are identical to the implicit build. */
+int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel);
 /* mark the cloud's cached grids stale (allocations are kept): the next use rebuilds them */
 int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud);
 /* exact 1-NN of host queries (nq x 3) within the prepared radius: idx = -1 when none. (test / debug entry) */
