@@ -82,6 +82,73 @@ __global__ void __launch_bounds__(1024, 1) topk_kernel(const float *__restrict__
   }
 }
 
+// The common case (the scores fit in shared memory, K <= 128) without a block barrier per winner: the 32 warps first extract, each
+// on its own, the top K of the elements they own (K warp-wide arg-max rounds over the staged scores), then warp 0 merges the 32
+// sorted candidate lists (lane l holds the head of warp l's list).  Scores are staged as order-preserving 32-bit keys (0 = taken /
+// exhausted, below every real key) so that a warp-wide arg-max is two redux.sync instructions -- the largest key, then the lowest
+// index holding it -- instead of a ten-shuffle butterfly.  Same total order (score descending, ties -> lower id; NaN = -inf;
+// -0 = +0), same records.
+__device__ __forceinline__ unsigned int topk_key(float v) {
+  if (!(v == v)) v = -INFINITY;   // NaN scores never win
+  if (v == 0.f) v = 0.f;          // -0 and +0 tie (as in a float comparison)
+  const unsigned int u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);   // >= 0x007fffff (-inf): never 0
+}
+// every lane brings its best (key, index) (key 0 = nothing); returns the warp's winner index or -1, its key in `key`
+__device__ __forceinline__ int topk_warp_argmax(unsigned int &key, int idx) {
+  const unsigned int m = __reduce_max_sync(0xffffffffu, key);
+  const int w = __reduce_min_sync(0xffffffffu, (key == m) ? idx : 0x7fffffff);
+  key = m;
+  return m != 0u ? w : -1;
+}
+__global__ void __launch_bounds__(1024, 1) topk_lists_kernel(const float *__restrict__ poses, const float *__restrict__ scores, int H,
+                                                            int K, int32_t id_offset, int32_t frame, hop_pose_rec *__restrict__ out) {
+  extern __shared__ unsigned int s_dyn[];
+  __shared__ int s_win[128];
+  const int KS = K | 1;                                      // odd list stride: the merge's 32 heads fall into 32 banks
+  unsigned int *s_key = s_dyn;                               // H, padded to a multiple of 32
+  unsigned int *c_key = s_dyn + ((H + 31) & ~31);            // 32 lists x KS
+  int *c_idx = reinterpret_cast<int *>(c_key + 32 * KS);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  for (int i = tid; i < H; i += 1024) s_key[i] = topk_key(scores[i]);   // a warp only ever touches the elements it stages here
+  __syncwarp();
+  for (int k = 0; k < K; ++k) {
+    unsigned int bk = 0u;
+    int bi = 0x7fffffff;
+    for (int i = tid; i < H; i += 1024) {
+      const unsigned int v = s_key[i];
+      if (v > bk) { bk = v; bi = i; }  // ascending i: first (lowest id) wins ties
+    }
+    const int w = topk_warp_argmax(bk, bi);
+    if (lane == 0) {
+      c_key[warp * KS + k] = bk; c_idx[warp * KS + k] = w;
+      if (w >= 0) s_key[w] = 0u;
+    }
+    __syncwarp();
+  }
+  __syncthreads();
+  if (warp == 0) {
+    int head = 0;
+    for (int k = 0; k < K; ++k) {
+      unsigned int bk = head < K ? c_key[lane * KS + head] : 0u;
+      const int mine = (head < K && bk != 0u) ? c_idx[lane * KS + head] : 0x7fffffff;
+      const int w = topk_warp_argmax(bk, mine);
+      if (w >= 0 && mine == w) ++head;
+      if (lane == 0) s_win[k] = w;
+    }
+  }
+  __syncthreads();
+  for (int t = tid; t < 20 * K; t += 1024) {
+    const int k = t / 20, f = t - 20 * k, b = s_win[k];
+    float *rec = reinterpret_cast<float *>(out + k);
+    if (f < 16) rec[f] = b >= 0 ? poses[16 * (size_t)b + f] : ((f % 5 == 0) ? 1.f : 0.f);
+    else if (f == 16) rec[16] = b >= 0 ? scores[b] : -INFINITY;
+    else if (f == 17) reinterpret_cast<int32_t *>(rec)[17] = b >= 0 ? b + id_offset : -1;
+    else if (f == 18) reinterpret_cast<int32_t *>(rec)[18] = frame;
+    else reinterpret_cast<int32_t *>(rec)[19] = 0;
+  }
+}
+
 }  // namespace
 
 int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset, int32_t frame,
@@ -94,7 +161,13 @@ int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, i
   if (!taken) { ctx->err = "topk: scratch allocation failed"; return HOP_ENOMEM; }
   ProfScope ps(ctx, HOP_PROF_TOPK);
   const size_t smem = sizeof(float) * (size_t)H;
-  if (smem <= 200 * 1024) {
+  const size_t smem_lists = sizeof(float) * (size_t)((H + 31) & ~31) + 8 * (size_t)32 * (size_t)(K | 1);
+  static const bool rounds_only = getenv("HOP_TOPK_ROUNDS") != nullptr;   // the one-barrier-pair-per-winner kernel (A/B knob)
+  if (K <= 128 && smem_lists <= 200 * 1024 && !rounds_only) {
+    static bool attr_set = false;
+    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(topk_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    topk_lists_kernel<<<1, 1024, smem_lists, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out);
+  } else if (smem <= 200 * 1024) {
     static bool attr_set = false;
     if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
     topk_kernel<true><<<1, 1024, smem, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);

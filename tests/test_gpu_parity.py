@@ -210,6 +210,29 @@ def test_select_topk_order_and_ties(ctx):
     assert list(few["id"][3:]) == [-1, -1] and np.all(np.isneginf(few["score"][3:]))
 
 
+@pytest.mark.parametrize("H,K", [(1, 1), (31, 16), (33, 40), (1024, 16), (1025, 128), (4096, 16), (20000, 100), (45000, 128), (60000, 16), (500, 200)])
+def test_select_topk_sizes_nan_and_all_paths(ctx, H, K):
+    """every selection kernel (per-warp lists + merge, K rounds in shared memory, K rounds over global memory) against numpy:
+    heavy ties, NaN scores (never win, ordered last by id), -inf scores, K > H"""
+    rng = np.random.default_rng(H + K)
+    poses = rng.normal(size=(H, 4, 4)).astype(np.float32)
+    scores = rng.integers(0, max(2, H // 8), H).astype(np.float32)
+    scores[rng.random(H) < 0.05] = np.nan
+    scores[rng.random(H) < 0.02] = -np.inf
+    top = ctx.select_topk(poses, scores, K, id_offset=3, frame=2)
+    key = np.where(np.isnan(scores), -np.inf, scores)
+    order = np.lexsort((np.arange(H), -key))[:K]
+    n = len(order)
+    assert np.array_equal(top["id"][:n], order + 3)
+    assert np.array_equal(top["score"][:n], scores[order], equal_nan=True)
+    assert np.array_equal(top["pose"][:n], hop_colmajor(poses[order]))
+    assert np.all(top["id"][n:] == -1) and np.all(np.isneginf(top["score"][n:])) and np.all(top["frame"] == 2)
+
+
+def hop_colmajor(p):
+    return np.ascontiguousarray(np.transpose(p, (0, 2, 1))).reshape(len(p), 16)
+
+
 def test_pose_estimator_mirror_refine_and_select(ctx):
     """PoseEstimator::refineByICP + selectBest through the host mirror == the oracle's restatement of both."""
     import hop_b200
