@@ -228,8 +228,30 @@ URDF = """<?xml version="1.0"?>
 """
 
 
+URDF_TRICKY = """<?xml version="1.0" encoding="utf-8"?>
+<!DOCTYPE robot>
+<!-- <link name="ghost"/> inside a comment -->
+<robot name = "h" xmlns:xacro="http://www.ros.org/wiki/xacro">
+  <material name="grey"><color rgba="0.5 0.5 0.5 1"/></material>
+  <link name="base_link">
+    <inertial><mass value="1"/><origin xyz="9 9 9"/></inertial>
+    <visual>
+      <origin rpy = '0 0 0'   xyz="1e-3 -2E-3 .5"/>
+      <geometry><mesh filename="package://a/b&gt;c.STL" scale="0.001 0.001 0.001" /></geometry>
+      <material name="grey"/>
+    </visual>
+  </link>
+  <link name="finger_1_1"><visual><geometry><mesh filename="a>b.STL"/></geometry></visual>text &amp; more</link>
+  <joint name="j" type="revolute"><origin xyz="0 1 2"
+      rpy="0 0 1.5707963267948966"/><parent link="base_link"/><child link="finger_1_1"/><limit lower="0" upper="1"/></joint>
+</robot>
+"""
+
+
 @needs_tool
-def test_urdf_reader_matches_elementtree(tmp_path):
+@pytest.mark.parametrize("URDF,names", [(URDF, ["base_link", "finger_1_1", "finger_1_2"]), (URDF_TRICKY, ["base_link", "finger_1_1"])],
+                         ids=["t42_like", "declarations_comments_quotes_entities"])
+def test_urdf_reader_matches_elementtree(tmp_path, URDF, names):
     """the built-in XML-subset reader + parseUrdfLinks (what Hand::parseURDF reads, Hand.cpp:375-502) against xml.etree + scipy"""
     import xml.etree.ElementTree as ET
     from scipy.spatial.transform import Rotation
@@ -237,7 +259,7 @@ def test_urdf_reader_matches_elementtree(tmp_path):
     rc, out = _tool("urdf", tmp_path / "hand.urdf")
     assert rc == 0, out
     rows = [l.split() for l in out.strip().split("\n")]
-    assert [r[0] for r in rows] == ["base_link", "finger_1_1", "finger_1_2"]          # the rail is skipped
+    assert [r[0] for r in rows] == names                                               # the rail is skipped
     root = ET.fromstring(URDF)
 
     def pose(el):
