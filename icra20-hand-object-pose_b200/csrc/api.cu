@@ -372,6 +372,7 @@ int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const fl
   int rc = hop_get_nn_grid(ctx, model, params->dist, 0.f, &Gm);
   if (rc != HOP_OK) return rc;
   // the reciprocal neighbour is at most `dist` away (see lcp_score_kernel); a little head room for rounding
+  // (callers that prefetch this grid with hop_cloud_prepare_nn_async pass the same dist * 1.01f: hop_c_api.h, capi.py prepare_lcp_scene, PoseEstimator.cpp)
   rc = hop_get_nn_grid(ctx, scene, params->dist * 1.01f, 0.f, &Gs);
   if (rc != HOP_OK) return rc;
   rc = hop_cloud_query_order(ctx, scene);
