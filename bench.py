@@ -43,7 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
-    ap.add_argument("--solver", type=int, default=0, help="0 = exact per-iteration minimiser (parity path), 1 = Gauss-Newton")
+    ap.add_argument("--solver", type=int, default=0, help="0 = replay of the reference's LM (parity path), 1 = Gauss-Newton, 2 = exact per-iteration minimiser")
     ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
@@ -330,7 +330,7 @@ def main():
         e2e_value = world * FPS * H * args.steps / (e2e_ms * 1e-3)
         # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
         # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
-        fused = args.solver == 0
+        fused = args.solver != 1
         corr_ms, corr_n = prof["icp_fused" if fused else "icp_correspond"]
         corr_bytes = float(iters_sum) * 32.0 * (ns + nm)
         achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
@@ -342,7 +342,7 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": FPS, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
-                       "icp_solver": "exact" if args.solver == 0 else "gauss-newton", "mean_icp_iterations": iters_mean,
+                       "icp_solver": {0: "reference-lm-replay", 1: "gauss-newton", 2: "exact"}[args.solver], "mean_icp_iterations": iters_mean,
                        "nn_grid_icp": g_icp, "nn_grid_lcp": g_lcp,
                        "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps, "of": stage_note},
                        "kernel_ms": kernels},

@@ -1,6 +1,7 @@
 // api.cu -- the C ABI of libhop.so (include/hop_c_api.h): context, clouds, host/device entry points.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "hop_common.cuh"
@@ -164,6 +165,14 @@ int hop_create(int device, hop_ctx **out) {
   hop_ctx *ctx = new hop_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
+  {  // tuning knobs: read once here, never in a launch path
+    const char *v;
+    if ((v = getenv("HOP_FUSED_VARIANT"))) ctx->tune.fused_variant = atoi(v);
+    ctx->tune.fused_profile = getenv("HOP_FUSED_PROFILE") != nullptr;
+    if ((v = getenv("HOP_LCP_VARIANT"))) ctx->tune.lcp_variant = atoi(v);
+    if ((v = getenv("HOP_VOXEL_MAX_FRAC"))) ctx->tune.voxel_max_frac = (float)atof(v);
+    ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
+  }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) != cudaSuccess) {
     g_create_error = "hop_create: stream/counter allocation failed";
@@ -183,6 +192,7 @@ int hop_create(int device, hop_ctx **out) {
 }
 
 void hop_destroy(hop_ctx *ctx) {
+  HOP_ENTER(ctx);
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
@@ -195,6 +205,7 @@ void hop_destroy(hop_ctx *ctx) {
   cudaFree(ctx->d_io);
   cudaFreeHost(ctx->h_pinned);
   cudaFree(ctx->d_counter);
+  cudaFree(ctx->d_fused_prof);
   for (ProfSpan &s : ctx->spans) { cudaEventDestroy(s.a); cudaEventDestroy(s.b); }
   for (cudaEvent_t e : ctx->event_pool) cudaEventDestroy(e);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -204,6 +215,7 @@ void hop_destroy(hop_ctx *ctx) {
 const char *hop_last_error(const hop_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int hop_set_stream(hop_ctx *ctx, void *cuda_stream) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   if (ctx->side) HOP_CUDA(ctx, cudaStreamSynchronize(ctx->side));
@@ -219,6 +231,7 @@ int hop_set_stream(hop_ctx *ctx, void *cuda_stream) {
 }
 
 int hop_sync(hop_ctx *ctx) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
@@ -238,6 +251,7 @@ static int profile_collect(hop_ctx *ctx) {
 }
 
 int hop_profile_enable(hop_ctx *ctx, int on) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   int rc = profile_collect(ctx);
   if (rc != HOP_OK) return rc;
@@ -247,6 +261,7 @@ int hop_profile_enable(hop_ctx *ctx, int on) {
 }
 
 int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans) {
+  HOP_ENTER(ctx);
   if (!ctx || kind < 0 || kind >= HOP_PROF_KINDS) return HOP_EINVAL;
   int rc = profile_collect(ctx);
   if (rc != HOP_OK) return rc;
@@ -266,37 +281,44 @@ void hop_default_lcp_params(hop_lcp_params *p) {
 }
 
 int hop_malloc(hop_ctx *ctx, size_t bytes, void **dev_ptr) {
+  HOP_ENTER(ctx);
   if (!ctx || !dev_ptr) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaMalloc(dev_ptr, bytes ? bytes : 1));
   return HOP_OK;
 }
 int hop_free(hop_ctx *ctx, void *dev_ptr) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaFree(dev_ptr));
   return HOP_OK;
 }
 int hop_host_alloc(hop_ctx *ctx, size_t bytes, void **host_ptr) {
+  HOP_ENTER(ctx);
   if (!ctx || !host_ptr) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaHostAlloc(host_ptr, bytes ? bytes : 1, cudaHostAllocDefault));
   return HOP_OK;
 }
 int hop_host_free(hop_ctx *ctx, void *host_ptr) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaFreeHost(host_ptr));
   return HOP_OK;
 }
 int hop_memcpy_h2d(hop_ctx *ctx, void *dst_dev, const void *src_host, size_t bytes) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, ctx->stream));
   return HOP_OK;
 }
 int hop_memcpy_d2h(hop_ctx *ctx, void *dst_host, const void *src_dev, size_t bytes) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   HOP_CUDA(ctx, cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
   return HOP_OK;
 }
 
 int hop_cloud_upload(hop_ctx *ctx, const float *xyz, const float *nrm, const float *prob, int n, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx || !out) return HOP_EINVAL;
   hop_cloud *c = new hop_cloud();
   int rc = cloud_fill(ctx, c, xyz, nrm, prob, n);
@@ -306,11 +328,13 @@ int hop_cloud_upload(hop_ctx *ctx, const float *xyz, const float *nrm, const flo
 }
 
 int hop_cloud_update(hop_ctx *ctx, hop_cloud *cloud, const float *xyz, const float *nrm, const float *prob, int n) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud) return HOP_EINVAL;
   return cloud_fill(ctx, cloud, xyz, nrm, prob, n);
 }
 
 int hop_cloud_free(hop_ctx *ctx, hop_cloud *cloud) {
+  HOP_ENTER(ctx);
   if (!cloud) return HOP_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   if (ctx && ctx->side) cudaStreamSynchronize(ctx->side);
@@ -325,6 +349,7 @@ int hop_cloud_size(const hop_cloud *cloud) { return cloud ? cloud->n : 0; }
 // ---- K4 -------------------------------------------------------------------------------------------------------
 int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *d_poses_inout, int H, const hop_icp_params *params,
                        int32_t *d_iters_out, int32_t *d_converged_out) {
+  HOP_ENTER(ctx);
   if (!ctx || !scene || !model || !params || H < 0 || (H > 0 && !d_poses_inout)) { if (ctx) ctx->err = "hop_icp_refine: bad arguments"; return HOP_EINVAL; }
   if (H == 0) return HOP_OK;
   if (!(params->max_dist > 0.f)) { ctx->err = "hop_icp_refine: max_dist must be > 0"; return HOP_EINVAL; }
@@ -339,6 +364,7 @@ int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *
 
 int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *poses_inout, int H, const hop_icp_params *params,
                    int32_t *iters_out, int32_t *converged_out) {
+  HOP_ENTER(ctx);
   if (!ctx || (H > 0 && !poses_inout)) return HOP_EINVAL;
   if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
   const size_t pb = sizeof(float) * 16 * (size_t)H, ib = sizeof(int32_t) * (size_t)H;
@@ -361,6 +387,7 @@ int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *pose
 // ---- K5 -------------------------------------------------------------------------------------------------------
 int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H, const hop_lcp_params *params,
                       int use_weights, float *d_scores_out) {
+  HOP_ENTER(ctx);
   if (!ctx || !scene || !model || !params || H < 0 || (H > 0 && (!d_poses || !d_scores_out))) { if (ctx) ctx->err = "hop_lcp_score: bad arguments"; return HOP_EINVAL; }
   if (H == 0) return HOP_OK;
   if (!(params->dist > 0.f)) { ctx->err = "hop_lcp_score: dist must be > 0"; return HOP_EINVAL; }
@@ -383,6 +410,7 @@ int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const fl
 
 int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *poses, int H, const hop_lcp_params *params,
                   int use_weights, float *scores_out) {
+  HOP_ENTER(ctx);
   if (!ctx || (H > 0 && (!poses || !scores_out))) return HOP_EINVAL;
   if (H <= 0) return H == 0 ? HOP_OK : HOP_EINVAL;
   const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H;
@@ -400,12 +428,14 @@ int hop_lcp_score(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float 
 // ---- winners ---------------------------------------------------------------------------------------------------
 int hop_select_topk_dev(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset, int32_t frame,
                         hop_pose_rec *d_out) {
+  HOP_ENTER(ctx);
   if (!ctx || H < 0 || K < 0 || (K > 0 && !d_out) || (H > 0 && (!d_poses || !d_scores))) return HOP_EINVAL;
   return hop_launch_topk(ctx, d_poses, d_scores, H, K, id_offset, frame, d_out);
 }
 
 int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H, int K, int32_t id_offset, int32_t frame,
                     hop_pose_rec *out) {
+  HOP_ENTER(ctx);
   if (!ctx || H < 0 || K < 0 || (K > 0 && !out) || (H > 0 && (!poses || !scores))) return HOP_EINVAL;
   if (K == 0) return HOP_OK;
   const size_t pb = sizeof(float) * 16 * (size_t)H, sb = sizeof(float) * (size_t)H, rb = sizeof(hop_pose_rec) * (size_t)K;

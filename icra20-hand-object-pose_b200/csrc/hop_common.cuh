@@ -5,6 +5,7 @@
 #include <math.h>
 
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/hop_c_api.h"
@@ -217,8 +218,29 @@ struct hop_cloud {
 // per-kernel timing with CUDA events on the launching stream (hop_profile_*): bench.py's roofline source
 struct ProfSpan { int kind; cudaEvent_t a, b; };
 
+// tuning knobs (environment, read ONCE in hop_create; never in a launch path)
+struct HopTuning {
+  int fused_variant = 0;      // HOP_FUSED_VARIANT: 1 = 256-thread CTAs, 2 = 128-thread CTAs, 0 = by batch size
+  bool fused_profile = false; // HOP_FUSED_PROFILE: per-phase cycle accounting of icp_fused_kernel
+  int lcp_variant = 0;        // HOP_LCP_VARIANT: resident CTAs per SM of lcp_score_kernel
+  float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
+  bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
+};
+
 struct hop_ctx {
   int device = 0;
+  HopTuning tune;
+  // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a function: remembered per context (= per device),
+  // not per process, so a second context on another GPU opts its kernels in too
+  std::unordered_map<const void *, size_t> func_smem;
+  template <typename F> cudaError_t func_smem_optin(F *func, size_t bytes) {
+    size_t &have = func_smem[(const void *)func];
+    if (bytes <= have) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) have = bytes;
+    return e;
+  }
+  long long *d_fused_prof = nullptr;   // HOP_FUSED_PROFILE counters (this context's device)
   bool profiling = false;
   std::vector<ProfSpan> spans;
   std::vector<cudaEvent_t> event_pool;
@@ -259,6 +281,20 @@ struct ProfScope {
   }
   ~ProfScope() { if (idx >= 0) cudaEventRecord(ctx->spans[idx].b, ctx->stream); }
 };
+
+// Every extern "C" entry point that takes a context runs with the context's device current, whatever the caller (or torch)
+// left selected, and restores the caller's device on return.
+struct HopDeviceGuard {
+  int prev = -1; bool switched = false;
+  explicit HopDeviceGuard(const hop_ctx *c) {
+    if (!c) return;
+    if (cudaGetDevice(&prev) == cudaSuccess && prev != c->device) switched = cudaSetDevice(c->device) == cudaSuccess;
+  }
+  ~HopDeviceGuard() { if (switched) cudaSetDevice(prev); }
+  HopDeviceGuard(const HopDeviceGuard &) = delete;
+  HopDeviceGuard &operator=(const HopDeviceGuard &) = delete;
+};
+#define HOP_ENTER(ctx) HopDeviceGuard hop_device_guard_(ctx)
 
 #define HOP_CUDA(ctx, call)                                                                            \
   do {                                                                                                 \

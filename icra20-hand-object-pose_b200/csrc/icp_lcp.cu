@@ -27,6 +27,7 @@
 #include <utility>
 
 #include "hop_common.cuh"
+#include "lm_replay.cuh"
 
 namespace {
 
@@ -298,6 +299,32 @@ __device__ void solve_gn(const float *sums, float *R, float *t) {
 }
 
 
+// The reference's own solver (PCL's TransformationEstimationPointToPlane = float lmdif), replayed on the moments: see
+// lm_replay.cuh.  Called by all lanes of one warp; returns the increment W(x) in all lanes.
+__device__ __noinline__ void solve_lm_replay(const float *sums, int lane, float *R, float *t) {
+  lmr::MomentsDev A{sums, lane};
+  float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  lmr::lm_replay_solve(A, x, nullptr);
+  float y[13];
+  lmr::warp_y(x, y);
+#pragma unroll
+  for (int e = 0; e < 9; ++e) R[e] = (e % 4 == 0) ? 1.f + y[e] : y[e];   // exact: y = fl(R) - I
+  t[0] = x[0]; t[1] = x[1]; t[2] = x[2];
+}
+
+// SOLVER: 0 = replay of the reference's LM (parity path, default), 1 = one Gauss-Newton step, 2 = exact minimiser
+// Returns false when the reference's LM would run away along an unconstrained translation (lm_replay.cuh,
+// translation_unconstrained): the caller ends the ICP of the hypothesis "not converged", pose unchanged.
+template <int SOLVER>
+__device__ __forceinline__ bool solve_increment(const float *sums, int lane, float *R, float *t) {
+  if constexpr (SOLVER == 0) {
+    if (lmr::translation_unconstrained(lmr::MomentsDev{sums, lane})) return false;
+    solve_lm_replay(sums, lane, R, t);
+  } else if constexpr (SOLVER == 1) solve_gn(sums, R, t);
+  else solve_exact(sums, nullptr, lane, R, t);
+  return true;
+}
+
 // ------------------------------------------------------------------------------------------------------------
 // per-hypothesis ICP state (global memory, 128 bytes)
 // ------------------------------------------------------------------------------------------------------------
@@ -399,7 +426,7 @@ struct SolveArgs {
 template <int NW, int TEAM, int SOLVER>
 __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
   constexpr int NT = NW / TEAM;
-  using AccT = Acc<SOLVER>;
+  using AccT = Acc<SOLVER == 1 ? 1 : 0>;
   __shared__ __align__(16) float s_part[NW][NACC_PAD];
   __shared__ __align__(16) float s_work[NW][WORK];
   __shared__ float s_red[NW][32 * 33];
@@ -473,13 +500,18 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
   int iters = st->iters;
   bool converged = false, finished = false;
   Rigid X = state_load(st->X);
+  bool runaway = false;
+  Rigid inc;
+  if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, inc.r, inc.t);
   if (cnt < 3) {
     finished = true;  // "Not enough correspondences": hasConverged() false -> identity -> pose unchanged
+  } else if (runaway) {
+    // the reference's LM slides the scene metres off the model here; its next iteration finds no correspondences
+    ++iters;
+    finished = true;
+    if (tw == 0 && lane == 0) st->iters = iters;
   } else {
-    Rigid inc;
     if (cnt >= 6) {
-      if (SOLVER == 0) solve_exact(sums, W, lane, inc.r, inc.t);
-      else solve_gn(sums, inc.r, inc.t);
     } else if (cnt >= 4) {
       // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
 #pragma unroll
@@ -585,7 +617,7 @@ struct FusedArgs {
 
 // THREADS per CTA (a multiple of 128: four moment slices x THREADS/128 parts of the chunk), CHUNK scene points whose
 // records sit in shared memory at a time, PROF = with the cycle accounting, MINB resident CTAs per SM.
-template <int THREADS, int CHUNK, bool PROF, int MINB>
+template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
   constexpr int PARTS = THREADS / 128;
   extern __shared__ __align__(16) float4 fused_smem[];
@@ -676,11 +708,17 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
         const float *sums = s_tot;
         const float cnt_f = sums[92], sumd2 = sums[91];
         const int cnt = (int)(cnt_f + 0.5f);
+        bool runaway = false;
+        Rigid inc;
+        if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, inc.r, inc.t);
         if (cnt < 3) {
           finished = true;  // "Not enough correspondences": hasConverged() false -> pose unchanged
+        } else if (runaway) {
+          // the reference's LM slides the scene metres off the model here; its next iteration finds no correspondences
+          ++iters;
+          finished = true;
         } else {
-          Rigid inc;
-          if (cnt >= 6) solve_exact(sums, nullptr, lane, inc.r, inc.t);
+          if (cnt >= 6) {}
           else if (cnt >= 4) {  // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
 #pragma unroll
             for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
@@ -731,18 +769,24 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
   }
 }
 
-template <int THREADS, int CHUNK, bool PROF, int MINB>
-static cudaError_t launch_fused(const FusedArgs &f, int H, int sm_count, cudaStream_t stream) {
+template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
+static cudaError_t launch_fused(hop_ctx *ctx, const FusedArgs &f, int H) {
   const size_t smem = 2 * (size_t)CHUNK * sizeof(float4);
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(icp_fused_kernel<THREADS, CHUNK, PROF, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    attr_set = true;
-  }
-  const int grid_ctas = (int)std::min<long>((long)H, (long)sm_count * MINB);
-  icp_fused_kernel<THREADS, CHUNK, PROF, MINB><<<grid_ctas, THREADS, smem, stream>>>(f);
+  cudaError_t e = ctx->func_smem_optin(icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER>, smem);
+  if (e != cudaSuccess) return e;
+  const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * MINB);
+  icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER><<<grid_ctas, THREADS, smem, ctx->stream>>>(f);
   return cudaGetLastError();
+}
+
+// CTA shape by batch size.  Small batches: 256-thread CTAs (a hypothesis finishes sooner, shorter tail); large batches: 128-thread
+// CTAs (the serial small solve idles 3 warps instead of 7), 8 of them per SM at 64 registers -- the few spilled bytes cost less
+// than the extra warps hide (15.39 -> 14.78 ms at the headline size; small batches lose with it).  Record chunk = 4 points per
+// thread: the rest of the 256 KB stays L1.
+template <int SOLVER>
+static cudaError_t launch_fused_solver(hop_ctx *ctx, const FusedArgs &f, int H, bool small_ctas, bool prof_on) {
+  if (prof_on) return small_ctas ? launch_fused<128, 512, true, 6, SOLVER>(ctx, f, H) : launch_fused<256, 1024, true, 3, SOLVER>(ctx, f, H);
+  return small_ctas ? launch_fused<128, 512, false, 8, SOLVER>(ctx, f, H) : launch_fused<256, 1024, false, 3, SOLVER>(ctx, f, H);
 }
 
 // ------------------------------------------------------------------------------------------------------------
@@ -850,6 +894,7 @@ static void launch_solve(hop_ctx *ctx, const SolveArgs &s, int Hb, int solver) {
   constexpr int NT = SOLVE_NW / TEAM;
   const int grid = (Hb + NT - 1) / NT;
   if (solver == 1) icp_solve_kernel<SOLVE_NW, TEAM, 1><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
+  else if (solver == 2) icp_solve_kernel<SOLVE_NW, TEAM, 2><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
   else icp_solve_kernel<SOLVE_NW, TEAM, 0><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
 }
 
@@ -860,37 +905,28 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
   if (H <= 0) return HOP_OK;
   if (p.mode != 0) { ctx->err = "hop_icp_refine: mode 1 (point-to-point) not built yet"; return HOP_EINVAL; }
   const int max_iter = p.max_iter < 1 ? 1 : p.max_iter;
-  if (p.solver == 0 && p.pipeline != 1) {
-    // fused pipeline (default for the parity solver): one persistent launch for the whole batch
+  if (p.solver < 0 || p.solver > 2) { ctx->err = "hop_icp_refine: solver must be 0 (reference LM), 1 (Gauss-Newton) or 2 (exact minimiser)"; return HOP_EINVAL; }
+  if (p.solver != 1 && p.pipeline != 1) {
+    // fused pipeline (default): one persistent launch for the whole batch
     FusedArgs f;
     f.scene = scene; f.model_nv = model.nv; f.grid = grid; f.poses = d_poses; f.H = H; f.iters_out = d_iters; f.conv_out = d_conv;
     f.counter = ctx->d_counter;
     f.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
     f.max_d2 = p.max_dist * p.max_dist; f.max_iter = max_iter; f.abs_mse_eps = p.abs_mse_eps;
     HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
-    static const int variant = getenv("HOP_FUSED_VARIANT") ? atoi(getenv("HOP_FUSED_VARIANT")) : 0;  // tuning knob: 1 = 256-thread CTAs, 2 = 128-thread CTAs
-    static const bool prof_on = getenv("HOP_FUSED_PROFILE") != nullptr;
-    static long long *d_prof = nullptr;
-    if (prof_on && !d_prof) { HOP_CUDA(ctx, cudaMalloc(&d_prof, 6 * sizeof(long long))); }
-    if (prof_on) HOP_CUDA(ctx, cudaMemsetAsync(d_prof, 0, 6 * sizeof(long long), ctx->stream));
-    f.prof = prof_on ? d_prof : nullptr;
+    const int variant = ctx->tune.fused_variant;
+    const bool prof_on = ctx->tune.fused_profile;
+    if (prof_on && !ctx->d_fused_prof) { HOP_CUDA(ctx, cudaMalloc(&ctx->d_fused_prof, 6 * sizeof(long long))); }
+    if (prof_on) HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_fused_prof, 0, 6 * sizeof(long long), ctx->stream));
+    f.prof = prof_on ? ctx->d_fused_prof : nullptr;
     {
       ProfScope ps(ctx, HOP_PROF_ICP_FUSED);
-      cudaError_t e;
-      // small batches: 256-thread CTAs (a hypothesis finishes sooner, shorter tail); large batches: 128-thread CTAs (the
-      // serial small solve idles 3 warps instead of 7).  Record chunk = 4 points per thread: the rest of the 256 KB stays L1.
       const bool small_ctas = variant == 2 || (variant == 0 && (long)H >= 24L * ctx->sm_count);
-      if (prof_on) e = small_ctas ? launch_fused<128, 512, true, 6>(f, H, ctx->sm_count, ctx->stream)
-                                  : launch_fused<256, 1024, true, 3>(f, H, ctx->sm_count, ctx->stream);
-      // (large batches: 8 CTAs of 128 threads at 64 registers -- the few spilled bytes cost less than the extra warps hide:
-      //  15.39 -> 14.78 ms at the headline size; small batches lose with it)
-      else e = small_ctas ? launch_fused<128, 512, false, 8>(f, H, ctx->sm_count, ctx->stream)
-                          : launch_fused<256, 1024, false, 3>(f, H, ctx->sm_count, ctx->stream);
-      HOP_CUDA(ctx, e);
+      HOP_CUDA(ctx, p.solver == 0 ? launch_fused_solver<0>(ctx, f, H, small_ctas, prof_on) : launch_fused_solver<2>(ctx, f, H, small_ctas, prof_on));
     }
     if (prof_on) {
       long long hp[6];
-      HOP_CUDA(ctx, cudaMemcpyAsync(hp, d_prof, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
+      HOP_CUDA(ctx, cudaMemcpyAsync(hp, ctx->d_fused_prof, sizeof(hp), cudaMemcpyDeviceToHost, ctx->stream));
       HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
       const double tot = (double)std::max<long long>(hp[5], 1);
       fprintf(stderr, "[hop fused profile] H=%d passes=%lld  A %.1f%%  barrier %.1f%%  B %.1f%%  solve %.1f%%  other %.1f%%  (CTA cycles %.3g)\n", H, hp[4],
@@ -972,7 +1008,7 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_b
     const int Hb = std::min(Hb_max, H - h0);
     a.poses = d_poses + 16 * (size_t)h0; a.scores = d_scores + h0;
     ProfScope ps(ctx, HOP_PROF_LCP_SCORE);
-    static const int lcp_variant = getenv("HOP_LCP_VARIANT") ? atoi(getenv("HOP_LCP_VARIANT")) : 0;  // tuning knob
+    const int lcp_variant = ctx->tune.lcp_variant;
     if (lcp_variant == 1) lcp_score_kernel<5><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
     else if (lcp_variant == 2) lcp_score_kernel<6><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
     else if (lcp_variant == 4) lcp_score_kernel<4><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);

@@ -223,6 +223,7 @@ double geodesic_gate(float thr) {
 
 extern "C" int hop_cluster_poses_gpu(hop_ctx *ctx, const float *poses, const float *scores, const int32_t *ids, int n, float angle_diff_deg,
                                      float dist_diff, const float *symmetry_deg, int32_t *keep_out, int32_t *n_keep) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (n < 0 || !n_keep || (n > 0 && (!poses || !scores || !keep_out)) || !symmetry_deg) { ctx->err = "hop_cluster_poses_gpu: bad arguments"; return HOP_EINVAL; }
   *n_keep = 0;
@@ -261,8 +262,7 @@ extern "C" int hop_cluster_poses_gpu(hop_ctx *ctx, const float *poses, const flo
   HOP_CUDA(ctx, cudaMemcpyAsync(d_feat, feat.data(), sizeof(ClFeat) * (size_t)n, cudaMemcpyHostToDevice, st));
   HOP_CUDA(ctx, cudaMemsetAsync(d_nkeep, 0, sizeof(int), st));
   const size_t smem = sizeof(ClFeat) * CL_BLOCK + sizeof(unsigned int) * CL_BLOCK * CL_ROW;
-  static bool attr_set = false;
-  if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(cluster_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  HOP_CUDA(ctx, ctx->func_smem_optin(cluster_block_kernel, smem));
   {
     ProfScope ps(ctx, HOP_PROF_CLUSTER);
     for (int b0 = 0; b0 < n; b0 += CL_BLOCK) {

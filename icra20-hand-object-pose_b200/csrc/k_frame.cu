@@ -368,6 +368,7 @@ extern "C" void hop_default_frame_params(hop_frame_params *p) {
 
 extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *fp, hop_cloud **scene,
                                   int32_t *stage_counts) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!depth_mm || width <= 0 || height <= 0 || !fp || !scene) { ctx->err = "hop_frame_to_scene: bad arguments"; return HOP_EINVAL; }
   if (!(fp->leaf_dense > 0.f) || !(fp->leaf_object > 0.f) || !(fp->normal_radius > 0.f)) { ctx->err = "hop_frame_to_scene: leaf sizes and radius must be > 0"; return HOP_EINVAL; }
@@ -570,6 +571,7 @@ int keep_flagged(hop_ctx *ctx, const hop_cloud *in, const unsigned char *flag, h
 }  // namespace
 
 extern "C" int hop_cloud_voxel_grid(hop_ctx *ctx, const hop_cloud *in, float leaf, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in || !(leaf > 0.f)) { ctx->err = "hop_cloud_voxel_grid: bad arguments"; return HOP_EINVAL; }
   cudaStream_t st = ctx->stream;
@@ -584,6 +586,7 @@ extern "C" int hop_cloud_voxel_grid(hop_ctx *ctx, const hop_cloud *in, float lea
 }
 
 extern "C" int hop_cloud_transform(hop_ctx *ctx, const hop_cloud *in, const float *T, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in || !T) { ctx->err = "hop_cloud_transform: bad arguments"; return HOP_EINVAL; }
   cudaStream_t st = ctx->stream;
@@ -597,6 +600,7 @@ extern "C" int hop_cloud_transform(hop_ctx *ctx, const hop_cloud *in, const floa
 }
 
 extern "C" int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axis, float lo, float hi, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in || axis < 0 || axis > 2) { ctx->err = "hop_cloud_pass_through: bad arguments"; return HOP_EINVAL; }
   FBuf fl(ctx->stream);
@@ -609,6 +613,7 @@ extern "C" int hop_cloud_pass_through(hop_ctx *ctx, const hop_cloud *in, int axi
 }
 
 extern "C" int hop_cloud_handbase_region(hop_ctx *ctx, const hop_cloud *in, float y1, float z1, float y2, float z2, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in) { ctx->err = "hop_cloud_handbase_region: bad arguments"; return HOP_EINVAL; }
   FBuf fl(ctx->stream);
@@ -621,6 +626,7 @@ extern "C" int hop_cloud_handbase_region(hop_ctx *ctx, const hop_cloud *in, floa
 }
 
 extern "C" int hop_cloud_radius_outlier_removal(hop_ctx *ctx, const hop_cloud *in, float radius, int min_neighbors, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in || !(radius > 0.f) || min_neighbors < 0) { ctx->err = "hop_cloud_radius_outlier_removal: bad arguments"; return HOP_EINVAL; }
   FBuf fl(ctx->stream);
@@ -634,6 +640,7 @@ extern "C" int hop_cloud_radius_outlier_removal(hop_ctx *ctx, const hop_cloud *i
 }
 
 extern "C" int hop_cloud_statistical_outlier_removal(hop_ctx *ctx, const hop_cloud *in, int mean_k, float stddev_mul, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!in || !out || *out == in || mean_k < 1 || mean_k + 1 > SOR_KMAX) { ctx->err = "hop_cloud_statistical_outlier_removal: bad arguments (mean_k 1..64)"; return HOP_EINVAL; }
   cudaStream_t st = ctx->stream;
@@ -725,6 +732,7 @@ Xf xf_of(const float *colmajor) {
 
 extern "C" int hop_remove_hand_points(hop_ctx *ctx, const hop_cloud *scene, const hop_cloud *const *links, const int32_t *link_kind, int n_links,
                                       const hop_hand_removal_params *params, hop_cloud **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!scene || !params || !out || n_links < 0 || n_links > MAX_LINKS || (n_links > 0 && (!links || !link_kind))) {
     ctx->err = "hop_remove_hand_points: bad arguments (at most 16 links)"; return HOP_EINVAL;
@@ -769,6 +777,7 @@ extern "C" int hop_remove_hand_points(hop_ctx *ctx, const hop_cloud *scene, cons
 }
 
 extern "C" int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud) return HOP_EINVAL;
   const int n = cloud->n;
   if (n <= 0) return HOP_OK;

@@ -268,6 +268,7 @@ __global__ void __launch_bounds__(1024, 1) argmin_kernel(const double *__restric
 extern "C" int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop_cloud *scene_normals,
                                     hop_cloud *scene_noswivel, const hop_finger_params *params, const double *d_thetas,
                                     const float *d_half_cs, int S, double *d_cost, int32_t *d_best) {
+  HOP_ENTER(ctx);
   if (!ctx || !finger || !scene_hand || !scene_noswivel || !params || S < 0) { if (ctx) ctx->err = "hop_hand_overlap: bad arguments"; return HOP_EINVAL; }
   if (S == 0) return HOP_OK;
   if (!d_thetas || !d_cost) { ctx->err = "hop_hand_overlap: null state/cost buffer"; return HOP_EINVAL; }
@@ -293,8 +294,7 @@ extern "C" int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *
   a.thr2 = params->dist_thres * params->dist_thres;
   a.cost = d_cost;
   const size_t smem = 2 * (size_t)HAND_CHUNK * sizeof(float4);
-  static bool attr_set = false;
-  if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(hand_overlap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr_set = true; }
+  HOP_CUDA(ctx, ctx->func_smem_optin(hand_overlap_kernel, smem));
   a.matches = (int *)ctx->ensure_work(sizeof(int) * (size_t)S);
   if (!a.matches) { ctx->err = "hop_hand_overlap: work buffer allocation failed"; return HOP_ENOMEM; }
   {
@@ -314,6 +314,7 @@ extern "C" int hop_hand_overlap_dev(hop_ctx *ctx, hop_cloud *finger, hop_cloud *
 
 extern "C" int hop_hand_overlap(hop_ctx *ctx, hop_cloud *finger, hop_cloud *scene_hand, hop_cloud *scene_normals, hop_cloud *scene_noswivel,
                                 const hop_finger_params *params, const double *thetas, int S, double *cost_out, int32_t *best_out) {
+  HOP_ENTER(ctx);
   if (!ctx || S < 0 || (S > 0 && (!thetas || !cost_out))) return HOP_EINVAL;
   if (best_out) *best_out = -1;
   if (S == 0) return HOP_OK;
@@ -373,6 +374,7 @@ __global__ void __launch_bounds__(128) hand_height_kernel(HeightArgs a) {
 
 extern "C" int hop_adjust_hand_height(hop_ctx *ctx, hop_cloud *hand_cloud, hop_cloud *scene_handbase, const float *heights, int n_heights,
                                       int32_t *match_counts, int32_t *best_index) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!hand_cloud || !scene_handbase || !heights || n_heights < 1 || n_heights > 4096 || !best_index) { ctx->err = "hop_adjust_hand_height: bad arguments"; return HOP_EINVAL; }
   std::vector<int32_t> counts(n_heights, 0);

@@ -367,6 +367,7 @@ extern "C" void hop_default_render_params(hop_render_params *p) {
 
 extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *params, const float *depth_m, const float *hand_V, int hand_nv,
                                        const int32_t *hand_F, int hand_nf, hop_render_scene **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!out || !depth_m || hand_nv < 0 || hand_nf < 0 || (hand_nf > 0 && (!hand_V || !hand_F))) { ctx->err = "hop_render_scene_create: bad arguments"; return HOP_EINVAL; }
   int rc = check_params(ctx, params);
@@ -413,6 +414,7 @@ extern "C" int hop_render_scene_create(hop_ctx *ctx, const hop_render_params *pa
 }
 
 extern "C" int hop_render_scene_destroy(hop_ctx *ctx, hop_render_scene *s) {
+  HOP_ENTER(ctx);
   if (!s) return HOP_OK;
   cudaStream_t st = ctx ? ctx->stream : (cudaStream_t)0;   // stream-ordered: the frees queue behind the scene's last use on the context's stream
   cudaFreeAsync(s->d_real, st); cudaFreeAsync(s->d_zhand, st); cudaFreeAsync(s->d_base_diff, st); cudaFreeAsync(s->d_prefix, st);
@@ -439,6 +441,7 @@ int upload_object(hop_ctx *ctx, const float *V, int nv, const int32_t *F, int nf
 
 extern "C" int hop_render_depth(hop_ctx *ctx, const hop_render_scene *scene, const float *obj_V, int obj_nv, const int32_t *obj_F, int obj_nf,
                                 const float *pose, float *depth, uint8_t *mask) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!scene || !pose || !depth) { ctx->err = "hop_render_depth: bad arguments"; return HOP_EINVAL; }
   float *d_V; int32_t *d_F;
@@ -465,6 +468,7 @@ extern "C" int hop_render_depth(hop_ctx *ctx, const hop_render_scene *scene, con
 
 extern "C" int hop_reject_by_render(hop_ctx *ctx, const hop_render_scene *scene, const float *obj_V, int obj_nv, const int32_t *obj_F, int obj_nf,
                                     const float *poses, int H, float *wrong_ratio, int32_t *order, int32_t *n_keep) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!scene || H < 0 || (H > 0 && (!poses || !wrong_ratio))) { ctx->err = "hop_reject_by_render: bad arguments"; return HOP_EINVAL; }
   if (n_keep) *n_keep = 0;
@@ -551,8 +555,7 @@ extern "C" int hop_reject_by_render(hop_ctx *ctx, const hop_render_scene *scene,
       if (base_bytes + per_lane > budget) { ctx->err = "hop_reject_by_render: image too wide for the walk kernel's shared memory"; return HOP_EINVAL; }
       const int lanes = (int)std::min<size_t>(32, (budget - base_bytes) / per_lane);
       const size_t smem = base_bytes + per_lane * (size_t)lanes;
-      static size_t attr = 0;
-      if (smem > attr) { HOP_CUDA(ctx, cudaFuncSetAttribute(walk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = smem; }
+      HOP_CUDA(ctx, ctx->func_smem_optin(walk_kernel, smem));
       walk_kernel<<<(count + lanes - 1) / lanes, WALK_THREADS, smem, st>>>(wa, stride, lanes, from_top);
       ctx->launches += 1;
     }

@@ -294,6 +294,7 @@ struct DevBuf {
 }  // namespace
 
 extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_poses, float *hyp_lcp, int capacity, int32_t *n_hyp) {
+  HOP_ENTER(ctx);
   if (!ctx || !plan || capacity < 0 || (capacity > 0 && (!hyp_poses || !hyp_lcp))) { if (ctx) ctx->err = "hop_super4pcs_run: bad arguments"; return HOP_EINVAL; }
   if (n_hyp) *n_hyp = 0;
   plan->trial_ranges.clear(); plan->pairs.clear(); plan->quads.clear(); plan->trials_executed = 0;

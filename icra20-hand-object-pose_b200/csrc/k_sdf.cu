@@ -382,6 +382,7 @@ MeshDev mesh_dev(const hop_mesh *m) { return m ? MeshDev{m->d_hot, m->d_cold, m-
 }  // namespace
 
 extern "C" int hop_mesh_upload(hop_ctx *ctx, const float *V, int nv, const int32_t *F, int nf, hop_mesh **out) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!out || !V || !F || nv < 3 || nf < 1) { ctx->err = "hop_mesh_upload: bad arguments"; return HOP_EINVAL; }
   for (int k = 0; k < 3 * nf; ++k) if (F[k] < 0 || F[k] >= nv) { ctx->err = "hop_mesh_upload: face index out of range"; return HOP_EINVAL; }
@@ -440,6 +441,7 @@ extern "C" int hop_mesh_upload(hop_ctx *ctx, const float *V, int nv, const int32
 }
 
 extern "C" int hop_mesh_free(hop_ctx *ctx, hop_mesh *mesh) {
+  HOP_ENTER(ctx);
   if (!mesh) return HOP_OK;
   if (ctx) cudaStreamSynchronize(ctx->stream);
   cudaFree(mesh->d_hot); cudaFree(mesh->d_cold);
@@ -449,6 +451,7 @@ extern "C" int hop_mesh_free(hop_ctx *ctx, hop_mesh *mesh) {
 
 extern "C" int hop_sdf_query(hop_ctx *ctx, const hop_mesh *mesh, const float *pts, int n, const float *point_transforms, int H, float *S,
                              int32_t *I, float *min_out, float *max_out, int32_t *n_inside) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!mesh || n < 0 || H < 0 || (n > 0 && !pts)) { ctx->err = "hop_sdf_query: bad arguments"; return HOP_EINVAL; }
   if (H == 0) return HOP_OK;
@@ -504,6 +507,7 @@ extern "C" int hop_sdf_query(hop_ctx *ctx, const hop_mesh *mesh, const float *pt
 extern "C" int hop_reject_by_collision_dev(hop_ctx *ctx, const hop_mesh *object, const hop_mesh *const *finger_meshes, hop_cloud *const *finger_clouds,
                                            hop_cloud *scene_without_hand, hop_cloud *hand_cloud, hop_cloud *model, const float *d_poses, int H,
                                            const hop_collision_params *params, int32_t *d_keep, int32_t *d_reason, float *d_diag) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (!object || !params || H < 0 || (H > 0 && (!d_poses || !d_keep))) { ctx->err = "hop_reject_by_collision: bad arguments"; return HOP_EINVAL; }
   if (H == 0) return HOP_OK;
@@ -540,6 +544,7 @@ extern "C" int hop_reject_by_collision_dev(hop_ctx *ctx, const hop_mesh *object,
 extern "C" int hop_reject_by_collision(hop_ctx *ctx, const hop_mesh *object, const hop_mesh *const *finger_meshes, hop_cloud *const *finger_clouds,
                                        hop_cloud *scene_without_hand, hop_cloud *hand_cloud, hop_cloud *model, const float *poses, int H,
                                        const hop_collision_params *params, int32_t *keep, int32_t *reason, float *diag) {
+  HOP_ENTER(ctx);
   if (!ctx) return HOP_EINVAL;
   if (H < 0 || (H > 0 && (!poses || !keep))) { ctx->err = "hop_reject_by_collision: bad arguments"; return HOP_EINVAL; }
   if (H == 0) return HOP_OK;

@@ -165,6 +165,7 @@ extern "C" int hop_verify_lcp_dev(hop_ctx *ctx, hop_cloud *P_centered, const flo
                                   const int32_t *d_quads, const int32_t *d_quad_trial, int M, const float *centroid_P,
                                   const float *centroid_Q, float delta, float *d_poses, float *d_lcp, int32_t *d_valid,
                                   int32_t *d_n_valid) {
+  HOP_ENTER(ctx);
   if (!ctx || !P_centered || M < 0 || nQ < 0 || T < 0) return HOP_EINVAL;
   if (M == 0) { if (d_n_valid) HOP_CUDA(ctx, cudaMemsetAsync(d_n_valid, 0, sizeof(int32_t), ctx->stream)); return HOP_OK; }
   if (!d_Q || !d_bases || !d_quads || !d_quad_trial || !d_poses || !d_lcp || !d_valid || !centroid_P || !centroid_Q || !(delta > 0.f) ||
@@ -218,6 +219,7 @@ extern "C" int hop_verify_lcp_dev(hop_ctx *ctx, hop_cloud *P_centered, const flo
 extern "C" int hop_verify_lcp(hop_ctx *ctx, hop_cloud *P_centered, const float *Q_xyz, int nQ, const int32_t *bases, int T,
                               const int32_t *quads, const int32_t *quad_trial, int M, const float *centroid_P, const float *centroid_Q,
                               float delta, float *poses, float *lcp, int32_t *valid, float *hyp_poses, float *hyp_lcp, int32_t *n_hyp) {
+  HOP_ENTER(ctx);
   if (!ctx || M < 0) return HOP_EINVAL;
   if (n_hyp) *n_hyp = 0;
   if (M == 0) return HOP_OK;

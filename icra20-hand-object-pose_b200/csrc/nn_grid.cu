@@ -223,13 +223,12 @@ void hop_free_nn_grid(NNGridHost *g) {
   delete g;
 }
 
-static float auto_voxel(const hop_cloud *c, float radius) {
+static float auto_voxel(const hop_cloud *c, float radius, float max_frac) {
   // point spacing estimate from the bounding-box surface (clouds on this path are surface samples)
   float dx = std::max(c->bbox_max[0] - c->bbox_min[0], 1e-6f), dy = std::max(c->bbox_max[1] - c->bbox_min[1], 1e-6f),
         dz = std::max(c->bbox_max[2] - c->bbox_min[2], 1e-6f);
   float area = dx * dy + dy * dz + dz * dx;  // ~ half the box surface
   float spacing = std::sqrt(area / std::max(c->n, 1));
-  static const float max_frac = getenv("HOP_VOXEL_MAX_FRAC") ? (float)atof(getenv("HOP_VOXEL_MAX_FRAC")) : 1.0f;  // tuning knob
   return std::min(std::max(spacing, radius / 12.f), radius * max_frac);
 }
 
@@ -237,7 +236,7 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
   if (!cloud || cloud->n <= 0 || !(radius > 0.f)) { ctx->err = "hop_build_nn_grid: empty cloud or bad radius"; return HOP_EINVAL; }
   ProfScope ps(ctx, HOP_PROF_NN_BUILD);
   NNGridHost *G = *out ? *out : new NNGridHost();
-  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius);
+  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius, ctx->tune.voxel_max_frac);
   const int64_t kMaxVox = 48ll << 20;
   GridGeom g;
   for (;;) {
@@ -364,6 +363,7 @@ static int get_nn_grid_on_current_stream(hop_ctx *ctx, hop_cloud *cloud, float r
 }
 
 extern "C" int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, int64_t *stats) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud) return HOP_EINVAL;
   NNGridHost *G = nullptr;
   int rc = hop_get_nn_grid(ctx, cloud, radius, voxel, &G);
@@ -381,6 +381,7 @@ extern "C" int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius
 // stream so far (the cloud's upload, the last consumers of the grid's previous contents), concurrent with whatever the main
 // stream is given next.  The first main-stream call that looks the grid up waits for it (hop_get_nn_grid).
 extern "C" int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud) return HOP_EINVAL;
   if (!ctx->side) {
     HOP_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->side, cudaStreamNonBlocking));
@@ -408,12 +409,14 @@ extern "C" int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float 
 }
 
 extern "C" int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud) return HOP_EINVAL;
   cloud->version++;
   return HOP_OK;
 }
 
 extern "C" int hop_cloud_nn_query(hop_ctx *ctx, hop_cloud *cloud, float radius, const float *queries, int nq, int32_t *idx, float *d2) {
+  HOP_ENTER(ctx);
   if (!ctx || !cloud || !queries || !idx || !d2 || nq < 0) return HOP_EINVAL;
   if (nq == 0) return HOP_OK;
   NNGridHost *G = nullptr;

@@ -162,14 +162,12 @@ int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, i
   ProfScope ps(ctx, HOP_PROF_TOPK);
   const size_t smem = sizeof(float) * (size_t)H;
   const size_t smem_lists = sizeof(float) * (size_t)((H + 31) & ~31) + 8 * (size_t)32 * (size_t)(K | 1);
-  static const bool rounds_only = getenv("HOP_TOPK_ROUNDS") != nullptr;   // the one-barrier-pair-per-winner kernel (A/B knob)
+  const bool rounds_only = ctx->tune.topk_rounds;   // the one-barrier-pair-per-winner kernel (A/B knob)
   if (K <= 128 && smem_lists <= 200 * 1024 && !rounds_only) {
-    static bool attr_set = false;
-    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(topk_lists_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    HOP_CUDA(ctx, ctx->func_smem_optin(topk_lists_kernel, 200 * 1024));
     topk_lists_kernel<<<1, 1024, smem_lists, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out);
   } else if (smem <= 200 * 1024) {
-    static bool attr_set = false;
-    if (!attr_set) { HOP_CUDA(ctx, cudaFuncSetAttribute(topk_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_set = true; }
+    HOP_CUDA(ctx, ctx->func_smem_optin(topk_kernel<true>, 200 * 1024));
     topk_kernel<true><<<1, 1024, smem, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);
   } else {
     topk_kernel<false><<<1, 1024, 0, ctx->stream>>>(d_poses, d_scores, H, K, id_offset, frame, d_out, taken);

@@ -62,8 +62,10 @@ typedef struct hop_icp_params {
   float max_dist;       /* max_corres_dist: icp_dist_thres (0.01) */
   double abs_mse_eps;   /* setAbsoluteMSE(1e-6) */
   int32_t mode;         /* 0 = point-to-plane (the reference's hot ICP); 1 = point-to-point SVD (Utils.cpp:135-184) */
-  int32_t solver;       /* mode 0 only: 0 = exact nonlinear least squares per iteration (what PCL's LM converges to);
-                                         1 = one Gauss-Newton step per iteration (fewer registers, not the parity path) */
+  int32_t solver;       /* mode 0 only: 0 = the reference's own per-iteration solver, PCL's float Levenberg-Marquardt with its forward-
+                           difference Jacobian and MINPACK stopping rules, replayed on the 13x13 moments (csrc/lm_replay.cuh): the
+                           parity path and the default;  1 = one Gauss-Newton step per iteration;  2 = exact minimiser of every
+                           iteration's objective (goes further along weak directions than the reference does: not parity) */
   int32_t team_warps;   /* warps cooperating on one hypothesis: 0 = auto, else 1/2/4/8 */
   int32_t pipeline;     /* mode 0, solver 0: 0 = fused (whole ICP of a hypothesis in one CTA, one launch per batch); 1 = two
                            launches per iteration (correspondence records through global memory) */

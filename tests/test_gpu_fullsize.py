@@ -13,6 +13,7 @@ import pytest
 
 from hop_b200 import hand, synth
 from oracle import cpu_oracle as O
+from parity_util import assert_icp_bound
 
 pytestmark = pytest.mark.gpu
 POS_TOL, ROT_TOL = 1e-3, 1.0
@@ -51,21 +52,13 @@ def _p2plane_fit(s, sn, m, mn, poses, dist=0.01, angle=45.0):
     return np.array(rms), np.array(cnt)
 
 
-def _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, max_iter, frac=0.9, by_score=False):
+def _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, max_iter, name=None):
+    """the 1 mm / 1 deg bound on every sampled hypothesis whose reference answer is reproducible (tests/parity_util.py); the
+    sample includes the 10 % fully random hypotheses of SURVEY 8d, which sit at the edge of the 1 cm gate"""
     ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp[idx], max_iter=max_iter)
-    dt, dr = synth.pose_error(got[idx], ref)
-    ok = (dt <= POS_TOL) & (dr <= ROT_TOL)
-    if by_score:
-        # Long runs on objects whose visible part leaves a direction unconstrained (one or two faces of a box, a cylinder's
-        # axis): point-to-plane ICP slides freely there and 50 iterations of rounding decide where it stops.  The poses are
-        # then compared by the quantity ICP minimises: the point-to-plane RMS over the gated correspondences (and their number).
-        rms_g, n_g = _p2plane_fit(s, sn, m, mn, got[idx])
-        rms_r, n_r = _p2plane_fit(s, sn, m, mn, ref)
-        ok = ok | ((rms_g <= 1.05 * rms_r + 2e-5) & (n_g >= 0.97 * n_r - 2))
-    assert ok.mean() >= frac, (ok.mean(), np.sort(dt)[-5:], np.sort(dr)[-5:])
-    # (the 10 % fully random hypotheses sit at the edge of the 1 cm gate: they may keep or lose their last correspondences in
-    #  a different iteration than the oracle's run of the same chaotic sequence)
-    assert np.mean(cv[idx] == rcv) >= 0.9
+    ok, unstable, weak = assert_icp_bound(got[idx], ref, s, sn, m, mn, hyp[idx], name=name, max_iter=max_iter, sanity=0.8,
+                                          flags=(it[idx], cv[idx], rit, rcv))
+    print(f"sample of {len(idx)}: within bound {ok.mean():.3f}, reference unstable {unstable.mean():.3f}, weak {weak.mean():.3f}")
 
 
 @pytest.mark.parametrize("name,H,n_check", [("C2", None, 96), ("headline", 4096, 48)])
@@ -76,7 +69,7 @@ def test_icp_lcp_full_size_sample_and_properties(ctx, name, H, n_check):
     got, it, cv = ctx.icp_refine(scene, model, hyp, p)
     rng = np.random.default_rng(3)
     idx = np.sort(rng.choice(len(hyp), n_check, replace=False))
-    _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, wl["max_iter"])
+    _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, wl["max_iter"], name=wl["model"])
     # batch invariance: reversed order, and a small sub-batch (different CTA shape: 256-thread CTAs below 24 x SMs)
     got_r, it_r, cv_r = ctx.icp_refine(scene, model, hyp[::-1].copy(), p)
     assert np.array_equal(got_r[::-1], got) and np.array_equal(it_r[::-1], it) and np.array_equal(cv_r[::-1], cv)
@@ -127,7 +120,7 @@ def test_c3_three_objects_icp_to_convergence(ctx):
         got, it, cv = ctx.icp_refine(scene, model, hyp, p)
         assert np.isfinite(got).all(), (name, np.nonzero(~np.isfinite(got).all(axis=(1, 2)))[0][:10])
         idx = np.arange(0, 8192, 128)
-        _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, 50, frac=0.85, by_score=True)
+        _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, 50, name=name)
         assert (it < 50).mean() > 0.9 and it.max() <= 50
         # fixed point in the sense that matters on a partly unconstrained object: refining the refined poses again does not
         # lower the objective any further (it may still slide along the free directions)
@@ -159,7 +152,7 @@ def test_c5_stress_sizes(ctx):
     assert (gi[inside] == ki[inside]).mean() > 0.999
     got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(max_iter=10))
     idx = np.arange(0, 512, 32)
-    _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, 10, frac=0.85)
+    _check_sample_against_oracle(got, it, cv, s, sn, m, mn, hyp, idx, 10, name="ellipse")
     sc = ctx.lcp_score(scene, model, got)
     _, ref_sc = O.select_best(s, sn, m, mn, got[idx[:8]])
     assert np.all(np.abs(sc[idx[:8]] - ref_sc) <= 3e-4 * np.maximum(np.abs(ref_sc), 1.0)), np.abs(sc[idx[:8]] - ref_sc).max()

@@ -10,6 +10,7 @@ import pytest
 
 from hop_b200 import synth
 from oracle import cpu_oracle as O
+from parity_util import assert_icp_bound
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -117,20 +118,33 @@ def _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=0, max_iter=10, pipeline=
 
 @pytest.mark.parametrize("name,ns,nm", [("ellipse", 600, 3000), ("cuboid", 800, 5000), ("cylinder", 500, 2000), ("tless", 700, 4000)])
 def test_icp_refine_matches_oracle_in_the_convergence_basin(ctx, name, ns, nm):
-    """Hypotheses around the ground truth (the ones Super4PCS hands to refineByICP): every refined pose within
+    """Hypotheses around the ground truth (the ones Super4PCS hands to refineByICP): EVERY refined pose within
     1 mm / 1 deg of the reference algorithm's, same convergence flags."""
     m, mn, s, sn, conf, gt, hyp = _case(name, ns, nm, 96, seed=51, random_frac=0.0, rot_sigma_deg=3.0, trans_sigma=0.003)
     got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp)
     assert np.array_equal(cv, rcv)
     dt, dr = synth.pose_error_sym(got, ref, name)  # rotation about a continuous symmetry axis is unobservable
     ok = (dt <= POS_TOL) & (dr <= ROT_TOL)
-    assert ok.mean() >= 0.97, (dt.max(), dr.max(), np.nonzero(~ok)[0])
-    assert np.median(dt) < 1e-4 and np.median(dr) < 0.2
-    assert np.mean(np.abs(it - rit) <= 1) >= 0.95
+    assert ok.all(), (dt.max(), dr.max(), np.nonzero(~ok)[0])
+    assert dt.max() < 3e-4 and dr.max() < 0.5      # (measured: 0.1 mm / 0.13 deg)
+    assert np.mean(it == rit) >= 0.95
     # and both agree with the ground truth about as well
     egt, _ = synth.pose_error(got, np.repeat(gt[None], len(got), 0))
     rgt, _ = synth.pose_error(ref, np.repeat(gt[None], len(ref), 0))
     assert abs(np.median(egt) - np.median(rgt)) < 2e-4
+
+
+@pytest.mark.parametrize("name,ns,nm,seed", [("ellipse", 2000, 10000, 7), ("cuboid", 2000, 10000, 8), ("cuboid", 1500, 8000, 18),
+                                             ("cylinder", 2000, 10000, 10), ("tless", 2000, 10000, 9)])
+def test_icp_refine_bound_on_coarse_hypotheses(ctx, name, ns, nm, seed):
+    """5 deg / 5 mm hypotheses: the bound holds on every hypothesis whose reference answer is reproducible
+    (parity_util); on a box many coarse hypotheses see one or two faces only -- the reference's LM then runs away along the
+    free translation and the ICP returns 'not converged, pose unchanged', which the kernel reproduces."""
+    m, mn, s, sn, conf, gt, hyp = _case(name, ns, nm, 256, seed=seed, random_frac=0.0)
+    got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp)
+    ok, unstable, weak = assert_icp_bound(got, ref, s, sn, m, mn, hyp, name=name, flags=(it, cv, rit, rcv))
+    print(f"{name} {ns}: within bound {ok.mean():.4f}, reference unstable {unstable.mean():.3f}, weak {weak.mean():.3f}, "
+          f"not converged in the reference {np.mean(rcv == 0):.3f}")
 
 
 @pytest.mark.parametrize("team", [1, 2, 4, 8])
@@ -138,8 +152,7 @@ def test_icp_refine_team_sizes_agree(ctx, team):
     """the two-launch pipeline (pipeline=1) with every warp-team size"""
     m, mn, s, sn, conf, gt, hyp = _case("ellipse", 520, 2500, 40, seed=61, random_frac=0.0)
     got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp, team=team, pipeline=1)
-    assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.95
-    assert np.array_equal(cv, rcv)
+    assert_icp_bound(got, ref, s, sn, m, mn, hyp, name="ellipse", flags=(it, cv, rit, rcv))
 
 
 @pytest.mark.parametrize("name,ns,nm", [("ellipse", 600, 3000), ("cuboid", 2100, 5000)])
@@ -153,6 +166,19 @@ def test_icp_pipelines_agree(ctx, name, ns, nm):
     assert np.percentile(dt, 95) < 2e-5 and np.percentile(dr, 95) < 0.02
 
 
+@pytest.mark.parametrize("solver", [1, 2])
+def test_icp_other_solvers_reach_the_same_basin(ctx, solver):
+    """solver 1 (one Gauss-Newton step per iteration) and 2 (exact minimiser of each iteration's objective) are NOT the parity
+    path: they go further along weak directions than the reference's LM.  They must still land at the same optimum."""
+    m, mn, s, sn, conf, gt, hyp = _case("ellipse", 600, 3000, 64, seed=51, random_frac=0.0, rot_sigma_deg=3.0, trans_sigma=0.003)
+    scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
+    got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(solver=solver))
+    ref, _, _ = O.refine_by_icp(s, sn, m, mn, hyp)
+    dt, dr = synth.pose_error(got, ref)
+    assert np.median(dt) < 2e-4 and np.median(dr) < 0.3 and np.mean((dt <= 3e-3) & (dr <= 3.0)) >= 0.95
+    scene.free(); model.free()
+
+
 def test_icp_refine_semantics_of_the_reference(ctx):
     m, mn, s, sn, conf, gt, hyp = _case("ellipse", 500, 2000, 16, seed=71, random_frac=0.0)
     scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
@@ -160,14 +186,12 @@ def test_icp_refine_semantics_of_the_reference(ctx):
     far = hyp[:4].copy(); far[:, :3, 3] += 1.0
     got, it, cv = ctx.icp_refine(scene, model, far)
     assert np.all(it == 0) and np.all(cv == 0) and np.allclose(got, far, atol=1e-6)
-    # (2) max_iter = 1: one iteration, "converged" by the iteration rule
+    # (2) max_iter = 1: one iteration, "converged" by the iteration rule; one LM solve on identical correspondences
     got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(max_iter=1))
     ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp, max_iter=1)
     dt, dr = synth.pose_error(got, ref)
-    # one iteration = one LM solve on identical correspondences: the float LM of the reference stops at ftol =
-    # sqrt(eps) short of the minimum along the ellipsoid's weak directions, the GPU solve does not
     assert np.all(it == 1) and np.all(cv == 1)
-    assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.9 and np.median(dt) < 1e-4 and np.median(dr) < 0.3
+    assert np.all((dt <= POS_TOL) & (dr <= ROT_TOL)), (dt.max(), dr.max())
     # (3) empty batch
     got, it, cv = ctx.icp_refine(scene, model, hyp[:0])
     assert got.shape == (0, 4, 4)
@@ -176,10 +200,39 @@ def test_icp_refine_semantics_of_the_reference(ctx):
 
 
 def test_icp_refine_streamed_scene(ctx):
-    """7000-point scene: tiles are streamed through the TMA ring instead of staying resident."""
+    """7000-point scene: many record chunks per iteration."""
     m, mn, s, sn, conf, gt, hyp = _case("ellipse", 7000, 4000, 24, seed=81, random_frac=0.0)
     got, it, cv, ref, rit, rcv, dt, dr = _icp_parity(ctx, m, mn, s, sn, conf, gt, hyp)
-    assert np.mean((dt <= POS_TOL) & (dr <= ROT_TOL)) >= 0.95 and np.array_equal(cv, rcv)
+    assert_icp_bound(got, ref, s, sn, m, mn, hyp, name="ellipse", flags=(it, cv, rit, rcv))
+
+
+def test_icp_runaway_on_unconstrained_translation(ctx):
+    """Two faces of a box sharing an edge: the correspondences' normals span a plane, translation along the edge is free, the
+    scatter matrix of the normals is singular.  The reference's LM divides rounding noise by rounding noise, slides the scene
+    metres along the edge and the ICP ends 'not converged' -> pose unchanged (lm_replay.cuh, translation_unconstrained)."""
+    rng = np.random.default_rng(0)
+    n = 6000
+    a = np.stack([rng.uniform(-0.04, 0.04, n // 2), rng.uniform(-0.025, 0.025, n // 2), np.full(n // 2, 0.015)], 1)
+    b = np.stack([np.full(n // 2, 0.04), rng.uniform(-0.025, 0.025, n // 2), rng.uniform(-0.015, 0.015, n // 2)], 1)
+    m = np.concatenate([a, b]).astype(np.float32)
+    mn = np.concatenate([np.tile([[0, 0, 1.0]], (n // 2, 1)), np.tile([[1.0, 0, 0]], (n // 2, 1))]).astype(np.float32)
+    # (a generic rotation: with a face normal exactly along a camera axis the reference's Jacobian has exactly zero columns,
+    #  MINPACK drops them and does not run away -- measure zero, not special-cased)
+    gt = np.eye(4, dtype=np.float32); gt[:3, :3] = synth.random_rotation(rng); gt[:3, 3] = [0.02, -0.01, 0.35]
+    pick = rng.choice(n, 800, replace=False)
+    s = (m[pick] @ gt[:3, :3].T + gt[:3, 3] + rng.normal(0, 3e-4, (800, 3))).astype(np.float32)
+    sn = (mn[pick] @ gt[:3, :3].T).astype(np.float32)
+    hyp = synth.make_hypotheses(gt, 64, seed=3, random_frac=0.0, rot_sigma_deg=2.0, trans_sigma=0.002)
+    scene, model = ctx.upload_cloud(s, sn), ctx.upload_cloud(m, mn)
+    got, it, cv = ctx.icp_refine(scene, model, hyp)
+    ref, rit, rcv = O.refine_by_icp(s, sn, m, mn, hyp)
+    assert np.all(rcv == 0) and np.all(rit == 1)             # what the reference algorithm does
+    assert np.array_equal(cv, rcv) and np.array_equal(it, rit)
+    assert np.allclose(got, hyp, atol=1e-6) and np.allclose(ref, hyp, atol=1e-6)
+    # the exact minimiser (solver 2) refines such a hypothesis instead: a different answer than the reference's
+    got2, it2, cv2 = ctx.icp_refine(scene, model, hyp, ctx.icp_params(solver=2))
+    assert cv2.mean() > 0.9
+    scene.free(); model.free()
 
 
 def test_golden_fixture_through_the_c_abi(ctx):
