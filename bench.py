@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2")
+    ap.add_argument("--pipeline", type=int, default=0, help="0 = persistent fused kernel (default), 1 = per-iteration moments + solve kernels")
     ap.add_argument("--solver", type=int, default=0, help="0 = replay of the reference's LM (parity path), 1 = Gauss-Newton, 2 = exact per-iteration minimiser")
     ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the cpu_baseline sample (0 = auto)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -184,7 +185,7 @@ def main():
     H, ns, nm = wl["H"], wl["n_scene"], wl["n_model"]
     FPS = int(wl.get("frames_per_step", 1))   # frames of one rank in one step (C4: 16), one all-gather of winners per step
     model = ctx.upload_cloud(*model_np)
-    icp_p = ctx.icp_params(max_iter=wl["max_iter"], solver=args.solver)
+    icp_p = ctx.icp_params(max_iter=wl["max_iter"], solver=args.solver, pipeline=args.pipeline)
     lcp_p = ctx.lcp_params()
     # per-model structures are built once (like weights): not part of a frame's step
     g_icp = model.prepare_nn(icp_p.max_dist)
@@ -277,6 +278,7 @@ def main():
         p["iters"] = ctx.pinned_array((H,), np.int32)
         p["conv"] = ctx.pinned_array((H,), np.int32)
         p["scores"] = ctx.pinned_array((H,), np.float32)
+        p["win"] = ctx.pinned_array((1,), hop_b200.capi.POSE_REC_DTYPE)
         pin.append(p)
     import ctypes as C
     vp = C.c_void_p
@@ -288,12 +290,10 @@ def main():
         best = []
         for f in range(FPS):
             p = pin[(k * FPS + f) % N_FRAMES]
-            p["work"][...] = p["hyp"]
             ctx._check(ctx.L.hop_cloud_update(ctx.h, e2e_scene.handle, ptr(p["xyz"]), ptr(p["nrm"]), ptr(p["conf"]), ns))
-            e2e_scene.prepare_lcp_scene(lcp_p)
-            ctx._check(ctx.L.hop_icp_refine(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(icp_p), ptr(p["iters"]), ptr(p["conv"])))
-            ctx._check(ctx.L.hop_lcp_score(ctx.h, e2e_scene.handle, model.handle, ptr(p["work"]), H, C.byref(lcp_p), 0, ptr(p["scores"])))
-            best.append(int(np.argmax(p["scores"])))  # selectBest's arg-max on the host, like the reference
+            ctx._check(ctx.L.hop_refine_score_select(ctx.h, e2e_scene.handle, model.handle, None, ptr(p["hyp"]), H, C.byref(icp_p), C.byref(lcp_p), 0, 1,
+                                                     ptr(p["work"]), ptr(p["scores"]), ptr(p["iters"]), ptr(p["conv"]), ptr(p["win"])))
+            best.append(int(p["win"]["id"][0]))  # selectBest's arg-max
         return best
 
     for w in range(max(args.warmup, N_FRAMES)):
@@ -311,8 +311,8 @@ def main():
         e2e_ms += e0.elapsed_time(e1)
     barrier()
     clocks = sampler.summary()
-    h2d = FPS * (ns * 7 * 4 + 2 * H * 64)
-    d2h = FPS * (H * 64 + H * 8 + H * 4)
+    h2d = FPS * (ns * 7 * 4 + H * 64)               # the frame's cloud + the hypotheses, once
+    d2h = FPS * (H * 64 + H * 8 + H * 4 + 80)       # refined poses, iterations + flags, scores, the winner record
 
     # ---- max over ranks ----
     if world > 1:
@@ -330,7 +330,7 @@ def main():
         e2e_value = world * FPS * H * args.steps / (e2e_ms * 1e-3)
         # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
         # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
-        fused = args.solver != 1
+        fused = args.pipeline != 1
         corr_ms, corr_n = prof["icp_fused" if fused else "icp_correspond"]
         corr_bytes = float(iters_sum) * 32.0 * (ns + nm)
         achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
@@ -342,18 +342,19 @@ def main():
             "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": FPS, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
-                       "icp_solver": {0: "reference-lm-replay", 1: "gauss-newton", 2: "exact"}[args.solver], "mean_icp_iterations": iters_mean,
+                       "icp_solver": {0: "reference-lm-replay", 1: "gauss-newton", 2: "exact"}[args.solver],
+                       "icp_pipeline": {0: "persistent fused", 1: "moments+solve per iteration"}[args.pipeline], "mean_icp_iterations": iters_mean,
                        "nn_grid_icp": g_icp, "nn_grid_lcp": g_lcp,
                        "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps, "of": stage_note},
                        "kernel_ms": kernels},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "icp_fused_kernel" if fused else "icp_correspond_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": "icp_fused_kernel" if fused else "icp_moments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if fused else None,
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
                          "algorithmic_bytes_per_launch": corr_bytes / max(corr_n, 1), "kernel_ms_per_launch": corr_ms / max(corr_n, 1),
-                         "launches": int(corr_n),
+                         "launches": int(corr_n), "kernel_ms_per_step": corr_ms / args.steps,
                          "note": "algorithmic = 32 B x (N_scene + N_model) per executed ICP iteration per hypothesis (the brute-force "
                                  "streaming model of SURVEY 8d); the kernel itself gathers from an L2-resident voxel grid, so real DRAM "
                                  "traffic (`traffic`, ncu) is far below it; what bounds it is the L1TEX pipe (81.7 % of peak at the headline "

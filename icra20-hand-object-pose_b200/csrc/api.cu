@@ -169,6 +169,8 @@ int hop_create(int device, hop_ctx **out) {
     const char *v;
     if ((v = getenv("HOP_FUSED_VARIANT"))) ctx->tune.fused_variant = atoi(v);
     ctx->tune.fused_profile = getenv("HOP_FUSED_PROFILE") != nullptr;
+    if ((v = getenv("HOP_FUSED_SLOTS"))) ctx->tune.fused_slots = atoi(v);
+    if ((v = getenv("HOP_MOM_GROUP"))) ctx->tune.mom_group_chunks = atoi(v);
     if ((v = getenv("HOP_LCP_VARIANT"))) ctx->tune.lcp_variant = atoi(v);
     if ((v = getenv("HOP_VOXEL_MAX_FRAC"))) ctx->tune.voxel_max_frac = (float)atof(v);
     ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
@@ -357,9 +359,16 @@ int hop_icp_refine_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *
   NNGridHost *G = nullptr;
   int rc = hop_get_nn_grid(ctx, model, params->max_dist, 0.f, &G);
   if (rc != HOP_OK) return rc;
+  NNGridHost *Gs = nullptr;
+  if (params->mode == 1) {   // reciprocal correspondences: the scene's own grid (the reverse neighbour is within max_dist as well)
+    if (scene->n <= 0) { ctx->err = "hop_icp_refine: empty scene cloud"; return HOP_EINVAL; }
+    rc = hop_get_nn_grid(ctx, scene, params->max_dist * 1.01f, 0.f, &Gs);
+    if (rc != HOP_OK) return rc;
+  }
   rc = hop_cloud_query_order(ctx, scene);   // the scene is only iterated: walk it along a Morton curve
   if (rc != HOP_OK) return rc;
-  return hop_launch_icp(ctx, scene->dev_query(), model->dev(), G->dev, d_poses_inout, H, *params, d_iters_out, d_converged_out);
+  return hop_launch_icp(ctx, scene->dev_query(), model->dev(), G->dev, Gs ? &Gs->dev : nullptr, d_poses_inout, H, *params, d_iters_out,
+                        d_converged_out);
 }
 
 int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *poses_inout, int H, const hop_icp_params *params,
@@ -450,6 +459,61 @@ int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H
   int rc = hop_launch_topk(ctx, d_poses, d_scores, H, K, id_offset, frame, d_out);
   if (rc == HOP_OK) cudaMemcpyAsync(out, d_out, rb, cudaMemcpyDeviceToHost, ctx->stream);
   if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
+// ---- refineByICP + selectBest in one call ------------------------------------------------------------------------------------
+int hop_refine_score_select_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model_icp, hop_cloud *model_lcp, float *d_poses_inout, int H,
+                                const hop_icp_params *icp, const hop_lcp_params *lcp, int use_weights, int K, int32_t id_offset, int32_t frame,
+                                int32_t *d_iters, int32_t *d_conv, float *d_scores, hop_pose_rec *d_winners) {
+  HOP_ENTER(ctx);
+  if (!ctx || !scene || !model_icp || !icp || !lcp || H < 0 || K < 0 || (H > 0 && (!d_poses_inout || !d_scores)) || (K > 0 && !d_winners)) {
+    if (ctx) ctx->err = "hop_refine_score_select: bad arguments";
+    return HOP_EINVAL;
+  }
+  if (!model_lcp) model_lcp = model_icp;
+  int rc = HOP_OK;
+  if (H > 0) {
+    // the scene grid of the scoring pass depends on the frame only: built on the second stream while the ICP runs
+    if (scene->n > 0 && model_lcp->n > 0 && lcp->dist > 0.f) {
+      rc = hop_cloud_prepare_nn_async(ctx, scene, lcp->dist * 1.01f, 0.f);
+      if (rc != HOP_OK) return rc;
+    }
+    rc = hop_icp_refine_dev(ctx, scene, model_icp, d_poses_inout, H, icp, d_iters, d_conv);
+    if (rc != HOP_OK) return rc;
+    rc = hop_lcp_score_dev(ctx, scene, model_lcp, d_poses_inout, H, lcp, use_weights, d_scores);
+    if (rc != HOP_OK) return rc;
+  }
+  if (K > 0) rc = hop_launch_topk(ctx, d_poses_inout, d_scores, H, K, id_offset, frame, d_winners);
+  return rc;
+}
+
+int hop_refine_score_select(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model_icp, hop_cloud *model_lcp, const float *poses_in, int H,
+                            const hop_icp_params *icp, const hop_lcp_params *lcp, int use_weights, int K, float *poses_out,
+                            float *scores_out, int32_t *iters_out, int32_t *converged_out, hop_pose_rec *winners) {
+  HOP_ENTER(ctx);
+  if (!ctx || H < 0 || K < 0 || (H > 0 && !poses_in) || (K > 0 && !winners)) { if (ctx) ctx->err = "hop_refine_score_select: bad arguments"; return HOP_EINVAL; }
+  if (H == 0 && K == 0) return HOP_OK;
+  auto up = [](size_t v) { return (v + 255) / 256 * 256; };
+  const size_t pb = up(sizeof(float) * 16 * (size_t)H), ib = up(sizeof(int32_t) * (size_t)H), sb = up(sizeof(float) * (size_t)H);
+  const size_t rb = up(sizeof(hop_pose_rec) * (size_t)K);
+  char *d = (char *)ctx->ensure_io(pb + 2 * ib + sb + rb + 256);
+  if (!d) { ctx->err = "hop_refine_score_select: staging allocation failed"; return HOP_ENOMEM; }
+  float *d_poses = (float *)d;
+  int32_t *d_it = (int32_t *)(d + pb), *d_cv = (int32_t *)(d + pb + ib);
+  float *d_scores = (float *)(d + pb + 2 * ib);
+  hop_pose_rec *d_rec = (hop_pose_rec *)(d + pb + 2 * ib + sb);
+  if (H > 0) HOP_CUDA(ctx, cudaMemcpyAsync(d_poses, poses_in, sizeof(float) * 16 * (size_t)H, cudaMemcpyHostToDevice, ctx->stream));
+  int rc = hop_refine_score_select_dev(ctx, scene, model_icp, model_lcp, d_poses, H, icp, lcp, use_weights, K, 0, 0, d_it, d_cv, d_scores, d_rec);
+  if (rc != HOP_OK) return rc;
+  if (H > 0) {
+    if (poses_out) HOP_CUDA(ctx, cudaMemcpyAsync(poses_out, d_poses, sizeof(float) * 16 * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    if (scores_out) HOP_CUDA(ctx, cudaMemcpyAsync(scores_out, d_scores, sizeof(float) * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    if (iters_out) HOP_CUDA(ctx, cudaMemcpyAsync(iters_out, d_it, sizeof(int32_t) * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+    if (converged_out) HOP_CUDA(ctx, cudaMemcpyAsync(converged_out, d_cv, sizeof(int32_t) * (size_t)H, cudaMemcpyDeviceToHost, ctx->stream));
+  }
+  if (K > 0) HOP_CUDA(ctx, cudaMemcpyAsync(winners, d_rec, sizeof(hop_pose_rec) * (size_t)K, cudaMemcpyDeviceToHost, ctx->stream));
   HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return HOP_OK;
 }

@@ -222,6 +222,8 @@ struct ProfSpan { int kind; cudaEvent_t a, b; };
 struct HopTuning {
   int fused_variant = 0;      // HOP_FUSED_VARIANT: 1 = 256-thread CTAs, 2 = 128-thread CTAs, 0 = by batch size
   bool fused_profile = false; // HOP_FUSED_PROFILE: per-phase cycle accounting of icp_fused_kernel
+  int fused_slots = 0;        // HOP_FUSED_SLOTS: hypotheses per CTA at a time (0 = the batch's fair share, capped by the CTA's warps)
+  int mom_group_chunks = 0;   // HOP_MOM_GROUP: 512-point chunks per work item of icp_moments_kernel (0 = auto)
   int lcp_variant = 0;        // HOP_LCP_VARIANT: resident CTAs per SM of lcp_score_kernel
   float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
@@ -317,8 +319,8 @@ int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, N
 void hop_free_nn_grid(NNGridHost *g);
 int hop_cloud_query_order(hop_ctx *ctx, hop_cloud *cloud);  // (re)builds d_pw_q / d_nv_q when stale
 // implemented in icp_lcp.cu
-int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, float *d_poses, int H,
-                   const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv);
+int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, const NNGridDev *scene_grid,
+                   float *d_poses, int H, const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv);
 int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_by_index, const CloudDev &model, const NNGridDev &model_grid,
                    const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
                    float *d_scores);

@@ -8,16 +8,22 @@
 //     nearest-neighbour grid never move; the SCENE is carried into the model frame by X = pose^-1 and ICP iterates
 //     on X.  The point-to-plane objective is frame invariant, and the refined pose is simply X_final^-1
 //     ( = T_icp^-1 * pose of PoseEstimator.cpp:267 ).
-//   * The work is gather bound (one voxel cell + a short candidate list + one normal per scene point, all L2
-//     resident), so it is laid out FLAT: one thread per (hypothesis, scene point) at full occupancy, instead of a
-//     warp that owns a hypothesis for the whole ICP (which leaves the SMs latency bound at small batch sizes and
-//     pays the slowest hypothesis' tail).  Each ICP iteration is two launches:
-//        icp_correspond_kernel  grid (scene tiles, hypotheses): nearest neighbour + both rejectors, writes one
-//                               32-byte correspondence record per scene point (coalesced, two float4 planes);
-//        icp_solve_kernel       one warp team per hypothesis: streams the records, accumulates the moments of the
-//                               point-to-plane objective in registers, warp-shuffle reduction, cooperative small
-//                               solve, PCL's convergence rule, state update.
-//     Converged hypotheses retire at once: their tiles exit at the first instruction of later iterations.
+//   * The work is gather bound (one voxel cell + a short candidate list + one normal per scene point, all L2 resident) and
+//     the per-iteration solve is the reference's SERIAL float LM (lm_replay.cuh), tens of thousands of dependent cycles that
+//     want ~250 registers.  Two shapes, chosen per call (hop_icp_params.pipeline):
+//       0 (default) persistent fused: the whole ICP of a hypothesis inside one CTA (icp_fused_kernel, ONE launch per batch);
+//          a CTA carries up to one hypothesis per warp, so the solves of a CTA run in parallel on its warps and a hypothesis
+//          whose LM takes 300 evaluations (2 % do; the mean is 31) delays nobody but itself.
+//       1 iteration-synchronous: per ICP iteration
+//            icp_moments_kernel  persistent CTAs stride over (active hypothesis, group of scene chunks) work items at full
+//                                occupancy: correspondences -> 32-byte records in SHARED memory -> the 13x13 moments of the
+//                                point-to-plane residual; 93 partial sums per item go to HBM (384 B; never the records);
+//            icp_solve_kernel    one warp per active hypothesis with the register file to itself: fixed-order sum of the
+//                                partials, the LM replay, PCL's convergence rule, state update, survivors -> next list.
+//          Re-balances the machine every iteration, but every launch waits for its slowest LM run (measured: 3.7 vs 2.3 ms at
+//          2 k x 10 k x 1024, 31.8 vs 28.2 ms at 10 k x 10 k x 16 384).  The point-to-point mode (mode 1, a closed-form solve)
+//          runs on this pipeline; for mode 0 it is the cross-check of the fused kernel (test_icp_pipelines_agree).
+//     Converged hypotheses retire at once in both.
 //   * K5 is one flat launch (thread per hypothesis x scene point) + a fixed-order reduction of the tile partials.
 //   * No tensor cores: these are gathers and small reductions, not dense contractions.
 #include <cfloat>
@@ -85,70 +91,6 @@ __device__ __forceinline__ void so3_exp(float wx, float wy, float wz, float *R) 
   R[6] = -a * wy + b * wx * wz;        R[7] = a * wx + b * wy * wz;         R[8] = 1.f - b * (wx * wx + wy * wy);
 }
 
-// ------------------------------------------------------------------------------------------------------------
-// accumulation policies for the point-to-plane step
-//   residual of a correspondence under an increment (dR, dt) applied to the already-moved point p:
-//       r = n . (dR p + dt - m) = u . [vec(dR - I); dt] + c ,   u = [n (x) p ; n] (12),  c = n . (p - m)
-//   SOLVER 0 ("exact"): accumulate the 13x13 moment matrix of a = [u; c]  -> the full nonlinear objective
-//       f(dR,dt) = y^T A y is then known in closed form and is minimised to convergence (what PCL's LM does with
-//       its 400-evaluation budget) without revisiting the points.
-//   SOLVER 1 ("gn"): accumulate J^T J (21) and J^T c (6), J = [p x n ; n]: one Gauss-Newton step per iteration.
-// ------------------------------------------------------------------------------------------------------------
-template <int SOLVER> struct Acc;
-
-template <> struct Acc<0> {
-  static constexpr int NA = 91;          // upper triangle of 13x13
-  static constexpr int NACC = NA + 2;    // + sum d^2, count
-  float a[NACC];
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-  }
-  __device__ __forceinline__ void add(float3 p, float3 n, float c, float d2) {
-    float v[13];
-    v[0] = n.x * p.x; v[1] = n.x * p.y; v[2] = n.x * p.z;
-    v[3] = n.y * p.x; v[4] = n.y * p.y; v[5] = n.y * p.z;
-    v[6] = n.z * p.x; v[7] = n.z * p.y; v[8] = n.z * p.z;
-    v[9] = n.x; v[10] = n.y; v[11] = n.z;
-    v[12] = c;
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 13; ++i)
-#pragma unroll
-      for (int j = i; j < 13; ++j) { a[k] = fmaf(v[i], v[j], a[k]); ++k; }
-    a[NA] += d2;
-    a[NA + 1] += 1.f;
-  }
-};
-
-template <> struct Acc<1> {
-  static constexpr int NA = 28;          // 21 (J^T J upper) + 6 (J^T c) + 1 (c^2)
-  static constexpr int NACC = NA + 2;
-  float a[NACC];
-  __device__ __forceinline__ void clear() {
-#pragma unroll
-    for (int k = 0; k < NACC; ++k) a[k] = 0.f;
-  }
-  __device__ __forceinline__ void add(float3 p, float3 n, float c, float d2) {
-    float J[6];
-    J[0] = p.y * n.z - p.z * n.y; J[1] = p.z * n.x - p.x * n.z; J[2] = p.x * n.y - p.y * n.x;
-    J[3] = n.x; J[4] = n.y; J[5] = n.z;
-    int k = 0;
-#pragma unroll
-    for (int i = 0; i < 6; ++i)
-#pragma unroll
-      for (int j = i; j < 6; ++j) { a[k] = fmaf(J[i], J[j], a[k]); ++k; }
-#pragma unroll
-    for (int i = 0; i < 6; ++i) a[21 + i] = fmaf(J[i], c, a[21 + i]);
-    a[27] = fmaf(c, c, a[27]);
-    a[NA] += d2;
-    a[NA + 1] += 1.f;
-  }
-};
-
-constexpr int NACC_PAD = 96;
-constexpr int WORK = 96;   // per warp: team totals
-
 __device__ __forceinline__ int tri13(int i, int j) {  // index of (i,j), i<=j, in the row-major upper triangle
   return i * 13 - (i * (i - 1)) / 2 + (j - i);
 }
@@ -158,8 +100,7 @@ __device__ __forceinline__ int tri13(int i, int j) {  // index of (i,j), i<=j, i
 // sums: the 91 reduced moments (shared memory).  Register resident: lane i < 13 owns row i of A, (R,t) and every
 // small matrix are replicated in all lanes, rows meet through warp shuffles (no shared-memory round trips, no
 // local memory).  All lanes return the same (R,t).
-__device__ __forceinline__ void solve_exact(const float *sums, float *W, int lane, float *R, float *t) {
-  (void)W;
+__device__ __forceinline__ void solve_exact(const float *sums, int lane, float *R, float *t, int max_inner) {
   const unsigned FULL = 0xffffffffu;
   float Arow[13];
   {
@@ -185,7 +126,7 @@ __device__ __forceinline__ void solve_exact(const float *sums, float *W, int lan
   float lambda = 0.f;
   const float ftol = 3.4526698e-4f;  // sqrt(FLT_EPSILON)
   int rejects = 0;
-  for (int inner = 0; inner < 12; ++inner) {
+  for (int inner = 0; inner < max_inner; ++inner) {
     if (!(f > 0.f)) break;
     // Jacobian of y w.r.t. (w, tau): d vec(R)/dw_k = vec([e_k]x R), d t/d tau = I.   B = A J, this lane's row:
     float B[6];
@@ -280,29 +221,10 @@ __device__ __forceinline__ void solve_exact(const float *sums, float *W, int lan
   }
 }
 
-// One Gauss-Newton step from the 28 reduced sums
-__device__ void solve_gn(const float *sums, float *R, float *t) {
-  float Hl[36], gl[6], dx[6];
-  int k = 0;
-#pragma unroll
-  for (int i = 0; i < 6; ++i)
-#pragma unroll
-    for (int j = i; j < 6; ++j) { float v = sums[k++]; Hl[6 * i + j] = v; Hl[6 * j + i] = v; }
-#pragma unroll
-  for (int i = 0; i < 6; ++i) gl[i] = sums[21 + i];
-  float lambda = 0.f;
-  bool ok = chol_solve6(Hl, gl, lambda, dx);
-  for (int r = 0; !ok && r < 8; ++r) { lambda = fmaxf(lambda * 10.f, 1e-6f); ok = chol_solve6(Hl, gl, lambda, dx); }
-  if (!ok) { dx[0] = dx[1] = dx[2] = dx[3] = dx[4] = dx[5] = 0.f; }
-  so3_exp(dx[0], dx[1], dx[2], R);
-  t[0] = dx[3]; t[1] = dx[4]; t[2] = dx[5];
-}
-
-
 // The reference's own solver (PCL's TransformationEstimationPointToPlane = float lmdif), replayed on the moments: see
 // lm_replay.cuh.  Called by all lanes of one warp; returns the increment W(x) in all lanes.
-__device__ __noinline__ void solve_lm_replay(const float *sums, int lane, float *R, float *t) {
-  lmr::MomentsDev A{sums, lane};
+__device__ __noinline__ void solve_lm_replay(const float *sums, int lane, lmr::LmrScratch *scr, float *R, float *t) {
+  lmr::MomentsDev A{sums, lane, scr};
   float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   lmr::lm_replay_solve(A, x, nullptr);
   float y[13];
@@ -316,12 +238,13 @@ __device__ __noinline__ void solve_lm_replay(const float *sums, int lane, float 
 // Returns false when the reference's LM would run away along an unconstrained translation (lm_replay.cuh,
 // translation_unconstrained): the caller ends the ICP of the hypothesis "not converged", pose unchanged.
 template <int SOLVER>
-__device__ __forceinline__ bool solve_increment(const float *sums, int lane, float *R, float *t) {
+__device__ __forceinline__ bool solve_increment(const float *sums, int lane, lmr::LmrScratch *scr, float *R, float *t) {
   if constexpr (SOLVER == 0) {
-    if (lmr::translation_unconstrained(lmr::MomentsDev{sums, lane})) return false;
-    solve_lm_replay(sums, lane, R, t);
-  } else if constexpr (SOLVER == 1) solve_gn(sums, R, t);
-  else solve_exact(sums, nullptr, lane, R, t);
+    const lmr::MomentsDev A{sums, lane, scr};
+    lmr::moments_prepare(A);
+    if (lmr::translation_unconstrained(A)) return false;
+    solve_lm_replay(sums, lane, scr, R, t);
+  } else solve_exact(sums, lane, R, t, SOLVER == 1 ? 1 : 12);   // (a Gauss-Newton step = the first step of the exact minimiser)
   return true;
 }
 
@@ -364,55 +287,298 @@ __global__ void icp_init_kernel(const float *__restrict__ poses, int H, IcpState
   list0[h] = h;
 }
 
-struct CorrArgs {
+constexpr int SLICE = 24;
+
+__host__ __device__ constexpr int tri_row(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i; }
+__host__ __device__ constexpr int tri_col(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i + k; }
+
+template <int S, int E>
+__device__ __forceinline__ void acc_one(float (&acc)[SLICE], const float (&v)[13], float d2) {
+  constexpr int k = SLICE * S + E;
+  if constexpr (k < 91) acc[E] = fmaf(v[tri_row(k)], v[tri_col(k)], acc[E]);
+  else if constexpr (k == 91) acc[E] += d2;
+  else if constexpr (k == 92) acc[E] += 1.f;
+}
+template <int S, int... E>
+__device__ __forceinline__ void acc_slice(float (&acc)[SLICE], const float (&v)[13], float d2, std::integer_sequence<int, E...>) {
+  (acc_one<S, E>(acc, v, d2), ...);
+}
+
+// phase B: this warp's slice (24 of the 91 + 2 sums) of the moments over records [begin, end) in shared memory
+template <int S>
+__device__ __forceinline__ void accumulate_chunk(float (&acc)[SLICE], const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
+  for (int i = begin + lane; i < end; i += 32) {
+    const float4 q1 = rec1[i];
+    if (!(q1.w >= 0.f)) continue;
+    const float4 q0 = rec0[i];
+    float v[13];
+    v[0] = q1.x * q0.x; v[1] = q1.x * q0.y; v[2] = q1.x * q0.z;
+    v[3] = q1.y * q0.x; v[4] = q1.y * q0.y; v[5] = q1.y * q0.z;
+    v[6] = q1.z * q0.x; v[7] = q1.z * q0.y; v[8] = q1.z * q0.z;
+    v[9] = q1.x; v[10] = q1.y; v[11] = q1.z;
+    v[12] = q0.w;
+    acc_slice<S>(acc, v, q1.w, std::make_integer_sequence<int, SLICE>());
+  }
+}
+
+// phase A: CorrespondenceEstimation (exact 1-NN, d^2 <= max_dist^2) + CorrespondenceRejectorSurfaceNormal (rotated source
+// normal . target normal > cos(angle)) of scene points [c0, c0 + cnt) -> 32-byte records in shared memory:
+// rec0 = (p.xyz, n.(p - m)), rec1 = (n.xyz, d^2 | -1 when there is no correspondence)
+template <int THREADS>
+__device__ __forceinline__ void correspond_chunk(const CloudDev &scene, const float4 *__restrict__ model_nv, const NNGridDev &grid,
+                                                 const Rigid &X, float cos_thr, float max_d2, int c0, int cnt, float4 *rec0,
+                                                 float4 *rec1, int tid) {
+  for (int i = tid; i < cnt; i += THREADS) {
+    const float4 sp = __ldg(&scene.pw[c0 + i]);
+    const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
+    float bd; float4 bp;
+    const int j = nn_query(grid, p.x, p.y, p.z, bd, bp);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, -1.f);
+    if (j >= 0 && bd <= max_d2) {
+      const float4 sn = __ldg(&scene.nv[c0 + i]);
+      const float4 mn = __ldg(&model_nv[j]);
+      const float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
+      const float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
+      if (dot >= cos_thr) {
+        r0 = make_float4(p.x, p.y, p.z, mn.x * (p.x - bp.x) + mn.y * (p.y - bp.y) + mn.z * (p.z - bp.z));
+        r1 = make_float4(mn.x, mn.y, mn.z, bd);
+      }
+    }
+    rec0[i] = r0;
+    rec1[i] = r1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// K4, pipeline 0: one ICP iteration of every active hypothesis = icp_moments_kernel + icp_solve_kernel
+// ------------------------------------------------------------------------------------------------------------
+struct MomArgs {
   CloudDev scene;
   const float4 *model_nv;
   NNGridDev grid;
   const IcpState *state;   // already offset to the batch
   const int *list;         // active hypotheses of this iteration (batch-local ids)
   const int *n_active;
-  int n_tiles;
+  int n_groups, group_pts; // a work item = (position in the list, group of group_pts scene points)
   float cos_thr;           // smallest float whose double value exceeds cos(angle)
   float max_d2;
-  float4 *rec0, *rec1;     // [position in list][n_padded]: (p.xyz, n.(p-m)) and (n.xyz, d^2 | -1 when rejected)
+  float *partial;          // [position in list][n_groups][96]: the item's 91 moments, sum d^2, count (mode 1: 17 Kabsch sums)
+  NNGridDev sgrid;         // mode 1: the scene's own grid (reciprocal correspondences)
 };
 
-// K4a: correspondence estimation + rejection.  CorrespondenceEstimation (exact 1-NN, d^2 <= max_dist^2) and
-// CorrespondenceRejectorSurfaceNormal (rotated source normal . target normal > cos(angle)).
-// Persistent CTAs stride over the (active hypothesis, scene tile) work items; one thread per scene point.
-__global__ void __launch_bounds__(TILE) icp_correspond_kernel(CorrArgs a) {
-  const int n_work = __ldg(a.n_active) * a.n_tiles;
+template <int THREADS, int CHUNK, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icp_moments_kernel(MomArgs a) {
+  constexpr int PARTS = THREADS / 128;
+  __shared__ __align__(16) float4 rec0[CHUNK], rec1[CHUNK];
+  __shared__ __align__(16) float s_sums[PARTS][96];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = warp & 3, part = warp >> 2;
+  const int n_work = __ldg(a.n_active) * a.n_groups;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
-    const int pos = w / a.n_tiles, tile = w - pos * a.n_tiles;
-    const IcpState *st = a.state + __ldg(&a.list[pos]);
-    const Rigid X = state_load(st->X);
-    const int i = tile * TILE + threadIdx.x;
-    const float4 sp = __ldg(&a.scene.pw[i]);
-    const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
-    float bd; float4 bp;
-    const int j = nn_query(a.grid, p.x, p.y, p.z, bd, bp);
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, -1.f);
-    if (j >= 0 && bd <= a.max_d2) {
-      const float4 sn = __ldg(&a.scene.nv[i]);
-      const float4 mn = __ldg(&a.model_nv[j]);
-      const float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
-      const float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
-      if (dot >= a.cos_thr) {
-        r0 = make_float4(p.x, p.y, p.z, mn.x * (p.x - bp.x) + mn.y * (p.y - bp.y) + mn.z * (p.z - bp.z));
-        r1 = make_float4(mn.x, mn.y, mn.z, bd);
+    const int pos = w / a.n_groups, g = w - pos * a.n_groups;
+    const Rigid X = state_load(a.state[__ldg(&a.list[pos])].X);
+    const int begin = g * a.group_pts, end = min(a.scene.n_padded, begin + a.group_pts);
+    float acc[SLICE];
+#pragma unroll
+    for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
+    for (int c0 = begin; c0 < end; c0 += CHUNK) {
+      const int cnt = min(CHUNK, end - c0);
+      correspond_chunk<THREADS>(a.scene, a.model_nv, a.grid, X, a.cos_thr, a.max_d2, c0, cnt, rec0, rec1, tid);
+      __syncthreads();
+      const int per = (cnt + PARTS - 1) / PARTS;
+      const int hb = min(part * per, cnt), he = min(hb + per, cnt);
+      switch (slice) {
+        case 0: accumulate_chunk<0>(acc, rec0, rec1, hb, he, lane); break;
+        case 1: accumulate_chunk<1>(acc, rec0, rec1, hb, he, lane); break;
+        case 2: accumulate_chunk<2>(acc, rec0, rec1, hb, he, lane); break;
+        default: accumulate_chunk<3>(acc, rec0, rec1, hb, he, lane); break;
       }
+      __syncthreads();
     }
-    const size_t o = (size_t)pos * a.scene.n_padded + i;
-    a.rec0[o] = r0;
-    a.rec1[o] = r1;
+    float mine = 0.f;
+#pragma unroll
+    for (int e = 0; e < SLICE; ++e) {
+      const float tot = warp_sum(acc[e]);
+      if (lane == e) mine = tot;
+    }
+    float *out = a.partial + (size_t)w * 96;
+    if (PARTS == 1) {
+      if (lane < SLICE) out[SLICE * slice + lane] = mine;
+    } else {
+      if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
+      __syncthreads();
+      for (int k = tid; k < 96; k += THREADS) {
+        float t = s_sums[0][k];
+#pragma unroll
+        for (int q = 1; q < PARTS; ++q) t += s_sums[q][k];
+        out[k] = t;
+      }
+      // (the next item writes s_sums only after the barriers of its own chunk loop)
+    }
   }
 }
 
+// ---- mode 1: Utils::runICP(segment, model, T, max_corres_dist) (Utils.cpp:135-164) = PCL's default point-to-point ICP with
+// reciprocal correspondences and TransformationEstimationSVD (pcl::umeyama without scaling) ------------------------------------
+constexpr int KAB = 17;   // sum p (3), sum m (3), sum p m^T (9, row = p), sum d^2, count
+
+// CorrespondenceEstimation::determineReciprocalCorrespondences: scene point i -> nearest model point j (d^2 <= max^2) -> the
+// nearest SCENE point of j must be i again (and within max).  The scene does not move either: the reverse query is made with
+// X^-1 m_j against the scene's own grid (a rigid motion keeps distances); "is i" = the same coordinates (two scene points with
+// identical coordinates are both accepted, PCL keeps the one whose index the kd-tree returns).
+template <int THREADS>
+__device__ __forceinline__ void correspond_chunk_reciprocal(const CloudDev &scene, const NNGridDev &grid, const NNGridDev &sgrid,
+                                                            const Rigid &X, const Rigid &Xi, float max_d2, int c0, int cnt, float4 *rec0,
+                                                            float4 *rec1, int tid) {
+  for (int i = tid; i < cnt; i += THREADS) {
+    const float4 sp = __ldg(&scene.pw[c0 + i]);
+    const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
+    float bd; float4 bp;
+    const int j = nn_query(grid, p.x, p.y, p.z, bd, bp);
+    float4 r0 = make_float4(0.f, 0.f, 0.f, -1.f), r1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (j >= 0 && bd <= max_d2) {
+      const float3 q = rigid_apply(Xi, bp.x, bp.y, bp.z);
+      float ed; float4 ep;
+      const int k = nn_query(sgrid, q.x, q.y, q.z, ed, ep);
+      if (k >= 0 && ed <= max_d2 && ep.x == sp.x && ep.y == sp.y && ep.z == sp.z) {
+        r0 = make_float4(p.x, p.y, p.z, bd);
+        r1 = make_float4(bp.x, bp.y, bp.z, 0.f);
+      }
+    }
+    rec0[i] = r0;
+    rec1[i] = r1;
+  }
+}
+
+template <int THREADS, int CHUNK, int MINB>
+__global__ void __launch_bounds__(THREADS, MINB) icp_kabsch_sums_kernel(MomArgs a) {
+  constexpr int NW = THREADS / 32;
+  __shared__ __align__(16) float4 rec0[CHUNK], rec1[CHUNK];
+  __shared__ float s_sums[NW][KAB];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_work = __ldg(a.n_active) * a.n_groups;
+  for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
+    const int pos = w / a.n_groups, g = w - pos * a.n_groups;
+    const Rigid X = state_load(a.state[__ldg(&a.list[pos])].X);
+    const Rigid Xi = rigid_inverse(X);
+    const int begin = g * a.group_pts, end = min(a.scene.n_padded, begin + a.group_pts);
+    float acc[KAB];
+#pragma unroll
+    for (int e = 0; e < KAB; ++e) acc[e] = 0.f;
+    for (int c0 = begin; c0 < end; c0 += CHUNK) {
+      const int cnt = min(CHUNK, end - c0);
+      correspond_chunk_reciprocal<THREADS>(a.scene, a.grid, a.sgrid, X, Xi, a.max_d2, c0, cnt, rec0, rec1, tid);
+      __syncthreads();
+      for (int i = tid; i < cnt; i += THREADS) {
+        const float4 q0 = rec0[i];
+        if (!(q0.w >= 0.f)) continue;
+        const float4 q1 = rec1[i];
+        acc[0] += q0.x; acc[1] += q0.y; acc[2] += q0.z;
+        acc[3] += q1.x; acc[4] += q1.y; acc[5] += q1.z;
+        acc[6] = fmaf(q0.x, q1.x, acc[6]); acc[7] = fmaf(q0.x, q1.y, acc[7]); acc[8] = fmaf(q0.x, q1.z, acc[8]);
+        acc[9] = fmaf(q0.y, q1.x, acc[9]); acc[10] = fmaf(q0.y, q1.y, acc[10]); acc[11] = fmaf(q0.y, q1.z, acc[11]);
+        acc[12] = fmaf(q0.z, q1.x, acc[12]); acc[13] = fmaf(q0.z, q1.y, acc[13]); acc[14] = fmaf(q0.z, q1.z, acc[14]);
+        acc[15] += q0.w; acc[16] += 1.f;
+      }
+      __syncthreads();
+    }
+#pragma unroll
+    for (int e = 0; e < KAB; ++e) {
+      const float tot = warp_sum(acc[e]);
+      if (lane == 0) s_sums[warp][e] = tot;
+    }
+    __syncthreads();
+    float *out = a.partial + (size_t)w * 96;
+    if (tid < 96) {
+      float t = 0.f;
+      if (tid < KAB) {
+#pragma unroll
+        for (int q = 0; q < NW; ++q) t += s_sums[q][tid];
+      }
+      out[tid] = t;
+    }
+    __syncthreads();
+  }
+}
+
+// eigen decomposition of a symmetric 3x3 (cyclic Jacobi, double): A -> diagonal, V = eigenvectors in columns
+__device__ __forceinline__ void sym3_jacobi(double (&A)[3][3], double (&V)[3][3]) {
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) V[i][j] = i == j ? 1.0 : 0.0;
+  for (int sweep = 0; sweep < 12; ++sweep) {
+    const double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int q = p + 1; q < 3; ++q) {
+        if (A[p][q] == 0.0) continue;
+        const double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+        const double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+        const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { const double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+      }
+  }
+}
+
+// Kabsch / Umeyama (no scaling) from the 17 sums: R, t minimising sum |R p + t - m|^2.  S = sum (m - cm)(p - cp)^T = U D V^T,
+// R = U diag(1, 1, det) V^T; the third columns of U and V are built as cross products, which folds the reflection case in.
+// Returns false for a degenerate configuration (rank < 2): the caller keeps the identity increment.
+__device__ __forceinline__ bool solve_kabsch(const float *sums, float *R, float *t) {
+  const double n = (double)sums[16];
+  double cp[3], cm[3], S[3][3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { cp[k] = (double)sums[k] / n; cm[k] = (double)sums[3 + k] / n; }
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) S[r][c] = (double)sums[6 + 3 * c + r] - n * cm[r] * cp[c];   // sums[6 + 3 a + b] = sum p_a m_b
+  double A[3][3], V[3][3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+#pragma unroll
+    for (int c = 0; c < 3; ++c) A[r][c] = S[0][r] * S[0][c] + S[1][r] * S[1][c] + S[2][r] * S[2][c];
+  sym3_jacobi(A, V);
+  // the two largest eigenvalues (columns i0, i1)
+  const double e0 = A[0][0], e1 = A[1][1], e2 = A[2][2];
+  int i0 = 0, i1 = 1;
+  if (e0 <= e1 && e0 <= e2) { i0 = 1; i1 = 2; } else if (e1 <= e0 && e1 <= e2) { i0 = 0; i1 = 2; }
+  const double d0 = i0 == 0 ? e0 : e1, d1 = i1 == 1 ? e1 : e2;
+  const double big = fmax(d0, d1), small = fmin(d0, d1);
+  if (!(big > 0.0) || !(small > 1e-24 * big)) return false;
+  double v0[3], v1[3], u0[3], u1[3];
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { v0[k] = i0 == 0 ? V[k][0] : V[k][1]; v1[k] = i1 == 1 ? V[k][1] : V[k][2]; }
+  const double is0 = 1.0 / sqrt(d0), is1 = 1.0 / sqrt(d1);
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    u0[r] = (S[r][0] * v0[0] + S[r][1] * v0[1] + S[r][2] * v0[2]) * is0;
+    u1[r] = (S[r][0] * v1[0] + S[r][1] * v1[1] + S[r][2] * v1[2]) * is1;
+  }
+  const double v2[3] = {v0[1] * v1[2] - v0[2] * v1[1], v0[2] * v1[0] - v0[0] * v1[2], v0[0] * v1[1] - v0[1] * v1[0]};
+  const double u2[3] = {u0[1] * u1[2] - u0[2] * u1[1], u0[2] * u1[0] - u0[0] * u1[2], u0[0] * u1[1] - u0[1] * u1[0]};
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    double Rr[3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) { Rr[c] = u0[r] * v0[c] + u1[r] * v1[c] + u2[r] * v2[c]; R[3 * r + c] = (float)Rr[c]; }
+    t[r] = (float)(cm[r] - (Rr[0] * cp[0] + Rr[1] * cp[1] + Rr[2] * cp[2]));
+  }
+  return true;
+}
+
 struct SolveArgs {
-  const float4 *rec0, *rec1;
-  int n_padded;
-  IcpState *state;     // offset to the batch
-  float *poses;        // offset to the batch: Hb x 16, written when a hypothesis finishes converged
+  const float *partial;  // [position in list][n_groups][96]
+  int n_groups;
+  IcpState *state;       // offset to the batch
+  float *poses;          // offset to the batch: Hb x 16, written when a hypothesis finishes converged
   int32_t *iters_out, *conv_out;  // offset to the batch (may be null)
   const int *list;       // active hypotheses of this iteration
   const int *n_active;
@@ -422,96 +588,58 @@ struct SolveArgs {
   double abs_mse_eps;
 };
 
-// K4b: TransformationEstimationPointToPlane (LM) + DefaultConvergenceCriteria for one hypothesis per warp team.
-template <int NW, int TEAM, int SOLVER>
-__global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
-  constexpr int NT = NW / TEAM;
-  using AccT = Acc<SOLVER == 1 ? 1 : 0>;
-  __shared__ __align__(16) float s_part[NW][NACC_PAD];
-  __shared__ __align__(16) float s_work[NW][WORK];
-  __shared__ float s_red[NW][32 * 33];
+// TransformationEstimationPointToPlane (the reference's LM) + DefaultConvergenceCriteria: one warp per active hypothesis, no
+// register cap (the LM replay keeps its 6x6 matrices, the double Gram matrix and its Cholesky factor in registers).
+constexpr int SOLVE_WARPS = 4;
+template <int SOLVER>
+__global__ void __launch_bounds__(SOLVE_WARPS * 32) icp_solve_kernel(SolveArgs a) {
+  __shared__ __align__(16) float s_tot[SOLVE_WARPS][96];
+  __shared__ __align__(16) lmr::LmrScratch s_scr[SOLVER == 0 ? SOLVE_WARPS : 1];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int team = warp / TEAM, tw = warp % TEAM;
-  const int pos = blockIdx.x * NT + team;
-  const bool active = pos < __ldg(a.n_active);
-  const int h = active ? __ldg(&a.list[pos]) : 0;
+  const int pos = blockIdx.x * SOLVE_WARPS + warp;
+  if (pos >= __ldg(a.n_active)) return;   // (no block-wide barrier below)
+  const int h = __ldg(&a.list[pos]);
   IcpState *st = a.state + h;
-
-  AccT acc;
-  acc.clear();
-  if (active) {
-    const float4 *r0 = a.rec0 + (size_t)pos * a.n_padded;
-    const float4 *r1 = a.rec1 + (size_t)pos * a.n_padded;
-    constexpr int STEP = 32 * TEAM, U = 4;  // n_padded is a multiple of 256 = 8 * 32: whole batches for TEAM <= 2
-    for (int i0 = tw * 32 + lane; i0 < a.n_padded; i0 += STEP * U) {
-      float4 q0[U], q1[U];
-#pragma unroll
-      for (int u = 0; u < U; ++u) {  // all loads of the batch in flight before the first use
-        const int i = i0 + u * STEP;
-        const bool in = i < a.n_padded;
-        q1[u] = in ? __ldcs(&r1[i]) : make_float4(0.f, 0.f, 0.f, -1.f);
-        q0[u] = in ? __ldcs(&r0[i]) : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-#pragma unroll
-      for (int u = 0; u < U; ++u)
-        if (q1[u].w >= 0.f) acc.add(make_float3(q0[u].x, q0[u].y, q0[u].z), make_float3(q1[u].x, q1[u].y, q1[u].z), q0[u].w, q1[u].w);
-    }
-  }
-  // ---- reduce inside the warp through a padded shared-memory transpose (32 accumulators at a time): lane l ends
-  //      with the totals of accumulators l, 32 + l, 64 + l; then across the team ----
-  float *my_part = s_part[warp];
+  float *sums = s_tot[warp];
   {
-    float *buf = s_red[warp];
-#pragma unroll
-    for (int c = 0; c < (AccT::NACC + 31) / 32; ++c) {
-#pragma unroll
-      for (int k = 0; k < 32; ++k)
-        if (32 * c + k < AccT::NACC) buf[k * 33 + lane] = acc.a[32 * c + k];
-      __syncwarp();
-      if (32 * c + lane < AccT::NACC) {
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < 32; ++j) s += buf[lane * 33 + j];
-        my_part[32 * c + lane] = s;
-      }
-      __syncwarp();
+    const float *p = a.partial + (size_t)pos * a.n_groups * 96;
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    for (int g = 0; g < a.n_groups; ++g) {   // fixed order: bits do not depend on which CTA produced which partial
+      t0 += __ldcs(p + g * 96 + lane); t1 += __ldcs(p + g * 96 + 32 + lane); t2 += __ldcs(p + g * 96 + 64 + lane);
     }
-  }
-  float *W = s_work[warp];
-  const float *sums = my_part;
-  if (TEAM > 1) {
-    __syncthreads();
-    if (tw != 0) return;  // the team's first warp sums the partial rows in a fixed order and solves
-    float *tot = W;
-    for (int k = lane; k < AccT::NACC; k += 32) {
-      float s = 0.f;
-#pragma unroll
-      for (int q = 0; q < TEAM; ++q) s += s_part[team * TEAM + q][k];
-      tot[k] = s;
-    }
-    sums = tot;
+    sums[lane] = t0; sums[32 + lane] = t1; sums[64 + lane] = t2;
   }
   __syncwarp();
-  if (!active) return;
-
-  const float cnt_f = sums[AccT::NA + 1];
-  const float sumd2 = sums[AccT::NA];
+  const float cnt_f = SOLVER == 3 ? sums[16] : sums[92], sumd2 = SOLVER == 3 ? sums[15] : sums[91];
   const int cnt = (int)(cnt_f + 0.5f);
   int iters = st->iters;
-  bool converged = false, finished = false;
+  bool converged = false, finished = false, runaway = false;
   Rigid X = state_load(st->X);
-  bool runaway = false;
   Rigid inc;
-  if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, inc.r, inc.t);
+  if constexpr (SOLVER == 3) {
+    // TransformationEstimationSVD works from 3 correspondences up; a degenerate set leaves the identity
+    if (cnt >= 3 && !solve_kabsch(sums, inc.r, inc.t)) {
+#pragma unroll
+      for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
+      inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
+    }
+  } else if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, &s_scr[SOLVER == 0 ? warp : 0], inc.r, inc.t);
+  if (SOLVER != 3 && cnt >= 6 && !runaway) {
+    bool finite = true;   // |q| > 1 inside the reference's LM gives NaN residuals; a step accepted there ends as a NaN transform
+#pragma unroll
+    for (int e = 0; e < 9; ++e) finite = finite && isfinite(inc.r[e]);
+    runaway = !(finite && isfinite(inc.t[0]) && isfinite(inc.t[1]) && isfinite(inc.t[2]));
+  }
   if (cnt < 3) {
     finished = true;  // "Not enough correspondences": hasConverged() false -> identity -> pose unchanged
   } else if (runaway) {
-    // the reference's LM slides the scene metres off the model here; its next iteration finds no correspondences
+    // the reference's LM slides the scene metres off the model here (or returns a NaN transform); its next iteration finds no
+    // correspondences: not converged, pose unchanged
     ++iters;
     finished = true;
-    if (tw == 0 && lane == 0) st->iters = iters;
+    if (lane == 0) st->iters = iters;
   } else {
-    if (cnt >= 6) {
+    if (SOLVER == 3 || cnt >= 6) {
     } else if (cnt >= 4) {
       // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
 #pragma unroll
@@ -534,7 +662,7 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
       }
     }
     finished = converged;
-    if (tw == 0 && lane == 0) {
+    if (lane == 0) {
 #pragma unroll
       for (int e = 0; e < 9; ++e) { st->X[e] = X.r[e]; st->inc[e] = inc.r[e]; }
 #pragma unroll
@@ -543,8 +671,8 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
       st->iters = iters;
     }
   }
-  if (!finished && tw == 0 && lane == 0) a.next_list[atomicAdd(a.next_count, 1)] = h;
-  if (finished && tw == 0 && lane == 0) {
+  if (!finished && lane == 0) a.next_list[atomicAdd(a.next_count, 1)] = h;
+  if (finished && lane == 0) {
     st->status = converged ? 1 : 2;
     if (converged) {
       Rigid P = rigid_inverse(X);
@@ -568,39 +696,6 @@ __global__ void __launch_bounds__(NW * 32, 1) icp_solve_kernel(SolveArgs a) {
 //   threads through shared memory.  A hypothesis that converges frees its CTA for the next one at once; there is no
 //   per-iteration launch, no inter-CTA dependency and nothing but the pose is written to HBM.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int SLICE = 24;
-
-__host__ __device__ constexpr int tri_row(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i; }
-__host__ __device__ constexpr int tri_col(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i + k; }
-
-template <int S, int E>
-__device__ __forceinline__ void acc_one(float (&acc)[SLICE], const float (&v)[13], float d2) {
-  constexpr int k = SLICE * S + E;
-  if constexpr (k < 91) acc[E] = fmaf(v[tri_row(k)], v[tri_col(k)], acc[E]);
-  else if constexpr (k == 91) acc[E] += d2;
-  else if constexpr (k == 92) acc[E] += 1.f;
-}
-template <int S, int... E>
-__device__ __forceinline__ void acc_slice(float (&acc)[SLICE], const float (&v)[13], float d2, std::integer_sequence<int, E...>) {
-  (acc_one<S, E>(acc, v, d2), ...);
-}
-
-template <int S>
-__device__ __forceinline__ void accumulate_chunk(float (&acc)[SLICE], const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
-  for (int i = begin + lane; i < end; i += 32) {
-    const float4 q1 = rec1[i];
-    if (!(q1.w >= 0.f)) continue;
-    const float4 q0 = rec0[i];
-    float v[13];
-    v[0] = q1.x * q0.x; v[1] = q1.x * q0.y; v[2] = q1.x * q0.z;
-    v[3] = q1.y * q0.x; v[4] = q1.y * q0.y; v[5] = q1.y * q0.z;
-    v[6] = q1.z * q0.x; v[7] = q1.z * q0.y; v[8] = q1.z * q0.z;
-    v[9] = q1.x; v[10] = q1.y; v[11] = q1.z;
-    v[12] = q0.w;
-    acc_slice<S>(acc, v, q1.w, std::make_integer_sequence<int, SLICE>());
-  }
-}
-
 struct FusedArgs {
   CloudDev scene;
   const float4 *model_nv;
@@ -613,40 +708,81 @@ struct FusedArgs {
   int max_iter;
   double abs_mse_eps;
   long long *prof;   // null, or 6 cycle counters (HOP_FUSED_PROFILE=1)
+  int slots_max;     // hypotheses a CTA carries at a time (<= its warps): the batch's fair share per CTA
+};
+
+// One hypothesis' state between its ICP iterations (shared memory; the slot is owned by warp `slot` during the solve)
+struct __align__(16) FusedSlot {
+  float X[12];        // scene -> model frame, the iterate
+  float inc[12];      // previous increment (PCL keeps transformation_ when LM early-returns)
+  double prev_mse;
+  int h;              // hypothesis of the batch in this slot, -1 = free
+  int iters;
 };
 
 // THREADS per CTA (a multiple of 128: four moment slices x THREADS/128 parts of the chunk), CHUNK scene points whose
 // records sit in shared memory at a time, PROF = with the cycle accounting, MINB resident CTAs per SM.
+//
+// A CTA carries up to one hypothesis per warp ("slots").  One round = for every occupied slot the cooperative passes over the
+// scene (phase A correspondences + phase B moments, all warps on one slot at a time: the same gather efficiency as one
+// hypothesis per CTA), then ALL solves of the round at once, warp w on slot w.  The per-iteration solve is the reference's serial
+// LM (lm_replay.cuh: tens of thousands of dependent cycles); with one hypothesis per CTA the other warps idle through it (59 %
+// of the CTA's cycles at 2 k scene points, 19 % at 10 k), with slots it costs 1/THREADS*32 of that per hypothesis.  A slot that
+// finishes takes the next hypothesis of the queue at the start of the next round.  slots_max (host) = fair share of the batch
+// per CTA, so a small batch still spreads over every SM instead of filling the slots of the first CTAs.
 template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
   constexpr int PARTS = THREADS / 128;
+  constexpr int NW = THREADS / 32;
   extern __shared__ __align__(16) float4 fused_smem[];
   float4 *rec0 = fused_smem, *rec1 = fused_smem + CHUNK;
   __shared__ __align__(16) float s_sums[PARTS][96];
-  __shared__ __align__(16) float s_tot[96];
-  __shared__ float s_X[12];
-  __shared__ int s_ctl[2];
+  __shared__ __align__(16) float s_tot[NW][96];
+  __shared__ FusedSlot s_slot[NW];
+  // the LM replay's per-warp scratch lives in the record buffers: they are idle while the round's solves run, and shared memory
+  // taken from L1 costs phase A its hit rate (2.3 KB x warps x 8 CTAs per SM: 18.8 -> 21.2 ms at the headline size)
+  static_assert(sizeof(lmr::LmrScratch) * NW <= 2 * CHUNK * sizeof(float4), "LM scratch does not fit the record buffers");
+  lmr::LmrScratch *s_scr = reinterpret_cast<lmr::LmrScratch *>(fused_smem);
+  __shared__ int s_ctl[2];   // [0] occupied slots this round  [1] queue exhausted
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = warp & 3, part = warp >> 2;
+  const int n_slots = min(NW, max(1, a.slots_max));
   // optional cycle accounting (thread 0 of every CTA): [0] phase A  [1] wait at the barrier after A  [2] phase B + barrier
   // [3] reduction + solve + broadcast  [4] passes  [5] whole CTA life time
   long long t_acc[6] = {0, 0, 0, 0, 0, 0}, t_mark = 0;
   const long long t_start = PROF ? clock64() : 0;
+  if (tid < NW) s_slot[tid].h = -1;
+  if (tid == 0) s_ctl[1] = 0;
+  __syncthreads();
   for (;;) {
-    if (tid == 0) s_ctl[0] = atomicAdd(a.counter, 1);
-    __syncthreads();
-    const int h = s_ctl[0];
-    if (h >= a.H) break;
-    Rigid X = rigid_inverse(rigid_load_colmajor(a.poses + 16 * (size_t)h));
-    // convergence state (meaningful on warp 0; uniform across its lanes)
-    Rigid inc_prev;
+    // ---- refill: every free slot takes the next hypothesis of the queue ----
+    if (warp == 0) {
+      int mine = lane < n_slots ? s_slot[lane].h : 0;
+      if (lane < n_slots && mine < 0 && !s_ctl[1]) {
+        const int h = atomicAdd(a.counter, 1);
+        if (h < a.H) {
+          FusedSlot &S = s_slot[lane];
+          const Rigid X = rigid_inverse(rigid_load_colmajor(a.poses + 16 * (size_t)h));
 #pragma unroll
-    for (int e = 0; e < 9; ++e) inc_prev.r[e] = (e % 4 == 0) ? 1.f : 0.f;
-    inc_prev.t[0] = inc_prev.t[1] = inc_prev.t[2] = 0.f;
-    double prev_mse = DBL_MAX;
-    int iters = 0;
-    bool finished = false, converged = false;
-    while (!finished) {
+          for (int e = 0; e < 9; ++e) { S.X[e] = X.r[e]; S.inc[e] = (e % 4 == 0) ? 1.f : 0.f; }
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { S.X[9 + e] = X.t[e]; S.inc[9 + e] = 0.f; }
+          S.prev_mse = DBL_MAX; S.iters = 0; S.h = h;
+          mine = h;
+        } else s_ctl[1] = 1;   // (benign race: every writer stores 1)
+      }
+      const unsigned occ = __ballot_sync(0xffffffffu, lane < n_slots && mine >= 0);
+      if (lane == 0) s_ctl[0] = __popc(occ);
+    }
+    __syncthreads();
+    if (s_ctl[0] == 0) break;
+    // ---- the passes over the scene, one occupied slot at a time, all warps together ----
+    for (int g = 0; g < n_slots; ++g) {
+      if (s_slot[g].h < 0) continue;   // uniform
+      Rigid X;
+#pragma unroll
+      for (int e = 0; e < 9; ++e) X.r[e] = s_slot[g].X[e];
+      X.t[0] = s_slot[g].X[9]; X.t[1] = s_slot[g].X[10]; X.t[2] = s_slot[g].X[11];
       float acc[SLICE];
 #pragma unroll
       for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
@@ -654,25 +790,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
         const int cnt = min(CHUNK, a.scene.n_padded - c0);
         // ---- phase A: correspondences of this chunk -> shared memory ----
         if (PROF && tid == 0) t_mark = clock64();
-        for (int i = tid; i < cnt; i += THREADS) {
-          const float4 sp = __ldg(&a.scene.pw[c0 + i]);
-          const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
-          float bd; float4 bp;
-          const int j = nn_query(a.grid, p.x, p.y, p.z, bd, bp);
-          float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = make_float4(0.f, 0.f, 0.f, -1.f);
-          if (j >= 0 && bd <= a.max_d2) {
-            const float4 sn = __ldg(&a.scene.nv[c0 + i]);
-            const float4 mn = __ldg(&a.model_nv[j]);
-            const float3 ns = rigid_rotate(X, sn.x, sn.y, sn.z);
-            const float dot = ns.x * mn.x + ns.y * mn.y + ns.z * mn.z;
-            if (dot >= a.cos_thr) {
-              r0 = make_float4(p.x, p.y, p.z, mn.x * (p.x - bp.x) + mn.y * (p.y - bp.y) + mn.z * (p.z - bp.z));
-              r1 = make_float4(mn.x, mn.y, mn.z, bd);
-            }
-          }
-          rec0[i] = r0;
-          rec1[i] = r1;
-        }
+        correspond_chunk<THREADS>(a.scene, a.model_nv, a.grid, X, a.cos_thr, a.max_d2, c0, cnt, rec0, rec1, tid);
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[0] += t - t_mark; t_mark = t; }
         __syncthreads();
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[1] += t - t_mark; t_mark = t; }
@@ -688,79 +806,106 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
         __syncthreads();
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[2] += t - t_mark; t_mark = t; }
       }
-      // ---- reduce: lanes -> warp totals -> the parts of the chunk ----
+      // ---- reduce: lanes -> warp totals -> the parts of the chunk -> this slot's 93 sums ----
       float mine = 0.f;
 #pragma unroll
       for (int e = 0; e < SLICE; ++e) {
         const float tot = warp_sum(acc[e]);
         if (lane == e) mine = tot;
       }
-      if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
-      __syncthreads();
-      if (warp == 0) {
-        for (int k = lane; k < 96; k += 32) {
-          float s = s_sums[0][k];
+      if (PARTS == 1) {
+        if (lane < SLICE) s_tot[g][SLICE * slice + lane] = mine;
+      } else {
+        if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
+        __syncthreads();
+        for (int k = tid; k < 96; k += THREADS) {
+          float t = s_sums[0][k];
 #pragma unroll
-          for (int q = 1; q < PARTS; ++q) s += s_sums[q][k];
-          s_tot[k] = s;
+          for (int q = 1; q < PARTS; ++q) t += s_sums[q][k];
+          s_tot[g][k] = t;
         }
-        __syncwarp();
-        const float *sums = s_tot;
-        const float cnt_f = sums[92], sumd2 = sums[91];
-        const int cnt = (int)(cnt_f + 0.5f);
-        bool runaway = false;
-        Rigid inc;
-        if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, inc.r, inc.t);
-        if (cnt < 3) {
-          finished = true;  // "Not enough correspondences": hasConverged() false -> pose unchanged
-        } else if (runaway) {
-          // the reference's LM slides the scene metres off the model here; its next iteration finds no correspondences
-          ++iters;
-          finished = true;
-        } else {
-          if (cnt >= 6) {}
-          else if (cnt >= 4) {  // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
+        // (the next slot writes s_sums only after the barriers of its own chunk loop)
+      }
+      if (PROF && tid == 0) { const long long t = clock64(); t_acc[3] += t - t_mark; t_mark = t; t_acc[4] += 1; }
+    }
+    __syncthreads();
+    // ---- the solves of this round, warp w on slot w ----
+    if (PROF && tid == 0) t_mark = clock64();
+    if (warp < n_slots && s_slot[warp].h >= 0) {
+      FusedSlot &S = s_slot[warp];
+      const float *sums = s_tot[warp];
+      const float cnt_f = sums[92], sumd2 = sums[91];
+      const int cnt = (int)(cnt_f + 0.5f);
+      Rigid X;
 #pragma unroll
-            for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
-            inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
-          } else inc = inc_prev;  // PCL's LM returns early with < 4 correspondences, transformation_ keeps its old value
-          X = rigid_compose(inc, X);
-          inc_prev = inc;
-          ++iters;
-          if (iters >= a.max_iter) converged = true;
+      for (int e = 0; e < 9; ++e) X.r[e] = S.X[e];
+      X.t[0] = S.X[9]; X.t[1] = S.X[10]; X.t[2] = S.X[11];
+      int iters = S.iters;
+      bool finished = false, converged = false, runaway = false;
+      Rigid inc;
+      if (cnt >= 6) runaway = !solve_increment<SOLVER>(sums, lane, &s_scr[SOLVER == 0 ? warp : 0], inc.r, inc.t);
+      if (cnt >= 6 && !runaway) {
+        bool finite = true;   // |q| > 1 inside the reference's LM gives NaN residuals; a step accepted there ends as a NaN transform
+#pragma unroll
+        for (int e = 0; e < 9; ++e) finite = finite && isfinite(inc.r[e]);
+        finite = finite && isfinite(inc.t[0]) && isfinite(inc.t[1]) && isfinite(inc.t[2]);
+        runaway = !finite;
+      }
+      if (cnt < 3) {
+        finished = true;  // "Not enough correspondences": hasConverged() false -> pose unchanged
+      } else if (runaway) {
+        // the reference's LM slides the scene metres off the model here (or returns a NaN transform); its next iteration finds
+        // no correspondences: not converged, pose unchanged
+        ++iters;
+        finished = true;
+      } else {
+        if (cnt >= 6) {}
+        else if (cnt >= 4) {  // Eigen LM: m < n -> ImproperInputParameters, x stays 0 -> identity increment
+#pragma unroll
+          for (int e = 0; e < 9; ++e) inc.r[e] = (e % 4 == 0) ? 1.f : 0.f;
+          inc.t[0] = inc.t[1] = inc.t[2] = 0.f;
+        } else {              // PCL's LM returns early with < 4 correspondences, transformation_ keeps its old value
+#pragma unroll
+          for (int e = 0; e < 9; ++e) inc.r[e] = S.inc[e];
+          inc.t[0] = S.inc[9]; inc.t[1] = S.inc[10]; inc.t[2] = S.inc[11];
+        }
+        X = rigid_compose(inc, X);
+        ++iters;
+        double prev_mse = S.prev_mse;
+        if (iters >= a.max_iter) converged = true;
+        else {
+          const double cos_angle = 0.5 * ((double)inc.r[0] + (double)inc.r[4] + (double)inc.r[8] - 1.0);
+          const double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
+          if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
           else {
-            const double cos_angle = 0.5 * ((double)inc.r[0] + (double)inc.r[4] + (double)inc.r[8] - 1.0);
-            const double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
-            if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
-            else {
-              const double mse = (double)sumd2 / (double)cnt;
-              if (fabs(mse - prev_mse) < a.abs_mse_eps) converged = true;
-              prev_mse = mse;
-            }
+            const double mse = (double)sumd2 / (double)cnt;
+            if (fabs(mse - prev_mse) < a.abs_mse_eps) converged = true;
+            prev_mse = mse;
           }
-          finished = converged;
         }
+        finished = converged;
+        __syncwarp();
         if (lane == 0) {
 #pragma unroll
-          for (int e = 0; e < 9; ++e) s_X[e] = X.r[e];
-          s_X[9] = X.t[0]; s_X[10] = X.t[1]; s_X[11] = X.t[2];
-          s_ctl[1] = (finished ? 1 : 0) | (converged ? 2 : 0);
+          for (int e = 0; e < 9; ++e) { S.X[e] = X.r[e]; S.inc[e] = inc.r[e]; }
+#pragma unroll
+          for (int e = 0; e < 3; ++e) { S.X[9 + e] = X.t[e]; S.inc[9 + e] = inc.t[e]; }
+          S.prev_mse = prev_mse;
         }
       }
-      __syncthreads();
-      if (PROF && tid == 0) { const long long t = clock64(); t_acc[3] += t - t_mark; t_mark = t; t_acc[4] += 1; }
-#pragma unroll
-      for (int e = 0; e < 9; ++e) X.r[e] = s_X[e];
-      X.t[0] = s_X[9]; X.t[1] = s_X[10]; X.t[2] = s_X[11];
-      finished = (s_ctl[1] & 1) != 0;
-      converged = (s_ctl[1] & 2) != 0;
+      if (lane == 0) {
+        S.iters = iters;
+        if (finished) {
+          const int h = S.h;
+          if (converged) { const Rigid P = rigid_inverse(X); rigid_store_colmajor(P, a.poses + 16 * (size_t)h); }
+          if (a.iters_out) a.iters_out[h] = iters;
+          if (a.conv_out) a.conv_out[h] = converged ? 1 : 0;
+          S.h = -1;
+        }
+      }
     }
-    if (tid == 0) {
-      if (converged) { const Rigid P = rigid_inverse(X); rigid_store_colmajor(P, a.poses + 16 * (size_t)h); }
-      if (a.iters_out) a.iters_out[h] = iters;
-      if (a.conv_out) a.conv_out[h] = converged ? 1 : 0;
-    }
-    __syncthreads();  // s_ctl / s_X are reused by the next hypothesis
+    __syncthreads();
+    if (PROF && tid == 0) { const long long t = clock64(); t_acc[3] += t - t_mark; }
   }
   if (PROF && tid == 0) {
     t_acc[5] = clock64() - t_start;
@@ -770,11 +915,13 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
 }
 
 template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
-static cudaError_t launch_fused(hop_ctx *ctx, const FusedArgs &f, int H) {
+static cudaError_t launch_fused(hop_ctx *ctx, FusedArgs f, int H) {
   const size_t smem = 2 * (size_t)CHUNK * sizeof(float4);
   cudaError_t e = ctx->func_smem_optin(icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER>, smem);
   if (e != cudaSuccess) return e;
   const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * MINB);
+  const int fair = (H + grid_ctas - 1) / grid_ctas;
+  f.slots_max = ctx->tune.fused_slots > 0 ? ctx->tune.fused_slots : fair;
   icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER><<<grid_ctas, THREADS, smem, ctx->stream>>>(f);
   return cudaGetLastError();
 }
@@ -878,41 +1025,28 @@ static float float_above(double thr) {
   return f;
 }
 
-static int pick_team(int H, int sm_count, int nw, int requested) {
-  if (requested == 1 || requested == 2 || requested == 4 || requested == 8) return requested;
-  // enough independent hypotheses to give every warp slot its own?  otherwise split hypotheses across warps
-  const long slots = (long)sm_count * nw;
-  int team = 1;
-  while (team < 8 && (long)H * team < slots) team *= 2;
-  return team;
-}
-
-constexpr int SOLVE_NW = 8;
-
-template <int TEAM>
-static void launch_solve(hop_ctx *ctx, const SolveArgs &s, int Hb, int solver) {
-  constexpr int NT = SOLVE_NW / TEAM;
-  const int grid = (Hb + NT - 1) / NT;
-  if (solver == 1) icp_solve_kernel<SOLVE_NW, TEAM, 1><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
-  else if (solver == 2) icp_solve_kernel<SOLVE_NW, TEAM, 2><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
-  else icp_solve_kernel<SOLVE_NW, TEAM, 0><<<grid, SOLVE_NW * 32, 0, ctx->stream>>>(s);
+template <int SOLVER>
+static void launch_solve(hop_ctx *ctx, const SolveArgs &s, int Hb) {
+  icp_solve_kernel<SOLVER><<<(Hb + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, ctx->stream>>>(s);
 }
 
 }  // namespace
 
-int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, float *d_poses, int H,
-                   const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv) {
+int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, const NNGridDev *scene_grid,
+                   float *d_poses, int H, const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv) {
   if (H <= 0) return HOP_OK;
-  if (p.mode != 0) { ctx->err = "hop_icp_refine: mode 1 (point-to-point) not built yet"; return HOP_EINVAL; }
-  const int max_iter = p.max_iter < 1 ? 1 : p.max_iter;
+  if (p.mode != 0 && p.mode != 1) { ctx->err = "hop_icp_refine: mode must be 0 (point-to-plane) or 1 (point-to-point)"; return HOP_EINVAL; }
+  if (p.mode == 1 && !scene_grid) { ctx->err = "hop_icp_refine: mode 1 needs the scene grid"; return HOP_EINVAL; }
   if (p.solver < 0 || p.solver > 2) { ctx->err = "hop_icp_refine: solver must be 0 (reference LM), 1 (Gauss-Newton) or 2 (exact minimiser)"; return HOP_EINVAL; }
-  if (p.solver != 1 && p.pipeline != 1) {
-    // fused pipeline (default): one persistent launch for the whole batch
+  const int max_iter = p.max_iter < 1 ? 1 : p.max_iter;
+  const float cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
+  const float max_d2 = p.max_dist * p.max_dist;
+  if (p.pipeline != 1 && p.mode == 0) {
+    // persistent fused pipeline (default): one launch for the whole batch
     FusedArgs f;
     f.scene = scene; f.model_nv = model.nv; f.grid = grid; f.poses = d_poses; f.H = H; f.iters_out = d_iters; f.conv_out = d_conv;
     f.counter = ctx->d_counter;
-    f.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
-    f.max_d2 = p.max_dist * p.max_dist; f.max_iter = max_iter; f.abs_mse_eps = p.abs_mse_eps;
+    f.cos_thr = cos_thr; f.max_d2 = max_d2; f.max_iter = max_iter; f.abs_mse_eps = p.abs_mse_eps;
     HOP_CUDA(ctx, cudaMemsetAsync(ctx->d_counter, 0, sizeof(int), ctx->stream));
     const int variant = ctx->tune.fused_variant;
     const bool prof_on = ctx->tune.fused_profile;
@@ -922,7 +1056,9 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
     {
       ProfScope ps(ctx, HOP_PROF_ICP_FUSED);
       const bool small_ctas = variant == 2 || (variant == 0 && (long)H >= 24L * ctx->sm_count);
-      HOP_CUDA(ctx, p.solver == 0 ? launch_fused_solver<0>(ctx, f, H, small_ctas, prof_on) : launch_fused_solver<2>(ctx, f, H, small_ctas, prof_on));
+      HOP_CUDA(ctx, p.solver == 0   ? launch_fused_solver<0>(ctx, f, H, small_ctas, prof_on)
+                    : p.solver == 1 ? launch_fused_solver<1>(ctx, f, H, small_ctas, prof_on)
+                                    : launch_fused_solver<2>(ctx, f, H, small_ctas, prof_on));
     }
     if (prof_on) {
       long long hp[6];
@@ -936,49 +1072,54 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
     HOP_CUDA(ctx, cudaGetLastError());
     return HOP_OK;
   }
-  const int n_tiles = scene.n_padded / TILE;
-  // hypotheses per batch: bounded by the correspondence-record buffer (32 B per hypothesis x scene point)
-  const size_t rec_per_h = (size_t)scene.n_padded * 32;
-  const size_t rec_budget = (size_t)1 << 30;
-  const int Hb_max = (int)std::min<size_t>((size_t)H, std::max<size_t>(1, rec_budget / rec_per_h));
+  // ---- iteration-synchronous pipeline (pipeline 1, and mode 1): sums + solve, two launches per ICP iteration ----
+  constexpr int MOM_THREADS = 128, MOM_CHUNK = 512, MOM_MINB = 8;
+  const int n_chunks = (scene.n_padded + MOM_CHUNK - 1) / MOM_CHUNK;
+  // a work item = one hypothesis x a group of chunks: small enough that a handful of active hypotheses still spread over the
+  // machine (latency of the late iterations), large enough that the partial sums stay a small fraction of the traffic
+  const int group_chunks = ctx->tune.mom_group_chunks > 0 ? ctx->tune.mom_group_chunks : std::max(2, (n_chunks + 15) / 16);
+  const int n_groups = (n_chunks + group_chunks - 1) / group_chunks;
+  const int group_pts = group_chunks * MOM_CHUNK;
+  const size_t part_per_h = (size_t)n_groups * 96 * sizeof(float);
+  const size_t part_budget = (size_t)256 << 20;
+  const int Hb_max = (int)std::min<size_t>((size_t)H, std::max<size_t>(1, part_budget / part_per_h));
   auto up = [](size_t v) { return (v + 255) / 256 * 256; };
   const size_t state_bytes = up(sizeof(IcpState) * (size_t)Hb_max), list_bytes = up(sizeof(int) * (size_t)Hb_max);
   const size_t cnt_bytes = up(sizeof(int) * (size_t)(max_iter + 1));
-  char *base = (char *)ctx->ensure_work(state_bytes + 2 * list_bytes + cnt_bytes + rec_per_h * Hb_max);
+  char *base = (char *)ctx->ensure_work(state_bytes + 2 * list_bytes + cnt_bytes + part_per_h * Hb_max);
   if (!base) { ctx->err = "hop_icp_refine: work buffer allocation failed"; return HOP_ENOMEM; }
   IcpState *state = (IcpState *)base;
   int *lists[2] = {(int *)(base + state_bytes), (int *)(base + state_bytes + list_bytes)};
   int *counters = (int *)(base + state_bytes + 2 * list_bytes);
-  float4 *rec0 = (float4 *)(base + state_bytes + 2 * list_bytes + cnt_bytes);
-  float4 *rec1 = rec0 + (size_t)Hb_max * scene.n_padded;
+  float *partial = (float *)(base + state_bytes + 2 * list_bytes + cnt_bytes);
 
   for (int h0 = 0; h0 < H; h0 += Hb_max) {
     const int Hb = std::min(Hb_max, H - h0);
     const int n_init = std::max(Hb, max_iter + 1);
     icp_init_kernel<<<(n_init + 127) / 128, 128, 0, ctx->stream>>>(d_poses + 16 * (size_t)h0, Hb, state, lists[0], counters, max_iter + 1);
     ctx->launches += 1;
-    CorrArgs c;
-    c.scene = scene; c.model_nv = model.nv; c.grid = grid; c.state = state; c.n_tiles = n_tiles;
-    c.cos_thr = float_above(cos((double)p.angle_deg / 180.0 * M_PI));
-    c.max_d2 = p.max_dist * p.max_dist;
-    c.rec0 = rec0; c.rec1 = rec1;
+    MomArgs c;
+    c.scene = scene; c.model_nv = model.nv; c.grid = grid; c.state = state; c.n_groups = n_groups; c.group_pts = group_pts;
+    c.cos_thr = cos_thr; c.max_d2 = max_d2; c.partial = partial;
+    if (scene_grid) c.sgrid = *scene_grid; else c.sgrid = grid;
     SolveArgs s;
-    s.rec0 = rec0; s.rec1 = rec1; s.n_padded = scene.n_padded; s.state = state; s.poses = d_poses + 16 * (size_t)h0;
+    s.partial = partial; s.n_groups = n_groups; s.state = state; s.poses = d_poses + 16 * (size_t)h0;
     s.iters_out = d_iters ? d_iters + h0 : nullptr; s.conv_out = d_conv ? d_conv + h0 : nullptr;
     s.max_iter = max_iter; s.abs_mse_eps = p.abs_mse_eps;
-    const int team = pick_team(Hb, ctx->sm_count, SOLVE_NW, p.team_warps);
-    const int corr_grid = (int)std::min<long>((long)n_tiles * Hb, (long)ctx->sm_count * 16);
+    const int mom_grid = (int)std::min<long>((long)n_groups * Hb, (long)ctx->sm_count * MOM_MINB);
     for (int it = 0; it < max_iter; ++it) {
       c.list = lists[it & 1]; c.n_active = counters + it;
       s.list = c.list; s.n_active = c.n_active; s.next_list = lists[(it + 1) & 1]; s.next_count = counters + it + 1;
-      { ProfScope ps(ctx, HOP_PROF_ICP_CORRESPOND); icp_correspond_kernel<<<corr_grid, TILE, 0, ctx->stream>>>(c); }
-      ProfScope ps(ctx, HOP_PROF_ICP_SOLVE);
-      switch (team) {
-        case 1: launch_solve<1>(ctx, s, Hb, p.solver); break;
-        case 2: launch_solve<2>(ctx, s, Hb, p.solver); break;
-        case 4: launch_solve<4>(ctx, s, Hb, p.solver); break;
-        default: launch_solve<8>(ctx, s, Hb, p.solver); break;
+      {
+        ProfScope ps(ctx, HOP_PROF_ICP_CORRESPOND);
+        if (p.mode == 1) icp_kabsch_sums_kernel<MOM_THREADS, MOM_CHUNK, MOM_MINB><<<mom_grid, MOM_THREADS, 0, ctx->stream>>>(c);
+        else icp_moments_kernel<MOM_THREADS, MOM_CHUNK, MOM_MINB><<<mom_grid, MOM_THREADS, 0, ctx->stream>>>(c);
       }
+      ProfScope ps(ctx, HOP_PROF_ICP_SOLVE);
+      if (p.mode == 1) launch_solve<3>(ctx, s, Hb);
+      else if (p.solver == 0) launch_solve<0>(ctx, s, Hb);
+      else if (p.solver == 1) launch_solve<1>(ctx, s, Hb);
+      else launch_solve<2>(ctx, s, Hb);
       ctx->launches += 2;
     }
   }

@@ -61,6 +61,11 @@ LMR_HD float sub(float a, float b) {
   volatile float r = a - b; return r;
 #endif
 }
+// Division and square root.  fdiv / fsqrt: correctly rounded, used where the reference's bits matter (W(x): the forward
+// differences y(x + h e_j) - y(x) are a few ulps of R's entries when h = sqrt(eps)|x_j| is tiny).  qdiv / qsqrt: the MINPACK
+// algebra on the 6x6 factors, where the replay differs from the reference's Householder QR in the last bits anyway: on the device
+// a reciprocal / reciprocal square root of the special function unit (<= 2 ulp) instead of the 10-25 instruction IEEE sequences --
+// the solve is one long dependent chain per hypothesis, its instruction count is its latency.
 LMR_HD float fdiv(float a, float b) {
 #if defined(__CUDA_ARCH__)
   return __fdiv_rn(a, b);
@@ -71,6 +76,24 @@ LMR_HD float fdiv(float a, float b) {
 LMR_HD float fsqrt(float a) {
 #if defined(__CUDA_ARCH__)
   return __fsqrt_rn(a);
+#else
+  return sqrtf(a);
+#endif
+}
+LMR_HD float qdiv(float a, float b) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(b));
+  return a * r;
+#else
+  return a / b;
+#endif
+}
+LMR_HD float qsqrt(float a) {
+#if defined(__CUDA_ARCH__)
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a));
+  return r;
 #else
   return sqrtf(a);
 #endif
@@ -94,40 +117,82 @@ LMR_HD void warp_y(const float *x, float *y) {
 }
 
 // 2-norm of a short float vector the way Eigen's stableNorm / blueNorm deliver it (correctly scaled, double inside)
+#if defined(__CUDACC__)
+__device__ __noinline__ float norm6_dev(float a0, float a1, float a2, float a3, float a4, float a5) {
+  double s = (double)a0 * (double)a0;
+  s += (double)a1 * (double)a1; s += (double)a2 * (double)a2; s += (double)a3 * (double)a3;
+  s += (double)a4 * (double)a4; s += (double)a5 * (double)a5;
+  return qsqrt((float)s);
+}
+#endif
 LMR_HD float norm6(const float *v) {
+#if defined(__CUDA_ARCH__)
+  return norm6_dev(v[0], v[1], v[2], v[3], v[4], v[5]);   // one copy of the code for the ~20 call sites
+#else
   double s = 0.0;
   for (int i = 0; i < N; ++i) s += (double)v[i] * (double)v[i];
-  return (float)sqrt(s);
+  return sqrtf((float)s);
+#endif
 }
 
 // ---- the quantities lmdif reads from the residual vector and the Jacobian, from the moments -------------------------
 // Host: plain loops over a full 13x13 double matrix.  Device: the 91 float sums stay in shared memory, lane i < 13 of the
 // calling warp owns row i, the replicated results meet through shuffles (all 32 lanes must call, with uniform arguments).
 #if defined(__CUDACC__)
+// Per-warp scratch in shared memory (LMR_SCRATCH_BYTES, 16-byte aligned).  The solver's code must stay small: unrolled and
+// shuffle-based it was ~10 k instructions (160 KB), more than the SM's instruction cache -- every warp then waits ~90 cycles per
+// instruction on instruction fetch (ncu: stalled_no_instruction).  Exchanging the small vectors through shared memory instead of
+// 64-bit shuffles and keeping the helpers out of line brings the hot loop to a few thousand instructions.
+struct LmrScratch {
+  double g[16];        // A y
+  double U[12][6];     // rows of A (D h)
+  double G[24];        // the 21 entries of the upper triangle of (D h)^T A (D h)
+  float A[NY * NY];    // the moment matrix, full symmetric storage
+  float D[N][12];      // columns of D h: y(x + h_j e_j) - y(x)
+  float M[12][N];      // the same, transposed (row i = entry i of every column)
+  float h[8];          // the steps h_j
+};
+#define LMR_SCRATCH_BYTES ((int)sizeof(lmr::LmrScratch))
+
 struct MomentsDev {
   const float *sums;   // upper triangle of the 13x13 moment matrix, row-major (shared memory)
   int lane;
-
-  __device__ __forceinline__ double at(int i, int j) const {
-    const int lo = i < j ? i : j, hi = i < j ? j : i;
-    return (double)sums[lo * 13 - (lo * (lo - 1)) / 2 + (hi - lo)];
-  }
+  LmrScratch *scr;     // this warp's scratch
+  __device__ __forceinline__ double at(int i, int j) const { return (double)scr->A[i * NY + j]; }
 };
+// expand the packed upper triangle into full storage (all 32 lanes)
+__device__ __forceinline__ void moments_prepare(const MomentsDev &A) {
+  for (int e = A.lane; e < NY * NY; e += 32) {
+    const int i = e / NY, j = e - i * NY;
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    A.scr->A[e] = A.sums[lo * 13 - (lo * (lo - 1)) / 2 + (hi - lo)];
+  }
+  __syncwarp();
+}
+// 1 / h in double: float reciprocal + one Newton step (relative error ~1e-14)
+__device__ __forceinline__ double rcp_h(float h) {
+  const double r = (double)__frcp_rn(h);
+  return r * (2.0 - (double)h * r);
+}
 // g = A y (replicated), returns y^T A y
-__device__ __forceinline__ double quad(const MomentsDev &A, const float *y, double *g) {
+__device__ __noinline__ double quad(const MomentsDev &A, const float *y, double *g) {
+  LmrScratch &S = *A.scr;
   const int li = A.lane < NY ? A.lane : NY - 1;
   double gi = 0.0;
 #pragma unroll
-  for (int j = 0; j < NY; ++j) gi = fma(A.at(li, j), (double)y[j], gi);
+  for (int j = 0; j < NY; ++j) gi = fma((double)S.A[li * NY + j], (double)y[j], gi);
+  __syncwarp();
+  if (A.lane < NY) S.g[A.lane] = gi;
+  __syncwarp();
   double f2 = 0.0;
 #pragma unroll
-  for (int j = 0; j < NY; ++j) { g[j] = __shfl_sync(0xffffffffu, gi, j); f2 = fma(g[j], (double)y[j], f2); }
+  for (int j = 0; j < NY; ++j) { g[j] = S.g[j]; f2 = fma(g[j], (double)y[j], f2); }
   return f2;
 }
 // Forward-difference Jacobian as moments: G = J^T J (upper triangle valid), b = J^T f.  Lane j < 6 evaluates W(x + h_j e_j);
 // a translation column of D has the single entry (fl(x_j + h) - x_j) / h, a rotation column the nine entries of dR / h.
-__device__ __forceinline__ void gram(const MomentsDev &A, const float *x, const float *y, const double *g, float h_eps, double (*G)[N], double *b, float *h_out) {
-  const unsigned FULL = 0xffffffffu;
+__device__ __noinline__ void gram(const MomentsDev &A, const float *x, const float *y, const double *g, float h_eps, double (*G)[N], double *b, float *h_out) {
+  LmrScratch &S = *A.scr;
   const int lane = A.lane;
   float xx[N], hj = 1.f;
 #pragma unroll
@@ -136,57 +201,55 @@ __device__ __forceinline__ void gram(const MomentsDev &A, const float *x, const 
     if (h == 0.f) h = h_eps;
     xx[k] = lane == k ? add(x[k], h) : x[k];
     if (lane == k) hj = h;
+    h_out[k] = h;
   }
   float yj[NY];
   warp_y(xx, yj);
-  float dy[12];
+  __syncwarp();
+  if (lane < N) {
 #pragma unroll
-  for (int i = 0; i < 12; ++i) dy[i] = sub(yj[i], y[i]);
-  // broadcast the columns; `mine[k]` = this lane's row entry of column k of D*h (lane = row index of y)
-  float dr[3][9], dt[3], mine[N], hs[N];
-#pragma unroll
-  for (int k = 0; k < N; ++k) { hs[k] = __shfl_sync(FULL, hj, k); mine[k] = 0.f; h_out[k] = hs[k]; }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) { dt[c] = __shfl_sync(FULL, dy[9 + c], c); if (lane == 9 + c) mine[c] = dt[c]; }
-#pragma unroll
-  for (int r = 0; r < 3; ++r)
-#pragma unroll
-    for (int k = 0; k < 9; ++k) { dr[r][k] = __shfl_sync(FULL, dy[k], 3 + r); if (lane == k) mine[3 + r] = dr[r][k]; }
-  // this lane's row of A D (unscaled): u[j] = sum_l A[lane][l] (D h)[l][j]
-  const int li = lane < 12 ? lane : 11;
-  double u[N], arow[12];
-#pragma unroll
-  for (int l = 0; l < 12; ++l) arow[l] = A.at(li, l);
-#pragma unroll
-  for (int c = 0; c < 3; ++c) u[c] = arow[9 + c] * (double)dt[c];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    double s = 0.0;
-#pragma unroll
-    for (int k = 0; k < 9; ++k) s = fma(arow[k], (double)dr[r][k], s);
-    u[3 + r] = s;
+    for (int i = 0; i < 12; ++i) { const float d = sub(yj[i], y[i]); S.D[lane][i] = d; S.M[i][lane] = d; }
+    S.h[lane] = hj;
   }
-  double inv_h[N];
+  __syncwarp();
+  // this lane's row of A (D h): U[lane][j] = sum_l A[lane][l] (D h)[l][j]; a translation column has one entry, a rotation column nine
+  if (lane < 12) {
 #pragma unroll
-  for (int k = 0; k < N; ++k) inv_h[k] = 1.0 / (double)hs[k];
+    for (int c = 0; c < 3; ++c) S.U[lane][c] = (double)S.A[lane * NY + 9 + c] * (double)S.D[c][9 + c];
 #pragma unroll
-  for (int j = 0; j < N; ++j)
+    for (int r = 0; r < 3; ++r) {
+      double s = 0.0;
 #pragma unroll
-    for (int k = j; k < N; ++k) {
-      double p = lane < 12 ? (double)mine[j] * u[k] : 0.0;
-#pragma unroll
-      for (int o = 8; o > 0; o >>= 1) p += __shfl_xor_sync(FULL, p, o);   // rows 0..11 live in lanes 0..15
-      p = __shfl_sync(FULL, p, 0);
-      G[j][k] = p * inv_h[j] * inv_h[k];
+      for (int k = 0; k < 9; ++k) s = fma((double)S.A[lane * NY + k], (double)S.D[3 + r][k], s);
+      S.U[lane][3 + r] = s;
     }
+  }
+  __syncwarp();
+  if (lane < 21) {   // entry (j, k), j <= k, of the upper triangle, row-major
+    int j = 0, l = lane;
+    while (l >= N - j) { l -= N - j; ++j; }
+    const int k = j + l;
+    double acc = 0.0;
+#pragma unroll 1
+    for (int i = 0; i < 12; ++i) acc = fma((double)S.M[i][j], S.U[i][k], acc);
+    S.G[lane] = acc * (rcp_h(S.h[j]) * rcp_h(S.h[k]));
+  }
+  __syncwarp();
+  {
+    int e = 0;
 #pragma unroll
-  for (int c = 0; c < 3; ++c) b[c] = (double)dt[c] * g[9 + c] * inv_h[c];
+    for (int j = 0; j < N; ++j)
+#pragma unroll
+      for (int k = j; k < N; ++k) G[j][k] = S.G[e++];
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) b[c] = (double)S.D[c][9 + c] * g[9 + c] * rcp_h(h_out[c]);
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < 9; ++k) s = fma((double)dr[r][k], g[k], s);
-    b[3 + r] = s * inv_h[3 + r];
+    for (int k = 0; k < 9; ++k) s = fma((double)S.D[3 + r][k], g[k], s);
+    b[3 + r] = s * rcp_h(h_out[3 + r]);
   }
 }
 #endif
@@ -237,41 +300,48 @@ inline void gram(const Moments &A, const float *x, const float *y, const double 
   }
 }
 
+// Hot path (every LM step): small fully unrolled loops, everything in registers.  Cold path (lmpar's iteration on the LM
+// parameter, entered only when the Gauss-Newton step leaves the trust region): rolled loops in a function of its own -- unrolled it
+// is ~15 k instructions, more than the instruction cache holds, and every solve then stalls on instruction fetch.
 #if defined(__CUDA_ARCH__)
 #define LMR_UNROLL _Pragma("unroll")
+#define LMR_ROLL _Pragma("unroll 1")
+#define LMR_COLD __device__ __noinline__
 #else
 #define LMR_UNROLL
+#define LMR_ROLL
+#define LMR_COLD inline
 #endif
 
 // MINPACK qrsolv on the 6x6 upper-triangular r (identity column order): least squares of [R; D] z = [qtb; 0].  r's strict
 // lower triangle receives the transposed factor S (lmpar's Newton correction reads it), sdiag its diagonal.
-LMR_HD void qrsolv(float (*r)[N], const float *diag, const float *qtb, float *x, float *sdiag) {
+LMR_COLD void qrsolv(float (*r)[N], const float *diag, const float *qtb, float *x, float *sdiag) {
   float wa[N];
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) {
-    LMR_UNROLL
+    LMR_ROLL
     for (int i = j; i < N; ++i) r[i][j] = r[j][i];
     x[j] = r[j][j];
     wa[j] = qtb[j];
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) {
     if (diag[j] != 0.f) {
-      LMR_UNROLL
+      LMR_ROLL
       for (int k = j; k < N; ++k) sdiag[k] = 0.f;
       sdiag[j] = diag[j];
       float qtbpj = 0.f;
-      LMR_UNROLL
+      LMR_ROLL
       for (int k = j; k < N; ++k) {
         if (sdiag[k] == 0.f) continue;
         float sn, cs;  // Givens rotation eliminating sdiag[k] against r[k][k] (Eigen's makeGivens differs only in rounding)
-        if (fabsf(r[k][k]) < fabsf(sdiag[k])) { const float ct = r[k][k] / sdiag[k]; sn = 0.5f / sqrtf(0.25f + 0.25f * ct * ct); cs = sn * ct; }
-        else { const float tn = sdiag[k] / r[k][k]; cs = 0.5f / sqrtf(0.25f + 0.25f * tn * tn); sn = cs * tn; }
+        if (fabsf(r[k][k]) < fabsf(sdiag[k])) { const float ct = qdiv(r[k][k], sdiag[k]); sn = qdiv(0.5f, qsqrt(0.25f + 0.25f * ct * ct)); cs = sn * ct; }
+        else { const float tn = qdiv(sdiag[k], r[k][k]); cs = qdiv(0.5f, qsqrt(0.25f + 0.25f * tn * tn)); sn = cs * tn; }
         r[k][k] = cs * r[k][k] + sn * sdiag[k];
         const float tmp = cs * wa[k] + sn * qtbpj;
         qtbpj = -sn * wa[k] + cs * qtbpj;
         wa[k] = tmp;
-        LMR_UNROLL
+        LMR_ROLL
         for (int i = k + 1; i < N; ++i) {
           const float t2 = cs * r[i][k] + sn * sdiag[i];
           sdiag[i] = -sn * r[i][k] + cs * sdiag[i];
@@ -283,45 +353,45 @@ LMR_HD void qrsolv(float (*r)[N], const float *diag, const float *qtb, float *x,
     r[j][j] = x[j];
   }
   int nsing = N;
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) {
     if (sdiag[j] == 0.f && nsing == N) nsing = j;
     if (nsing < N) wa[j] = 0.f;
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = N - 1; j >= 0; --j) {
     if (j < nsing) {
       float sum = 0.f;
-      LMR_UNROLL
+      LMR_ROLL
       for (int i = j + 1; i < N; ++i) sum += r[i][j] * wa[i];   // wa[i] = 0 beyond nsing
-      wa[j] = (wa[j] - sum) / sdiag[j];
+      wa[j] = qdiv(wa[j] - sum, sdiag[j]);
     }
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) x[j] = wa[j];
 }
 
 // MINPACK lmpar: the LM parameter par with | |D x| - delta | <= 0.1 delta (or par = 0 when the Gauss-Newton step fits)
-LMR_HD void lmpar(float (*r)[N], const float *diag, const float *qtb, float delta, float &par, float *x) {
+LMR_COLD void lmpar_iterate(float (*r)[N], const float *diag, const float *qtb, float delta, float &par, float *x) {
   const float dwarf = FLT_MIN;
   float wa1[N], wa2[N], sdiag[N];
   int nsing = N;
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) {
     wa1[j] = qtb[j];
     if (r[j][j] == 0.f && nsing == N) nsing = j;
     if (nsing < N) wa1[j] = 0.f;
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = N - 1; j >= 0; --j) {
     if (j < nsing) {
-      wa1[j] /= r[j][j];
+      wa1[j] = qdiv(wa1[j], r[j][j]);
       const float t = wa1[j];
-      LMR_UNROLL
+      LMR_ROLL
       for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * t;
     }
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) { x[j] = wa1[j]; wa2[j] = diag[j] * x[j]; }
   int iter = 0;
   float dxnorm = norm6(wa2);
@@ -329,60 +399,60 @@ LMR_HD void lmpar(float (*r)[N], const float *diag, const float *qtb, float delt
   if (fp <= 0.1f * delta) { par = 0.f; return; }
   float parl = 0.f;
   if (nsing >= N) {
-    LMR_UNROLL
-    for (int j = 0; j < N; ++j) wa1[j] = diag[j] * (wa2[j] / dxnorm);
-    LMR_UNROLL
+    LMR_ROLL
+    for (int j = 0; j < N; ++j) wa1[j] = diag[j] * qdiv(wa2[j], dxnorm);
+    LMR_ROLL
     for (int j = 0; j < N; ++j) {
       float sum = 0.f;
-      LMR_UNROLL
+      LMR_ROLL
       for (int i = 0; i < j; ++i) sum += r[i][j] * wa1[i];
-      wa1[j] = (wa1[j] - sum) / r[j][j];
+      wa1[j] = qdiv(wa1[j] - sum, r[j][j]);
     }
     const float t = norm6(wa1);
-    parl = fp / delta / t / t;
+    parl = qdiv(qdiv(qdiv(fp, delta), t), t);
   }
-  LMR_UNROLL
+  LMR_ROLL
   for (int j = 0; j < N; ++j) {
     float sum = 0.f;
-    LMR_UNROLL
+    LMR_ROLL
     for (int i = 0; i <= j; ++i) sum += r[i][j] * qtb[i];
-    wa1[j] = sum / diag[j];
+    wa1[j] = qdiv(sum, diag[j]);
   }
   const float gnorm = norm6(wa1);
-  float paru = gnorm / delta;
-  if (paru == 0.f) paru = dwarf / fminf(delta, 0.1f);
+  float paru = qdiv(gnorm, delta);
+  if (paru == 0.f) paru = qdiv(dwarf, fminf(delta, 0.1f));
   par = fmaxf(par, parl);
   par = fminf(par, paru);
-  if (par == 0.f) par = gnorm / dxnorm;
+  if (par == 0.f) par = qdiv(gnorm, dxnorm);
   for (;;) {
     ++iter;
     if (par == 0.f) par = fmaxf(dwarf, 0.001f * paru);
-    const float sq = sqrtf(par);
-    LMR_UNROLL
+    const float sq = qsqrt(par);
+    LMR_ROLL
     for (int j = 0; j < N; ++j) wa1[j] = sq * diag[j];
     float rr[N][N];
-    LMR_UNROLL
+    LMR_ROLL
     for (int i = 0; i < N; ++i)
-      LMR_UNROLL
+      LMR_ROLL
       for (int j = 0; j < N; ++j) rr[i][j] = r[i][j];
     qrsolv(rr, wa1, qtb, x, sdiag);
-    LMR_UNROLL
+    LMR_ROLL
     for (int j = 0; j < N; ++j) wa2[j] = diag[j] * x[j];
     dxnorm = norm6(wa2);
     float temp = fp;
     fp = dxnorm - delta;
     if (fabsf(fp) <= 0.1f * delta || (parl == 0.f && fp <= temp && temp < 0.f) || iter == 10) break;
-    LMR_UNROLL
-    for (int j = 0; j < N; ++j) wa1[j] = diag[j] * (wa2[j] / dxnorm);
-    LMR_UNROLL
+    LMR_ROLL
+    for (int j = 0; j < N; ++j) wa1[j] = diag[j] * qdiv(wa2[j], dxnorm);
+    LMR_ROLL
     for (int j = 0; j < N; ++j) {
-      wa1[j] /= sdiag[j];
+      wa1[j] = qdiv(wa1[j], sdiag[j]);
       const float t = wa1[j];
-      LMR_UNROLL
+      LMR_ROLL
       for (int i = j + 1; i < N; ++i) wa1[i] -= rr[i][j] * t;
     }
     temp = norm6(wa1);
-    const float parc = fp / delta / temp / temp;
+    const float parc = qdiv(qdiv(qdiv(fp, delta), temp), temp);
     if (fp > 0.f) parl = fmaxf(parl, par);
     if (fp < 0.f) paru = fminf(paru, par);
     par = fmaxf(parl, par + parc);
@@ -414,6 +484,59 @@ LMR_HD bool translation_unconstrained(const MomentsT &A) {
   return !(d2 > tol * n22);
 }
 
+// lmpar, hot part: the Gauss-Newton step and the test that it fits the trust region (then par = 0: the common case).  Otherwise
+// the whole of MINPACK's lmpar runs in the cold function, on copies (so that r stays in registers here).
+LMR_HD void lmpar(const float (*r)[N], const float *diag, const float *qtb, float delta, float &par, float *x) {
+  float wa1[N], wa2[N];
+  bool full_rank = true;
+  LMR_UNROLL
+  for (int j = 0; j < N; ++j) { wa1[j] = qtb[j]; full_rank = full_rank && r[j][j] != 0.f; }
+  if (full_rank) {
+    LMR_UNROLL
+    for (int j = N - 1; j >= 0; --j) {
+      wa1[j] = qdiv(wa1[j], r[j][j]);
+      const float t = wa1[j];
+      LMR_UNROLL
+      for (int i = 0; i < j; ++i) wa1[i] -= r[i][j] * t;
+    }
+    LMR_UNROLL
+    for (int j = 0; j < N; ++j) wa2[j] = diag[j] * wa1[j];
+    const float fp = norm6(wa2) - delta;
+    if (fp <= 0.1f * delta) {
+      LMR_UNROLL
+      for (int j = 0; j < N; ++j) x[j] = wa1[j];
+      par = 0.f;
+      return;
+    }
+  }
+  float rc[N][N], dc[N], qc[N], xc[N];
+  LMR_UNROLL
+  for (int i = 0; i < N; ++i) {
+    dc[i] = diag[i]; qc[i] = qtb[i];
+    LMR_UNROLL
+    for (int j = 0; j < N; ++j) rc[i][j] = r[i][j];
+  }
+  lmpar_iterate(rc, dc, qc, delta, par, xc);
+  LMR_UNROLL
+  for (int j = 0; j < N; ++j) x[j] = xc[j];
+}
+
+// sqrt and reciprocal of a Cholesky pivot (0 for a non-positive one); out of line on the device: one copy for the six pivots
+#if defined(__CUDACC__)
+__device__ __forceinline__ void chol_pivot_dev(double d, double *dd, double *inv) {
+  const double ri = d > 0.0 ? rsqrt(d) : 0.0;   // (2 ulp; the factor only has to be good to float precision)
+  *inv = ri; *dd = d > 0.0 ? d * ri : 0.0;
+}
+#endif
+LMR_HD void chol_pivot(double d, double &dd, double &inv) {
+#if defined(__CUDA_ARCH__)
+  chol_pivot_dev(d, &dd, &inv);
+#else
+  dd = d > 0.0 ? sqrt(d) : 0.0;
+  inv = dd > 0.0 ? 1.0 / dd : 0.0;
+#endif
+}
+
 // The LM run.  x (6) must be zero on entry (PCL starts from the identity); returns Eigen's LevenbergMarquardtSpace status.
 // Device: called by all 32 lanes of one warp with identical arguments.
 template <typename MomentsT>
@@ -427,14 +550,14 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
   float par = 0.f, delta = 0.f, xnorm = 0.f;
   warp_y(x, y);
   double f2 = quad(A, y, g);
-  float fnorm = (float)sqrt(f2 > 0.0 ? f2 : 0.0);
+  float fnorm = qsqrt(f2 > 0.0 ? (float)f2 : 0.f);
   for (;;) {
     double G[N][N], b[N];
     float hs[N];
     gram(A, x, y, g, h_eps, G, b, hs);
     nfev += N + 1;   // NumericalDiff::df (Forward) re-evaluates f(x) first: n + 1 evaluations
     LMR_UNROLL
-    for (int j = 0; j < N; ++j) wa2[j] = (float)sqrt(G[j][j] > 0.0 ? G[j][j] : 0.0);
+    for (int j = 0; j < N; ++j) wa2[j] = qsqrt(G[j][j] > 0.0 ? (float)G[j][j] : 0.f);
     // ---- R and Q^T f of the QR of J = Cholesky of G, R^-T J^T f.  The reference pivots its Householder QR on the column
     //      norms; the order only changes the rounding of what follows (the step is a function of J^T J), and a Cholesky
     //      factorisation in double needs no pivoting for accuracy, so the columns keep their order. ----
@@ -446,8 +569,8 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
         double d = G[j][j];
         LMR_UNROLL
         for (int i = 0; i < j; ++i) d -= Lr[i][j] * Lr[i][j];
-        const double dd = d > 0.0 ? sqrt(d) : 0.0;
-        const double inv = dd > 0.0 ? 1.0 / dd : 0.0;
+        double dd, inv;
+        chol_pivot(d, dd, inv);
         Lr[j][j] = dd;
         LMR_UNROLL
         for (int k = j + 1; k < N; ++k) {
@@ -480,8 +603,8 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
         if (wa2[j] != 0.f) {
           float s = 0.f;
           LMR_UNROLL
-          for (int i = 0; i <= j; ++i) s += r[i][j] * (qtf[i] / fnorm);
-          gnorm = fmaxf(gnorm, fabsf(s / wa2[j]));
+          for (int i = 0; i <= j; ++i) s += r[i][j] * qdiv(qtf[i], fnorm);
+          gnorm = fmaxf(gnorm, fabsf(qdiv(s, wa2[j])));
         }
     }
     if (gnorm <= gtol) { status = 4; break; }
@@ -500,9 +623,9 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
       warp_y(wa2, y1);
       const double f21 = quad(A, y1, g1);
       ++nfev;
-      const float fnorm1 = (float)sqrt(f21 > 0.0 ? f21 : 0.0);
+      const float fnorm1 = qsqrt(f21 > 0.0 ? (float)f21 : 0.f);
       float actred = -1.f;
-      if (0.1f * fnorm1 < fnorm) { const float q = fnorm1 / fnorm; actred = 1.f - q * q; }
+      if (0.1f * fnorm1 < fnorm) { const float q = qdiv(fnorm1, fnorm); actred = 1.f - q * q; }
       LMR_UNROLL
       for (int i = 0; i < N; ++i) {
         float s = 0.f;
@@ -510,20 +633,20 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
         for (int j = i; j < N; ++j) s += r[i][j] * wa1[j];
         wa3[i] = s;
       }
-      float t1 = norm6(wa3) / fnorm; t1 *= t1;
-      float t2 = sqrtf(par) * pnorm / fnorm; t2 *= t2;
-      const float prered = t1 + t2 / 0.5f;
+      float t1 = qdiv(norm6(wa3), fnorm); t1 *= t1;
+      float t2 = qdiv(qsqrt(par) * pnorm, fnorm); t2 *= t2;
+      const float prered = t1 + qdiv(t2, 0.5f);
       const float dirder = -(t1 + t2);
       ratio = 0.f;
-      if (prered != 0.f) ratio = actred / prered;
+      if (prered != 0.f) ratio = qdiv(actred, prered);
       if (ratio <= 0.25f) {
         float temp = 0.5f;
-        if (actred < 0.f) temp = 0.5f * dirder / (dirder + 0.5f * actred);
+        if (actred < 0.f) temp = qdiv(0.5f * dirder, dirder + 0.5f * actred);
         if (0.1f * fnorm1 >= fnorm || temp < 0.1f) temp = 0.1f;
-        delta = temp * fminf(delta, pnorm / 0.1f);
-        par /= temp;
+        delta = temp * fminf(delta, qdiv(pnorm, 0.1f));
+        par = qdiv(par, temp);
       } else if (!(par != 0.f && ratio < 0.75f)) {
-        delta = pnorm / 0.5f;
+        delta = qdiv(pnorm, 0.5f);
         par = 0.5f * par;
       }
       if (ratio >= 1e-4f) {

@@ -190,6 +190,10 @@ def load_library():
     L.hop_render_scene_destroy.argtypes = [_vp, _vp]
     L.hop_render_depth.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
     L.hop_reject_by_render.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, _vp, C.c_int, _vp, _vp, _vp]
+    L.hop_refine_score_select.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), C.POINTER(LcpParams), C.c_int, C.c_int,
+                                          _vp, _vp, _vp, _vp, _vp]
+    L.hop_refine_score_select_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), C.POINTER(LcpParams), C.c_int, C.c_int,
+                                              C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
     for name in declared_symbols():
         fn = getattr(L, name)  # raises AttributeError when an export is missing
         if fn.restype is C.c_int and name not in ("hop_cloud_size",):
@@ -728,7 +732,28 @@ class Context:
         self._check(self.L.hop_select_topk(self.h, _ptr(flat), _ptr(scores), len(flat), K, id_offset, frame, _ptr(out)))
         return out
 
+    def refine_score_select(self, scene, model_icp, poses, K=1, model_lcp=None, icp_params=None, lcp_params=None, use_weights=False):
+        """refineByICP + selectBest in one visit to the device (hop_refine_score_select): returns refined poses (H,4,4), scores,
+        iterations, converged, winners (K records, score descending)."""
+        icp_params = icp_params or self.icp_params()
+        lcp_params = lcp_params or self.lcp_params()
+        flat = poses_to_colmajor(poses)
+        H = len(flat)
+        scores, iters, conv = np.zeros(H, np.float32), np.zeros(H, np.int32), np.zeros(H, np.int32)
+        win = np.zeros(K, POSE_REC_DTYPE)
+        self._check(self.L.hop_refine_score_select(self.h, scene.handle, model_icp.handle, model_lcp.handle if model_lcp else None, _ptr(flat), H,
+                                                   C.byref(icp_params), C.byref(lcp_params), int(use_weights), K, _ptr(flat), _ptr(scores),
+                                                   _ptr(iters), _ptr(conv), _ptr(win) if K else None))
+        return colmajor_to_poses(flat), scores, iters, conv, win
+
     # ---- device-pointer variants (inputs already resident in HBM) ----
+    def refine_score_select_dev(self, scene, model_icp, d_poses, H, icp_params, lcp_params, K, d_scores, d_winners, model_lcp=None,
+                                d_iters=None, d_conv=None, use_weights=False, id_offset=0, frame=0):
+        self._check(self.L.hop_refine_score_select_dev(self.h, scene.handle, model_icp.handle, model_lcp.handle if model_lcp else None,
+                                                       _vp(d_poses), H, C.byref(icp_params), C.byref(lcp_params), int(use_weights), K,
+                                                       id_offset, frame, _vp(d_iters) if d_iters else None, _vp(d_conv) if d_conv else None,
+                                                       _vp(d_scores), _vp(d_winners) if d_winners else None))
+
     def icp_refine_dev(self, scene, model, d_poses, H, params, d_iters=None, d_conv=None):
         self._check(self.L.hop_icp_refine_dev(self.h, scene.handle, model.handle, _vp(d_poses), H, C.byref(params),
                                               _vp(d_iters) if d_iters else None, _vp(d_conv) if d_conv else None))

@@ -206,29 +206,55 @@ void PoseEstimator::clusterPoses(float angle_diff, float dist_diff, bool assign_
 void PoseEstimator::refineByICP() {
   const size_t n = std::min<size_t>(_pose_hypos.size(), 100);   // PoseEstimator.cpp:241
   _pose_hypos.resize(n);
+  _scored_poses.clear(); _scored_lcp.clear();
   if (n == 0) return;
-  std::vector<float> poses(16 * n);
+  std::vector<float> poses(16 * n), scores(n);
   for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
   hop_icp_params p;
   hop_default_icp_params(&p);   // 10 iterations, abs MSE 1e-6 (Utils.cpp:207-208; PoseEstimator.cpp:266)
   p.angle_deg = cfg->yml["icp_angle_thres"].as<float>(45.f);
   p.max_dist = cfg->yml["icp_dist_thres"].as<float>(0.01f);
-  // the scene grid selectBest's computeLCP needs depends on the frame only: built on the context's second stream while the ICP runs
-  check(hop_cloud_prepare_nn_async(ctx, d_scene, cfg->yml["lcp"]["dist"].as<float>(0.001f) * 1.01f, 0.f), "hop_cloud_prepare_nn_async");
-  check(hop_icp_refine(ctx, d_scene, d_model, poses.data(), (int)n, &p, nullptr, nullptr), "hop_icp_refine");
+  hop_lcp_params q;
+  hop_default_lcp_params(&q);
+  q.dist = cfg->yml["lcp"]["dist"].as<float>(0.001f);
+  q.angle_deg = cfg->yml["lcp"]["normal_angle"].as<float>(10.f);
+  // One visit to the device: the hypotheses go up once, are refined (K4) and scored (K5, what selectBest will ask for: the score
+  // of a hypothesis does not depend on which others survive the pruning in between), and come back with one synchronisation.
+  check(hop_refine_score_select(ctx, d_scene, d_model, d_model001, poses.data(), (int)n, &p, &q, 0, 0, poses.data(), scores.data(), nullptr, nullptr,
+                                nullptr), "hop_refine_score_select");
   for (size_t i = 0; i < n; ++i) std::memcpy(_pose_hypos[i]._pose.data(), &poses[16 * i], 64);
+  _scored_poses.swap(poses); _scored_lcp.swap(scores);
+  _scored_lcp_dist = q.dist; _scored_lcp_angle = q.angle_deg;
 }
 
 void PoseEstimator::selectBest(PoseHypo &best_hypo) {
   const size_t n = _pose_hypos.size();
   if (n == 0) return;
-  std::vector<float> poses(16 * n), scores(n);
-  for (size_t i = 0; i < n; ++i) std::memcpy(&poses[16 * i], _pose_hypos[i]._pose.data(), 64);
   hop_lcp_params p;
   hop_default_lcp_params(&p);
   p.dist = cfg->yml["lcp"]["dist"].as<float>(0.001f);
   p.angle_deg = cfg->yml["lcp"]["normal_angle"].as<float>(10.f);
-  check(hop_lcp_score(ctx, d_scene, d_model001, poses.data(), (int)n, &p, 0, scores.data()), "hop_lcp_score");
+  std::vector<float> scores(n);
+  // scores refineByICP already brought back: valid for a hypothesis whose pose is bit-identical to a refined one
+  std::vector<size_t> todo;
+  const bool cache_ok = !_scored_lcp.empty() && _scored_lcp_dist == p.dist && _scored_lcp_angle == p.angle_deg;
+  for (size_t i = 0; i < n; ++i) {
+    bool hit = false;
+    if (cache_ok) {
+      const size_t id = (size_t)_pose_hypos[i]._id;
+      size_t k = id < _scored_lcp.size() && std::memcmp(&_scored_poses[16 * id], _pose_hypos[i]._pose.data(), 64) == 0 ? id : _scored_lcp.size();
+      for (size_t j = 0; k == _scored_lcp.size() && j < _scored_lcp.size(); ++j)
+        if (std::memcmp(&_scored_poses[16 * j], _pose_hypos[i]._pose.data(), 64) == 0) k = j;
+      if (k < _scored_lcp.size()) { scores[i] = _scored_lcp[k]; hit = true; }
+    }
+    if (!hit) todo.push_back(i);
+  }
+  if (!todo.empty()) {
+    std::vector<float> poses(16 * todo.size()), sc(todo.size());
+    for (size_t t = 0; t < todo.size(); ++t) std::memcpy(&poses[16 * t], _pose_hypos[todo[t]]._pose.data(), 64);
+    check(hop_lcp_score(ctx, d_scene, d_model001, poses.data(), (int)todo.size(), &p, 0, sc.data()), "hop_lcp_score");
+    for (size_t t = 0; t < todo.size(); ++t) scores[todo[t]] = sc[t];
+  }
   float best_lcp = 0;
   best_hypo = _pose_hypos[0];
   for (size_t i = 0; i < n; ++i) {

@@ -54,6 +54,9 @@ class PoseEstimator {
   hop_ctx *ctx;
   Cloud _model, _model001;
   hop_cloud *d_scene = nullptr, *d_model = nullptr, *d_model001 = nullptr;
+  // what refineByICP's single device visit brought back for selectBest: refined poses (n x 16) and their LCP scores
+  std::vector<float> _scored_poses, _scored_lcp;
+  float _scored_lcp_dist = 0.f, _scored_lcp_angle = 0.f;
   std::map<std::string, hop_mesh *> _meshes;
   std::vector<float> _obj_mesh_V;      // _obj_mesh (model frame), kept for the renderer
   std::vector<int32_t> _obj_mesh_F;

@@ -66,9 +66,11 @@ typedef struct hop_icp_params {
                            difference Jacobian and MINPACK stopping rules, replayed on the 13x13 moments (csrc/lm_replay.cuh): the
                            parity path and the default;  1 = one Gauss-Newton step per iteration;  2 = exact minimiser of every
                            iteration's objective (goes further along weak directions than the reference does: not parity) */
-  int32_t team_warps;   /* warps cooperating on one hypothesis: 0 = auto, else 1/2/4/8 */
-  int32_t pipeline;     /* mode 0, solver 0: 0 = fused (whole ICP of a hypothesis in one CTA, one launch per batch); 1 = two
-                           launches per iteration (correspondence records through global memory) */
+  int32_t team_warps;   /* reserved (was: warps cooperating on one hypothesis); ignored */
+  int32_t pipeline;     /* mode 0: 0 = persistent fused (default): the whole ICP of a hypothesis inside one CTA, one launch per batch, a
+                           CTA's warps solve its hypotheses in parallel;  1 = iteration-synchronous: per ICP iteration one launch that
+                           turns correspondences into the 13x13 moments of every active hypothesis (records stay in shared memory) and
+                           one that solves, one warp per hypothesis.  mode 1 always runs iteration-synchronous. */
 } hop_icp_params;
 
 /* Utils::computeLCP arguments (Utils.cpp:372) */
@@ -91,8 +93,8 @@ int hop_sync(hop_ctx *ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t hop_launch_count(const hop_ctx *ctx);
 /* ---- per-kernel device timing (CUDA events on the context's stream around each launch of a kernel family) ------ */
-#define HOP_PROF_ICP_CORRESPOND 0 /* icp_correspond_kernel: NN + rejection, one launch per ICP iteration */
-#define HOP_PROF_ICP_SOLVE 1      /* icp_solve_kernel: moments + point-to-plane solve + convergence */
+#define HOP_PROF_ICP_CORRESPOND 0 /* icp_moments_kernel / icp_kabsch_sums_kernel: NN + rejection + sums, one launch per ICP iteration (pipeline 1, mode 1) */
+#define HOP_PROF_ICP_SOLVE 1      /* icp_solve_kernel: the reference's LM on the moments + convergence, one launch per ICP iteration */
 #define HOP_PROF_LCP_SCORE 2      /* lcp_score_kernel (+ its fixed-order reduction) */
 #define HOP_PROF_NN_BUILD 3       /* nearest-neighbour grid builds (all kernels of one build = one span) */
 #define HOP_PROF_TOPK 4
@@ -432,6 +434,23 @@ int hop_select_topk_dev(hop_ctx *ctx, const float *d_poses, const float *d_score
                         int32_t frame, hop_pose_rec *d_out);
 int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H, int K, int32_t id_offset,
                     int32_t frame, hop_pose_rec *out);
+
+/* ---- refineByICP + selectBest in one call ------------------------------------------------------------------------- */
+/* main_realdata_auto.cpp:199-204 runs PoseEstimator::refineByICP (PoseEstimator.cpp:235-275) and, after the pruning steps,
+ * PoseEstimator::selectBest (:465-502) on the same hypotheses; the LCP score of a hypothesis does not depend on the others, so
+ * both can be done in one visit to the device: poses up once, K4 -> K5 -> top-K, results down once, ONE synchronisation (the
+ * separate entry points upload the poses twice and synchronise twice).
+ *   model_icp : the 5 mm model of refineByICP (_model); model_lcp : the 1 mm model of selectBest (_model001), NULL = model_icp
+ *   poses_in  : H x 16 model2scene;  poses_out (may be NULL, may alias poses_in) : the refined poses
+ *   scores_out / iters_out / converged_out (H, may be NULL) : as hop_lcp_score / hop_icp_refine
+ *   winners   : K records, score descending, ties -> lower index (K = 0: none; K = 1: selectBest's arg-max) */
+int hop_refine_score_select(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model_icp, hop_cloud *model_lcp, const float *poses_in, int H,
+                            const hop_icp_params *icp, const hop_lcp_params *lcp, int use_weights, int K, float *poses_out,
+                            float *scores_out, int32_t *iters_out, int32_t *converged_out, hop_pose_rec *winners);
+/* device buffers, stream-ordered, no synchronisation; d_winners may be the send slot of the all-gather of winners */
+int hop_refine_score_select_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model_icp, hop_cloud *model_lcp, float *d_poses_inout, int H,
+                                const hop_icp_params *icp, const hop_lcp_params *lcp, int use_weights, int K, int32_t id_offset,
+                                int32_t frame, int32_t *d_iters, int32_t *d_conv, float *d_scores, hop_pose_rec *d_winners);
 
 #ifdef __cplusplus
 }

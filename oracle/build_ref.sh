@@ -24,6 +24,7 @@ if [ -f "$HERE/ref_opengr.cpp" ]; then
   INCS="-I$TMP -I$GR $INCS"
 fi
 if [ -f "$HERE/ref_cluster.cpp" ]; then SRCS="$SRCS $HERE/ref_cluster.cpp"; fi
+if [ -f "$HERE/ref_umeyama.cpp" ]; then SRCS="$SRCS $HERE/ref_umeyama.cpp"; fi
 # the reference's vendored libigl (header-only use): signed distance to a mesh, what SDFchecker calls
 if [ -f "$HERE/ref_sdf.cpp" ] && [ -f "$REF/src/perception/include/igl/signed_distance.h" ]; then
   SRCS="$SRCS $HERE/ref_sdf.cpp"

@@ -253,6 +253,42 @@ def refine_by_icp(s_xyz, s_nrm, m_xyz, m_nrm, poses, max_iter=10, angle=45.0, di
     return colmajor_to_poses(flat), iters, conv
 
 
+def kabsch(src, dst):
+    """rigid T (4,4) minimising sum |R s + t - d|^2 (the restatement of pcl::umeyama without scaling), or None when degenerate"""
+    src, dst = _c(src), _c(dst)
+    T = np.empty(16, np.float32)
+    L = lib()
+    L.hop_oracle_kabsch.restype = C.c_int
+    L.hop_oracle_kabsch.argtypes = [_f32p, _f32p, C.c_int, _f32p]
+    return colmajor_to_poses(T)[0] if L.hop_oracle_kabsch(src, dst, len(src), T) else None
+
+
+def ref_umeyama(src, dst):
+    """the reference tree's own Eigen::umeyama (oracle/_ref)"""
+    src, dst = _c(src), _c(dst)
+    T = np.empty(16, np.float32)
+    R = ref()
+    R.hop_ref_umeyama.argtypes = [_f32p, _f32p, C.c_int, _f32p]
+    R.hop_ref_umeyama.restype = None
+    R.hop_ref_umeyama(src, dst, len(src), T)
+    return colmajor_to_poses(T)[0]
+
+
+def refine_by_icp_p2p(s_xyz, m_xyz, poses, max_iter=100, dist=0.01, abs_mse_eps=1e-12, nthreads=0):
+    """Utils::runICP(segment, model, T, max_corres_dist) (Utils.cpp:135-164: reciprocal correspondences + SVD) per hypothesis, with
+    the pose update of PoseEstimator::refineByICP.  Returns refined (H,4,4), iterations, converged."""
+    s_xyz, m_xyz = _c(s_xyz), _c(m_xyz)
+    flat = poses_to_colmajor(poses)
+    H = len(flat)
+    iters, conv = np.zeros(H, np.int32), np.zeros(H, np.int32)
+    L = lib()
+    L.hop_oracle_refine_by_icp_p2p.restype = None
+    L.hop_oracle_refine_by_icp_p2p.argtypes = [_f32p, C.c_int, _f32p, C.c_int, _f32p, C.c_int, C.c_int, C.c_float, C.c_double, C.c_int,
+                                               _i32p, _i32p]
+    L.hop_oracle_refine_by_icp_p2p(s_xyz, len(s_xyz), m_xyz, len(m_xyz), flat, H, max_iter, dist, abs_mse_eps, nthreads, iters, conv)
+    return colmajor_to_poses(flat), iters, conv
+
+
 def select_best(s_xyz, s_nrm, m_xyz, m_nrm, poses, dist=0.001, angle=10.0, weights=None, nthreads=0):
     s_xyz, s_nrm, m_xyz, m_nrm = _c(s_xyz), _c(s_nrm), _c(m_xyz), _c(m_nrm)
     flat = poses_to_colmajor(poses)

@@ -687,6 +687,137 @@ void hop_oracle_refine_by_icp(const float *s_xyz, const float *s_nrm, int ns, co
   }
 }
 
+/* ------------------------------------------------------------------------------------------------
+ * Utils::runICP(pclSegment, pclModel, offsetTransform, max_corres_dist)            Utils.cpp:135-164
+ * = pcl::IterativeClosestPoint<PointXYZRGBNormal, PointXYZRGBNormal> with its defaults (PCL 1.9):
+ *   setUseReciprocalCorrespondences(true)  -> CorrespondenceEstimation::determineReciprocalCorrespondences: source point i
+ *       -> nearest target j (d^2 <= max^2) -> nearest SOURCE point of target j must be i (and within max)
+ *   TransformationEstimationSVD (use_umeyama = true): pcl::umeyama = Eigen::umeyama without scaling, float
+ *   setMaximumIterations(100); DefaultConvergenceCriteria: absolute MSE 1e-12 (default), relative MSE overwritten with
+ *   -DBL_MAX, rotation threshold 1.0 / translation threshold 0 (transformation_epsilon_ = 0)
+ *   setRANSACIterations(100) has no effect without a CorrespondenceRejectorSampleConsensus (none is added).
+ * The Kabsch step: R = U diag(1,1,+-1) V^T of the cross-covariance, t = c_tgt - R c_src (tests pin it against the reference
+ * tree's own Eigen::umeyama, oracle/_ref).  PARITY UNPINNED against PCL itself (not installed).
+ * Output as hop_oracle_run_icp: T = final transformation (identity when not converged); returns the iterations.
+ * ---------------------------------------------------------------------------------------------- */
+static void sym3_jacobi(double A[3][3], double V[3][3]) { /* eigen decomposition of a symmetric 3x3: A -> diag, V = vectors */
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) V[i][j] = i == j;
+  for (int sweep = 0; sweep < 60; ++sweep) {
+    double off = fabs(A[0][1]) + fabs(A[0][2]) + fabs(A[1][2]);
+    if (off < 1e-300) break;
+    for (int p = 0; p < 2; ++p) for (int q = p + 1; q < 3; ++q) {
+      if (A[p][q] == 0.0) continue;
+      double theta = (A[q][q] - A[p][p]) / (2.0 * A[p][q]);
+      double t = (theta >= 0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+      double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+      for (int k = 0; k < 3; ++k) { double akp = A[k][p], akq = A[k][q]; A[k][p] = c * akp - sn * akq; A[k][q] = sn * akp + c * akq; }
+      for (int k = 0; k < 3; ++k) { double apk = A[p][k], aqk = A[q][k]; A[p][k] = c * apk - sn * aqk; A[q][k] = sn * apk + c * aqk; }
+      for (int k = 0; k < 3; ++k) { double vkp = V[k][p], vkq = V[k][q]; V[k][p] = c * vkp - sn * vkq; V[k][q] = sn * vkp + c * vkq; }
+    }
+  }
+}
+
+/* rigid transform (4x4 col-major) minimising sum |R s + t - d|^2 over n pairs; returns 0 when the configuration is degenerate */
+int hop_oracle_kabsch(const float *src, const float *dst, int n, float *T) {
+  double cs[3] = {0, 0, 0}, cd[3] = {0, 0, 0};
+  for (int i = 0; i < n; ++i) for (int k = 0; k < 3; ++k) { cs[k] += src[3 * i + k]; cd[k] += dst[3 * i + k]; }
+  for (int k = 0; k < 3; ++k) { cs[k] /= n; cd[k] /= n; }
+  double S[3][3] = {{0}}; /* sigma = sum (d - cd)(s - cs)^T */
+  for (int i = 0; i < n; ++i)
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) S[r][c] += (dst[3 * i + r] - cd[r]) * (src[3 * i + c] - cs[c]);
+  /* S = U D V^T:  S^T S = V D^2 V^T */
+  double A[3][3], V[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { A[r][c] = 0; for (int k = 0; k < 3; ++k) A[r][c] += S[k][r] * S[k][c]; }
+  sym3_jacobi(A, V);
+  int ord[3] = {0, 1, 2}; /* singular values descending */
+  for (int a = 0; a < 2; ++a) for (int b = a + 1; b < 3; ++b) if (A[ord[b]][ord[b]] > A[ord[a]][ord[a]]) { int t = ord[a]; ord[a] = ord[b]; ord[b] = t; }
+  double Vs[3][3], U[3][3], sv[3];
+  for (int c = 0; c < 3; ++c) { sv[c] = sqrt(fmax(A[ord[c]][ord[c]], 0.0)); for (int r = 0; r < 3; ++r) Vs[r][c] = V[r][ord[c]]; }
+  if (!(sv[1] > 1e-12 * sv[0]) || !(sv[0] > 0)) return 0; /* rank < 2: no unique rotation */
+  for (int c = 0; c < 2; ++c) for (int r = 0; r < 3; ++r) { double u = 0; for (int k = 0; k < 3; ++k) u += S[r][k] * Vs[k][c]; U[r][c] = u / sv[c]; }
+  /* third columns by cross products so that det U = det V = +1, then the reflection case flips the sign of the last term */
+  double v2[3] = {Vs[1][0] * Vs[2][1] - Vs[2][0] * Vs[1][1], Vs[2][0] * Vs[0][1] - Vs[0][0] * Vs[2][1], Vs[0][0] * Vs[1][1] - Vs[1][0] * Vs[0][1]};
+  double u2[3] = {U[1][0] * U[2][1] - U[2][0] * U[1][1], U[2][0] * U[0][1] - U[0][0] * U[2][1], U[0][0] * U[1][1] - U[1][0] * U[0][1]};
+  /* with det U = det V = +1 the optimal rotation is U V^T with all three terms positive (the sign of det(S) is absorbed) */
+  double R[3][3];
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) R[r][c] = U[r][0] * Vs[c][0] + U[r][1] * Vs[c][1] + u2[r] * v2[c];
+  memset(T, 0, 16 * sizeof(float));
+  for (int r = 0; r < 3; ++r) {
+    for (int c = 0; c < 3; ++c) M4(T, r, c) = (float)R[r][c];
+    M4(T, r, 3) = (float)(cd[r] - (R[r][0] * cs[0] + R[r][1] * cs[1] + R[r][2] * cs[2]));
+  }
+  M4(T, 3, 3) = 1.f;
+  return 1;
+}
+
+int hop_oracle_run_icp_p2p(const float *src_xyz, int ns, const float *tgt_xyz, int nt, float *T_out, int max_iter,
+                           float max_corres_dist, double abs_mse_eps, int *converged_out) {
+  float *sx = (float *)malloc(sizeof(float) * 3 * (size_t)(ns + 1));
+  memcpy(sx, src_xyz, sizeof(float) * 3 * (size_t)ns);
+  kd_tree *tree = kd_build(tgt_xyz, nt);
+  const float max_d2 = max_corres_dist * max_corres_dist;
+  float final_T[16], T[16];
+  m4_identity(final_T); m4_identity(T);
+  float *cs = (float *)malloc(sizeof(float) * 6 * (size_t)(ns + 1)), *ct = cs + 3 * (size_t)ns;
+  double prev_mse = DBL_MAX;
+  int iters = 0, converged = 0;
+  if (max_iter < 1) max_iter = 1;
+  for (;;) {
+    kd_tree *rtree = kd_build(sx, ns); /* tree_reciprocal_: the (moved) source cloud */
+    int m = 0; double mse = 0.0;
+    for (int i = 0; i < ns; ++i) {
+      float d2, e2;
+      int j = kd_nn(tree, sx + 3 * i, &d2);
+      if (j < 0 || d2 > max_d2) continue;
+      int k = kd_nn(rtree, tgt_xyz + 3 * j, &e2);
+      if (e2 > max_d2 || k != i) continue;
+      memcpy(cs + 3 * m, sx + 3 * i, 12); memcpy(ct + 3 * m, tgt_xyz + 3 * j, 12);
+      mse += d2; ++m;
+    }
+    kd_free(rtree);
+    if (m < 3) { converged = 0; break; }
+    if (!hop_oracle_kabsch(cs, ct, m, T)) m4_identity(T);
+    hop_oracle_transform_cloud(T, sx, NULL, ns, sx, NULL);
+    m4_mul(T, final_T, final_T);
+    ++iters;
+    if (iters >= max_iter) { converged = 1; break; }
+    double cos_angle = 0.5 * ((double)M4(T, 0, 0) + (double)M4(T, 1, 1) + (double)M4(T, 2, 2) - 1.0);
+    double tsq = (double)M4(T, 0, 3) * M4(T, 0, 3) + (double)M4(T, 1, 3) * M4(T, 1, 3) + (double)M4(T, 2, 3) * M4(T, 2, 3);
+    if (cos_angle >= 1.0 && tsq <= 0.0) { converged = 1; break; }
+    mse /= (double)m;
+    if (fabs(mse - prev_mse) < abs_mse_eps) { converged = 1; break; }
+    prev_mse = mse;
+  }
+  if (converged) memcpy(T_out, final_T, sizeof(final_T)); else m4_identity(T_out);
+  if (converged_out) *converged_out = converged;
+  kd_free(tree); free(sx); free(cs);
+  return iters;
+}
+
+/* a batch of hypotheses like hop_oracle_refine_by_icp (the model is moved by the hypothesis, the scene is the source) */
+void hop_oracle_refine_by_icp_p2p(const float *s_xyz, int ns, const float *m_xyz, int nm, float *poses, int H, int max_iter,
+                                  float dist_thres, double abs_mse_eps, int nthreads, int *iters_out, int *converged_out) {
+#ifdef _OPENMP
+  if (nthreads > 0) omp_set_num_threads(nthreads);
+#endif
+#pragma omp parallel
+  {
+    float *mx = (float *)malloc(sizeof(float) * 3 * (size_t)(nm + 1));
+#pragma omp for schedule(dynamic)
+    for (int i = 0; i < H; ++i) {
+      float *pose = poses + 16 * (size_t)i;
+      float T[16], Tinv[16], out[16];
+      hop_oracle_transform_cloud(pose, m_xyz, NULL, nm, mx, NULL);
+      int conv = 0;
+      int it = hop_oracle_run_icp_p2p(s_xyz, ns, mx, nm, T, max_iter, dist_thres, abs_mse_eps, &conv);
+      if (m4_inverse(T, Tinv) == 0) { m4_mul(Tinv, pose, out); memcpy(pose, out, sizeof(out)); }
+      if (iters_out) iters_out[i] = it;
+      if (converged_out) converged_out[i] = conv;
+    }
+    free(mx);
+  }
+}
+
 /* PoseEstimator::selectBest (PoseEstimator.cpp:474-498): LCP of every hypothesis, returns argmax (first best) */
 int hop_oracle_select_best(const float *s_xyz, const float *s_nrm, int ns, const float *weights, const float *m_xyz,
                            const float *m_nrm, int nm, const float *poses, int H, float lcp_dist, float normal_angle,

@@ -9,8 +9,8 @@ list the others:
 
   unstable : the oracle's own result moves by more than 0.25 mm / 0.25 deg under four 1e-7 m perturbations of the hypothesis
              translation or when its LM step is the reference tree's Eigen LM (oracle/_ref) instead of the C restatement;
-  weak     : the first iteration's point-to-plane Jacobian (columns scaled to unit norm) has a singular-value ratio below
-             5e-3: along the weak direction the reference's LM stops where the rounding noise of its forward-difference
+  weak     : the first iteration's point-to-plane Jacobian in the reference's parametrisation (translation + rotation about the
+             camera origin, columns scaled to unit norm as MINPACK does) has a singular-value ratio below 5e-3: along the weak direction the reference's LM stops where the rounding noise of its forward-difference
              Jacobian (h = sqrt(eps)|x_j|: as small as 1e-8) stalls it, not where the objective does.
 """
 import numpy as np
@@ -53,7 +53,7 @@ def first_iteration_conditioning(s, sn, m, mn, hyp, dist=0.01, angle=45.0):
         if keep.sum() < 6:
             continue
         p, n = s[keep].astype(np.float64), mnn[j[keep]].astype(np.float64)
-        J = np.hstack([n, 2 * np.cross(p - p.mean(0), n)])
+        J = np.hstack([n, 2 * np.cross(p, n)])   # the reference's own parametrisation: rotations about the camera origin
         nrm = np.linalg.norm(J, axis=0)
         if nrm.min() <= 0:
             continue
