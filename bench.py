@@ -1,17 +1,22 @@
 #!/usr/bin/env python
 """bench.py -- pose hypotheses/s through the hot path (ICP refinement K4 + LCP scoring K5 + winner selection).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2|headline|C3|tiny] [--impl ours|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload headline|C2|C3|C4|C5|tiny] [--scaling weak|strong] [--impl ours|reference]
 
 One "step" = one depth frame: the frame's scene cloud and its batch of H pose hypotheses go through
   [scene NN-grid build] -> icp_refine (K4) -> lcp_score (K5) -> top-K winners (-> one all-gather of winners when N>1).
+Default workload: the north-star headline (10 k-point scene x 10 k-point model, H = 16 384, 10 ICP iterations); BASELINE config C2
+(2 k x 10 k, H = 1024) is measured in the same run and reported under config.also, and one Super4PCS registration and one
+hand-state grid (K1) of the C2 sizes under config.stage_ms (what a whole "Super4PCS + ICP" frame adds around the hot kernels).
 `value`  : hypotheses/s with the scene cloud and hypotheses already resident in HBM (CUDA events, L2 flushed between steps).
-`e2e`    : the same through the host-buffer C ABI (hop_cloud_update + hop_icp_refine + hop_lcp_score: what
-           PoseEstimator::refineByICP()/selectBest() call), pinned host inputs, H2D + D2H inside the timed region.
-`roofline`: dominant kernel (icp_fused_kernel): algorithmic bytes / its own CUDA-event time vs the measured HBM peak.
+`e2e`    : the same through the host-buffer C ABI (hop_cloud_update + hop_refine_score_select: what PoseEstimator::refineByICP()
+           / selectBest() call), pinned host inputs, H2D + D2H inside the timed region.
+`roofline`: dominant kernel (icp_fused_kernel): algorithmic bytes / its own CUDA-event time vs the measured HBM peak; `limiter` and
+           the *_pct fields name what ncu says actually bounds it.
 `cpu_baseline`: the oracle port of the reference algorithm on this box's host cores (bounded sample), rank 0, N=1.
-Multi-GPU: frames are independent -> every rank processes its own frames (weak scaling), one NCCL all-gather of the
-per-rank winner records per step.
+Multi-GPU: --scaling weak (default): every rank its own frames; --scaling strong: the SAME frames, hypotheses [r H/G, (r+1) H/G) per
+rank.  Either way ONE all-gather of the per-rank winner records per step, through libhop's C ABI (hop_gather_winners_dev: NCCL,
+on its own stream, overlapped with the next step's kernels); torch.distributed only hands out the NCCL id and takes the max over ranks.
 """
 import argparse
 import json
@@ -27,12 +32,17 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "icra20-hand-object-pose_b200"))
 
-METRIC = "pose hypotheses/sec (ICP-refined + LCP-scored)"
+METRIC = "pose hypotheses/sec (Super4PCS+ICP) per frame at 1/2/4/8 B200 vs CPU ref"   # BASELINE.json's metric string
+METRIC_NOTE = "hypotheses ICP-refined (K4) + LCP-scored (K5) + winners selected per second; config.stage_ms adds the Super4PCS and K1 stages of a frame"
 UNIT = "hypotheses/s"
 TOPK = 16
-# dram__bytes_read.sum + dram__bytes_write.sum of one icp_fused_kernel launch (a whole C2 batch), from the ncu --set full
-# captures summarised in profiles/r01_ncu_icp_fused_kernel_C2.txt and _headline.txt; other workloads were not captured -> null
-TRAFFIC_BYTES_PER_LAUNCH = {"C2": 30083840, "headline": 36006144}
+# from the committed ncu --set full captures of one icp_fused_kernel launch (profiles/r02_ncu_icp_fused_kernel_<workload>.txt):
+# dram__bytes_read.sum + dram__bytes_write.sum, and what the capture says bounds the kernel; other workloads were not captured
+NCU_CAPTURE = {}
+try:
+    NCU_CAPTURE = json.load(open(os.path.join(ROOT, "profiles", "r02_ncu_capture_summary.json")))
+except Exception:
+    pass
 N_FRAMES = 4  # distinct synthetic frames cycled through the steps (a step = `frames_per_step` consecutive frames, default 1)
 
 
@@ -42,7 +52,10 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--workload", default="headline")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--no-also", action="store_true", help="skip the C2 line under config.also")
+    ap.add_argument("--no-stages", action="store_true", help="skip config.stage_ms (Super4PCS registration + K1 grid)")
     ap.add_argument("--pipeline", type=int, default=0, help="0 = persistent fused kernel (default), 1 = per-iteration moments + solve kernels")
     ap.add_argument("--solver", type=int, default=0, help="0 = replay of the reference's LM (parity path), 1 = Gauss-Newton, 2 = exact per-iteration minimiser")
     ap.add_argument("--cpu-sample", type=int, default=0, help="hypotheses in the cpu_baseline sample (0 = auto)")
@@ -55,7 +68,7 @@ def make_frames(wl, rank):
     m, mn = synth.make_model(wl["model"], wl["n_model"], seed=1)
     frames = []
     for f in range(N_FRAMES):
-        seed = 1000 * 2 + 17 * rank + f
+        seed = 1000 * 2 + 17 * rank + f   # (strong scaling passes rank 0 for every rank: the same frames everywhere)
         s, sn, conf, gt = synth.make_scene(wl["model"], wl["n_scene"], seed=seed)
         hy = synth.make_hypotheses(gt, wl["H"], seed=seed + 500)
         frames.append(dict(xyz=s, nrm=sn, conf=conf, gt=gt, hyp=hy))
@@ -134,7 +147,7 @@ def run_reference(args, wl, rank, world, out):
         r, dt, threads = cpu_baseline_run(model, frames[k % N_FRAMES], wl, sample)
         t_total += dt
     value = sample * args.steps / t_total
-    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+    line = {"impl": "reference", "metric": METRIC, "metric_note": METRIC_NOTE, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": args.workload, **wl, "sample_hypotheses_per_step": sample},
@@ -153,36 +166,91 @@ def claim_stdout():
     return real
 
 
-def main():
-    args = parse()
-    out = claim_stdout()
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    from hop_b200 import synth
-    wl = synth.workload(args.workload)
+def stage_ms(ctx, args):
+    """One Super4PCS registration (host plan + K2a pairs + K2b congruent sets + K3 verification) and one K1 grid of joint angles at
+    the C2 sizes: the stages a whole frame of the BASELINE metric adds around K4 / K5.  Milliseconds; the compiled reference's own
+    Super4PCS on the same input when oracle/_ref is present (kind: reference)."""
+    import ctypes as C
+    import hop_b200
+    from hop_b200 import capi, hand, synth
+    res = {}
+    case = synth.make_hand_case(seed=5, n_finger=300, n_hand=3000)
+    prop = hand.FingerProperty(case["finger_xyz"], case["scalars"]["num_division"])
+    p = hand.finger_params(prop, case["scalars"])
+    finger = ctx.upload_cloud(case["finger_xyz"], case["finger_nrm"])
+    scene = ctx.upload_cloud(case["scene_xyz"], case["scene_nrm"])
+    lookup = ctx.upload_cloud(case["lookup_xyz"], case["lookup_nrm"])
+    nosw = ctx.upload_cloud(case["noswivel_xyz"], case["noswivel_nrm"])
+    thetas = np.deg2rad(np.linspace(0, 120, 4096))
 
-    if args.impl == "reference":
-        run_reference(args, wl, rank, world, out)
-        return
+    def timed(fn, n=10):
+        for _ in range(3):
+            fn()
+        ctx.sync()
+        ctx.profile_enable(True)
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        ctx.sync()
+        dt = (time.perf_counter() - t0) / n
+        prof = ctx.profile_read()
+        ctx.profile_enable(False)
+        return dt * 1e3, {k: v[0] / n for k, v in prof.items() if v[1]}
 
+    dt, prof = timed(lambda: ctx.hand_overlap(finger, scene, nosw, p, thetas, lookup))
+    res["k1_hand_states_4096"] = {"e2e_ms": dt, "kernel_ms": prof.get("hand_overlap")}
+    m, mn = synth.make_model("ellipse", 10000, seed=1)
+    s, sn, conf, gt = synth.make_scene("ellipse", 2000, seed=2)
+    sub = slice(None, None, max(1, len(m) // 400))
+    keys = capi.ppf_table(m[sub], mn[sub]) if hasattr(capi, "ppf_table") else None
+    if keys is None:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_stages
+        keys = bench_stages.ppf_keys(m, mn, stride=max(1, len(m) // 400))
+    plans = {}
+
+    def plan():
+        plans["p"] = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=100))
+
+    t0 = time.perf_counter()
+    for _ in range(5):
+        plan()
+    t_plan = (time.perf_counter() - t0) / 5 * 1e3
+    out = {}
+
+    def run():
+        out["r"] = ctx.super4pcs_run(plans["p"], capacity=400000)
+
+    dt, prof = timed(run)
+    res["super4pcs_registration"] = {"host_plan_ms": t_plan, "device_e2e_ms": dt, "k2a_pairs_ms": prof.get("s4pcs_pairs"), "k2b_join_ms": prof.get("s4pcs_join"),
+                                     "k3_verify_ms": prof.get("verify_lcp"), "hypotheses_emitted": int(len(out["r"][1])), "sizes": "2 k scene x 10 k model, 100 samples, 30 trials planned"}
+    if not args.no_cpu_baseline:
+        try:
+            from oracle import cpu_oracle as O
+            if O.ref() is not None and hasattr(O.ref(), "hop_ref_s4pcs_run"):
+                thr = host_threads()
+                t0 = time.perf_counter()
+                r = O.ref_super4pcs(s, sn, conf, m, mn, keys, sample_size=100, nthreads=thr)
+                res["super4pcs_registration"]["cpu_reference"] = {"ms": (time.perf_counter() - t0) * 1e3, "kind": "reference", "cores": thr,
+                                                                  "hypotheses_emitted": int(len(r["lcp"]))}
+        except Exception as e:   # the checker is optional here
+            res["super4pcs_registration"]["cpu_reference"] = {"unavailable": str(e)[:100]}
+    for c in (finger, scene, lookup, nosw):
+        c.free()
+    return res
+
+
+def measure(ctx, args, wl, wl_name, rank, world, dev, stream, comm_ready, with_cpu):
+    """K steps of one workload on this rank; returns the numbers of the JSON line (rank 0 composes it)."""
     import torch
     import torch.distributed as dist
     import hop_b200
-
-    torch.cuda.set_device(local_rank)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    dev = torch.device("cuda", local_rank)
-
-    ctx = hop_b200.Context(local_rank)  # raises when the CUDA library / device is missing: no fallback
-    # a real (non-default) stream: everything libhop enqueues and every timing event lives on it
-    stream = torch.cuda.Stream(device=dev)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-
-    model_np, frames = make_frames(wl, rank)
-    H, ns, nm = wl["H"], wl["n_scene"], wl["n_model"]
+    from hop_b200 import distributed as D
+    strong = args.scaling == "strong" and world > 1
+    model_np, frames = make_frames(wl, 0 if strong else rank)
+    H_all, ns, nm = wl["H"], wl["n_scene"], wl["n_model"]
+    hb, he = D.shard_range(H_all, rank, world) if strong else (0, H_all)
+    H = he - hb
     FPS = int(wl.get("frames_per_step", 1))   # frames of one rank in one step (C4: 16), one all-gather of winners per step
     model = ctx.upload_cloud(*model_np)
     icp_p = ctx.icp_params(max_iter=wl["max_iter"], solver=args.solver, pipeline=args.pipeline)
@@ -193,16 +261,16 @@ def main():
 
     # ---- device-resident inputs for `value` ----
     scenes = [ctx.upload_cloud(f["xyz"], f["nrm"], f["conf"]) for f in frames]
-    d_hyp = [torch.from_numpy(hop_b200.capi.poses_to_colmajor(f["hyp"])).to(dev) for f in frames]
+    d_hyp = [torch.from_numpy(hop_b200.capi.poses_to_colmajor(f["hyp"][hb:he])).to(dev) for f in frames]
     d_pose = torch.empty((H, 16), dtype=torch.float32, device=dev)
     d_iters = torch.zeros(H, dtype=torch.int32, device=dev)
     d_conv = torch.zeros(H, dtype=torch.int32, device=dev)
     d_score = torch.zeros(H, dtype=torch.float32, device=dev)
-    d_send = torch.zeros(FPS * TOPK * 80, dtype=torch.uint8, device=dev)
-    d_recv = torch.zeros(world * FPS * TOPK * 80, dtype=torch.uint8, device=dev)
+    d_send = [torch.zeros(FPS * TOPK * 80, dtype=torch.uint8, device=dev) for _ in range(2)]      # double buffered: the gather of
+    d_recv = [torch.zeros(world * FPS * TOPK * 80, dtype=torch.uint8, device=dev) for _ in range(2)]  # step k travels during step k + 1
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    def step_value(k, evs=None, on_frame=None):
+    def step_value(k, evs=None, on_frame=None, last=False):
         if evs: evs[0].record(stream)
         for f in range(FPS):
             fi = (k * FPS + f) % N_FRAMES
@@ -214,10 +282,15 @@ def main():
             if evs and f == 0: evs[1].record(stream)
             ctx.lcp_score_dev(sc, model, d_pose.data_ptr(), H, lcp_p, d_score.data_ptr())
             if evs and f == 0: evs[2].record(stream)
-            ctx.select_topk_dev(d_pose.data_ptr(), d_score.data_ptr(), H, TOPK, d_send.data_ptr() + f * TOPK * 80, id_offset=0, frame=rank * FPS + f)
+            ctx.select_topk_dev(d_pose.data_ptr(), d_score.data_ptr(), H, TOPK, d_send[k & 1].data_ptr() + f * TOPK * 80, id_offset=hb, frame=rank * FPS + f)
             if on_frame: on_frame()
-        if world > 1:
-            dist.all_gather_into_tensor(d_recv, d_send)
+        if world > 1 and comm_ready:
+            # the previous step's gather has had a whole step to finish: order this stream after it (its receive buffer is reused
+            # two steps later), then send this step's records on the communicator's stream without blocking the next step
+            ctx.gather_wait(False)
+            ctx.gather_winners_dev(d_send[k & 1].data_ptr(), FPS * TOPK, d_recv[k & 1].data_ptr(), overlap=True)
+            if last:
+                ctx.gather_wait(False)
         if evs: evs[3].record(stream)
 
     def barrier():
@@ -226,21 +299,20 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up ----
-    # (every distinct frame is visited at least once: a frame's first visit allocates its scene grid)
+    # ---- warm-up (every distinct frame is visited at least once: a frame's first visit allocates its scene grid) ----
     for w in range(max(args.warmup, N_FRAMES)):
         step_value(w)
     barrier()
 
     # ---- timed: K steps, device time per step from events, L2 flushed before each ----
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(dev.index)
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
     l0 = ctx.launch_count()
     barrier()
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        step_value(k, ev[k])
+        step_value(k, ev[k], last=(k == args.steps - 1))
     barrier()
     launches = ctx.launch_count() - l0
     t_step = np.array([e[0].elapsed_time(e[3]) for e in ev])
@@ -248,6 +320,38 @@ def main():
     t_lcp = np.array([e[1].elapsed_time(e[2]) for e in ev])
     total_ms = float(t_step.sum())
     iters_mean = float(d_iters.float().mean().item())
+    last_buf = (args.steps - 1) & 1
+    gathered = np.frombuffer(d_recv[last_buf].cpu().numpy().tobytes(), dtype=hop_b200.capi.POSE_REC_DTYPE).copy() if world > 1 and comm_ready else None
+
+    # ---- the collective alone (not overlapped): device time of one all-gather of this size ----
+    allgather_us = None
+    if world > 1 and comm_ready:
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for _ in range(5):
+            ctx.gather_winners_dev(d_send[0].data_ptr(), FPS * TOPK, d_recv[0].data_ptr(), overlap=False)
+        barrier()
+        g0.record(stream)
+        for _ in range(20):
+            ctx.gather_winners_dev(d_send[0].data_ptr(), FPS * TOPK, d_recv[0].data_ptr(), overlap=False)
+        g1.record(stream)
+        torch.cuda.synchronize()
+        allgather_us = g0.elapsed_time(g1) / 20 * 1e3
+
+    # ---- strong scaling: the merged winners of the last step == the winners of the whole batch on one GPU ----
+    winners_match = None
+    if strong and comm_ready:
+        fi = ((args.steps - 1) * FPS) % N_FRAMES
+        full = torch.from_numpy(hop_b200.capi.poses_to_colmajor(frames[fi]["hyp"])).to(dev)
+        f_it = torch.zeros(H_all, dtype=torch.int32, device=dev); f_cv = torch.zeros(H_all, dtype=torch.int32, device=dev)
+        f_sc = torch.zeros(H_all, dtype=torch.float32, device=dev); f_out = torch.zeros(TOPK * 80, dtype=torch.uint8, device=dev)
+        ctx.icp_refine_dev(scenes[fi], model, full.data_ptr(), H_all, icp_p, f_it.data_ptr(), f_cv.data_ptr())
+        ctx.lcp_score_dev(scenes[fi], model, full.data_ptr(), H_all, lcp_p, f_sc.data_ptr())
+        ctx.select_topk_dev(full.data_ptr(), f_sc.data_ptr(), H_all, TOPK, f_out.data_ptr(), id_offset=0, frame=0)
+        torch.cuda.synchronize()
+        single = np.frombuffer(f_out.cpu().numpy().tobytes(), dtype=hop_b200.capi.POSE_REC_DTYPE)
+        merged = D.merge_winners(gathered, TOPK)
+        winners_match = bool(np.array_equal(merged["id"], single["id"]) and np.array_equal(merged["score"], single["score"])
+                             and np.array_equal(merged["pose"], single["pose"]))
 
     # ---- per-kernel device time: the same K steps again with libhop's event profiling on (CUDA events recorded on
     #      the launching stream around every launch of each kernel family; kept out of the `value` timing) ----
@@ -260,7 +364,7 @@ def main():
 
     for k in range(args.steps):
         flush.fill_(k & 0xFF)
-        step_value(k, None, count_iters)
+        step_value(k, None, count_iters, last=(k == args.steps - 1))
     iters_sum = iters_box[0]
     prof = ctx.profile_read()
     ctx.profile_enable(False)
@@ -273,7 +377,7 @@ def main():
         for k in p:
             p[k][...] = f[k]
         p["hyp"] = ctx.pinned_array((H, 16), np.float32)
-        p["hyp"][...] = hop_b200.capi.poses_to_colmajor(f["hyp"])
+        p["hyp"][...] = hop_b200.capi.poses_to_colmajor(f["hyp"][hb:he])
         p["work"] = ctx.pinned_array((H, 16), np.float32)
         p["iters"] = ctx.pinned_array((H,), np.int32)
         p["conv"] = ctx.pinned_array((H,), np.int32)
@@ -319,6 +423,72 @@ def main():
         t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         total_ms, e2e_ms = float(t[0].item()), float(t[1].item())
+        its = torch.tensor([float(iters_sum)], dtype=torch.float64, device=dev)
+        dist.all_reduce(its, op=dist.ReduceOp.SUM)
+
+    units = (H_all if strong else world * H) * FPS * args.steps   # hypotheses all ranks processed in the K steps
+    res = {"value": units / (total_ms * 1e-3), "e2e_value": units / (e2e_ms * 1e-3), "ms_per_step": total_ms / args.steps, "e2e_ms_per_step": e2e_ms / args.steps,
+           "h2d": h2d, "d2h": d2h, "launches": int(launches), "clocks": clocks, "iters_mean": iters_mean, "iters_sum": iters_sum, "prof": prof,
+           "t_icp": float(np.mean(t_icp)), "t_lcp": float(np.mean(t_lcp)), "FPS": FPS, "H_rank": H, "g_icp": g_icp, "g_lcp": g_lcp,
+           "allgather_us": allgather_us, "winners_match": winners_match, "cpu": None}
+    if with_cpu and rank == 0:
+        # bounded sample of the same workload: whole frames' batches (or the first hypotheses of one) for >= ~10 s of CPU work
+        probe_rate, _, thr = cpu_baseline_run(model_np, frames[0], wl, min(8, H_all))
+        sample = args.cpu_sample or int(max(8, min(H_all, probe_rate * 12.0)))
+        done, spent, k = 0, 0.0, 0
+        while spent < 10.0 and k < 64:
+            rate, dt, thr = cpu_baseline_run(model_np, frames[k % N_FRAMES], wl, sample)
+            done, spent, k = done + sample, spent + dt, k + 1
+        res["cpu"] = {"value": done / spent, "unit": UNIT, "cores": thr, "kind": "port",
+                      "sample": f"{k} x first {sample} of {H_all} hypotheses (frames cycled), {thr} OpenMP threads, {spent:.1f} s"}
+    for c in scenes + [model, e2e_scene]:
+        c.free()
+    return res
+
+
+def main():
+    args = parse()
+    out = claim_stdout()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    from hop_b200 import synth
+    wl = synth.workload(args.workload)
+
+    if args.impl == "reference":
+        run_reference(args, wl, rank, world, out)
+        return
+
+    import torch
+    import torch.distributed as dist
+    import hop_b200
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = hop_b200.Context(local_rank)  # raises when the CUDA library / device is missing: no fallback
+    # a real (non-default) stream: everything libhop enqueues and every timing event lives on it
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    comm_ready = False
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+        # plumbing only: rank 0's NCCL id reaches the others; the data-path collective is libhop's own (hop_gather_winners_dev)
+        box = [hop_b200.capi.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(box[0], rank, world)
+        comm_ready = True
+
+    r = measure(ctx, args, wl, args.workload, rank, world, dev, stream, comm_ready, with_cpu=(world == 1 and not args.no_cpu_baseline))
+    also = None
+    if args.workload == "headline" and not args.no_also:
+        also = measure(ctx, args, synth.workload("C2"), "C2", rank, world, dev, stream, comm_ready, with_cpu=False)
+    stages = None
+    if rank == 0 and world == 1 and not args.no_stages:
+        try:
+            stages = stage_ms(ctx, args)
+        except Exception as e:
+            stages = {"unavailable": str(e)[:200]}
 
     if rank == 0:
         peaks = {}
@@ -326,53 +496,63 @@ def main():
         if os.path.exists(pk):
             peaks = json.load(open(pk))
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        value = world * FPS * H * args.steps / (total_ms * 1e-3)
-        e2e_value = world * FPS * H * args.steps / (e2e_ms * 1e-3)
-        # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
-        # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
-        fused = args.pipeline != 1
-        corr_ms, corr_n = prof["icp_fused" if fused else "icp_correspond"]
-        corr_bytes = float(iters_sum) * 32.0 * (ns + nm)
-        achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
-        icp_ms = float(np.mean(t_icp))
-        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in prof.items() if v[1]}
-        stage_note = "first frame of the step" if FPS > 1 else "the step's frame"
+
+        def roofline(res, w, wname):
+            # Dominant kernel: icp_fused_kernel (the whole ICP of the batch, one launch per step).  ALGORITHMIC bytes (SURVEY
+            # 8d): every executed ICP iteration of a hypothesis streams the scene and the model once as 2 x float4 = 32 B/pt.
+            fused = args.pipeline != 1
+            corr_ms, corr_n = res["prof"]["icp_fused" if fused else "icp_correspond"]
+            corr_bytes = float(res["iters_sum"]) * 32.0 * (w["n_scene"] + w["n_model"])
+            achieved = corr_bytes / (corr_ms * 1e-3) / 1e9
+            cap = NCU_CAPTURE.get(wname, {}) if fused else {}
+            return {"bound": "hbm", "kernel": "icp_fused_kernel" if fused else "icp_moments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                    "frac": achieved / peak, "traffic": cap.get("dram_bytes_per_launch"),
+                    "limiter": cap.get("limiter", "l1tex"), "l1tex_pct": cap.get("l1tex_pct"), "dram_pct": cap.get("dram_pct"),
+                    "warps_active_pct": cap.get("warps_active_pct"), "issue_active_pct": cap.get("issue_active_pct"),
+                    "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
+                    "algorithmic_bytes_per_launch": corr_bytes / max(corr_n, 1), "kernel_ms_per_launch": corr_ms / max(corr_n, 1),
+                    "launches": int(corr_n), "kernel_ms_per_step": corr_ms / args.steps,
+                    "note": "achieved = ALGORITHMIC bytes, 32 B x (N_scene + N_model) per executed ICP iteration per hypothesis (the brute-force "
+                            "streaming model of SURVEY 8d), over the kernel's own CUDA-event time; frac = that over the measured HBM copy peak, as the "
+                            "contract asks.  The kernel itself gathers from an L2-resident voxel grid: its real DRAM traffic (`traffic`, ncu) is ~0.1 % of "
+                            "the algorithmic bytes and DRAM is idle (`dram_pct`); what bounds it is the L1TEX pipe delivering the gathers' sectors "
+                            "(`limiter`, `l1tex_pct`), plus the serial LM replay of every iteration (12 % of the CTA cycles at this size)"}
+
+        kernels = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps} for k, v in r["prof"].items() if v[1]}
+        stage_note = "first frame of the step" if r["FPS"] > 1 else "the step's frame"
+        cfg = {"workload": args.workload, **wl, "frames_per_rank_per_step": r["FPS"], "hypotheses_per_rank": r["H_rank"], "topk": TOPK,
+               "l2": "flushed between steps (256 MiB write)",
+               "icp_solver": {0: "reference-lm-replay", 1: "gauss-newton", 2: "exact"}[args.solver],
+               "icp_pipeline": {0: "persistent fused", 1: "moments+solve per iteration"}[args.pipeline], "mean_icp_iterations": r["iters_mean"],
+               "nn_grid_icp": r["g_icp"], "nn_grid_lcp": r["g_lcp"],
+               "stage_ms": {"icp_refine": r["t_icp"], "lcp_score": r["t_lcp"], "step": r["ms_per_step"], "of": stage_note},
+               "kernel_ms": kernels}
+        if stages is not None:
+            cfg["stage_ms"]["frame_stages_C2_sizes"] = stages
+        if world > 1:
+            cfg["collective"] = {"what": "ncclAllGather of %d x 80 B per rank per step through hop_gather_winners_dev (C ABI), on its own stream, overlapped "
+                                         "with the next step" % (r["FPS"] * TOPK), "allgather_us_alone": r["allgather_us"]}
+            if r["winners_match"] is not None:
+                cfg["collective"]["winners_match"] = r["winners_match"]
+        if also is not None:
+            cfg["also"] = {"C2": {"workload": synth.workload("C2"), "value": also["value"], "unit": UNIT, "ms_per_step": also["ms_per_step"],
+                                  "e2e": {"value": also["e2e_value"], "ms_per_step": also["e2e_ms_per_step"], "h2d_bytes_per_step": also["h2d"],
+                                          "d2h_bytes_per_step": also["d2h"]},
+                                  "mean_icp_iterations": also["iters_mean"], "roofline": roofline(also, synth.workload("C2"), "C2"),
+                                  "kernel_ms": {k: v[0] / args.steps for k, v in also["prof"].items() if v[1]}}}
         line = {
-            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": args.workload, **wl, "frames_per_rank_per_step": FPS, "topk": TOPK, "l2": "flushed between steps (256 MiB write)",
-                       "icp_solver": {0: "reference-lm-replay", 1: "gauss-newton", 2: "exact"}[args.solver],
-                       "icp_pipeline": {0: "persistent fused", 1: "moments+solve per iteration"}[args.pipeline], "mean_icp_iterations": iters_mean,
-                       "nn_grid_icp": g_icp, "nn_grid_lcp": g_lcp,
-                       "stage_ms": {"icp_refine": icp_ms, "lcp_score": float(np.mean(t_lcp)), "step": total_ms / args.steps, "of": stage_note},
-                       "kernel_ms": kernels},
-            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_ms / args.steps},
-            "gpu_launches": int(launches),
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "icp_fused_kernel" if fused else "icp_moments_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": TRAFFIC_BYTES_PER_LAUNCH.get(args.workload) if fused else None,
-                         "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650 GB/s (of fallback)",
-                         "algorithmic_bytes_per_launch": corr_bytes / max(corr_n, 1), "kernel_ms_per_launch": corr_ms / max(corr_n, 1),
-                         "launches": int(corr_n), "kernel_ms_per_step": corr_ms / args.steps,
-                         "note": "algorithmic = 32 B x (N_scene + N_model) per executed ICP iteration per hypothesis (the brute-force "
-                                 "streaming model of SURVEY 8d); the kernel itself gathers from an L2-resident voxel grid, so real DRAM "
-                                 "traffic (`traffic`, ncu) is far below it; what bounds it is the L1TEX pipe (81.7 % of peak at the headline "
-                                 "size, profiles/r01_ncu_icp_fused_kernel_headline.txt)"},
+            "metric": METRIC, "metric_note": METRIC_NOTE, "value": r["value"], "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": cfg,
+            "e2e": {"value": r["e2e_value"], "unit": UNIT, "h2d_bytes_per_step": r["h2d"], "d2h_bytes_per_step": r["d2h"], "ms_per_step": r["e2e_ms_per_step"]},
+            "gpu_launches": r["launches"], "clocks": r["clocks"], "roofline": roofline(r, wl, args.workload),
         }
-        if world == 1 and not args.no_cpu_baseline:
-            # bounded sample of the same workload: whole frames' batches (or the first hypotheses of one) for >= ~10 s of CPU work
-            probe_rate, _, thr = cpu_baseline_run(model_np, frames[0], wl, min(8, H))
-            sample = args.cpu_sample or int(max(8, min(H, probe_rate * 12.0)))
-            done, spent, k = 0, 0.0, 0
-            while spent < 10.0 and k < 64:
-                rate, dt, thr = cpu_baseline_run(model_np, frames[k % N_FRAMES], wl, sample)
-                done, spent, k = done + sample, spent + dt, k + 1
-            line["cpu_baseline"] = {"value": done / spent, "unit": UNIT, "cores": thr, "kind": "port",
-                                    "sample": f"{k} x first {sample} of {H} hypotheses (frames cycled), {thr} OpenMP threads, {spent:.1f} s"}
+        if r["cpu"] is not None:
+            line["cpu_baseline"] = r["cpu"]
         print(json.dumps(line), file=out, flush=True)
     if world > 1:
         dist.destroy_process_group()
+    ctx.close()
 
 
 if __name__ == "__main__":

@@ -198,6 +198,7 @@ void hop_destroy(hop_ctx *ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  hop_comm_destroy(ctx);
   if (ctx->s4_scene) { hop_cloud_free(ctx, ctx->s4_scene); ctx->s4_scene = nullptr; }
   if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);

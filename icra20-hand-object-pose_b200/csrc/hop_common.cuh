@@ -229,8 +229,11 @@ struct HopTuning {
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
 };
 
+struct hop_comm;   // comm.cu: the NCCL communicator of a context (null for a single-GPU context)
+
 struct hop_ctx {
   int device = 0;
+  hop_comm *comm = nullptr;
   HopTuning tune;
   // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a function: remembered per context (= per device),
   // not per process, so a second context on another GPU opts its kernels in too

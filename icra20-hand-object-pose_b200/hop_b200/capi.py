@@ -194,6 +194,13 @@ def load_library():
                                           _vp, _vp, _vp, _vp, _vp]
     L.hop_refine_score_select_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), C.POINTER(LcpParams), C.c_int, C.c_int,
                                               C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
+    L.hop_comm_unique_id.argtypes = [_vp]
+    L.hop_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
+    L.hop_comm_destroy.argtypes = [_vp]
+    L.hop_comm_rank.argtypes = [_vp, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.hop_gather_winners.argtypes = [_vp, _vp, C.c_int, _vp]
+    L.hop_gather_winners_dev.argtypes = [_vp, _vp, C.c_int, _vp, C.c_int]
+    L.hop_gather_wait.argtypes = [_vp, C.c_int]
     for name in declared_symbols():
         fn = getattr(L, name)  # raises AttributeError when an export is missing
         if fn.restype is C.c_int and name not in ("hop_cloud_size",):
@@ -211,6 +218,16 @@ def _f32(a, shape_last=None):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(_vp)
+
+
+def comm_unique_id():
+    """rank 0: the ncclUniqueId (128 bytes) every rank passes to Context.comm_init"""
+    L = load_library()
+    buf = (C.c_char * 128)()
+    rc = L.hop_comm_unique_id(buf)
+    if rc != 0:
+        raise HopError(f"hop_comm_unique_id failed ({rc}): is libnccl.so.2 on the loader path?")
+    return bytes(buf)
 
 
 def poses_to_colmajor(poses):
@@ -745,6 +762,27 @@ class Context:
                                                    C.byref(icp_params), C.byref(lcp_params), int(use_weights), K, _ptr(flat), _ptr(scores),
                                                    _ptr(iters), _ptr(conv), _ptr(win) if K else None))
         return colmajor_to_poses(flat), scores, iters, conv, win
+
+    # ---- the one collective: all-gather of winner records through the C ABI (NCCL bound at run time) ----
+    def comm_init(self, unique_id, rank, world):
+        """unique_id: the 128 bytes rank 0 got from comm_unique_id() and handed to every rank"""
+        buf = (C.c_char * 128).from_buffer_copy(bytes(unique_id))
+        self._check(self.L.hop_comm_init(self.h, buf, int(rank), int(world)))
+
+    def gather_winners(self, local):
+        """host records (numpy POSE_REC_DTYPE, K) -> world x K records, rank-major"""
+        local = np.ascontiguousarray(local)
+        r, w = C.c_int(0), C.c_int(1)
+        self._check(self.L.hop_comm_rank(self.h, C.byref(r), C.byref(w)))
+        out = np.zeros(w.value * len(local), POSE_REC_DTYPE)
+        self._check(self.L.hop_gather_winners(self.h, _ptr(local), len(local), _ptr(out)))
+        return out
+
+    def gather_winners_dev(self, d_send, K, d_recv, overlap=False):
+        self._check(self.L.hop_gather_winners_dev(self.h, _vp(d_send), int(K), _vp(d_recv), int(overlap)))
+
+    def gather_wait(self, block_host=False):
+        self._check(self.L.hop_gather_wait(self.h, int(block_host)))
 
     # ---- device-pointer variants (inputs already resident in HBM) ----
     def refine_score_select_dev(self, scene, model_icp, d_poses, H, icp_params, lcp_params, K, d_scores, d_winners, model_lcp=None,

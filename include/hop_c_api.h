@@ -435,6 +435,28 @@ int hop_select_topk_dev(hop_ctx *ctx, const float *d_poses, const float *d_score
 int hop_select_topk(hop_ctx *ctx, const float *poses, const float *scores, int H, int K, int32_t id_offset,
                     int32_t frame, hop_pose_rec *out);
 
+/* ---- the one collective: an all-gather of the per-rank winner records --------------------------------------- */
+/* The reference spreads its hypotheses over OpenMP threads (PoseEstimator.cpp:247-258, 474-483); here a frame's batch is
+ * partitioned over GPUs -- rank r of G takes hypotheses [r H / G, (r + 1) H / G) -- one hop_ctx per GPU (one process per GPU, or one
+ * host thread per context), and the only exchange is ONE ncclAllGather of K x 80 bytes per rank.  Every rank then holds the same
+ * world x K records and finishes selectBest / clusterPoses identically.  NCCL is bound at run time (libnccl.so.2).
+ *   hop_comm_unique_id : rank 0 creates the 128-byte ncclUniqueId and hands it to the other ranks (any side channel)
+ *   hop_comm_init      : ncclCommInitRank on the context's device (collective: every rank calls it)
+ *   hop_gather_winners : host buffers, local K records -> all world x K records (rank-major), blocking
+ *   hop_gather_winners_dev : device buffers; overlap = 0 stream-ordered on the context's stream; overlap = 1 on the communicator's own
+ *                        stream, after what the context's stream has enqueued so far, WITHOUT blocking it (the next frame's
+ *                        kernels run while the records travel); hop_gather_wait orders the context's stream (block_host = 0) or
+ *                        the host (1) after the gather.  d_send is typically the slot hop_select_topk_dev /
+ *                        hop_refine_score_select_dev just wrote. */
+#define HOP_COMM_ID_BYTES 128
+int hop_comm_unique_id(void *id_out_128);
+int hop_comm_init(hop_ctx *ctx, const void *id_128, int rank, int world);
+int hop_comm_destroy(hop_ctx *ctx);
+int hop_comm_rank(const hop_ctx *ctx, int *rank, int *world);
+int hop_gather_winners(hop_ctx *ctx, const hop_pose_rec *local, int K, hop_pose_rec *all);
+int hop_gather_winners_dev(hop_ctx *ctx, const hop_pose_rec *d_send, int K, hop_pose_rec *d_recv, int overlap);
+int hop_gather_wait(hop_ctx *ctx, int block_host);
+
 /* ---- refineByICP + selectBest in one call ------------------------------------------------------------------------- */
 /* main_realdata_auto.cpp:199-204 runs PoseEstimator::refineByICP (PoseEstimator.cpp:235-275) and, after the pruning steps,
  * PoseEstimator::selectBest (:465-502) on the same hypotheses; the LCP score of a hypothesis does not depend on the others, so
