@@ -161,6 +161,9 @@ int hop_create(int device, hop_ctx **out) {
     g_create_error = "hop_create: libhop is built for sm_100a (B200) only; device is sm_" + std::to_string(prop.major) + std::to_string(prop.minor);
     return HOP_ENODEV;
   }
+  // the context's resources are created with its device current; the caller's current device is restored on every return path
+  struct Restore { int prev = -1; ~Restore() { if (prev >= 0) cudaSetDevice(prev); } } restore;
+  if (cudaGetDevice(&restore.prev) != cudaSuccess) restore.prev = -1;
   if (cudaSetDevice(device) != cudaSuccess) { g_create_error = "hop_create: cudaSetDevice failed"; return HOP_ECUDA; }
   hop_ctx *ctx = new hop_ctx();
   ctx->device = device;
@@ -196,7 +199,6 @@ int hop_create(int device, hop_ctx **out) {
 void hop_destroy(hop_ctx *ctx) {
   HOP_ENTER(ctx);
   if (!ctx) return;
-  cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   hop_comm_destroy(ctx);
   if (ctx->s4_scene) { hop_cloud_free(ctx, ctx->s4_scene); ctx->s4_scene = nullptr; }

@@ -287,26 +287,29 @@ __global__ void icp_init_kernel(const float *__restrict__ poses, int H, IcpState
   list0[h] = h;
 }
 
-constexpr int SLICE = 24;
-
+// The 91 moments + sum d^2 + count = 93 sums are split into NSL slices of SZ = 96 / NSL accumulators, one slice per warp: every warp
+// reads ALL records of a chunk and accumulates only its slice.  A lane therefore adds the records lane, lane + 32, ... of the whole
+// scene in order, whatever the CTA width (4 warps x 24 or 8 warps x 12): the bits of the sums -- and with them every accept / stop
+// decision of the replayed LM -- do not depend on the CTA shape the batch size picks, so a shard of a batch (strong scaling) refines
+// to the same bits as the whole batch.
 __host__ __device__ constexpr int tri_row(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i; }
 __host__ __device__ constexpr int tri_col(int k) { int i = 0; while (k >= 13 - i) { k -= 13 - i; ++i; } return i + k; }
 
-template <int S, int E>
-__device__ __forceinline__ void acc_one(float (&acc)[SLICE], const float (&v)[13], float d2) {
-  constexpr int k = SLICE * S + E;
+template <int SZ, int S, int E>
+__device__ __forceinline__ void acc_one(float (&acc)[SZ], const float (&v)[13], float d2) {
+  constexpr int k = SZ * S + E;
   if constexpr (k < 91) acc[E] = fmaf(v[tri_row(k)], v[tri_col(k)], acc[E]);
   else if constexpr (k == 91) acc[E] += d2;
   else if constexpr (k == 92) acc[E] += 1.f;
 }
-template <int S, int... E>
-__device__ __forceinline__ void acc_slice(float (&acc)[SLICE], const float (&v)[13], float d2, std::integer_sequence<int, E...>) {
-  (acc_one<S, E>(acc, v, d2), ...);
+template <int SZ, int S, int... E>
+__device__ __forceinline__ void acc_slice(float (&acc)[SZ], const float (&v)[13], float d2, std::integer_sequence<int, E...>) {
+  (acc_one<SZ, S, E>(acc, v, d2), ...);
 }
 
-// phase B: this warp's slice (24 of the 91 + 2 sums) of the moments over records [begin, end) in shared memory
-template <int S>
-__device__ __forceinline__ void accumulate_chunk(float (&acc)[SLICE], const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
+// phase B: this warp's slice of the moments over records [begin, end) in shared memory
+template <int SZ, int S>
+__device__ __forceinline__ void accumulate_chunk(float (&acc)[SZ], const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
   for (int i = begin + lane; i < end; i += 32) {
     const float4 q1 = rec1[i];
     if (!(q1.w >= 0.f)) continue;
@@ -317,7 +320,27 @@ __device__ __forceinline__ void accumulate_chunk(float (&acc)[SLICE], const floa
     v[6] = q1.z * q0.x; v[7] = q1.z * q0.y; v[8] = q1.z * q0.z;
     v[9] = q1.x; v[10] = q1.y; v[11] = q1.z;
     v[12] = q0.w;
-    acc_slice<S>(acc, v, q1.w, std::make_integer_sequence<int, SLICE>());
+    acc_slice<SZ, S>(acc, v, q1.w, std::make_integer_sequence<int, SZ>());
+  }
+}
+template <int NSL>
+__device__ __forceinline__ void accumulate_slice(float (&acc)[96 / NSL], int slice, const float4 *rec0, const float4 *rec1, int begin, int end, int lane) {
+  constexpr int SZ = 96 / NSL;
+  switch (slice) {
+    case 0: accumulate_chunk<SZ, 0>(acc, rec0, rec1, begin, end, lane); break;
+    case 1: accumulate_chunk<SZ, 1>(acc, rec0, rec1, begin, end, lane); break;
+    case 2: accumulate_chunk<SZ, 2>(acc, rec0, rec1, begin, end, lane); break;
+    case 3: accumulate_chunk<SZ, 3>(acc, rec0, rec1, begin, end, lane); break;
+    default:
+      if constexpr (NSL > 4) {
+        switch (slice) {
+          case 4: accumulate_chunk<SZ, 4>(acc, rec0, rec1, begin, end, lane); break;
+          case 5: accumulate_chunk<SZ, 5>(acc, rec0, rec1, begin, end, lane); break;
+          case 6: accumulate_chunk<SZ, 6>(acc, rec0, rec1, begin, end, lane); break;
+          default: accumulate_chunk<SZ, 7>(acc, rec0, rec1, begin, end, lane); break;
+        }
+      }
+      break;
   }
 }
 
@@ -368,53 +391,32 @@ struct MomArgs {
 
 template <int THREADS, int CHUNK, int MINB>
 __global__ void __launch_bounds__(THREADS, MINB) icp_moments_kernel(MomArgs a) {
-  constexpr int PARTS = THREADS / 128;
+  constexpr int NSL = THREADS / 32, SZ = 96 / NSL;
+  static_assert(NSL == 4 || NSL == 8, "one slice of the moments per warp");
   __shared__ __align__(16) float4 rec0[CHUNK], rec1[CHUNK];
-  __shared__ __align__(16) float s_sums[PARTS][96];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slice = warp & 3, part = warp >> 2;
   const int n_work = __ldg(a.n_active) * a.n_groups;
   for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
     const int pos = w / a.n_groups, g = w - pos * a.n_groups;
     const Rigid X = state_load(a.state[__ldg(&a.list[pos])].X);
     const int begin = g * a.group_pts, end = min(a.scene.n_padded, begin + a.group_pts);
-    float acc[SLICE];
+    float acc[SZ];
 #pragma unroll
-    for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
+    for (int e = 0; e < SZ; ++e) acc[e] = 0.f;
     for (int c0 = begin; c0 < end; c0 += CHUNK) {
       const int cnt = min(CHUNK, end - c0);
       correspond_chunk<THREADS>(a.scene, a.model_nv, a.grid, X, a.cos_thr, a.max_d2, c0, cnt, rec0, rec1, tid);
       __syncthreads();
-      const int per = (cnt + PARTS - 1) / PARTS;
-      const int hb = min(part * per, cnt), he = min(hb + per, cnt);
-      switch (slice) {
-        case 0: accumulate_chunk<0>(acc, rec0, rec1, hb, he, lane); break;
-        case 1: accumulate_chunk<1>(acc, rec0, rec1, hb, he, lane); break;
-        case 2: accumulate_chunk<2>(acc, rec0, rec1, hb, he, lane); break;
-        default: accumulate_chunk<3>(acc, rec0, rec1, hb, he, lane); break;
-      }
+      accumulate_slice<NSL>(acc, warp, rec0, rec1, 0, cnt, lane);
       __syncthreads();
     }
     float mine = 0.f;
 #pragma unroll
-    for (int e = 0; e < SLICE; ++e) {
+    for (int e = 0; e < SZ; ++e) {
       const float tot = warp_sum(acc[e]);
       if (lane == e) mine = tot;
     }
-    float *out = a.partial + (size_t)w * 96;
-    if (PARTS == 1) {
-      if (lane < SLICE) out[SLICE * slice + lane] = mine;
-    } else {
-      if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
-      __syncthreads();
-      for (int k = tid; k < 96; k += THREADS) {
-        float t = s_sums[0][k];
-#pragma unroll
-        for (int q = 1; q < PARTS; ++q) t += s_sums[q][k];
-        out[k] = t;
-      }
-      // (the next item writes s_sums only after the barriers of its own chunk loop)
-    }
+    if (lane < SZ) a.partial[(size_t)w * 96 + SZ * warp + lane] = mine;
   }
 }
 
@@ -732,11 +734,10 @@ struct __align__(16) FusedSlot {
 // per CTA, so a small batch still spreads over every SM instead of filling the slots of the first CTAs.
 template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
-  constexpr int PARTS = THREADS / 128;
-  constexpr int NW = THREADS / 32;
+  constexpr int NW = THREADS / 32, SZ = 96 / NW;
+  static_assert(NW == 4 || NW == 8, "one slice of the moments per warp");
   extern __shared__ __align__(16) float4 fused_smem[];
   float4 *rec0 = fused_smem, *rec1 = fused_smem + CHUNK;
-  __shared__ __align__(16) float s_sums[PARTS][96];
   __shared__ __align__(16) float s_tot[NW][96];
   __shared__ FusedSlot s_slot[NW];
   // the LM replay's per-warp scratch lives in the record buffers: they are idle while the round's solves run, and shared memory
@@ -745,7 +746,6 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
   lmr::LmrScratch *s_scr = reinterpret_cast<lmr::LmrScratch *>(fused_smem);
   __shared__ int s_ctl[2];   // [0] occupied slots this round  [1] queue exhausted
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int slice = warp & 3, part = warp >> 2;
   const int n_slots = min(NW, max(1, a.slots_max));
   // optional cycle accounting (thread 0 of every CTA): [0] phase A  [1] wait at the barrier after A  [2] phase B + barrier
   // [3] reduction + solve + broadcast  [4] passes  [5] whole CTA life time
@@ -783,9 +783,9 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
 #pragma unroll
       for (int e = 0; e < 9; ++e) X.r[e] = s_slot[g].X[e];
       X.t[0] = s_slot[g].X[9]; X.t[1] = s_slot[g].X[10]; X.t[2] = s_slot[g].X[11];
-      float acc[SLICE];
+      float acc[SZ];
 #pragma unroll
-      for (int e = 0; e < SLICE; ++e) acc[e] = 0.f;
+      for (int e = 0; e < SZ; ++e) acc[e] = 0.f;
       for (int c0 = 0; c0 < a.scene.n_padded; c0 += CHUNK) {
         const int cnt = min(CHUNK, a.scene.n_padded - c0);
         // ---- phase A: correspondences of this chunk -> shared memory ----
@@ -794,38 +794,19 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[0] += t - t_mark; t_mark = t; }
         __syncthreads();
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[1] += t - t_mark; t_mark = t; }
-        // ---- phase B: this warp's slice of the moments over its part of the chunk ----
-        const int per = (cnt + PARTS - 1) / PARTS;
-        const int hb = min(part * per, cnt), he = min(hb + per, cnt);
-        switch (slice) {
-          case 0: accumulate_chunk<0>(acc, rec0, rec1, hb, he, lane); break;
-          case 1: accumulate_chunk<1>(acc, rec0, rec1, hb, he, lane); break;
-          case 2: accumulate_chunk<2>(acc, rec0, rec1, hb, he, lane); break;
-          default: accumulate_chunk<3>(acc, rec0, rec1, hb, he, lane); break;
-        }
+        // ---- phase B: this warp's slice of the moments over the whole chunk ----
+        accumulate_slice<NW>(acc, warp, rec0, rec1, 0, cnt, lane);
         __syncthreads();
         if (PROF && tid == 0) { const long long t = clock64(); t_acc[2] += t - t_mark; t_mark = t; }
       }
-      // ---- reduce: lanes -> warp totals -> the parts of the chunk -> this slot's 93 sums ----
+      // ---- reduce: lanes -> this slot's 93 sums ----
       float mine = 0.f;
 #pragma unroll
-      for (int e = 0; e < SLICE; ++e) {
+      for (int e = 0; e < SZ; ++e) {
         const float tot = warp_sum(acc[e]);
         if (lane == e) mine = tot;
       }
-      if (PARTS == 1) {
-        if (lane < SLICE) s_tot[g][SLICE * slice + lane] = mine;
-      } else {
-        if (lane < SLICE) s_sums[part][SLICE * slice + lane] = mine;
-        __syncthreads();
-        for (int k = tid; k < 96; k += THREADS) {
-          float t = s_sums[0][k];
-#pragma unroll
-          for (int q = 1; q < PARTS; ++q) t += s_sums[q][k];
-          s_tot[g][k] = t;
-        }
-        // (the next slot writes s_sums only after the barriers of its own chunk loop)
-      }
+      if (lane < SZ) s_tot[g][SZ * warp + lane] = mine;
       if (PROF && tid == 0) { const long long t = clock64(); t_acc[3] += t - t_mark; t_mark = t; t_acc[4] += 1; }
     }
     __syncthreads();
@@ -954,16 +935,18 @@ struct LcpArgs {
   float *scores;
 };
 
-// CTA = (hypothesis, split): one thread per scene point of every `splits`-th tile; the pose algebra is done once per
-// CTA; the CTA's sum goes to partial[h][split]
+// CTA = (hypothesis, split): one thread per scene point of every `splits`-th tile; the pose algebra is done once per CTA.  Every
+// TILE's sum is reduced in a fixed order and stored on its own (partial[h][tile]); lcp_reduce_kernel then adds the tiles in order:
+// the bits of a hypothesis' score depend on the scene only, not on the batch size (which picks `splits`) or its position in it --
+// a sharded batch (strong scaling) must merge to the winners of the whole batch, score for score.
 template <int MINB>
 __global__ void __launch_bounds__(TILE, MINB) lcp_score_kernel(LcpArgs a) {
   __shared__ float s_w[TILE / 32];
   const int h = blockIdx.y;
   const Rigid T = rigid_load_colmajor(a.poses + 16 * (size_t)h);
   const Rigid Ti = rigid_inverse(T);
-  float score = 0.f;
   for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+    float score = 0.f;
     const int i = tile * TILE + threadIdx.x;
     const float4 sp = __ldg(&a.scene.pw[i]);
     const float3 p = rigid_apply(Ti, sp.x, sp.y, sp.z);   // scene point in the model frame
@@ -996,19 +979,20 @@ __global__ void __launch_bounds__(TILE, MINB) lcp_score_kernel(LcpArgs a) {
         }
       }
     }
-  }
-  score = warp_sum(score);
-  if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = score;
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    float s = 0.f;
+    score = warp_sum(score);
+    if ((threadIdx.x & 31) == 0) s_w[threadIdx.x >> 5] = score;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
 #pragma unroll
-    for (int w = 0; w < TILE / 32; ++w) s += s_w[w];
-    a.partial[(size_t)h * gridDim.x + blockIdx.x] = s;
+      for (int w = 0; w < TILE / 32; ++w) s += s_w[w];
+      a.partial[(size_t)h * a.n_tiles + tile] = s;
+    }
+    __syncthreads();
   }
 }
 
-// fixed-order sum of the tile partials (deterministic bits run to run)
+// fixed-order sum of the tile partials (deterministic bits run to run and batch to batch)
 __global__ void lcp_reduce_kernel(const float *__restrict__ partial, int n_tiles, int H, float *__restrict__ scores) {
   int h = blockIdx.x * blockDim.x + threadIdx.x;
   if (h >= H) return;
@@ -1142,7 +1126,7 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_b
   int splits = (int)((8L * ctx->sm_count + H - 1) / H);
   splits = std::max(1, std::min(splits, n_tiles));
   a.n_tiles = n_tiles;
-  float *partial = (float *)ctx->ensure_work(sizeof(float) * (size_t)std::min(H, Hb_max) * splits);
+  float *partial = (float *)ctx->ensure_work(sizeof(float) * (size_t)std::min(H, Hb_max) * n_tiles);
   if (!partial) { ctx->err = "hop_lcp_score: work buffer allocation failed"; return HOP_ENOMEM; }
   a.partial = partial;
   for (int h0 = 0; h0 < H; h0 += Hb_max) {
@@ -1154,7 +1138,7 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_b
     else if (lcp_variant == 2) lcp_score_kernel<6><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
     else if (lcp_variant == 4) lcp_score_kernel<4><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);
     else lcp_score_kernel<8><<<dim3(splits, Hb), TILE, 0, ctx->stream>>>(a);   // full occupancy: the kernel waits on gathers (measured 4 -> 8 CTAs/SM: -14 %)
-    lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, splits, Hb, d_scores + h0);
+    lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, n_tiles, Hb, d_scores + h0);
     ctx->launches += 2;
   }
   HOP_CUDA(ctx, cudaGetLastError());

@@ -60,7 +60,7 @@ __global__ void backproject_kernel(const uint16_t *__restrict__ depth_mm, int w,
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= w * h) return;
   const int u = i / w, v = i - u * w;
-  float d = __fmul_rn((float)depth_mm[i], 0.001f);
+  float d = __double2float_rn((double)(float)depth_mm[i] * 0.001);   // (float)depthShort * SR300_DEPTH_UNIT: the unit is a double literal (Utils.cpp:44)
   if ((double)d > 2.0 || (double)d < 0.1) d = 0.f;
   const bool ok = (double)d > 0.1 && (double)d < 2.0;
   float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -791,4 +791,437 @@ extern "C" int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *x
     if (nrm) { nrm[3 * i] = nv[i].x; nrm[3 * i + 1] = nv[i].y; nrm[3 * i + 2] = nv[i].z; }
   }
   return HOP_OK;
+}
+
+
+// ====================================================================================================================
+// The two PCL normal estimators of main_realdata_auto's hand branch
+//   Utils::calNormalIntegralImage(scene_rgb, -1, 0.02, 10, true)   Utils.cpp:294-329, main_realdata_auto.cpp:61
+//       pcl::IntegralImageNormalEstimation, SIMPLE_3D_GRADIENT, depth dependent smoothing, on the ORGANIZED frame
+//   Utils::calNormalMLS(object1, 0.003)                             Utils.cpp:268-292, main_realdata_auto.cpp:160
+//       pcl::MovingLeastSquares, order 2: projects every point onto its fitted surface and takes the normal there
+// Restated from PCL 1.9.1 (not installed: parity unpinned against PCL; oracle/hop_oracle_frame.c is the checker).
+// ====================================================================================================================
+namespace {
+
+// Utils::readDepthImage + convert3dOrganizedRGB: every pixel, invalid ones are (0, 0, 0) (Utils.cpp:103-110)
+__global__ void organized_kernel(const uint16_t *__restrict__ depth_mm, int w, int h, float fx, float fy, float cx, float cy,
+                                 float4 *__restrict__ pts) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const int u = i / w, v = i - u * w;
+  float d = __double2float_rn((double)(float)depth_mm[i] * 0.001);
+  if ((double)d > 2.0 || (double)d < 0.1) d = 0.f;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if ((double)d > 0.1 && (double)d < 2.0) {
+    p.x = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cx), d), fx);
+    p.y = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cy), d), fy);
+    p.z = d;
+  }
+  pts[i] = p;
+}
+
+// depth-change map: a pixel and its right / lower neighbour are marked when their depths differ by more than
+// max_depth_change_factor (|z| + 1) 2 or one of them is not finite (all writes store 0: order free)
+__global__ void depth_change_kernel(const float4 *__restrict__ pts, int w, int h, float factor, unsigned char *__restrict__ change) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const int ri = i / w, ci = i - ri * w;
+  if (ri >= h - 1 || ci >= w - 1) return;
+  const float depth = pts[i].z, depthR = pts[i + 1].z, depthD = pts[i + w].z;
+  const float thr = __fmul_rn(__fmul_rn(factor, __fadd_rn(fabsf(depth), 1.0f)), 2.0f);
+  if (fabs((double)__fsub_rn(depth, depthR)) > (double)thr || !isfinite(depth) || !isfinite(depthR)) { change[i] = 0; change[i + 1] = 0; }
+  if (fabs((double)__fsub_rn(depth, depthD)) > (double)thr || !isfinite(depth) || !isfinite(depthD)) { change[i] = 0; change[i + w] = 0; }
+}
+
+__global__ void dist_init_kernel(const unsigned char *__restrict__ change, int n, float far, float *__restrict__ dist) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) dist[i] = change[i] == 0 ? 0.0f : far;
+}
+
+// PCL's two-pass chamfer distance (weights 1 / 1.4), exactly: the passes are sequential recurrences (a cell needs its left
+// neighbour of the same row and three cells of the previous row) and the float sums of 1.0f and 1.4f round, so the order of the
+// additions is part of the result ((int)distance later picks the smoothing rectangle).  One CTA walks the skewed wavefront
+// t = 2 row + column: thread = row, one column per step, every dependency was produced at least one step (one barrier) earlier.
+// FORWARD: rows 1 .. h-1, columns 1 .. w-1 (at the last column PCL reads previous_row[w] = the first cell of the current row).
+// backward: rows h-2 .. 0, columns w-2 .. 0 (at column 0 it reads next_row[-1] = the last cell of the current row).
+template <bool FORWARD>
+__global__ void __launch_bounds__(1024, 1) chamfer_kernel(float *__restrict__ dist, int w, int h) {
+  const int r = threadIdx.x;                 // FORWARD: row 1 + r; backward: row h - 2 - r
+  const int rows = h - 1;
+  const int steps = 2 * (rows - 1) + (w - 1);
+  for (int base = 0; base < rows; base += blockDim.x) {   // (more rows than threads: bands, each band after the previous one)
+    const int rr = base + r;
+    const bool have = rr < rows;
+    const int row = FORWARD ? 1 + rr : h - 2 - rr;
+    float *cur = dist + (size_t)row * w;
+    const float *adj = FORWARD ? cur - w : cur + w;        // the previous (forward) / next (backward) row
+    const int band_rows = min((int)blockDim.x, rows - base);
+    const int band_steps = 2 * (band_rows - 1) + (w - 1);
+    for (int t = 0; t < band_steps; ++t) {
+      const int k = t - 2 * r;                              // this row's column counter at step t
+      if (have && k >= 0 && k < w - 1) {
+        if (FORWARD) {
+          const int ci = 1 + k;
+          const float upLeft = __fadd_rn(adj[ci - 1], 1.4f), up = __fadd_rn(adj[ci], 1.0f), upRight = __fadd_rn(adj[ci + 1], 1.4f);
+          const float left = __fadd_rn(cur[ci - 1], 1.0f), center = cur[ci];
+          const float mv = fminf(fminf(upLeft, up), fminf(left, upRight));
+          if (mv < center) cur[ci] = mv;
+        } else {
+          const int ci = w - 2 - k;
+          const float lowerLeft = __fadd_rn(adj[ci - 1], 1.4f), lower = __fadd_rn(adj[ci], 1.0f), lowerRight = __fadd_rn(adj[ci + 1], 1.4f);
+          const float right = __fadd_rn(cur[ci + 1], 1.0f), center = cur[ci];
+          const float mv = fminf(fminf(lowerLeft, lower), fminf(right, lowerRight));
+          if (mv < center) cur[ci] = mv;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  (void)steps;
+}
+
+// IntegralImage2D<float, 3>: first-order sums in double.  Row pass: one thread per image row, sequential prefix (PCL's so_far).
+__global__ void ii_rows_kernel(const float4 *__restrict__ pts, int w, int h, double *__restrict__ rowsum /* h x w x 3 */) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= h) return;
+  double s0 = 0, s1 = 0, s2 = 0;
+  for (int c = 0; c < w; ++c) {
+    const float4 p = pts[(size_t)r * w + c];
+    if (finite3(p.x, p.y, p.z)) { s0 += p.x; s1 += p.y; s2 += p.z; }
+    double *o = rowsum + 3 * ((size_t)r * w + c);
+    o[0] = s0; o[1] = s1; o[2] = s2;
+  }
+}
+// Column pass: I[r + 1][c + 1] = I[r][c + 1] + so_far(r, c), one thread per (column, channel)
+__global__ void ii_cols_kernel(const double *__restrict__ rowsum, int w, int h, double *__restrict__ I /* (h + 1) x (w + 1) x 3 */) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= 3 * (w + 1)) return;
+  const int c1 = t / 3, k = t - 3 * c1;   // column of the integral image
+  double acc = 0.0;
+  I[3 * (size_t)c1 + k] = 0.0;
+  for (int r = 0; r < h; ++r) {
+    if (c1 > 0) acc += rowsum[3 * ((size_t)r * w + c1 - 1) + k];
+    I[3 * ((size_t)(r + 1) * (w + 1) + c1) + k] = c1 > 0 ? acc : 0.0;
+  }
+}
+
+__device__ __forceinline__ void ii_sum(const double *__restrict__ I, int W1, int sx, int sy, int ww, int hh, double *out) {
+  const size_t ul = (size_t)sy * W1 + sx, ur = ul + ww, ll = (size_t)(sy + hh) * W1 + sx, lr = ll + ww;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[k] = I[3 * lr + k] + I[3 * ul + k] - I[3 * ur + k] - I[3 * ll + k];
+}
+
+// computeFeatureFull + computePointNormal (SIMPLE_3D_GRADIENT), border policy IGNORE, viewpoint (0, 0, 0)
+__global__ void ii_normal_kernel(const float4 *__restrict__ pts, const float *__restrict__ dist, const double *__restrict__ I, int w, int h,
+                                 float smoothing_size, float4 *__restrict__ nrm) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= w * h) return;
+  const float nan = __int_as_float(0x7fc00000);
+  float4 out = make_float4(nan, nan, nan, 0.f);
+  const int ri = i / w, ci = i - ri * w, border = (int)smoothing_size;
+  const float4 p = pts[i];
+  if (ri >= border && ri < h - border && ci >= border && ci < w - border && isfinite(p.z)) {
+    const float smoothing = fminf(dist[i], __fadd_rn(smoothing_size, __fdiv_rn(p.z, 10.0f)));
+    if (smoothing > 2.0f) {
+      const int rw = (int)smoothing, rh = rw, rw2 = rw / 2, rh2 = rh / 2, W1 = w + 1;
+      double a1[3], a2[3], gx[3], gy[3];
+      ii_sum(I, W1, ci + rw2, ri - rh2, 1, rh, a1); ii_sum(I, W1, ci - rw2, ri - rh2, 1, rh, a2);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gx[k] = a1[k] - a2[k];
+      ii_sum(I, W1, ci - rw2, ri + rh2, rw, 1, a1); ii_sum(I, W1, ci - rw2, ri - rh2, rw, 1, a2);
+#pragma unroll
+      for (int k = 0; k < 3; ++k) gy[k] = a1[k] - a2[k];
+      const double n0 = __dmul_rn(gy[1], gx[2]) - __dmul_rn(gy[2], gx[1]), n1 = __dmul_rn(gy[2], gx[0]) - __dmul_rn(gy[0], gx[2]),
+                   n2 = __dmul_rn(gy[0], gx[1]) - __dmul_rn(gy[1], gx[0]);
+      const double len = __dadd_rn(__dadd_rn(__dmul_rn(n0, n0), __dmul_rn(n1, n1)), __dmul_rn(n2, n2));
+      if (len != 0.0) {
+        const double s = sqrt(len);
+        float nx = (float)(n0 / s), ny = (float)(n1 / s), nz = (float)(n2 / s);
+        const float vx = __fsub_rn(0.f, p.x), vy = __fsub_rn(0.f, p.y), vz = __fsub_rn(0.f, p.z);
+        const float cos_theta = __fadd_rn(__fadd_rn(__fmul_rn(vx, nx), __fmul_rn(vy, ny)), __fmul_rn(vz, nz));
+        if (cos_theta < 0) { nx = -nx; ny = -ny; nz = -nz; }
+        out = make_float4(nx, ny, nz, 1.f);
+      }
+    }
+  }
+  nrm[i] = out;
+}
+
+__global__ void valid_z_flag_kernel(const float4 *__restrict__ pts, int n, unsigned char *__restrict__ flag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { const float z = pts[i].z; flag[i] = ((double)z >= 0.1 && (double)z <= 2.0) ? 1 : 0; }   // PassThrough z in [0.1, 2.0]
+}
+
+// ---- MovingLeastSquares, order 2 -----------------------------------------------------------------------------------
+__device__ void eigen33_smallest(const double (&A)[3][3], double (&ev)[3]) {   // pcl::eigen33 (common/impl/eigen.hpp)
+  double scale = 0.0;
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) scale = fmax(scale, fabs(A[i][j]));
+  if (scale <= DBL_MIN) scale = 1.0;
+  double S[3][3];
+#pragma unroll
+  for (int i = 0; i < 3; ++i)
+#pragma unroll
+    for (int j = 0; j < 3; ++j) S[i][j] = A[i][j] / scale;
+  double roots[3];
+  const double c0 = S[0][0] * S[1][1] * S[2][2] + 2.0 * S[0][1] * S[0][2] * S[1][2] - S[0][0] * S[1][2] * S[1][2] - S[1][1] * S[0][2] * S[0][2] -
+                    S[2][2] * S[0][1] * S[0][1];
+  const double c1 = S[0][0] * S[1][1] - S[0][1] * S[0][1] + S[0][0] * S[2][2] - S[0][2] * S[0][2] + S[1][1] * S[2][2] - S[1][2] * S[1][2];
+  const double c2 = S[0][0] + S[1][1] + S[2][2];
+  bool quadratic = fabs(c0) < DBL_EPSILON;
+  if (!quadratic) {
+    const double s_inv3 = 1.0 / 3.0, s_sqrt3 = sqrt(3.0);
+    const double c2_over_3 = c2 * s_inv3;
+    double a_over_3 = (c1 - c2 * c2_over_3) * s_inv3;
+    if (a_over_3 > 0.0) a_over_3 = 0.0;
+    const double half_b = 0.5 * (c0 + c2_over_3 * (2.0 * c2_over_3 * c2_over_3 - c1));
+    double q = half_b * half_b + a_over_3 * a_over_3 * a_over_3;
+    if (q > 0.0) q = 0.0;
+    const double rho = sqrt(-a_over_3);
+    const double theta = atan2(sqrt(-q), half_b) * s_inv3;
+    const double ct = cos(theta), st = sin(theta);
+    roots[0] = c2_over_3 + 2.0 * rho * ct;
+    roots[1] = c2_over_3 - rho * (ct + s_sqrt3 * st);
+    roots[2] = c2_over_3 - rho * (ct - s_sqrt3 * st);
+    if (roots[0] >= roots[1]) { const double t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    if (roots[1] >= roots[2]) {
+      double t = roots[1]; roots[1] = roots[2]; roots[2] = t;
+      if (roots[0] >= roots[1]) { t = roots[0]; roots[0] = roots[1]; roots[1] = t; }
+    }
+    if (roots[0] <= 0.0) quadratic = true;
+  }
+  if (quadratic) {
+    roots[0] = 0.0;
+    double d = c2 * c2 - 4.0 * c1;
+    if (d < 0.0) d = 0.0;
+    const double sd = sqrt(d);
+    roots[2] = 0.5 * (c2 + sd); roots[1] = 0.5 * (c2 - sd);
+  }
+#pragma unroll
+  for (int i = 0; i < 3; ++i) S[i][i] -= roots[0];
+  const double v1[3] = {S[0][1] * S[1][2] - S[0][2] * S[1][1], S[0][2] * S[1][0] - S[0][0] * S[1][2], S[0][0] * S[1][1] - S[0][1] * S[1][0]};
+  const double v2[3] = {S[0][1] * S[2][2] - S[0][2] * S[2][1], S[0][2] * S[2][0] - S[0][0] * S[2][2], S[0][0] * S[2][1] - S[0][1] * S[2][0]};
+  const double v3[3] = {S[1][1] * S[2][2] - S[1][2] * S[2][1], S[1][2] * S[2][0] - S[1][0] * S[2][2], S[1][0] * S[2][1] - S[1][1] * S[2][0]};
+  const double l1 = v1[0] * v1[0] + v1[1] * v1[1] + v1[2] * v1[2], l2 = v2[0] * v2[0] + v2[1] * v2[1] + v2[2] * v2[2],
+               l3 = v3[0] * v3[0] + v3[1] * v3[1] + v3[2] * v3[2];
+  const double *v = v3; double l = l3;
+  if (l1 >= l2 && l1 >= l3) { v = v1; l = l1; } else if (l2 >= l1 && l2 >= l3) { v = v2; l = l2; }
+  const double s = sqrt(l);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) ev[k] = v[k] / s;
+}
+
+// visits every point within the radius of p (float distance test, FLANN's operation order), neighbours in cell order
+template <typename F>
+__device__ __forceinline__ void for_neighbours(const float4 p, const float4 *__restrict__ sorted, const int *__restrict__ cell_start,
+                                               const int *__restrict__ cell_end, const CellGeom &g, float r2, F f) {
+  int ca, cb, cc;
+  cell_of(g, p, ca, cb, cc);
+  for (int dc = -1; dc <= 1; ++dc)
+    for (int db = -1; db <= 1; ++db)
+      for (int da = -1; da <= 1; ++da) {
+        const int a = ca + da, b = cb + db, c = cc + dc;
+        if ((unsigned)a >= (unsigned)g.dim[0] || (unsigned)b >= (unsigned)g.dim[1] || (unsigned)c >= (unsigned)g.dim[2]) continue;
+        const int cell = (c * g.dim[1] + b) * g.dim[0] + a;
+        for (int j = cell_start[cell]; j < cell_end[cell]; ++j) {
+          const float4 q = sorted[j];
+          const float dx = __fsub_rn(q.x, p.x), dy = __fsub_rn(q.y, p.y), dz = __fsub_rn(q.z, p.z);
+          if (__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)) <= r2) f(q);
+        }
+      }
+}
+
+__global__ void mls_kernel(const float4 *__restrict__ pts, int n, const float4 *__restrict__ sorted, const int *__restrict__ cell_start,
+                           const int *__restrict__ cell_end, CellGeom g, float radius, float4 *__restrict__ out_p, float4 *__restrict__ out_n,
+                           unsigned char *__restrict__ valid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = pts[i];
+  const float r2f = __fmul_rn(radius, radius);
+  const double r2 = (double)radius * (double)radius;
+  const float nan = __int_as_float(0x7fc00000);
+  // computeMeanAndCovarianceMatrix: one pass, double accumulators of x, y, z and the six products
+  double acc[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int m = 0;
+  for_neighbours(p, sorted, cell_start, cell_end, g, r2f, [&](const float4 q) {
+    acc[0] += (double)q.x * q.x; acc[1] += (double)q.x * q.y; acc[2] += (double)q.x * q.z;
+    acc[3] += (double)q.y * q.y; acc[4] += (double)q.y * q.z; acc[5] += (double)q.z * q.z;
+    acc[6] += q.x; acc[7] += q.y; acc[8] += q.z;
+    ++m;
+  });
+  valid[i] = m >= 3 ? 1 : 0;
+  out_p[i] = p;
+  out_n[i] = make_float4(nan, nan, nan, 0.f);
+  if (m < 3) return;
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] /= (double)m;
+  double C[3][3];
+  C[0][0] = acc[0] - acc[6] * acc[6]; C[0][1] = acc[1] - acc[6] * acc[7]; C[0][2] = acc[2] - acc[6] * acc[8];
+  C[1][1] = acc[3] - acc[7] * acc[7]; C[1][2] = acc[4] - acc[7] * acc[8]; C[2][2] = acc[5] - acc[8] * acc[8];
+  C[1][0] = C[0][1]; C[2][0] = C[0][2]; C[2][1] = C[1][2];
+  double pn[3];
+  eigen33_smallest(C, pn);
+  if (!isfinite(pn[0]) || !isfinite(pn[1]) || !isfinite(pn[2])) return;
+  const double d4 = -(pn[0] * acc[6] + pn[1] * acc[7] + pn[2] * acc[8]);
+  const double distance = (double)p.x * pn[0] + (double)p.y * pn[1] + (double)p.z * pn[2] + d4;
+  const double mean[3] = {(double)p.x - distance * pn[0], (double)p.y - distance * pn[1], (double)p.z - distance * pn[2]};
+  double va[3], ua[3];
+  if (!(fabs(pn[0]) <= 1e-12 * fabs(pn[2])) || !(fabs(pn[1]) <= 1e-12 * fabs(pn[2]))) {   // Eigen unitOrthogonal()
+    const double inv = 1.0 / sqrt(pn[0] * pn[0] + pn[1] * pn[1]);
+    va[0] = -pn[1] * inv; va[1] = pn[0] * inv; va[2] = 0.0;
+  } else {
+    const double inv = 1.0 / sqrt(pn[1] * pn[1] + pn[2] * pn[2]);
+    va[0] = 0.0; va[1] = -pn[2] * inv; va[2] = pn[1] * inv;
+  }
+  ua[0] = pn[1] * va[2] - pn[2] * va[1]; ua[1] = pn[2] * va[0] - pn[0] * va[2]; ua[2] = pn[0] * va[1] - pn[1] * va[0];
+  double c6[6] = {0, 0, 0, 0, 0, 0};
+  bool have_poly = false;
+  if (m >= 6) {
+    double A[21], rhs[6];   // upper triangle of P W P^T, row-major; P W f
+#pragma unroll
+    for (int k = 0; k < 21; ++k) A[k] = 0.0;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) rhs[k] = 0.0;
+    for_neighbours(p, sorted, cell_start, cell_end, g, r2f, [&](const float4 q) {
+      const double de[3] = {(double)q.x - mean[0], (double)q.y - mean[1], (double)q.z - mean[2]};
+      const double wgt = exp(-(de[0] * de[0] + de[1] * de[1] + de[2] * de[2]) / r2);
+      const double u = de[0] * ua[0] + de[1] * ua[1] + de[2] * ua[2], v = de[0] * va[0] + de[1] * va[1] + de[2] * va[2];
+      const double f = de[0] * pn[0] + de[1] * pn[1] + de[2] * pn[2];
+      const double P[6] = {1.0, v, v * v, u, u * v, u * u};   // (ui, vi): (0,0) (0,1) (0,2) (1,0) (1,1) (2,0)
+      int e = 0;
+#pragma unroll
+      for (int a = 0; a < 6; ++a) {
+        rhs[a] += P[a] * wgt * f;
+#pragma unroll
+        for (int b = a; b < 6; ++b) A[e++] += P[a] * wgt * P[b];
+      }
+    });
+    // LLT solve
+    double L[6][6];
+    bool ok = true;
+    {
+      auto at = [&](int a, int b) { const int lo = a < b ? a : b, hi = a < b ? b : a; return A[lo * 6 - lo * (lo - 1) / 2 + (hi - lo)]; };
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {
+        double d = at(j, j);
+#pragma unroll
+        for (int k = 0; k < j; ++k) d -= L[j][k] * L[j][k];
+        if (!(d > 0.0)) { ok = false; d = 1.0; }
+        L[j][j] = sqrt(d);
+#pragma unroll
+        for (int r = j + 1; r < 6; ++r) {
+          double s = at(r, j);
+#pragma unroll
+          for (int k = 0; k < j; ++k) s -= L[r][k] * L[j][k];
+          L[r][j] = s / L[j][j];
+        }
+      }
+    }
+    if (ok) {
+#pragma unroll
+      for (int r = 0; r < 6; ++r) { double s = rhs[r]; for (int k = 0; k < r; ++k) s -= L[r][k] * rhs[k]; rhs[r] = s / L[r][r]; }
+#pragma unroll
+      for (int r = 5; r >= 0; --r) { double s = rhs[r]; for (int k = r + 1; k < 6; ++k) s -= L[k][r] * rhs[k]; rhs[r] = s / L[r][r]; }
+#pragma unroll
+      for (int k = 0; k < 6; ++k) c6[k] = rhs[k];
+      have_poly = isfinite(c6[0]);
+    }
+  }
+  double pt[3], nv[3];
+  if (have_poly) {   // projectPointSimpleToPolynomialSurface at (u, v) = (0, 0)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { pt[k] = mean[k] + c6[0] * pn[k]; nv[k] = pn[k] - c6[3] * ua[k] - c6[1] * va[k]; }
+    const double l = sqrt(nv[0] * nv[0] + nv[1] * nv[1] + nv[2] * nv[2]);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) nv[k] /= l;
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) { pt[k] = mean[k]; nv[k] = pn[k]; }
+  }
+  out_p[i] = make_float4((float)pt[0], (float)pt[1], (float)pt[2], p.w);
+  out_n[i] = make_float4((float)nv[0], (float)nv[1], (float)nv[2], 1.f);
+}
+
+}  // namespace
+
+// Utils::readDepthImage + convert3dOrganizedRGB + calNormalIntegralImage(-1, 0.02, 10, true) + PassThrough(z, 0.1, 2.0)
+// (main_realdata_auto.cpp:54-70): the frame's valid pixels in raster order with their integral-image normals (NaN where PCL
+// writes none) -- the cloud `scene_organized` / `scene_rgb` of the reference before its voxel grid.
+extern "C" int hop_frame_organized(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *fp, float max_depth_change_factor,
+                                   float normal_smoothing_size, hop_cloud **out) {
+  HOP_ENTER(ctx);
+  if (!ctx) return HOP_EINVAL;
+  if (!depth_mm || width < 3 || height < 3 || !fp || !out || !(normal_smoothing_size >= 1.f)) { ctx->err = "hop_frame_organized: bad arguments"; return HOP_EINVAL; }
+  ProfScope ps(ctx, HOP_PROF_FRAME);
+  cudaStream_t st = ctx->stream;
+  const int npx = width * height;
+  FBuf d_depth(st), P(st), N(st), ch(st), dist(st), rows(st), I(st), fl(st), CP(st), CN(st);
+  FR_CUDA(d_depth.alloc(sizeof(uint16_t) * (size_t)npx)); FR_CUDA(P.alloc(sizeof(float4) * (size_t)npx)); FR_CUDA(N.alloc(sizeof(float4) * (size_t)npx));
+  FR_CUDA(ch.alloc((size_t)npx)); FR_CUDA(dist.alloc(sizeof(float) * (size_t)npx)); FR_CUDA(fl.alloc((size_t)npx));
+  FR_CUDA(rows.alloc(sizeof(double) * 3 * (size_t)npx)); FR_CUDA(I.alloc(sizeof(double) * 3 * (size_t)(width + 1) * (height + 1)));
+  FR_CUDA(CP.alloc(sizeof(float4) * (size_t)npx)); FR_CUDA(CN.alloc(sizeof(float4) * (size_t)npx));
+  FR_CUDA(cudaMemcpyAsync(d_depth.p, depth_mm, sizeof(uint16_t) * (size_t)npx, cudaMemcpyHostToDevice, st));
+  organized_kernel<<<blocks(npx), 256, 0, st>>>(d_depth.as<uint16_t>(), width, height, fp->fx, fp->fy, fp->cx, fp->cy, P.as<float4>());
+  FR_CUDA(cudaMemsetAsync(ch.p, 255, (size_t)npx, st));
+  depth_change_kernel<<<blocks(npx), 256, 0, st>>>(P.as<float4>(), width, height, max_depth_change_factor, ch.as<unsigned char>());
+  dist_init_kernel<<<blocks(npx), 256, 0, st>>>(ch.as<unsigned char>(), npx, (float)(width + height), dist.as<float>());
+  const int cham_threads = std::min(1024, ((height - 1) + 31) / 32 * 32);
+  chamfer_kernel<true><<<1, cham_threads, 0, st>>>(dist.as<float>(), width, height);
+  chamfer_kernel<false><<<1, cham_threads, 0, st>>>(dist.as<float>(), width, height);
+  ii_rows_kernel<<<(height + 63) / 64, 64, 0, st>>>(P.as<float4>(), width, height, rows.as<double>());
+  ii_cols_kernel<<<(3 * (width + 1) + 63) / 64, 64, 0, st>>>(rows.as<double>(), width, height, I.as<double>());
+  ii_normal_kernel<<<blocks(npx), 256, 0, st>>>(P.as<float4>(), dist.as<float>(), I.as<double>(), width, height, normal_smoothing_size, N.as<float4>());
+  valid_z_flag_kernel<<<blocks(npx), 256, 0, st>>>(P.as<float4>(), npx, fl.as<unsigned char>());
+  ctx->launches += 9;
+  int n = 0, rc;
+  if ((rc = compact2(ctx, P.as<float4>(), N.as<float4>(), fl.as<unsigned char>(), npx, CP.as<float4>(), CN.as<float4>(), &n)) != HOP_OK) return rc;
+  return make_cloud(ctx, CP.as<float4>(), CN.as<float4>(), n, out);
+}
+
+// Utils::calNormalMLS (Utils.cpp:268-292): pcl::MovingLeastSquares (order 2, radius search, normals): the points with at least
+// three neighbours, projected onto their fitted surfaces, with the surface normals there (not oriented); the weight channel
+// (confidence) travels with the points.  Points keep their input order.
+extern "C" int hop_cloud_mls(hop_ctx *ctx, const hop_cloud *in, float radius, hop_cloud **out) {
+  HOP_ENTER(ctx);
+  if (!ctx) return HOP_EINVAL;
+  if (!in || !out || *out == in || !(radius > 0.f)) { ctx->err = "hop_cloud_mls: bad arguments"; return HOP_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  const int n = in->n;
+  FBuf OP(st), ON(st), fl(st), CP(st), CN(st);
+  int kept = 0, rc;
+  if (n > 0) {
+    ProfScope ps(ctx, HOP_PROF_FRAME);
+    float mn[3], mx[3];
+    if ((rc = cloud_bounds(ctx, in->d_pw, n, mn, mx)) != HOP_OK) return rc;
+    CellGeom g;
+    g.inv = 1.f / radius;
+    double ncell = 1;
+    for (int k = 0; k < 3; ++k) {
+      g.mn[k] = (int)std::floor(mn[k] * g.inv);
+      g.dim[k] = (int)std::floor(mx[k] * g.inv) - g.mn[k] + 1;
+      ncell *= g.dim[k];
+    }
+    if (!(ncell < 2.5e8)) { ctx->err = "hop_cloud_mls: radius too small for the cloud's extent"; return HOP_EINVAL; }
+    const int nce = (int)ncell;
+    FBuf k0(st), k1(st), i0(st), i1(st), cs(st), ce(st), sorted(st), tmp(st);
+    FR_CUDA(k0.alloc(sizeof(unsigned int) * (size_t)n)); FR_CUDA(k1.alloc(sizeof(unsigned int) * (size_t)n));
+    FR_CUDA(i0.alloc(sizeof(int) * (size_t)n)); FR_CUDA(i1.alloc(sizeof(int) * (size_t)n));
+    FR_CUDA(cs.alloc(sizeof(int) * (size_t)nce)); FR_CUDA(ce.alloc(sizeof(int) * (size_t)nce)); FR_CUDA(sorted.alloc(sizeof(float4) * (size_t)n));
+    FR_CUDA(OP.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(ON.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(fl.alloc((size_t)n));
+    FR_CUDA(CP.alloc(sizeof(float4) * (size_t)n)); FR_CUDA(CN.alloc(sizeof(float4) * (size_t)n));
+    FR_CUDA(cudaMemsetAsync(cs.p, 0, sizeof(int) * (size_t)nce, st)); FR_CUDA(cudaMemsetAsync(ce.p, 0, sizeof(int) * (size_t)nce, st));
+    cell_key_kernel<<<blocks(n), 256, 0, st>>>(in->d_pw, n, g, k0.as<unsigned int>(), i0.as<int>());
+    size_t sort_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, k0.as<unsigned int>(), k1.as<unsigned int>(), i0.as<int>(), i1.as<int>(), n, 0, 32, st);
+    FR_CUDA(tmp.alloc(sort_bytes));
+    cub::DeviceRadixSort::SortPairs(tmp.p, sort_bytes, k0.as<unsigned int>(), k1.as<unsigned int>(), i0.as<int>(), i1.as<int>(), n, 0, 32, st);
+    cell_range_kernel<<<blocks(n), 256, 0, st>>>(k1.as<unsigned int>(), i1.as<int>(), in->d_pw, n, cs.as<int>(), ce.as<int>(), sorted.as<float4>());
+    mls_kernel<<<(n + 63) / 64, 64, 0, st>>>(in->d_pw, n, sorted.as<float4>(), cs.as<int>(), ce.as<int>(), g, radius, OP.as<float4>(), ON.as<float4>(), fl.as<unsigned char>());
+    ctx->launches += 4;
+    if ((rc = compact2(ctx, OP.as<float4>(), ON.as<float4>(), fl.as<unsigned char>(), n, CP.as<float4>(), CN.as<float4>(), &kept)) != HOP_OK) return rc;
+  }
+  return make_cloud(ctx, CP.as<float4>(), CN.as<float4>(), kept, out);
 }

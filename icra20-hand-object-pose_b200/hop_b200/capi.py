@@ -194,6 +194,8 @@ def load_library():
                                           _vp, _vp, _vp, _vp, _vp]
     L.hop_refine_score_select_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), C.POINTER(LcpParams), C.c_int, C.c_int,
                                               C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
+    L.hop_frame_organized.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(FrameParams), C.c_float, C.c_float, C.POINTER(_vp)]
+    L.hop_cloud_mls.argtypes = [_vp, _vp, C.c_float, C.POINTER(_vp)]
     L.hop_comm_unique_id.argtypes = [_vp]
     L.hop_comm_init.argtypes = [_vp, _vp, C.c_int, C.c_int]
     L.hop_comm_destroy.argtypes = [_vp]
@@ -388,6 +390,10 @@ class Cloud:
 
     def radius_outlier_removal(self, radius, min_neighbors):
         return self._new(self.ctx.L.hop_cloud_radius_outlier_removal, C.c_float(radius), int(min_neighbors))
+
+    def mls(self, radius):
+        """Utils::calNormalMLS: the points with >= 3 neighbours projected onto their MLS surfaces, with the surface normals"""
+        return self._new(self.ctx.L.hop_cloud_mls, C.c_float(radius))
 
     def statistical_outlier_removal(self, mean_k, stddev_mul):
         return self._new(self.ctx.L.hop_cloud_statistical_outlier_removal, int(mean_k), C.c_float(stddev_mul))

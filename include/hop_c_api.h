@@ -347,6 +347,18 @@ typedef struct hop_hand_removal_params {
 } hop_hand_removal_params;
 int hop_remove_hand_points(hop_ctx *ctx, const hop_cloud *scene, const hop_cloud *const *links, const int32_t *link_kind, int n_links,
                            const hop_hand_removal_params *params, hop_cloud **out);
+/* The two PCL normal estimators around the hand branch of main_realdata_auto (restated from PCL 1.9.1):
+ *   hop_frame_organized  Utils::readDepthImage + convert3dOrganizedRGB + Utils::calNormalIntegralImage(cloud, -1, 0.02, 10, true) +
+ *                        PassThrough(z, 0.1, 2.0)  (main_realdata_auto.cpp:54-70; Utils.cpp:294-329): the frame's valid pixels in raster
+ *                        order with their integral-image normals (pcl::IntegralImageNormalEstimation, SIMPLE_3D_GRADIENT, depth dependent
+ *                        smoothing, viewpoint at the origin; NaN where PCL writes none) -- the reference's scene_organized.  Only the
+ *                        intrinsics of `params` are read.
+ *   hop_cloud_mls        Utils::calNormalMLS(cloud, radius)  (main_realdata_auto.cpp:160; Utils.cpp:268-292): pcl::MovingLeastSquares of
+ *                        order 2 -- the points with at least three neighbours within the radius, PROJECTED onto their fitted surfaces,
+ *                        with the surface normals there (not oriented, like PCL); input order, the weight channel travels along. */
+int hop_frame_organized(hop_ctx *ctx, const uint16_t *depth_mm, int width, int height, const hop_frame_params *params,
+                        float max_depth_change_factor, float normal_smoothing_size, hop_cloud **out);
+int hop_cloud_mls(hop_ctx *ctx, const hop_cloud *in, float radius, hop_cloud **out);
 /* copies a device cloud back (tests, debugging output such as scene_normals.ply); any pointer may be NULL */
 int hop_cloud_download(hop_ctx *ctx, const hop_cloud *cloud, float *xyz, float *nrm, float *prob);
 

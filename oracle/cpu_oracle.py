@@ -289,6 +289,45 @@ def refine_by_icp_p2p(s_xyz, m_xyz, poses, max_iter=100, dist=0.01, abs_mse_eps=
     return colmajor_to_poses(flat), iters, conv
 
 
+def integral_image_normals(xyz_organized, max_depth_change_factor=0.02, smoothing=10.0):
+    """Utils::calNormalIntegralImage(cloud, -1, 0.02, 10, true): xyz_organized (h, w, 3) -> normals (h, w, 3), NaN where PCL writes none"""
+    a = np.ascontiguousarray(xyz_organized, np.float32)
+    h, w = a.shape[:2]
+    out = np.empty((h, w, 3), np.float32)
+    L = lib()
+    L.hop_oracle_integral_image_normals.restype = None
+    L.hop_oracle_integral_image_normals.argtypes = [_f32p, C.c_int, C.c_int, C.c_float, C.c_float, _f32p]
+    L.hop_oracle_integral_image_normals(a.reshape(-1), w, h, max_depth_change_factor, smoothing, out.reshape(-1))
+    return out
+
+
+def organized_cloud(depth_mm, K):
+    """Utils::readDepthImage + convert3dOrganizedRGB (Utils.cpp:36-55, 78-115): (h, w, 3) float32, invalid pixels (0, 0, 0)"""
+    d = (depth_mm.astype(np.float32).astype(np.float64) * 0.001).astype(np.float32)
+    d = np.where((d.astype(np.float64) > 2.0) | (d.astype(np.float64) < 0.1), np.float32(0), d)
+    ok = (d.astype(np.float64) > 0.1) & (d.astype(np.float64) < 2.0)
+    h, w = d.shape
+    v, u = np.meshgrid(np.arange(w, dtype=np.float32), np.arange(h, dtype=np.float32))
+    fx, fy, cx, cy = [np.float32(x) for x in K]
+    x = ((v - cx) * d) / fx
+    y = ((u - cy) * d) / fy
+    out = np.stack([x, y, d], -1).astype(np.float32)
+    out[~ok] = 0
+    return out
+
+
+def mls(xyz, radius):
+    """Utils::calNormalMLS: returns (projected xyz, normals, valid mask) for every input point"""
+    a = _c(xyz)
+    n = len(a)
+    po, no, va = np.empty((n, 3), np.float32), np.empty((n, 3), np.float32), np.zeros(n, np.int32)
+    L = lib()
+    L.hop_oracle_mls.restype = None
+    L.hop_oracle_mls.argtypes = [_f32p, C.c_int, C.c_float, _f32p, _f32p, _i32p]
+    L.hop_oracle_mls(a.reshape(-1), n, radius, po.reshape(-1), no.reshape(-1), va)
+    return po, no, va.astype(bool)
+
+
 def select_best(s_xyz, s_nrm, m_xyz, m_nrm, poses, dist=0.001, angle=10.0, weights=None, nthreads=0):
     s_xyz, s_nrm, m_xyz, m_nrm = _c(s_xyz), _c(s_nrm), _c(m_xyz), _c(m_nrm)
     flat = poses_to_colmajor(poses)

@@ -74,10 +74,9 @@ def test_icp_lcp_full_size_sample_and_properties(ctx, name, H, n_check):
     got_r, it_r, cv_r = ctx.icp_refine(scene, model, hyp[::-1].copy(), p)
     assert np.array_equal(got_r[::-1], got) and np.array_equal(it_r[::-1], it) and np.array_equal(cv_r[::-1], cv)
     got_s, it_s, cv_s = ctx.icp_refine(scene, model, hyp[idx], p)
-    same = it_s == it[idx]                               # (the two CTA shapes sum the moments in a different order; the replayed
-    assert same.mean() >= 0.9 and np.mean(cv_s == cv[idx]) >= 0.95   #  LM's accept / stop tests are discrete: a last-bit change can flip one)
-    dt, dr = synth.pose_error(got_s[same], got[idx][same])
-    assert np.percentile(dt, 90) < 2e-5 and np.percentile(dr, 90) < 0.05
+    # (a lane adds the records lane, lane + 32, ... of the whole scene in order whatever the CTA width: the moments, hence every
+    #  decision of the replayed LM, are bit-identical for a sub-batch -- what lets a sharded batch merge to the single-GPU winners)
+    assert np.array_equal(it_s, it[idx]) and np.array_equal(cv_s, cv[idx]) and np.array_equal(got_s, got[idx])
     # fixed point: refine the refined poses once more
     conv = cv.astype(bool) & (it < wl["max_iter"])
     again, it2, cv2 = ctx.icp_refine(scene, model, got, p)
@@ -95,6 +94,7 @@ def test_icp_lcp_full_size_sample_and_properties(ctx, name, H, n_check):
     assert np.all(np.abs(sc[idx[:24]] - ref_sc) <= 3e-4 * np.maximum(np.abs(ref_sc), 1.0)), np.abs(sc[idx[:24]] - ref_sc).max()
     sc_r = ctx.lcp_score(scene, model, got[::-1].copy())
     assert np.array_equal(sc_r[::-1], sc)
+    assert np.array_equal(ctx.lcp_score(scene, model, got[idx]), sc[idx])   # ... and under a change of the batch size
     scene_w1 = ctx.upload_cloud(s, sn, conf)
     scene_w2 = ctx.upload_cloud(s, sn, (2.0 * conf).astype(np.float32))
     w1 = ctx.lcp_score(scene_w1, model, got[idx], use_weights=True)
