@@ -201,16 +201,14 @@ def stage_ms(ctx, args):
     res["k1_hand_states_4096"] = {"e2e_ms": dt, "kernel_ms": prof.get("hand_overlap")}
     m, mn = synth.make_model("ellipse", 10000, seed=1)
     s, sn, conf, gt = synth.make_scene("ellipse", 2000, seed=2)
-    sub = slice(None, None, max(1, len(m) // 400))
-    keys = capi.ppf_table(m[sub], mn[sub]) if hasattr(capi, "ppf_table") else None
-    if keys is None:
-        sys.path.insert(0, os.path.join(ROOT, "tools"))
-        import bench_stages
-        keys = bench_stages.ppf_keys(m, mn, stride=max(1, len(m) // 400))
+    sub = slice(None, None, max(1, len(m) // 400))     # the 5 mm "ppf_density" model of computePPF.cpp: ~400 points
+    t0 = time.perf_counter()
+    keys = ctx.ppf_table(m[sub], mn[sub])
+    t_table = (time.perf_counter() - t0) * 1e3
     plans = {}
 
     def plan():
-        plans["p"] = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=100))
+        plans["p"] = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=100), ctx=ctx)
 
     t0 = time.perf_counter()
     for _ in range(5):
@@ -222,7 +220,7 @@ def stage_ms(ctx, args):
         out["r"] = ctx.super4pcs_run(plans["p"], capacity=400000)
 
     dt, prof = timed(run)
-    res["super4pcs_registration"] = {"host_plan_ms": t_plan, "device_e2e_ms": dt, "k2a_pairs_ms": prof.get("s4pcs_pairs"), "k2b_join_ms": prof.get("s4pcs_join"),
+    res["super4pcs_registration"] = {"plan_ms": t_plan, "ppf_table_build_ms_once_per_model": t_table, "ppf_keys": int(len(keys)), "device_e2e_ms": dt, "k2a_pairs_ms": prof.get("s4pcs_pairs"), "k2b_join_ms": prof.get("s4pcs_join"),
                                      "k3_verify_ms": prof.get("verify_lcp"), "hypotheses_emitted": int(len(out["r"][1])), "sizes": "2 k scene x 10 k model, 100 samples, 30 trials planned"}
     if not args.no_cpu_baseline:
         try:

@@ -422,7 +422,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_moments_kernel(MomArgs a) {
 
 // ---- mode 1: Utils::runICP(segment, model, T, max_corres_dist) (Utils.cpp:135-164) = PCL's default point-to-point ICP with
 // reciprocal correspondences and TransformationEstimationSVD (pcl::umeyama without scaling) ------------------------------------
-constexpr int KAB = 17;   // sum p (3), sum m (3), sum p m^T (9, row = p), sum d^2, count
+constexpr int KAB = 18;   // sum p (3), sum m (3), sum p m^T (9, row = p), sum d^2 as a double (2 words), count
 
 // CorrespondenceEstimation::determineReciprocalCorrespondences: scene point i -> nearest model point j (d^2 <= max^2) -> the
 // nearest SCENE point of j must be i again (and within max).  The scene does not move either: the reverse query is made with
@@ -464,9 +464,10 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kabsch_sums_kernel(MomArgs 
     const Rigid X = state_load(a.state[__ldg(&a.list[pos])].X);
     const Rigid Xi = rigid_inverse(X);
     const int begin = g * a.group_pts, end = min(a.scene.n_padded, begin + a.group_pts);
-    float acc[KAB];
-#pragma unroll
-    for (int e = 0; e < KAB; ++e) acc[e] = 0.f;
+    float acc[16];
+    double acc_d2 = 0.0;   // PCL sums the squared distances of the correspondences into a double (DefaultConvergenceCriteria::calculateMSE)
+#pragma unroll             // and compares successive means against 1e-12: a float sum would decide the stop by its own rounding
+    for (int e = 0; e < 16; ++e) acc[e] = 0.f;
     for (int c0 = begin; c0 < end; c0 += CHUNK) {
       const int cnt = min(CHUNK, end - c0);
       correspond_chunk_reciprocal<THREADS>(a.scene, a.grid, a.sgrid, X, Xi, a.max_d2, c0, cnt, rec0, rec1, tid);
@@ -480,22 +481,30 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_kabsch_sums_kernel(MomArgs 
         acc[6] = fmaf(q0.x, q1.x, acc[6]); acc[7] = fmaf(q0.x, q1.y, acc[7]); acc[8] = fmaf(q0.x, q1.z, acc[8]);
         acc[9] = fmaf(q0.y, q1.x, acc[9]); acc[10] = fmaf(q0.y, q1.y, acc[10]); acc[11] = fmaf(q0.y, q1.z, acc[11]);
         acc[12] = fmaf(q0.z, q1.x, acc[12]); acc[13] = fmaf(q0.z, q1.y, acc[13]); acc[14] = fmaf(q0.z, q1.z, acc[14]);
-        acc[15] += q0.w; acc[16] += 1.f;
+        acc_d2 += (double)q0.w; acc[15] += 1.f;
       }
       __syncthreads();
     }
 #pragma unroll
-    for (int e = 0; e < KAB; ++e) {
+    for (int e = 0; e < 16; ++e) {
       const float tot = warp_sum(acc[e]);
-      if (lane == 0) s_sums[warp][e] = tot;
+      if (lane == 0) s_sums[warp][e < 15 ? e : 17] = tot;
     }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc_d2 += __shfl_xor_sync(0xffffffffu, acc_d2, o);
+    if (lane == 0) { s_sums[warp][15] = __int_as_float(__double2hiint(acc_d2)); s_sums[warp][16] = __int_as_float(__double2loint(acc_d2)); }
     __syncthreads();
     float *out = a.partial + (size_t)w * 96;
     if (tid < 96) {
       float t = 0.f;
-      if (tid < KAB) {
+      if (tid < KAB && tid != 15 && tid != 16) {
 #pragma unroll
         for (int q = 0; q < NW; ++q) t += s_sums[q][tid];
+      } else if (tid == 15 || tid == 16) {
+        double d = 0.0;
+#pragma unroll
+        for (int q = 0; q < NW; ++q) d += __hiloint2double(__float_as_int(s_sums[q][15]), __float_as_int(s_sums[q][16]));
+        t = tid == 15 ? __int_as_float(__double2hiint(d)) : __int_as_float(__double2loint(d));
       }
       out[tid] = t;
     }
@@ -534,7 +543,7 @@ __device__ __forceinline__ void sym3_jacobi(double (&A)[3][3], double (&V)[3][3]
 // R = U diag(1, 1, det) V^T; the third columns of U and V are built as cross products, which folds the reflection case in.
 // Returns false for a degenerate configuration (rank < 2): the caller keeps the identity increment.
 __device__ __forceinline__ bool solve_kabsch(const float *sums, float *R, float *t) {
-  const double n = (double)sums[16];
+  const double n = (double)sums[17];
   double cp[3], cm[3], S[3][3];
 #pragma unroll
   for (int k = 0; k < 3; ++k) { cp[k] = (double)sums[k] / n; cm[k] = (double)sums[3 + k] / n; }
@@ -606,13 +615,17 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) icp_solve_kernel(SolveArgs a
   {
     const float *p = a.partial + (size_t)pos * a.n_groups * 96;
     float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+    double dsum = 0.0;
     for (int g = 0; g < a.n_groups; ++g) {   // fixed order: bits do not depend on which CTA produced which partial
       t0 += __ldcs(p + g * 96 + lane); t1 += __ldcs(p + g * 96 + 32 + lane); t2 += __ldcs(p + g * 96 + 64 + lane);
+      if (SOLVER == 3) dsum += __hiloint2double(__float_as_int(__ldcs(p + g * 96 + 15)), __float_as_int(__ldcs(p + g * 96 + 16)));
     }
     sums[lane] = t0; sums[32 + lane] = t1; sums[64 + lane] = t2;
+    if (SOLVER == 3) { __syncwarp(); if (lane == 0) { sums[15] = __int_as_float(__double2hiint(dsum)); sums[16] = __int_as_float(__double2loint(dsum)); } }
   }
   __syncwarp();
-  const float cnt_f = SOLVER == 3 ? sums[16] : sums[92], sumd2 = SOLVER == 3 ? sums[15] : sums[91];
+  const float cnt_f = SOLVER == 3 ? sums[17] : sums[92];
+  const double sumd2 = SOLVER == 3 ? __hiloint2double(__float_as_int(sums[15]), __float_as_int(sums[16])) : (double)sums[91];
   const int cnt = (int)(cnt_f + 0.5f);
   int iters = st->iters;
   bool converged = false, finished = false, runaway = false;
@@ -659,7 +672,7 @@ __global__ void __launch_bounds__(SOLVE_WARPS * 32) icp_solve_kernel(SolveArgs a
       double tsq = (double)inc.t[0] * inc.t[0] + (double)inc.t[1] * inc.t[1] + (double)inc.t[2] * inc.t[2];
       if (cos_angle >= 1.0 && tsq <= 0.0) converged = true;
       else {
-        mse = (double)sumd2 / (double)cnt;
+        mse = sumd2 / (double)cnt;
         if (fabs(mse - st->prev_mse) < a.abs_mse_eps) converged = true;
       }
     }

@@ -1,5 +1,12 @@
-// k_s4pcs_plan.cu -- HOST side of Super4PCS: everything that consumes the reference's random streams, planned for all
-// trials before the device starts (no GPU code in this file; it is part of libhop.so because runSuper4pcs calls it).
+// k_s4pcs_plan.cu -- the planner of Super4PCS: everything that consumes the reference's random streams, planned for all
+// trials before the congruent-set kernels start.  The random draws are serial and stay on the host; what they consult -- "does the
+// PPF key of this pair of scene points exist in the model's table?" (gr::computePPF + the std::map lookup, matchBase.hpp:27-68,
+// 134,159,201) -- is data parallel and comes from the device when a context is given (hop_s4pcs_plan_create_gpu): one launch fills a
+// bit matrix of ALL pairs of scene points (up to 6144 points; row by row on demand above), the host planner then only reads bits.
+// The keys truncate acos(.) / pi * 180 to an integer: a pair whose angle lies within 2e-4 degrees of an integer (or whose cosine is
+// within 1e-6 of +-1) is flagged by the kernel and re-evaluated on the host with the reference's libm, so the pools -- and with them
+// the replayed random streams -- stay bit-identical (tests/test_s4pcs_plan.py, tests/test_gpu_s4pcs.py).
+// hop_ppf_table_build does the same for the model's table itself (computePPF.cpp:56-107: all pairs of the 5 mm model).
 //
 //   MatchBase::init                 src/OpenGR_4pcs/src/gr/algorithms/matchBase.hpp:382-462
 //   UniformDistSampler              src/OpenGR_4pcs/src/gr/sampling.h:67-145
@@ -21,6 +28,12 @@
 #include <random>
 #include <unordered_set>
 
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_select.cuh>
+
+#include <unordered_map>
+
+#include "hop_common.cuh"
 #include "s4pcs.h"
 
 namespace {
@@ -65,6 +78,130 @@ inline uint64_t pack_key(const int *k) {
   return ((uint64_t)(uint16_t)k[0] << 48) | ((uint64_t)(uint16_t)k[1] << 32) | ((uint64_t)(uint16_t)k[2] << 16) | (uint64_t)(uint16_t)k[3];
 }
 
+
+// ---- device side: PPF keys of point pairs ---------------------------------------------------------------------------------
+__device__ __forceinline__ float d_dot3(const float *a, const float *b) {   // Eigen's 3-term reduction: t0 + (t1 + t2), no FMA
+  return __fadd_rn(__fmul_rn(a[0], b[0]), __fadd_rn(__fmul_rn(a[1], b[1]), __fmul_rn(a[2], b[2])));
+}
+__device__ __forceinline__ void d_normalize(float *a) {
+  const float z = d_dot3(a, a);
+  if (z > 0.f) { const float sq = __fsqrt_rn(z); a[0] = __fdiv_rn(a[0], sq); a[1] = __fdiv_rn(a[1], sq); a[2] = __fdiv_rn(a[2], sq); }
+}
+__device__ __forceinline__ int d_closest_bin(int value, int discretization) {
+  const int lower = value - (value % discretization), upper = lower + discretization;
+  return (value - lower < upper - value) ? lower : upper;
+}
+// angle bin of acos(x) / pi * 180 the way the host computes it (float acosf, double division); `amb` is raised when the host's libm
+// could land on the other side of an integer
+__device__ __forceinline__ int d_angle_deg(float x, bool &amb) {
+  if (!(fabsf(x) <= 1.f - 1e-6f)) { amb = true; return 0; }
+  const float af = (float)acos((double)x);
+  const double deg = (double)af / M_PI * 180.0;
+  const double fr = deg - floor(deg);
+  if (fr < 2e-4 || fr > 1.0 - 2e-4) amb = true;
+  return (int)deg;
+}
+// gr::computePPF for the pair (a, b); returns the packed key (or ~0 when a field leaves 16 bits)
+__device__ __forceinline__ uint64_t d_ppf_key(const float4 pa, const float4 na, const float4 pb, const float4 nb, bool &amb) {
+  float n1[3] = {na.x, na.y, na.z}, n2[3] = {nb.x, nb.y, nb.z};
+  d_normalize(n1); d_normalize(n1); d_normalize(n2); d_normalize(n2);   // compute_ppf normalises twice (the points' normals once already)
+  const float ab[3] = {__fsub_rn(pa.x, pb.x), __fsub_rn(pa.y, pb.y), __fsub_rn(pa.z, pb.z)};
+  const int dist = (int)__fmul_rn(__fsqrt_rn(d_dot3(ab, ab)), 1000.f);
+  float d[3] = {__fsub_rn(pb.x, pa.x), __fsub_rn(pb.y, pa.y), __fsub_rn(pb.z, pa.z)};
+  d_normalize(d);
+  const int a1 = d_angle_deg(d_dot3(n1, d), amb), a2 = d_angle_deg(d_dot3(n2, d), amb), a3 = d_angle_deg(d_dot3(n1, n2), amb);
+  const int k[4] = {d_closest_bin(dist, 5), d_closest_bin(a1, 10), d_closest_bin(a2, 10), d_closest_bin(a3, 10)};
+  if (k[0] < 0 || k[0] > 65535 || k[1] < 0 || k[1] > 65535 || k[2] < 0 || k[2] > 65535 || k[3] < 0 || k[3] > 65535) return ~0ull;
+  return ((uint64_t)k[0] << 48) | ((uint64_t)k[1] << 32) | ((uint64_t)k[2] << 16) | (uint64_t)k[3];
+}
+__device__ __forceinline__ bool d_key_in_table(const uint64_t *__restrict__ keys, int n, uint64_t key) {
+  int lo = 0, hi = n;
+  while (lo < hi) { const int mid = (lo + hi) >> 1; if (keys[mid] < key) lo = mid + 1; else hi = mid; }
+  return lo < n && keys[lo] == key;
+}
+// rows[r] x every point j: member bit = key(P[rows[r]], P[j]) is in the table, amb bit = the host must re-evaluate the pair
+__global__ void ppf_rows_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, int n, const int *__restrict__ rows, int n_rows,
+                                const uint64_t *__restrict__ keys, int n_keys, uint32_t *__restrict__ member, uint32_t *__restrict__ ambig, int words) {
+  const int r = blockIdx.y, j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = rows ? rows[r] : r;
+  bool amb = false, mem = false;
+  if (j < n && j != i) {
+    const uint64_t key = d_ppf_key(pos[i], nrm[i], pos[j], nrm[j], amb);
+    mem = key != ~0ull && d_key_in_table(keys, n_keys, key);
+  }
+  const unsigned mb = __ballot_sync(0xffffffffu, mem), ab = __ballot_sync(0xffffffffu, amb);
+  if ((threadIdx.x & 31) == 0 && (j >> 5) < words) { member[(size_t)r * words + (j >> 5)] = mb; ambig[(size_t)r * words + (j >> 5)] = ab; }
+}
+// all pairs i < j of a cloud: packed key (or ~0 for an ambiguous / out-of-range pair, which the host re-evaluates)
+__global__ void ppf_pairs_kernel(const float4 *__restrict__ pos, const float4 *__restrict__ nrm, int n, uint64_t *__restrict__ keys, unsigned char *__restrict__ ambig) {
+  const size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= (size_t)n * n) return;
+  const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+  uint64_t key = ~0ull;
+  bool amb = false;
+  if (i < j) { key = d_ppf_key(pos[i], nrm[i], pos[j], nrm[j], amb); if (amb) key = ~0ull; }
+  keys[t] = key;
+  ambig[t] = (i < j && amb) ? 1 : 0;
+}
+
+// "is the PPF key of (P[a], P[b]) in the table?" answered from device-computed bits; ambiguous pairs fall back to the host formula
+struct PpfBits {
+  hop_ctx *ctx = nullptr;
+  int n = 0, words = 0, n_keys = 0;
+  bool full = false;
+  float4 *d_pos = nullptr, *d_nrm = nullptr;
+  uint64_t *d_keys = nullptr;
+  uint32_t *d_member = nullptr, *d_ambig = nullptr;
+  int *d_rows = nullptr;
+  std::vector<uint32_t> member, ambig;                       // full mode: n x words
+  std::unordered_map<int, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> rows;   // row mode: fetched on demand
+  int launches = 0;
+  ~PpfBits() { if (ctx) { HopDeviceGuard g(ctx); cudaFree(d_pos); cudaFree(d_nrm); cudaFree(d_keys); cudaFree(d_member); cudaFree(d_ambig); cudaFree(d_rows); } }
+  int init(hop_ctx *c, const std::vector<S4Pt> &P, const std::vector<uint64_t> &sorted_keys) {
+    ctx = c; n = (int)P.size(); words = (n + 31) / 32; n_keys = (int)sorted_keys.size();
+    if (n == 0) return HOP_OK;
+    std::vector<float4> hp(n), hn(n);
+    for (int i = 0; i < n; ++i) { hp[i] = make_float4(P[i].p[0], P[i].p[1], P[i].p[2], 0.f); hn[i] = make_float4(P[i].n[0], P[i].n[1], P[i].n[2], 0.f); }
+    HOP_CUDA(ctx, cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); HOP_CUDA(ctx, cudaMalloc(&d_nrm, sizeof(float4) * (size_t)n));
+    HOP_CUDA(ctx, cudaMalloc(&d_keys, sizeof(uint64_t) * (size_t)std::max(n_keys, 1)));
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_pos, hp.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    HOP_CUDA(ctx, cudaMemcpyAsync(d_nrm, hn.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
+    if (n_keys) HOP_CUDA(ctx, cudaMemcpyAsync(d_keys, sorted_keys.data(), sizeof(uint64_t) * (size_t)n_keys, cudaMemcpyHostToDevice, ctx->stream));
+    full = n <= 6144;
+    const size_t rows_alloc = full ? (size_t)n : 64;
+    HOP_CUDA(ctx, cudaMalloc(&d_member, sizeof(uint32_t) * rows_alloc * words)); HOP_CUDA(ctx, cudaMalloc(&d_ambig, sizeof(uint32_t) * rows_alloc * words));
+    HOP_CUDA(ctx, cudaMalloc(&d_rows, sizeof(int) * 64));
+    if (full) {
+      ppf_rows_kernel<<<dim3((n + 255) / 256, n), 256, 0, ctx->stream>>>(d_pos, d_nrm, n, nullptr, n, d_keys, n_keys, d_member, d_ambig, words);
+      ctx->launches += 1; ++launches;
+      member.resize((size_t)n * words); ambig.resize((size_t)n * words);
+      HOP_CUDA(ctx, cudaMemcpyAsync(member.data(), d_member, sizeof(uint32_t) * member.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      HOP_CUDA(ctx, cudaMemcpyAsync(ambig.data(), d_ambig, sizeof(uint32_t) * ambig.size(), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return HOP_OK;
+  }
+  // the row of point a (row mode: one launch + copy per first use)
+  bool row(int a, const uint32_t *&m, const uint32_t *&am) {
+    if (full) { m = &member[(size_t)a * words]; am = &ambig[(size_t)a * words]; return true; }
+    auto it = rows.find(a);
+    if (it == rows.end()) {
+      if (cudaMemcpyAsync(d_rows, &a, sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
+      ppf_rows_kernel<<<dim3((n + 255) / 256, 1), 256, 0, ctx->stream>>>(d_pos, d_nrm, n, d_rows, 1, d_keys, n_keys, d_member, d_ambig, words);
+      ctx->launches += 1; ++launches;
+      std::pair<std::vector<uint32_t>, std::vector<uint32_t>> r;
+      r.first.resize(words); r.second.resize(words);
+      if (cudaMemcpyAsync(r.first.data(), d_member, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaMemcpyAsync(r.second.data(), d_ambig, sizeof(uint32_t) * words, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+          cudaStreamSynchronize(ctx->stream) != cudaSuccess)
+        return false;
+      it = rows.emplace(a, std::move(r)).first;
+    }
+    m = it->second.first.data(); am = it->second.second.data();
+    return true;
+  }
+};
+
 struct Planner {
   hop_s4pcs_plan &pl;
   std::unordered_set<uint64_t> keys;
@@ -76,11 +213,39 @@ struct Planner {
 
   explicit Planner(hop_s4pcs_plan &p) : pl(p), random_generator(p.opt.random_seed ? p.opt.random_seed : std::mt19937::default_seed), point_index_engine(0) {}
 
+  PpfBits *bits = nullptr;   // device-computed membership (hop_s4pcs_plan_create_gpu), null = evaluate on the host
   bool has_ppf(const S4Pt &a, const S4Pt &b) const {
     int k[4];
     compute_ppf(a, b, k);
     if (k[0] < 0 || k[0] > 65535 || k[1] < 0 || k[1] > 65535 || k[2] < 0 || k[2] > 65535 || k[3] < 0 || k[3] > 65535) return false;
     return keys.count(pack_key(k)) != 0;
+  }
+  // membership of the pair of scene points (a, b): a bit of the device matrix, the host formula for flagged pairs
+  bool has_ppf_idx(int a, int b) const {
+    if (bits && a != b) {
+      const uint32_t *m, *am;
+      if (bits->full || bits->rows.count(a)) {
+        if (bits->row(a, m, am)) {
+          if (!((am[b >> 5] >> (b & 31)) & 1u)) return (m[b >> 5] >> (b & 31)) & 1u;
+        }
+      }
+    }
+    return has_ppf(pl.P[a], pl.P[b]);
+  }
+  // the whole row of point a at once (the O(N) scans): member[i] for every i
+  void ppf_row(int a, std::vector<unsigned char> &out, const std::vector<int> *subset) const {
+    const std::vector<S4Pt> &P = pl.P;
+    const int n = subset ? (int)subset->size() : (int)P.size();
+    out.assign(n, 0);
+    const uint32_t *m = nullptr, *am = nullptr;
+    const bool dev = bits && bits->row(a, m, am);
+#pragma omp parallel for schedule(static) if (!dev && n >= 512)
+    for (int t = 0; t < n; ++t) {
+      const int i = subset ? (*subset)[t] : t;
+      if (i == a) continue;
+      if (dev && !((am[i >> 5] >> (i & 31)) & 1u)) out[t] = (m[i >> 5] >> (i & 31)) & 1u;
+      else out[t] = has_ppf(P[a], P[i]) ? 1 : 0;
+    }
   }
 
   // MatchBase::init
@@ -156,9 +321,7 @@ struct Planner {
     std::vector<float> probs;
     // (the membership tests -- three acos and a set lookup per point -- are the planner's O(N) cost: evaluated on all host
     //  threads with the same libm, gathered in index order, so the pool is the one a sequential loop builds)
-    member.assign(number_of_points, 0);
-#pragma omp parallel for schedule(static) if (number_of_points >= 512)
-    for (int i = 0; i < number_of_points; ++i) member[i] = (i != first_point && has_ppf(P[first_point], P[i])) ? 1 : 0;
+    ppf_row(first_point, member, nullptr);
     for (int i = 0; i < number_of_points; ++i)
       if (member[i]) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
     if (sample_pool.size() < 3) return false;
@@ -168,7 +331,7 @@ struct Planner {
       const int second_point = sampler1(point_index_engine);
       const int third_point = sampler1(point_index_engine);
       if (second_point == third_point) continue;
-      if (!has_ppf(P[sample_pool[second_point]], P[sample_pool[third_point]])) continue;
+      if (!has_ppf_idx(sample_pool[second_point], sample_pool[third_point])) continue;
       probs[second_point] *= pl.opt.dispersion;
       probs[third_point] *= pl.opt.dispersion;
       const V3 u = sub(P[sample_pool[second_point]].p, P[first_point].p);
@@ -183,11 +346,15 @@ struct Planner {
     std::vector<int> backup = sample_pool;
     sample_pool.clear();
     const int nb = (int)backup.size();
-    member.assign(nb, 0);
-#pragma omp parallel for schedule(static) if (nb >= 512)
-    for (int i = 0; i < nb; ++i) {
-      if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
-      member[i] = (has_ppf(P[base2], P[backup[i]]) && has_ppf(P[base3], P[backup[i]])) ? 1 : 0;
+    {
+      std::vector<unsigned char> m2, m3;
+      ppf_row(base2, m2, &backup);
+      ppf_row(base3, m3, &backup);
+      member.assign(nb, 0);
+      for (int i = 0; i < nb; ++i) {
+        if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
+        member[i] = (m2[i] && m3[i]) ? 1 : 0;
+      }
     }
     // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
     // a point id (match4pcsBase.hpp:159): reproduced
@@ -331,8 +498,8 @@ void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const fl
   for (int k = 0; k < 4; ++k) key[k] = k4[k];
 }
 
-int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm,
-                          int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
+static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm,
+                       int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
   if (!out) return HOP_EINVAL;
   *out = nullptr;
   if (!opt || nP < 0 || nQ < 0 || n_keys < 0 || (nP > 0 && (!P_xyz || !P_nrm)) || (nQ > 0 && (!Q_xyz || !Q_nrm)) || (n_keys > 0 && !ppf_keys) ||
@@ -346,8 +513,91 @@ int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P
     if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) planner.keys.insert(pack_key(k));
   }
   planner.init(P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ);
+  PpfBits bits;
+  if (ctx && pl->P.size() >= 4 && pl->Q.size() >= 4) {
+    std::vector<uint64_t> sorted(planner.keys.begin(), planner.keys.end());
+    std::sort(sorted.begin(), sorted.end());
+    const int rc = bits.init(ctx, pl->P, sorted);
+    if (rc != HOP_OK) { delete pl; return rc; }
+    planner.bits = &bits;
+  }
   planner.plan_trials();
   *out = pl;
+  return HOP_OK;
+}
+
+int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm,
+                          int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
+  return plan_create(nullptr, P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ, ppf_keys, n_keys, opt, out);
+}
+
+int hop_s4pcs_plan_create_gpu(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz,
+                              const float *Q_nrm, int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
+  HOP_ENTER(ctx);
+  if (!ctx) return HOP_EINVAL;
+  return plan_create(ctx, P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ, ppf_keys, n_keys, opt, out);
+}
+
+// computePPF.cpp:56-107: the table of the model = the distinct keys of all its point pairs, sorted.  keys_out: capacity x 4 ints
+// (may be NULL to ask for the count); *n_keys = the number of distinct keys.
+int hop_ppf_table_build(hop_ctx *ctx, const float *xyz, const float *nrm, int n, int32_t *keys_out, int capacity, int32_t *n_keys) {
+  HOP_ENTER(ctx);
+  if (!ctx || n < 0 || (n > 0 && (!xyz || !nrm)) || !n_keys || capacity < 0 || (capacity > 0 && !keys_out)) { if (ctx) ctx->err = "hop_ppf_table_build: bad arguments"; return HOP_EINVAL; }
+  *n_keys = 0;
+  if (n < 2) return HOP_OK;
+  if (n > 20000) { ctx->err = "hop_ppf_table_build: more than 20000 model points (the table is built from the 5 mm model)"; return HOP_EINVAL; }
+  cudaStream_t st = ctx->stream;
+  const size_t np = (size_t)n * n;
+  std::vector<float4> hp(n), hn(n);
+  for (int i = 0; i < n; ++i) {   // Point3D::set_normal normalises once
+    V3 nn = normalized(V3{nrm[3 * i], nrm[3 * i + 1], nrm[3 * i + 2]});
+    hp[i] = make_float4(xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2], 0.f); hn[i] = make_float4(nn[0], nn[1], nn[2], 0.f);
+  }
+  float4 *d_pos = nullptr, *d_nrm = nullptr; uint64_t *d_k = nullptr, *d_s = nullptr, *d_u = nullptr; unsigned char *d_amb = nullptr; int *d_cnt = nullptr; void *d_tmp = nullptr;
+  auto release = [&]() { cudaFree(d_pos); cudaFree(d_nrm); cudaFree(d_k); cudaFree(d_s); cudaFree(d_u); cudaFree(d_amb); cudaFree(d_cnt); cudaFree(d_tmp); };
+#define PT_CUDA(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { ctx->err = std::string(#call) + ": " + cudaGetErrorString(e_); release(); return HOP_ECUDA; } } while (0)
+  PT_CUDA(cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); PT_CUDA(cudaMalloc(&d_nrm, sizeof(float4) * (size_t)n));
+  PT_CUDA(cudaMalloc(&d_k, sizeof(uint64_t) * np)); PT_CUDA(cudaMalloc(&d_s, sizeof(uint64_t) * np)); PT_CUDA(cudaMalloc(&d_u, sizeof(uint64_t) * np));
+  PT_CUDA(cudaMalloc(&d_amb, np)); PT_CUDA(cudaMalloc(&d_cnt, sizeof(int)));
+  PT_CUDA(cudaMemcpyAsync(d_pos, hp.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  PT_CUDA(cudaMemcpyAsync(d_nrm, hn.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, st));
+  ppf_pairs_kernel<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_pos, d_nrm, n, d_k, d_amb);
+  size_t b1 = 0, b2 = 0;
+  cub::DeviceRadixSort::SortKeys(nullptr, b1, d_k, d_s, (int)np, 0, 64, st);
+  cub::DeviceSelect::Unique(nullptr, b2, d_s, d_u, d_cnt, (int)np, st);
+  PT_CUDA(cudaMalloc(&d_tmp, std::max(b1, b2)));
+  cub::DeviceRadixSort::SortKeys(d_tmp, b1, d_k, d_s, (int)np, 0, 64, st);
+  cub::DeviceSelect::Unique(d_tmp, b2, d_s, d_u, d_cnt, (int)np, st);
+  ctx->launches += 3;
+  int cnt = 0;
+  std::vector<unsigned char> amb(np);
+  PT_CUDA(cudaMemcpyAsync(&cnt, d_cnt, sizeof(int), cudaMemcpyDeviceToHost, st));
+  PT_CUDA(cudaMemcpyAsync(amb.data(), d_amb, np, cudaMemcpyDeviceToHost, st));
+  PT_CUDA(cudaStreamSynchronize(st));
+  std::vector<uint64_t> uniq(cnt);
+  if (cnt) PT_CUDA(cudaMemcpy(uniq.data(), d_u, sizeof(uint64_t) * (size_t)cnt, cudaMemcpyDeviceToHost));
+  release();
+#undef PT_CUDA
+  if (!uniq.empty() && uniq.back() == ~0ull) uniq.pop_back();   // the marker of skipped (i >= j), ambiguous and out-of-range pairs
+  // the flagged pairs with the reference's libm
+  bool added = false;
+  for (size_t t = 0; t < np; ++t)
+    if (amb[t]) {
+      const int i = (int)(t / n), j = (int)(t - (size_t)i * n);
+      S4Pt a, b;
+      for (int k = 0; k < 3; ++k) { a.p[k] = (&hp[i].x)[k]; b.p[k] = (&hp[j].x)[k]; a.n[k] = (&hn[i].x)[k]; b.n[k] = (&hn[j].x)[k]; }
+      int k4[4];
+      compute_ppf(a, b, k4);
+      if (k4[0] < 0 || k4[0] > 65535 || k4[1] < 0 || k4[1] > 65535 || k4[2] < 0 || k4[2] > 65535 || k4[3] < 0 || k4[3] > 65535) continue;
+      uniq.push_back(pack_key(k4));
+      added = true;
+    }
+  if (added) { std::sort(uniq.begin(), uniq.end()); uniq.erase(std::unique(uniq.begin(), uniq.end()), uniq.end()); }
+  *n_keys = (int32_t)uniq.size();
+  for (size_t t = 0; t < uniq.size() && (int)t < capacity; ++t) {
+    keys_out[4 * t] = (int32_t)(uniq[t] >> 48); keys_out[4 * t + 1] = (int32_t)((uniq[t] >> 32) & 0xffff);
+    keys_out[4 * t + 2] = (int32_t)((uniq[t] >> 16) & 0xffff); keys_out[4 * t + 3] = (int32_t)(uniq[t] & 0xffff);
+  }
   return HOP_OK;
 }
 

@@ -194,6 +194,8 @@ def load_library():
                                           _vp, _vp, _vp, _vp, _vp]
     L.hop_refine_score_select_dev.argtypes = [_vp, _vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), C.POINTER(LcpParams), C.c_int, C.c_int,
                                               C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
+    L.hop_s4pcs_plan_create_gpu.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(S4pcsOptions), C.POINTER(_vp)]
+    L.hop_ppf_table_build.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int32)]
     L.hop_frame_organized.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(FrameParams), C.c_float, C.c_float, C.POINTER(_vp)]
     L.hop_cloud_mls.argtypes = [_vp, _vp, C.c_float, C.POINTER(_vp)]
     L.hop_comm_unique_id.argtypes = [_vp]
@@ -274,17 +276,22 @@ def cluster_poses(poses, scores, angle_diff_deg, dist_diff, symmetry_deg=(360.0,
 
 
 class S4pcsPlan:
-    """hop_s4pcs_plan*: the host-side plan of one Super4PCS registration (sampling + all bases); no GPU needed."""
+    """hop_s4pcs_plan*: the plan of one Super4PCS registration (sampling + all bases).  ctx = None: entirely on the host (no GPU
+    needed); with a Context the planner's PPF-membership scans are answered by the device (hop_s4pcs_plan_create_gpu), same plan."""
 
-    def __init__(self, P_xyz, P_nrm, P_prob, Q_xyz, Q_nrm, ppf_keys, options=None):
+    def __init__(self, P_xyz, P_nrm, P_prob, Q_xyz, Q_nrm, ppf_keys, options=None, ctx=None):
         self.L = load_library()
         self.options = options or s4pcs_options()
         P_xyz, P_nrm, Q_xyz, Q_nrm = _f32(P_xyz, 3), _f32(P_nrm, 3), _f32(Q_xyz, 3), _f32(Q_nrm, 3)
         prob = None if P_prob is None else _f32(P_prob)
         keys = np.ascontiguousarray(ppf_keys, np.int32).reshape(-1, 4)
         h = _vp()
-        rc = self.L.hop_s4pcs_plan_create(_ptr(P_xyz), _ptr(P_nrm), _ptr(prob), len(P_xyz), _ptr(Q_xyz), _ptr(Q_nrm), len(Q_xyz), _ptr(keys),
-                                          len(keys), C.byref(self.options), C.byref(h))
+        if ctx is None:
+            rc = self.L.hop_s4pcs_plan_create(_ptr(P_xyz), _ptr(P_nrm), _ptr(prob), len(P_xyz), _ptr(Q_xyz), _ptr(Q_nrm), len(Q_xyz), _ptr(keys),
+                                              len(keys), C.byref(self.options), C.byref(h))
+        else:
+            rc = self.L.hop_s4pcs_plan_create_gpu(ctx.h, _ptr(P_xyz), _ptr(P_nrm), _ptr(prob), len(P_xyz), _ptr(Q_xyz), _ptr(Q_nrm), len(Q_xyz),
+                                                  _ptr(keys), len(keys), C.byref(self.options), C.byref(h))
         if rc != 0:
             raise HopError(f"hop_s4pcs_plan_create failed ({rc})")
         self.h = h
@@ -609,6 +616,23 @@ class Context:
             scene.n = n
             return scene, counts
         return Cloud(self, handle, n), counts
+
+    def ppf_table(self, xyz, nrm):
+        """the model's PPF table (computePPF.cpp:56-107) on the device: distinct keys (n, 4) int32, sorted"""
+        xyz, nrm = _f32(xyz, 3), _f32(nrm, 3)
+        nk = C.c_int32(0)
+        self._check(self.L.hop_ppf_table_build(self.h, _ptr(xyz), _ptr(nrm), len(xyz), None, 0, C.byref(nk)))
+        keys = np.zeros((max(nk.value, 1), 4), np.int32)
+        self._check(self.L.hop_ppf_table_build(self.h, _ptr(xyz), _ptr(nrm), len(xyz), _ptr(keys), nk.value, C.byref(nk)))
+        return keys[: nk.value]
+
+    def frame_organized(self, depth_mm, params, max_depth_change_factor=0.02, normal_smoothing_size=10.0):
+        """depth image -> the frame's valid pixels (raster order) with PCL's integral-image normals (hop_frame_organized)"""
+        depth_mm = np.ascontiguousarray(depth_mm, np.uint16)
+        h, w = depth_mm.shape
+        out = _vp()
+        self._check(self.L.hop_frame_organized(self.h, _ptr(depth_mm), w, h, C.byref(params), max_depth_change_factor, normal_smoothing_size, C.byref(out)))
+        return Cloud(self, out, int(self.L.hop_cloud_size(out)))
 
     def cluster_poses(self, poses, scores, angle_diff_deg, dist_diff, symmetry_deg=(360.0, 360.0, 360.0), ids=None):
         """PoseEstimator::clusterPoses with the comparisons on the device (hop_cluster_poses_gpu): the same keep list as the

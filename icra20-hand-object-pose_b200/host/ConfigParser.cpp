@@ -1,3 +1,4 @@
+#include <cstdlib>
 #include "ConfigParser.h"
 
 #include <cstdio>
@@ -20,6 +21,7 @@ static bool fill44(const std::vector<float> &d, Mat4f &M) {
 void ConfigParser::parseYMLFile(std::string) {
   {
     std::vector<float> K = yml["cam_K"].as<std::vector<float>>();
+    if (K.size() < 9) { printf("config: cam_K needs 9 numbers (got %d)\n", (int)K.size()); exit(1); }
     for (int i = 0; i < 9; i++) cam_intrinsic(i / 3, i % 3) = K[i];
   }
   endeffector2global.setIdentity();
@@ -35,6 +37,7 @@ void ConfigParser::parseYMLFile(std::string) {
   }
   {
     std::vector<float> data = yml["cam1_in_leftarm"].as<std::vector<float>>();   // xyz, q(xyzw)
+    if (data.size() < 7) { printf("config: cam1_in_leftarm needs 7 numbers, xyz + quaternion xyzw (got %d)\n", (int)data.size()); exit(1); }
     cam1_in_leftarm.setIdentity();
     cam1_in_leftarm(0, 3) = data[0]; cam1_in_leftarm(1, 3) = data[1]; cam1_in_leftarm(2, 3) = data[2];
     quat_to_rot(data[6], data[3], data[4], data[5], cam1_in_leftarm);

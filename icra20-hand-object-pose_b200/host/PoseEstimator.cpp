@@ -163,17 +163,27 @@ bool PoseEstimator::runSuper4pcs(const std::vector<int32_t> &ppf_keys) {
   o.max_color_distance = cfg->super4pcs_max_color_distance;
   const Cloud &P = _scene_high_confidence;
   hop_s4pcs_plan *plan = nullptr;
-  int rc = hop_s4pcs_plan_create(P.xyz.data(), P.nrm.data(), P.conf.data(), (int)P.size(), _model.xyz.data(), _model.nrm.data(), (int)_model.size(),
+  // (the planner's PPF-membership scans run on the device; the random draws it replays stay on the host)
+  int rc = hop_s4pcs_plan_create_gpu(ctx, P.xyz.data(), P.nrm.data(), P.conf.data(), (int)P.size(), _model.xyz.data(), _model.nrm.data(), (int)_model.size(),
                                  ppf_keys.data(), (int)(ppf_keys.size() / 4), &o, &plan);
   if (rc != HOP_OK) { fprintf(stderr, "hop_s4pcs_plan_create failed (%d)\n", rc); return false; }
   const int cap = cfg->b200_max_hypotheses;   // the reference reserves 20000 (super4pcs.h:134)
   std::vector<float> poses(16 * (size_t)cap), lcp(cap);
   int32_t n = 0;
   rc = hop_super4pcs_run(ctx, plan, poses.data(), lcp.data(), cap, &n);
+  if (rc == HOP_OK && n > cap) {
+    // the reference only reserve()s 20000 and keeps every hypothesis (super4pcs.h:134): fetch them all -- dropping the tail in
+    // (trial, quadrilateral) emission order could lose the best hypotheses of the later trials before clusterPoses sorts
+    printf("runSuper4pcs: %d hypotheses exceed b200_max_hypotheses = %d, fetching all of them\n", (int)n, cap);
+    poses.resize(16 * (size_t)n); lcp.resize((size_t)n);
+    const int all = n;
+    rc = hop_super4pcs_run(ctx, plan, poses.data(), lcp.data(), all, &n);
+    n = std::min<int32_t>(n, all);
+  } else n = std::min<int32_t>(n, cap);
   hop_s4pcs_plan_destroy(plan);
   check(rc, "hop_super4pcs_run");
   _pose_hypos.clear();
-  for (int i = 0; i < std::min<int>(n, cap); ++i) {
+  for (int i = 0; i < n; ++i) {
     Mat4f T;
     std::memcpy(T.data(), &poses[16 * (size_t)i], 64);
     _pose_hypos.push_back(PoseHypo(T, i, lcp[i]));

@@ -134,6 +134,15 @@ bool loadOBJMesh(const std::string &path, std::vector<float> &V, std::vector<int
   return true;
 }
 
+bool saveOBJMesh(const std::string &path, const std::vector<float> &V, const std::vector<int32_t> &F) {
+  std::ofstream f(path);
+  if (!f) return false;
+  f.precision(9);
+  for (size_t i = 0; i + 2 < V.size(); i += 3) f << "v " << V[i] << " " << V[i + 1] << " " << V[i + 2] << "\n";
+  for (size_t i = 0; i + 2 < F.size(); i += 3) f << "f " << F[i] + 1 << " " << F[i + 1] + 1 << " " << F[i + 2] + 1 << "\n";
+  return true;
+}
+
 bool saveOBJVertices(const std::string &path, const Cloud &c) {
   std::ofstream f(path);
   if (!f) return false;
@@ -160,11 +169,17 @@ bool readPNG16(const std::string &path, std::vector<uint16_t> &pix, int &width, 
     const std::string type((const char *)&buf[o + 4], 4);
     if (o + 12 + len > buf.size()) return fail("truncated PNG chunk");
     const unsigned char *d = &buf[o + 8];
-    if (type == "IHDR") { width = (int)be32(o + 8); height = (int)be32(o + 12); depth = d[8]; ctype = d[9]; interlace = d[12]; }
+    if (type == "IHDR") {
+      if (len != 13) return fail("bad PNG IHDR chunk");
+      const uint32_t w32 = be32(o + 8), h32 = be32(o + 12);
+      if (w32 == 0 || h32 == 0 || w32 > 16384 || h32 > 16384) return fail("PNG dimensions out of range");
+      width = (int)w32; height = (int)h32; depth = d[8]; ctype = d[9]; interlace = d[12];
+    }
     else if (type == "IDAT") idat.insert(idat.end(), d, d + len);
     else if (type == "IEND") break;
     o += 12 + len;
   }
+  if (width <= 0 || height <= 0) return fail("PNG without an IHDR chunk");
   if (ctype != 0 || (depth != 16 && depth != 8) || interlace != 0) return fail("only non-interlaced 8/16-bit grayscale PNGs are supported");
   const int bpp = depth / 8;
   const size_t stride = (size_t)width * bpp;
@@ -217,10 +232,10 @@ void readDepthImage(std::vector<float> &depth_m, int &w, int &h, const std::stri
   std::vector<uint16_t> raw;
   std::string err;
   if (!readPNG16(path, raw, w, h, &err)) { printf("readDepthImage: %s\n", err.c_str()); depth_m.clear(); w = h = 0; return; }
-  const float SR300_DEPTH_UNIT = 0.001f;  // Utils.h: depth PNGs are millimetres
+  const double SR300_DEPTH_UNIT = 0.001;  // Utils.h:107: a double literal -- the product is taken in double and rounded to float once
   depth_m.resize(raw.size());
   for (size_t i = 0; i < raw.size(); ++i) {
-    const float d = (float)raw[i] * SR300_DEPTH_UNIT;
+    const float d = (float)((double)(float)raw[i] * SR300_DEPTH_UNIT);
     depth_m[i] = (d > 2.0 || d < 0.1) ? 0.f : d;
   }
 }

@@ -25,6 +25,7 @@ bool savePLYFile(const std::string &path, const Cloud &c);                      
 // igl::readOBJ as SDFchecker::registerMesh uses it (SDFchecker.cpp:36-49): "v x y z" vertices, "f a b c" faces (a/b/c forms and
 // negative indices accepted, polygons fanned into triangles); V = nv x 3, F = nf x 3 zero-based
 bool loadOBJMesh(const std::string &path, std::vector<float> &V, std::vector<int32_t> &F, std::string *err = nullptr);
+bool saveOBJMesh(const std::string &path, const std::vector<float> &V, const std::vector<int32_t> &F);   // "v" + "f" lines (best.obj)
 bool saveOBJVertices(const std::string &path, const Cloud &c);                      // "v x y z" lines (best.obj stand-in when no mesh)
 bool readPNG16(const std::string &path, std::vector<uint16_t> &pix, int &width, int &height, std::string *err = nullptr);
 bool parsePoseTxt(const std::string &path, std::vector<float> &data);               // Utils.cpp:516-543: whitespace separated floats

@@ -205,6 +205,17 @@ typedef struct hop_s4pcs_plan hop_s4pcs_plan;
 int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz,
                           const float *Q_nrm, int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt,
                           hop_s4pcs_plan **out);
+/* The same plan with the planner's O(N) scans answered by the device: "is the PPF key of this pair of scene points in the table?"
+ * is computed for all pairs in one launch (a bit matrix; row by row on demand above 6144 scene points) and the host planner, which
+ * alone consumes the random streams, reads bits.  Pairs whose angles sit within 2e-4 degrees of an integer are re-evaluated on the host
+ * with the reference's libm, so the plan is bit-identical to hop_s4pcs_plan_create's. */
+int hop_s4pcs_plan_create_gpu(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz,
+                              const float *Q_nrm, int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt,
+                              hop_s4pcs_plan **out);
+/* The model's PPF table (src/perception/src/app/computePPF.cpp:56-107: gr::computePPF of all point pairs of the 5 mm model): the
+ * distinct keys, sorted, as the reference's std::map holds them.  keys_out: capacity x 4 ints (NULL + capacity 0 asks for the
+ * count); *n_keys = number of distinct keys.  All-pairs kernel + device sort / unique; boundary pairs re-evaluated on the host. */
+int hop_ppf_table_build(hop_ctx *ctx, const float *xyz, const float *nrm, int n, int32_t *keys_out, int capacity, int32_t *n_keys);
 void hop_s4pcs_plan_destroy(hop_s4pcs_plan *plan);
 /* sizes: [0] nP [1] sampled nQ [2] trials planned [3] pairs kept [4] quadrilaterals kept [5] trials executed */
 int hop_s4pcs_plan_sizes(const hop_s4pcs_plan *plan, int32_t *sizes);

@@ -1,0 +1,169 @@
+"""main_realdata_auto WITH a hand model: the hand branch of the reference's entry point (main_realdata_auto.cpp:54-181) through the
+preserved executable -- organized cloud + integral-image normals, HandT42::setCurScene / matchOneComponentPSO x4 (K1) /
+adjustHandHeight / makeHandCloud / removeSurroundingPointsAndAssignProbability, MLS normals, then Super4PCS -> ICP -> LCP -- on a
+depth frame rendered from a synthetic two-finger hand holding an ellipsoid (the reference's URDF, link clouds and object models are an
+external download).  Checked against the ground truth of the synthetic frame: joint angles, object pose (ADI, the reference's own
+metric), the four output files, confidences below 1 next to the hand."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from hop_b200 import synth
+from test_gpu_hand_cpp import _urdf, _rotx
+from test_host_cpp import _write_ply
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+MAIN = os.path.join(ROOT, "icra20-hand-object-pose_b200", "host", "main_realdata_auto")
+K = (616.5961303710938, 616.59619140625, 307.6278076171875, 239.68692016601562)
+
+CFG = """cam_K: [616.5961303710938, 0.0, 307.6278076171875, 0.0, 616.59619140625, 239.68692016601562, 0.0, 0.0, 1.0]
+cam1_in_leftarm: [0.0,0.0,0.0,0.0,0.0,0.0,1.0]
+handbase_in_palm: [1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1]
+out_dir: {out}
+rgb_path: {out}/rgb.png
+depth_path: {out}/depth.png
+palm_in_baselink: {out}/handbase_in_cam.txt
+leftarm_in_base: {out}/eye.txt
+model_name: ellipse
+object_model_path: {out}/object.ply
+ppf_path: {out}/no_table
+object_symmetry:
+  ellipse:
+    x: 180
+    y: 180
+    z: 180
+near_hand_dist: 0.003
+hand_match:
+  finger1_min_match: 5
+  finger2_min_match: 5
+  finger1_dist_thres: 0.005
+  finger2_dist_thres: 0.005
+  finger1_normal_angle: 60
+  finger2_normal_angle: 60
+  check_normal: true
+  max_outter_pts: 300
+  outter_pt_dist: 0.002
+  outter_pt_dist_weight: 1
+lcp:
+  dist: 0.001
+  normal_angle: 10
+pose_estimator_high_confidence_thres: 0.8
+icp_dist_thres: 0.01
+icp_angle_thres: 45
+super4pcs_sample_size: 100
+super4pcs_overlap: 0.2
+super4pcs_delta: 0.003
+super4pcs_dispersion: 0.5
+super4pcs_success_quadrilaterals: 10
+pose_estimator_use_physics: false
+"""
+
+
+def _scene(seed=1):
+    """the synthetic hand of test_gpu_hand_cpp (two fingers of two links + a base) holding an ellipsoid, all in the hand-base frame,
+    as DENSE surface samples with the part they belong to"""
+    rng = np.random.default_rng(seed)
+    size = (0.02, 0.012, 0.06)
+    links, tf_parent, parent = {}, {}, {}
+    for name in ("finger_1_1", "finger_1_2", "finger_2_1", "finger_2_2"):
+        links[name] = synth.make_finger_cloud(900, seed=seed + len(links), size=size)
+    bp, bn = synth._cuboid(rng, 1500, 0.06, 0.13, 0.02)
+    links["base_link"] = ((bp + [-0.09, 0.0, 0.035]).astype(np.float32), bn.astype(np.float32))
+    left = np.eye(4); left[:3, 3] = [-0.15, -0.055, 0.02]
+    right = np.eye(4); right[:3, :3] = np.diag([-1.0, -1.0, 1.0]); right[:3, 3] = [-0.15, 0.055, 0.02]
+    out = np.eye(4); out[:3, 3] = [0, 0, -0.06]
+    tf_parent.update(finger_1_1=left, finger_1_2=out, finger_2_1=right, finger_2_2=out, base_link=np.eye(4))
+    parent.update(finger_1_1="base_link", finger_1_2="finger_1_1", finger_2_1="base_link", finger_2_2="finger_2_1", base_link="base_link")
+    truth = dict(finger_1_1=10.0, finger_1_2=6.0, finger_2_1=8.0, finger_2_2=5.0)
+    in_hb = {"base_link": np.eye(4)}
+    for f in ("1", "2"):
+        in_hb[f"finger_{f}_1"] = tf_parent[f"finger_{f}_1"] @ _rotx(truth[f"finger_{f}_1"])
+        in_hb[f"finger_{f}_2"] = in_hb[f"finger_{f}_1"] @ out @ _rotx(truth[f"finger_{f}_2"])
+    dense = []
+    for name in links:
+        if name == "base_link":
+            x, _ = synth._cuboid(rng, 400000, 0.06, 0.13, 0.02)
+            x = x + [-0.09, 0.0, 0.035]
+        else:
+            x, _ = synth.make_finger_cloud(250000, seed=seed + 70 + len(dense), size=size)
+        T = in_hb[name]
+        dense.append(x.astype(np.float64) @ T[:3, :3].T + T[:3, 3])
+    obj_axes = (0.022, 0.016, 0.015)
+    ox, on = synth._ellipsoid(rng, 400000, *obj_axes)
+    obj_in_hb = np.eye(4); obj_in_hb[:3, :3] = synth._rot_from_rotvec(np.array([0.3, 0.2, -0.4])); obj_in_hb[:3, 3] = [-0.15, 0.0, -0.075]
+    dense.append(ox.astype(np.float64) @ obj_in_hb[:3, :3].T + obj_in_hb[:3, 3])
+    # the camera looks along +x of the hand base, image "down" = -z (the direction the fingers point), 45 cm away, a little to the side
+    cam_in_hb = np.eye(4)
+    cam_in_hb[:3, :3] = np.array([[0, 0, 1.0], [-1.0, 0, 0], [0, -1.0, 0]])
+    cam_in_hb[:3, 3] = [-0.60, 0.03, -0.04]
+    hic = np.linalg.inv(cam_in_hb)
+    return links, tf_parent, parent, truth, hic, dense, obj_in_hb, obj_axes
+
+
+def _splat(points_cam, shape=(480, 640)):
+    u = np.round(points_cam[:, 0] * K[0] / points_cam[:, 2] + K[2]).astype(int)
+    v = np.round(points_cam[:, 1] * K[1] / points_cam[:, 2] + K[3]).astype(int)
+    ok = (u >= 0) & (u < shape[1]) & (v >= 0) & (v < shape[0]) & (points_cam[:, 2] > 0.1)
+    depth = np.full(shape, np.inf)
+    np.minimum.at(depth, (v[ok], u[ok]), points_cam[ok, 2])
+    return depth
+
+
+@pytest.mark.skipif(not os.path.exists(MAIN), reason="main_realdata_auto not built")
+def test_main_realdata_auto_with_the_hand_branch(tmp_path):
+    import cv2
+    from scipy.spatial import cKDTree
+    links, tf_parent, parent, truth, hic, dense, obj_in_hb, obj_axes = _scene()
+    out = str(tmp_path)
+    (tmp_path / "cfg.yaml").write_text(CFG.format(out=out) + _urdf(links, tf_parent, parent, out))
+    np.savetxt(out + "/eye.txt", np.eye(4))
+    np.savetxt(out + "/handbase_in_cam.txt", hic)
+    rng = np.random.default_rng(5)
+    mo, mon = synth._ellipsoid(rng, 60000, *obj_axes)
+    _write_ply(out + "/object.ply", mo.astype(np.float32), mon.astype(np.float32), binary=True)
+    depth = np.full((480, 640), np.inf)
+    part = np.full((480, 640), -1)
+    for k, P in enumerate(dense):
+        d = _splat(P @ hic[:3, :3].T + hic[:3, 3])
+        closer = d < depth
+        depth[closer] = d[closer]; part[closer] = k
+    depth[~np.isfinite(depth)] = 0
+    depth_mm = np.round(depth * 1000 + (depth > 0) * rng.normal(0, 0.3, depth.shape)).astype(np.uint16)
+    cv2.imwrite(out + "/depth.png", depth_mm)
+    r = subprocess.run([MAIN, out + "/cfg.yaml"], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    lines = r.stdout.splitlines()
+    assert "best tf:" in r.stdout and not any("hand model not available" in l for l in lines)
+    # the four reference outputs (main_realdata_auto.cpp:209-221)
+    for f in ("best.obj", "scene_normals.ply", "hand.ply", "model2scene.txt"):
+        assert os.path.exists(os.path.join(out, f)) and os.path.getsize(os.path.join(out, f)) > 0, f
+    # K1 through the preserved entry point: the joint angles of the links it matched
+    got = {}
+    for l in lines:
+        if l.startswith("tf_self "):
+            _, name, c, s = l.split()
+            got[name] = np.rad2deg(np.arctan2(float(s), float(c)))
+    assert set(got) == set(truth)
+    matched = [n for n in truth if abs(got[n]) > 1e-6]
+    assert len(matched) >= 2, (got, r.stdout[-2500:])
+    for n in matched:   # (one view of a 2 x 6 cm link, millimetre depth quantisation: a few degrees)
+        assert abs(got[n] - truth[n]) < 6.0, (n, got, truth, r.stdout[-2500:])
+    # the object pose: ADI below 3 mm
+    est = np.loadtxt(out + "/model2scene.txt")
+    gt = hic @ obj_in_hb
+    sub = mo[::30].astype(np.float64)
+    adi = cKDTree(sub @ gt[:3, :3].T + gt[:3, 3]).query(sub @ est[:3, :3].T + est[:3, 3])[0].mean()
+    assert adi < 3e-3, (adi, r.stdout[-2500:])
+    # scene_normals.ply = the object segment after the hand removal: mostly object points, confidences in [0, 1] and < 1 next to the hand
+    txt = open(out + "/scene_normals.ply").read().split("end_header\n")[1]
+    seg = np.array([[float(v) for v in l.split()] for l in txt.strip().split("\n")])
+    obj_cam = dense[-1] @ hic[:3, :3].T + hic[:3, 3]
+    d_obj = cKDTree(obj_cam[::20]).query(seg[:, :3])[0]
+    assert (d_obj < 0.003).mean() > 0.6, (d_obj < 0.003).mean()
+    conf = seg[:, 6]
+    assert np.all((conf >= 0) & (conf <= 1)) and conf.min() < 0.99 and np.median(conf[d_obj < 0.002]) > 0.5
+    n = seg[:, 3:6]
+    assert np.all(np.einsum("ij,ij->i", n, -seg[:, :3]) >= -1e-6)          # normals towards the camera

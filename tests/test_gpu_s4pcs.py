@@ -127,3 +127,31 @@ def test_full_pipeline_matches_the_reference_pipeline(ctx, name, seed):
     # same winner within the north-star tolerance, or at least no worse against the ground truth than the reference's
     assert (dt[0] <= 1e-3 and dr[0] <= 1.0) or (egt[0] <= egt_ref[0] + 5e-4), (dt, dr, egt, egt_ref)
     assert abs(best._lcp_score - sc[bi]) <= 0.05 * max(sc[bi], 1.0) or best._lcp_score >= sc[bi]
+
+
+@pytest.mark.parametrize("name,seed,nq,ns", [("ellipse", 2, 400, 500), ("cuboid", 3, 400, 2000), ("tless", 4, 1500, 7000)])
+def test_device_assisted_plan_is_bit_identical(ctx, name, seed, nq, ns):
+    """hop_s4pcs_plan_create_gpu: the planner's PPF-membership scans come from the device (a bit matrix of all scene pairs up to 6144
+    points, rows on demand above: the 7000-point case), pairs at a bin boundary are re-evaluated on the host -- the pools, hence the
+    replayed random streams, hence every base and invariant must equal the host planner's bit for bit (which test_s4pcs_plan.py pins
+    against the compiled reference)."""
+    m, mn = synth.make_model(name, nq, seed=1)
+    keys = O.ref_ppf_keys(m[:400], mn[:400])
+    s, sn, conf, gt = synth.make_scene(name, ns, seed=seed)
+    a = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options())
+    b = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(), ctx=ctx)
+    ga, gb = a.get(), b.get()
+    for x, y in zip(ga, gb):
+        assert np.array_equal(np.asarray(x), np.asarray(y))
+    assert a.sizes() == b.sizes() and np.asarray(ga[-2])[:, 0].sum() > 0      # some bases were found
+    a.close(); b.close()
+
+
+@pytest.mark.parametrize("name,n", [("ellipse", 400), ("cuboid", 640), ("tless", 300)])
+def test_device_ppf_table_equals_the_references(ctx, name, n):
+    """hop_ppf_table_build (all-pairs kernel + device sort / unique, boundary pairs on the host) against the reference's own
+    gr::computePPF over all pairs (oracle/_ref): the same set of keys"""
+    m, mn = synth.make_model(name, n, seed=3)
+    got = ctx.ppf_table(m, mn)
+    ref = O.ref_ppf_keys(m, mn)
+    assert got.shape == ref.shape and np.array_equal(got, np.array(sorted(map(tuple, ref.tolist())), np.int32).reshape(-1, 4))
