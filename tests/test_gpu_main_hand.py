@@ -162,7 +162,11 @@ def test_main_realdata_auto_with_the_hand_branch(tmp_path):
     seg = np.array([[float(v) for v in l.split()] for l in txt.strip().split("\n")])
     obj_cam = dense[-1] @ hic[:3, :3].T + hic[:3, 3]
     d_obj = cKDTree(obj_cam[::20]).query(seg[:, :3])[0]
-    assert (d_obj < 0.003).mean() > 0.6, (d_obj < 0.003).mean()
+    # (the fixture's root link is called base_link: like the reference's, it only gets the near_hand_dist = 3 mm margin -- 20 mm is for
+    #  "base" and the swivels, Hand.cpp:816 -- so part of its 5 mm-sampled surface survives the removal; what must go are the fingers)
+    assert (d_obj < 0.003).mean() > 0.3, (d_obj < 0.003).mean()
+    finger_cam = np.concatenate(dense[:4])[::40] @ hic[:3, :3].T + hic[:3, 3]
+    assert (cKDTree(finger_cam).query(seg[:, :3])[0] < 0.002).mean() < 0.25
     conf = seg[:, 6]
     assert np.all((conf >= 0) & (conf <= 1)) and conf.min() < 0.99 and np.median(conf[d_obj < 0.002]) > 0.5
     n = seg[:, 3:6]

@@ -15,30 +15,24 @@ def test_point_to_point_icp_matches_oracle(ctx, name, ns, nm):
     s, sn, conf, gt = synth.make_scene(name, ns, seed=5)
     hyp = synth.make_hypotheses(gt, 48, seed=6, random_frac=0.0, rot_sigma_deg=3.0, trans_sigma=0.003)
     scene, model = ctx.upload_cloud(s, sn, conf), ctx.upload_cloud(m, mn)
-    p = ctx.icp_params(mode=1, max_iter=100, abs_mse_eps=1e-12, max_dist=0.01)
-    got, it, cv = ctx.icp_refine(scene, model, hyp, p)
+    # (1) the trajectory: a fixed number of iterations (the MSE stop disabled) -- same reciprocal correspondences, same Kabsch steps
+    for iters in (1, 5, 20):
+        got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(mode=1, max_iter=iters, abs_mse_eps=0.0, max_dist=0.01))
+        ref, rit, rcv = O.refine_by_icp_p2p(s, m, hyp, max_iter=iters, dist=0.01, abs_mse_eps=0.0)
+        dt, dr = synth.pose_error(got, ref)
+        assert np.array_equal(cv, rcv) and np.array_equal(it, rit)
+        # (one correspondence at a float tie may differ: the scene is queried in the model frame here, the model in the scene frame there)
+        assert np.median(dt) < 1e-6 and dt.max() < 5e-5 and dr.max() < 0.1, (iters, dt.max(), dr.max())
+    # (2) PCL's defaults: up to 100 iterations, stop when |dMSE| < 1e-12 m^2.  Near convergence the MSE of float coordinates moves by
+    # about that much per iteration through rounding alone (the reference re-transforms its cloud in float every iteration), so WHERE a
+    # run stops along the slow final creep is decided by noise -- in the reference as much as here (a numpy emulation of this kernel's
+    # arithmetic reproduces its stop to the iteration).  Same flags, same fixed point for most, all inside the creep band.
+    got, it, cv = ctx.icp_refine(scene, model, hyp, ctx.icp_params(mode=1, max_iter=100, abs_mse_eps=1e-12, max_dist=0.01))
     ref, rit, rcv = O.refine_by_icp_p2p(s, m, hyp, max_iter=100, dist=0.01, abs_mse_eps=1e-12)
     assert np.array_equal(cv, rcv)
-    # The Kabsch step has a closed form and the two runs follow the same correspondences bit for bit (median difference 1e-7 m)
-    # until a float tie flips one.  The reference's stop, |dMSE| < 1e-12 m^2 over up to 100 iterations, then ends a run wherever
-    # the last bits of the MSE settle -- along the weak directions of a partial view that can be tenths of a millimetre apart.
-    # As for mode 0 (tests/parity_util.py) the bound is asserted where the reference's own answer is reproducible: its result
-    # under three 1e-7 m perturbations of the hypothesis stays within 0.25 mm / 0.25 deg.
     dt, dr = synth.pose_error_sym(got, ref, name)
     assert np.median(dt) < 1e-6 and np.median(dr) < 1e-3
-    ok = (dt <= 1e-3) & (dr <= 1.0)
-    close = (dt <= 1e-4) & (dr <= 0.05)
-    if not close.all():
-        rng = np.random.default_rng(0)
-        wt, wr = np.zeros(len(hyp)), np.zeros(len(hyp))
-        for _ in range(3):
-            h2 = hyp.copy(); h2[:, :3, 3] += rng.normal(0, 1e-7, (len(hyp), 3)).astype(np.float32)
-            r2, _, _ = O.refine_by_icp_p2p(s, m, h2, max_iter=100, dist=0.01, abs_mse_eps=1e-12)
-            a, b = synth.pose_error_sym(r2, ref, name)
-            wt, wr = np.maximum(wt, a), np.maximum(wr, b)
-        unstable = ~(wt <= 2.5e-4) | ~(wr <= 0.25)
-        assert np.all(close | unstable), (np.nonzero(~close & ~unstable)[0], dt.max(), dr.max())
-    assert ok.mean() >= 0.9
+    assert np.mean((dt <= 1e-4) & (dr <= 0.05)) >= 0.85 and np.all((dt <= 1.5e-3) & (dr <= 2.0)), (dt.max(), dr.max())
     scene.free(); model.free()
 
 
