@@ -396,6 +396,28 @@ int hop_icp_refine(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, float *pose
   return HOP_OK;
 }
 
+// diagnostics: the inner solver of K4 alone (host buffers)
+int hop_debug_lm_solve(hop_ctx *ctx, const float *sums, int n, float *x_out, int32_t *nfev_out, int32_t *status_out, int64_t *cycles_out) {
+  HOP_ENTER(ctx);
+  if (!ctx || n < 0 || (n > 0 && (!sums || !x_out || !nfev_out || !status_out))) { if (ctx) ctx->err = "hop_debug_lm_solve: bad arguments"; return HOP_EINVAL; }
+  if (n == 0) return HOP_OK;
+  const size_t sb = sizeof(float) * 96 * (size_t)n, xb = sizeof(float) * 6 * (size_t)n, ib = sizeof(int32_t) * (size_t)n, cb = sizeof(long long) * (size_t)n;
+  char *d = (char *)ctx->ensure_io(cb + sb + xb + 2 * ib);
+  if (!d) { ctx->err = "hop_debug_lm_solve: staging allocation failed"; return HOP_ENOMEM; }
+  long long *d_cy = (long long *)d;
+  float *d_sums = (float *)(d + cb), *d_x = (float *)(d + cb + sb);
+  int32_t *d_nf = (int32_t *)(d + cb + sb + xb), *d_st = d_nf + n;
+  HOP_CUDA(ctx, cudaMemcpyAsync(d_sums, sums, sb, cudaMemcpyHostToDevice, ctx->stream));
+  const int rc = hop_debug_lm_solve_launch(ctx, d_sums, n, d_x, d_nf, d_st, cycles_out ? d_cy : nullptr);
+  if (rc != HOP_OK) return rc;
+  HOP_CUDA(ctx, cudaMemcpyAsync(x_out, d_x, xb, cudaMemcpyDeviceToHost, ctx->stream));
+  HOP_CUDA(ctx, cudaMemcpyAsync(nfev_out, d_nf, ib, cudaMemcpyDeviceToHost, ctx->stream));
+  HOP_CUDA(ctx, cudaMemcpyAsync(status_out, d_st, ib, cudaMemcpyDeviceToHost, ctx->stream));
+  if (cycles_out) HOP_CUDA(ctx, cudaMemcpyAsync(cycles_out, d_cy, cb, cudaMemcpyDeviceToHost, ctx->stream));
+  HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return HOP_OK;
+}
+
 // ---- K5 -------------------------------------------------------------------------------------------------------
 int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H, const hop_lcp_params *params,
                       int use_weights, float *d_scores_out) {

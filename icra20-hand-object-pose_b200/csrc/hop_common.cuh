@@ -327,6 +327,7 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
 int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_by_index, const CloudDev &model, const NNGridDev &model_grid,
                    const NNGridDev &scene_grid, const float *d_poses, int H, const hop_lcp_params &p, int use_weights,
                    float *d_scores);
+int hop_debug_lm_solve_launch(hop_ctx *ctx, const float *d_sums, int n, float *d_x, int32_t *d_nfev, int32_t *d_status, long long *d_cycles);
 // implemented in select.cu
 int hop_launch_topk(hop_ctx *ctx, const float *d_poses, const float *d_scores, int H, int K, int32_t id_offset, int32_t frame,
                     hop_pose_rec *d_out);

@@ -33,7 +33,7 @@
 #include <utility>
 
 #include "hop_common.cuh"
-#include "lm_replay.cuh"
+#include "lm_replay_warp.cuh"
 
 namespace {
 
@@ -225,8 +225,8 @@ __device__ __forceinline__ void solve_exact(const float *sums, int lane, float *
 // lm_replay.cuh.  Called by all lanes of one warp; returns the increment W(x) in all lanes.
 __device__ __noinline__ void solve_lm_replay(const float *sums, int lane, lmr::LmrScratch *scr, float *R, float *t) {
   lmr::MomentsDev A{sums, lane, scr};
-  float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  lmr::lm_replay_solve(A, x, nullptr);
+  float x[6];
+  lmr::lm_replay_solve_warp(A, x, nullptr);
   float y[13];
   lmr::warp_y(x, y);
 #pragma unroll
@@ -351,6 +351,10 @@ template <int THREADS>
 __device__ __forceinline__ void correspond_chunk(const CloudDev &scene, const float4 *__restrict__ model_nv, const NNGridDev &grid,
                                                  const Rigid &X, float cos_thr, float max_d2, int c0, int cnt, float4 *rec0,
                                                  float4 *rec1, int tid) {
+  // (one point at a time per thread.  Keeping the same stage of 2 or 4 points in flight -- points, cells, candidate position k of every
+  //  list, winners' normals -- was tried for the small batches that cannot hide the gathers' latency with other warps: bit-identical
+  //  records, but 17.1 -> 25.9 ms at the headline size and 1.51 -> 1.70 ms at C2: the lists advance in lockstep to the longest one and the
+  //  extra live points spill at 64 registers.  gpurun_out/r02p_*)
   for (int i = tid; i < cnt; i += THREADS) {
     const float4 sp = __ldg(&scene.pw[c0 + i]);
     const float3 p = rigid_apply(X, sp.x, sp.y, sp.z);
@@ -1027,6 +1031,35 @@ static void launch_solve(hop_ctx *ctx, const SolveArgs &s, int Hb) {
   icp_solve_kernel<SOLVER><<<(Hb + SOLVE_WARPS - 1) / SOLVE_WARPS, SOLVE_WARPS * 32, 0, ctx->stream>>>(s);
 }
 
+
+// diagnostics: the LM replay on caller-supplied moments, one warp per problem (tests/test_gpu_lm.py pins lm_replay_warp.cuh against
+// the host build of the scalar program)
+__global__ void __launch_bounds__(32) lm_debug_kernel(const float *__restrict__ sums, int n, float *__restrict__ x_out, int32_t *__restrict__ nfev_out,
+                                                       int32_t *__restrict__ status_out, long long *__restrict__ cycles_out) {
+  __shared__ __align__(16) float s_sums[96];
+  __shared__ __align__(16) lmr::LmrScratch s_scr;
+  const int lane = threadIdx.x;
+  for (int p = blockIdx.x; p < n; p += gridDim.x) {
+    __syncwarp();
+    for (int e = lane; e < 96; e += 32) s_sums[e] = sums[(size_t)p * 96 + e];
+    __syncwarp();
+    const lmr::MomentsDev A{s_sums, lane, &s_scr};
+    lmr::moments_prepare(A);
+    float x[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int nfev = 0, status = -1;
+    const long long t0 = clock64();
+    if (!lmr::translation_unconstrained(A)) status = lmr::lm_replay_solve_warp(A, x, &nfev);
+    const long long t1 = clock64();
+    if (lane == 0) {
+      if (cycles_out) cycles_out[p] = t1 - t0;
+#pragma unroll
+      for (int j = 0; j < 6; ++j) x_out[(size_t)p * 6 + j] = x[j];
+      nfev_out[p] = nfev;
+      status_out[p] = status;
+    }
+  }
+}
+
 }  // namespace
 
 int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, const NNGridDev *scene_grid,
@@ -1154,6 +1187,14 @@ int hop_launch_lcp(hop_ctx *ctx, const CloudDev &scene, const float4 *scene_nv_b
     lcp_reduce_kernel<<<(Hb + 127) / 128, 128, 0, ctx->stream>>>(partial, n_tiles, Hb, d_scores + h0);
     ctx->launches += 2;
   }
+  HOP_CUDA(ctx, cudaGetLastError());
+  return HOP_OK;
+}
+
+int hop_debug_lm_solve_launch(hop_ctx *ctx, const float *d_sums, int n, float *d_x, int32_t *d_nfev, int32_t *d_status, long long *d_cycles) {
+  if (n <= 0) return HOP_OK;
+  lm_debug_kernel<<<std::min(n, ctx->sm_count * 16), 32, 0, ctx->stream>>>(d_sums, n, d_x, d_nfev, d_status, d_cycles);
+  ctx->launches += 1;
   HOP_CUDA(ctx, cudaGetLastError());
   return HOP_OK;
 }

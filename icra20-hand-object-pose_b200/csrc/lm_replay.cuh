@@ -36,6 +36,14 @@
 
 namespace lmr {
 
+#if defined(LMR_STATS) && !defined(__CUDA_ARCH__)
+struct Stats { long long solves, outer, trials, lmpar_cold, qrsolv; };   // host-side work counters (tools/lm_replay_eval.py)
+inline Stats &stats() { static Stats s = {0, 0, 0, 0, 0}; return s; }
+#define LMR_COUNT(f) (++lmr::stats().f)
+#else
+#define LMR_COUNT(f) ((void)0)
+#endif
+
 constexpr int N = 6;
 constexpr int NY = 13;
 
@@ -146,11 +154,13 @@ LMR_HD float norm6(const float *v) {
 struct LmrScratch {
   double g[16];        // A y
   double U[12][6];     // rows of A (D h)
-  double G[24];        // the 21 entries of the upper triangle of (D h)^T A (D h)
+  double G[28];        // the 21 entries of the upper triangle of J^T J, then (lm_replay_warp.cuh) the 6 entries of J^T f
   float A[NY * NY];    // the moment matrix, full symmetric storage
   float D[N][12];      // columns of D h: y(x + h_j e_j) - y(x)
   float M[12][N];      // the same, transposed (row i = entry i of every column)
   float h[8];          // the steps h_j
+  float R[N][N];       // lm_replay_warp.cuh: the float Cholesky factor (upper triangle, zeros below)
+  double Gc[8][N];     // lm_replay_warp.cuh: [J^T J | J^T f | 0] by columns, zeros below the diagonal (column k = the 6 numbers lane k owns)
 };
 #define LMR_SCRATCH_BYTES ((int)sizeof(lmr::LmrScratch))
 
@@ -316,6 +326,7 @@ inline void gram(const Moments &A, const float *x, const float *y, const double 
 // MINPACK qrsolv on the 6x6 upper-triangular r (identity column order): least squares of [R; D] z = [qtb; 0].  r's strict
 // lower triangle receives the transposed factor S (lmpar's Newton correction reads it), sdiag its diagonal.
 LMR_COLD void qrsolv(float (*r)[N], const float *diag, const float *qtb, float *x, float *sdiag) {
+  LMR_COUNT(qrsolv);
   float wa[N];
   LMR_ROLL
   for (int j = 0; j < N; ++j) {
@@ -397,6 +408,7 @@ LMR_COLD void lmpar_iterate(float (*r)[N], const float *diag, const float *qtb, 
   float dxnorm = norm6(wa2);
   float fp = dxnorm - delta;
   if (fp <= 0.1f * delta) { par = 0.f; return; }
+  LMR_COUNT(lmpar_cold);
   float parl = 0.f;
   if (nsing >= N) {
     LMR_ROLL
@@ -551,7 +563,9 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
   warp_y(x, y);
   double f2 = quad(A, y, g);
   float fnorm = qsqrt(f2 > 0.0 ? (float)f2 : 0.f);
+  LMR_COUNT(solves);
   for (;;) {
+    LMR_COUNT(outer);
     double G[N][N], b[N];
     float hs[N];
     gram(A, x, y, g, h_eps, G, b, hs);
@@ -613,6 +627,7 @@ LMR_HD int lm_replay_solve(const MomentsT &A, float *x, int *nfev_out) {
     float ratio;
     bool done = false;
     do {
+      LMR_COUNT(trials);
       lmpar(r, diag, qtf, delta, par, wa1);
       LMR_UNROLL
       for (int j = 0; j < N; ++j) { wa1[j] = -wa1[j]; wa2[j] = x[j] + wa1[j]; wa3[j] = diag[j] * wa1[j]; }

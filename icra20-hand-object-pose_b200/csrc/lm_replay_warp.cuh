@@ -1,0 +1,300 @@
+// lm_replay_warp.cuh -- the LM replay of lm_replay.cuh, laid out over the lanes of the calling warp (device only).
+//
+// lm_replay_solve (lm_replay.cuh) is the scalar program: on the device every lane would execute all of it redundantly, ~2.2 k
+// dependent instructions per outer LM iteration with the 6x6 double matrices spilling at the fused kernel's register cap --
+// ~26 k cycles per outer iteration (ncu source page, profiles/r02_*).  The solve is a latency chain, and on small batches the
+// slowest hypothesis' chain IS the kernel time.  Here the 6-vectors and the 6x6 factors are DISTRIBUTED:
+//   lane j (mod 8)  owns parameter j: its diag entry, column j of J^T J through the Cholesky factorisation (lane 6: the column
+//                   J^T f, which the same elimination turns into Q^T f), row j of R for the back substitution;
+//   lane i (mod 16) owns row i of the 13x13 moment matrix (registers) for y^T A y.
+// Scalars of MINPACK's control flow (fnorm, par, delta, ratio ...) are replicated.  Every reduction is an xor butterfly, whose
+// result is bitwise the same in all lanes (a + b == b + a at every level), so the warp never diverges on them.  The float
+// operations of MINPACK's algebra keep the order of the scalar program; sums carried in double (norms, Gram products)
+// associate differently, which moves a float result by at most its last bit.  Rare path -- the Gauss-Newton step leaves the
+// trust region -- is lm_replay.cuh's replicated lmpar_iterate, fed from the factor in shared memory.
+//
+// The scalar program stays the specification: tests/test_gpu_lm.py solves the same moment matrices with this file (through
+// hop_debug_lm_solve) and with the host build of lm_replay.cuh, which tests/test_lm_replay.py pins against the reference tree's
+// own Eigen LM.
+#pragma once
+#include "lm_replay.cuh"
+
+#if defined(__CUDACC__)
+namespace lmr {
+
+__device__ __forceinline__ double bfly_sum16(double v) {
+#pragma unroll
+  for (int o = 8; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double bfly_sum8(double v) {
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float bfly_max8(float v) {
+#pragma unroll
+  for (int o = 4; o >= 1; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// entry l of a replicated short vector (l is lane dependent: a select chain, no local memory)
+template <typename T, int LEN>
+__device__ __forceinline__ T pick(const T (&v)[LEN], int l) {
+  T r = (T)0;
+#pragma unroll
+  for (int j = 0; j < LEN; ++j) r = (l == j) ? v[j] : r;
+  return r;
+}
+// 2-norm of a 6-vector whose entry j sits in lane j (mod 8); lanes 6, 7 pass own = false
+__device__ __forceinline__ float norm6_w(float v, bool own) {
+  const double s = own ? (double)v * (double)v : 0.0;
+  return qsqrt((float)bfly_sum8(s));
+}
+// y^T A y, lane (mod 16) on row l16 of A (shared memory; the loads do not depend on y and issue ahead of the chain);
+// g_own = (A y)_row, 0 on the lanes without a row
+__device__ __forceinline__ double quad_w(const float *Arow, const float (&y)[NY], int l16, double &g_own) {
+  double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+  for (int j = 0; j + 1 < NY; j += 2) {
+    s0 = fma((double)Arow[j], (double)y[j], s0);
+    s1 = fma((double)Arow[j + 1], (double)y[j + 1], s1);
+  }
+  s0 = fma((double)Arow[NY - 1], (double)y[NY - 1], s0);
+  g_own = l16 < NY ? s0 + s1 : 0.0;
+  return bfly_sum16(g_own * (double)pick(y, l16));
+}
+
+// The LM run from x = 0.  All 32 lanes call with the same arguments; A.scr->A must hold the expanded moments (moments_prepare).
+// x_out (6, replicated) receives the minimiser the reference's LM stops at; returns Eigen's LevenbergMarquardtSpace status.
+__device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_out, int *nfev_out) {
+  LmrScratch &S = *A.scr;
+  const unsigned FULL = 0xffffffffu;
+  const int lane = A.lane, l8 = lane & 7, l16 = lane & 15;
+  const bool own6 = l8 < N;
+  const float eps = FLT_EPSILON;
+  const float h_eps = 3.4526698e-4f, ftol = h_eps, xtol = h_eps, gtol = 0.f, factor = 100.f;   // sqrt(FLT_EPSILON)
+  const int maxfev = 400;
+  const float *Ar = S.A + (l16 < NY ? l16 : NY - 1) * NY;   // this lane's row of the moment matrix
+  // this lane's entry of [J^T J | J^T f] in the Gram step: (gj, gk) of the upper triangle for lanes 0..20, J^T f entry gj for 21..26
+  int gj = 0, gk = 0;
+  if (lane < 21) {
+    int l = lane;
+    while (l >= N - gj) { l -= N - gj; ++gj; }
+    gk = gj + l;
+  } else if (lane < 27) gj = gk = lane - 21;
+  double *const g_dst = &S.Gc[gk + (lane >= 21 ? N - gk : 0)][gj];   // where this lane's entry goes: column gk row gj / column 6 row gj
+  const double *const g_col = S.Gc[l8];                              // the column this lane owns in the factorisation
+  for (int e = lane; e < 8 * N; e += 32) (&S.Gc[0][0])[e] = 0.0;    // (only the upper triangle is ever written again)
+  __syncwarp();
+  float x[N] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, y[NY];
+  float dg = 0.f;   // diag[l8]
+  double g_own;
+  int nfev = 1, iter = 1, status = 0;
+  float par = 0.f, delta = 0.f, xnorm = 0.f;
+  warp_y(x, y);
+  const double f2 = quad_w(Ar, y, l16, g_own);
+  float fnorm = qsqrt(f2 > 0.0 ? (float)f2 : 0.f);
+  for (;;) {
+    // ---- forward-difference Jacobian as moments.  Lane j < 6 evaluates W(x + h_j e_j); a translation column of D has the single
+    //      entry (fl(x_j + h) - x_j) / h, a rotation column the nine entries of dR / h ----
+    {
+      float hj = h_eps * fabsf(pick(x, l8));   // lanes 6, 7: x = 0 there, they evaluate W(x + h e_none) = W(x) for nothing
+      if (hj == 0.f) hj = h_eps;
+      const float xp = add(pick(x, l8), hj);
+      float xx[N];
+#pragma unroll
+      for (int k = 0; k < N; ++k) xx[k] = l8 == k ? xp : x[k];
+      float yj[NY];
+      warp_y(xx, yj);
+      __syncwarp();
+      if (lane < N) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) {
+          const float d = sub(yj[i], y[i]);
+          S.D[lane][i] = d;
+          S.M[i][lane] = d;
+        }
+        S.h[lane] = hj;
+      }
+      if (lane < NY) S.g[lane] = g_own;
+      __syncwarp();
+      if (lane < 12) {   // row `lane` of A (D h)
+#pragma unroll
+        for (int cc = 0; cc < 3; ++cc) S.U[lane][cc] = (double)Ar[9 + cc] * (double)S.D[cc][9 + cc];
+        double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+#pragma unroll
+        for (int k = 0; k < 9; ++k) {
+          const double a = (double)Ar[k];
+          u0 = fma(a, (double)S.D[3][k], u0);
+          u1 = fma(a, (double)S.D[4][k], u1);
+          u2 = fma(a, (double)S.D[5][k], u2);
+        }
+        S.U[lane][3] = u0; S.U[lane][4] = u1; S.U[lane][5] = u2;
+      }
+      __syncwarp();
+      if (lane < 27) {
+        double a0 = 0.0, a1 = 0.0, scale;
+        if (lane < 21) {   // (J^T J)(gj, gk) = (D h)_gj . A (D h)_gk / (h_gj h_gk)
+#pragma unroll
+          for (int i = 0; i < 12; i += 2) {
+            a0 = fma((double)S.M[i][gj], S.U[i][gk], a0);
+            a1 = fma((double)S.M[i + 1][gj], S.U[i + 1][gk], a1);
+          }
+          scale = rcp_h(S.h[gj]) * rcp_h(S.h[gk]);
+        } else {           // (J^T f)(gj) = (D h)_gj . (A y) / h_gj   (the entries a column does not have are exact zeros)
+#pragma unroll
+          for (int i = 0; i < 12; i += 2) {
+            a0 = fma((double)S.D[gj][i], S.g[i], a0);
+            a1 = fma((double)S.D[gj][i + 1], S.g[i + 1], a1);
+          }
+          scale = rcp_h(S.h[gj]);
+        }
+        *g_dst = (a0 + a1) * scale;
+      }
+      __syncwarp();
+    }
+    nfev += N + 1;   // NumericalDiff::df (Forward) re-evaluates f(x) first: n + 1 evaluations
+    // ---- column l8 of [J^T J | J^T f] -> column l8 of [R | Q^T f].  R and Q^T f of the QR of J = Cholesky factor of J^T J and
+    //      R^-T J^T f (lm_replay.cuh); right-looking elimination, row i of the factor travels by shuffle ----
+    double c[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) c[i] = g_col[i];
+    const double gdiag = pick(c, l8);   // (J^T J)(l8, l8); 0 on lanes 6, 7
+    const float wa2 = qsqrt(gdiag > 0.0 ? (float)gdiag : 0.f);   // column norm of J
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const double dp = __shfl_sync(FULL, c[i], i);   // the pivot, all earlier rows eliminated
+      double dd, inv;
+      chol_pivot_dev(dp, &dd, &inv);
+      double rik = l8 == i ? dd : c[i] * inv;          // R(i, l8) / (Q^T f)(i); 0 on the lanes left of the pivot
+      if (l8 == N) rik = (double)(float)rik;           // (the scalar program rounds Q^T f to float before it is used below)
+      c[i] = rik;
+#pragma unroll
+      for (int m = i + 1; m < N; ++m) {
+        const double rim = __shfl_sync(FULL, rik, m);  // R(i, m)
+        if (l8 >= m) c[m] = fma(-rim, rik, c[m]);
+      }
+    }
+    float rc[N], qtf[N];
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      rc[i] = (own6 && i <= l8) ? (float)c[i] : 0.f;    // column l8 of r
+      qtf[i] = (float)__shfl_sync(FULL, c[i], N);
+    }
+    __syncwarp();
+    if (lane < N) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) S.R[i][lane] = rc[i];
+    }
+    __syncwarp();
+    float rr[N];   // row l8 of r
+#pragma unroll
+    for (int k = 0; k < N; ++k) rr[k] = own6 ? S.R[l8][k] : 0.f;
+    const float rdiag = pick(rr, l8);
+    if (iter == 1) {
+      dg = own6 ? (wa2 == 0.f ? 1.f : wa2) : 0.f;
+      xnorm = norm6_w(dg * pick(x, l8), own6);
+      delta = factor * xnorm;
+      if (delta == 0.f) delta = factor;
+    }
+    float gnorm = 0.f;
+    if (fnorm != 0.f) {
+      float s = 0.f;
+#pragma unroll
+      for (int i = 0; i < N; ++i)
+        if (i <= l8) s = fmaf(rc[i], qdiv(qtf[i], fnorm), s);
+      gnorm = bfly_max8((own6 && wa2 != 0.f) ? fabsf(qdiv(s, wa2)) : 0.f);
+    }
+    if (gnorm <= gtol) { status = 4; break; }
+    dg = fmaxf(dg, wa2);
+    const float rinv = qdiv(1.f, rdiag);
+    float ratio;
+    bool done = false;
+    do {
+      // ---- lmpar: the Gauss-Newton step and the test that it fits the trust region (then par = 0: the common case) ----
+      float step[N];
+      bool fits = false;
+      if (__all_sync(FULL, !own6 || rdiag != 0.f)) {
+        float acc = pick(qtf, l8);
+#pragma unroll
+        for (int k = N - 1; k >= 0; --k) {
+          step[k] = __shfl_sync(FULL, acc * rinv, k);
+          if (l8 < k) acc = fmaf(-rr[k], step[k], acc);
+        }
+        const float fp = norm6_w(dg * pick(step, l8), own6) - delta;
+        fits = fp <= 0.1f * delta;
+      }
+      if (fits) par = 0.f;
+      else {
+        float rc2[N][N], dc[N], qc[N];
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          dc[i] = __shfl_sync(FULL, dg, i);
+          qc[i] = qtf[i];
+#pragma unroll
+          for (int j = 0; j < N; ++j) rc2[i][j] = S.R[i][j];
+        }
+        lmpar_iterate(rc2, dc, qc, delta, par, step);
+      }
+      float x1[N];   // p = -step
+#pragma unroll
+      for (int j = 0; j < N; ++j) x1[j] = x[j] + -step[j];
+      const float pnorm = norm6_w(dg * -pick(step, l8), own6);
+      if (iter == 1) delta = fminf(delta, pnorm);
+      float y1[NY];
+      double g1_own;
+      warp_y(x1, y1);
+      const double f21 = quad_w(Ar, y1, l16, g1_own);
+      ++nfev;
+      const float fnorm1 = qsqrt(f21 > 0.0 ? (float)f21 : 0.f);
+      float actred = -1.f;
+      if (0.1f * fnorm1 < fnorm) { const float q = qdiv(fnorm1, fnorm); actred = 1.f - q * q; }
+      float rp = 0.f;   // (R p)(l8)
+#pragma unroll
+      for (int j = 0; j < N; ++j)
+        if (j >= l8) rp = fmaf(rr[j], -step[j], rp);
+      float t1 = qdiv(norm6_w(rp, own6), fnorm); t1 *= t1;
+      float t2 = qdiv(qsqrt(par) * pnorm, fnorm); t2 *= t2;
+      const float prered = t1 + qdiv(t2, 0.5f);
+      const float dirder = -(t1 + t2);
+      ratio = 0.f;
+      if (prered != 0.f) ratio = qdiv(actred, prered);
+      if (ratio <= 0.25f) {
+        float temp = 0.5f;
+        if (actred < 0.f) temp = qdiv(0.5f * dirder, dirder + 0.5f * actred);
+        if (0.1f * fnorm1 >= fnorm || temp < 0.1f) temp = 0.1f;
+        delta = temp * fminf(delta, qdiv(pnorm, 0.1f));
+        par = qdiv(par, temp);
+      } else if (!(par != 0.f && ratio < 0.75f)) {
+        delta = qdiv(pnorm, 0.5f);
+        par = 0.5f * par;
+      }
+      if (ratio >= 1e-4f) {
+#pragma unroll
+        for (int j = 0; j < N; ++j) x[j] = x1[j];
+#pragma unroll
+        for (int i = 0; i < NY; ++i) y[i] = y1[i];
+        g_own = g1_own;
+        xnorm = norm6_w(dg * pick(x, l8), own6);
+        fnorm = fnorm1;
+        ++iter;
+      }
+      const bool small_f = fabsf(actred) <= ftol && prered <= ftol && 0.5f * ratio <= 1.f;
+      if (small_f && delta <= xtol * xnorm) { status = 3; done = true; break; }
+      if (small_f) { status = 1; done = true; break; }
+      if (delta <= xtol * xnorm) { status = 2; done = true; break; }
+      if (nfev >= maxfev) { status = 5; done = true; break; }
+      if (fabsf(actred) <= eps && prered <= eps && 0.5f * ratio <= 1.f) { status = 6; done = true; break; }
+      if (delta <= eps * xnorm) { status = 7; done = true; break; }
+      if (gnorm <= eps) { status = 8; done = true; break; }
+    } while (ratio < 1e-4f);
+    if (done) break;
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) x_out[j] = x[j];
+  if (nfev_out) *nfev_out = nfev;
+  return status;
+}
+
+}  // namespace lmr
+#endif  // __CUDACC__

@@ -196,6 +196,7 @@ def load_library():
                                               C.c_int32, C.c_int32, _vp, _vp, _vp, _vp]
     L.hop_s4pcs_plan_create_gpu.argtypes = [_vp, _vp, _vp, _vp, C.c_int, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(S4pcsOptions), C.POINTER(_vp)]
     L.hop_ppf_table_build.argtypes = [_vp, _vp, _vp, C.c_int, _vp, C.c_int, C.POINTER(C.c_int32)]
+    L.hop_debug_lm_solve.argtypes = [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]
     L.hop_frame_organized.argtypes = [_vp, _vp, C.c_int, C.c_int, C.POINTER(FrameParams), C.c_float, C.c_float, C.POINTER(_vp)]
     L.hop_cloud_mls.argtypes = [_vp, _vp, C.c_float, C.POINTER(_vp)]
     L.hop_comm_unique_id.argtypes = [_vp]
@@ -616,6 +617,16 @@ class Context:
             scene.n = n
             return scene, counts
         return Cloud(self, handle, n), counts
+
+    def debug_lm_solve(self, sums, with_cycles=False):
+        """K4's inner solver alone on n moment sets (n x 96 float32: the packed upper triangle of the 13x13 moment matrix + 5 unused).
+        Returns (x [n, 6], nfev [n], status [n]); status -1 = translation unconstrained."""
+        sums = np.ascontiguousarray(sums, np.float32).reshape(-1, 96)
+        n = len(sums)
+        x = np.zeros((n, 6), np.float32); nfev = np.zeros(n, np.int32); st = np.zeros(n, np.int32)
+        cyc = np.zeros(n, np.int64)
+        self._check(self.L.hop_debug_lm_solve(self.h, sums.ctypes.data, n, x.ctypes.data, nfev.ctypes.data, st.ctypes.data, cyc.ctypes.data if with_cycles else None))
+        return (x, nfev, st, cyc) if with_cycles else (x, nfev, st)
 
     def ppf_table(self, xyz, nrm):
         """the model's PPF table (computePPF.cpp:56-107) on the device: distinct keys (n, 4) int32, sorted"""

@@ -111,6 +111,12 @@ int64_t hop_launch_count(const hop_ctx *ctx);
 int hop_profile_enable(hop_ctx *ctx, int on);  /* also resets the accumulated numbers */
 /* synchronises the stream, folds the finished spans in, returns accumulated milliseconds and span count of `kind` */
 int hop_profile_read(hop_ctx *ctx, int kind, double *total_ms, int64_t *spans);
+/* diagnostics: K4's inner solver alone -- the replay of the reference's LM (TransformationEstimationPointToPlane, PCL 1.9, as
+ * Utils.cpp:188-229 runs it) on n caller-supplied moment sets.  sums: n x 96 floats, the packed upper triangle of the 13x13 moment
+ * matrix (91, row-major) + 5 unused; x_out: n x 6 (translation, quaternion vector part); status_out: Eigen's LevenbergMarquardtSpace
+ * status, -1 when the translation is unconstrained (the kernel then ends the hypothesis "not converged"); cycles_out (may be NULL):
+ * SM clock cycles of each solve.  Host buffers. */
+int hop_debug_lm_solve(hop_ctx *ctx, const float *sums, int n, float *x_out, int32_t *nfev_out, int32_t *status_out, int64_t *cycles_out);
 void hop_default_icp_params(hop_icp_params *p);
 void hop_default_lcp_params(hop_lcp_params *p);
 

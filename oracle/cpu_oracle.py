@@ -232,6 +232,12 @@ def warp6d(x):
     return colmajor_to_poses(T)[0]
 
 
+def warp_y13(x):
+    """y(x) = [vec(R(x)) - vec(I); t(x); 1] of csrc/lm_replay.cuh, from the oracle's WarpPointRigid6D (float64 array of 13)."""
+    T = warp6d(x).astype(np.float64)
+    return np.concatenate([(T[:3, :3] - np.eye(3)).reshape(-1), T[:3, 3], [1.0]])
+
+
 def run_icp(src_xyz, src_nrm, tgt_xyz, tgt_nrm, max_iter=10, angle=45.0, dist=0.01, abs_mse_eps=1e-6):
     src_xyz, src_nrm, tgt_xyz, tgt_nrm = _c(src_xyz), _c(src_nrm), _c(tgt_xyz), _c(tgt_nrm)
     T = np.empty(16, np.float32)

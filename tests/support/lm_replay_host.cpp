@@ -3,6 +3,7 @@
 // Same signature as the oracle's LM backend hook (hop_oracle_set_lm_backend), so a whole oracle ICP can be run with it.
 #include <cstdlib>
 #include <cstring>
+#define LMR_STATS 1
 #include "../../icra20-hand-object-pose_b200/csrc/lm_replay.cuh"
 
 static int g_acc_mode = 0;  // 0: float, 256 interleaved partial sums (like the kernel's lanes) 1: float sequential 2: double
@@ -59,4 +60,12 @@ extern "C" int hop_lmr_point_to_plane(const float *src, const float *tgt, const 
   double A13[169];
   hop_lmr_moments(src, tgt, nrm, m, A13);
   return hop_lmr_solve_moments(A13, x, nfev);
+}
+
+// work counters of the solves since the last reset: {solves, outer iterations, trial steps, lmpar calls that left the Gauss-Newton
+// step (MINPACK's iteration on the LM parameter), qrsolv calls}
+extern "C" void hop_lmr_stats(long long *out5, int reset) {
+  lmr::Stats &s = lmr::stats();
+  out5[0] = s.solves; out5[1] = s.outer; out5[2] = s.trials; out5[3] = s.lmpar_cold; out5[4] = s.qrsolv;
+  if (reset) s = lmr::Stats{0, 0, 0, 0, 0};
 }
