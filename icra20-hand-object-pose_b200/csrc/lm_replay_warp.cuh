@@ -10,8 +10,10 @@
 // Scalars of MINPACK's control flow (fnorm, par, delta, ratio ...) are replicated.  Every reduction is an xor butterfly, whose
 // result is bitwise the same in all lanes (a + b == b + a at every level), so the warp never diverges on them.  The float
 // operations of MINPACK's algebra keep the order of the scalar program; sums carried in double (norms, Gram products)
-// associate differently, which moves a float result by at most its last bit.  Rare path -- the Gauss-Newton step leaves the
-// trust region -- is lm_replay.cuh's replicated lmpar_iterate, fed from the factor in shared memory.
+// associate differently, which moves a float result by at most its last bit.  lmpar's iteration on the LM parameter (the Gauss-Newton step
+// leaves the trust region: 3 % of the trial steps, but most of those of the hardest hypotheses, where the replicated rolled
+// version cost 15-30 k cycles per qrsolv) is distributed the same way; only a rank-deficient R falls back to lm_replay.cuh's
+// scalar lmpar_iterate, fed from the factor in shared memory.
 //
 // The scalar program stays the specification: tests/test_gpu_lm.py solves the same moment matrices with this file (through
 // hop_debug_lm_solve) and with the host build of lm_replay.cuh, which tests/test_lm_replay.py pins against the reference tree's
@@ -62,6 +64,121 @@ __device__ __forceinline__ double quad_w(const float *Arow, const float (&y)[NY]
   s0 = fma((double)Arow[NY - 1], (double)y[NY - 1], s0);
   g_own = l16 < NY ? s0 + s1 : 0.0;
   return bfly_sum16(g_own * (double)pick(y, l16));
+}
+
+// MINPACK qrsolv, lane i (mod 8) on row i of the lower triangle: least squares of [R; D] z = [Q^T f; 0].  In: s[k] = R(k, i) for k < i
+// (row i of R^T), rd = R(i, i), dd = D(i), wa = (Q^T f)(i).  Out: s[k] = S(i, k) for k < i, sdiag = S(i, i), wa = z(i).
+// The Givens rotation of step (j, k) is computed by every lane from the two broadcast numbers it depends on; lane k applies it to
+// its diagonal, lanes i > k to their column-k entry.  Same rotations in the same order as the scalar qrsolv.
+__device__ __forceinline__ void qrsolv_w(float (&s)[N], float rd, float dd, float &wa, float &sdiag, int l8, bool own6) {
+  const unsigned FULL = 0xffffffffu;
+  float sd = 0.f;
+#pragma unroll 1
+  for (int j = 0; j < N; ++j) {
+    const float dj = __shfl_sync(FULL, dd, j);
+    if (dj == 0.f) continue;
+    sd = l8 == j ? dj : 0.f;   // sdiag[j] = diag[j], sdiag[k > j] = 0 (entries left of j are final and not read again)
+    float qtbpj = 0.f;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      if (k < j) continue;
+      const float sdk = __shfl_sync(FULL, sd, k);
+      if (sdk == 0.f) continue;
+      const float rkk = __shfl_sync(FULL, rd, k), wak = __shfl_sync(FULL, wa, k);
+      float sn, cs;
+      if (fabsf(rkk) < fabsf(sdk)) { const float ct = qdiv(rkk, sdk); sn = qdiv(0.5f, qsqrt(0.25f + 0.25f * ct * ct)); cs = sn * ct; }
+      else { const float tn = qdiv(sdk, rkk); cs = qdiv(0.5f, qsqrt(0.25f + 0.25f * tn * tn)); sn = cs * tn; }
+      const float tmp = cs * wak + sn * qtbpj;
+      qtbpj = -sn * wak + cs * qtbpj;
+      if (l8 == k) { rd = cs * rkk + sn * sdk; wa = tmp; }
+      if (l8 > k) {
+        const float t2 = cs * s[k] + sn * sd;
+        sd = -sn * s[k] + cs * sd;
+        s[k] = t2;
+      }
+    }
+  }
+  sdiag = rd;   // (a column whose D entry is 0 keeps R's diagonal, as in the scalar program)
+  const unsigned sing = __ballot_sync(FULL, own6 && sdiag == 0.f) & 0x3fu;
+  const int nsing = sing ? __ffs((int)sing) - 1 : N;
+  if (l8 >= nsing) wa = 0.f;
+#pragma unroll
+  for (int j = N - 1; j >= 0; --j) {
+    const float pj = s[j] * wa;   // S(i, j) z(i) on lanes i > j (their z is final)
+    float sum = 0.f;
+#pragma unroll
+    for (int i = j + 1; i < N; ++i) sum += __shfl_sync(FULL, pj, i);
+    if (l8 == j && j < nsing) wa = qdiv(wa - sum, sdiag);
+  }
+}
+
+// MINPACK lmpar beyond the Gauss-Newton step (full-rank R): the iteration on the LM parameter, distributed like the rest.
+// rc = column l8 of R, rd = R(l8, l8), dg = diag(l8), qtf replicated; step (replicated) holds the Gauss-Newton step on entry and the
+// LM step on exit; dxnorm = |D step| of the Gauss-Newton step.
+__device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, float dg, const float (&qtf)[N], float delta, float dxnorm, float &par,
+                                                float (&step)[N], int l8, bool own6) {
+  const unsigned FULL = 0xffffffffu;
+  const float dwarf = FLT_MIN;
+  float fp = dxnorm - delta;
+  float xj = pick(step, l8);        // x(l8)
+  float wa2 = dg * xj;
+  // parl: |R^-T D^2 x / |D x||^-2 scaled (Newton step on phi at par = 0)
+  float parl;
+  {
+    const float w = dg * qdiv(wa2, dxnorm);
+    float sum = 0.f, fin_own = 0.f;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+      const float fin = qdiv(w - sum, rd);                 // final on lane i: its sum over the rows above is complete
+      const float vi = __shfl_sync(FULL, fin, i);
+      if (l8 == i) fin_own = fin;
+      if (l8 > i) sum = fmaf(rc[i], vi, sum);
+    }
+    const float t = norm6_w(fin_own, own6);
+    parl = qdiv(qdiv(qdiv(fp, delta), t), t);
+  }
+  float gs = 0.f;
+#pragma unroll
+  for (int i = 0; i < N; ++i)
+    if (i <= l8) gs = fmaf(rc[i], qtf[i], gs);
+  const float gnorm = norm6_w(own6 ? qdiv(gs, dg) : 0.f, own6);
+  float paru = qdiv(gnorm, delta);
+  if (paru == 0.f) paru = qdiv(dwarf, fminf(delta, 0.1f));
+  par = fmaxf(par, parl);
+  par = fminf(par, paru);
+  if (par == 0.f) par = qdiv(gnorm, dxnorm);
+  const float qtf_own = pick(qtf, l8);
+  int iter = 0;
+  for (;;) {
+    ++iter;
+    if (par == 0.f) par = fmaxf(dwarf, 0.001f * paru);
+    const float sq = qsqrt(par);
+    float s[N], wa = own6 ? qtf_own : 0.f, sdiag;
+#pragma unroll
+    for (int k = 0; k < N; ++k) s[k] = k < l8 ? rc[k] : 0.f;
+    qrsolv_w(s, rd, own6 ? sq * dg : 0.f, wa, sdiag, l8, own6);
+    xj = wa;
+    wa2 = dg * xj;
+    dxnorm = norm6_w(wa2, own6);
+    const float temp0 = fp;
+    fp = dxnorm - delta;
+    if (fabsf(fp) <= 0.1f * delta || (parl == 0.f && fp <= temp0 && temp0 < 0.f) || iter == 10) break;
+    float w = dg * qdiv(wa2, dxnorm), fin_own = 0.f;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+      const float fin = qdiv(w, sdiag);                    // final on lane j
+      const float t = __shfl_sync(FULL, fin, j);
+      if (l8 == j) fin_own = fin;
+      if (l8 > j) w = fmaf(-s[j], t, w);
+    }
+    const float temp = norm6_w(fin_own, own6);
+    const float parc = qdiv(qdiv(qdiv(fp, delta), temp), temp);
+    if (fp > 0.f) parl = fmaxf(parl, par);
+    if (fp < 0.f) paru = fminf(paru, par);
+    par = fmaxf(parl, par + parc);
+  }
+#pragma unroll
+  for (int j = 0; j < N; ++j) step[j] = __shfl_sync(FULL, xj, j);
 }
 
 // The LM run from x = 0.  All 32 lanes call with the same arguments; A.scr->A must hold the expanded moments (moments_prepare).
@@ -213,7 +330,6 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
     do {
       // ---- lmpar: the Gauss-Newton step and the test that it fits the trust region (then par = 0: the common case) ----
       float step[N];
-      bool fits = false;
       if (__all_sync(FULL, !own6 || rdiag != 0.f)) {
         float acc = pick(qtf, l8);
 #pragma unroll
@@ -221,11 +337,10 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
           step[k] = __shfl_sync(FULL, acc * rinv, k);
           if (l8 < k) acc = fmaf(-rr[k], step[k], acc);
         }
-        const float fp = norm6_w(dg * pick(step, l8), own6) - delta;
-        fits = fp <= 0.1f * delta;
-      }
-      if (fits) par = 0.f;
-      else {
+        const float dxnorm = norm6_w(dg * pick(step, l8), own6);
+        if (dxnorm - delta <= 0.1f * delta) par = 0.f;
+        else lmpar_iterate_w(rc, rdiag, dg, qtf, delta, dxnorm, par, step, l8, own6);
+      } else {   // rank-deficient R (a zero pivot): the scalar program, from the factor in shared memory
         float rc2[N][N], dc[N], qc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
