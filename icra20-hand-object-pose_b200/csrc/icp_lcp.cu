@@ -747,8 +747,8 @@ struct __align__(16) FusedSlot {
 // hypothesis per CTA), then ALL solves of the round at once, warp w on slot w.  The per-iteration solve is the reference's serial
 // LM (lm_replay.cuh: tens of thousands of dependent cycles); with one hypothesis per CTA the other warps idle through it (59 %
 // of the CTA's cycles at 2 k scene points, 19 % at 10 k), with slots it costs 1/THREADS*32 of that per hypothesis.  A slot that
-// finishes takes the next hypothesis of the queue at the start of the next round.  slots_max (host) = fair share of the batch
-// per CTA, so a small batch still spreads over every SM instead of filling the slots of the first CTAs.
+// finishes takes the next hypothesis of the queue at the start of the next round.  slots_max (host, launch_fused) never exceeds the
+// fair share of the batch per CTA, so a small batch still spreads over every SM instead of filling the slots of the first CTAs.
 template <int THREADS, int CHUNK, bool PROF, int MINB, int SOLVER>
 __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
   constexpr int NW = THREADS / 32, SZ = 96 / NW;
@@ -918,8 +918,12 @@ static cudaError_t launch_fused(hop_ctx *ctx, FusedArgs f, int H) {
   cudaError_t e = ctx->func_smem_optin(icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER>, smem);
   if (e != cudaSuccess) return e;
   const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * MINB);
+  // Slots per CTA.  Since the solve became short against a pass over the scene (lm_replay_warp.cuh) the parallel solves of a round buy
+  // less than its barrier costs (every slot waits for the round's longest solve): 128-thread CTAs carry at most two hypotheses, and a
+  // 256-thread CTA with three or fewer to do takes them one after the other (C2: 0.96 -> 0.85 ms, headline 16.2 -> 16.0, gpurun_out/r02s_*)
   const int fair = (H + grid_ctas - 1) / grid_ctas;
-  f.slots_max = ctx->tune.fused_slots > 0 ? ctx->tune.fused_slots : fair;
+  const int slots = THREADS == 128 ? std::min(fair, 2) : (fair <= 3 ? 1 : fair);
+  f.slots_max = ctx->tune.fused_slots > 0 ? ctx->tune.fused_slots : slots;
   icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER><<<grid_ctas, THREADS, smem, ctx->stream>>>(f);
   return cudaGetLastError();
 }
@@ -930,9 +934,6 @@ static cudaError_t launch_fused(hop_ctx *ctx, FusedArgs f, int H) {
 // thread: the rest of the 256 KB stays L1.
 template <int SOLVER>
 static cudaError_t launch_fused_solver(hop_ctx *ctx, const FusedArgs &f, int H, bool small_ctas, bool prof_on) {
-  if constexpr (SOLVER == 0) {   // experiment (HOP_FUSED_VARIANT=3): 256-thread CTAs, four per SM at 64 registers
-    if (ctx->tune.fused_variant == 3 && !prof_on) return launch_fused<256, 1024, false, 4, SOLVER>(ctx, f, H);
-  }
   if (prof_on) return small_ctas ? launch_fused<128, 512, true, 6, SOLVER>(ctx, f, H) : launch_fused<256, 1024, true, 3, SOLVER>(ctx, f, H);
   return small_ctas ? launch_fused<128, 512, false, 8, SOLVER>(ctx, f, H) : launch_fused<256, 1024, false, 3, SOLVER>(ctx, f, H);
 }

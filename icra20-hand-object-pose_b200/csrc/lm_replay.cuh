@@ -160,6 +160,7 @@ struct LmrScratch {
   float M[12][N];      // the same, transposed (row i = entry i of every column)
   float h[8];          // the steps h_j
   float R[N][N];       // lm_replay_warp.cuh: the float Cholesky factor (upper triangle, zeros below)
+  double nb[2][8];     // lm_replay_warp.cuh: the squares of a distributed 6-vector on their way to its norm (double buffered)
   double Gc[8][N];     // lm_replay_warp.cuh: [J^T J | J^T f | 0] by columns, zeros below the diagonal (column k = the 6 numbers lane k owns)
 };
 #define LMR_SCRATCH_BYTES ((int)sizeof(lmr::LmrScratch))

@@ -47,10 +47,22 @@ __device__ __forceinline__ T pick(const T (&v)[LEN], int l) {
   for (int j = 0; j < LEN; ++j) r = (l == j) ? v[j] : r;
   return r;
 }
-// 2-norm of a 6-vector whose entry j sits in lane j (mod 8); lanes 6, 7 pass own = false
-__device__ __forceinline__ float norm6_w(float v, bool own) {
-  const double s = own ? (double)v * (double)v : 0.0;
-  return qsqrt((float)bfly_sum8(s));
+// 2-norm of a 6-vector whose entry j sits in lane j (mod 8).  The squares meet in shared memory and every lane adds them in index
+// order (the scalar program's norm6; bitwise the same in all lanes): 13 instructions against 30 for a butterfly of 64-bit shuffles.
+// Two buffers in turn: the barrier of call n + 1 separates the reads of call n from the writes of call n + 2.
+struct NormBuf {
+  double (*nb)[8];
+  int tog;
+};
+__device__ __forceinline__ float norm6_w(float v, int lane, NormBuf &B) {
+  double *b = B.nb[B.tog];
+  B.tog ^= 1;
+  if (lane < N) b[lane] = (double)v * (double)v;
+  __syncwarp();
+  double s = b[0];
+#pragma unroll
+  for (int i = 1; i < N; ++i) s += b[i];
+  return qsqrt((float)s);
 }
 // y^T A y, lane (mod 16) on row l16 of A (shared memory; the loads do not depend on y and issue ahead of the chain);
 // g_own = (A y)_row, 0 on the lanes without a row
@@ -116,8 +128,10 @@ __device__ __forceinline__ void qrsolv_w(float (&s)[N], float rd, float dd, floa
 // rc = column l8 of R, rd = R(l8, l8), dg = diag(l8), qtf replicated; step (replicated) holds the Gauss-Newton step on entry and the
 // LM step on exit; dxnorm = |D step| of the Gauss-Newton step.
 __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, float dg, const float (&qtf)[N], float delta, float dxnorm, float &par,
-                                                float (&step)[N], int l8, bool own6) {
+                                                float (&step)[N], int lane, NormBuf &NB) {
   const unsigned FULL = 0xffffffffu;
+  const int l8 = lane & 7;
+  const bool own6 = l8 < N;
   const float dwarf = FLT_MIN;
   float fp = dxnorm - delta;
   float xj = pick(step, l8);        // x(l8)
@@ -134,14 +148,14 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
       if (l8 == i) fin_own = fin;
       if (l8 > i) sum = fmaf(rc[i], vi, sum);
     }
-    const float t = norm6_w(fin_own, own6);
+    const float t = norm6_w(fin_own, lane, NB);
     parl = qdiv(qdiv(qdiv(fp, delta), t), t);
   }
   float gs = 0.f;
 #pragma unroll
   for (int i = 0; i < N; ++i)
     if (i <= l8) gs = fmaf(rc[i], qtf[i], gs);
-  const float gnorm = norm6_w(own6 ? qdiv(gs, dg) : 0.f, own6);
+  const float gnorm = norm6_w(own6 ? qdiv(gs, dg) : 0.f, lane, NB);
   float paru = qdiv(gnorm, delta);
   if (paru == 0.f) paru = qdiv(dwarf, fminf(delta, 0.1f));
   par = fmaxf(par, parl);
@@ -159,7 +173,7 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
     qrsolv_w(s, rd, own6 ? sq * dg : 0.f, wa, sdiag, l8, own6);
     xj = wa;
     wa2 = dg * xj;
-    dxnorm = norm6_w(wa2, own6);
+    dxnorm = norm6_w(wa2, lane, NB);
     const float temp0 = fp;
     fp = dxnorm - delta;
     if (fabsf(fp) <= 0.1f * delta || (parl == 0.f && fp <= temp0 && temp0 < 0.f) || iter == 10) break;
@@ -171,7 +185,7 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
       if (l8 == j) fin_own = fin;
       if (l8 > j) w = fmaf(-s[j], t, w);
     }
-    const float temp = norm6_w(fin_own, own6);
+    const float temp = norm6_w(fin_own, lane, NB);
     const float parc = qdiv(qdiv(qdiv(fp, delta), temp), temp);
     if (fp > 0.f) parl = fmaxf(parl, par);
     if (fp < 0.f) paru = fminf(paru, par);
@@ -188,6 +202,7 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
   const unsigned FULL = 0xffffffffu;
   const int lane = A.lane, l8 = lane & 7, l16 = lane & 15;
   const bool own6 = l8 < N;
+  NormBuf NB{S.nb, 0};
   const float eps = FLT_EPSILON;
   const float h_eps = 3.4526698e-4f, ftol = h_eps, xtol = h_eps, gtol = 0.f, factor = 100.f;   // sqrt(FLT_EPSILON)
   const int maxfev = 400;
@@ -272,45 +287,47 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
     }
     nfev += N + 1;   // NumericalDiff::df (Forward) re-evaluates f(x) first: n + 1 evaluations
     // ---- column l8 of [J^T J | J^T f] -> column l8 of [R | Q^T f].  R and Q^T f of the QR of J = Cholesky factor of J^T J and
-    //      R^-T J^T f (lm_replay.cuh); right-looking elimination, row i of the factor travels by shuffle ----
-    double c[N];
+    //      R^-T J^T f (lm_replay.cuh); right-looking elimination, row i of the factor travels through shared memory ----
+    double c[N], dgl[N];   // dgl: the diagonal of the block still to eliminate, replicated (every lane sees every row of the factor go by)
 #pragma unroll
-    for (int i = 0; i < N; ++i) c[i] = g_col[i];
+    for (int i = 0; i < N; ++i) { c[i] = g_col[i]; dgl[i] = S.Gc[i][i]; }
     const double gdiag = pick(c, l8);   // (J^T J)(l8, l8); 0 on lanes 6, 7
     const float wa2 = qsqrt(gdiag > 0.0 ? (float)gdiag : 0.f);   // column norm of J
 #pragma unroll
     for (int i = 0; i < N; ++i) {
-      const double dp = __shfl_sync(FULL, c[i], i);   // the pivot, all earlier rows eliminated
       double dd, inv;
-      chol_pivot_dev(dp, &dd, &inv);
+      chol_pivot_dev(dgl[i], &dd, &inv);               // the pivot: all earlier rows eliminated
       double rik = l8 == i ? dd : c[i] * inv;          // R(i, l8) / (Q^T f)(i); 0 on the lanes left of the pivot
       if (l8 == N) rik = (double)(float)rik;           // (the scalar program rounds Q^T f to float before it is used below)
       c[i] = rik;
+      if (i + 1 < N) {
+        if (lane > i && lane < N) S.U[i][lane] = rik;  // row i of the factor, right of the pivot (S.U is idle after the Gram step)
+        __syncwarp();
 #pragma unroll
-      for (int m = i + 1; m < N; ++m) {
-        const double rim = __shfl_sync(FULL, rik, m);  // R(i, m)
-        if (l8 >= m) c[m] = fma(-rim, rik, c[m]);
+        for (int m = i + 1; m < N; ++m) {
+          const double rim = S.U[i][m];                // R(i, m)
+          if (l8 >= m) c[m] = fma(-rim, rik, c[m]);
+          dgl[m] = fma(-rim, rim, dgl[m]);
+        }
       }
     }
-    float rc[N], qtf[N];
+    float rc[N], qtf[N], rr[N];   // column l8 of r, Q^T f (replicated), row l8 of r
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      rc[i] = (own6 && i <= l8) ? (float)c[i] : 0.f;    // column l8 of r
-      qtf[i] = (float)__shfl_sync(FULL, c[i], N);
+    for (int i = 0; i < N; ++i) rc[i] = (own6 && i <= l8) ? (float)c[i] : 0.f;
+    if (lane == N) {
+#pragma unroll
+      for (int i = 0; i < N; ++i) S.h[i] = (float)c[i];   // (the steps h_j are not read again before the next Gram step rewrites them)
     }
     __syncwarp();
-    if (lane < N) {
+    const float rdiag = pick(rc, l8);
 #pragma unroll
-      for (int i = 0; i < N; ++i) S.R[i][lane] = rc[i];
+    for (int k = 0; k < N; ++k) {
+      qtf[k] = S.h[k];
+      rr[k] = (own6 && k > l8) ? (float)S.U[l8 < N ? l8 : 0][k] : (k == l8 ? rdiag : 0.f);
     }
-    __syncwarp();
-    float rr[N];   // row l8 of r
-#pragma unroll
-    for (int k = 0; k < N; ++k) rr[k] = own6 ? S.R[l8][k] : 0.f;
-    const float rdiag = pick(rr, l8);
     if (iter == 1) {
       dg = own6 ? (wa2 == 0.f ? 1.f : wa2) : 0.f;
-      xnorm = norm6_w(dg * pick(x, l8), own6);
+      xnorm = norm6_w(dg * pick(x, l8), lane, NB);
       delta = factor * xnorm;
       if (delta == 0.f) delta = factor;
     }
@@ -337,10 +354,16 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
           step[k] = __shfl_sync(FULL, acc * rinv, k);
           if (l8 < k) acc = fmaf(-rr[k], step[k], acc);
         }
-        const float dxnorm = norm6_w(dg * pick(step, l8), own6);
+        const float dxnorm = norm6_w(dg * pick(step, l8), lane, NB);
         if (dxnorm - delta <= 0.1f * delta) par = 0.f;
-        else lmpar_iterate_w(rc, rdiag, dg, qtf, delta, dxnorm, par, step, l8, own6);
+        else lmpar_iterate_w(rc, rdiag, dg, qtf, delta, dxnorm, par, step, lane, NB);
       } else {   // rank-deficient R (a zero pivot): the scalar program, from the factor in shared memory
+        __syncwarp();
+        if (lane < N) {
+#pragma unroll
+          for (int i = 0; i < N; ++i) S.R[i][lane] = rc[i];
+        }
+        __syncwarp();
         float rc2[N][N], dc[N], qc[N];
 #pragma unroll
         for (int i = 0; i < N; ++i) {
@@ -354,7 +377,7 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
       float x1[N];   // p = -step
 #pragma unroll
       for (int j = 0; j < N; ++j) x1[j] = x[j] + -step[j];
-      const float pnorm = norm6_w(dg * -pick(step, l8), own6);
+      const float pnorm = norm6_w(dg * -pick(step, l8), lane, NB);
       if (iter == 1) delta = fminf(delta, pnorm);
       float y1[NY];
       double g1_own;
@@ -368,7 +391,7 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
 #pragma unroll
       for (int j = 0; j < N; ++j)
         if (j >= l8) rp = fmaf(rr[j], -step[j], rp);
-      float t1 = qdiv(norm6_w(rp, own6), fnorm); t1 *= t1;
+      float t1 = qdiv(norm6_w(rp, lane, NB), fnorm); t1 *= t1;
       float t2 = qdiv(qsqrt(par) * pnorm, fnorm); t2 *= t2;
       const float prered = t1 + qdiv(t2, 0.5f);
       const float dirder = -(t1 + t2);
@@ -390,7 +413,7 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
 #pragma unroll
         for (int i = 0; i < NY; ++i) y[i] = y1[i];
         g_own = g1_own;
-        xnorm = norm6_w(dg * pick(x, l8), own6);
+        xnorm = norm6_w(dg * pick(x, l8), lane, NB);
         fnorm = fnorm1;
         ++iter;
       }

@@ -17,10 +17,10 @@ PY
 run headline headline HOP_X=0
 run headline_prof headline HOP_FUSED_PROFILE=1
 run C2 C2 HOP_X=0
-run C2_s1 C2 HOP_FUSED_SLOTS=1
-run C2_v2 C2 HOP_FUSED_VARIANT=2
+
+
 run C2_prof C2 HOP_FUSED_PROFILE=1
 run C3 C3 HOP_X=0
 run C4 C4 HOP_X=0
-run C4_v2_s2 C4 HOP_FUSED_VARIANT=2 HOP_FUSED_SLOTS=2
-run C4_v2_s1 C4 HOP_FUSED_VARIANT=2 HOP_FUSED_SLOTS=1
+
+
