@@ -352,7 +352,11 @@ def main():
     if os.path.exists(main_bin) and args.sizes == "C2":
         import subprocess, tempfile, cv2
         from scipy.spatial import cKDTree
-        with tempfile.TemporaryDirectory() as td:
+        import contextlib
+        keep = os.environ.get("HOP_KEEP_FRAME_DIR")   # keep the frame's config + inputs (e.g. to profile the executable on them)
+        if keep:
+            os.makedirs(keep, exist_ok=True)
+        with (contextlib.nullcontext(keep) if keep else tempfile.TemporaryDirectory()) as td:
             cfg = f"""cam_K: [{Kc[0]}, 0.0, {Kc[2]}, 0.0, {Kc[1]}, {Kc[3]}, 0.0, 0.0, 1.0]
 cam1_in_leftarm: [0.0,0.0,0.0,0.0,0.0,0.0,1.0]
 handbase_in_palm: [1,0,0,0, 0,1,0,0, 0,0,1,0, 0,0,0,1]
