@@ -177,6 +177,7 @@ int hop_create(int device, hop_ctx **out) {
     if ((v = getenv("HOP_LCP_VARIANT"))) ctx->tune.lcp_variant = atoi(v);
     if ((v = getenv("HOP_VOXEL_MAX_FRAC"))) ctx->tune.voxel_max_frac = (float)atof(v);
     ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
+    ctx->tune.trace = getenv("HOP_TRACE") != nullptr;
   }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) != cudaSuccess) {
@@ -197,9 +198,15 @@ int hop_create(int device, hop_ctx **out) {
 }
 
 void hop_destroy(hop_ctx *ctx) {
-  HOP_ENTER(ctx);
+  HopDeviceGuard guard(ctx);
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
+  if (ctx->tune.trace && !ctx->trace.empty()) {
+    std::vector<std::pair<std::string, HopTraceEntry>> rows(ctx->trace.begin(), ctx->trace.end());
+    std::sort(rows.begin(), rows.end(), [](const auto &a, const auto &b) { return a.second.ms > b.second.ms; });
+    fprintf(stderr, "[hop trace] device %d: host wall time per C-ABI entry point (inclusive)\n", ctx->device);
+    for (const auto &r : rows) fprintf(stderr, "[hop trace] %-36s %8lld calls %10.3f ms %9.4f ms/call\n", r.first.c_str(), r.second.calls, r.second.ms, r.second.ms / (double)r.second.calls);
+  }
   hop_comm_destroy(ctx);
   if (ctx->s4_scene) { hop_cloud_free(ctx, ctx->s4_scene); ctx->s4_scene = nullptr; }
   if (ctx->side) { cudaStreamSynchronize(ctx->side); cudaStreamDestroy(ctx->side); }

@@ -4,6 +4,8 @@
 #include <stdint.h>
 #include <math.h>
 
+#include <chrono>
+#include <map>
 #include <string>
 #include <unordered_map>
 #include <vector>
@@ -227,14 +229,18 @@ struct HopTuning {
   int lcp_variant = 0;        // HOP_LCP_VARIANT: resident CTAs per SM of lcp_score_kernel
   float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
+  bool trace = false;         // HOP_TRACE: host wall time and call count of every C-ABI entry point, printed by hop_destroy
 };
 
 struct hop_comm;   // comm.cu: the NCCL communicator of a context (null for a single-GPU context)
+
+struct HopTraceEntry { long long calls = 0; double ms = 0.0; };
 
 struct hop_ctx {
   int device = 0;
   hop_comm *comm = nullptr;
   HopTuning tune;
+  std::map<std::string, HopTraceEntry> trace;   // HOP_TRACE: per entry point (inclusive: an entry point that calls another counts both)
   // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute of a function: remembered per context (= per device),
   // not per process, so a second context on another GPU opts its kernels in too
   std::unordered_map<const void *, size_t> func_smem;
@@ -299,7 +305,22 @@ struct HopDeviceGuard {
   HopDeviceGuard(const HopDeviceGuard &) = delete;
   HopDeviceGuard &operator=(const HopDeviceGuard &) = delete;
 };
-#define HOP_ENTER(ctx) HopDeviceGuard hop_device_guard_(ctx)
+// host-side tracing of the C ABI (HOP_TRACE=1): where a frame's wall time goes between the kernels
+struct HopTraceScope {
+  hop_ctx *c; const char *fn; std::chrono::steady_clock::time_point t0;
+  HopTraceScope(const hop_ctx *ctx, const char *f) : c(ctx && ctx->tune.trace ? const_cast<hop_ctx *>(ctx) : nullptr), fn(f) {
+    if (c) t0 = std::chrono::steady_clock::now();
+  }
+  ~HopTraceScope() {
+    if (!c) return;
+    HopTraceEntry &e = c->trace[fn];
+    e.calls += 1;
+    e.ms += std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  }
+  HopTraceScope(const HopTraceScope &) = delete;
+  HopTraceScope &operator=(const HopTraceScope &) = delete;
+};
+#define HOP_ENTER(ctx) HopDeviceGuard hop_device_guard_(ctx); HopTraceScope hop_trace_scope_(ctx, __func__)
 
 #define HOP_CUDA(ctx, call)                                                                            \
   do {                                                                                                 \

@@ -775,7 +775,9 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
     // ---- refill: every free slot takes the next hypothesis of the queue ----
     if (warp == 0) {
       int mine = lane < n_slots ? s_slot[lane].h : 0;
-      if (lane < n_slots && mine < 0 && !s_ctl[1]) {
+      const int exhausted = s_ctl[1];
+      __syncwarp();   // (every lane has read the flag before any lane sets it)
+      if (lane < n_slots && mine < 0 && !exhausted) {
         const int h = atomicAdd(a.counter, 1);
         if (h < a.H) {
           FusedSlot &S = s_slot[lane];
@@ -786,7 +788,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
           for (int e = 0; e < 3; ++e) { S.X[9 + e] = X.t[e]; S.inc[9 + e] = 0.f; }
           S.prev_mse = DBL_MAX; S.iters = 0; S.h = h;
           mine = h;
-        } else s_ctl[1] = 1;   // (benign race: every writer stores 1)
+        } else s_ctl[1] = 1;   // (every writer stores 1)
       }
       const unsigned occ = __ballot_sync(0xffffffffu, lane < n_slots && mine >= 0);
       if (lane == 0) s_ctl[0] = __popc(occ);
@@ -891,6 +893,7 @@ __global__ void __launch_bounds__(THREADS, MINB) icp_fused_kernel(FusedArgs a) {
           S.prev_mse = prev_mse;
         }
       }
+      __syncwarp();   // (the lanes' reads of the slot above come before lane 0 rewrites it, whichever branch was taken)
       if (lane == 0) {
         S.iters = iters;
         if (finished) {
