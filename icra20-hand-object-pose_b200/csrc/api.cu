@@ -178,6 +178,7 @@ int hop_create(int device, hop_ctx **out) {
     if ((v = getenv("HOP_VOXEL_MAX_FRAC"))) ctx->tune.voxel_max_frac = (float)atof(v);
     ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
     ctx->tune.trace = getenv("HOP_TRACE") != nullptr;
+    ctx->tune.cluster_blocks = getenv("HOP_CLUSTER_BLOCKS") != nullptr;
   }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaMalloc(&ctx->d_counter, 64 * sizeof(int)) != cudaSuccess) {

@@ -229,6 +229,7 @@ struct HopTuning {
   int lcp_variant = 0;        // HOP_LCP_VARIANT: resident CTAs per SM of lcp_score_kernel
   float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
+  bool cluster_blocks = false; // HOP_CLUSTER_BLOCKS: hop_cluster_poses_gpu always through the blocked kernels (A/B knob; default: the bit matrix up to 4096 hypotheses)
   bool trace = false;         // HOP_TRACE: host wall time and call count of every C-ABI entry point, printed by hop_destroy
 };
 

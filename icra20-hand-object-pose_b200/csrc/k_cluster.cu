@@ -205,6 +205,27 @@ __global__ void __launch_bounds__(CL_BLOCK, 1) cluster_block_kernel(const ClFeat
   }
 }
 
+// Batches of a few thousand hypotheses (a frame's Super4PCS output): the whole upper-triangular "i suppresses j" relation as a bit
+// matrix, one thread per (row, word), every SM busy for a few microseconds; the greedy walk over it -- sequential by definition, a few
+// thousand steps of "if not removed: keep, OR the row in" -- runs on the host on the downloaded matrix.  Same pair test, same order of
+// decisions as the blocked kernels above, which a single CTA walks at ~200 us per 1024 hypotheses.
+constexpr int CL_MATRIX_MAX = 4096;   // 4096 x 128 words = 2 MB over PCIe
+
+__global__ void __launch_bounds__(128) cluster_matrix_kernel(const ClFeat *__restrict__ feat, int n, int words, unsigned int *__restrict__ rows, ClParams p) {
+  const int i = blockIdx.y;
+  const int w = blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= words) return;
+  unsigned int bits = 0u;
+  if (32 * w + 31 > i) {
+    const ClFeat A = feat[i];
+    for (int b = 0; b < 32; ++b) {
+      const int j = 32 * w + b;
+      if (j > i && j < n && cl_close(A, feat[j], p)) bits |= 1u << b;
+    }
+  }
+  rows[(size_t)i * words + w] = bits;
+}
+
 // smallest double x in [-1, 1] with (float)acos(x) <= thr (2 when there is none)
 double geodesic_gate(float thr) {
   auto ok = [&](double x) { return (float)std::acos(x) <= thr; };
@@ -260,6 +281,31 @@ extern "C" int hop_cluster_poses_gpu(hop_ctx *ctx, const float *poses, const flo
   int *d_keep = (int *)(base + feat_bytes), *d_nkeep = d_keep + n;
   unsigned char *d_sup = (unsigned char *)(base + feat_bytes + keep_bytes);
   HOP_CUDA(ctx, cudaMemcpyAsync(d_feat, feat.data(), sizeof(ClFeat) * (size_t)n, cudaMemcpyHostToDevice, st));
+  if (n <= CL_MATRIX_MAX && !ctx->tune.cluster_blocks) {
+    const int words = (n + 31) / 32;
+    const size_t mat_bytes = sizeof(unsigned int) * (size_t)n * words;
+    unsigned int *d_mat = (unsigned int *)ctx->ensure_scratch(mat_bytes);
+    unsigned int *h_mat = (unsigned int *)ctx->ensure_pinned(mat_bytes);
+    if (!d_mat || !h_mat) { ctx->err = "hop_cluster_poses_gpu: matrix allocation failed"; return HOP_ENOMEM; }
+    {
+      ProfScope ps(ctx, HOP_PROF_CLUSTER);
+      cluster_matrix_kernel<<<dim3((words + 127) / 128, n), 128, 0, st>>>(d_feat, n, words, d_mat, p);
+      ctx->launches += 1;
+    }
+    HOP_CUDA(ctx, cudaGetLastError());
+    HOP_CUDA(ctx, cudaMemcpyAsync(h_mat, d_mat, mat_bytes, cudaMemcpyDeviceToHost, st));
+    HOP_CUDA(ctx, cudaStreamSynchronize(st));
+    std::vector<unsigned int> removed(words, 0u);
+    int nk = 0;
+    for (int k = 0; k < n; ++k) {
+      if ((removed[k >> 5] >> (k & 31)) & 1u) continue;
+      keep_out[nk++] = order[k];
+      const unsigned int *row = h_mat + (size_t)k * words;
+      for (int w = k >> 5; w < words; ++w) removed[w] |= row[w];
+    }
+    *n_keep = nk;
+    return HOP_OK;
+  }
   HOP_CUDA(ctx, cudaMemsetAsync(d_nkeep, 0, sizeof(int), st));
   const size_t smem = sizeof(ClFeat) * CL_BLOCK + sizeof(unsigned int) * CL_BLOCK * CL_ROW;
   HOP_CUDA(ctx, ctx->func_smem_optin(cluster_block_kernel, smem));

@@ -156,21 +156,27 @@ struct PpfBits {
   std::vector<uint32_t> member, ambig;                       // full mode: n x words
   std::unordered_map<int, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> rows;   // row mode: fetched on demand
   int launches = 0;
-  ~PpfBits() { if (ctx) { HopDeviceGuard g(ctx); cudaFree(d_pos); cudaFree(d_nrm); cudaFree(d_keys); cudaFree(d_member); cudaFree(d_ambig); cudaFree(d_rows); } }
+  // stream-ordered allocations from the context's pool: a plan is made once per frame
+  ~PpfBits() {
+    if (!ctx) return;
+    HopDeviceGuard g(ctx);
+    void *bufs[6] = {d_pos, d_nrm, d_keys, d_member, d_ambig, d_rows};
+    for (void *b : bufs) if (b) cudaFreeAsync(b, ctx->stream);
+  }
   int init(hop_ctx *c, const std::vector<S4Pt> &P, const std::vector<uint64_t> &sorted_keys) {
     ctx = c; n = (int)P.size(); words = (n + 31) / 32; n_keys = (int)sorted_keys.size();
     if (n == 0) return HOP_OK;
     std::vector<float4> hp(n), hn(n);
     for (int i = 0; i < n; ++i) { hp[i] = make_float4(P[i].p[0], P[i].p[1], P[i].p[2], 0.f); hn[i] = make_float4(P[i].n[0], P[i].n[1], P[i].n[2], 0.f); }
-    HOP_CUDA(ctx, cudaMalloc(&d_pos, sizeof(float4) * (size_t)n)); HOP_CUDA(ctx, cudaMalloc(&d_nrm, sizeof(float4) * (size_t)n));
-    HOP_CUDA(ctx, cudaMalloc(&d_keys, sizeof(uint64_t) * (size_t)std::max(n_keys, 1)));
+    HOP_CUDA(ctx, cudaMallocAsync(&d_pos, sizeof(float4) * (size_t)n, ctx->stream)); HOP_CUDA(ctx, cudaMallocAsync(&d_nrm, sizeof(float4) * (size_t)n, ctx->stream));
+    HOP_CUDA(ctx, cudaMallocAsync(&d_keys, sizeof(uint64_t) * (size_t)std::max(n_keys, 1), ctx->stream));
     HOP_CUDA(ctx, cudaMemcpyAsync(d_pos, hp.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     HOP_CUDA(ctx, cudaMemcpyAsync(d_nrm, hn.data(), sizeof(float4) * (size_t)n, cudaMemcpyHostToDevice, ctx->stream));
     if (n_keys) HOP_CUDA(ctx, cudaMemcpyAsync(d_keys, sorted_keys.data(), sizeof(uint64_t) * (size_t)n_keys, cudaMemcpyHostToDevice, ctx->stream));
     full = n <= 6144;
     const size_t rows_alloc = full ? (size_t)n : 64;
-    HOP_CUDA(ctx, cudaMalloc(&d_member, sizeof(uint32_t) * rows_alloc * words)); HOP_CUDA(ctx, cudaMalloc(&d_ambig, sizeof(uint32_t) * rows_alloc * words));
-    HOP_CUDA(ctx, cudaMalloc(&d_rows, sizeof(int) * 64));
+    HOP_CUDA(ctx, cudaMallocAsync(&d_member, sizeof(uint32_t) * rows_alloc * words, ctx->stream)); HOP_CUDA(ctx, cudaMallocAsync(&d_ambig, sizeof(uint32_t) * rows_alloc * words, ctx->stream));
+    HOP_CUDA(ctx, cudaMallocAsync(&d_rows, sizeof(int) * 64, ctx->stream));
     if (full) {
       ppf_rows_kernel<<<dim3((n + 255) / 256, n), 256, 0, ctx->stream>>>(d_pos, d_nrm, n, nullptr, n, d_keys, n_keys, d_member, d_ambig, words);
       ctx->launches += 1; ++launches;
@@ -309,27 +315,70 @@ struct Planner {
     for (size_t i = 0; i < nq; ++i) for (int k = 0; k < 3; ++k) pl.Qunit[3 * i + k] = (pl.Q[i].p[k] - pl.gcenter[k]) / pl.ratio + 0.5f;
   }
 
+  // One draw of std::discrete_distribution<int>(w, w + n) from `engine`, without building the distribution (libstdc++ 13,
+  // bits/random.tcc: param_type::_M_initialize normalises every weight by the sequential double sum, partial_sum gives the
+  // cumulative table with its last entry forced to 1, operator() draws generate_canonical<double, 53> and returns the
+  // upper_bound).  Same doubles in the same order, so the same index; the scan stops at the answer instead of finishing the
+  // table, and nothing is allocated.  The reference constructs a distribution per draw (matchBase.hpp:120-140): at ~1000
+  // points and 30 trials that construction was most of the planner's host time.  tests/test_s4pcs_plan.py pins the bases bit for bit
+  // against the reference compiled here, i.e. against the real std::discrete_distribution.
+  template <typename W>
+  static int draw_discrete(const W *w, int n, std::mt19937 &engine) {
+    if (n < 2) return 0;   // (an empty or one-entry table: libstdc++ returns 0 without touching the engine)
+    double sum = 0.0;
+    for (int i = 0; i < n; ++i) sum += (double)w[i];
+    const double p = std::generate_canonical<double, std::numeric_limits<double>::digits>(engine);
+    double acc = 0.0;
+    for (int k = 0; k + 1 < n; ++k) {
+      acc = k == 0 ? (double)w[0] / sum : acc + (double)w[k] / sum;
+      if (acc > p) return k;
+    }
+    return n - 1;
+  }
+
   // SelectRandomTriangle (matchBase.hpp:111-212).  sample_pool is returned as the pool for the 4th point.
+  std::vector<float> tri_probs;   // scratch of select_random_triangle (kept across calls: no allocation per trial)
+  std::vector<int> tri_backup;
   bool select_random_triangle(int &base1, int &base2, int &base3, std::vector<int> &sample_pool) {
     const std::vector<S4Pt> &P = pl.P;
     const int number_of_points = (int)P.size();
     base1 = base2 = base3 = -1;
-    std::discrete_distribution<> sampler(point_probs.begin(), point_probs.end());
-    const int first_point = sampler(point_index_engine);
+    const int first_point = draw_discrete(point_probs.data(), number_of_points, point_index_engine);
     point_probs[first_point] *= pl.opt.dispersion;
     sample_pool.clear();
-    std::vector<float> probs;
-    // (the membership tests -- three acos and a set lookup per point -- are the planner's O(N) cost: evaluated on all host
-    //  threads with the same libm, gathered in index order, so the pool is the one a sequential loop builds)
-    ppf_row(first_point, member, nullptr);
-    for (int i = 0; i < number_of_points; ++i)
-      if (member[i]) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
+    std::vector<float> &probs = tri_probs;
+    probs.clear();
+    // (the membership tests -- three acos and a set lookup per point -- are the planner's O(N) cost: a bit of the device's matrix
+    //  when there is one, else evaluated on all host threads with the same libm, gathered in index order, so the pool is the one
+    //  a sequential loop builds)
+    const uint32_t *m1 = nullptr, *a1 = nullptr;
+    if (bits && bits->row(first_point, m1, a1)) {
+      // straight from the device's bit row: 32 points per word, the host formula only for the flagged (ambiguous) pairs
+      for (int w0 = 0; w0 < number_of_points; w0 += 32) {
+        const uint32_t amb = a1[w0 >> 5];
+        uint32_t mem = m1[w0 >> 5] & ~amb;
+        for (uint32_t rest = amb; rest; rest &= rest - 1) {
+          const int i = w0 + __builtin_ctz(rest);
+          if (i < number_of_points && i != first_point && has_ppf(P[first_point], P[i])) mem |= 1u << (i - w0);
+        }
+        if (first_point >= w0 && first_point < w0 + 32) mem &= ~(1u << (first_point - w0));
+        for (; mem; mem &= mem - 1) {
+          const int i = w0 + __builtin_ctz(mem);
+          if (i >= number_of_points) break;
+          sample_pool.push_back(i); probs.push_back(point_probs[i]);
+        }
+      }
+    } else {
+      ppf_row(first_point, member, nullptr);
+      for (int i = 0; i < number_of_points; ++i)
+        if (member[i]) { sample_pool.push_back(i); probs.push_back(point_probs[i]); }
+    }
     if (sample_pool.size() < 3) return false;
     const float sq_max_base_diameter = max_base_diameter * max_base_diameter;
+    const int n_pool = (int)sample_pool.size();
     for (int i = 0; (size_t)i < sample_pool.size() * sample_pool.size() / 4; ++i) {
-      std::discrete_distribution<> sampler1(probs.begin(), probs.end());
-      const int second_point = sampler1(point_index_engine);
-      const int third_point = sampler1(point_index_engine);
+      const int second_point = draw_discrete(probs.data(), n_pool, point_index_engine);
+      const int third_point = draw_discrete(probs.data(), n_pool, point_index_engine);
       if (second_point == third_point) continue;
       if (!has_ppf_idx(sample_pool[second_point], sample_pool[third_point])) continue;
       probs[second_point] *= pl.opt.dispersion;
@@ -343,23 +392,31 @@ struct Planner {
       }
     }
     if (base2 == -1 || base3 == -1) return false;
-    std::vector<int> backup = sample_pool;
+    std::vector<int> &backup = tri_backup;
+    backup.swap(sample_pool);
     sample_pool.clear();
     const int nb = (int)backup.size();
-    {
+    // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
+    // a point id (match4pcsBase.hpp:159): reproduced
+    const uint32_t *m2 = nullptr, *a2 = nullptr, *m3 = nullptr, *a3 = nullptr;
+    if (bits && bits->row(base2, m2, a2) && bits->row(base3, m3, a3)) {
+      for (int i = 0; i < nb; ++i) {
+        const int q = backup[i], w = q >> 5, b = q & 31;
+        if (q == base2 || q == base3 || q == base1) continue;
+        const bool in2 = ((a2[w] >> b) & 1u) ? has_ppf(P[base2], P[q]) : ((m2[w] >> b) & 1u) != 0;
+        if (!in2) continue;
+        const bool in3 = ((a3[w] >> b) & 1u) ? has_ppf(P[base3], P[q]) : ((m3[w] >> b) & 1u) != 0;
+        if (in3) sample_pool.push_back(i);
+      }
+    } else {
       std::vector<unsigned char> m2, m3;
       ppf_row(base2, m2, &backup);
       ppf_row(base3, m3, &backup);
-      member.assign(nb, 0);
       for (int i = 0; i < nb; ++i) {
         if (backup[i] == base2 || backup[i] == base3 || backup[i] == base1) continue;
-        member[i] = (m2[i] && m3[i]) ? 1 : 0;
+        if (m2[i] && m3[i]) sample_pool.push_back(i);
       }
     }
-    // the reference stores the POOL INDEX i here, not the point id backup[i] (matchBase.hpp:203), and later uses it as
-    // a point id (match4pcsBase.hpp:159): reproduced
-    for (int i = 0; i < nb; ++i)
-      if (member[i]) sample_pool.push_back(i);
     if (sample_pool.size() < 1) return false;
     return base1 != -1 && base2 != -1 && base3 != -1;
   }
@@ -508,20 +565,42 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
   hop_s4pcs_plan *pl = new hop_s4pcs_plan();
   pl->opt = *opt;
   Planner planner(*pl);
-  for (int i = 0; i < n_keys; ++i) {
-    const int k[4] = {ppf_keys[4 * i], ppf_keys[4 * i + 1], ppf_keys[4 * i + 2], ppf_keys[4 * i + 3]};
-    if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) planner.keys.insert(pack_key(k));
+  {
+    HopTraceScope ts(ctx, "  plan: key set");
+    for (int i = 0; i < n_keys; ++i) {
+      const int k[4] = {ppf_keys[4 * i], ppf_keys[4 * i + 1], ppf_keys[4 * i + 2], ppf_keys[4 * i + 3]};
+      if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) planner.keys.insert(pack_key(k));
+    }
   }
-  planner.init(P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ);
+  {
+    HopTraceScope ts(ctx, "  plan: MatchBase::init");
+    planner.init(P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ);
+  }
   PpfBits bits;
   if (ctx && pl->P.size() >= 4 && pl->Q.size() >= 4) {
+    HopTraceScope ts(ctx, "  plan: PPF membership on the device");
     std::vector<uint64_t> sorted(planner.keys.begin(), planner.keys.end());
     std::sort(sorted.begin(), sorted.end());
     const int rc = bits.init(ctx, pl->P, sorted);
     if (rc != HOP_OK) { delete pl; return rc; }
     planner.bits = &bits;
+  } else if (!ctx && getenv("HOP_PLAN_HOSTBITS")) {
+    // debugging aid (no GPU needed): the membership matrix the device would deliver, computed with the host formula, so that the
+    // trial loop runs the way it does behind hop_s4pcs_plan_create_gpu (HOP_PLAN_DEBUG prints its time)
+    const int n = (int)pl->P.size();
+    bits.n = n; bits.words = (n + 31) / 32; bits.full = true;
+    bits.member.assign((size_t)n * bits.words, 0u); bits.ambig.assign((size_t)n * bits.words, 0u);
+    for (int a = 0; a < n; ++a)
+      for (int b = 0; b < n; ++b)
+        if (a != b && planner.has_ppf(pl->P[a], pl->P[b])) bits.member[(size_t)a * bits.words + (b >> 5)] |= 1u << (b & 31);
+    planner.bits = &bits;
   }
-  planner.plan_trials();
+  {
+    HopTraceScope ts(ctx, "  plan: trials (RNG replay)");
+    const auto t0 = std::chrono::steady_clock::now();
+    planner.plan_trials();
+    if (getenv("HOP_PLAN_DEBUG")) fprintf(stderr, "[plan debug] nP %zu trials_ms %.3f\n", pl->P.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+  }
   *out = pl;
   return HOP_OK;
 }

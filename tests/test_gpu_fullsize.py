@@ -228,11 +228,13 @@ def test_verify_lcp_c5_batch_of_replicated_sets(ctx):
 
 @pytest.mark.parametrize("n,angle,dist,sym,spread", [(3000, 30.0, 0.015, (360.0, 360.0, 360.0), "wide"), (20000, 30.0, 0.015, (0.0, 180.0, 180.0), "wide"),
                                                     (20000, 5.0, 0.003, (360.0, 360.0, 360.0), "tight"), (1500, 5.0, 0.003, (180.0, 0.0, -1.0), "tight"),
-                                                    (1025, 30.0, 0.015, (360.0, 360.0, 360.0), "tight")])
+                                                    (1025, 30.0, 0.015, (360.0, 360.0, 360.0), "tight"),
+                                                    (4096, 30.0, 0.015, (360.0, 360.0, 360.0), "tight"), (4097, 30.0, 0.015, (360.0, 360.0, 360.0), "wide")])
 def test_cluster_poses_on_the_device_keeps_the_same_list(ctx, n, angle, dist, sym, spread):
     """hop_cluster_poses_gpu against the host hop_cluster_poses (itself pinned against the reference tree's Eigen): the keep
     list must be identical, element by element -- spread-out hypotheses (many clusters), tight ones (many suppressions per
-    cluster, ties in the score), symmetric objects, block boundaries (n = 1025)."""
+    cluster, ties in the score), symmetric objects, block boundaries (n = 1025), both device paths (the bit matrix walked on the host up to
+    4096 hypotheses, the blocked kernels beyond)."""
     from hop_b200 import capi
     s, sn, conf, gt = synth.make_scene("ellipse", 500, seed=2)
     kw = dict(rot_sigma_deg=20, trans_sigma=0.02, random_frac=0.3) if spread == "wide" else dict(rot_sigma_deg=4, trans_sigma=0.003, random_frac=0.05)

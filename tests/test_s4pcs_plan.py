@@ -72,3 +72,20 @@ def test_plan_degenerate_inputs():
     plan = capi.S4pcsPlan(s[:3], sn[:3], conf[:3], m, mn, np.zeros((0, 4), np.int32))
     assert not plan.get()["base_ok"].any()
     plan.close()
+
+
+@pytest.mark.parametrize("name,seed,ns", [("ellipse", 2, 959), ("cuboid", 3, 700), ("tless", 4, 1200)])
+def test_plan_from_a_membership_matrix_equals_the_host_plan(name, seed, ns, monkeypatch):
+    """hop_s4pcs_plan_create_gpu feeds the planner a bit matrix of PPF membership and the planner then walks bit rows instead of calling the
+    host formula per pair.  HOP_PLAN_HOSTBITS builds that matrix with the host formula (no GPU needed): the plan -- sample, bases,
+    invariants of all 30 trials -- must be the one the per-pair path makes (which the test above pins against the compiled reference)."""
+    m, mn = synth.make_model(name, 4000, seed=1)
+    sub = slice(None, None, 16)
+    keys = np.unique(np.array([capi.compute_ppf(m[sub][i], mn[sub][i], m[sub][j], mn[sub][j]) for i in range(0, 250, 3) for j in range(250) if i != j], np.int32), axis=0)
+    s, sn, conf, gt = synth.make_scene(name, ns, seed=seed)
+    host = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=100)).get()
+    monkeypatch.setenv("HOP_PLAN_HOSTBITS", "1")
+    bits = capi.S4pcsPlan(s, sn, conf, m, mn, keys, capi.s4pcs_options(sample_size=100)).get()
+    assert host.keys() == bits.keys() and int(np.sum(host["base_ok"])) >= 5
+    for k in host:
+        assert np.array_equal(np.asarray(host[k]), np.asarray(bits[k])), k

@@ -1,0 +1,8 @@
+#!/bin/bash
+OUT=gpurun_out; mkdir -p $OUT; TAG=${1:-r03b}
+
+export HOP_KEEP_FRAME_DIR=/tmp/hop_frame
+timeout 900 python tools/bench_stages.py --steps 3 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_bench_stages.json 2> $OUT/${TAG}_bench_stages.err; echo "stages exit $?"
+BIN=icra20-hand-object-pose_b200/host/main_realdata_auto
+HOP_TRACE=1 $BIN /tmp/hop_frame/cfg.yaml 20 > $OUT/${TAG}_main_out.txt 2> $OUT/${TAG}_main_trace.txt; grep timing_ms $OUT/${TAG}_main_out.txt | tail -3; grep "hop trace" $OUT/${TAG}_main_trace.txt | head -12
+
