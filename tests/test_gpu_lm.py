@@ -86,3 +86,28 @@ def test_warp_lm_follows_the_scalar_program(ctx, lmr, name, kw):
     assert n_same_nfev >= 0.5 * len(mats), (n_same_nfev, len(mats))
     if name == "cuboid" and kw["rot_sigma_deg"] < 5:
         assert worst < 2e-4, worst
+
+
+def test_warp_lm_rank_deficient_jacobian(ctx, lmr):
+    """Source points all at the origin: the three rotation columns of the Jacobian are exactly zero, the Cholesky factor has zero pivots
+    and lmpar takes MINPACK's rank-deficient branch -- on the device the one place that falls back to the scalar lmpar_iterate, fed from
+    the factor in shared memory.  Same translation as the host program; the rotation parameters stay 0."""
+    rng = np.random.default_rng(5)
+    sums, mats = [], []
+    for k in range(16):
+        n = rng.normal(size=(200, 3)).astype(np.float32)
+        n /= np.linalg.norm(n, axis=1, keepdims=True)
+        src = np.zeros((200, 3), np.float32)
+        tgt = (rng.normal(scale=0.004, size=3).astype(np.float32) + rng.normal(scale=1e-4, size=(200, 3)).astype(np.float32))
+        A = np.zeros(169, np.float64)
+        lmr.hop_lmr_moments(src, np.ascontiguousarray(tgt), np.ascontiguousarray(n), 200, A)
+        mats.append(A.reshape(13, 13)); sums.append(_pack(mats[-1]))
+    x_dev, nfev_dev, st_dev = ctx.debug_lm_solve(np.stack(sums))
+    for k, A in enumerate(mats):
+        Af = np.ascontiguousarray(A.astype(np.float32).astype(np.float64))
+        x = np.zeros(6, np.float32)
+        nfev = C.c_int(0)
+        st = lmr.hop_lmr_solve_moments(Af.reshape(-1), x, C.byref(nfev))
+        assert st >= 1 and st_dev[k] >= 1 and np.isfinite(x_dev[k]).all()
+        assert np.all(x_dev[k][3:] == 0) and np.all(x[3:] == 0)
+        assert np.abs(x_dev[k][:3] - x[:3]).max() < 2e-6, (k, x, x_dev[k])
