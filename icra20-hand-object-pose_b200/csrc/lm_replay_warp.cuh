@@ -78,64 +78,77 @@ __device__ __forceinline__ double quad_w(const float *Arow, const float (&y)[NY]
   return bfly_sum16(g_own * (double)pick(y, l16));
 }
 
-// MINPACK qrsolv, lane i (mod 8) on row i of the lower triangle: least squares of [R; D] z = [Q^T f; 0].  In: s[k] = R(k, i) for k < i
-// (row i of R^T), rd = R(i, i), dd = D(i), wa = (Q^T f)(i).  Out: s[k] = S(i, k) for k < i, sdiag = S(i, i), wa = z(i).
-// The Givens rotation of step (j, k) is computed by every lane from the two broadcast numbers it depends on; lane k applies it to
-// its diagonal, lanes i > k to their column-k entry.  Same rotations in the same order as the scalar qrsolv.
-__device__ __forceinline__ void qrsolv_w(float (&s)[N], float rd, float dd, float &wa, float &sdiag, int l8, bool own6) {
-  const unsigned FULL = 0xffffffffu;
-  float sd = 0.f;
-#pragma unroll 1
-  for (int j = 0; j < N; ++j) {
-    const float dj = __shfl_sync(FULL, dd, j);
-    if (dj == 0.f) continue;
-    sd = l8 == j ? dj : 0.f;   // sdiag[j] = diag[j], sdiag[k > j] = 0 (entries left of j are final and not read again)
-    float qtbpj = 0.f;
+// Right-looking Cholesky of a 6x6 matrix with one right-hand side, column l8 per lane (lanes 0..5: columns of M, upper part; lane 6: the
+// right-hand side b; lane 7: zeros).  In: c[i] = M(i, l8) for i <= l8 (0 below) / b(i); dgl = the diagonal of M, replicated.
+// Out: c[i] = S(i, l8) for i <= l8 with M = S^T S / (S^-T b)(i), rounded to float on the way like the scalar program's Q^T f.
+// Row i of the factor, right of the pivot, travels through S.U[i][.] (which is idle after the Gram step) and stays there: the row
+// owners read their row of S from it afterwards.  Every lane tracks the whole diagonal of the block still to eliminate, so the
+// pivot needs no broadcast.  A non-positive pivot zeroes its row (chol_pivot).
+__device__ __forceinline__ void chol_w(LmrScratch &S, double (&c)[N], double (&dgl)[N], int lane, int l8) {
+  __syncwarp();   // (the rows of the previous factor in S.U have been read)
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      if (k < j) continue;
-      const float sdk = __shfl_sync(FULL, sd, k);
-      if (sdk == 0.f) continue;
-      const float rkk = __shfl_sync(FULL, rd, k), wak = __shfl_sync(FULL, wa, k);
-      float sn, cs;
-      if (fabsf(rkk) < fabsf(sdk)) { const float ct = qdiv(rkk, sdk); sn = qdiv(0.5f, qsqrt(0.25f + 0.25f * ct * ct)); cs = sn * ct; }
-      else { const float tn = qdiv(sdk, rkk); cs = qdiv(0.5f, qsqrt(0.25f + 0.25f * tn * tn)); sn = cs * tn; }
-      const float tmp = cs * wak + sn * qtbpj;
-      qtbpj = -sn * wak + cs * qtbpj;
-      if (l8 == k) { rd = cs * rkk + sn * sdk; wa = tmp; }
-      if (l8 > k) {
-        const float t2 = cs * s[k] + sn * sd;
-        sd = -sn * s[k] + cs * sd;
-        s[k] = t2;
+  for (int i = 0; i < N; ++i) {
+    double dd, inv;
+    chol_pivot_dev(dgl[i], &dd, &inv);
+    double rik = l8 == i ? dd : c[i] * inv;
+    if (l8 == N) rik = (double)(float)rik;
+    c[i] = rik;
+    if (i + 1 < N) {
+      if (lane > i && lane < N) S.U[i][lane] = rik;
+      __syncwarp();
+#pragma unroll
+      for (int m = i + 1; m < N; ++m) {
+        const double rim = S.U[i][m];
+        if (l8 >= m) c[m] = fma(-rim, rik, c[m]);
+        dgl[m] = fma(-rim, rim, dgl[m]);
       }
     }
   }
-  sdiag = rd;   // (a column whose D entry is 0 keeps R's diagonal, as in the scalar program)
-  const unsigned sing = __ballot_sync(FULL, own6 && sdiag == 0.f) & 0x3fu;
-  const int nsing = sing ? __ffs((int)sing) - 1 : N;
-  if (l8 >= nsing) wa = 0.f;
+}
+// after chol_w: column l8 of the float factor (rc), its row l8 (rr, from S.U), S^-T b replicated (q, through S.h)
+__device__ __forceinline__ void chol_fetch(LmrScratch &S, const double (&c)[N], float (&rc)[N], float (&rr)[N], float (&q)[N], int lane, int l8) {
+  const bool own6 = l8 < N;
 #pragma unroll
-  for (int j = N - 1; j >= 0; --j) {
-    const float pj = s[j] * wa;   // S(i, j) z(i) on lanes i > j (their z is final)
-    float sum = 0.f;
+  for (int i = 0; i < N; ++i) rc[i] = (own6 && i <= l8) ? (float)c[i] : 0.f;
+  if (lane == N) {
 #pragma unroll
-    for (int i = j + 1; i < N; ++i) sum += __shfl_sync(FULL, pj, i);
-    if (l8 == j && j < nsing) wa = qdiv(wa - sum, sdiag);
+    for (int i = 0; i < N; ++i) S.h[i] = (float)c[i];   // (the steps h_j are not read again before the next Gram step rewrites them)
+  }
+  __syncwarp();
+  const float rdiag = pick(rc, l8);
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    q[k] = S.h[k];
+    rr[k] = (own6 && k > l8) ? (float)S.U[l8 < N ? l8 : 0][k] : (k == l8 ? rdiag : 0.f);
+  }
+  __syncwarp();   // (S.h may be rewritten by the next factorisation)
+}
+// R z = q by back substitution, row l8 of R per lane (rr), rinv = 1 / R(l8, l8); z replicated.  MINPACK's order: z(k) is final
+// before it is subtracted from the rows above.
+__device__ __forceinline__ void backsolve_w(const float (&rr)[N], float rinv, const float (&q)[N], float (&z)[N], int l8) {
+  float acc = pick(q, l8);
+#pragma unroll
+  for (int k = N - 1; k >= 0; --k) {
+    z[k] = __shfl_sync(0xffffffffu, acc * rinv, k);
+    if (l8 < k) acc = fmaf(-rr[k], z[k], acc);
   }
 }
 
 // MINPACK lmpar beyond the Gauss-Newton step (full-rank R): the iteration on the LM parameter, distributed like the rest.
-// rc = column l8 of R, rd = R(l8, l8), dg = diag(l8), qtf replicated; step (replicated) holds the Gauss-Newton step on entry and the
-// LM step on exit; dxnorm = |D step| of the Gauss-Newton step.
-__device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, float dg, const float (&qtf)[N], float delta, float dxnorm, float &par,
-                                                float (&step)[N], int lane, NormBuf &NB) {
+// The scalar program's qrsolv eliminates the rows sqrt(par) D of [R; sqrt(par) D] with 21 Givens rotations, one after the other, to get
+// the factor S of R^T R + par D^2 and the step.  R^T R is J^T J and R^T Q^T f is J^T f, both still in shared memory from the Gram step: S is
+// the Cholesky factor of J^T J + par D^2 and the step solves S^T S x = J^T f -- the factorisation this file already has, ~800 cycles
+// instead of ~6 k for the rotation chain (in double, so at least as close to the exact step as the reference's float rotations).
+// rc = column l8 of R, rd = R(l8, l8), dg = diag(l8), qtf replicated; step (replicated) holds the Gauss-Newton step on entry and the LM
+// step on exit; dxnorm = |D step| of the Gauss-Newton step; g_col = this lane's column of [J^T J | J^T f] (S.Gc).
+__device__ __forceinline__ void lmpar_iterate_w(LmrScratch &S, const double *g_col, const float (&rc)[N], float rd, float dg, const float (&qtf)[N], float delta,
+                                                float dxnorm, float &par, float (&step)[N], int lane, NormBuf &NB) {
   const unsigned FULL = 0xffffffffu;
   const int l8 = lane & 7;
   const bool own6 = l8 < N;
   const float dwarf = FLT_MIN;
   float fp = dxnorm - delta;
-  float xj = pick(step, l8);        // x(l8)
-  float wa2 = dg * xj;
+  float wa2 = dg * pick(step, l8);
   // parl: |R^-T D^2 x / |D x||^-2 scaled (Newton step on phi at par = 0)
   float parl;
   {
@@ -161,18 +174,26 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
   par = fmaxf(par, parl);
   par = fminf(par, paru);
   if (par == 0.f) par = qdiv(gnorm, dxnorm);
-  const float qtf_own = pick(qtf, l8);
+  double d2[N];   // diag^2, replicated
+#pragma unroll
+  for (int i = 0; i < N; ++i) { const double d = (double)__shfl_sync(FULL, dg, i); d2[i] = d * d; }
   int iter = 0;
   for (;;) {
     ++iter;
     if (par == 0.f) par = fmaxf(dwarf, 0.001f * paru);
-    const float sq = qsqrt(par);
-    float s[N], wa = own6 ? qtf_own : 0.f, sdiag;
+    double c[N], dgl[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) s[k] = k < l8 ? rc[k] : 0.f;
-    qrsolv_w(s, rd, own6 ? sq * dg : 0.f, wa, sdiag, l8, own6);
-    xj = wa;
-    wa2 = dg * xj;
+    for (int i = 0; i < N; ++i) {
+      const double add = (double)par * d2[i];
+      dgl[i] = S.Gc[i][i] + add;
+      c[i] = g_col[i] + ((own6 && i == l8) ? add : 0.0);
+    }
+    chol_w(S, c, dgl, lane, l8);
+    float sc[N], sr[N], sq[N];
+    chol_fetch(S, c, sc, sr, sq, lane, l8);
+    const float sdiag = pick(sc, l8);
+    backsolve_w(sr, qdiv(1.f, sdiag), sq, step, l8);
+    wa2 = dg * pick(step, l8);
     dxnorm = norm6_w(wa2, lane, NB);
     const float temp0 = fp;
     fp = dxnorm - delta;
@@ -183,7 +204,7 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
       const float fin = qdiv(w, sdiag);                    // final on lane j
       const float t = __shfl_sync(FULL, fin, j);
       if (l8 == j) fin_own = fin;
-      if (l8 > j) w = fmaf(-s[j], t, w);
+      if (l8 > j) w = fmaf(-sc[j], t, w);
     }
     const float temp = norm6_w(fin_own, lane, NB);
     const float parc = qdiv(qdiv(qdiv(fp, delta), temp), temp);
@@ -191,8 +212,6 @@ __device__ __forceinline__ void lmpar_iterate_w(const float (&rc)[N], float rd, 
     if (fp < 0.f) paru = fminf(paru, par);
     par = fmaxf(parl, par + parc);
   }
-#pragma unroll
-  for (int j = 0; j < N; ++j) step[j] = __shfl_sync(FULL, xj, j);
 }
 
 // The LM run from x = 0.  All 32 lanes call with the same arguments; A.scr->A must hold the expanded moments (moments_prepare).
@@ -293,38 +312,10 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
     for (int i = 0; i < N; ++i) { c[i] = g_col[i]; dgl[i] = S.Gc[i][i]; }
     const double gdiag = pick(c, l8);   // (J^T J)(l8, l8); 0 on lanes 6, 7
     const float wa2 = qsqrt(gdiag > 0.0 ? (float)gdiag : 0.f);   // column norm of J
-#pragma unroll
-    for (int i = 0; i < N; ++i) {
-      double dd, inv;
-      chol_pivot_dev(dgl[i], &dd, &inv);               // the pivot: all earlier rows eliminated
-      double rik = l8 == i ? dd : c[i] * inv;          // R(i, l8) / (Q^T f)(i); 0 on the lanes left of the pivot
-      if (l8 == N) rik = (double)(float)rik;           // (the scalar program rounds Q^T f to float before it is used below)
-      c[i] = rik;
-      if (i + 1 < N) {
-        if (lane > i && lane < N) S.U[i][lane] = rik;  // row i of the factor, right of the pivot (S.U is idle after the Gram step)
-        __syncwarp();
-#pragma unroll
-        for (int m = i + 1; m < N; ++m) {
-          const double rim = S.U[i][m];                // R(i, m)
-          if (l8 >= m) c[m] = fma(-rim, rik, c[m]);
-          dgl[m] = fma(-rim, rim, dgl[m]);
-        }
-      }
-    }
+    chol_w(S, c, dgl, lane, l8);
     float rc[N], qtf[N], rr[N];   // column l8 of r, Q^T f (replicated), row l8 of r
-#pragma unroll
-    for (int i = 0; i < N; ++i) rc[i] = (own6 && i <= l8) ? (float)c[i] : 0.f;
-    if (lane == N) {
-#pragma unroll
-      for (int i = 0; i < N; ++i) S.h[i] = (float)c[i];   // (the steps h_j are not read again before the next Gram step rewrites them)
-    }
-    __syncwarp();
+    chol_fetch(S, c, rc, rr, qtf, lane, l8);
     const float rdiag = pick(rc, l8);
-#pragma unroll
-    for (int k = 0; k < N; ++k) {
-      qtf[k] = S.h[k];
-      rr[k] = (own6 && k > l8) ? (float)S.U[l8 < N ? l8 : 0][k] : (k == l8 ? rdiag : 0.f);
-    }
     if (iter == 1) {
       dg = own6 ? (wa2 == 0.f ? 1.f : wa2) : 0.f;
       xnorm = norm6_w(dg * pick(x, l8), lane, NB);
@@ -348,15 +339,10 @@ __device__ __noinline__ int lm_replay_solve_warp(const MomentsDev &A, float *x_o
       // ---- lmpar: the Gauss-Newton step and the test that it fits the trust region (then par = 0: the common case) ----
       float step[N];
       if (__all_sync(FULL, !own6 || rdiag != 0.f)) {
-        float acc = pick(qtf, l8);
-#pragma unroll
-        for (int k = N - 1; k >= 0; --k) {
-          step[k] = __shfl_sync(FULL, acc * rinv, k);
-          if (l8 < k) acc = fmaf(-rr[k], step[k], acc);
-        }
+        backsolve_w(rr, rinv, qtf, step, l8);
         const float dxnorm = norm6_w(dg * pick(step, l8), lane, NB);
         if (dxnorm - delta <= 0.1f * delta) par = 0.f;
-        else lmpar_iterate_w(rc, rdiag, dg, qtf, delta, dxnorm, par, step, lane, NB);
+        else lmpar_iterate_w(S, g_col, rc, rdiag, dg, qtf, delta, dxnorm, par, step, lane, NB);
       } else {   // rank-deficient R (a zero pivot): the scalar program, from the factor in shared memory
         __syncwarp();
         if (lane < N) {
