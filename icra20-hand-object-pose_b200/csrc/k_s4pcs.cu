@@ -517,23 +517,23 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     ctx->err = std::string("hop_super4pcs_run: ") + cudaGetErrorString(ce);
     return HOP_ENOMEM;
   }
+  cudaMemsetAsync(bPoses.p, 0, 64 * (size_t)M, st); cudaMemsetAsync(bLcp.p, 0, 4 * (size_t)M, st);   // (the records past the emitted count travel too)
   cudaMemcpyAsync(bBases.p, bases.data(), sizeof(int32_t) * 4 * T, cudaMemcpyHostToDevice, st);
   cudaMemcpyAsync(bQc.p, Qc.data(), sizeof(float) * 3 * nQ, cudaMemcpyHostToDevice, st);
   rc = hop_verify_lcp_dev(ctx, Pcloud, bQc.as<float>(), nQ, bBases.as<int32_t>(), T, (const int32_t *)bQuads.p, bQuadTrial.as<int32_t>(), M,
                           plan->centroid_P, plan->centroid_Q, delta, bPoses.as<float>(), bLcp.as<float>(), bValid.as<int32_t>(), bN.as<int32_t>());
   int32_t n = 0;
   if (rc == HOP_OK) {
+    // one round trip: the count and, with it, as many records as the caller has room for (n <= M is known here; the records past n
+    // are whatever the buffers held and are not reported)
+    const int k = std::min<int>(M, capacity);
     cudaMemcpyAsync(&n, bN.p, sizeof(int32_t), cudaMemcpyDeviceToHost, st);
-    if (cudaStreamSynchronize(st) != cudaSuccess) rc = HOP_ECUDA;
-  }
-  if (rc == HOP_OK) {
-    const int k = std::min<int>(n, capacity);
     if (k > 0) {
       cudaMemcpyAsync(hyp_poses, bPoses.p, 64 * (size_t)k, cudaMemcpyDeviceToHost, st);
       cudaMemcpyAsync(hyp_lcp, bLcp.p, 4 * (size_t)k, cudaMemcpyDeviceToHost, st);
-      if (cudaStreamSynchronize(st) != cudaSuccess) rc = HOP_ECUDA;
     }
-    if (n_hyp) *n_hyp = n;
+    if (cudaStreamSynchronize(st) != cudaSuccess) rc = HOP_ECUDA;
+    if (rc == HOP_OK && n_hyp) *n_hyp = n;
   }
   if (rc == HOP_ECUDA) ctx->err = std::string("hop_super4pcs_run: ") + cudaGetErrorString(cudaGetLastError());
   return rc;

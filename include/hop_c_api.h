@@ -239,7 +239,8 @@ void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const fl
 /* The device part of a planned registration: pair extraction (K2a), congruent-set search (K2b) and verification (K3) of
  * all trials, stopping like Perform_N_steps (:129-194) after success_quadrilaterals successful trials.  hyp_poses
  * (capacity x 16, column-major, model -> scene) / hyp_lcp: every congruent quadrilateral with LCP > 0, in (trial,
- * quadrilateral) order; *n_hyp = how many there are (may exceed capacity: the first `capacity` are written). */
+ * quadrilateral) order; *n_hyp = how many there are (may exceed capacity: the first `capacity` are written; entries of the
+ * buffers past min(*n_hyp, capacity) may be overwritten with zeros). */
 int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_poses, float *hyp_lcp, int capacity, int32_t *n_hyp);
 
 /* ---- pose clustering (host) ------------------------------------------------------------------------------------- */
