@@ -176,6 +176,7 @@ int hop_create(int device, hop_ctx **out) {
     if ((v = getenv("HOP_MOM_GROUP"))) ctx->tune.mom_group_chunks = atoi(v);
     if ((v = getenv("HOP_LCP_VARIANT"))) ctx->tune.lcp_variant = atoi(v);
     if ((v = getenv("HOP_VOXEL_MAX_FRAC"))) ctx->tune.voxel_max_frac = (float)atof(v);
+    if ((v = getenv("HOP_VOXEL_SCALE"))) ctx->tune.voxel_scale = (float)atof(v);
     ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
     ctx->tune.trace = getenv("HOP_TRACE") != nullptr;
     ctx->tune.cluster_blocks = getenv("HOP_CLUSTER_BLOCKS") != nullptr;

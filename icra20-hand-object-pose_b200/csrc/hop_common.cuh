@@ -227,6 +227,7 @@ struct HopTuning {
   int fused_slots = 0;        // HOP_FUSED_SLOTS: hypotheses per CTA at a time (0 = the batch's fair share, capped by the CTA's warps)
   int mom_group_chunks = 0;   // HOP_MOM_GROUP: 512-point chunks per work item of icp_moments_kernel (0 = auto)
   int lcp_variant = 0;        // HOP_LCP_VARIANT: resident CTAs per SM of lcp_score_kernel
+  float voxel_scale = 0.7f;   // HOP_VOXEL_SCALE: multiplies the point-spacing estimate of the NN grids' automatic voxel edge (nn_grid.cu: auto_voxel)
   float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
   bool cluster_blocks = false; // HOP_CLUSTER_BLOCKS: hop_cluster_poses_gpu always through the blocked kernels (A/B knob; default: the bit matrix up to 4096 hypotheses)

@@ -223,20 +223,25 @@ void hop_free_nn_grid(NNGridHost *g) {
   delete g;
 }
 
-static float auto_voxel(const hop_cloud *c, float radius, float max_frac) {
-  // point spacing estimate from the bounding-box surface (clouds on this path are surface samples)
+// The voxel edge when the caller names none: `scale` x the point spacing estimated from the bounding-box surface (clouds on this path are
+// surface samples), not below radius / 12 x scale, not above radius x max_frac.  Both hot kernels are bound by the L1TEX data pipe and
+// most of its wavefronts are candidate-list entries: shorter lists beat fewer cells.  Measured at the headline size
+// (10 k-point model, gpurun_out/r03i, r03j): scale 1.0 -> ICP 16.0 ms + LCP 4.6; 0.85 -> 15.5 + 4.2; 0.7 -> 14.9 + 3.9; 0.5 -> 15.4 + 3.5 (and
+// 4x the memory); 1.25 -> 16.9 + 5.2.  0.7: 52 MB instead of 25 MB for the model's ICP grid, +8 % hypotheses/s there, +14 % at 50 k x 50 k,
+// neutral on the small batches and on the frame path.
+static float auto_voxel(const hop_cloud *c, float radius, float max_frac, float scale) {
   float dx = std::max(c->bbox_max[0] - c->bbox_min[0], 1e-6f), dy = std::max(c->bbox_max[1] - c->bbox_min[1], 1e-6f),
         dz = std::max(c->bbox_max[2] - c->bbox_min[2], 1e-6f);
   float area = dx * dy + dy * dz + dz * dx;  // ~ half the box surface
   float spacing = std::sqrt(area / std::max(c->n, 1));
-  return std::min(std::max(spacing, radius / 12.f), radius * max_frac);
+  return std::min(std::max(spacing, radius / 12.f) * scale, radius * max_frac);
 }
 
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
   if (!cloud || cloud->n <= 0 || !(radius > 0.f)) { ctx->err = "hop_build_nn_grid: empty cloud or bad radius"; return HOP_EINVAL; }
   ProfScope ps(ctx, HOP_PROF_NN_BUILD);
   NNGridHost *G = *out ? *out : new NNGridHost();
-  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius, ctx->tune.voxel_max_frac);
+  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius, ctx->tune.voxel_max_frac, ctx->tune.voxel_scale);
   const int64_t kMaxVox = 48ll << 20;
   GridGeom g;
   for (;;) {
