@@ -251,7 +251,7 @@ def measure(ctx, args, wl, wl_name, rank, world, dev, stream, comm_ready, with_c
     hb, he = D.shard_range(H_all, rank, world) if strong else (0, H_all)
     H = he - hb
     FPS = int(wl.get("frames_per_step", 1))   # frames of one rank in one step (C4: 16), one all-gather of winners per step
-    model = ctx.upload_cloud(*model_np)
+    model = ctx.upload_cloud(*model_np).hint_static()   # (what PoseEstimator does with its model clouds)
     icp_p = ctx.icp_params(max_iter=wl["max_iter"], solver=args.solver, pipeline=args.pipeline)
     lcp_p = ctx.lcp_params()
     # per-model structures are built once (like weights): not part of a frame's step

@@ -206,6 +206,7 @@ struct hop_cloud {
   float *d_stage = nullptr;  // raw xyz|nrm|prob staging (capacity * 7 floats)
   float bbox_min[3] = {0, 0, 0}, bbox_max[3] = {0, 0, 0};
   uint64_t version = 0;  // bumped by hop_cloud_update; grids are rebuilt when stale
+  bool is_static = false;  // hop_cloud_hint_static: contents stay (a model): its grids are built once, so they may be finer
   std::vector<NNGridHost *> grids;
   std::vector<uint64_t> grid_version;
   // query-order copy: the same points sorted along a Morton curve, so that the 32 lanes of a warp iterating the cloud fall

@@ -241,7 +241,11 @@ int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel,
   if (!cloud || cloud->n <= 0 || !(radius > 0.f)) { ctx->err = "hop_build_nn_grid: empty cloud or bad radius"; return HOP_EINVAL; }
   ProfScope ps(ctx, HOP_PROF_NN_BUILD);
   NNGridHost *G = *out ? *out : new NNGridHost();
-  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius, ctx->tune.voxel_max_frac, ctx->tune.voxel_scale);
+  // a grid with a small radius (LCP: 1 mm) is capped at a fraction of the radius; for a cloud that stays (hop_cloud_hint_static: the model)
+  // half of it -- the lists of lcp_score_kernel's first query get shorter (its 4.3 ms at the headline size go to 3.5-3.9, gpurun_out/r03l) --
+  // while a per-frame scene grid keeps the whole radius: its build is (radius / edge)^3 scatter work on every frame
+  const float max_frac = cloud->is_static ? std::min(ctx->tune.voxel_max_frac, 0.5f) : ctx->tune.voxel_max_frac;
+  float e = voxel > 0.f ? voxel : auto_voxel(cloud, radius, max_frac, ctx->tune.voxel_scale);
   const int64_t kMaxVox = 48ll << 20;
   GridGeom g;
   for (;;) {
@@ -410,6 +414,13 @@ extern "C" int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float 
   ctx->stream = main_stream;
   if (rc != HOP_OK) return rc;
   HOP_CUDA(ctx, e);
+  return HOP_OK;
+}
+
+extern "C" int hop_cloud_hint_static(hop_ctx *ctx, hop_cloud *cloud, int is_static) {
+  HOP_ENTER(ctx);
+  if (!ctx || !cloud) return HOP_EINVAL;
+  cloud->is_static = is_static != 0;   // (applies to grids built from now on; results do not depend on it)
   return HOP_OK;
 }
 

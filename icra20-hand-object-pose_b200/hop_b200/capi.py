@@ -143,6 +143,7 @@ def load_library():
     L.hop_cloud_prepare_nn.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_int64)]
     L.hop_cloud_prepare_nn_async.argtypes = [_vp, _vp, C.c_float, C.c_float]
     L.hop_cloud_drop_nn.argtypes = [_vp, _vp]
+    L.hop_cloud_hint_static.argtypes = [_vp, _vp, C.c_int]
     L.hop_cloud_nn_query.argtypes = [_vp, _vp, C.c_float, _vp, C.c_int, _vp, _vp]
     L.hop_icp_refine.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
     L.hop_icp_refine_dev.argtypes = [_vp, _vp, _vp, _vp, C.c_int, C.POINTER(IcpParams), _vp, _vp]
@@ -361,6 +362,11 @@ class Cloud:
     def prepare_lcp_scene(self, lcp_params):
         """the scene grid hop_lcp_score's reciprocal term needs (radius lcp.dist * 1.01f, api.cu), built ahead on the second stream"""
         self.prepare_nn_async(float(np.float32(lcp_params.dist) * np.float32(1.01)))
+
+    def hint_static(self, is_static=True):
+        """hop_cloud_hint_static: the cloud is a model (contents stay); grids built afterwards may be finer.  Returns self."""
+        self.ctx._check(self.ctx.L.hop_cloud_hint_static(self.ctx.h, self.handle, int(is_static)))
+        return self
 
     def drop_nn(self):
         self.ctx._check(self.ctx.L.hop_cloud_drop_nn(self.ctx.h, self.handle))

@@ -54,12 +54,12 @@ class PoseEstimator:
 
     def setModel(self, model_xyz, model_nrm, model001_xyz=None, model001_nrm=None):
         """_model (5 mm, ICP / Super4PCS) and _model001 (1 mm, scoring) (main_realdata_auto.cpp:33-38)."""
-        self._model = self.ctx.upload_cloud(model_xyz, model_nrm)
+        self._model = self.ctx.upload_cloud(model_xyz, model_nrm).hint_static()
         self._model_host = (np.asarray(model_xyz, np.float32), np.asarray(model_nrm, np.float32))
         if model001_xyz is None:
             self._model001 = self._model
         else:
-            self._model001 = self.ctx.upload_cloud(model001_xyz, model001_nrm)
+            self._model001 = self.ctx.upload_cloud(model001_xyz, model001_nrm).hint_static()
             self._model001_host = np.asarray(model001_xyz, np.float32)
 
     def setPoseHypos(self, poses, scores=None):

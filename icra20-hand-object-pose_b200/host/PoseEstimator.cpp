@@ -14,6 +14,7 @@ void PoseEstimator::check(int rc, const char *what) {
 PoseEstimator::PoseEstimator(ConfigParser *cfg1, const Cloud &model, const Cloud &model001, hop_ctx *c) : cfg(cfg1), ctx(c), _model(model), _model001(model001) {
   check(hop_cloud_upload(ctx, _model.xyz.data(), _model.nrm.data(), nullptr, (int)_model.size(), &d_model), "upload model");
   check(hop_cloud_upload(ctx, _model001.xyz.data(), _model001.nrm.data(), nullptr, (int)_model001.size(), &d_model001), "upload model001");
+  check(hop_cloud_hint_static(ctx, d_model, 1), "hint model"); check(hop_cloud_hint_static(ctx, d_model001, 1), "hint model001");   // loaded once: finer NN grids
 }
 
 PoseEstimator::~PoseEstimator() {

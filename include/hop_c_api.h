@@ -149,6 +149,10 @@ int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float vox
 int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel);
 /* mark the cloud's cached grids stale (allocations are kept): the next use rebuilds them */
 int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud);
+/* Hint: this cloud's contents stay (the object model, loaded once per PoseEstimator -- PoseEstimator.cpp:22-60).  Grids built for it afterwards
+ * may use finer voxels (more memory, a longer build, shorter candidate lists in every later query).  A performance hint only: every query
+ * is exact either way. */
+int hop_cloud_hint_static(hop_ctx *ctx, hop_cloud *cloud, int is_static);
 /* exact 1-NN of host queries (nq x 3) within the prepared radius: idx = -1 when none. (test / debug entry) */
 int hop_cloud_nn_query(hop_ctx *ctx, hop_cloud *cloud, float radius, const float *queries, int nq, int32_t *idx, float *d2);
 

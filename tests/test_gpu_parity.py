@@ -374,3 +374,20 @@ def test_icp_with_the_hand_base_parameters(ctx):
     dt, dr = synth.pose_error(got, ref)
     assert np.array_equal(cv, rcv) and np.all(dt <= POS_TOL) and np.all(dr <= ROT_TOL), (dt, dr)
     scene.free(); model.free()
+
+
+def test_static_hint_changes_the_grid_not_the_results(ctx):
+    """hop_cloud_hint_static lets a model's grids use finer voxels (lists get shorter); every query stays exact, so poses and scores are
+    the same bits with and without it."""
+    m, mn = synth.make_model("ellipse", 6000, seed=1)
+    s, sn, conf, gt = synth.make_scene("ellipse", 1500, seed=5)
+    hyp = synth.make_hypotheses(gt, 96, seed=6)
+    scene = ctx.upload_cloud(s, sn, conf)
+    plain, hinted = ctx.upload_cloud(m, mn), ctx.upload_cloud(m, mn).hint_static()
+    lp = ctx.lcp_params()
+    st_plain, st_hint = plain.prepare_nn(lp.dist), hinted.prepare_nn(lp.dist)
+    assert st_hint["voxels"] > st_plain["voxels"] and st_hint["max_list"] <= st_plain["max_list"]
+    a = ctx.icp_refine(scene, plain, hyp, ctx.icp_params(max_iter=10))
+    b = ctx.icp_refine(scene, hinted, hyp, ctx.icp_params(max_iter=10))
+    assert all(np.array_equal(x, y) for x, y in zip(a, b))
+    assert np.array_equal(ctx.lcp_score(scene, plain, a[0], lp), ctx.lcp_score(scene, hinted, a[0], lp))
