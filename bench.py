@@ -276,7 +276,7 @@ def measure(ctx, args, wl, wl_name, rank, world, dev, stream, comm_ready, with_c
             d_pose.copy_(d_hyp[fi])  # ICP refines in place; keep the inputs pristine (device-to-device, 64 KB per 1024)
             sc = scenes[fi]
             sc.drop_nn()  # the scene's reciprocal-NN grid is per-frame work: rebuilt inside the timed step ...
-            sc.prepare_lcp_scene(lcp_p)  # ... on the context's second stream, while the ICP runs (the LCP kernel waits for it)
+            sc.prepare_lcp_scene(lcp_p, batch=H)  # ... on the context's second stream, while the ICP runs (the LCP kernel waits for it)
             ctx.icp_refine_dev(sc, model, d_pose.data_ptr(), H, icp_p, d_iters.data_ptr(), d_conv.data_ptr())
             if evs and f == 0: evs[1].record(stream)
             ctx.lcp_score_dev(sc, model, d_pose.data_ptr(), H, lcp_p, d_score.data_ptr())

@@ -428,6 +428,25 @@ int hop_debug_lm_solve(hop_ctx *ctx, const float *sums, int n, float *x_out, int
 }
 
 // ---- K5 -------------------------------------------------------------------------------------------------------
+// The scene grid of the scoring pass (the reciprocal term's nearest scene point): radius = dist with a little head room for rounding,
+// voxel edge by the size of the batch that will query it.  Its build is per-frame work, (radius / edge)^3 scatter operations per scene
+// point; its lists are walked once per hypothesis and matched scene point.  From a few thousand hypotheses up the finer grid pays
+// (10 k x 10 k x 16 384: build 0.2 -> 4 ms on the second stream, hidden behind the ICP; lcp_score_kernel 4.3 -> 3.5 ms); a frame's 100
+// hypotheses, or 4096 on a 2 k-point scene, are better off with the cheap build (gpurun_out/r03l, r03o).
+static const int kLcpFineGridBatch = 8192;
+static float lcp_scene_radius(const hop_lcp_params *p) { return p->dist * 1.01f; }
+static float lcp_scene_voxel(hop_ctx *ctx, hop_cloud *scene, const hop_lcp_params *p, int batch) {
+  return batch >= kLcpFineGridBatch ? hop_auto_voxel(ctx, scene, lcp_scene_radius(p), 0.5f) : 0.f;   // 0 = the cloud's own default
+}
+
+int hop_lcp_prepare_scene_async(hop_ctx *ctx, hop_cloud *scene, const hop_lcp_params *params, int expected_hypotheses) {
+  HOP_ENTER(ctx);
+  if (!ctx || !scene || !params) { if (ctx) ctx->err = "hop_lcp_prepare_scene_async: bad arguments"; return HOP_EINVAL; }
+  if (!(params->dist > 0.f)) { ctx->err = "hop_lcp_prepare_scene_async: dist must be > 0"; return HOP_EINVAL; }
+  if (scene->n <= 0) return HOP_OK;
+  return hop_cloud_prepare_nn_async(ctx, scene, lcp_scene_radius(params), lcp_scene_voxel(ctx, scene, params, expected_hypotheses));
+}
+
 int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const float *d_poses, int H, const hop_lcp_params *params,
                       int use_weights, float *d_scores_out) {
   HOP_ENTER(ctx);
@@ -441,9 +460,9 @@ int hop_lcp_score_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model, const fl
   NNGridHost *Gm = nullptr, *Gs = nullptr;
   int rc = hop_get_nn_grid(ctx, model, params->dist, 0.f, &Gm);
   if (rc != HOP_OK) return rc;
-  // the reciprocal neighbour is at most `dist` away (see lcp_score_kernel); a little head room for rounding
-  // (callers that prefetch this grid with hop_cloud_prepare_nn_async pass the same dist * 1.01f: hop_c_api.h, capi.py prepare_lcp_scene, PoseEstimator.cpp)
-  rc = hop_get_nn_grid(ctx, scene, params->dist * 1.01f, 0.f, &Gs);
+  // the reciprocal neighbour is at most `dist` away (see lcp_score_kernel).  A grid prefetched for this radius (hop_lcp_prepare_scene_async)
+  // is taken as it is, whatever its voxel; otherwise it is built here, sized for this batch
+  rc = hop_get_nn_grid_any(ctx, scene, lcp_scene_radius(params), lcp_scene_voxel(ctx, scene, params, H), &Gs);
   if (rc != HOP_OK) return rc;
   rc = hop_cloud_query_order(ctx, scene);
   if (rc != HOP_OK) return rc;
@@ -511,7 +530,7 @@ int hop_refine_score_select_dev(hop_ctx *ctx, hop_cloud *scene, hop_cloud *model
   if (H > 0) {
     // the scene grid of the scoring pass depends on the frame only: built on the second stream while the ICP runs
     if (scene->n > 0 && model_lcp->n > 0 && lcp->dist > 0.f) {
-      rc = hop_cloud_prepare_nn_async(ctx, scene, lcp->dist * 1.01f, 0.f);
+      rc = hop_cloud_prepare_nn_async(ctx, scene, lcp_scene_radius(lcp), lcp_scene_voxel(ctx, scene, lcp, H));
       if (rc != HOP_OK) return rc;
     }
     rc = hop_icp_refine_dev(ctx, scene, model_icp, d_poses_inout, H, icp, d_iters, d_conv);

@@ -343,8 +343,10 @@ inline void hop_cloud_join_pending(hop_ctx *ctx, hop_cloud *c) {
 // implemented in nn_grid.cu
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
 int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out);
+int hop_get_nn_grid_any(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel_if_built, NNGridHost **out);
 void hop_free_nn_grid(NNGridHost *g);
 int hop_cloud_query_order(hop_ctx *ctx, hop_cloud *cloud);  // (re)builds d_pw_q / d_nv_q when stale
+float hop_auto_voxel(const hop_ctx *ctx, const hop_cloud *cloud, float radius, float max_frac);
 // implemented in icp_lcp.cu
 int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, const NNGridDev &grid, const NNGridDev *scene_grid,
                    float *d_poses, int H, const hop_icp_params &p, int32_t *d_iters, int32_t *d_conv);

@@ -237,6 +237,11 @@ static float auto_voxel(const hop_cloud *c, float radius, float max_frac, float 
   return std::min(std::max(spacing, radius / 12.f) * scale, radius * max_frac);
 }
 
+// the automatic voxel edge with the cap at `max_frac` x radius (callers that know more than the cloud: hop_lcp_scene_voxel, api.cu)
+float hop_auto_voxel(const hop_ctx *ctx, const hop_cloud *cloud, float radius, float max_frac) {
+  return auto_voxel(cloud, radius, std::min(ctx->tune.voxel_max_frac, max_frac), ctx->tune.voxel_scale);
+}
+
 int hop_build_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
   if (!cloud || cloud->n <= 0 || !(radius > 0.f)) { ctx->err = "hop_build_nn_grid: empty cloud or bad radius"; return HOP_EINVAL; }
   ProfScope ps(ctx, HOP_PROF_NN_BUILD);
@@ -349,11 +354,24 @@ int hop_get_nn_grid(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, N
   return get_nn_grid_on_current_stream(ctx, cloud, radius, voxel, out);
 }
 
+// an up-to-date grid of this radius as it is (whatever its voxel edge); built with `voxel_if_built` (0 = automatic) when there is none
+int hop_get_nn_grid_any(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel_if_built, NNGridHost **out) {
+  if (ctx->side && ctx->stream != ctx->side) hop_cloud_join_pending(ctx, cloud);
+  for (size_t i = 0; i < cloud->grids.size(); ++i) {
+    NNGridHost *G = cloud->grids[i];
+    if (std::fabs(G->radius - radius) <= 1e-9f + 1e-6f * radius && cloud->grid_version[i] == cloud->version) { *out = G; return HOP_OK; }
+  }
+  return get_nn_grid_on_current_stream(ctx, cloud, radius, voxel_if_built, out);
+}
+
 static int get_nn_grid_on_current_stream(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel, NNGridHost **out) {
   for (size_t i = 0; i < cloud->grids.size(); ++i) {
     NNGridHost *G = cloud->grids[i];
-    if (std::fabs(G->radius - radius) <= 1e-9f + 1e-6f * radius && (voxel <= 0.f || std::fabs(G->voxel - voxel) < 1e-9f)) {
-      if (cloud->grid_version[i] != cloud->version) {
+    // one grid per (cloud, radius): a request that names another voxel edge rebuilds it in place (an edge derived from the cloud's
+    // extent changes a little with every frame: a grid per edge would pile up)
+    if (std::fabs(G->radius - radius) <= 1e-9f + 1e-6f * radius) {
+      const bool other_voxel = voxel > 0.f && std::fabs(G->voxel - voxel) > 1e-6f * voxel;
+      if (cloud->grid_version[i] != cloud->version || other_voxel) {
         int rc = hop_build_nn_grid(ctx, cloud, radius, voxel, &cloud->grids[i]);
         if (rc != HOP_OK) return rc;
         cloud->grid_version[i] = cloud->version;

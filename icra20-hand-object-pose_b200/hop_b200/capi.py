@@ -142,6 +142,7 @@ def load_library():
     L.hop_cloud_size.argtypes = [_vp]
     L.hop_cloud_prepare_nn.argtypes = [_vp, _vp, C.c_float, C.c_float, C.POINTER(C.c_int64)]
     L.hop_cloud_prepare_nn_async.argtypes = [_vp, _vp, C.c_float, C.c_float]
+    L.hop_lcp_prepare_scene_async.argtypes = [_vp, _vp, _vp, C.c_int]
     L.hop_cloud_drop_nn.argtypes = [_vp, _vp]
     L.hop_cloud_hint_static.argtypes = [_vp, _vp, C.c_int]
     L.hop_cloud_nn_query.argtypes = [_vp, _vp, C.c_float, _vp, C.c_int, _vp, _vp]
@@ -359,9 +360,10 @@ class Cloud:
         """hop_cloud_prepare_nn_async: the grid is built on the context's second stream while the main stream goes on."""
         self.ctx._check(self.ctx.L.hop_cloud_prepare_nn_async(self.ctx.h, self.handle, radius, voxel))
 
-    def prepare_lcp_scene(self, lcp_params):
-        """the scene grid hop_lcp_score's reciprocal term needs (radius lcp.dist * 1.01f, api.cu), built ahead on the second stream"""
-        self.prepare_nn_async(float(np.float32(lcp_params.dist) * np.float32(1.01)))
+    def prepare_lcp_scene(self, lcp_params, batch=0):
+        """hop_lcp_prepare_scene_async: the scene grid hop_lcp_score's reciprocal term needs, built ahead on the second stream; `batch` =
+        how many hypotheses will be scored against this frame (chooses the voxel edge)."""
+        self.ctx._check(self.ctx.L.hop_lcp_prepare_scene_async(self.ctx.h, self.handle, C.byref(lcp_params), int(batch)))
 
     def hint_static(self, is_static=True):
         """hop_cloud_hint_static: the cloud is a model (contents stay); grids built afterwards may be finer.  Returns self."""

@@ -147,6 +147,10 @@ int hop_cloud_prepare_nn(hop_ctx *ctx, hop_cloud *cloud, float radius, float vox
  * hop_cloud_prepare_nn_async(scene, lcp.dist * 1.01f, 0) right after the upload (PoseEstimator::setCurScene) lets hop_lcp_score's
  * scene grid be built while hop_icp_refine runs.  Results are identical to the implicit build. */
 int hop_cloud_prepare_nn_async(hop_ctx *ctx, hop_cloud *cloud, float radius, float voxel);
+/* The scene grid hop_lcp_score needs for its reciprocal term, built ahead like hop_cloud_prepare_nn_async(scene, dist * 1.01, ...) with the
+ * voxel edge chosen for the number of hypotheses that will be scored against this frame (a batch of thousands repays a finer, slower-to-build
+ * grid; a frame's hundred do not).  PoseEstimator::setCurScene (PoseEstimator.cpp:22-60 sets the scene once per frame) is where a shim calls it. */
+int hop_lcp_prepare_scene_async(hop_ctx *ctx, hop_cloud *scene, const hop_lcp_params *params, int expected_hypotheses);
 /* mark the cloud's cached grids stale (allocations are kept): the next use rebuilds them */
 int hop_cloud_drop_nn(hop_ctx *ctx, hop_cloud *cloud);
 /* Hint: this cloud's contents stay (the object model, loaded once per PoseEstimator -- PoseEstimator.cpp:22-60).  Grids built for it afterwards
