@@ -218,7 +218,7 @@ def stage_ms(ctx, args):
     out = {}
 
     def run():
-        out["r"] = ctx.super4pcs_run(plans["p"], capacity=400000)
+        out["r"] = ctx.super4pcs_run(plans["p"], capacity=20000)   # (the reference reserves 20000, super4pcs.h:134)
 
     dt, prof = timed(run)
     res["super4pcs_registration"] = {"plan_ms": t_plan, "ppf_table_build_ms_once_per_model": t_table, "ppf_keys": int(len(keys)), "device_e2e_ms": dt, "k2a_pairs_ms": prof.get("s4pcs_pairs"), "k2b_join_ms": prof.get("s4pcs_join"),

@@ -578,8 +578,8 @@ class Context:
 
     def super4pcs_run(self, plan, capacity=20000):
         """Device part of a planned registration.  Returns (poses (n,4,4) model -> scene, lcp (n,)) in (trial, quad) order."""
-        poses = np.zeros((capacity, 16), np.float32)
-        lcp = np.zeros(capacity, np.float32)
+        poses = np.empty((capacity, 16), np.float32)   # (only the first n rows are defined afterwards)
+        lcp = np.empty(capacity, np.float32)
         n = C.c_int32(0)
         self._check(self.L.hop_super4pcs_run(self.h, plan.h, _ptr(poses), _ptr(lcp), capacity, C.byref(n)))
         k = min(int(n.value), capacity)
