@@ -42,7 +42,6 @@ typedef std::array<float, 3> V3;
 
 inline V3 sub(const float *a, const float *b) { return V3{a[0] - b[0], a[1] - b[1], a[2] - b[2]}; }
 inline float dot(const V3 &a, const V3 &b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
-inline float dotp(const float *a, const float *b) { return a[0] * b[0] + (a[1] * b[1] + a[2] * b[2]); }
 inline float sqnorm(const V3 &a) { return dot(a, a); }
 inline float norm(const V3 &a) { return std::sqrt(sqnorm(a)); }
 inline V3 normalized(const V3 &a) {  // Eigen: z = squaredNorm(); z > 0 ? a / sqrt(z) : a
@@ -505,7 +504,7 @@ struct Planner {
         if (base4 != -1) {
           b3d[3] = P[base4];
           int id[4] = {base1, base2, base3, base4};
-          float inv1, inv2;
+          float inv1 = 0.f, inv2 = 0.f;
           if (try_quadrilateral(b3d, inv1, inv2, id)) {
             t.base_ok = 1;
             for (int k = 0; k < 4; ++k) { t.base[k] = id[k]; t.b[k] = b3d[k]; }
