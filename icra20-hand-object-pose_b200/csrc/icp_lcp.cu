@@ -937,7 +937,9 @@ static cudaError_t launch_fused(hop_ctx *ctx, FusedArgs f, int H) {
 // thread: the rest of the 256 KB stays L1.
 template <int SOLVER>
 static cudaError_t launch_fused_solver(hop_ctx *ctx, const FusedArgs &f, int H, bool small_ctas, bool prof_on) {
-  if (prof_on) return small_ctas ? launch_fused<128, 512, true, 6, SOLVER>(ctx, f, H) : launch_fused<256, 1024, true, 3, SOLVER>(ctx, f, H);
+  if constexpr (SOLVER == 0) {   // (the cycle accounting exists for the parity solver only)
+    if (prof_on) return small_ctas ? launch_fused<128, 512, true, 6, SOLVER>(ctx, f, H) : launch_fused<256, 1024, true, 3, SOLVER>(ctx, f, H);
+  }
   return small_ctas ? launch_fused<128, 512, false, 8, SOLVER>(ctx, f, H) : launch_fused<256, 1024, false, 3, SOLVER>(ctx, f, H);
 }
 
