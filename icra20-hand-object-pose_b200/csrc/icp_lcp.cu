@@ -922,10 +922,11 @@ static cudaError_t launch_fused(hop_ctx *ctx, FusedArgs f, int H) {
   if (e != cudaSuccess) return e;
   const int grid_ctas = (int)std::min<long>((long)H, (long)ctx->sm_count * MINB);
   // Slots per CTA.  Since the solve became short against a pass over the scene (lm_replay_warp.cuh) the parallel solves of a round buy
-  // less than its barrier costs (every slot waits for the round's longest solve): 128-thread CTAs carry at most two hypotheses, and a
-  // 256-thread CTA with three or fewer to do takes them one after the other (C2: 0.96 -> 0.85 ms, headline 16.2 -> 16.0, gpurun_out/r02s_*)
+  // less than its barrier costs (every slot waits for the round's longest solve): 128-thread CTAs carry two hypotheses only when each has
+  // more than four to do, and a 256-thread CTA with three or fewer takes them one after the other (C2: 0.96 -> 0.85 ms, headline 16.2 -> 16.0;
+  // profiles/r02_experiments.txt, runs r02s, r03s)
   const int fair = (H + grid_ctas - 1) / grid_ctas;
-  const int slots = THREADS == 128 ? std::min(fair, 2) : (fair <= 3 ? 1 : fair);
+  const int slots = THREADS == 128 ? (fair <= 4 ? 1 : 2) : (fair <= 3 ? 1 : fair);
   f.slots_max = ctx->tune.fused_slots > 0 ? ctx->tune.fused_slots : slots;
   icp_fused_kernel<THREADS, CHUNK, PROF, MINB, SOLVER><<<grid_ctas, THREADS, smem, ctx->stream>>>(f);
   return cudaGetLastError();
@@ -1094,7 +1095,9 @@ int hop_launch_icp(hop_ctx *ctx, const CloudDev &scene, const CloudDev &model, c
     f.prof = prof_on ? ctx->d_fused_prof : nullptr;
     {
       ProfScope ps(ctx, HOP_PROF_ICP_FUSED);
-      const bool small_ctas = variant == 2 || (variant == 0 && (long)H >= 24L * ctx->sm_count);
+      // by the batch's work, hypotheses x scene points (24 x SMs hypotheses at the 2 k-point scene the rule was measured on; a 10 k-point
+      // scene reaches it at a fifth of that: one rank's 2048-hypothesis share under strong scaling runs 4 % faster with the small CTAs)
+      const bool small_ctas = variant == 2 || (variant == 0 && (long long)H * scene.n_padded >= 24LL * ctx->sm_count * 2048LL);
       HOP_CUDA(ctx, p.solver == 0   ? launch_fused_solver<0>(ctx, f, H, small_ctas, prof_on)
                     : p.solver == 1 ? launch_fused_solver<1>(ctx, f, H, small_ctas, prof_on)
                                     : launch_fused_solver<2>(ctx, f, H, small_ctas, prof_on));

@@ -178,6 +178,10 @@ def workload(name):
         "C4": dict(model="ellipse", n_scene=2000, n_model=10000, H=4096, max_iter=10, frames_per_step=16),
         "C5": dict(model="ellipse", n_scene=50000, n_model=50000, H=65536, max_iter=10),
         "tiny": dict(model="ellipse", n_scene=500, n_model=2000, H=64, max_iter=10),
+        # one rank's share of the headline frame under strong scaling (N = 8, 4, 2): batch-shape experiments
+        "shard2k": dict(model="ellipse", n_scene=10000, n_model=10000, H=2048, max_iter=10),
+        "shard4k": dict(model="ellipse", n_scene=10000, n_model=10000, H=4096, max_iter=10),
+        "shard8k": dict(model="ellipse", n_scene=10000, n_model=10000, H=8192, max_iter=10),
     }
     return table[name]
 
