@@ -6,14 +6,15 @@
 // slowest hypothesis' chain IS the kernel time.  Here the 6-vectors and the 6x6 factors are DISTRIBUTED:
 //   lane j (mod 8)  owns parameter j: its diag entry, column j of J^T J through the Cholesky factorisation (lane 6: the column
 //                   J^T f, which the same elimination turns into Q^T f), row j of R for the back substitution;
-//   lane i (mod 16) owns row i of the 13x13 moment matrix (registers) for y^T A y.
-// Scalars of MINPACK's control flow (fnorm, par, delta, ratio ...) are replicated.  Every reduction is an xor butterfly, whose
-// result is bitwise the same in all lanes (a + b == b + a at every level), so the warp never diverges on them.  The float
-// operations of MINPACK's algebra keep the order of the scalar program; sums carried in double (norms, Gram products)
-// associate differently, which moves a float result by at most its last bit.  lmpar's iteration on the LM parameter (the Gauss-Newton step
-// leaves the trust region: 3 % of the trial steps, but most of those of the hardest hypotheses, where the replicated rolled
-// version cost 15-30 k cycles per qrsolv) is distributed the same way; only a rank-deficient R falls back to lm_replay.cuh's
-// scalar lmpar_iterate, fed from the factor in shared memory.
+//   lane i (mod 16) owns row i of the 13x13 moment matrix (shared memory) for y^T A y.
+// Scalars of MINPACK's control flow (fnorm, par, delta, ratio ...) are replicated.  Reductions either meet in shared memory and are
+// added by every lane in the same order, or are xor butterflies (bitwise the same in all lanes: a + b == b + a at every level), so the
+// warp never diverges on them.  The float operations of MINPACK's algebra keep the order of the scalar program; sums carried in double
+// (norms, Gram products) associate differently, which moves a float result by at most its last bit.  lmpar's iteration on the LM
+// parameter (the Gauss-Newton step leaves the trust region: 3 % of the trial steps, but most of those of the hardest hypotheses, where
+// the replicated rolled version cost 15-30 k cycles per qrsolv) is distributed the same way, and its inner solve is the Cholesky
+// factorisation of J^T J + par D^2 instead of qrsolv's chain of Givens rotations (lmpar_iterate_w); only a rank-deficient R falls
+// back to lm_replay.cuh's scalar lmpar_iterate, fed from the factor in shared memory.
 //
 // The scalar program stays the specification: tests/test_gpu_lm.py solves the same moment matrices with this file (through
 // hop_debug_lm_solve) and with the host build of lm_replay.cuh, which tests/test_lm_replay.py pins against the reference tree's
