@@ -604,6 +604,15 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
   return HOP_OK;
 }
 
+// diagnostics: `draws` indices from weights w[0..n) with the planner's table-free replica of std::discrete_distribution<int>, engine
+// std::mt19937(seed) -- tests/test_s4pcs_plan.py compares the stream with the standard library's own
+int hop_debug_draw_discrete(const float *w, int n, uint32_t seed, int draws, int32_t *out) {
+  if (n < 0 || draws < 0 || (n > 0 && !w) || (draws > 0 && !out)) return HOP_EINVAL;
+  std::mt19937 engine(seed);
+  for (int k = 0; k < draws; ++k) out[k] = Planner::draw_discrete(w, n, engine);
+  return HOP_OK;
+}
+
 int hop_s4pcs_plan_create(const float *P_xyz, const float *P_nrm, const float *P_prob, int nP, const float *Q_xyz, const float *Q_nrm,
                           int nQ, const int32_t *ppf_keys, int n_keys, const hop_s4pcs_options *opt, hop_s4pcs_plan **out) {
   return plan_create(nullptr, P_xyz, P_nrm, P_prob, nP, Q_xyz, Q_nrm, nQ, ppf_keys, n_keys, opt, out);

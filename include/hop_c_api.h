@@ -241,6 +241,9 @@ int hop_s4pcs_plan_get(const hop_s4pcs_plan *plan, float *Pc, float *Qc, int32_t
 /* after hop_super4pcs_run with keep_intermediates: trial_ranges T x 6 (pairs1 begin,end, pairs2 begin,end, quads begin,end),
  * pairs n x 2, quads m x 4 (indices into the sampled Q) */
 int hop_s4pcs_plan_intermediates(const hop_s4pcs_plan *plan, int32_t *trial_ranges, int32_t *pairs, int32_t *quads);
+/* diagnostics: the planner's replica of std::discrete_distribution<int>(w, w + n) drawing from std::mt19937(seed) (matchBase.hpp:120-140
+ * builds one per draw; the planner reproduces the draws without building the table) */
+int hop_debug_draw_discrete(const float *w, int n, uint32_t seed, int draws, int32_t *out);
 /* gr::computePPF for one pair (exposed for tests): key = 4 ints */
 void hop_compute_ppf(const float *p1, const float *n1, const float *p2, const float *n2, int32_t *key);
 

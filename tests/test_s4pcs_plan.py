@@ -89,3 +89,32 @@ def test_plan_from_a_membership_matrix_equals_the_host_plan(name, seed, ns, monk
     assert host.keys() == bits.keys() and int(np.sum(host["base_ok"])) >= 5
     for k in host:
         assert np.array_equal(np.asarray(host[k]), np.asarray(bits[k])), k
+
+
+def test_table_free_discrete_draws_equal_the_standard_library():
+    """The planner draws from std::discrete_distribution's tables without building them (k_s4pcs_plan.cu: draw_discrete).  Against the
+    standard library itself (tests/support/discrete_ref.cpp builds a distribution per draw, like matchBase.hpp:120-140): the same index
+    stream for random weights, zero weights, weights of very different size, one entry, no entry."""
+    import ctypes as C
+    import os
+    import subprocess
+    sup = os.path.join(os.path.dirname(os.path.abspath(__file__)), "support")
+    subprocess.run(["make", "-C", sup], check=True, capture_output=True)
+    ref = C.CDLL(os.path.join(sup, "libdiscrete_ref.so"))
+    lib = capi.load_library()
+    f32p = np.ctypeslib.ndpointer(dtype=np.float32, flags="C_CONTIGUOUS")
+    i32p = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+    ref.hop_ref_draw_discrete.argtypes = [f32p, C.c_int, C.c_uint32, C.c_int, i32p]
+    lib.hop_debug_draw_discrete.argtypes = [f32p, C.c_int, C.c_uint32, C.c_int, i32p]
+    rng = np.random.default_rng(1)
+    cases = [rng.random(n).astype(np.float32) for n in (2, 3, 17, 100, 959, 4096)]
+    cases += [np.where(rng.random(500) < 0.6, 0, rng.random(500)).astype(np.float32)]            # many zero weights
+    cases += [(rng.random(300) * 10.0 ** rng.integers(-20, 5, 300)).astype(np.float32)]          # 25 orders of magnitude
+    cases += [np.full(64, 0.5, np.float32) * np.float32(0.5) ** rng.integers(0, 12, 64)]        # the planner's own: powers of the dispersion
+    cases += [np.array([3.0], np.float32), np.zeros(0, np.float32)]
+    for w in cases:
+        w = np.ascontiguousarray(w, np.float32)
+        a, b = np.zeros(4000, np.int32), np.zeros(4000, np.int32)
+        ref.hop_ref_draw_discrete(w, len(w), 7, len(a), a)
+        assert lib.hop_debug_draw_discrete(w, len(w), 7, len(b), b) == 0
+        assert np.array_equal(a, b), len(w)
