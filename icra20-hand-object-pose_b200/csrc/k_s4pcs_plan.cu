@@ -152,7 +152,8 @@ struct PpfBits {
   uint64_t *d_keys = nullptr;
   uint32_t *d_member = nullptr, *d_ambig = nullptr;
   int *d_rows = nullptr;
-  std::vector<uint32_t> member, ambig;                       // full mode: n x words
+  std::vector<uint32_t> member, ambig;                       // full mode: n x words (backing store when the matrix was made on the host)
+  const uint32_t *member_p = nullptr, *ambig_p = nullptr;    // full mode: the matrices (the context's pinned buffer after a device build)
   std::unordered_map<int, std::pair<std::vector<uint32_t>, std::vector<uint32_t>>> rows;   // row mode: fetched on demand
   int launches = 0;
   // stream-ordered allocations from the context's pool: a plan is made once per frame
@@ -179,16 +180,20 @@ struct PpfBits {
     if (full) {
       ppf_rows_kernel<<<dim3((n + 255) / 256, n), 256, 0, ctx->stream>>>(d_pos, d_nrm, n, nullptr, n, d_keys, n_keys, d_member, d_ambig, words);
       ctx->launches += 1; ++launches;
-      member.resize((size_t)n * words); ambig.resize((size_t)n * words);
-      HOP_CUDA(ctx, cudaMemcpyAsync(member.data(), d_member, sizeof(uint32_t) * member.size(), cudaMemcpyDeviceToHost, ctx->stream));
-      HOP_CUDA(ctx, cudaMemcpyAsync(ambig.data(), d_ambig, sizeof(uint32_t) * ambig.size(), cudaMemcpyDeviceToHost, ctx->stream));
+      // into pinned memory: a pageable destination makes each copy a staged, synchronous one (1 MB at 2 k points)
+      const size_t cnt = (size_t)n * words;
+      uint32_t *pin = (uint32_t *)ctx->ensure_pinned(2 * sizeof(uint32_t) * cnt);
+      if (!pin) { ctx->err = "hop_s4pcs_plan_create_gpu: pinned buffer allocation failed"; return HOP_ENOMEM; }
+      HOP_CUDA(ctx, cudaMemcpyAsync(pin, d_member, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+      HOP_CUDA(ctx, cudaMemcpyAsync(pin + cnt, d_ambig, sizeof(uint32_t) * cnt, cudaMemcpyDeviceToHost, ctx->stream));
+      member_p = pin; ambig_p = pin + cnt;
     }
     HOP_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     return HOP_OK;
   }
   // the row of point a (row mode: one launch + copy per first use)
   bool row(int a, const uint32_t *&m, const uint32_t *&am) {
-    if (full) { m = &member[(size_t)a * words]; am = &ambig[(size_t)a * words]; return true; }
+    if (full) { m = member_p + (size_t)a * words; am = ambig_p + (size_t)a * words; return true; }
     auto it = rows.find(a);
     if (it == rows.end()) {
       if (cudaMemcpyAsync(d_rows, &a, sizeof(int), cudaMemcpyHostToDevice, ctx->stream) != cudaSuccess) return false;
@@ -209,7 +214,8 @@ struct PpfBits {
 
 struct Planner {
   hop_s4pcs_plan &pl;
-  std::unordered_set<uint64_t> keys;
+  std::unordered_set<uint64_t> keys;       // host path: a lookup per pair, millions per plan
+  std::vector<uint64_t> sorted_keys;       // device path: the table the membership kernel searches; the host only looks up the flagged pairs
   std::vector<float> point_probs;   // _point_probs (anneals across trials)
   std::mt19937 random_generator;    // randomGenerator_
   std::mt19937 point_index_engine;  // _point_index_engine, seeded 0 (matchBase.hpp:76)
@@ -223,7 +229,8 @@ struct Planner {
     int k[4];
     compute_ppf(a, b, k);
     if (k[0] < 0 || k[0] > 65535 || k[1] < 0 || k[1] > 65535 || k[2] < 0 || k[2] > 65535 || k[3] < 0 || k[3] > 65535) return false;
-    return keys.count(pack_key(k)) != 0;
+    const uint64_t key = pack_key(k);
+    return sorted_keys.empty() ? keys.count(key) != 0 : std::binary_search(sorted_keys.begin(), sorted_keys.end(), key);
   }
   // membership of the pair of scene points (a, b): a bit of the device matrix, the host formula for flagged pairs
   bool has_ppf_idx(int a, int b) const {
@@ -566,9 +573,17 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
   Planner planner(*pl);
   {
     HopTraceScope ts(ctx, "  plan: key set");
+    const bool device_path = ctx != nullptr || getenv("HOP_PLAN_HOSTBITS") != nullptr;
+    if (device_path) planner.sorted_keys.reserve((size_t)n_keys);
     for (int i = 0; i < n_keys; ++i) {
       const int k[4] = {ppf_keys[4 * i], ppf_keys[4 * i + 1], ppf_keys[4 * i + 2], ppf_keys[4 * i + 3]};
-      if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) planner.keys.insert(pack_key(k));
+      if (k[0] >= 0 && k[0] <= 65535 && k[1] >= 0 && k[1] <= 65535 && k[2] >= 0 && k[2] <= 65535 && k[3] >= 0 && k[3] <= 65535) {
+        if (device_path) planner.sorted_keys.push_back(pack_key(k)); else planner.keys.insert(pack_key(k));
+      }
+    }
+    if (device_path) {
+      std::sort(planner.sorted_keys.begin(), planner.sorted_keys.end());
+      planner.sorted_keys.erase(std::unique(planner.sorted_keys.begin(), planner.sorted_keys.end()), planner.sorted_keys.end());
     }
   }
   {
@@ -578,9 +593,7 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
   PpfBits bits;
   if (ctx && pl->P.size() >= 4 && pl->Q.size() >= 4) {
     HopTraceScope ts(ctx, "  plan: PPF membership on the device");
-    std::vector<uint64_t> sorted(planner.keys.begin(), planner.keys.end());
-    std::sort(sorted.begin(), sorted.end());
-    const int rc = bits.init(ctx, pl->P, sorted);
+    const int rc = bits.init(ctx, pl->P, planner.sorted_keys);
     if (rc != HOP_OK) { delete pl; return rc; }
     planner.bits = &bits;
   } else if (!ctx && getenv("HOP_PLAN_HOSTBITS")) {
@@ -592,6 +605,7 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
     for (int a = 0; a < n; ++a)
       for (int b = 0; b < n; ++b)
         if (a != b && planner.has_ppf(pl->P[a], pl->P[b])) bits.member[(size_t)a * bits.words + (b >> 5)] |= 1u << (b & 31);
+    bits.member_p = bits.member.data(); bits.ambig_p = bits.ambig.data();
     planner.bits = &bits;
   }
   {
