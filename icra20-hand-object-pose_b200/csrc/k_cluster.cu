@@ -264,6 +264,8 @@ extern "C" int hop_cluster_poses_gpu(hop_ctx *ctx, const float *poses, const flo
   for (int k = 0; k < 3; ++k) p.sym[k] = (float)((double)symmetry_deg[k] / 180 * M_PI);
   p.x_star = geodesic_gate(p.radian_thres);
   std::vector<ClFeat> feat(n);
+  // (three atan2, a sin / cos and a sqrt per hypothesis with the host's libm: 0.4 ms of a 0.5 ms call at 2.8 k hypotheses on one thread)
+#pragma omp parallel for schedule(static) if (n >= 512)
   for (int k = 0; k < n; ++k) {
     const float *P = poses + 16 * (size_t)order[k];
     const Euler e = euler_zyx(P);
