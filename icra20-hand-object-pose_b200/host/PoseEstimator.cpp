@@ -169,7 +169,8 @@ bool PoseEstimator::runSuper4pcs(const std::vector<int32_t> &ppf_keys) {
                                  ppf_keys.data(), (int)(ppf_keys.size() / 4), &o, &plan);
   if (rc != HOP_OK) { fprintf(stderr, "hop_s4pcs_plan_create failed (%d)\n", rc); return false; }
   const int cap = cfg->b200_max_hypotheses;   // the reference reserves 20000 (super4pcs.h:134)
-  std::vector<float> poses(16 * (size_t)cap), lcp(cap);
+  std::vector<float> &poses = _s4_poses, &lcp = _s4_lcp;
+  if (poses.size() < 16 * (size_t)cap) { poses.resize(16 * (size_t)cap); lcp.resize((size_t)cap); }
   int32_t n = 0;
   rc = hop_super4pcs_run(ctx, plan, poses.data(), lcp.data(), cap, &n);
   if (rc == HOP_OK && n > cap) {

@@ -56,6 +56,7 @@ class PoseEstimator {
   hop_cloud *d_scene = nullptr, *d_model = nullptr, *d_model001 = nullptr;
   // what refineByICP's single device visit brought back for selectBest: refined poses (n x 16) and their LCP scores
   std::vector<float> _scored_poses, _scored_lcp;
+  std::vector<float> _s4_poses, _s4_lcp;   // runSuper4pcs' receive buffers, kept from frame to frame (1.3 MB: zero-filling fresh pages was ~0.1 ms a frame)
   float _scored_lcp_dist = 0.f, _scored_lcp_angle = 0.f;
   std::map<std::string, hop_mesh *> _meshes;
   std::vector<float> _obj_mesh_V;      // _obj_mesh (model frame), kept for the renderer
