@@ -55,22 +55,48 @@ __device__ __forceinline__ void atomic_max_f(float *a, float v) {
 __device__ __forceinline__ bool finite3(float x, float y, float z) { return isfinite(x) && isfinite(y) && isfinite(z); }
 
 // Utils::readDepthImage + convert3dOrganized + PassThrough(z, 0.1, 2.0): valid pixel -> (x, y, z, confidence 1)
-__global__ void backproject_kernel(const uint16_t *__restrict__ depth_mm, int w, int h, float fx, float fy, float cx, float cy,
-                                   float4 *__restrict__ pts, unsigned char *__restrict__ flag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= w * h) return;
-  const int u = i / w, v = i - u * w;
-  float d = __double2float_rn((double)(float)depth_mm[i] * 0.001);   // (float)depthShort * SR300_DEPTH_UNIT: the unit is a double literal (Utils.cpp:44)
-  if ((double)d > 2.0 || (double)d < 0.1) d = 0.f;
-  const bool ok = (double)d > 0.1 && (double)d < 2.0;
-  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
-  if (ok) {
-    p.x = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cx), d), fx);
-    p.y = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cy), d), fy);
-    p.z = d;
+// bounds[0..2] = min, [3..5] = max over the points a stage KEEPS, accumulated by the stage's own kernel (all 32 lanes call): the next
+// stage's voxel geometry then comes back with the kept count in one round trip instead of a bounds kernel and a second one
+__device__ __forceinline__ void warp_bounds(bool keep, float x, float y, float z, float *__restrict__ bounds) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  if (keep && finite3(x, y, z)) { mn[0] = mx[0] = x; mn[1] = mx[1] = y; mn[2] = mx[2] = z; }
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xffffffffu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xffffffffu, mx[k], o));
+    }
   }
-  pts[i] = p;
-  flag[i] = ok ? 1 : 0;
+  if ((threadIdx.x & 31) == 0) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      if (mn[k] != FLT_MAX) atomic_min_f(&bounds[k], mn[k]);
+      if (mx[k] != -FLT_MAX) atomic_max_f(&bounds[3 + k], mx[k]);
+    }
+  }
+}
+
+__global__ void backproject_kernel(const uint16_t *__restrict__ depth_mm, int w, int h, float fx, float fy, float cx, float cy,
+                                   float4 *__restrict__ pts, unsigned char *__restrict__ flag, float *__restrict__ bounds) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const bool in = i < w * h;
+  bool ok = false;
+  float4 p = make_float4(0.f, 0.f, 0.f, 1.f);
+  if (in) {
+    const int u = i / w, v = i - u * w;
+    float d = __double2float_rn((double)(float)depth_mm[i] * 0.001);   // (float)depthShort * SR300_DEPTH_UNIT: the unit is a double literal (Utils.cpp:44)
+    if ((double)d > 2.0 || (double)d < 0.1) d = 0.f;
+    ok = (double)d > 0.1 && (double)d < 2.0;
+    if (ok) {
+      p.x = __fdiv_rn(__fmul_rn(__fsub_rn((float)v, cx), d), fx);
+      p.y = __fdiv_rn(__fmul_rn(__fsub_rn((float)u, cy), d), fy);
+      p.z = d;
+    }
+    pts[i] = p;
+    flag[i] = ok ? 1 : 0;
+  }
+  if (bounds) warp_bounds(ok, p.x, p.y, p.z, bounds);
 }
 
 // bounds[0..2] = min, [3..5] = max over finite points
@@ -147,14 +173,19 @@ __device__ __forceinline__ float xf_row(const Xf &T, int r, float x, float y, fl
 
 // camera -> hand base, PassThrough z / x / y (lo <= v <= hi, finite), hand base -> camera
 __global__ void crop_kernel(const float4 *__restrict__ pts, int n, Xf T, Xf Ti, float3 lo, float3 hi, float4 *__restrict__ out,
-                            unsigned char *__restrict__ flag) {
+                            unsigned char *__restrict__ flag, float *__restrict__ bounds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
-  const float x = xf_row(T, 0, p.x, p.y, p.z), y = xf_row(T, 1, p.x, p.y, p.z), z = xf_row(T, 2, p.x, p.y, p.z);
-  const bool ok = finite3(x, y, z) && !(z < lo.z || z > hi.z) && !(x < lo.x || x > hi.x) && !(y < lo.y || y > hi.y);
-  out[i] = make_float4(xf_row(Ti, 0, x, y, z), xf_row(Ti, 1, x, y, z), xf_row(Ti, 2, x, y, z), p.w);
-  flag[i] = ok ? 1 : 0;
+  bool ok = false;
+  float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    const float4 p = pts[i];
+    const float x = xf_row(T, 0, p.x, p.y, p.z), y = xf_row(T, 1, p.x, p.y, p.z), z = xf_row(T, 2, p.x, p.y, p.z);
+    ok = finite3(x, y, z) && !(z < lo.z || z > hi.z) && !(x < lo.x || x > hi.x) && !(y < lo.y || y > hi.y);
+    q = make_float4(xf_row(Ti, 0, x, y, z), xf_row(Ti, 1, x, y, z), xf_row(Ti, 2, x, y, z), p.w);
+    out[i] = q;
+    flag[i] = ok ? 1 : 0;
+  }
+  if (bounds) warp_bounds(ok, q.x, q.y, q.z, bounds);
 }
 
 struct CellGeom { float inv; int mn[3], dim[3]; };
@@ -247,16 +278,20 @@ __global__ void normals_kernel(const float4 *__restrict__ pts, int n, const floa
 
 // removeAllNaN + pcl::flipNormalTowardsViewpoint(origin) + confidence 1 (main_realdata_auto.cpp:160-177)
 __global__ void finish_kernel(const float4 *__restrict__ pts, const float4 *__restrict__ nrm, int n, float4 *__restrict__ out_pts,
-                              float4 *__restrict__ out_nrm, unsigned char *__restrict__ flag) {
+                              float4 *__restrict__ out_nrm, unsigned char *__restrict__ flag, float *__restrict__ bounds) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  const float4 p = pts[i];
-  float4 q = nrm[i];
-  const bool ok = finite3(p.x, p.y, p.z) && finite3(q.x, q.y, q.z);
-  if (__fsub_rn(__fsub_rn(__fmul_rn(-p.x, q.x), __fmul_rn(p.y, q.y)), __fmul_rn(p.z, q.z)) < 0.f) { q.x = -q.x; q.y = -q.y; q.z = -q.z; }
-  out_pts[i] = make_float4(p.x, p.y, p.z, 1.f);
-  out_nrm[i] = q;
-  flag[i] = ok ? 1 : 0;
+  bool ok = false;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i < n) {
+    p = pts[i];
+    float4 q = nrm[i];
+    ok = finite3(p.x, p.y, p.z) && finite3(q.x, q.y, q.z);
+    if (__fsub_rn(__fsub_rn(__fmul_rn(-p.x, q.x), __fmul_rn(p.y, q.y)), __fmul_rn(p.z, q.z)) < 0.f) { q.x = -q.x; q.y = -q.y; q.z = -q.z; }
+    out_pts[i] = make_float4(p.x, p.y, p.z, 1.f);
+    out_nrm[i] = q;
+    flag[i] = ok ? 1 : 0;
+  }
+  if (bounds) warp_bounds(ok, p.x, p.y, p.z, bounds);
 }
 
 // compacted (xyz, conf) / normal arrays -> the cloud's padded streams
@@ -276,7 +311,9 @@ __global__ void to_cloud_kernel(const float4 *__restrict__ pts, const float4 *__
 inline int blocks(int n) { return (n + 255) / 256; }
 
 // order-preserving compaction of up to two parallel float4 arrays; returns the kept count (synchronises)
-int compact2(hop_ctx *ctx, const float4 *a, const float4 *b, const unsigned char *flag, int n, float4 *oa, float4 *ob, int *kept) {
+// d_bounds (may be null): six floats the producing kernel accumulated (warp_bounds) -> bounds_out[0..2] = min, [3..5] = max, with the count
+int compact2(hop_ctx *ctx, const float4 *a, const float4 *b, const unsigned char *flag, int n, float4 *oa, float4 *ob, int *kept,
+             const float *d_bounds = nullptr, float *bounds_out = nullptr) {
   cudaStream_t st = ctx->stream;
   *kept = 0;
   if (n <= 0) return HOP_OK;
@@ -289,6 +326,7 @@ int compact2(hop_ctx *ctx, const float4 *a, const float4 *b, const unsigned char
   if (b) cub::DeviceSelect::Flagged(tmp.p, bytes, b, flag, ob, cnt.as<int>(), n, st);
   ctx->launches += b ? 2 : 1;
   FR_CUDA(cudaMemcpyAsync(kept, cnt.p, sizeof(int), cudaMemcpyDeviceToHost, st));
+  if (d_bounds && bounds_out) FR_CUDA(cudaMemcpyAsync(bounds_out, d_bounds, 6 * sizeof(float), cudaMemcpyDeviceToHost, st));
   FR_CUDA(cudaStreamSynchronize(st));
   return HOP_OK;
 }
@@ -309,13 +347,17 @@ int cloud_bounds(hop_ctx *ctx, const float4 *pts, int n, float *mn, float *mx) {
 }
 
 // pcl::VoxelGrid on device arrays; out arrays must hold n entries
-int voxel_grid(hop_ctx *ctx, const float4 *pts, const float4 *nrm, int n, float leaf, float4 *out_pts, float4 *out_nrm, int *m_out) {
+int voxel_grid(hop_ctx *ctx, const float4 *pts, const float4 *nrm, int n, float leaf, float4 *out_pts, float4 *out_nrm, int *m_out,
+               const float *known_bounds = nullptr /* min xyz, max xyz of pts when the caller already has them */) {
   cudaStream_t st = ctx->stream;
   *m_out = 0;
   if (n <= 0) return HOP_OK;
   float mn[3], mx[3];
-  int rc = cloud_bounds(ctx, pts, n, mn, mx);
-  if (rc != HOP_OK) return rc;
+  if (known_bounds) { for (int k = 0; k < 3; ++k) { mn[k] = known_bounds[k]; mx[k] = known_bounds[3 + k]; } }
+  else {
+    int rc = cloud_bounds(ctx, pts, n, mn, mx);
+    if (rc != HOP_OK) return rc;
+  }
   LeafGeom g;
   g.inv = 1.0f / leaf;
   for (int k = 0; k < 3; ++k) { g.minb[k] = (long long)std::floor(mn[k] * g.inv); g.divb[k] = (long long)std::floor(mx[k] * g.inv) - g.minb[k] + 1; }
@@ -380,32 +422,40 @@ extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int wi
   FR_CUDA(d_depth.alloc(sizeof(uint16_t) * (size_t)npx));
   FR_CUDA(A.alloc(sizeof(float4) * (size_t)npx)); FR_CUDA(B.alloc(sizeof(float4) * (size_t)npx)); FR_CUDA(fl.alloc((size_t)npx));
   FR_CUDA(cudaMemcpyAsync(d_depth.p, depth_mm, sizeof(uint16_t) * (size_t)npx, cudaMemcpyHostToDevice, st));
+  // the bounding boxes of the three kept sets (valid pixels, cropped points, final points) are accumulated by the kernels that decide
+  // what is kept and come back with the counts: three round trips fewer per frame than a bounds pass before every consumer
+  FBuf bnd(st);
+  FR_CUDA(bnd.alloc(18 * sizeof(float)));
+  static const float kBoundsInit[18] = {FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX, FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX,
+                                        FLT_MAX, FLT_MAX, FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX};
+  FR_CUDA(cudaMemcpyAsync(bnd.p, kBoundsInit, sizeof(kBoundsInit), cudaMemcpyHostToDevice, st));
+  float *d_bnd = bnd.as<float>();
+  float bnd_valid[6], bnd_crop[6], bnd_final[6];
   // 1. back-projection, raster order
-  backproject_kernel<<<blocks(npx), 256, 0, st>>>(d_depth.as<uint16_t>(), width, height, fp->fx, fp->fy, fp->cx, fp->cy, A.as<float4>(), fl.as<unsigned char>());
+  backproject_kernel<<<blocks(npx), 256, 0, st>>>(d_depth.as<uint16_t>(), width, height, fp->fx, fp->fy, fp->cx, fp->cy, A.as<float4>(), fl.as<unsigned char>(), d_bnd);
   ctx->launches += 1;
   int n = 0, rc;
-  if ((rc = compact2(ctx, A.as<float4>(), nullptr, fl.as<unsigned char>(), npx, B.as<float4>(), nullptr, &n)) != HOP_OK) return rc;
+  if ((rc = compact2(ctx, A.as<float4>(), nullptr, fl.as<unsigned char>(), npx, B.as<float4>(), nullptr, &n, d_bnd, bnd_valid)) != HOP_OK) return rc;
   counts[0] = n;
   // 2. dense voxel grid
   int m = 0;
-  if ((rc = voxel_grid(ctx, B.as<float4>(), nullptr, n, fp->leaf_dense, A.as<float4>(), nullptr, &m)) != HOP_OK) return rc;
+  if ((rc = voxel_grid(ctx, B.as<float4>(), nullptr, n, fp->leaf_dense, A.as<float4>(), nullptr, &m, bnd_valid)) != HOP_OK) return rc;
   counts[1] = m;
   // 3. crop in the hand-base frame
   int nc = 0;
   if (m > 0) {
     crop_kernel<<<blocks(m), 256, 0, st>>>(A.as<float4>(), m, rows_of(fp->cam_in_handbase), rows_of(fp->handbase_in_cam),
                                            make_float3(fp->box_min[0], fp->box_min[1], fp->box_min[2]), make_float3(fp->box_max[0], fp->box_max[1], fp->box_max[2]),
-                                           B.as<float4>(), fl.as<unsigned char>());
+                                           B.as<float4>(), fl.as<unsigned char>(), d_bnd + 6);
     ctx->launches += 1;
-    if ((rc = compact2(ctx, B.as<float4>(), nullptr, fl.as<unsigned char>(), m, A.as<float4>(), nullptr, &nc)) != HOP_OK) return rc;
+    if ((rc = compact2(ctx, B.as<float4>(), nullptr, fl.as<unsigned char>(), m, A.as<float4>(), nullptr, &nc, d_bnd + 6, bnd_crop)) != HOP_OK) return rc;
   }
   counts[2] = nc;
   // 4. normals over normal_radius
   int mo = 0, nf = 0;
   FR_CUDA(NA.alloc(sizeof(float4) * (size_t)std::max(nc, 1))); FR_CUDA(NB.alloc(sizeof(float4) * (size_t)std::max(nc, 1)));
   if (nc > 0) {
-    float mn[3], mx[3];
-    if ((rc = cloud_bounds(ctx, A.as<float4>(), nc, mn, mx)) != HOP_OK) return rc;
+    const float *mn = bnd_crop, *mx = bnd_crop + 3;
     CellGeom g;
     g.inv = 1.f / fp->normal_radius;
     double ncell = 1;
@@ -431,11 +481,11 @@ extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int wi
                                                      make_float3(fp->viewpoint[0], fp->viewpoint[1], fp->viewpoint[2]), NA.as<float4>());
     ctx->launches += 4;
     // 5. object voxel grid with normals, NaN removal, flip, confidence
-    if ((rc = voxel_grid(ctx, A.as<float4>(), NA.as<float4>(), nc, fp->leaf_object, B.as<float4>(), NB.as<float4>(), &mo)) != HOP_OK) return rc;
+    if ((rc = voxel_grid(ctx, A.as<float4>(), NA.as<float4>(), nc, fp->leaf_object, B.as<float4>(), NB.as<float4>(), &mo, bnd_crop)) != HOP_OK) return rc;
     if (mo > 0) {
-      finish_kernel<<<blocks(mo), 256, 0, st>>>(B.as<float4>(), NB.as<float4>(), mo, A.as<float4>(), NA.as<float4>(), fl.as<unsigned char>());
+      finish_kernel<<<blocks(mo), 256, 0, st>>>(B.as<float4>(), NB.as<float4>(), mo, A.as<float4>(), NA.as<float4>(), fl.as<unsigned char>(), d_bnd + 12);
       ctx->launches += 1;
-      if ((rc = compact2(ctx, A.as<float4>(), NA.as<float4>(), fl.as<unsigned char>(), mo, B.as<float4>(), NB.as<float4>(), &nf)) != HOP_OK) return rc;
+      if ((rc = compact2(ctx, A.as<float4>(), NA.as<float4>(), fl.as<unsigned char>(), mo, B.as<float4>(), NB.as<float4>(), &nf, d_bnd + 12, bnd_final)) != HOP_OK) return rc;
     }
   }
   counts[3] = mo; counts[4] = nf;
@@ -446,9 +496,7 @@ extern "C" int hop_frame_to_scene(hop_ctx *ctx, const uint16_t *depth_mm, int wi
   if (rc != HOP_OK) { if (!*scene) hop_cloud_free(ctx, c); return rc; }
   to_cloud_kernel<<<blocks(c->n_padded), 256, 0, st>>>(B.as<float4>(), NB.as<float4>(), nf, c->n_padded, c->d_pw, c->d_nv);
   ctx->launches += 1;
-  float mn[3] = {0, 0, 0}, mx[3] = {0, 0, 0};
-  if (nf > 0 && (rc = cloud_bounds(ctx, B.as<float4>(), nf, mn, mx)) != HOP_OK) { if (!*scene) hop_cloud_free(ctx, c); return rc; }
-  for (int k = 0; k < 3; ++k) { c->bbox_min[k] = mn[k]; c->bbox_max[k] = mx[k]; }
+  for (int k = 0; k < 3; ++k) { c->bbox_min[k] = nf > 0 ? bnd_final[k] : 0.f; c->bbox_max[k] = nf > 0 ? bnd_final[3 + k] : 0.f; }
   FR_CUDA(cudaGetLastError());
   *scene = c;
   return HOP_OK;
