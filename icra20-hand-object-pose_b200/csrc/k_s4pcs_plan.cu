@@ -501,13 +501,26 @@ struct Planner {
         base4 = -1;
         float best_distance = std::numeric_limits<float>::max();
         const float too_small = std::pow(max_base_diameter * kBaseTooSmall, 2);
-        for (unsigned int i = 0; i < sample_pool.size(); ++i) {
-          const S4Pt &p = P[sample_pool[i]];
-          if (sqnorm(sub(p.p, b3d[0].p)) >= too_small && sqnorm(sub(p.p, b3d[1].p)) >= too_small && sqnorm(sub(p.p, b3d[2].p)) >= too_small) {
-            const float distance = std::abs(A * p.p[0] + B * p.p[1] + C * p.p[2] - 1.0);
-            if (distance < best_distance) { best_distance = distance; base4 = int(sample_pool[i]); }
+        // the pool point nearest to the plane of the triangle, the FIRST of equals (the reference's strict '<' in pool order): on all host
+        // threads for the pools of large scenes (18 of 27 ms per plan at 50 k points), every thread on an ascending block of the pool
+        const int n_pool = (int)sample_pool.size();
+        int best_i = -1;
+#pragma omp parallel if (n_pool >= 4096)
+        {
+          int bi = -1;
+          float bd = std::numeric_limits<float>::max();
+#pragma omp for schedule(static) nowait
+          for (int i = 0; i < n_pool; ++i) {
+            const S4Pt &p = P[sample_pool[i]];
+            if (sqnorm(sub(p.p, b3d[0].p)) >= too_small && sqnorm(sub(p.p, b3d[1].p)) >= too_small && sqnorm(sub(p.p, b3d[2].p)) >= too_small) {
+              const float distance = std::abs(A * p.p[0] + B * p.p[1] + C * p.p[2] - 1.0);
+              if (distance < bd) { bd = distance; bi = i; }
+            }
           }
+#pragma omp critical(hop_plan_base4)
+          if (bi >= 0 && (bd < best_distance || (bd == best_distance && bi < best_i))) { best_distance = bd; best_i = bi; }
         }
+        if (best_i >= 0) base4 = int(sample_pool[best_i]);
         if (base4 != -1) {
           b3d[3] = P[base4];
           int id[4] = {base1, base2, base3, base4};

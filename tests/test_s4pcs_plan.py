@@ -24,7 +24,8 @@ def test_compute_ppf_matches_reference():
 
 
 @needs_ref
-@pytest.mark.parametrize("name,seed,nq,ns", [("ellipse", 2, 400, 500), ("cuboid", 3, 400, 500), ("tless", 4, 1500, 800), ("cylinder", 5, 90, 300)])
+@pytest.mark.parametrize("name,seed,nq,ns", [("ellipse", 2, 400, 500), ("cuboid", 3, 400, 500), ("tless", 4, 1500, 800), ("cylinder", 5, 90, 300),
+                                             ("ellipse", 7, 400, 9000)])   # (a pool beyond 4096 points: the 4th base point is searched on all host threads)
 def test_plan_matches_compiled_reference(name, seed, nq, ns):
     m, mn = synth.make_model(name, nq, seed=1)
     keys = O.ref_ppf_keys(m[:400], mn[:400])
