@@ -360,6 +360,19 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     g.delta = delta;
   }
 
+  std::unique_ptr<HopTraceScope> trace(new HopTraceScope(ctx, "  s4run: uploads + K2a + select + sync"));
+  // ---- the scene of the verification step (K3) goes up first and its NN grid is built on the context's second stream while K2a / K2b run.
+  //      The centred scene lives in a cloud the context keeps from frame to frame: its buffers and the buffers of its NN grid are reused (a
+  //      fresh cloud per call costs a dozen cudaMalloc / cudaFree round trips, 1.5 ms of a 2 ms call) ----
+  {
+    std::vector<float> Pxyz(3 * (size_t)nP), Pn(3 * (size_t)nP);
+    for (int i = 0; i < nP; ++i) for (int k = 0; k < 3; ++k) { Pxyz[3 * i + k] = plan->P[i].p[k]; Pn[3 * i + k] = plan->P[i].n[k]; }
+    int rc0 = ctx->s4_scene ? hop_cloud_update(ctx, ctx->s4_scene, Pxyz.data(), Pn.data(), nullptr, nP)
+                            : hop_cloud_upload(ctx, Pxyz.data(), Pn.data(), nullptr, nP, &ctx->s4_scene);
+    if (rc0 != HOP_OK) return rc0;
+    rc0 = hop_cloud_prepare_nn_async(ctx, ctx->s4_scene, delta, 0.f);
+    if (rc0 != HOP_OK) return rc0;
+  }
   // ---- uploads ----
   const long long NP = (long long)nQ * (nQ - 1) / 2;
   DevBuf bQp(st), bQn(st), bQu(st), bEx(st), bTp(st), bFlags(st), bCnt(st), bSel(st), bCub(st);
@@ -400,6 +413,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
   HOP_CUDA(ctx, cudaMemcpyAsync(cnt.data(), bCnt.p, sizeof(int) * (2 * T + 4), cudaMemcpyDeviceToHost, st));
   HOP_CUDA(ctx, cudaStreamSynchronize(st));
   const int n_sel = cnt[2 * T];
+  trace.reset(new HopTraceScope(ctx, "  s4run: layout + K2b count + scan + sync"));
 
   // layout of the ordered-pair records: first-set records of all trials, then second-set records of all trials
   std::vector<int> ex_begin(2 * T), rec_base(2 * T), r2_begin(T), r2_end(T), r1_begin(T), r1_end(T);
@@ -446,6 +460,7 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
     std::vector<int> offs(n1 + 1);
     HOP_CUDA(ctx, cudaMemcpyAsync(offs.data(), bOffsets.p, sizeof(int) * ((size_t)n1 + 1), cudaMemcpyDeviceToHost, st));
     HOP_CUDA(ctx, cudaStreamSynchronize(st));
+    trace.reset(new HopTraceScope(ctx, "  s4run: K2b fill"));
     int successes = 0;
     T_exec = T;
     for (int t = 0; t < T; ++t) {
@@ -497,16 +512,12 @@ extern "C" int hop_super4pcs_run(hop_ctx *ctx, hop_s4pcs_plan *plan, float *hyp_
   }
   if (M == 0) return HOP_OK;
 
+  trace.reset(new HopTraceScope(ctx, "  s4run: K3 (cloud update, grid, verify, download)"));
   // ---- K3 on every quadrilateral of the executed trials ----
-  std::vector<float> Pxyz(3 * (size_t)nP), Pn(3 * (size_t)nP), Qc(3 * (size_t)nQ);
-  for (int i = 0; i < nP; ++i) for (int k = 0; k < 3; ++k) { Pxyz[3 * i + k] = plan->P[i].p[k]; Pn[3 * i + k] = plan->P[i].n[k]; }
+  std::vector<float> Qc(3 * (size_t)nQ);
   for (int i = 0; i < nQ; ++i) for (int k = 0; k < 3; ++k) Qc[3 * i + k] = plan->Q[i].p[k];
-  // the centred scene lives in a cloud the context keeps from frame to frame: its buffers and the buffers of its NN grid are
-  // reused (a fresh cloud per call costs a dozen cudaMalloc / cudaFree round trips, 1.5 ms of a 2 ms call)
-  int rc = ctx->s4_scene ? hop_cloud_update(ctx, ctx->s4_scene, Pxyz.data(), Pn.data(), nullptr, nP)
-                         : hop_cloud_upload(ctx, Pxyz.data(), Pn.data(), nullptr, nP, &ctx->s4_scene);
-  if (rc != HOP_OK) return rc;
   hop_cloud *Pcloud = ctx->s4_scene;
+  int rc = HOP_OK;
   std::vector<int32_t> bases(4 * (size_t)T);
   for (int t = 0; t < T; ++t) for (int k = 0; k < 4; ++k) bases[4 * t + k] = plan->trials[t].base[k];
   DevBuf bBases(st), bQc(st), bPoses(st), bLcp(st), bValid(st), bN(st);
