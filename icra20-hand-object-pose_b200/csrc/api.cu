@@ -179,6 +179,7 @@ int hop_create(int device, hop_ctx **out) {
     if ((v = getenv("HOP_VOXEL_SCALE"))) ctx->tune.voxel_scale = (float)atof(v);
     ctx->tune.topk_rounds = getenv("HOP_TOPK_ROUNDS") != nullptr;
     ctx->tune.trace = getenv("HOP_TRACE") != nullptr;
+    ctx->tune.plan_debug = getenv("HOP_PLAN_DEBUG") != nullptr;
     ctx->tune.cluster_blocks = getenv("HOP_CLUSTER_BLOCKS") != nullptr;
   }
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess ||

@@ -232,6 +232,7 @@ struct HopTuning {
   float voxel_max_frac = 1.f; // HOP_VOXEL_MAX_FRAC
   bool topk_rounds = false;   // HOP_TOPK_ROUNDS: the one-barrier-pair-per-winner kernel (A/B knob)
   bool cluster_blocks = false; // HOP_CLUSTER_BLOCKS: hop_cluster_poses_gpu always through the blocked kernels (A/B knob; default: the bit matrix up to 4096 hypotheses)
+  bool plan_debug = false;    // HOP_PLAN_DEBUG: the Super4PCS planner prints its trial loop's time
   bool trace = false;         // HOP_TRACE: host wall time and call count of every C-ABI entry point, printed by hop_destroy
 };
 

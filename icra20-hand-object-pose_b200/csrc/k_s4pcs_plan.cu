@@ -625,7 +625,7 @@ static int plan_create(hop_ctx *ctx, const float *P_xyz, const float *P_nrm, con
     HopTraceScope ts(ctx, "  plan: trials (RNG replay)");
     const auto t0 = std::chrono::steady_clock::now();
     planner.plan_trials();
-    if (getenv("HOP_PLAN_DEBUG")) fprintf(stderr, "[plan debug] nP %zu trials_ms %.3f\n", pl->P.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    if (ctx ? ctx->tune.plan_debug : getenv("HOP_PLAN_DEBUG") != nullptr) fprintf(stderr, "[plan debug] nP %zu trials_ms %.3f\n", pl->P.size(), std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
   }
   *out = pl;
   return HOP_OK;
