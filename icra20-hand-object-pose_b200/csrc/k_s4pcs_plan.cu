@@ -329,10 +329,17 @@ struct Planner {
   // points and 30 trials that construction was most of the planner's host time.  tests/test_s4pcs_plan.py pins the bases bit for bit
   // against the reference compiled here, i.e. against the real std::discrete_distribution.
   template <typename W>
-  static int draw_discrete(const W *w, int n, std::mt19937 &engine) {
-    if (n < 2) return 0;   // (an empty or one-entry table: libstdc++ returns 0 without touching the engine)
+  static double weight_sum(const W *w, int n) {   // std::accumulate(prob.begin(), prob.end(), 0.0)
     double sum = 0.0;
     for (int i = 0; i < n; ++i) sum += (double)w[i];
+    return sum;
+  }
+  template <typename W>
+  static int draw_discrete(const W *w, int n, std::mt19937 &engine) { return draw_discrete(w, n, weight_sum(w, n), engine); }
+  // (sum = weight_sum(w, n): callers that draw twice from unchanged weights add them up once)
+  template <typename W>
+  static int draw_discrete(const W *w, int n, double sum, std::mt19937 &engine) {
+    if (n < 2) return 0;   // (an empty or one-entry table: libstdc++ returns 0 without touching the engine)
     const double p = std::generate_canonical<double, std::numeric_limits<double>::digits>(engine);
     double acc = 0.0;
     for (int k = 0; k + 1 < n; ++k) {
@@ -382,13 +389,15 @@ struct Planner {
     if (sample_pool.size() < 3) return false;
     const float sq_max_base_diameter = max_base_diameter * max_base_diameter;
     const int n_pool = (int)sample_pool.size();
+    double pool_sum = weight_sum(probs.data(), n_pool);   // (the weights only change after a pair passed the PPF test)
     for (int i = 0; (size_t)i < sample_pool.size() * sample_pool.size() / 4; ++i) {
-      const int second_point = draw_discrete(probs.data(), n_pool, point_index_engine);
-      const int third_point = draw_discrete(probs.data(), n_pool, point_index_engine);
+      const int second_point = draw_discrete(probs.data(), n_pool, pool_sum, point_index_engine);
+      const int third_point = draw_discrete(probs.data(), n_pool, pool_sum, point_index_engine);
       if (second_point == third_point) continue;
       if (!has_ppf_idx(sample_pool[second_point], sample_pool[third_point])) continue;
       probs[second_point] *= pl.opt.dispersion;
       probs[third_point] *= pl.opt.dispersion;
+      pool_sum = weight_sum(probs.data(), n_pool);
       const V3 u = sub(P[sample_pool[second_point]].p, P[first_point].p);
       const V3 w = sub(P[sample_pool[third_point]].p, P[first_point].p);
       const float how_wide = dot(normalized(u), normalized(w));
